@@ -1,0 +1,73 @@
+"""Builds cap2det_b200/lib/libcap2det_b200.so (sm_100a only) with nvcc, in-tree.
+
+The library is a plain C-ABI shared object (include/cap2det_b200.h); it is loaded with ctypes
+by cap2det_b200/capi.py.  Nothing here depends on torch.
+"""
+import concurrent.futures
+import hashlib
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(ROOT, 'csrc')
+LIB_DIR = os.path.join(ROOT, 'lib')
+LIB_PATH = os.path.join(LIB_DIR, 'libcap2det_b200.so')
+NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
+
+
+def _sources():
+  return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))
+
+
+def _fingerprint():
+  h = hashlib.sha256()
+  for d, names in ((CSRC, sorted(os.listdir(CSRC))),
+                   (os.path.join(ROOT, '..', 'include'), sorted(os.listdir(os.path.join(ROOT, '..', 'include'))))):
+    for f in names:
+      if f.endswith(('.cu', '.cuh', '.h')):
+        h.update(f.encode())
+        with open(os.path.join(d, f), 'rb') as fid:
+          h.update(fid.read())
+  h.update(' '.join(FLAGS).encode())
+  return h.hexdigest()
+
+
+def build_library(force=False, verbose=False):
+  """Compiles every .cu under csrc/ and links the shared library.  Returns its path."""
+  os.makedirs(LIB_DIR, exist_ok=True)
+  stamp = os.path.join(LIB_DIR, 'build.stamp')
+  fp = _fingerprint()
+  if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+    with open(stamp) as fid:
+      if fid.read().strip() == fp:
+        return LIB_PATH
+  if not os.path.exists(NVCC):
+    raise RuntimeError('nvcc not found at %s and no up-to-date %s' % (NVCC, LIB_PATH))
+  objs = []
+
+  def compile_one(src):
+    obj = os.path.join(LIB_DIR, src[:-3] + '.o')
+    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+    if verbose:
+      sys.stderr.write(r.stderr)
+    return obj
+
+  with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+    objs = list(ex.map(compile_one, _sources()))
+  cmd = [NVCC, '-shared', '-o', LIB_PATH] + objs + ['-lcudart']
+  r = subprocess.run(cmd, capture_output=True, text=True)
+  if r.returncode != 0:
+    raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+  with open(stamp, 'w') as fid:
+    fid.write(fp)
+  return LIB_PATH
+
+
+if __name__ == '__main__':
+  print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))

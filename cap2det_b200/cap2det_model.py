@@ -1,0 +1,260 @@
+"""Cap2Det model (models/cap2det_model.py) on the B200 CUDA library.
+
+Same contract as the reference's ``Model``: ``Model(model_proto, is_training)``,
+``build_prediction(examples) -> dict`` (keys per core/standard_fields.py, shapes per
+models/cap2det_model.py:201-214 and :142-149), ``build_loss(predictions, examples) -> dict`` with
+``midn_cross_entropy_loss`` and ``oicr_cross_entropy_loss_at_{1..K}`` (:296,325),
+``build_evaluation`` (:332-343), ``get_variables_to_train``.  There is no graph: "build" runs the
+kernels eagerly on the current CUDA stream and the loss tensors carry autograd history whose
+backward nodes call the fused CUDA backward kernels.
+
+The backbone (first_stage_feature_extraction) is outside this path: callers pass the stride-16
+feature map as ``examples['features_to_crop']`` ([B,Hf,Wf,576] NHWC fp32).
+"""
+import math
+
+import torch
+
+from cap2det_b200 import config
+from cap2det_b200 import ops
+from cap2det_b200.label_extractor import build_label_extractor
+from cap2det_b200.model_base import ModelBase
+from cap2det_b200.post_process import build_post_processor
+from cap2det_b200.registry import register_model_class
+from cap2det_b200.standard_fields import Cap2DetPredictions
+from cap2det_b200.standard_fields import DetectionResultFields
+from cap2det_b200.standard_fields import InputDataFields
+
+_HEAD_SCOPE = 'second_stage_feature_extraction/InceptionV2/'
+
+
+def _trunc_normal_(t, std, gen):
+  # tf.truncated_normal_initializer: resample outside +-2 sigma
+  torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
+
+
+class Model(ModelBase):
+  """Cap2Det model."""
+
+  def __init__(self, model_proto, is_training=False, device=None, head_dtype=torch.float32, seed=0):
+    """Initializes the model.
+
+    Args:
+      model_proto: a config.Cap2DetModel (mirror of cap2det_model_pb2.Cap2DetModel).
+      is_training: if True, dropout is active and losses can be built.
+      device: CUDA device (default: current).
+      head_dtype: torch.float32 (CUDA-core fp32 path, 1e-5 parity) or torch.bfloat16
+        (tcgen05 tensor-core path, 2e-2 parity) for the ROI tensor and the Mixed_5 head.
+    """
+    super(Model, self).__init__(model_proto, is_training)
+    if not isinstance(model_proto, config.Cap2DetModel):
+      raise ValueError('The model_proto has to be an instance of Cap2DetModel.')
+    options = model_proto
+    self._device = torch.device(device if device is not None else 'cuda')
+    self._head_dtype = head_dtype
+    self._midn_postprocess_fn = build_post_processor(options.midn_post_processor)
+    self._oicr_postprocess_fn = build_post_processor(options.oicr_post_processor)
+    self._label_extractor = build_label_extractor(options.label_extractor, self._device)
+    self._assert_status = None
+    self._init_variables(seed)
+
+  # ---- variables ------------------------------------------------------------------------------
+  def _init_variables(self, seed):
+    options = self._model_proto
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(seed)
+    C = self._label_extractor.num_classes
+    K = options.oicr_iterations
+    self._num_classes = C
+    # Box-classifier head: one packed fp32 buffer (layout: include/cap2det_b200.h, K2/K3).
+    self._head_specs = ops.head_conv_specs()
+    head = torch.zeros((ops.head_param_floats(),), dtype=torch.float32)
+    for name, k, cin, cout, _, off in self._head_specs:
+      nw = cout * k * k * cin
+      w = head[off['weights']:off['weights'] + nw]
+      if name.endswith('Conv2d_0a_1x1') or name.endswith('Conv2d_0b_1x1'):
+        _trunc_normal_(w, 0.09, gen)                        # slim inception_v2: trunc_normal(0.09) on 1x1 reducers
+      else:
+        fan_in, fan_out = k * k * cin, k * k * cout         # slim default xavier_initializer (uniform)
+        lim = math.sqrt(6.0 / (fan_in + fan_out))
+        w.uniform_(-lim, lim, generator=gen)
+      head[off['gamma']:off['gamma'] + cout] = 1.0
+      head[off['moving_variance']:off['moving_variance'] + cout] = 1.0
+    self.head_params = head.to(self._device).requires_grad_(True)
+    # FC layers: rows [0,C) midn/proba_r_given_c, [C,2C) midn/proba_c_given_r, then oicr/iter{i} (1+C each).
+    n_out = 2 * C + K * (C + 1)
+    init = options.fc_hyperparams.initializer
+    std = 0.01
+    if init.WhichOneof('initializer_oneof') == 'truncated_normal_initializer':
+      std = init.truncated_normal_initializer.stddev
+    w = torch.zeros((n_out, ops.HEAD_FEATURE_DIMS), dtype=torch.float32)
+    if std > 0:
+      _trunc_normal_(w, std, gen)
+    self.fc_weights = w.to(self._device).requires_grad_(True)
+    self.fc_biases = torch.zeros((n_out,), dtype=torch.float32, device=self._device).requires_grad_(True)
+    self._col_r, self._col_c = 0, C
+    self._col_oicr = [2 * C + i * (C + 1) for i in range(K)]
+
+  def get_variables_to_train(self):
+    """models/model_base.py:60-66: all trainable variables."""
+    return [self.head_params, self.fc_weights, self.fc_biases]
+
+  def named_variables(self):
+    """TF variable name -> view (head weights are OHWI = transposed TF HWIO; FC weights [out,in])."""
+    out = {}
+    hp = self.head_params.detach()
+    for name, k, cin, cout, _, off in self._head_specs:
+      scope = _HEAD_SCOPE + name
+      out[scope + '/weights'] = hp[off['weights']:off['weights'] + cout * k * k * cin].view(cout, k, k, cin)
+      out[scope + '/BatchNorm/gamma'] = hp[off['gamma']:off['gamma'] + cout]
+      out[scope + '/BatchNorm/beta'] = hp[off['beta']:off['beta'] + cout]
+      out[scope + '/BatchNorm/moving_mean'] = hp[off['moving_mean']:off['moving_mean'] + cout]
+      out[scope + '/BatchNorm/moving_variance'] = hp[off['moving_variance']:off['moving_variance'] + cout]
+    C = self._num_classes
+    fw, fb = self.fc_weights.detach(), self.fc_biases.detach()
+    out['midn/proba_r_given_c/weights'] = fw[0:C]; out['midn/proba_r_given_c/biases'] = fb[0:C]
+    out['midn/proba_c_given_r/weights'] = fw[C:2 * C]; out['midn/proba_c_given_r/biases'] = fb[C:2 * C]
+    for i, col in enumerate(self._col_oicr):
+      out['oicr/iter%d/weights' % (i + 1)] = fw[col:col + C + 1]
+      out['oicr/iter%d/biases' % (i + 1)] = fb[col:col + C + 1]
+    return out
+
+  # ---- forward --------------------------------------------------------------------------------
+  def _build_prediction(self, examples, features_to_crop):
+    """models/cap2det_model.py:152-216 for one feature map."""
+    options = self._model_proto
+    frcnn = options.frcnn_options
+    is_training = self._is_training
+    num_proposals = examples[InputDataFields.num_proposals].to(torch.int32).contiguous()
+    proposals = examples[InputDataFields.proposals].contiguous()
+    B, P, _ = proposals.shape
+    C = self._num_classes
+    if frcnn.dropout_on_feature_map:
+      raise NotImplementedError('dropout_on_feature_map is off in every reference config (configs/*.pbtxt:55)')
+    # models/utils.py:147-160
+    x0 = ops.roi_crop_maxpool(features_to_crop, proposals, frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
+                              frcnn.maxpool_stride, out_dtype=self._head_dtype)
+    # models/utils.py:165-177
+    keep_mask = None
+    keep_prob = frcnn.dropout_keep_prob
+    if is_training and keep_prob < 1.0:
+      keep_mask = examples.get(InputDataFields.dropout_keep_mask)
+      if keep_mask is None:   # TF1 slim.dropout: floor(keep_prob + uniform[0,1))
+        keep_mask = torch.floor(keep_prob + torch.rand((B * P, ops.HEAD_FEATURE_DIMS), device=x0.device))
+    feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
+                           need_dx0=features_to_crop.requires_grad)
+    # models/cap2det_model.py:79-88,190-197: the five FC layers as one product
+    logits_all = ops.fc_concat(feat, self.fc_weights, self.fc_biases).view(B, P, -1)
+    midn_class_logits, midn_proposal_scores, midn_proba_r_given_c = ops.midn(
+        logits_all, self._col_r, self._col_c, C, num_proposals)
+    predictions = {}
+    for i, col in enumerate(self._col_oicr):
+      predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i + 1)] = logits_all[:, :, col:col + C + 1]
+    predictions.update({
+        DetectionResultFields.class_labels: self._label_extractor.classes,
+        DetectionResultFields.num_proposals: num_proposals,
+        DetectionResultFields.proposal_boxes: proposals,
+        Cap2DetPredictions.midn_class_logits: midn_class_logits,
+        Cap2DetPredictions.midn_proba_r_given_c: midn_proba_r_given_c,
+        Cap2DetPredictions.oicr_proposal_scores + '_at_0': midn_proposal_scores,
+        '_logits_all': logits_all,
+        '_proposal_features': feat,
+    })
+    return predictions
+
+  def _postprocess(self, predictions):
+    """models/cap2det_model.py:111-150."""
+    results = {}
+    oicr_iterations = self._model_proto.oicr_iterations
+    proposals = predictions[DetectionResultFields.proposal_boxes]
+    for i in range(1 + oicr_iterations):
+      post_process_fn = self._midn_postprocess_fn
+      proposal_scores = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)].detach()
+      if i > 0:
+        post_process_fn = self._oicr_postprocess_fn
+        proposal_scores = ops.softmax_rows(proposal_scores)[:, :, 1:]
+      num_detections, boxes, scores, classes, _ = post_process_fn(proposals, proposal_scores)
+      results[DetectionResultFields.num_detections + '_at_{}'.format(i)] = num_detections
+      results[DetectionResultFields.detection_boxes + '_at_{}'.format(i)] = boxes
+      results[DetectionResultFields.detection_scores + '_at_{}'.format(i)] = scores
+      results[DetectionResultFields.detection_classes + '_at_{}'.format(i)] = classes
+    return results
+
+  def build_prediction(self, examples, **kwargs):
+    """models/cap2det_model.py:218-272."""
+    options = self._model_proto
+    fmaps = examples.get(InputDataFields.features_to_crop)
+    if fmaps is None:
+      raise NotImplementedError(
+          "examples['features_to_crop'] is required: the Inception-v2 backbone (first_stage_feature_extraction) "
+          'is outside the proposal hot path (SURVEY.md 8(f) rank 2)')
+    if self._is_training or len(options.eval_min_dimension) == 0:
+      if isinstance(fmaps, (list, tuple)):
+        raise ValueError('a single feature map is expected outside multi-scale evaluation')
+      predictions = self._build_prediction(examples, fmaps)
+      predictions.update(self._postprocess(predictions))
+      return predictions
+    # Multi-scale evaluation (:231-272): one feature map per entry of eval_min_dimension.
+    if not isinstance(fmaps, (list, tuple)):
+      fmaps = [fmaps]
+    if fmaps[0].shape[0] != 1:
+      raise ValueError('multi-scale evaluation needs batch size 1 (models/cap2det_model.py:237)')
+    K = options.oicr_iterations
+    sums = [None] * (1 + K)
+    predictions = None
+    with torch.no_grad():
+      for fmap in fmaps:
+        predictions = self._build_prediction(examples, fmap)
+        for i in range(1 + K):
+          s = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)]
+          sums[i] = s.clone() if sums[i] is None else sums[i] + s
+      for i in range(1 + K):   # tf.reduce_mean over the stacked scales (:263-267)
+        predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)] = sums[i] / float(len(fmaps))
+      predictions.update(self._postprocess(predictions))
+    return predictions
+
+  # ---- losses ---------------------------------------------------------------------------------
+  def build_loss(self, predictions, examples, **kwargs):
+    """models/cap2det_model.py:274-330."""
+    options = self._model_proto
+    loss_dict = {}
+    labels = self._label_extractor.extract_labels(examples)
+    loss_dict['midn_cross_entropy_loss'] = ops.sigmoid_ce_mean(
+        labels, predictions[Cap2DetPredictions.midn_class_logits], options.midn_loss_weight)
+    num_proposals = predictions[DetectionResultFields.num_proposals]
+    proposals = predictions[DetectionResultFields.proposal_boxes]
+    logits_all = predictions['_logits_all']
+    C = self._num_classes
+    scores_0 = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_0']
+    if options.oicr_use_proba_r_given_c:
+      scores_0 = predictions[Cap2DetPredictions.midn_proba_r_given_c]
+    scores_0 = scores_0.detach()
+    aux = []
+    for i, col in enumerate(self._col_oicr):
+      ind, proposal_labels, status = ops.oicr_assign(labels, num_proposals, proposals, scores_0,
+                                                     options.oicr_iou_threshold)
+      self._assert_status = status if self._assert_status is None else (self._assert_status | status)
+      loss_dict['oicr_cross_entropy_loss_at_{}'.format(i + 1)] = ops.oicr_cross_entropy(
+          logits_all, col, proposal_labels, num_proposals, options.oicr_loss_weight)
+      aux.append((ind, proposal_labels))
+      if i + 1 < len(self._col_oicr):
+        scores_0 = ops.softmax_rows(logits_all.detach()[:, :, col:col + C + 1])[:, :, 1:]      # :328
+    self.last_oicr_assignments = aux
+    self.last_labels = labels
+    return loss_dict
+
+  def raise_if_assert_failed(self):
+    """The reference's graph-time tf.Assert("Probabilities not sum to ONE", models/utils.py:92-95),
+    checked after the step (one device->host read) instead of stalling the launch queue."""
+    if self._assert_status is not None:
+      failed = int(self._assert_status.item()) != 0
+      self._assert_status = None
+      if failed:
+        raise RuntimeError('Probabilities not sum to ONE')
+
+  def build_evaluation(self, predictions, examples, **kwargs):
+    """models/cap2det_model.py:332-343."""
+    return {}
+
+
+register_model_class(config.Cap2DetModel.ext, Model)

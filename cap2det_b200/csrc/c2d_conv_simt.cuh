@@ -1,0 +1,380 @@
+// fp32 CUDA-core implicit-GEMM convolution kernels (forward / data-gradient / weight-gradient),
+// 3x3 pooling and the small element-wise kernels of the box-classifier head.
+//
+// This is the *fp32 parity path* (1e-5 vs the oracle); the bf16 tcgen05 path lives in
+// c2d_gemm_tc.cuh.  All tensors are NHWC with an explicit leading dimension so that branch
+// outputs are written straight into their channel slice of the Inception concat buffers.
+#pragma once
+#include "c2d_common.cuh"
+
+namespace c2d {
+
+// Geometry of the gather that builds the implicit-GEMM "A" rows.
+//   mode 0 (forward):  GEMM row = output pixel (n, oy, ox) on [Hrow,Wrow]; tap (dy,dx) reads the
+//                      source pixel (oy*stride + dy - pad, ox*stride + dx - pad) on [Hsrc,Wsrc].
+//   mode 1 (dgrad):    GEMM row = input pixel (n, y, x) on [Hrow,Wrow]; tap (dy,dx) reads the
+//                      output-gradient pixel ((y + pad - dy)/stride, (x + pad - dx)/stride) on
+//                      [Hsrc,Wsrc] when divisible and in range.
+struct ConvGeom {
+  int Hrow, Wrow, Hsrc, Wsrc, k, stride, pad, mode;
+};
+
+__device__ __forceinline__ int conv_src_pixel(const ConvGeom& g, int n, int ry, int rx, int tap) {
+  int dy = tap / g.k, dx = tap - dy * g.k;
+  int sy, sx;
+  if (g.mode == 0) {
+    sy = ry * g.stride + dy - g.pad;
+    sx = rx * g.stride + dx - g.pad;
+  } else {
+    int ty = ry + g.pad - dy, tx = rx + g.pad - dx;
+    if (ty < 0 || tx < 0 || (ty % g.stride) != 0 || (tx % g.stride) != 0) return -1;
+    sy = ty / g.stride;
+    sx = tx / g.stride;
+  }
+  if (sy < 0 || sy >= g.Hsrc || sx < 0 || sx >= g.Wsrc) return -1;
+  return (n * g.Hsrc + sy) * g.Wsrc + sx;
+}
+
+constexpr int SG_BM = 128, SG_BN = 64, SG_BK = 16;
+
+// C[m, n] (+)= act( sum_{tap,kc} A[src(m,tap), kc] * W[n, tap*Kc + kc] + bias[n] )
+//   A: [*, lda] fp32 rows of Kc channels;  W: [N, taps*Kc] (K-major);  C: [M, ldc].
+template <bool RELU, bool ACCUM>
+__global__ void __launch_bounds__(256)
+igemm_f32_kernel(const float* __restrict__ A, int lda, int Kc, ConvGeom g, const float* __restrict__ W,
+                 const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * SG_BM, n0 = blockIdx.y * SG_BN;
+  const int taps = g.k * g.k;
+  const int Ktot = taps * Kc;
+  const int hw = g.Hrow * g.Wrow;
+  // A loader: 2 rows per thread (row = tid/4 + i*64), k quad = tid%4
+  const int a_kq = tid & 3;
+  int a_n[2], a_y[2], a_x[2];
+  bool a_ok[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int m = m0 + (tid >> 2) + i * 64;
+    a_ok[i] = m < M;
+    int mm = a_ok[i] ? m : 0;
+    a_n[i] = mm / hw;
+    int r = mm - a_n[i] * hw;
+    a_y[i] = r / g.Wrow;
+    a_x[i] = r - a_y[i] * g.Wrow;
+  }
+  const int b_n = tid >> 2, b_kq = tid & 3;
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += SG_BK) {
+    const int tap = k0 / Kc;
+    const int kc0 = k0 - tap * Kc;
+    float4 av[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a_ok[i]) {
+        int pix = conv_src_pixel(g, a_n[i], a_y[i], a_x[i], tap);
+        if (pix >= 0) av[i] = __ldg(reinterpret_cast<const float4*>(A + (size_t)pix * lda + kc0 + a_kq * 4));
+      }
+    }
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + b_n < N) bv = __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + b_n) * Ktot + k0 + b_kq * 4));
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      int row = (tid >> 2) + i * 64;
+      As[a_kq * 4 + 0][row] = av[i].x;
+      As[a_kq * 4 + 1][row] = av[i].y;
+      As[a_kq * 4 + 2][row] = av[i].z;
+      As[a_kq * 4 + 3][row] = av[i].w;
+    }
+    Bs[b_kq * 4 + 0][b_n] = bv.x;
+    Bs[b_kq * 4 + 1][b_n] = bv.y;
+    Bs[b_kq * 4 + 2][b_n] = bv.z;
+    Bs[b_kq * 4 + 3][b_n] = bv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; ++kk) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int m = m0 + ty * 8 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (RELU) v = fmaxf(v, 0.f);
+      float* c = C + (size_t)m * ldc + n;
+      if (ACCUM) v += *c;
+      *c = v;
+    }
+  }
+}
+
+// dW[co, tap*Kc + ci] += sum_m dY[m, co] * X[src(m,tap), ci]     (atomic split over m)
+//   grid.x = ceil(Kc/64) * ceil(N/64), grid.y = taps, grid.z = row splits.
+__global__ void __launch_bounds__(256)
+wgrad_f32_kernel(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int Kc,
+                 ConvGeom g, int M, int rows_per_split, float* __restrict__ dW) {
+  __shared__ float Ys[16][64 + 4];
+  __shared__ float Xs[16][64 + 4];
+  const int tid = threadIdx.x;
+  const int ci_tiles = (Kc + 63) / 64;
+  const int ci0 = (blockIdx.x % ci_tiles) * 64, co0 = (blockIdx.x / ci_tiles) * 64;
+  const int tap = blockIdx.y;
+  const int taps = g.k * g.k;
+  const int hw = g.Hrow * g.Wrow;
+  const int m_begin = blockIdx.z * rows_per_split;
+  const int m_end = min(M, m_begin + rows_per_split);
+  const int lr = tid >> 4, lq = tid & 15;   // loader: row in chunk, column quad
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int mb = m_begin; mb < m_end; mb += 16) {
+    int m = mb + lr;
+    float4 yv = make_float4(0.f, 0.f, 0.f, 0.f), xv = yv;
+    if (m < m_end) {
+      int co = co0 + lq * 4;
+      const float* yp = dY + (size_t)m * ldy + co;
+      if (co + 3 < N) yv = *reinterpret_cast<const float4*>(yp);
+      else {
+        if (co < N) yv.x = yp[0];
+        if (co + 1 < N) yv.y = yp[1];
+        if (co + 2 < N) yv.z = yp[2];
+      }
+      int n = m / hw, r = m - n * hw;
+      int ry = r / g.Wrow, rx = r - ry * g.Wrow;
+      int pix = conv_src_pixel(g, n, ry, rx, tap);
+      int ci = ci0 + lq * 4;
+      if (pix >= 0 && ci < Kc) xv = __ldg(reinterpret_cast<const float4*>(X + (size_t)pix * ldx + ci));
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&Ys[lr][lq * 4]) = yv;
+    *reinterpret_cast<float4*>(&Xs[lr][lq * 4]) = xv;
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&Ys[kk][ty * 4]);
+      float4 b = *reinterpret_cast<const float4*>(&Xs[kk][tx * 4]);
+      float aa[4] = {a.x, a.y, a.z, a.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int co = co0 + ty * 4 + i;
+    if (co >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ci = ci0 + tx * 4 + j;
+      if (ci >= Kc) continue;
+      if (acc[i][j] != 0.f) atomicAdd(dW + ((size_t)co * taps + tap) * Kc + ci, acc[i][j]);
+    }
+  }
+}
+
+// ---- element-wise / pooling kernels, templated on the activation type T -----------------------
+
+// du = dy * (y > 0) in place on a [M, C] slice (leading dim ld), dshift[c] += sum_m du.
+// grid (ceil(C/4 / 32), row chunks), block (32, 8).
+template <typename T>
+__global__ void relu_bwd_colsum_kernel(T* __restrict__ dy, const T* __restrict__ y, int ld, int M, int C,
+                                       int rows_per_cta, float* __restrict__ dshift) {
+  __shared__ float4 red[8][32];
+  const int q = blockIdx.x * 32 + threadIdx.x;   // channel quad
+  const int m_begin = blockIdx.y * rows_per_cta;
+  const int m_end = min(M, m_begin + rows_per_cta);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q * 4 < C) {
+    for (int m = m_begin + threadIdx.y; m < m_end; m += 8) {
+      float4 g = ld4(dy + (size_t)m * ld + q * 4);
+      float4 v = ld4(y + (size_t)m * ld + q * 4);
+      g.x = v.x > 0.f ? g.x : 0.f;
+      g.y = v.y > 0.f ? g.y : 0.f;
+      g.z = v.z > 0.f ? g.z : 0.f;
+      g.w = v.w > 0.f ? g.w : 0.f;
+      st4(dy + (size_t)m * ld + q * 4, g);
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && q * 4 < C) {
+    for (int i = 1; i < 8; ++i) {
+      float4 o = red[i][threadIdx.x];
+      s.x += o.x; s.y += o.y; s.z += o.z; s.w += o.w;
+    }
+    atomicAdd(dshift + q * 4 + 0, s.x);
+    atomicAdd(dshift + q * 4 + 1, s.y);
+    atomicAdd(dshift + q * 4 + 2, s.z);
+    atomicAdd(dshift + q * 4 + 3, s.w);
+  }
+}
+
+// Column sums of a [M, N] fp32 matrix (bias gradient): out[n] += sum_m x[m, n].
+__global__ void colsum_f32_kernel(const float* __restrict__ x, int ld, int M, int N, int rows_per_cta,
+                                  float* __restrict__ out) {
+  __shared__ float red[8][32];
+  const int n = blockIdx.x * 32 + threadIdx.x;
+  const int m_begin = blockIdx.y * rows_per_cta;
+  const int m_end = min(M, m_begin + rows_per_cta);
+  float s = 0.f;
+  if (n < N)
+    for (int m = m_begin + threadIdx.y; m < m_end; m += 8) s += x[(size_t)m * ld + n];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && n < N) {
+    for (int i = 1; i < 8; ++i) s += red[i][threadIdx.x];
+    atomicAdd(out + n, s);
+  }
+}
+
+// 3x3 SAME pooling, one thread per (roi, channel): the whole HxW plane lives in registers.
+// MODE 0 = max (pads with -inf), 1 = avg (divides by the number of valid taps).
+template <typename T, int HIN, int STRIDE, int MODE>
+__global__ void pool3x3_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int n_rois, int C) {
+  constexpr int HOUT = (HIN + STRIDE - 1) / STRIDE;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float v[HIN * HIN];
+#pragma unroll
+  for (int i = 0; i < HIN * HIN; ++i) v[i] = Elem<T>::ld(x + ((size_t)n * HIN * HIN + i) * ldx + c);
+#pragma unroll
+  for (int oy = 0; oy < HOUT; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < HOUT; ++ox) {
+      float acc = MODE == 0 ? -INFINITY : 0.f;
+      int cnt = 0;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          int iy = oy * STRIDE + dy - 1, ix = ox * STRIDE + dx - 1;
+          if (iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) {
+            float t = v[iy * HIN + ix];
+            if (MODE == 0) acc = fmaxf(acc, t); else acc += t;
+            ++cnt;
+          }
+        }
+      if (MODE == 1) acc = acc / (float)cnt;
+      Elem<T>::st(y + ((size_t)n * HOUT * HOUT + oy * HOUT + ox) * ldy + c, acc);
+    }
+}
+
+// Backward of the above.  Max routes to the FIRST maximum in row-major window order.
+// dx (+)= ...; ACCUM selects accumulate vs overwrite of the destination.
+template <typename T, int HIN, int STRIDE, int MODE, bool ACCUM>
+__global__ void pool3x3_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int ldy,
+                                   T* __restrict__ dx, int lddx, int n_rois, int C) {
+  constexpr int HOUT = (HIN + STRIDE - 1) / STRIDE;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float v[HIN * HIN], g[HIN * HIN];
+#pragma unroll
+  for (int i = 0; i < HIN * HIN; ++i) {
+    v[i] = MODE == 0 ? Elem<T>::ld(x + ((size_t)n * HIN * HIN + i) * ldx + c) : 0.f;
+    g[i] = 0.f;
+  }
+#pragma unroll
+  for (int oy = 0; oy < HOUT; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < HOUT; ++ox) {
+      float go = Elem<T>::ld(dy + ((size_t)n * HOUT * HOUT + oy * HOUT + ox) * ldy + c);
+      if (MODE == 0) {
+        float best = -INFINITY;
+        int bi = -1;
+#pragma unroll
+        for (int dyy = 0; dyy < 3; ++dyy)
+#pragma unroll
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            int iy = oy * STRIDE + dyy - 1, ix = ox * STRIDE + dxx - 1;
+            if (iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) {
+              float t = v[iy * HIN + ix];
+              if (t > best || bi < 0) { best = t; bi = iy * HIN + ix; }
+            }
+          }
+#pragma unroll
+        for (int i = 0; i < HIN * HIN; ++i) g[i] += (i == bi) ? go : 0.f;
+      } else {
+        int cnt = 0;
+#pragma unroll
+        for (int dyy = 0; dyy < 3; ++dyy)
+#pragma unroll
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            int iy = oy * STRIDE + dyy - 1, ix = ox * STRIDE + dxx - 1;
+            if (iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) ++cnt;
+          }
+        float share = go / (float)cnt;
+#pragma unroll
+        for (int dyy = 0; dyy < 3; ++dyy)
+#pragma unroll
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            int iy = oy * STRIDE + dyy - 1, ix = ox * STRIDE + dxx - 1;
+            if (iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) g[iy * HIN + ix] += share;
+          }
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < HIN * HIN; ++i) {
+    T* p = dx + ((size_t)n * HIN * HIN + i) * lddx + c;
+    float o = g[i];
+    if (ACCUM) o += Elem<T>::ld(p);
+    Elem<T>::st(p, o);
+  }
+}
+
+// feat[n, c] = mean_{hw} x[n, hw, c] (* keep_mask[n,c] / keep_prob).  models/utils.py:169-174.
+template <typename T>
+__global__ void avgpool_dropout_fwd_kernel(const T* __restrict__ x, int hw, int C, const float* __restrict__ keep_mask,
+                                           float keep_prob, float* __restrict__ feat, int n_rois) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float s = 0.f;
+  for (int i = 0; i < hw; ++i) s += Elem<T>::ld(x + ((size_t)n * hw + i) * C + c);
+  s = s / (float)hw;
+  if (keep_mask) s = s / keep_prob * keep_mask[(size_t)n * C + c];
+  feat[(size_t)n * C + c] = s;
+}
+// dx[n, hw, c] = dfeat[n, c] * keep_mask / keep_prob / hw  (broadcast over hw)
+template <typename T>
+__global__ void avgpool_dropout_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ keep_mask,
+                                           float keep_prob, int hw, int C, T* __restrict__ dx, int n_rois) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float g = dfeat[(size_t)n * C + c];
+  if (keep_mask) g = g / keep_prob * keep_mask[(size_t)n * C + c];
+  g = g / (float)hw;
+  for (int i = 0; i < hw; ++i) Elem<T>::st(dx + ((size_t)n * hw + i) * C + c, g);
+}
+
+}  // namespace c2d

@@ -1,0 +1,189 @@
+// Library plumbing + core/box_utils.py and core/utils.py masked reductions on the GPU.
+#include <atomic>
+#include <stdarg.h>
+
+#include "c2d_common.cuh"
+
+namespace c2d {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---------------------------------------------------------------------------------
+// Box arithmetic.  Every reference TF op is one correctly rounded fp32 op here:
+// __fsub_rn/__fmul_rn/__fadd_rn/__fdiv_rn keep ptxas from contracting into FMAs, so
+// the IoU >= threshold mask is bit-identical to the op-by-op TF graph.
+// ---------------------------------------------------------------------------------
+__global__ void box_area_kernel(const float4* __restrict__ box, int n, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float4 b = box[i]; out[i] = box_area(b.x, b.y, b.z, b.w); }
+}
+__global__ void box_intersect_kernel(const float4* __restrict__ b1, const float4* __restrict__ b2, int n,
+                                     float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float4 a = b1[i], b = b2[i];
+    out[i] = make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fminf(a.z, b.z), fminf(a.w, b.w));
+  }
+}
+__global__ void box_iou_kernel(const float4* __restrict__ b1, const float4* __restrict__ b2, int n,
+                               float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = box_iou(b1[i], b2[i]);
+}
+__global__ void box_flip_kernel(const float4* __restrict__ box, int n, float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { float4 b = box[i]; out[i] = make_float4(b.x, __fsub_rn(1.0f, b.w), b.z, __fsub_rn(1.0f, b.y)); }
+}
+__global__ void box_scale_kernel(const float4* __restrict__ box, int n, float ih, float iw, float ph, float pw,
+                                 float4* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float4 b = box[i];
+    out[i] = make_float4(__fdiv_rn(__fmul_rn(b.x, ih), ph), __fdiv_rn(__fmul_rn(b.y, iw), pw),
+                         __fdiv_rn(__fmul_rn(b.z, ih), ph), __fdiv_rn(__fmul_rn(b.w, iw), pw));
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Masked reductions over axis m of data [n,m,d]; one warp per (n, d) column.
+// ---------------------------------------------------------------------------------
+__global__ void masked_reduce_kernel(const float* __restrict__ data, const float* __restrict__ mask, int n,
+                                     int m, int d, int op, float* __restrict__ out_f,
+                                     long long* __restrict__ out_i) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n * d) return;
+  int in = warp / d, id = warp % d;
+  const float* col = data + (size_t)in * m * d + id;
+  const float* mk = mask + (size_t)in * m;
+  if (op == C2D_MASKED_SUM || op == C2D_MASKED_AVG) {
+    float s = 0.f, c = 0.f;
+    for (int j = lane; j < m; j += 32) { s += __fmul_rn(col[(size_t)j * d], mk[j]); c += mk[j]; }
+    s = warp_sum(s); c = warp_sum(c);
+    if (lane == 0) out_f[warp] = (op == C2D_MASKED_SUM) ? s : __fdiv_rn(s, fmaxf(1e-10f, c));
+    return;
+  }
+  bool is_max = (op == C2D_MASKED_MAX || op == C2D_MASKED_ARGMAX);
+  // pass 1: axis extremum over ALL rows (masked rows included, core/utils.py:75,198)
+  float ext = is_max ? INFINITY : -INFINITY;
+  for (int j = lane; j < m; j += 32) {
+    float v = col[(size_t)j * d];
+    ext = is_max ? fminf(ext, v) : fmaxf(ext, v);
+  }
+  ext = is_max ? warp_min(ext) : warp_max(ext);
+  // pass 2: extremum of (x - ext) * mask with first-index tie break
+  float best = is_max ? -INFINITY : INFINITY;
+  int besti = 0x7fffffff;
+  for (int j = lane; j < m; j += 32) {
+    float v = __fmul_rn(__fsub_rn(col[(size_t)j * d], ext), mk[j]);
+    bool better = is_max ? (v > best) : (v < best);
+    if (better) { best = v; besti = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    bool better = is_max ? (ob > best) : (ob < best);
+    if (better || (ob == best && oi < besti)) { best = ob; besti = oi; }
+  }
+  if (lane == 0) {
+    if (op == C2D_MASKED_ARGMAX || op == C2D_MASKED_ARGMIN) out_i[warp] = (m > 0) ? besti : 0;
+    else out_f[warp] = __fadd_rn(best, ext);
+  }
+}
+
+// masked softmax along m: one warp per (n, d) column; three passes (max, sum, write).
+__global__ void masked_softmax_kernel(const float* __restrict__ data, const float* __restrict__ mask, int n,
+                                      int m, int d, float* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n * d) return;
+  int in = warp / d, id = warp % d;
+  const float* col = data + (size_t)in * m * d + id;
+  float* ocol = out + (size_t)in * m * d + id;
+  const float* mk = mask + (size_t)in * m;
+  float mx = -INFINITY;
+  for (int j = lane; j < m; j += 32)
+    mx = fmaxf(mx, __fsub_rn(col[(size_t)j * d], __fmul_rn(1e10f, __fsub_rn(1.0f, mk[j]))));
+  mx = warp_max(mx);
+  float s = 0.f;
+  for (int j = lane; j < m; j += 32)
+    s += expf(__fsub_rn(__fsub_rn(col[(size_t)j * d], __fmul_rn(1e10f, __fsub_rn(1.0f, mk[j]))), mx));
+  s = warp_sum(s);
+  for (int j = lane; j < m; j += 32)
+    ocol[(size_t)j * d] =
+        __fdiv_rn(expf(__fsub_rn(__fsub_rn(col[(size_t)j * d], __fmul_rn(1e10f, __fsub_rn(1.0f, mk[j]))), mx)), s);
+}
+
+}  // namespace c2d
+
+using namespace c2d;
+
+extern "C" {
+
+int c2d_version(void) { return 100; }
+const char* c2d_last_error(void) { return g_err; }
+long long c2d_launch_count(void) { return g_launches.load(); }
+void c2d_reset_launch_count(void) { g_launches.store(0); }
+
+#define BOX_LAUNCH(kernel, ...)                                              \
+  C2D_CHECK_ARG(n >= 0, "n must be >= 0");                                   \
+  if (n == 0) return C2D_OK;                                                 \
+  kernel<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(__VA_ARGS__);       \
+  count_launch();                                                            \
+  C2D_LAUNCH_OK();                                                           \
+  return C2D_OK;
+
+int c2d_box_area(const float* box, int n, float* area, c2d_stream_t stream) {
+  BOX_LAUNCH(box_area_kernel, (const float4*)box, n, area)
+}
+int c2d_box_intersect(const float* b1, const float* b2, int n, float* out, c2d_stream_t stream) {
+  BOX_LAUNCH(box_intersect_kernel, (const float4*)b1, (const float4*)b2, n, (float4*)out)
+}
+int c2d_box_iou(const float* b1, const float* b2, int n, float* iou, c2d_stream_t stream) {
+  BOX_LAUNCH(box_iou_kernel, (const float4*)b1, (const float4*)b2, n, iou)
+}
+int c2d_box_flip_left_right(const float* box, int n, float* out, c2d_stream_t stream) {
+  BOX_LAUNCH(box_flip_kernel, (const float4*)box, n, (float4*)out)
+}
+int c2d_box_scale_to_new_size(const float* box, int n, int img_h, int img_w, int pad_h, int pad_w, float* out,
+                              c2d_stream_t stream) {
+  BOX_LAUNCH(box_scale_kernel, (const float4*)box, n, (float)img_h, (float)img_w, (float)pad_h, (float)pad_w,
+             (float4*)out)
+}
+
+int c2d_masked_reduce(const float* data, const float* mask, int n, int m, int d, int op, float* out_f,
+                      long long* out_i, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0 && m >= 1 && d >= 1, "masked_reduce: bad shape n=%d m=%d d=%d", n, m, d);
+  C2D_CHECK_ARG(op >= C2D_MASKED_MAX && op <= C2D_MASKED_ARGMIN, "masked_reduce: bad op %d", op);
+  bool arg = (op == C2D_MASKED_ARGMAX || op == C2D_MASKED_ARGMIN);
+  C2D_CHECK_ARG(arg ? out_i != nullptr : out_f != nullptr, "masked_reduce: missing output buffer");
+  if (n == 0) return C2D_OK;
+  long long threads = (long long)n * d * 32;
+  masked_reduce_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(data, mask, n, m, d, op, out_f, out_i);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_masked_softmax(const float* data, const float* mask, int n, int m, int d, float* out,
+                       c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0 && m >= 1 && d >= 1, "masked_softmax: bad shape n=%d m=%d d=%d", n, m, d);
+  if (n == 0) return C2D_OK;
+  long long threads = (long long)n * d * 32;
+  masked_softmax_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(data, mask, n, m, d, out);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,346 @@
+// K7: per-class greedy NMS post-processing.  Reference: core/builder.py:31-65 wrapping the
+// OD-API batch_multiclass_non_max_suppression (semantics restated in SURVEY.md A.4):
+//   per class: score > score_thresh (strict), zero-area boxes dropped, greedy NMS in descending
+//   score order (ties: lower proposal index first), suppress on IoU > iou_thresh, at most
+//   max_size_per_class; then all classes merged, stable sort by score, top max_total_size.
+//
+// Kernel 1 (one CTA per (image, class)): 64-bit key bitonic sort in shared memory
+// (key = ~score_bits << 32 | index => descending score, ascending index), then *blocked* greedy
+// NMS: candidates are visited 64 at a time; a tile is first tested against the <=100 boxes kept
+// so far (all threads), then resolved inside the tile with a 64x64 suppression bitmask walked by
+// one thread.  Result is identical to the sequential greedy loop.
+// Kernel 2 (one CTA per image): merge the per-class lists with a second bitonic sort.
+#include "c2d_common.cuh"
+
+namespace c2d {
+
+constexpr int kNmsThreads = 512;
+constexpr int kTile = 64;
+
+// TF non_max_suppression_op.cc IOU(): canonicalised corners, 0 when an area is <= 0.
+__device__ __forceinline__ float nms_iou(float4 a, float4 b) {
+  float ymin_i = fminf(a.x, a.z), xmin_i = fminf(a.y, a.w), ymax_i = fmaxf(a.x, a.z), xmax_i = fmaxf(a.y, a.w);
+  float ymin_j = fminf(b.x, b.z), xmin_j = fminf(b.y, b.w), ymax_j = fmaxf(b.x, b.z), xmax_j = fmaxf(b.y, b.w);
+  float area_i = __fmul_rn(__fsub_rn(ymax_i, ymin_i), __fsub_rn(xmax_i, xmin_i));
+  float area_j = __fmul_rn(__fsub_rn(ymax_j, ymin_j), __fsub_rn(xmax_j, xmin_j));
+  if (area_i <= 0.f || area_j <= 0.f) return 0.f;
+  float ih = fmaxf(__fsub_rn(fminf(ymax_i, ymax_j), fmaxf(ymin_i, ymin_j)), 0.f);
+  float iw = fmaxf(__fsub_rn(fminf(xmax_i, xmax_j), fmaxf(xmin_i, xmin_j)), 0.f);
+  float inter = __fmul_rn(ih, iw);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_i, area_j), inter));
+}
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* keys, int n_pad) {
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+        int ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long a = keys[i], b = keys[ixj];
+          bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// grid (C, B); dynamic smem: n_pad * 8 bytes of keys.
+__global__ void __launch_bounds__(kNmsThreads)
+nms_per_class_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores, int lds, int P, int C,
+                     int n_pad, float score_thresh, float iou_thresh, int max_per_class,
+                     int* __restrict__ cls_count, int* __restrict__ cls_index, float* __restrict__ cls_score) {
+  extern __shared__ unsigned long long keys[];
+  __shared__ float4 kept_box[128];
+  __shared__ float4 tile_box[kTile];
+  __shared__ unsigned long long tile_mask[kTile];
+  __shared__ int tile_supp[kTile];
+  __shared__ int s_nkept, s_ncand;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float4* bx = boxes + (size_t)b * P;
+  const float* sc = scores + (size_t)b * P * lds + c;
+  if (threadIdx.x == 0) { s_nkept = 0; s_ncand = 0; }
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < P) {
+      float s = sc[(size_t)i * lds];
+      float4 q = bx[i];
+      float area = __fmul_rn(__fsub_rn(q.z, q.x), __fsub_rn(q.w, q.y));   // clip_to_window area filter
+      if (s > score_thresh && area > 0.f) {
+        // s > score_thresh >= 0 in every config; for generality map float order to uint order.
+        uint32_t u = __float_as_uint(s);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        key = ((unsigned long long)(~u) << 32) | (uint32_t)i;
+        ++local;
+      }
+    }
+    keys[i] = key;
+  }
+  if (local) atomicAdd(&s_ncand, local);
+  bitonic_sort_u64(keys, n_pad);
+  const int ncand = s_ncand;
+  const int out_base = (b * C + c) * max_per_class;
+  for (int t0 = 0; t0 < ncand; t0 += kTile) {
+    const int nt = min(kTile, ncand - t0);
+    const int nkept = s_nkept;
+    if (nkept >= max_per_class) break;
+    if (threadIdx.x < kTile) {
+      tile_supp[threadIdx.x] = 0;
+      tile_mask[threadIdx.x] = 0ull;
+      if (threadIdx.x < nt) tile_box[threadIdx.x] = bx[(uint32_t)(keys[t0 + threadIdx.x] & 0xffffffffull)];
+    }
+    __syncthreads();
+    // (a) tile vs already kept boxes
+    for (int w = threadIdx.x; w < nt * nkept; w += blockDim.x) {
+      int ti = w / nkept, kj = w - ti * nkept;
+      if (nms_iou(tile_box[ti], kept_box[kj]) > iou_thresh) tile_supp[ti] = 1;
+    }
+    // (b) intra-tile suppression bitmask: bit j of mask[i] => earlier-ranked i suppresses j (j > i)
+    for (int w = threadIdx.x; w < nt * nt; w += blockDim.x) {
+      int i = w / nt, j = w - i * nt;
+      if (j > i && nms_iou(tile_box[j], tile_box[i]) > iou_thresh) atomicOr(&tile_mask[i], 1ull << j);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long dead = 0ull;
+      int nk = nkept;
+      for (int i = 0; i < nt && nk < max_per_class; ++i) {
+        if (tile_supp[i] || ((dead >> i) & 1ull)) continue;
+        dead |= tile_mask[i];
+        unsigned long long key = keys[t0 + i];
+        uint32_t idx = (uint32_t)(key & 0xffffffffull);
+        kept_box[nk] = tile_box[i];
+        cls_index[out_base + nk] = (int)idx;
+        cls_score[out_base + nk] = sc[(size_t)idx * lds];
+        ++nk;
+      }
+      s_nkept = nk;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cls_count[b * C + c] = s_nkept;
+}
+
+// grid (B); dynamic smem m_pad * 8 bytes.  Concatenate classes in order, stable sort by score
+// descending, take max_total, pad.
+__global__ void __launch_bounds__(kNmsThreads)
+nms_merge_kernel(const float4* __restrict__ boxes, int P, int C, int max_per_class, int max_total, int m_pad,
+                 const int* __restrict__ cls_count, const int* __restrict__ cls_index,
+                 const float* __restrict__ cls_score, int* __restrict__ num_det, float4* __restrict__ out_boxes,
+                 float* __restrict__ out_scores, float* __restrict__ out_classes, int* __restrict__ out_index) {
+  extern __shared__ unsigned long long keys[];
+  __shared__ int s_total;
+  const int b = blockIdx.x;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  int local = 0;
+  for (int i = threadIdx.x; i < m_pad; i += blockDim.x) {
+    unsigned long long key = ~0ull;
+    if (i < C * max_per_class) {
+      int c = i / max_per_class, r = i - c * max_per_class;
+      if (r < cls_count[b * C + c]) {
+        uint32_t u = __float_as_uint(cls_score[(size_t)b * C * max_per_class + i]);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        key = ((unsigned long long)(~u) << 32) | (uint32_t)i;   // i ascending == (class, NMS rank) order
+        ++local;
+      }
+    }
+    keys[i] = key;
+  }
+  if (local) atomicAdd(&s_total, local);
+  bitonic_sort_u64(keys, m_pad);
+  const int n = min(s_total, max_total);
+  if (threadIdx.x == 0) num_det[b] = n;
+  for (int i = threadIdx.x; i < max_total; i += blockDim.x) {
+    size_t o = (size_t)b * max_total + i;
+    if (i < n) {
+      uint32_t slot = (uint32_t)(keys[i] & 0xffffffffull);
+      int c = slot / max_per_class;
+      int idx = cls_index[(size_t)b * C * max_per_class + slot];
+      out_boxes[o] = boxes[(size_t)b * P + idx];
+      out_scores[o] = cls_score[(size_t)b * C * max_per_class + slot];
+      out_classes[o] = (float)(c + 1);                         // core/builder.py:65
+      out_index[o] = idx;
+    } else {
+      out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+      out_scores[o] = 0.f;
+      out_classes[o] = 1.0f;                                   // 0 + 1 on the zero padding
+      out_index[o] = -1;
+    }
+  }
+}
+
+static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// ---- K9 / K8 label kernels -----------------------------------------------------------------
+__global__ void label_lut_kernel(const int* __restrict__ tok, int T, const int* __restrict__ lut, int V, int C,
+                                 float* __restrict__ labels) {
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) labels[(size_t)b * C + c] = 0.f;
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int id = tok[(size_t)b * T + t];
+    int cls = (id >= 0 && id < V) ? lut[id] : C;
+    if (cls >= 0 && cls < C) labels[(size_t)b * C + cls] = 1.0f;     // one_hot + reduce_max
+  }
+}
+
+// One CTA per image.  Dynamic smem: sim [T*C] + tinv [T] + cinv [C] floats.
+__global__ void __launch_bounds__(256)
+wordvec_match_kernel(const int* __restrict__ tok, int T, const float* __restrict__ emb, int V, int D,
+                     const int* __restrict__ class_ids, int C, const int* __restrict__ exact_lut,
+                     float* __restrict__ labels, float* __restrict__ sim_pooled) {
+  extern __shared__ float smf[];
+  float* sim = smf;            // [T][C]
+  float* tinv = sim + T * C;   // [T]
+  float* cinv = tinv + T;      // [C]
+  float* pooled = cinv + C;    // [C]
+  __shared__ int s_any, s_exact, s_arg;
+  const int b = blockIdx.x;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int* tk = tok + (size_t)b * T;
+  if (threadIdx.x == 0) { s_any = 0; s_exact = 0; s_arg = 0; }
+  // tf.nn.l2_normalize: x * rsqrt(max(sum(x^2), 1e-12))   (models/label_extractor.py:244-245)
+  for (int r = wid; r < T + C; r += nw) {
+    int row = r < T ? min(max(tk[r], 0), V) : class_ids[r - T];
+    const float* e = emb + (size_t)row * D;
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s += e[d] * e[d];
+    s = warp_sum(s);
+    float inv = 1.0f / sqrtf(fmaxf(s, 1e-12f));
+    if (lane == 0) { if (r < T) tinv[r] = inv; else cinv[r - T] = inv; }
+  }
+  __syncthreads();
+  for (int pair = wid; pair < T * C; pair += nw) {
+    int t = pair / C, c = pair - t * C;
+    const float* et = emb + (size_t)min(max(tk[t], 0), V) * D;
+    const float* ec = emb + (size_t)class_ids[c] * D;
+    float ti = tinv[t], ci = cinv[c];
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) s += __fmul_rn(__fmul_rn(ec[d], ci), __fmul_rn(et[d], ti));
+    s = warp_sum(s);
+    if (lane == 0) sim[pair] = s;
+  }
+  __syncthreads();
+  // masked_maximum over tokens (core/utils.py:63-79), mask = token != OOV (:302-308)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mn = INFINITY;
+    for (int t = 0; t < T; ++t) mn = fminf(mn, sim[t * C + c]);
+    float mx = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+      float m = (tk[t] != V) ? 1.f : 0.f;
+      mx = fmaxf(mx, __fmul_rn(__fsub_rn(sim[t * C + c], mn), m));
+    }
+    pooled[c] = __fadd_rn(mx, mn);
+    if (sim_pooled) sim_pooled[(size_t)b * C + c] = pooled[c];
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    int id = tk[t];
+    if (id != V) s_any = 1;
+    int cls = (id >= 0 && id < V) ? exact_lut[id] : C;
+    if (cls >= 0 && cls < C) s_exact = 1;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int arg = 0; float best = pooled[0];
+    for (int c = 1; c < C; ++c) if (pooled[c] > best) { best = pooled[c]; arg = c; }   // tf.argmax: first max
+    s_arg = arg;
+  }
+  __syncthreads();
+  const bool exact = s_exact != 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    labels[(size_t)b * C + c] = exact ? 0.f : ((s_any && c == s_arg) ? 1.f : 0.f);      // :310-317
+  __syncthreads();
+  if (exact)                                                                           // :321-328
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      int id = tk[t];
+      int cls = (id >= 0 && id < V) ? exact_lut[id] : C;
+      if (cls >= 0 && cls < C) labels[(size_t)b * C + cls] = 1.0f;
+    }
+}
+
+}  // namespace c2d
+
+using namespace c2d;
+
+extern "C" {
+
+size_t c2d_nms_workspace_bytes(int B, int P, int C, int max_size_per_class) {
+  (void)P;
+  size_t n = (size_t)B * C;
+  return n * sizeof(int) + n * max_size_per_class * (sizeof(int) + sizeof(float)) + 256;
+}
+
+int c2d_multiclass_nms(const float* boxes, const float* scores, int lds, int B, int P, int C, float score_thresh,
+                       float iou_thresh, int max_size_per_class, int max_total_size, int* num_detections,
+                       float* out_boxes, float* out_scores, float* out_classes, int* out_index, void* workspace,
+                       size_t workspace_bytes, c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 0 && P >= 1 && C >= 1 && lds >= C, "nms: bad shape B=%d P=%d C=%d lds=%d", B, P, C, lds);
+  C2D_CHECK_ARG(max_size_per_class >= 1 && max_total_size >= 1, "nms: bad max sizes");
+  C2D_CHECK_ARG(workspace_bytes >= c2d_nms_workspace_bytes(B, P, C, max_size_per_class), "nms: workspace too small");
+  if (B == 0) return C2D_OK;
+  const int n_pad = next_pow2(P < 64 ? 64 : P);
+  const int m_pad = next_pow2(C * max_size_per_class < 64 ? 64 : C * max_size_per_class);
+  if (max_size_per_class > 128 || n_pad > 16384 || m_pad > 16384) {
+    set_error("nms: supported up to 16384 proposals, max_size_per_class<=128, C*max_size_per_class<=16384");
+    return C2D_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int* cls_count = (int*)workspace;
+  int* cls_index = cls_count + (size_t)B * C;
+  float* cls_score = (float*)(cls_index + (size_t)B * C * max_size_per_class);
+  static bool attr_done = false;
+  if (!attr_done) {
+    C2D_CUDA_OK(cudaFuncSetAttribute(nms_per_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    C2D_CUDA_OK(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    attr_done = true;
+  }
+  nms_per_class_kernel<<<dim3(C, B), kNmsThreads, (size_t)n_pad * 8, st>>>(
+      (const float4*)boxes, scores, lds, P, C, n_pad, score_thresh, iou_thresh, max_size_per_class, cls_count,
+      cls_index, cls_score);
+  nms_merge_kernel<<<B, kNmsThreads, (size_t)m_pad * 8, st>>>((const float4*)boxes, P, C, max_size_per_class,
+                                                             max_total_size, m_pad, cls_count, cls_index, cls_score,
+                                                             num_detections, (float4*)out_boxes, out_scores,
+                                                             out_classes, out_index);
+  count_launch(2);
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_label_lut(const int* token_ids, int B, int T, const int* lut, int V, int C, float* labels,
+                  c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 0 && T >= 0 && V >= 0 && C >= 1, "label_lut: bad shape");
+  if (B == 0) return C2D_OK;
+  label_lut_kernel<<<B, 128, 0, (cudaStream_t)stream>>>(token_ids, T, lut, V, C, labels);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int V, int D, const int* class_ids,
+                      int C, const int* exact_lut, float* labels, float* sim_pooled, c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 0 && T >= 0 && V >= 1 && D >= 1 && C >= 1, "wordvec_match: bad shape");
+  if (B == 0) return C2D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T == 0) {   // models/label_extractor.py:35-38: no tokens => all zero
+    C2D_CUDA_OK(cudaMemsetAsync(labels, 0, (size_t)B * C * sizeof(float), st));
+    if (sim_pooled) C2D_CUDA_OK(cudaMemsetAsync(sim_pooled, 0, (size_t)B * C * sizeof(float), st));
+    return C2D_OK;
+  }
+  size_t smem = ((size_t)T * C + T + 2 * C) * sizeof(float);
+  if (smem > 200 * 1024) {
+    set_error("wordvec_match: T*C too large for shared memory (T=%d C=%d)", T, C);
+    return C2D_ERR_UNSUPPORTED;
+  }
+  C2D_CUDA_OK(cudaFuncSetAttribute(wordvec_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  wordvec_match_kernel<<<B, 256, smem, st>>>(token_ids, T, emb, V, D, class_ids, C, exact_lut, labels, sim_pooled);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// K1 / K1': fused tf.image.crop_and_resize (bilinear, extrapolation 0) + 2x2/2 VALID max-pool,
+// forward and backward.  Reference call sites: models/utils.py:147-160.
+//
+// One CTA per ROI.  Threads map to channel quads (float4, channel-contiguous => every warp
+// reads/writes 512 contiguous bytes); the 14+14 sample coordinates of the ROI are computed
+// once per CTA into shared memory with the exact op-by-op fp32 rounding of the TF CPU kernel
+// (no FMA contraction), so floor/ceil/in-range decisions match the oracle bit for bit.
+// The [N,14,14,C] crop tensor (903 MB / image in the TF graph) is never materialised:
+// HBM traffic is the feature map (L2 resident, 5.5 MB) + the pooled output.
+#include "c2d_common.cuh"
+
+namespace c2d {
+
+constexpr int kMaxCrop = 32;
+
+struct RoiCoords {
+  int lo[2][kMaxCrop];     // floor index   ([0] = y, [1] = x)
+  int hi[2][kMaxCrop];     // ceil index
+  float lerp[2][kMaxCrop];
+  int valid[2][kMaxCrop];
+};
+
+__device__ __forceinline__ void roi_setup_coords(RoiCoords& sc, float4 box, int Hf, int Wf, int crop) {
+  // threads [0,crop) -> y samples, threads [32, 32+crop) -> x samples
+  int t = threadIdx.x;
+  int axis = t >> 5, i = t & 31;
+  if (axis < 2 && i < crop) {
+    int size = axis == 0 ? Hf : Wf;
+    float lo = axis == 0 ? box.x : box.y;
+    float hi = axis == 0 ? box.z : box.w;
+    float sm1 = (float)(size - 1);
+    float coord;
+    if (crop > 1) {
+      float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), sm1), (float)(crop - 1));
+      coord = __fadd_rn(__fmul_rn(lo, sm1), __fmul_rn((float)i, scale));
+    } else {
+      coord = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo, hi)), sm1);
+    }
+    bool valid = !(coord < 0.0f || coord > sm1);
+    if (!valid) coord = 0.0f;
+    float fl = floorf(coord);
+    sc.lo[axis][i] = (int)fl;
+    sc.hi[axis][i] = (int)ceilf(coord);
+    sc.lerp[axis][i] = __fsub_rn(coord, fl);
+    sc.valid[axis][i] = valid ? 1 : 0;
+  }
+}
+
+__device__ __forceinline__ float lerp_rn(float a, float b, float t) {
+  return __fadd_rn(a, __fmul_rn(__fsub_rn(b, a), t));
+}
+
+// One bilinear sample of a channel quad.  img4 = feature map of this ROI's image as float4.
+__device__ __forceinline__ float4 roi_sample(const float4* __restrict__ img4, const RoiCoords& sc, int cy, int cx,
+                                             int Wf, int C4, int q) {
+  if (!(sc.valid[0][cy] & sc.valid[1][cx])) return make_float4(0.f, 0.f, 0.f, 0.f);
+  int t = sc.lo[0][cy], b = sc.hi[0][cy], l = sc.lo[1][cx], r = sc.hi[1][cx];
+  float yl = sc.lerp[0][cy], xl = sc.lerp[1][cx];
+  float4 tl = __ldg(img4 + ((size_t)t * Wf + l) * C4 + q);
+  float4 tr = __ldg(img4 + ((size_t)t * Wf + r) * C4 + q);
+  float4 bl = __ldg(img4 + ((size_t)b * Wf + l) * C4 + q);
+  float4 br = __ldg(img4 + ((size_t)b * Wf + r) * C4 + q);
+  float4 o;
+  o.x = lerp_rn(lerp_rn(tl.x, tr.x, xl), lerp_rn(bl.x, br.x, xl), yl);
+  o.y = lerp_rn(lerp_rn(tl.y, tr.y, xl), lerp_rn(bl.y, br.y, xl), yl);
+  o.z = lerp_rn(lerp_rn(tl.z, tr.z, xl), lerp_rn(bl.z, br.z, xl), yl);
+  o.w = lerp_rn(lerp_rn(tl.w, tr.w, xl), lerp_rn(bl.w, br.w, xl), yl);
+  return o;
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(288)
+roi_crop_maxpool_fwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
+                            int P, int crop, OutT* __restrict__ out) {
+  __shared__ RoiCoords sc;
+  const int roi = blockIdx.x;
+  const int b = roi / P;
+  roi_setup_coords(sc, boxes[roi], Hf, Wf, crop);
+  __syncthreads();
+  const int C4 = Cf >> 2, hp = crop >> 1;
+  const float4* img4 = reinterpret_cast<const float4*>(fmap + (size_t)b * Hf * Wf * Cf);
+  OutT* o = out + (size_t)roi * hp * hp * Cf;
+  const int items = hp * hp * C4;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    int q = w % C4, pos = w / C4;
+    int py = pos / hp, px = pos - py * hp;
+    float4 v00 = roi_sample(img4, sc, 2 * py, 2 * px, Wf, C4, q);
+    float4 v01 = roi_sample(img4, sc, 2 * py, 2 * px + 1, Wf, C4, q);
+    float4 v10 = roi_sample(img4, sc, 2 * py + 1, 2 * px, Wf, C4, q);
+    float4 v11 = roi_sample(img4, sc, 2 * py + 1, 2 * px + 1, Wf, C4, q);
+    float4 m;
+    m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x));
+    m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
+    m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z));
+    m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
+    st4(o + (size_t)pos * Cf + 4 * q, m);
+  }
+}
+
+// first maximum in row-major (dy,dx) window order
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  int k = 0; float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  return k;
+}
+
+__device__ __forceinline__ void scatter_one(float* __restrict__ dimg, const RoiCoords& sc, int cy, int cx, int Wf,
+                                            int Cf, int ch, float g) {
+  if (g == 0.0f || !(sc.valid[0][cy] & sc.valid[1][cx])) return;
+  int t = sc.lo[0][cy], b = sc.hi[0][cy], l = sc.lo[1][cx], r = sc.hi[1][cx];
+  float yl = sc.lerp[0][cy], xl = sc.lerp[1][cx];
+  float dtop = (1.0f - yl) * g, dbot = yl * g;   // CropAndResizeGradImage order
+  float w;
+  w = (1.0f - xl) * dtop; if (w != 0.f) atomicAdd(dimg + ((size_t)t * Wf + l) * Cf + ch, w);
+  w = xl * dtop;          if (w != 0.f) atomicAdd(dimg + ((size_t)t * Wf + r) * Cf + ch, w);
+  w = (1.0f - xl) * dbot; if (w != 0.f) atomicAdd(dimg + ((size_t)b * Wf + l) * Cf + ch, w);
+  w = xl * dbot;          if (w != 0.f) atomicAdd(dimg + ((size_t)b * Wf + r) * Cf + ch, w);
+}
+
+template <typename GradT>
+__global__ void __launch_bounds__(288)
+roi_crop_maxpool_bwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
+                            int P, int crop, const GradT* __restrict__ dout, float* __restrict__ dfmap) {
+  __shared__ RoiCoords sc;
+  const int roi = blockIdx.x;
+  const int b = roi / P;
+  roi_setup_coords(sc, boxes[roi], Hf, Wf, crop);
+  __syncthreads();
+  const int C4 = Cf >> 2, hp = crop >> 1;
+  const float4* img4 = reinterpret_cast<const float4*>(fmap + (size_t)b * Hf * Wf * Cf);
+  float* dimg = dfmap + (size_t)b * Hf * Wf * Cf;
+  const GradT* go = dout + (size_t)roi * hp * hp * Cf;
+  const int items = hp * hp * C4;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    int q = w % C4, pos = w / C4;
+    int py = pos / hp, px = pos - py * hp;
+    float4 g = ld4(go + (size_t)pos * Cf + 4 * q);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    float4 v00 = roi_sample(img4, sc, 2 * py, 2 * px, Wf, C4, q);
+    float4 v01 = roi_sample(img4, sc, 2 * py, 2 * px + 1, Wf, C4, q);
+    float4 v10 = roi_sample(img4, sc, 2 * py + 1, 2 * px, Wf, C4, q);
+    float4 v11 = roi_sample(img4, sc, 2 * py + 1, 2 * px + 1, Wf, C4, q);
+    int k;
+    k = argmax4(v00.x, v01.x, v10.x, v11.x);
+    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 0, g.x);
+    k = argmax4(v00.y, v01.y, v10.y, v11.y);
+    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 1, g.y);
+    k = argmax4(v00.z, v01.z, v10.z, v11.z);
+    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 2, g.z);
+    k = argmax4(v00.w, v01.w, v10.w, v11.w);
+    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 3, g.w);
+  }
+}
+
+static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k, int pool_s) {
+  C2D_CHECK_ARG(B >= 0 && P >= 0 && Hf >= 1 && Wf >= 1, "roi: bad shape B=%d P=%d Hf=%d Wf=%d", B, P, Hf, Wf);
+  C2D_CHECK_ARG(Cf >= 4 && Cf % 4 == 0, "roi: feature depth %d must be a multiple of 4", Cf);
+  if (!(pool_k == 2 && pool_s == 2 && crop >= 2 && crop <= kMaxCrop && crop % 2 == 0)) {
+    set_error("roi: only maxpool_kernel_size=2, maxpool_stride=2, even initial_crop_size<=%d supported "
+              "(got k=%d s=%d crop=%d)", kMaxCrop, pool_k, pool_s, crop);
+    return C2D_ERR_UNSUPPORTED;
+  }
+  return C2D_OK;
+}
+
+}  // namespace c2d
+
+using namespace c2d;
+
+extern "C" {
+
+int c2d_roi_crop_maxpool_fwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes, int P,
+                             int crop_size, int pool_k, int pool_s, void* out, int out_dtype, c2d_stream_t stream) {
+  int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
+  if (rc != C2D_OK) return rc;
+  C2D_CHECK_ARG(out_dtype == C2D_F32 || out_dtype == C2D_BF16, "roi: bad dtype %d", out_dtype);
+  if (B * P == 0) return C2D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (out_dtype == C2D_F32)
+    roi_crop_maxpool_fwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
+                                                             (float*)out);
+  else
+    roi_crop_maxpool_fwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
+                                                                     crop_size, (__nv_bfloat16*)out);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_roi_crop_maxpool_bwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes, int P,
+                             int crop_size, int pool_k, int pool_s, const void* dout, int dout_dtype, float* dfmap,
+                             c2d_stream_t stream) {
+  int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
+  if (rc != C2D_OK) return rc;
+  C2D_CHECK_ARG(dout_dtype == C2D_F32 || dout_dtype == C2D_BF16, "roi: bad dtype %d", dout_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return C2D_OK;
+  C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
+  if (P == 0) return C2D_OK;
+  if (dout_dtype == C2D_F32)
+    roi_crop_maxpool_bwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
+                                                             (const float*)dout, dfmap);
+  else
+    roi_crop_maxpool_bwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
+                                                                     crop_size, (const __nv_bfloat16*)dout, dfmap);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,362 @@
+"""torch-facing wrappers (autograd Functions) over the C ABI.  torch is used for device memory,
+streams and autograd bookkeeping only; every FLOP below runs in the hand-written CUDA library.
+"""
+import torch
+
+from cap2det_b200 import capi
+from cap2det_b200.capi import call, ptr, stream, require_cuda
+
+HEAD_FEATURE_DIMS = 1024
+HEAD_IN_HW = 7
+HEAD_IN_CH = 576
+
+
+def _rows(t):
+  """[..., n] float32 view whose rows are `ld` floats apart -> (ptr, ld, rows, n)."""
+  import ctypes
+  if t.dtype != torch.float32 or not t.is_cuda:
+    raise ValueError('expected a CUDA float32 tensor')
+  n = t.shape[-1]
+  rows = t.numel() // max(n, 1)
+  if t.is_contiguous():
+    return ctypes.c_void_p(t.data_ptr()), n, rows, n
+  if t.stride(-1) != 1:
+    raise ValueError('last dimension must be dense')
+  ld = t.stride(-2)
+  expect = ld
+  for d in range(t.dim() - 2, -1, -1):
+    if t.shape[d] != 1 and t.stride(d) != expect:
+      raise ValueError('rows must be uniformly strided')
+    expect *= t.shape[d]
+  return ctypes.c_void_p(t.data_ptr()), ld, rows, n
+
+
+def _f32(t):
+  if t.dtype != torch.float32:
+    raise ValueError('expected float32 tensor, got %s' % t.dtype)
+  return t
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: crop_and_resize + max_pool  (models/utils.py:147-160)
+# ---------------------------------------------------------------------------------------------
+class _RoiCropMaxPool(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, fmap, proposals, crop_size, pool_k, pool_s, out_dtype):
+    require_cuda(fmap, proposals)
+    _f32(fmap); _f32(proposals)
+    B, Hf, Wf, Cf = fmap.shape
+    P = proposals.shape[1]
+    hp = crop_size // pool_s
+    out = torch.empty((B * P, hp, hp, Cf), dtype=out_dtype, device=fmap.device)
+    call('c2d_roi_crop_maxpool_fwd', ptr(fmap), B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s,
+         ptr(out), capi.dtype_code(out_dtype), stream())
+    ctx.save_for_backward(fmap, proposals)
+    ctx.cfg = (crop_size, pool_k, pool_s)
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    fmap, proposals = ctx.saved_tensors
+    crop_size, pool_k, pool_s = ctx.cfg
+    B, Hf, Wf, Cf = fmap.shape
+    P = proposals.shape[1]
+    dout = dout.contiguous()
+    dfmap = torch.empty_like(fmap)
+    call('c2d_roi_crop_maxpool_bwd', ptr(fmap), B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s,
+         ptr(dout), capi.dtype_code(dout.dtype), ptr(dfmap), stream())
+    return dfmap, None, None, None, None, None
+
+
+def roi_crop_maxpool(fmap, proposals, crop_size=14, pool_k=2, pool_s=2, out_dtype=torch.float32):
+  """fmap [B,Hf,Wf,C] fp32, proposals [B,P,4] normalised -> [B*P, crop/2, crop/2, C]."""
+  return _RoiCropMaxPool.apply(fmap.contiguous(), proposals.contiguous(), crop_size, pool_k, pool_s, out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------
+# K2/K3: Mixed_5a..5c head + spatial mean + dropout  (models/utils.py:165-177)
+# ---------------------------------------------------------------------------------------------
+def head_conv_specs():
+  """[(tf_scope, k, cin, cout, stride, offsets dict)] of the packed head parameter buffer."""
+  import ctypes
+  lib = capi.load()
+  out = []
+  for i in range(lib.c2d_head_num_convs()):
+    k, cin, cout, stride = (ctypes.c_int() for _ in range(4))
+    name = ctypes.c_char_p()
+    capi.check(lib.c2d_head_conv_spec(i, ctypes.byref(k), ctypes.byref(cin), ctypes.byref(cout),
+                                      ctypes.byref(stride), ctypes.byref(name)))
+    offs = [ctypes.c_longlong() for _ in range(5)]
+    capi.check(lib.c2d_head_param_offsets(i, *[ctypes.byref(o) for o in offs]))
+    out.append((name.value.decode(), k.value, cin.value, cout.value, stride.value,
+                dict(zip(('weights', 'gamma', 'beta', 'moving_mean', 'moving_variance'),
+                         [o.value for o in offs]))))
+  return out
+
+
+def head_param_floats():
+  return int(capi.load().c2d_head_param_floats())
+
+
+class _HeadMixed5(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x0, params, keep_mask, keep_prob, need_dx0):
+    require_cuda(x0, params, keep_mask)
+    _f32(params)
+    n = x0.shape[0]
+    if tuple(x0.shape[1:]) != (HEAD_IN_HW, HEAD_IN_HW, HEAD_IN_CH):
+      raise ValueError('head expects [N,7,7,576] ROI features, got %s' % (tuple(x0.shape),))
+    dt = capi.dtype_code(x0.dtype)
+    lib = capi.load()
+    nbytes = lib.c2d_head_workspace_bytes(n, dt)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x0.device)
+    feat = torch.empty((n, HEAD_FEATURE_DIMS), dtype=torch.float32, device=x0.device)
+    call('c2d_head_mixed5_fwd', ptr(x0), n, dt, ptr(params), ptr(ws), nbytes, ptr(keep_mask), float(keep_prob),
+         ptr(feat), stream())
+    ctx.save_for_backward(x0, params, keep_mask, ws)
+    ctx.keep_prob = float(keep_prob)
+    ctx.need_dx0 = need_dx0
+    return feat
+
+  @staticmethod
+  def backward(ctx, dfeat):
+    x0, params, keep_mask, ws = ctx.saved_tensors
+    n = x0.shape[0]
+    dt = capi.dtype_code(x0.dtype)
+    dfeat = dfeat.contiguous()
+    dparams = torch.empty_like(params)
+    dx0 = torch.empty_like(x0) if (ctx.need_dx0 and ctx.needs_input_grad[0]) else None
+    call('c2d_head_mixed5_bwd', ptr(x0), n, dt, ptr(params), ptr(ws), ws.numel(), ptr(keep_mask), ctx.keep_prob,
+         ptr(dfeat), ptr(dparams), ptr(dx0), stream())
+    return dx0, dparams, None, None, None
+
+
+def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True):
+  """x0 [N,7,7,576] (fp32 or bf16), packed params fp32 -> proposal features [N,1024] fp32."""
+  return _HeadMixed5.apply(x0.contiguous(), params, keep_mask, keep_prob, need_dx0)
+
+
+# ---------------------------------------------------------------------------------------------
+# K4: concatenated fully connected layers  (models/cap2det_model.py:79-88,190-197)
+# ---------------------------------------------------------------------------------------------
+def _ld16(n):
+  return (n + 15) // 16 * 16
+
+
+class _FcConcat(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, w, b):
+    require_cuda(x, w, b)
+    M, D = x.shape
+    N = w.shape[0]
+    ld = _ld16(N)
+    y = torch.zeros((M, ld), dtype=torch.float32, device=x.device)
+    call('c2d_fc_fwd', ptr(x), M, D, ptr(w), ptr(b), N, ptr(y), ld, capi.C2D_F32, None, 0, stream())
+    ctx.save_for_backward(x, w)
+    return y
+
+  @staticmethod
+  def backward(ctx, dy):
+    x, w = ctx.saved_tensors
+    M, D = x.shape
+    N = w.shape[0]
+    ld = _ld16(N)
+    dy = dy.contiguous()
+    lib = capi.load()
+    nbytes = lib.c2d_fc_workspace_bytes(M, D, N, capi.C2D_F32)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+    dw = torch.empty_like(w)
+    db = torch.empty((N,), dtype=torch.float32, device=x.device)
+    call('c2d_fc_bwd', ptr(x), M, D, ptr(w), N, ptr(dy), ld, ptr(dx), ptr(dw), ptr(db), capi.C2D_F32, ptr(ws),
+         nbytes, stream())
+    return dx, dw, db
+
+
+def fc_concat(x, w, b):
+  """x [M,D] . w [N,D]^T + b [N] -> y [M, ld16(N)] (columns >= N are zero padding)."""
+  return _FcConcat.apply(x.contiguous(), w.contiguous(), b.contiguous())
+
+
+# ---------------------------------------------------------------------------------------------
+# K5: MIDN  (models/cap2det_model.py:70-109)
+# ---------------------------------------------------------------------------------------------
+class _Midn(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logits_all, col_r, col_c, num_classes, num_proposals):
+    """logits_all [B,P,ld] holds both streams: columns [col_r, col_r+C) and [col_c, col_c+C)."""
+    require_cuda(logits_all, num_proposals)
+    B, P, ld = logits_all.shape
+    C = num_classes
+    dev = logits_all.device
+    class_logits = torch.empty((B, C), dtype=torch.float32, device=dev)
+    scores = torch.empty((B, P, C), dtype=torch.float32, device=dev)
+    proba = torch.empty((B, P, C), dtype=torch.float32, device=dev)
+    base = logits_all.data_ptr()
+    import ctypes
+    call('c2d_midn_fwd', ctypes.c_void_p(base + 4 * col_r), ctypes.c_void_p(base + 4 * col_c), ld,
+         ptr(num_proposals), B, P, C, ptr(class_logits), ptr(scores), ptr(proba), stream())
+    ctx.save_for_backward(logits_all, num_proposals, class_logits, proba)
+    ctx.cfg = (col_r, col_c, C)
+    ctx.set_materialize_grads(False)
+    return class_logits, scores, proba
+
+  @staticmethod
+  def backward(ctx, d_cl, d_sc, d_pr):
+    import ctypes
+    logits_all, num_proposals, class_logits, proba = ctx.saved_tensors
+    col_r, col_c, C = ctx.cfg
+    B, P, ld = logits_all.shape
+    d_all = torch.zeros_like(logits_all)
+    d_cl = d_cl.contiguous() if d_cl is not None else None
+    d_sc = d_sc.contiguous() if d_sc is not None else None
+    d_pr = d_pr.contiguous() if d_pr is not None else None
+    base = logits_all.data_ptr()
+    dbase = d_all.data_ptr()
+    call('c2d_midn_bwd', ctypes.c_void_p(base + 4 * col_c), ld, ptr(num_proposals), B, P, C, ptr(class_logits),
+         ptr(proba), ptr(d_cl), ptr(d_sc), ptr(d_pr), ctypes.c_void_p(dbase + 4 * col_r),
+         ctypes.c_void_p(dbase + 4 * col_c), ld, stream())
+    return d_all, None, None, None, None
+
+
+def midn(logits_all, col_r, col_c, num_classes, num_proposals):
+  return _Midn.apply(logits_all, col_r, col_c, num_classes, num_proposals)
+
+
+# ---------------------------------------------------------------------------------------------
+# losses
+# ---------------------------------------------------------------------------------------------
+class _SigmoidCeMean(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, labels, logits, weight):
+    require_cuda(labels, logits)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    call('c2d_sigmoid_ce_mean_fwd', ptr(labels), ptr(logits), logits.numel(), float(weight), ptr(loss), stream())
+    ctx.save_for_backward(labels, logits)
+    ctx.weight = float(weight)
+    return loss
+
+  @staticmethod
+  def backward(ctx, dloss):
+    labels, logits = ctx.saved_tensors
+    dlogits = torch.empty_like(logits)
+    dloss = dloss.contiguous()
+    call('c2d_sigmoid_ce_mean_bwd', ptr(labels), ptr(logits), logits.numel(), ctx.weight, ptr(dloss), ptr(dlogits),
+         stream())
+    return None, dlogits, None
+
+
+def sigmoid_ce_mean(labels, logits, weight=1.0):
+  """weight * reduce_mean(sigmoid_cross_entropy_with_logits)  (models/cap2det_model.py:293-297)."""
+  return _SigmoidCeMean.apply(labels.contiguous(), logits.contiguous(), weight)
+
+
+def softmax_rows(x):
+  """tf.nn.softmax(x, axis=-1) for a [..., n] tensor (may be a column slice of a wider buffer)."""
+  p, ld, rows, n = _rows(x)
+  y = torch.empty(tuple(x.shape), dtype=torch.float32, device=x.device)
+  call('c2d_softmax_rows', p, ld, rows, n, ptr(y), n, stream())
+  return y
+
+
+def oicr_assign(labels, num_proposals, proposals, scores0_cls, iou_threshold):
+  """models/utils.py:37-95.  scores0_cls [B,P,C] (class columns of the previous stage; may be a slice).
+
+  Returns (proposal_ind [B,C] int64, proposal_labels [B,P,1+C], status int32 tensor)."""
+  require_cuda(labels, num_proposals, proposals)
+  B, P, C = scores0_cls.shape
+  s0_ptr, ld0, _, _ = _rows(scores0_cls)
+  dev = labels.device
+  ind = torch.empty((B, C), dtype=torch.int64, device=dev)
+  pl = torch.empty((B, P, C + 1), dtype=torch.float32, device=dev)
+  status = torch.empty((1,), dtype=torch.int32, device=dev)
+  call('c2d_oicr_assign', ptr(labels), ptr(num_proposals), ptr(proposals), s0_ptr, ld0,
+       float(iou_threshold), B, P, C, ptr(ind), ptr(pl), ptr(status), stream())
+  return ind, pl, status
+
+
+class _OicrCe(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, logits_all, col, proposal_labels, num_proposals, weight):
+    import ctypes
+    require_cuda(logits_all, proposal_labels, num_proposals)
+    B, P, ld = logits_all.shape
+    C = proposal_labels.shape[-1] - 1
+    loss = torch.empty((), dtype=torch.float32, device=logits_all.device)
+    call('c2d_oicr_ce_fwd', ptr(proposal_labels), ctypes.c_void_p(logits_all.data_ptr() + 4 * col), ld,
+         ptr(num_proposals), B, P, C, float(weight), ptr(loss), stream())
+    ctx.save_for_backward(logits_all, proposal_labels, num_proposals)
+    ctx.cfg = (col, float(weight))
+    return loss
+
+  @staticmethod
+  def backward(ctx, dloss):
+    import ctypes
+    logits_all, pl, num_proposals = ctx.saved_tensors
+    col, weight = ctx.cfg
+    B, P, ld = logits_all.shape
+    C = pl.shape[-1] - 1
+    d_all = torch.zeros_like(logits_all)
+    dloss = dloss.contiguous()
+    call('c2d_oicr_ce_bwd', ptr(pl), ctypes.c_void_p(logits_all.data_ptr() + 4 * col), ld, ptr(num_proposals),
+         B, P, C, weight, ptr(dloss), ctypes.c_void_p(d_all.data_ptr() + 4 * col), ld, stream())
+    return d_all, None, None, None, None
+
+
+def oicr_cross_entropy(logits_all, col, proposal_labels, num_proposals, weight=1.0):
+  """weight * calc_oicr_loss's soft-label CE on columns [col, col+1+C) of logits_all."""
+  return _OicrCe.apply(logits_all, col, proposal_labels.contiguous(), num_proposals, weight)
+
+
+# ---------------------------------------------------------------------------------------------
+# K7: NMS post-process (core/builder.py:31-65)
+# ---------------------------------------------------------------------------------------------
+def multiclass_nms(boxes, scores, score_thresh, iou_thresh, max_size_per_class, max_total_size):
+  """boxes [B,P,4], scores [B,P,C] -> (num_detections, boxes, scores, classes(1-based), index)."""
+  require_cuda(boxes)
+  boxes = boxes.contiguous()
+  B, P, C = scores.shape
+  sc_ptr, lds, _, _ = _rows(scores)
+  dev = boxes.device
+  lib = capi.load()
+  nbytes = lib.c2d_nms_workspace_bytes(B, P, C, max_size_per_class)
+  ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+  num = torch.empty((B,), dtype=torch.int32, device=dev)
+  ob = torch.empty((B, max_total_size, 4), dtype=torch.float32, device=dev)
+  osc = torch.empty((B, max_total_size), dtype=torch.float32, device=dev)
+  oc = torch.empty((B, max_total_size), dtype=torch.float32, device=dev)
+  oi = torch.empty((B, max_total_size), dtype=torch.int32, device=dev)
+  call('c2d_multiclass_nms', ptr(boxes), sc_ptr, lds, B, P, C, float(score_thresh), float(iou_thresh),
+       int(max_size_per_class), int(max_total_size), ptr(num), ptr(ob), ptr(osc), ptr(oc), ptr(oi), ptr(ws), nbytes,
+       stream())
+  return num, ob, osc, oc, oi
+
+
+# ---------------------------------------------------------------------------------------------
+# K8/K9: label kernels
+# ---------------------------------------------------------------------------------------------
+def label_lut(token_ids, lut, num_classes):
+  require_cuda(token_ids, lut)
+  B, T = token_ids.shape
+  labels = torch.empty((B, num_classes), dtype=torch.float32, device=token_ids.device)
+  call('c2d_label_lut', ptr(token_ids), B, T, ptr(lut), lut.numel(), num_classes, ptr(labels), stream())
+  return labels
+
+
+def wordvec_match(token_ids, emb, class_ids, exact_lut, return_similarity=False):
+  require_cuda(token_ids, emb, class_ids, exact_lut)
+  B, T = token_ids.shape
+  V = emb.shape[0] - 1
+  D = emb.shape[1]
+  C = class_ids.numel()
+  labels = torch.empty((B, C), dtype=torch.float32, device=token_ids.device)
+  sim = torch.empty((B, C), dtype=torch.float32, device=token_ids.device) if return_similarity else None
+  call('c2d_wordvec_match', ptr(token_ids), B, T, ptr(emb), V, D, ptr(class_ids), C, ptr(exact_lut), ptr(labels),
+       ptr(sim), stream())
+  return (labels, sim) if return_similarity else labels

@@ -1,0 +1,173 @@
+/*
+ * cap2det_b200 -- C ABI of the B200 (sm_100a) implementation of Cap2Det's per-image
+ * proposal hot path.
+ *
+ * The reference (yekeren/Cap2Det) is pure Python on TensorFlow 1.x; it has no FFI of its
+ * own.  Each entry point below replaces the TF / OD-API op call(s) of the reference that
+ * the comment cites (paths relative to the reference root).  All pointers are DEVICE
+ * pointers unless stated otherwise, tensors are dense row-major (NHWC / [B,P,.]) fp32
+ * unless a dtype argument says otherwise, `stream` is a cudaStream_t, nothing is
+ * allocated inside (callers pass workspaces sized by the *_workspace_bytes queries) and
+ * no call synchronises the device.  Every function returns C2D_OK (0) or a negative
+ * error code; c2d_last_error() returns the message (mirrors the reference's ValueError /
+ * tf.errors.InvalidArgumentError behaviour).
+ */
+#ifndef CAP2DET_B200_H_
+#define CAP2DET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* c2d_stream_t; /* cudaStream_t */
+
+enum {
+  C2D_OK = 0,
+  C2D_ERR_INVALID_ARG = -1, /* ValueError / InvalidArgumentError */
+  C2D_ERR_CUDA = -2,        /* launch or runtime failure */
+  C2D_ERR_UNSUPPORTED = -3  /* shape / option outside what the path uses */
+};
+
+enum { C2D_F32 = 0, C2D_BF16 = 1 };
+
+/* masked reductions, core/utils.py:63-214 */
+enum {
+  C2D_MASKED_MAX = 0,    /* masked_maximum  core/utils.py:63  */
+  C2D_MASKED_MIN = 1,    /* masked_minimum  core/utils.py:82  */
+  C2D_MASKED_SUM = 2,    /* masked_sum(_nd) core/utils.py:101,134 */
+  C2D_MASKED_AVG = 3,    /* masked_avg(_nd) core/utils.py:116,150 */
+  C2D_MASKED_ARGMAX = 4, /* masked_argmax   core/utils.py:187 */
+  C2D_MASKED_ARGMIN = 5  /* masked_argmin   core/utils.py:202 */
+};
+
+/* ---- library ------------------------------------------------------------------ */
+int c2d_version(void);
+const char* c2d_last_error(void);
+/* Kernels launched by this library since the last reset (all threads). */
+long long c2d_launch_count(void);
+void c2d_reset_launch_count(void);
+
+/* ---- core/box_utils.py:9-97 (boxes are [n,4] ymin,xmin,ymax,xmax) ---------------- */
+int c2d_box_area(const float* box, int n, float* area, c2d_stream_t stream);                        /* :44-57 */
+int c2d_box_intersect(const float* box1, const float* box2, int n, float* out, c2d_stream_t stream); /* :60-80 */
+int c2d_box_iou(const float* box1, const float* box2, int n, float* iou, c2d_stream_t stream);       /* :83-97 */
+int c2d_box_flip_left_right(const float* box, int n, float* out, c2d_stream_t stream);               /* :29-41 */
+int c2d_box_scale_to_new_size(const float* box, int n, int img_h, int img_w, int pad_h, int pad_w,
+                              float* out, c2d_stream_t stream);                                      /* :9-26 */
+
+/* ---- core/utils.py:63-214.  data [n,m,d], mask [n,m] (broadcast over d), reduce over m.
+ * Float results go to out_f [n,d]; ARGMAX/ARGMIN write int64 indices to out_i [n,d]. */
+int c2d_masked_reduce(const float* data, const float* mask, int n, int m, int d, int op,
+                      float* out_f, long long* out_i, c2d_stream_t stream);
+/* core/utils.py:172-184 masked_softmax over axis m: softmax(data - 1e10*(1-mask)). */
+int c2d_masked_softmax(const float* data, const float* mask, int n, int m, int d, float* out,
+                       c2d_stream_t stream);
+
+/* ---- K1: tf.image.crop_and_resize + slim.max_pool2d, models/utils.py:147-160 ------
+ * fmap [B,Hf,Wf,Cf] fp32, boxes [B*P,4] normalised, box b*P+p reads image b
+ * (models/utils.py:148-149).  out [B*P, crop/pool_s, crop/pool_s, Cf] in out_dtype.
+ * Supported: pool_k == pool_s == 2, crop_size even and <= 32, Cf % 4 == 0. */
+int c2d_roi_crop_maxpool_fwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes,
+                             int P, int crop_size, int pool_k, int pool_s, void* out, int out_dtype,
+                             c2d_stream_t stream);
+/* Gradient w.r.t. fmap (CropAndResizeGradImage o MaxPoolGrad).  dfmap is overwritten. */
+int c2d_roi_crop_maxpool_bwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes,
+                             int P, int crop_size, int pool_k, int pool_s, const void* dout,
+                             int dout_dtype, float* dfmap, c2d_stream_t stream);
+
+/* ---- K2/K3: box-classifier head, models/utils.py:165-177 ---------------------------
+ * extract_box_classifier_features (Inception-v2 Mixed_5a..5c, OD-API) -> reduce_mean over
+ * (1,2) -> slim.dropout.  Parameters live in ONE packed fp32 buffer; conv i stores
+ * weights OHWI [cout,k,k,cin] then gamma, beta, moving_mean, moving_variance [cout]. */
+int c2d_head_num_convs(void);
+int c2d_head_conv_spec(int i, int* k, int* cin, int* cout, int* stride, const char** tf_scope);
+long long c2d_head_param_floats(void);
+int c2d_head_param_offsets(int i, long long* weights, long long* gamma, long long* beta,
+                           long long* mean, long long* var);
+size_t c2d_head_workspace_bytes(int n_rois, int dtype);
+/* x0 [n,7,7,576] (dtype), feat [n,1024] fp32.  keep_mask [n,1024] of {0,1} or NULL
+ * (is_training False => identity, TF1 slim.dropout).  The workspace keeps the
+ * activations for c2d_head_mixed5_bwd. */
+int c2d_head_mixed5_fwd(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                        size_t workspace_bytes, const float* keep_mask, float keep_prob, float* feat,
+                        c2d_stream_t stream);
+/* dparams (packed like params; moving stats get 0) is overwritten; dx0 (dtype) may be NULL. */
+int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                        size_t workspace_bytes, const float* keep_mask, float keep_prob,
+                        const float* dfeat, float* dparams, void* dx0, c2d_stream_t stream);
+
+/* ---- K4: slim.fully_connected(activation_fn=None), models/cap2det_model.py:79-88,190-197.
+ * The 2 MIDN + K OICR layers run as ONE product: y[M,ldy] = x[M,D] . w[N,D]^T + b[N]. */
+size_t c2d_fc_workspace_bytes(int M, int D, int N, int dtype);
+int c2d_fc_fwd(const float* x, int M, int D, const float* w, const float* b, int N, float* y, int ldy,
+               int dtype, void* workspace, size_t workspace_bytes, c2d_stream_t stream);
+int c2d_fc_bwd(const float* x, int M, int D, const float* w, int N, const float* dy, int ldy,
+               float* dx, float* dw, float* db, int dtype, void* workspace, size_t workspace_bytes,
+               c2d_stream_t stream);
+
+/* ---- K5: MIDN scoring, models/cap2det_model.py:70-109 -------------------------------
+ * logits_* are [B,P,C] slices with row stride ld floats.  Outputs dense. */
+int c2d_midn_fwd(const float* logits_r_given_c, const float* logits_c_given_r, int ld,
+                 const int* num_proposals, int B, int P, int C, float* class_logits,
+                 float* proposal_scores, float* proba_r_given_c, c2d_stream_t stream);
+/* Any of d_class_logits [B,C], d_proposal_scores, d_proba [B,P,C] may be NULL (= 0).
+ * Writes d_logits_r / d_logits_c as [B,P,C] slices with row stride ldd. */
+int c2d_midn_bwd(const float* logits_c_given_r, int ld, const int* num_proposals, int B, int P, int C,
+                 const float* class_logits, const float* proba_r_given_c, const float* d_class_logits,
+                 const float* d_proposal_scores, const float* d_proba, float* d_logits_r,
+                 float* d_logits_c, int ldd, c2d_stream_t stream);
+
+/* tf.nn.sigmoid_cross_entropy_with_logits + reduce_mean * weight, models/cap2det_model.py:293-297 */
+int c2d_sigmoid_ce_mean_fwd(const float* labels, const float* logits, int n, float weight, float* loss,
+                            c2d_stream_t stream);
+int c2d_sigmoid_ce_mean_bwd(const float* labels, const float* logits, int n, float weight,
+                            const float* dloss, float* dlogits, c2d_stream_t stream);
+
+/* tf.nn.softmax(axis=-1) on rows with stride, models/cap2det_model.py:135,328 */
+int c2d_softmax_rows(const float* x, int ldx, int rows, int n, float* y, int ldy, c2d_stream_t stream);
+
+/* ---- K6: calc_oicr_loss, models/utils.py:15-105 ---------------------------------------
+ * scores0_cls points at class column 0 of the previous stage's scores (row stride ld0);
+ * (the reference's background column never enters the arg-max, models/utils.py:46).
+ * Writes proposal_ind [B,C] int64 (masked_argmax), proposal_labels [B,P,1+C] (normalised
+ * soft labels) and *status (device int): 0, or 1 if the reference's tf.Assert
+ * ("Probabilities not sum to ONE", models/utils.py:92-95) would fire. */
+int c2d_oicr_assign(const float* labels, const int* num_proposals, const float* proposals,
+                    const float* scores0_cls, int ld0, float iou_threshold, int B, int P, int C,
+                    long long* proposal_ind, float* proposal_labels, int* status, c2d_stream_t stream);
+/* loss (device scalar) = weight * mean_b( sum_p mask*CE(labels_p, scores1_p) / max(1e-10, n_b) ) */
+int c2d_oicr_ce_fwd(const float* proposal_labels, const float* scores1, int ld1, const int* num_proposals,
+                    int B, int P, int C, float weight, float* loss, c2d_stream_t stream);
+int c2d_oicr_ce_bwd(const float* proposal_labels, const float* scores1, int ld1, const int* num_proposals,
+                    int B, int P, int C, float weight, const float* dloss, float* dscores1, int ldd,
+                    c2d_stream_t stream);
+
+/* ---- K7: core/builder.py:31-65 (_post_process -> batch_multiclass_non_max_suppression) --
+ * boxes [B,P,4]; scores [B,P,C] with row stride lds.  Outputs: num_detections [B] int32,
+ * boxes [B,max_total,4], scores [B,max_total], classes [B,max_total] (1-based float, padding
+ * rows 1.0 like core/builder.py:65), index [B,max_total] int32 proposal index (-1 padding). */
+size_t c2d_nms_workspace_bytes(int B, int P, int C, int max_size_per_class);
+int c2d_multiclass_nms(const float* boxes, const float* scores, int lds, int B, int P, int C,
+                       float score_thresh, float iou_thresh, int max_size_per_class, int max_total_size,
+                       int* num_detections, float* out_boxes, float* out_scores, float* out_classes,
+                       int* out_index, void* workspace, size_t workspace_bytes, c2d_stream_t stream);
+
+/* ---- K9: _match_labels / ExtendMatch lookup, models/label_extractor.py:15-39,180-207 ----
+ * token_ids [B,T] int32 (host tokeniser output; strings never reach the GPU), lut [V] maps a
+ * token id to a class id or to C (out of vocabulary).  labels [B,C] in {0,1}. */
+int c2d_label_lut(const int* token_ids, int B, int T, const int* lut, int V, int C, float* labels,
+                  c2d_stream_t stream);
+/* ---- K8: WordVectorMatchExtractor.extract_labels, models/label_extractor.py:251-328 ------
+ * emb [V+1,D] (row V = OOV), class_ids [C] rows of the classes, exact_lut as c2d_label_lut.
+ * sim_pooled [B,C] may be NULL. */
+int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int V, int D,
+                      const int* class_ids, int C, const int* exact_lut, float* labels,
+                      float* sim_pooled, c2d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAP2DET_B200_H_ */

@@ -1,0 +1,130 @@
+"""CPU: config text-format parsing, registry/builder dispatch, tokenisation, C-ABI exports."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from cap2det_b200 import config, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PIPELINE = """
+train_reader { cap2det_reader { input_pattern: "x*" batch_size: 2 image_resizer { keep_aspect_ratio_resizer { min_dimension: 1000 } } } }
+model {
+  [Cap2DetModel.ext] {
+    midn_loss_weight: 1.0
+    oicr_loss_weight: 0.5
+    frcnn_options {
+      feature_extractor { type: 'faster_rcnn_inception_v2' first_stage_features_stride: 16 }
+      initial_crop_size: 14 maxpool_kernel_size: 2 maxpool_stride: 2
+      dropout_keep_prob: 0.5 dropout_on_feature_map: false
+      checkpoint_path: 'zoo/inception_v2_2016_08_28/inception_v2.ckpt'
+    }
+    fc_hyperparams { op: FC activation: RELU_6
+      regularizer { l2_regularizer { weight: 0.000001 } }
+      initializer { truncated_normal_initializer { mean: 0.0 stddev: 0.01 } } }
+    oicr_iterations: 3
+    oicr_iou_threshold: 0.6
+    midn_post_processor { score_thresh: 0.00001 iou_thresh: 0.4 max_size_per_class: 100 max_total_size: 300 }
+    oicr_post_processor { score_thresh: 0.00001 iou_thresh: 0.3 }
+    eval_min_dimension: 1200
+    eval_min_dimension: 800  # comment
+    label_extractor { groundtruth_extractor { label_file: 'data/voc_label.txt' } }
+  }
+}
+train_config { max_steps: 100000 learning_rate: 0.01 optimizer { adagrad { } }
+  gradient_multiplier { scope: 'first_stage_feature_extraction' multiplier: 0.0 }
+  gradient_multiplier { scope: 'second_stage_feature_extraction' multiplier: 1.0 }
+  sync_replicas: false }
+eval_config { steps: 100 }
+"""
+
+
+def test_parse_pipeline_text_format():
+  p = config.parse_text(PIPELINE, config.Pipeline)
+  (ext, m), = p.model.ListFields()
+  assert ext == config.Cap2DetModel.ext and isinstance(m, config.Cap2DetModel)
+  assert m.oicr_iterations == 3 and abs(m.oicr_iou_threshold - 0.6) < 1e-9
+  assert m.frcnn_options.initial_crop_size == 14 and m.frcnn_options.dropout_on_feature_map is False
+  assert m.frcnn_options.feature_extractor.batch_norm_trainable is False          # protos/frcnn.proto:46 default
+  assert m.midn_post_processor.iou_thresh == 0.4 and m.oicr_post_processor.max_total_size == 300
+  assert m.eval_min_dimension == [1200, 800]
+  assert m.oicr_use_proba_r_given_c is True                                       # protos/cap2det_model.proto:42
+  assert m.label_extractor.WhichOneof('label_extractor_oneof') == 'groundtruth_extractor'
+  assert m.fc_hyperparams.initializer.truncated_normal_initializer.stddev == 0.01
+  assert [g.multiplier for g in p.train_config.gradient_multiplier] == [0.0, 1.0]
+  assert not p.train_config.HasField('max_gradient_norm')
+
+
+def test_defaults_and_oneof():
+  m = config.Cap2DetModel()
+  assert m.midn_loss_weight == 1.0 and m.oicr_iterations == 0 and m.oicr_iou_threshold == 0.5
+  assert config.PostProcess().score_thresh == 1e-6
+  le = config.LabelExtractor()
+  assert le.WhichOneof('label_extractor_oneof') is None
+  le.exact_match_extractor = config.ExactMatchExtractor(label_file='a')
+  le.extend_match_extractor = config.ExtendMatchExtractor(label_file='b')
+  assert le.WhichOneof('label_extractor_oneof') == 'extend_match_extractor'
+  with pytest.raises(AttributeError):
+    m.no_such_field = 1
+
+
+def test_text_format_errors():
+  with pytest.raises(ValueError):
+    config.parse_text('oicr_iterations: "three"', config.Cap2DetModel)
+  with pytest.raises(ValueError):
+    config.parse_text('frcnn_options { initial_crop_size: 14 ', config.Cap2DetModel)
+
+
+def test_synthetic_generators_are_seeded_and_shaped():
+  import numpy as np
+  a = synthetic.make_proposals(np.random.default_rng(5), 2, 50)
+  b = synthetic.make_proposals(np.random.default_rng(5), 2, 50)
+  np.testing.assert_array_equal(a, b)
+  assert a.shape == (2, 50, 4) and a.dtype == np.float32
+  assert np.all(a[..., 2] > a[..., 0]) and np.all(a[..., 3] > a[..., 1]) and a.min() >= 0 and a.max() <= 1
+  assert synthetic.feature_map_shape(600, 1000) == (38, 63)
+  assert len(synthetic.COCO_CLASSES) == 80 and len(synthetic.VOC_CLASSES) == 20
+
+
+def _declared_symbols():
+  with open(os.path.join(ROOT, 'include', 'cap2det_b200.h')) as fid:
+    text = fid.read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  return sorted(set(re.findall(r'\b(c2d_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_c_abi_library_builds_and_exports_every_declared_symbol():
+  from cap2det_b200 import build, capi
+  path = build.build_library()
+  lib = ctypes.CDLL(path)
+  declared = _declared_symbols()
+  assert len(declared) >= 30
+  for name in declared:
+    assert hasattr(lib, name), 'missing export %s' % name
+  assert sorted(capi.SIGNATURES.keys()) == declared        # the ctypes table mirrors the header 1:1
+  assert lib.c2d_version() >= 100
+  # pure host queries (no GPU needed)
+  lib.c2d_head_param_floats.restype = ctypes.c_longlong
+  n_params = lib.c2d_head_param_floats()
+  assert n_params == 5893120 + 4 * (128 + 192 + 192 + 256 + 256 + 352 + 192 + 320 + 160 + 224 + 224 + 128
+                                    + 352 + 192 + 320 + 192 + 224 + 224 + 128)
+  assert lib.c2d_head_num_convs() == 19
+
+
+def test_product_code_never_imports_oracle():
+  pkg = os.path.join(ROOT, 'cap2det_b200')
+  for dirpath, _, files in os.walk(pkg):
+    for f in files:
+      if f.endswith('.py'):
+        with open(os.path.join(dirpath, f)) as fid:
+          src = fid.read()
+        assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_no_cpu_fallback_on_cpu_tensors():
+  import torch
+  from cap2det_b200 import box_utils
+  with pytest.raises(RuntimeError):
+    box_utils.area(torch.zeros(3, 4))

@@ -1,0 +1,92 @@
+"""CPU: self-consistency of the unpinned parts of the oracle (ROI, head, MIDN, OICR, NMS)."""
+import numpy as np
+import torch
+
+from oracle import roi, head, midn_oicr, nms, box_ops
+
+
+def test_crop_and_resize_identity_and_extrapolation():
+  rng = np.random.default_rng(0)
+  fmap = rng.standard_normal((1, 5, 6, 4)).astype(np.float32)
+  # a box covering the full map sampled at its own resolution reproduces the map
+  out = roi.crop_and_resize(fmap, np.array([[0, 0, 1, 1]], np.float32), [0], (5, 6))
+  np.testing.assert_allclose(out[0], fmap[0], atol=1e-6)
+  # samples outside [0, H-1] are zero (extrapolation_value 0)
+  out = roi.crop_and_resize(fmap, np.array([[-0.5, 0, 1.5, 1]], np.float32), [0], (4, 3))
+  assert np.all(out[0, 0] == 0) and np.all(out[0, -1] == 0)
+
+
+def test_roi_backward_matches_finite_difference_structure():
+  # gradient of sum(out * g) w.r.t. fmap equals the bwd (the map is piecewise linear in fmap)
+  rng = np.random.default_rng(1)
+  fmap = rng.standard_normal((2, 6, 7, 8)).astype(np.float32)
+  props = np.array([[[0.1, 0.1, 0.8, 0.9], [0.0, 0.3, 0.5, 1.0]], [[0.2, 0.0, 1.0, 0.6], [0, 0, 0, 0]]], np.float32)
+  g = rng.standard_normal((4, 2, 2, 8)).astype(np.float32)
+  d = roi.roi_crop_maxpool_bwd(fmap, props, g, crop=4)
+  eps_dir = rng.standard_normal(fmap.shape).astype(np.float32)
+  h = 1e-3
+  f1 = (roi.roi_crop_maxpool_fwd(fmap + h * eps_dir, props, crop=4).astype(np.float64) * g).sum()
+  f0 = (roi.roi_crop_maxpool_fwd(fmap - h * eps_dir, props, crop=4).astype(np.float64) * g).sum()
+  np.testing.assert_allclose((f1 - f0) / (2 * h), (d.astype(np.float64) * eps_dir).sum(), rtol=2e-2, atol=2e-2)
+
+
+def test_head_shapes_and_macs():
+  p = head.random_head_params(0)
+  x = torch.randn(2, 7, 7, 576)
+  y = head.head_mixed5(x, p)
+  assert tuple(y.shape) == (2, 4, 4, 1024)
+  macs = sum((16 if (s == 2 or 'Mixed_5a' not in n) else 49) * k * k * ci * co for n, k, ci, co, s in head.HEAD_CONVS)
+  assert macs == 114970624
+  assert sum(k * k * ci * co for _, k, ci, co, _ in head.HEAD_CONVS) == 5893120
+
+
+def test_midn_matches_reference_formula():
+  rng = np.random.default_rng(2)
+  lr = rng.standard_normal((2, 9, 3)).astype(np.float32)
+  lc = rng.standard_normal((2, 9, 3)).astype(np.float32)
+  cl, sc, pr = midn_oicr.midn(lr, lc, np.array([9, 5]))
+  pr = pr.numpy()
+  np.testing.assert_allclose(pr.sum(axis=1), 1.0, rtol=1e-5)
+  assert np.all(pr[1, 5:] == 0)
+  np.testing.assert_allclose(cl.numpy(), (lc * pr).sum(axis=1), rtol=1e-5)
+  np.testing.assert_allclose(sc.numpy(), 1 / (1 + np.exp(-cl.numpy()))[:, None, :] * pr, rtol=1e-5)
+
+
+def test_oicr_assign_rows_sum_to_one_and_label_gate():
+  rng = np.random.default_rng(3)
+  B, P, C = 2, 40, 5
+  props = np.sort(rng.uniform(0, 1, (B, P, 2, 2)), axis=2).transpose(0, 1, 2, 3).reshape(B, P, 4).astype(np.float32)
+  props = np.stack([props[..., 0], props[..., 1], props[..., 2], props[..., 3]], -1)
+  s0 = rng.uniform(0, 1, (B, P, C + 1)).astype(np.float32)
+  labels = np.array([[1, 0, 1, 0, 0], [0, 0, 0, 0, 0]], np.float32)
+  ind, pl, ok = midn_oicr.oicr_assign(labels, [P, 30], props, s0, 0.5)
+  assert ok and ind.shape == (B, C) and ind.dtype == np.int64
+  np.testing.assert_allclose(pl.sum(-1), 1.0, atol=1e-6)
+  assert np.all(pl[1, :, 0] == 1.0)                 # no positive label => everything background
+  assert np.all(pl[0, :, [2, 4, 5]] == 0)           # gated classes never get a target
+  assert pl[0, ind[0, 0], 1] > 0                    # the seed has IoU 1 with itself
+  assert np.all(ind[1] < 30)                        # seeds come from valid proposals
+
+
+def test_nms_basic_and_padding_rows():
+  boxes = np.array([[[0, 0, 1, 1], [0, 0, 1, 0.9], [0, 0, 0.2, 0.2], [0, 0, 0, 0]]], np.float32)
+  scores = np.array([[[0.9, 0.0], [0.8, 0.7], [0.6, 0.000001], [0.99, 0.99]]], np.float32)
+  n, b, s, c, k = nms.multiclass_nms(boxes, scores, 1e-5, 0.5, 100, 6)
+  # class 0: box0 kept, box1 suppressed (IoU .9), box2 kept; class 1: box1 kept; zero-area row dropped
+  assert n[0] == 3
+  np.testing.assert_array_equal(k[0, :3], [0, 1, 2])
+  np.testing.assert_allclose(s[0, :3], [0.9, 0.7, 0.6])
+  np.testing.assert_array_equal(c[0], [1, 2, 1, 1, 1, 1])      # padding rows read 1.0 (core/builder.py:65)
+  assert np.all(b[0, 3:] == 0)
+
+
+def test_nms_tie_rule_lower_index_first():
+  boxes = np.array([[[0, 0, 1, 1], [0, 0, 1, 1], [0.5, 0.5, 1, 1]]], np.float32)
+  scores = np.array([[[0.5], [0.5], [0.5]]], np.float32)
+  n, _, _, _, k = nms.multiclass_nms(boxes, scores, 1e-5, 0.5, 100, 5)
+  assert n[0] == 2 and list(k[0, :2]) == [0, 2]
+
+
+def test_seq_sum_matches_numpy_on_exact_values():
+  x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
+  np.testing.assert_array_equal(box_ops.seq_sum(x, 1), x.sum(1, keepdims=True))
