@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- proposals/s of the Cap2Det proposal hot path (ROI + head + MIL + OICR fwd+bwd).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+  python bench.py --impl reference ...                      (CPU restatement of the TF path)
+
+One step = one training pass over one synthetic batch of BASELINE.json configs[1]
+(coco17_exact_match: 2 images/GPU, 5 captions each, 80 classes, 2000 proposals/image, 3 OICR
+stages): caption label extraction, crop_and_resize+maxpool over the proposals, Mixed_5a-c head,
+FC layers, MIDN, OICR pseudo-labelling + losses, full backward (head weights, FC weights, feature
+map), gradient all-reduce (N>1) and the Adagrad update.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIG = dict(workload='coco17_exact_match train step (BASELINE configs[1])', images_per_gpu=2, proposals=2000,
+              classes=80, oicr_iterations=3, feature_map=[38, 63, 576], crop=14, captions_per_image=5)
+
+
+def load_peaks():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(path):
+    with open(path) as fid:
+      p = json.load(fid)
+    return dict(hbm_gbs=p['hbm_gbs'], bf16_tflops=p['bf16_tflops'], bf16_tflops_sustained=p['bf16_tflops_sustained'],
+                source='measured')
+  return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source='fallback')
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def make_host_batch(seed, B, P, vocab, plant):
+  from cap2det_b200 import synthetic
+  rng = np.random.default_rng(seed)
+  return dict(fmap=synthetic.make_feature_map(rng, B), proposals=synthetic.make_proposals(rng, B, P),
+              num_proposals=np.full((B,), P, np.int32),
+              captions=synthetic.make_captions(rng, B, vocab, plant, captions_per_image=CONFIG['captions_per_image']))
+
+
+def build_model(workdir, head_dtype, seed=0):
+  import torch
+  from cap2det_b200 import builder, config, synthetic
+  classes = synthetic.COCO_CLASSES
+  text = synthetic.model_options_text(
+      extractor='exact_match_extractor',
+      extractor_fields="label_file: '%s'" % synthetic.write_label_file(workdir, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  dt = torch.bfloat16 if head_dtype == 'bf16' else torch.float32
+  return builder.build(m, is_training=True), classes
+
+
+class ClockSampler(object):
+  """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+       'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+       'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.rows, self.proc = [], None
+    try:
+      self.proc = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                    '-lms', '100', '-i', str(gpu_index)], stdout=subprocess.PIPE, text=True)
+      self.thread = threading.Thread(target=self._read, daemon=True)
+      self.thread.start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(',')])
+
+  def stop(self):
+    if self.proc is None:
+      return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=2)
+    except Exception:
+      self.proc.kill()
+    sm, mx, reasons = [], [], set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx.append(float(r[2]))
+      except Exception:
+        continue
+      for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(name)
+    return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_baseline(seed, n_images=1, n_props=48, steps=1):
+  """The CPU oracle (port of the TF path) on a bounded sample of the same workload; proposals/s."""
+  import torch
+  from cap2det_b200 import synthetic
+  from oracle import head as ohead, labels as olabels
+  from tests import oracle_model
+  classes = synthetic.COCO_CLASSES
+  C, K = CONFIG['classes'], CONFIG['oicr_iterations']
+  rng = np.random.default_rng(seed)
+  vocab = synthetic.make_open_vocab(classes, 7379)
+  plant = olabels.replace_class_names(classes)
+  hb = make_host_batch(seed, n_images, n_props, vocab, plant)
+  p = ohead.random_head_params(0)
+  tp = {k: {kk: torch.from_numpy(v).requires_grad_(kk in ('weights', 'gamma', 'beta')) for kk, v in q.items()}
+        for k, q in p.items()}
+  N = 2 * C + K * (C + 1)
+  w = (rng.standard_normal((N, 1024)) * 0.01).astype(np.float32)
+  b = np.zeros(N, np.float32)
+  keep = (rng.uniform(size=(n_images * n_props, 1024)) < 0.5).astype(np.float32)
+  best = None
+  for _ in range(steps + 1):        # first pass is the warm-up
+    for q in tp.values():
+      for t in q.values():
+        t.grad = None
+    t0 = time.perf_counter()
+    labels = olabels.exact_match_extract(classes, hb['captions'])
+    oracle_model.forward_backward(hb['fmap'], hb['proposals'], hb['num_proposals'], labels, tp, w, b, keep, 0.5, C, K,
+                                  0.6, 1.0, 0.5)
+    dt = time.perf_counter() - t0
+    best = dt if best is None else min(best, dt)
+  return dict(value=n_images * n_props / best, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
+              sample='%d image(s) x %d proposals of the same config, one fwd+bwd step, best of %d (oracle/: NumPy + '
+                     'torch-CPU restatement of the TF 1.x path; TensorFlow itself is not installable)'
+                     % (n_images, n_props, steps), seconds_per_step=best)
+
+
+def run_reference(args):
+  """--impl reference: the CPU restatement, timed on the host cores (rank 0 only)."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  import torch
+  torch.set_num_threads(os.cpu_count() or 1)
+  n_props = 96
+  times = []
+  base = None
+  for i in range(args.warmup + args.steps):
+    base = cpu_baseline(1000 + i, n_images=1, n_props=n_props, steps=1)
+    if i >= args.warmup:
+      times.append(base['seconds_per_step'])
+    if sum(times) > 150:
+      break
+  ms = 1e3 * float(np.mean(times))
+  value = n_props / (ms / 1e3)
+  out = dict(metric='proposals/sec (ROI+head+MIL+OICR fwd+bwd)', value=value, unit='proposals/s', impl='reference',
+             n_gpus=args.gpus, steps=len(times), warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+             scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+             config=dict(CONFIG, sample='1 image x %d proposals per step' % n_props),
+             images_per_sec=value / CONFIG['proposals'],
+             cpu_baseline=dict(value=value, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
+                               sample=base['sample']),
+             e2e=dict(value=value, unit='proposals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+  print(json.dumps(out))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--head-dtype', default=os.environ.get('C2D_HEAD_DTYPE', 'auto'), choices=['auto', 'bf16', 'f32'])
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-kernel-table', action='store_true')
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+  if args.impl == 'reference':
+    return run_reference(args)
+
+  import torch
+  import torch.distributed as dist
+  from cap2det_b200 import capi, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+  torch.cuda.set_device(local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+  dev = torch.device('cuda', local_rank)
+  capi.load()
+  head_dtype = args.head_dtype
+  if head_dtype == 'auto':
+    head_dtype = 'bf16' if capi.load().c2d_has_tensor_core_head() else 'f32'
+
+  workdir = tempfile.mkdtemp()
+  B, P = CONFIG['images_per_gpu'], CONFIG['proposals']
+  model, classes = build_model(workdir, head_dtype)
+  if head_dtype == 'bf16':
+    model._head_dtype = torch.bfloat16
+  if world > 1:   # identical replicas
+    for v in model.get_variables_to_train():
+      dist.broadcast(v.data, src=0)
+  step = trainer.TrainStep(model, learning_rate=0.01, world_size=world)
+  vocab = synthetic.make_open_vocab(classes, 7379)
+  plant = [synthetic._MULTIWORD.get(c, c) for c in classes]
+  # a small pool of distinct batches so consecutive steps do not see identical data
+  n_pool = 4
+  host = [make_host_batch(1000 * 1 + rank * 97 + i, B, P, vocab, plant) for i in range(n_pool)]
+  pinned = [dict(fmap=torch.from_numpy(h['fmap']).pin_memory(), proposals=torch.from_numpy(h['proposals']).pin_memory(),
+                 num_proposals=torch.from_numpy(h['num_proposals']).pin_memory(), captions=h['captions']) for h in host]
+  resident = [{F.features_to_crop: p['fmap'].to(dev).requires_grad_(True), F.proposals: p['proposals'].to(dev),
+               F.num_proposals: p['num_proposals'].to(dev), F.concat_caption_string: p['captions']} for p in pinned]
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+  def sync_all():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  def run_resident(i):
+    ex = resident[i % n_pool]
+    ex[F.features_to_crop].grad = None
+    return step(ex)
+
+  def run_e2e(i):
+    p = pinned[i % n_pool]
+    ex = {F.features_to_crop: p['fmap'].to(dev, non_blocking=True).requires_grad_(True),
+          F.proposals: p['proposals'].to(dev, non_blocking=True),
+          F.num_proposals: p['num_proposals'].to(dev, non_blocking=True), F.concat_caption_string: p['captions']}
+    total = step(ex)
+    return float(total.cpu())          # device -> host read of the step's loss
+
+  def timed(fn, n_warm, n_steps, count_launches=False):
+    for i in range(n_warm):
+      fn(i)
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+    launches0 = capi.launch_count()
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+      flush.fill_(i & 255)             # flush L2 between timed iterations (outside the event pair)
+      ev[i][0].record()
+      fn(n_warm + i)
+      ev[i][1].record()
+    sync_all()
+    wall = time.perf_counter() - t0
+    launches = capi.launch_count() - launches0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), launches, wall
+
+  sampler = ClockSampler(local_rank) if rank == 0 else None
+  total_ms, launches, wall = timed(run_resident, args.warmup, args.steps)
+  clocks = sampler.stop() if sampler else None
+  e2e_ms, _, _ = timed(run_e2e, 2, args.steps)
+  model.raise_if_assert_failed()
+
+  props_per_step = world * B * P
+  value = props_per_step / (total_ms / args.steps / 1e3)
+  e2e_value = props_per_step / (e2e_ms / args.steps / 1e3)
+  h2d = sum(pinned[0][k].numel() * pinned[0][k].element_size() for k in ('fmap', 'proposals', 'num_proposals'))
+  T = len(pinned[0]['captions'][0])
+  h2d += B * T * 4                     # tokenised caption ids (int32)
+  out = dict(metric='proposals/sec (ROI+head+MIL+OICR fwd+bwd)', value=value, unit='proposals/s', n_gpus=world,
+             steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
+             scaling='weak', vs_baseline=None, dtype=head_dtype, data='synthetic',
+             config=dict(CONFIG, global_batch_images=world * B, parallelism='dp%d (by image)' % world,
+                         l2_handling='256 MB L2 flush between timed iterations', head_dtype=head_dtype),
+             images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
+             e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
+                      ms_per_step=e2e_ms / args.steps))
+  if rank == 0:
+    peaks = load_peaks()
+    if not args.no_kernel_table:
+      from cap2det_b200 import profiling
+      table = profiling.kernel_table(model, resident[0], peaks, head_dtype)
+      out['kernels'] = table['kernels']
+      out['roofline'] = table['dominant']
+      out['hbm_group'] = table['hbm_group']
+    if not args.no_cpu_baseline and world == 1:
+      out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=96, steps=2)
+    print(json.dumps(out))
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

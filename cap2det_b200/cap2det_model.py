@@ -180,9 +180,17 @@ class Model(ModelBase):
       results[DetectionResultFields.detection_classes + '_at_{}'.format(i)] = classes
     return results
 
-  def build_prediction(self, examples, **kwargs):
-    """models/cap2det_model.py:218-272."""
+  def build_prediction(self, examples, postprocess=None, **kwargs):
+    """models/cap2det_model.py:218-272.
+
+    `postprocess`: the reference builds the NMS sub-graph in every mode (:231-234) but a TF session
+    only executes what is fetched, and the training op never fetches detections.  With eager
+    execution the equivalent is: run NMS by default in eval/predict mode, skip it in training mode
+    unless postprocess=True.
+    """
     options = self._model_proto
+    if postprocess is None:
+      postprocess = not self._is_training
     fmaps = examples.get(InputDataFields.features_to_crop)
     if fmaps is None:
       raise NotImplementedError(
@@ -192,7 +200,8 @@ class Model(ModelBase):
       if isinstance(fmaps, (list, tuple)):
         raise ValueError('a single feature map is expected outside multi-scale evaluation')
       predictions = self._build_prediction(examples, fmaps)
-      predictions.update(self._postprocess(predictions))
+      if postprocess:
+        predictions.update(self._postprocess(predictions))
       return predictions
     # Multi-scale evaluation (:231-272): one feature map per entry of eval_min_dimension.
     if not isinstance(fmaps, (list, tuple)):

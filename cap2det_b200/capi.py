@@ -20,6 +20,7 @@ _c_int, _c_float, _c_ll, _c_sz, _p = (ctypes.c_int, ctypes.c_float, ctypes.c_lon
 SIGNATURES = {
     'c2d_version': (_c_int, []),
     'c2d_last_error': (ctypes.c_char_p, []),
+    'c2d_has_tensor_core_head': (_c_int, []),
     'c2d_launch_count': (_c_ll, []),
     'c2d_reset_launch_count': (None, []),
     'c2d_box_area': (_c_int, [_p, _c_int, _p, _p]),
@@ -55,6 +56,8 @@ SIGNATURES = {
     'c2d_multiclass_nms': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_int,
                                     _p, _p, _p, _p, _p, _p, _c_sz, _p]),
     'c2d_label_lut': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _p]),
+    'c2d_adagrad_update': (_c_int, [_p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _p]),
+    'c2d_l2_loss': (_c_int, [_p, _c_ll, _c_float, _p, _p]),
     'c2d_wordvec_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _c_int, _p, _p, _p, _p]),
 }
 

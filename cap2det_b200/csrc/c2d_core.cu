@@ -124,6 +124,34 @@ __global__ void masked_softmax_kernel(const float* __restrict__ data, const floa
         __fdiv_rn(expf(__fsub_rn(__fsub_rn(col[(size_t)j * d], __fmul_rn(1e10f, __fsub_rn(1.0f, mk[j]))), mx)), s);
 }
 
+__global__ void adagrad_kernel(float* __restrict__ var, float* __restrict__ accum, const float* __restrict__ grad,
+                               long long n, float lr, float grad_scale, float l2_scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    float v = var[i];
+    float g = grad[i] * grad_scale + l2_scale * v;
+    float a = accum[i] + g * g;
+    accum[i] = a;
+    var[i] = v - lr * g * rsqrtf(a);
+  }
+}
+
+__global__ void l2_loss_kernel(const float* __restrict__ w, long long n, float scale, float* __restrict__ out) {
+  __shared__ float sm[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += w[i] * w[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    atomicAdd(out, t * 0.5f * scale);
+  }
+}
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -181,6 +209,31 @@ int c2d_masked_softmax(const float* data, const float* mask, int n, int m, int d
   if (n == 0) return C2D_OK;
   long long threads = (long long)n * d * 32;
   masked_softmax_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(data, mask, n, m, d, out);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_adagrad_update(float* var, float* accum, const float* grad, long long n, float lr, float grad_scale,
+                       float l2_scale, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0, "adagrad: n must be >= 0");
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  adagrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(var, accum, grad, n, lr, grad_scale, l2_scale);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_l2_loss(const float* w, long long n, float scale, float* out, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0, "l2_loss: n must be >= 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  C2D_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148) blocks = 148;
+  l2_loss_kernel<<<blocks, 256, 0, st>>>(w, n, scale, out);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

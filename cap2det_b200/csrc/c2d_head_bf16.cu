@@ -5,6 +5,7 @@
 using namespace c2d;
 
 extern "C" {
+int c2d_has_tensor_core_head(void) { return 0; }
 int c2d_head_mixed5_fwd_bf16(const void*, int, const float*, const HeadPlan&, char*, const float*, float, float*,
                              cudaStream_t) {
   set_error("head: bf16 tcgen05 path not built yet");

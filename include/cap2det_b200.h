@@ -47,6 +47,8 @@ enum {
 int c2d_version(void);
 const char* c2d_last_error(void);
 /* Kernels launched by this library since the last reset (all threads). */
+/* 1 when the bf16 tcgen05/TMEM/TMA head path is compiled into this library. */
+int c2d_has_tensor_core_head(void);
 long long c2d_launch_count(void);
 void c2d_reset_launch_count(void);
 
@@ -166,6 +168,15 @@ int c2d_label_lut(const int* token_ids, int B, int T, const int* lut, int V, int
 int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int V, int D,
                       const int* class_ids, int C, const int* exact_lut, float* labels,
                       float* sim_pooled, c2d_stream_t stream);
+
+/* ---- trainer numerics around the path, train/trainer.py:85-146 -----
+ * One fused update: g = grad * grad_scale + l2_scale * var   (gradient multiplier / 1/G data-parallel
+ * averaging; slim l2_regularizer = scale * sum(w^2)/2 => d/dw = scale * w, core/training_utils.py:45-50)
+ * accum += g*g ; var -= lr * g * rsqrt(accum)                (tf.train.AdagradOptimizer, accum0 = 0.1) */
+int c2d_adagrad_update(float* var, float* accum, const float* grad, long long n, float lr, float grad_scale,
+                       float l2_scale, c2d_stream_t stream);
+/* slim l2_regularizer loss term: out (device scalar) = scale * sum(w^2) / 2 */
+int c2d_l2_loss(const float* w, long long n, float scale, float* out, c2d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,552 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on seeded inputs.
+
+Bit-exact: box arithmetic, IoU-threshold masks, OICR seeds / pseudo labels, extracted labels, NMS
+keep lists, ROI crop+pool forward.  Tolerance (written per test): scores, losses, gradients.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import box_ops, roi as oroi, head as ohead, midn_oicr, nms as onms, labels as olabels  # noqa: E402
+from tests import oracle_model  # noqa: E402
+
+RTOL_F32 = 1e-5      # north_star: 1e-5 relative (fp32) for scores, losses and gradients
+
+
+def dev(x, dtype=None):
+  t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+  return t if dtype is None else t.to(dtype)
+
+
+def rel_err(a, b):
+  a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+  return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _lib():
+  from cap2det_b200 import capi
+  assert torch.cuda.is_available(), 'the gpu-marked tests need a CUDA device'
+  capi.load()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_box_utils_golden_and_random_bit_exact(golden):
+  from cap2det_b200 import box_utils
+  g = golden
+  np.testing.assert_allclose(box_utils.area(dev(np.float32(g['area']['box']))).cpu(), g['area']['expected'])
+  np.testing.assert_allclose(box_utils.iou(dev(np.float32(g['iou']['box1'])), dev(np.float32(g['iou']['box2']))).cpu(),
+                             g['iou']['expected'], rtol=1e-6)
+  np.testing.assert_allclose(box_utils.intersect(dev(np.float32(g['intersect']['box1'])),
+                                                 dev(np.float32(g['intersect']['box2']))).cpu(), g['intersect']['expected'])
+  np.testing.assert_allclose(box_utils.flip_left_right(dev(np.float32(g['flip_left_right']['box']))).cpu(),
+                             g['flip_left_right']['expected'])
+  s = g['scale_to_new_size']
+  np.testing.assert_allclose(box_utils.scale_to_new_size(dev(np.float32(s['box'])), s['img_shape'], s['pad_shape']).cpu(),
+                             s['expected'])
+  rng = np.random.default_rng(0)
+  b1 = rng.uniform(-0.2, 1.2, (5000, 4)).astype(np.float32)
+  b2 = rng.uniform(-0.2, 1.2, (5000, 4)).astype(np.float32)
+  b2[:100] = b1[:100]
+  for fn, ofn in ((box_utils.area, box_ops.area),):
+    np.testing.assert_array_equal(fn(dev(b1)).cpu().numpy(), ofn(b1))
+  got = box_utils.iou(dev(b1), dev(b2)).cpu().numpy()
+  want = box_ops.iou(b1, b2)
+  np.testing.assert_array_equal(got.view(np.uint32)[~np.isnan(want)], want.view(np.uint32)[~np.isnan(want)])
+  assert np.array_equal(np.isnan(got), np.isnan(want))
+  np.testing.assert_array_equal(box_utils.intersect(dev(b1), dev(b2)).cpu().numpy(), box_ops.intersect(b1, b2))
+  np.testing.assert_array_equal(box_utils.flip_left_right(dev(b1)).cpu().numpy(), box_ops.flip_left_right(b1))
+  np.testing.assert_array_equal(box_utils.scale_to_new_size(dev(b1), (600, 1000), (640, 1024)).cpu().numpy(),
+                                box_ops.scale_to_new_size(b1, (600, 1000), (640, 1024)))
+
+
+def test_masked_ops_golden_and_random(golden):
+  from cap2det_b200 import utils
+  for name in ['masked_maximum', 'masked_minimum', 'masked_sum', 'masked_avg', 'masked_sum_nd', 'masked_avg_nd']:
+    for case in golden[name]:
+      got = getattr(utils, name)(dev(np.float32(case['data'])), dev(np.float32(case['mask']))).cpu().numpy()
+      np.testing.assert_allclose(got, case['expected'], rtol=1e-6, err_msg=name)
+  for case in golden['masked_softmax']:
+    got = utils.masked_softmax(dev(np.float32(case['data'])), dev(np.float32(case['mask']))).cpu().numpy()
+    np.testing.assert_allclose(got, case['expected'], atol=1e-7)
+  rng = np.random.default_rng(1)
+  data = rng.standard_normal((3, 257, 7)).astype(np.float32)
+  data[0, 5] = data[0, 3]                                    # manufactured tie: first index must win
+  mask = (rng.uniform(size=(3, 257)) < 0.7).astype(np.float32)
+  mask[2] = 0
+  np.testing.assert_array_equal(utils.masked_argmax(dev(data), dev(mask)).cpu().numpy(),
+                                box_ops.masked_argmax(data, mask[:, :, None]))
+  np.testing.assert_array_equal(utils.masked_argmin(dev(data), dev(mask)).cpu().numpy(),
+                                box_ops.masked_argmin(data, mask[:, :, None]))
+  np.testing.assert_array_equal(utils.masked_maximum(dev(data), dev(mask)).cpu().numpy(),
+                                box_ops.masked_maximum(data, mask[:, :, None]))
+  np.testing.assert_allclose(utils.masked_avg_nd(dev(data), dev(mask)).cpu().numpy(),
+                             box_ops.masked_avg_nd(data, mask), rtol=RTOL_F32, atol=1e-6)
+  np.testing.assert_allclose(utils.masked_softmax(dev(data), dev(mask)).cpu().numpy()[:2],
+                             box_ops.masked_softmax(data, mask[:, :, None], dim=1)[:2], rtol=RTOL_F32, atol=1e-9)
+
+
+# ---------------------------------------------------------------------------------------------
+def _roi_inputs(seed, B=2, P=37, Hf=9, Wf=13, C=24):
+  from cap2det_b200 import synthetic
+  rng = np.random.default_rng(seed)
+  fmap = np.maximum(rng.standard_normal((B, Hf, Wf, C)).astype(np.float32), 0)
+  props = synthetic.make_proposals(rng, B, P, image_h=Hf * 16, image_w=Wf * 16)
+  # edge cases: padded zero box, full image, box past the border (extrapolation), tiny box, inverted box
+  props[0, 0] = [0, 0, 0, 0]
+  props[0, 1] = [0, 0, 1, 1]
+  props[0, 2] = [-0.2, -0.1, 0.6, 1.3]
+  props[1, 0] = [0.5, 0.5, 0.5001, 0.5001]
+  props[1, 1] = [0.8, 0.7, 0.3, 0.2]
+  return fmap, props
+
+
+def test_roi_crop_maxpool_forward_bit_exact():
+  from cap2det_b200 import ops
+  fmap, props = _roi_inputs(2)
+  want = oroi.roi_crop_maxpool_fwd(fmap, props)
+  got = ops.roi_crop_maxpool(dev(fmap), dev(props)).cpu().numpy()
+  np.testing.assert_array_equal(got, want)
+  got16 = ops.roi_crop_maxpool(dev(fmap), dev(props), out_dtype=torch.bfloat16).float().cpu().numpy()
+  np.testing.assert_array_equal(got16, torch.from_numpy(want).to(torch.bfloat16).float().numpy())
+
+
+def test_roi_crop_maxpool_backward():
+  from cap2det_b200 import ops
+  fmap, props = _roi_inputs(3)
+  rng = np.random.default_rng(4)
+  g = rng.standard_normal((props.shape[0] * props.shape[1], 7, 7, fmap.shape[-1])).astype(np.float32)
+  f = dev(fmap).requires_grad_(True)
+  out = ops.roi_crop_maxpool(f, dev(props))
+  out.backward(dev(g))
+  want = oroi.roi_crop_maxpool_bwd(fmap, props, g)
+  assert rel_err(f.grad.cpu().numpy(), want) < RTOL_F32
+
+
+def test_roi_rejects_unsupported_options():
+  from cap2det_b200 import ops, capi
+  fmap, props = _roi_inputs(5)
+  with pytest.raises(capi.C2DError):
+    ops.roi_crop_maxpool(dev(fmap), dev(props), crop_size=14, pool_k=3, pool_s=2)
+
+
+# ---------------------------------------------------------------------------------------------
+def _head_setup(n=5, seed=6):
+  from cap2det_b200 import ops
+  p = ohead.random_head_params(seed)
+  flat = np.zeros((ops.head_param_floats(),), np.float32)
+  for name, k, cin, cout, _, off in ops.head_conv_specs():
+    q = p[name]
+    flat[off['weights']:off['weights'] + q['weights'].size] = q['weights'].reshape(-1)
+    flat[off['gamma']:off['gamma'] + cout] = q['gamma']
+    flat[off['beta']:off['beta'] + cout] = q['beta']
+    flat[off['moving_mean']:off['moving_mean'] + cout] = q['mean']
+    flat[off['moving_variance']:off['moving_variance'] + cout] = q['var']
+  rng = np.random.default_rng(seed + 1)
+  x0 = np.maximum(rng.standard_normal((n, 7, 7, 576)).astype(np.float32), 0)
+  return p, flat, x0
+
+
+def test_head_mixed5_forward_backward_fp32():
+  from cap2det_b200 import ops
+  p, flat, x0 = _head_setup()
+  n = x0.shape[0]
+  rng = np.random.default_rng(8)
+  keep = (rng.uniform(size=(n, 1024)) < 0.5).astype(np.float32)
+  dfeat = rng.standard_normal((n, 1024)).astype(np.float32)
+  # oracle
+  tp = {k: {kk: torch.from_numpy(v).requires_grad_(kk in ('weights', 'gamma', 'beta')) for kk, v in q.items()}
+        for k, q in p.items()}
+  xt = torch.from_numpy(x0).requires_grad_(True)
+  feat_o = ohead.avgpool_dropout(ohead.head_mixed5(xt, tp), 0.5, keep)
+  feat_o.backward(torch.from_numpy(dfeat))
+  # cuda
+  xd = dev(x0).requires_grad_(True)
+  pd = dev(flat).requires_grad_(True)
+  feat = ops.head_mixed5(xd, pd, dev(keep), 0.5)
+  assert rel_err(feat.detach().cpu().numpy(), feat_o.detach().numpy()) < RTOL_F32
+  feat.backward(dev(dfeat))
+  assert rel_err(xd.grad.cpu().numpy(), xt.grad.numpy()) < 5e-5
+  dflat = pd.grad.cpu().numpy()
+  for name, k, cin, cout, _, off in ops.head_conv_specs():
+    w = dflat[off['weights']:off['weights'] + cout * k * k * cin].reshape(cout, k, k, cin)
+    assert rel_err(w, tp[name]['weights'].grad.numpy()) < 5e-5, name
+    assert rel_err(dflat[off['gamma']:off['gamma'] + cout], tp[name]['gamma'].grad.numpy()) < 5e-5, name
+    assert rel_err(dflat[off['beta']:off['beta'] + cout], tp[name]['beta'].grad.numpy()) < 5e-5, name
+    assert np.all(dflat[off['moving_mean']:off['moving_mean'] + cout] == 0)
+  # eval mode: no mask => identity dropout
+  feat_eval = ops.head_mixed5(dev(x0), dev(flat), None, 1.0)
+  want = ohead.avgpool_dropout(ohead.head_mixed5(torch.from_numpy(x0), p), 1.0, None)
+  assert rel_err(feat_eval.cpu().numpy(), want.detach().numpy()) < RTOL_F32
+
+
+def test_fc_concat_forward_backward():
+  from cap2det_b200 import ops
+  rng = np.random.default_rng(9)
+  M, D, N = 150, 1024, 103
+  x = rng.standard_normal((M, D)).astype(np.float32)
+  w = (rng.standard_normal((N, D)) * 0.05).astype(np.float32)
+  b = rng.standard_normal(N).astype(np.float32)
+  dy = rng.standard_normal((M, N)).astype(np.float32)
+  xd, wd, bd = dev(x).requires_grad_(True), dev(w).requires_grad_(True), dev(b).requires_grad_(True)
+  y = ops.fc_concat(xd, wd, bd)
+  assert y.shape == (M, 112) and torch.all(y[:, N:] == 0)
+  want = x.astype(np.float64) @ w.T.astype(np.float64) + b
+  assert rel_err(y[:, :N].detach().cpu().numpy(), want) < RTOL_F32
+  dyp = torch.zeros_like(y); dyp[:, :N] = dev(dy)
+  y.backward(dyp)
+  assert rel_err(xd.grad.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64)) < RTOL_F32
+  assert rel_err(wd.grad.cpu().numpy(), dy.T.astype(np.float64) @ x.astype(np.float64)) < RTOL_F32
+  assert rel_err(bd.grad.cpu().numpy(), dy.astype(np.float64).sum(0)) < RTOL_F32
+
+
+# ---------------------------------------------------------------------------------------------
+def test_midn_forward_backward():
+  from cap2det_b200 import ops
+  rng = np.random.default_rng(10)
+  B, P, C = 2, 301, 20
+  ld = 112
+  logits = rng.standard_normal((B, P, ld)).astype(np.float32)
+  npr = np.array([P, 170], np.int32)
+  lo = torch.from_numpy(logits).requires_grad_(True)
+  cl_o, sc_o, pr_o = midn_oicr.midn(lo[:, :, 0:C], lo[:, :, C:2 * C], npr)
+  g_cl = rng.standard_normal((B, C)).astype(np.float32)
+  g_sc = rng.standard_normal((B, P, C)).astype(np.float32)
+  g_pr = rng.standard_normal((B, P, C)).astype(np.float32)
+  ((cl_o * torch.from_numpy(g_cl)).sum() + (sc_o * torch.from_numpy(g_sc)).sum()
+   + (pr_o * torch.from_numpy(g_pr)).sum()).backward()
+  ld_ = dev(logits).requires_grad_(True)
+  cl, sc, pr = ops.midn(ld_, 0, C, C, dev(npr))
+  assert rel_err(cl.detach().cpu().numpy(), cl_o.detach().numpy()) < RTOL_F32
+  assert rel_err(pr.detach().cpu().numpy(), pr_o.detach().numpy()) < RTOL_F32
+  assert rel_err(sc.detach().cpu().numpy(), sc_o.detach().numpy()) < RTOL_F32
+  assert torch.all(pr[1, 170:] == 0)
+  ((cl * dev(g_cl)).sum() + (sc * dev(g_sc)).sum() + (pr * dev(g_pr)).sum()).backward()
+  assert rel_err(ld_.grad.cpu().numpy(), lo.grad.numpy()) < 2e-5
+  # only the class-logit gradient (what build_loss uses)
+  ld2 = dev(logits).requires_grad_(True)
+  cl2, _, _ = ops.midn(ld2, 0, C, C, dev(npr))
+  (cl2 * dev(g_cl)).sum().backward()
+  lo2 = torch.from_numpy(logits).requires_grad_(True)
+  cl_o2, _, _ = midn_oicr.midn(lo2[:, :, 0:C], lo2[:, :, C:2 * C], npr)
+  (cl_o2 * torch.from_numpy(g_cl)).sum().backward()
+  assert rel_err(ld2.grad.cpu().numpy(), lo2.grad.numpy()) < 2e-5
+
+
+def _oicr_inputs(seed, B=2, P=400, C=20):
+  from cap2det_b200 import synthetic
+  rng = np.random.default_rng(seed)
+  props = synthetic.make_proposals(rng, B, P)
+  npr = np.array([P, P - 57], np.int32)[:B]
+  props[1, P - 57:] = 0                      # padded proposals (reader pads with zeros)
+  s0 = rng.uniform(0, 1, (B, P, C + 1)).astype(np.float32)
+  s0[0, 7, 3] = s0[0, 2, 3] = s0[0, :, 3].max() + 0.25      # exact tie for class 2 -> index 2 wins
+  labels = np.zeros((B, C), np.float32)
+  labels[0, [2, 5, 11]] = 1
+  labels[1, [0, 19]] = 1
+  return props, npr, s0, labels
+
+
+def test_oicr_assign_bit_exact():
+  from cap2det_b200 import ops
+  props, npr, s0, labels = _oicr_inputs(11)
+  ind_o, pl_o, ok = midn_oicr.oicr_assign(labels, npr, props, s0, 0.6)
+  assert ok
+  ind, pl, status = ops.oicr_assign(dev(labels), dev(npr), dev(props), dev(s0)[:, :, 1:], 0.6)
+  np.testing.assert_array_equal(ind.cpu().numpy(), ind_o)
+  np.testing.assert_array_equal(pl.cpu().numpy().view(np.uint32), pl_o.view(np.uint32))
+  assert int(status.item()) == 0
+  assert ind_o[0, 2] == 2                   # the manufactured tie resolved to the lowest index
+  # IoU >= threshold mask itself, against the op-by-op numpy IoU
+  seed = props[0, ind_o[0, 5]]
+  mask_o = box_ops.iou(props[0], np.broadcast_to(seed, props[0].shape)) >= np.float32(0.6)
+  np.testing.assert_array_equal(pl.cpu().numpy()[0, :, 6] > 0, mask_o)
+
+
+def test_oicr_cross_entropy_forward_backward():
+  from cap2det_b200 import ops
+  props, npr, s0, labels = _oicr_inputs(12)
+  B, P, C1 = s0.shape
+  _, pl, _ = midn_oicr.oicr_assign(labels, npr, props, s0, 0.6)
+  rng = np.random.default_rng(13)
+  ld, col = 112, 40
+  logits = rng.standard_normal((B, P, ld)).astype(np.float32) * 3
+  lo = torch.from_numpy(logits).requires_grad_(True)
+  want = midn_oicr.oicr_cross_entropy(pl, lo[:, :, col:col + C1], npr) * 0.5
+  want.backward()
+  ldv = dev(logits).requires_grad_(True)
+  got = ops.oicr_cross_entropy(ldv, col, dev(pl), dev(npr), 0.5)
+  assert abs(float(got) - float(want)) <= RTOL_F32 * abs(float(want))
+  got.backward()
+  assert rel_err(ldv.grad.cpu().numpy(), lo.grad.numpy()) < 2e-5
+  sm = ops.softmax_rows(dev(logits)[:, :, col:col + C1]).cpu().numpy()
+  np.testing.assert_allclose(sm, box_ops.softmax(logits[:, :, col:col + C1]), rtol=RTOL_F32, atol=1e-9)
+
+
+def test_sigmoid_ce_mean():
+  from cap2det_b200 import ops
+  rng = np.random.default_rng(14)
+  x = (rng.standard_normal((2, 80)) * 4).astype(np.float32)
+  z = (rng.uniform(size=(2, 80)) < 0.1).astype(np.float32)
+  xo = torch.from_numpy(x).requires_grad_(True)
+  want = midn_oicr.sigmoid_cross_entropy(z, xo).mean() * 1.0
+  want.backward()
+  xd = dev(x).requires_grad_(True)
+  got = ops.sigmoid_ce_mean(dev(z), xd, 1.0)
+  assert abs(float(got) - float(want)) <= RTOL_F32 * abs(float(want))
+  got.backward()
+  assert rel_err(xd.grad.cpu().numpy(), xo.grad.numpy()) < RTOL_F32
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('P,C,seed', [(300, 5, 15), (2000, 20, 16), (64, 3, 17)])
+def test_multiclass_nms_keep_lists_bit_exact(P, C, seed):
+  from cap2det_b200 import ops, synthetic
+  rng = np.random.default_rng(seed)
+  B = 2
+  props = synthetic.make_proposals(rng, B, P)
+  props[1, P - 9:] = 0                                  # padded rows are candidates too (zero area => dropped)
+  scores = rng.uniform(0, 1, (B, P, C)).astype(np.float32) ** 3
+  scores[0, :, 0] = 0                                   # a class with no candidate
+  scores[0, 5, 1] = scores[0, 3, 1] = 0.999             # tie: lower index first
+  n_o, b_o, s_o, c_o, k_o = onms.multiclass_nms(props, scores, 1e-5, 0.4, 100, 300)
+  n, b, s, c, k = ops.multiclass_nms(dev(props), dev(scores), 1e-5, 0.4, 100, 300)
+  np.testing.assert_array_equal(n.cpu().numpy(), n_o)
+  np.testing.assert_array_equal(k.cpu().numpy(), k_o)
+  np.testing.assert_array_equal(c.cpu().numpy(), c_o)
+  np.testing.assert_array_equal(s.cpu().numpy(), s_o)
+  np.testing.assert_array_equal(b.cpu().numpy(), b_o)
+
+
+def test_nms_on_strided_scores_and_small_limits():
+  from cap2det_b200 import ops, synthetic
+  rng = np.random.default_rng(18)
+  B, P, C = 1, 500, 4
+  props = synthetic.make_proposals(rng, B, P)
+  wide = rng.uniform(0, 1, (B, P, C + 1)).astype(np.float32)
+  n_o, b_o, s_o, c_o, k_o = onms.multiclass_nms(props, wide[:, :, 1:], 0.3, 0.3, 7, 10)
+  n, b, s, c, k = ops.multiclass_nms(dev(props), dev(wide)[:, :, 1:], 0.3, 0.3, 7, 10)
+  np.testing.assert_array_equal(n.cpu().numpy(), n_o)
+  np.testing.assert_array_equal(k.cpu().numpy(), k_o)
+  np.testing.assert_array_equal(s.cpu().numpy(), s_o)
+
+
+# ---------------------------------------------------------------------------------------------
+def _write(lines):
+  f = tempfile.NamedTemporaryFile('w', suffix='.txt', delete=False)
+  f.write('\n'.join(lines)); f.close()
+  return f.name
+
+
+def test_label_extractors_reference_vectors(golden):
+  from cap2det_b200 import config, label_extractor
+  from cap2det_b200.standard_fields import InputDataFields
+  for key, field, cls in (('groundtruth_extractor', InputDataFields.object_texts, label_extractor.GroundtruthExtractor),
+                          ('exact_match_extractor', InputDataFields.concat_caption_string, label_extractor.ExactMatchExtractor),
+                          ('extend_match_extractor', InputDataFields.concat_caption_string, label_extractor.ExtendMatchExtractor)):
+    g = golden[key]
+    opts = config.parse_text("%s { label_file: '%s' }" % (key, _write(g['label_file'])), config.LabelExtractor)
+    ex = label_extractor.build_label_extractor(opts)
+    assert isinstance(ex, cls)
+    assert ex.num_classes == len(g.get('classes', g['label_file']))
+    assert ex.classes == g.get('classes', g['label_file'])
+    np.testing.assert_array_equal(ex.extract_labels({field: g['texts']}).cpu().numpy(), g['expected'])
+    np.testing.assert_array_equal(ex.extract_labels({field: g['empty_texts']}).cpu().numpy(), g['empty_expected'])
+  with pytest.raises(ValueError):
+    label_extractor.build_label_extractor(config.LabelExtractor())
+
+
+def test_word_vector_match_extractor(golden):
+  from cap2det_b200 import config, label_extractor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields
+  from tests.test_oracle_golden import wordvec_fixture
+  g = golden['word_vector_match_extractor']
+  vocab, emb = wordvec_fixture()
+  d = tempfile.mkdtemp()
+  np.save(os.path.join(d, 'emb.npy'), emb[:-1])
+  opts = config.parse_text(
+      "word_vector_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+      "open_vocabulary_word_embedding_file: '%s' }" % (_write(g['label_file']), _write(vocab), os.path.join(d, 'emb.npy')),
+      config.LabelExtractor)
+  ex = label_extractor.build_label_extractor(opts)
+  f = InputDataFields.concat_caption_string
+  np.testing.assert_array_equal(ex.extract_labels({f: g['texts']}).cpu().numpy(), g['expected'])
+  np.testing.assert_array_equal(ex.extract_labels({f: g['empty_texts']}).cpu().numpy(), g['empty_expected'])
+  # synthetic COCO-sized case against the oracle (labels bit-exact, similarities 1e-5)
+  rng = np.random.default_rng(19)
+  classes = synthetic.COCO_CLASSES
+  vpath, epath, vocab, emb = synthetic.write_open_vocab(d, classes, rng, size=2000, dims=300)
+  opts = config.parse_text(
+      "word_vector_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+      "open_vocabulary_word_embedding_file: '%s' }" % (synthetic.write_label_file(d, classes), vpath, epath),
+      config.LabelExtractor)
+  ex = label_extractor.build_label_extractor(opts)
+  plant = olabels.replace_class_names(classes)
+  caps = synthetic.make_captions(rng, 6, vocab, plant, no_plant_images=(1, 3, 4))
+  caps[4] = ['zzz_oov'] * len(caps[4])                    # nothing in vocabulary -> all zero
+  labels, sim = ex.extract_labels({f: caps}, return_similarity=True)
+  emb_oov = ex._embedding_weights.cpu().numpy()
+  want, want_sim = olabels.word_vector_match_extract(classes, vocab, emb_oov, caps)
+  np.testing.assert_array_equal(labels.cpu().numpy(), want)
+  np.testing.assert_allclose(sim.cpu().numpy()[[0, 1, 2, 3, 5]], want_sim[[0, 1, 2, 3, 5]], rtol=1e-4, atol=2e-6)
+  assert want[4].sum() == 0 and want[1].sum() == 1 and want[0].sum() >= 1
+
+
+def test_extend_match_synthetic_table_against_oracle():
+  from cap2det_b200 import config, label_extractor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields
+  d = tempfile.mkdtemp()
+  rng = np.random.default_rng(20)
+  classes = synthetic.COCO_CLASSES
+  path = synthetic.write_synonym_file(d, classes)
+  ex = label_extractor.build_label_extractor(
+      config.parse_text("extend_match_extractor { label_file: '%s' }" % path, config.LabelExtractor))
+  ocls, name2id = olabels.parse_synonym_file(synthetic.make_synonym_table(classes))
+  vocab = synthetic.make_open_vocab(classes, 500)
+  caps = synthetic.make_captions(rng, 8, vocab, list(name2id.keys()), plant_range=(1, 6))
+  got = ex.extract_labels({InputDataFields.concat_caption_string: caps}).cpu().numpy()
+  np.testing.assert_array_equal(got, olabels.extend_match_extract(ocls, name2id, caps))
+  assert name2id['sharedsyn'] == max(i for i in range(80) if i % 7 == 3 and i % 11 != 5)
+
+
+# ---------------------------------------------------------------------------------------------
+def _build_model(C_classes, extractor_text, is_training=True, eval_dims=(), keep_prob=0.5, num_oicr=3):
+  from cap2det_b200 import builder, config, synthetic
+  text = synthetic.model_options_text(num_oicr=num_oicr, keep_prob=keep_prob, extractor=extractor_text[0],
+                                      extractor_fields=extractor_text[1], eval_min_dimension=eval_dims)
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  return builder.build(m, is_training=is_training)
+
+
+def test_model_train_step_end_to_end_fp32():
+  """build_prediction + build_loss + backward against the oracle composition (small P)."""
+  from cap2det_b200 import synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  C, K, B, P = 20, 3, 2, 48
+  model = _build_model(C, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)))
+  rng = np.random.default_rng(21)
+  fmap = synthetic.make_feature_map(rng, B, 160, 208)
+  props = synthetic.make_proposals(rng, B, P, 160, 208)
+  npr = np.array([P, P - 11], np.int32)
+  props[1, P - 11:] = 0
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  # give the FC layers a larger init so the logits are not all ~0
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+    model.fc_biases.copy_(dev((rng.standard_normal(model.fc_biases.shape[0]) * 0.1).astype(np.float32)))
+  fm = dev(fmap).requires_grad_(True)
+  examples = {F.features_to_crop: fm, F.num_proposals: dev(npr), F.proposals: dev(props), F.object_texts: texts,
+              F.dropout_keep_mask: dev(keep)}
+  pred = model.build_prediction(examples, postprocess=True)
+  loss = model.build_loss(pred, examples)
+  assert sorted(loss.keys()) == ['midn_cross_entropy_loss'] + ['oicr_cross_entropy_loss_at_%d' % i for i in (1, 2, 3)]
+  sum(loss.values()).backward()
+  model.raise_if_assert_failed()
+  labels = olabels.groundtruth_extract(classes, texts)
+  np.testing.assert_array_equal(model.last_labels.cpu().numpy(), labels)
+  want = oracle_model.forward_backward(
+      fmap, props, npr, labels, oracle_model.head_params_from_named(model.named_variables()),
+      model.fc_weights.detach().cpu().numpy(), model.fc_biases.detach().cpu().numpy(), keep, 0.5, C, K, 0.6, 1.0, 0.5)
+  assert rel_err(pred['midn_class_logits'].detach().cpu().numpy(), want['class_logits']) < 2e-5
+  assert rel_err(pred['midn_proba_r_given_c'].detach().cpu().numpy(), want['proba']) < 2e-5
+  assert rel_err(pred['oicr_proposal_scores_at_0'].detach().cpu().numpy(), want['scores0']) < 2e-5
+  for i in range(K):
+    got = pred['oicr_proposal_scores_at_%d' % (i + 1)].detach().cpu().numpy()
+    assert got.shape == (B, P, C + 1)
+    assert rel_err(got, want['logits'][:, :, 2 * C + i * (C + 1): 2 * C + (i + 1) * (C + 1)]) < 2e-5
+    ind, pl = model.last_oicr_assignments[i]
+    np.testing.assert_array_equal(ind.cpu().numpy(), want['aux'][i][0])           # pseudo-label seeds: bit-exact
+    np.testing.assert_array_equal(pl.cpu().numpy(), want['aux'][i][1])            # soft labels: bit-exact
+  for k, v in want['loss'].items():
+    assert abs(float(loss[k]) - v) <= 2e-5 * abs(v), k
+  assert rel_err(model.fc_weights.grad.cpu().numpy(), want['dfc_w']) < 1e-4
+  assert rel_err(model.fc_biases.grad.cpu().numpy(), want['dfc_b']) < 1e-4
+  assert rel_err(fm.grad.cpu().numpy(), want['dfmap']) < 1e-4
+  from cap2det_b200 import ops
+  dflat = model.head_params.grad.cpu().numpy()
+  for name, k, cin, cout, _, off in ops.head_conv_specs():
+    w = dflat[off['weights']:off['weights'] + cout * k * k * cin].reshape(cout, k, k, cin)
+    assert rel_err(w, want['dhead'][name]['weights']) < 1e-4, name
+    assert rel_err(dflat[off['gamma']:off['gamma'] + cout], want['dhead'][name]['gamma']) < 1e-4, name
+  # detections dict contract (models/cap2det_model.py:142-149)
+  for i in range(K + 1):
+    assert pred['num_detections_at_%d' % i].shape == (B,) and pred['num_detections_at_%d' % i].dtype == torch.int32
+    assert pred['detection_boxes_at_%d' % i].shape == (B, 300, 4)
+    assert pred['detection_scores_at_%d' % i].shape == (B, 300)
+    assert pred['detection_classes_at_%d' % i].shape == (B, 300)
+  s0 = pred['oicr_proposal_scores_at_0'].detach().cpu().numpy()
+  n_o, b_o, s_o, c_o, k_o = onms.multiclass_nms(props, s0, 1e-5, 0.4, 100, 300)
+  np.testing.assert_array_equal(pred['num_detections_at_0'].cpu().numpy(), n_o)
+  np.testing.assert_array_equal(pred['detection_classes_at_0'].cpu().numpy(), c_o)
+  np.testing.assert_array_equal(pred['detection_boxes_at_0'].cpu().numpy(), b_o)
+  assert pred['class_labels'] == classes
+
+
+def test_model_multiscale_eval_and_errors():
+  from cap2det_b200 import synthetic, config, cap2det_model
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  model = _build_model(20, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)),
+                       is_training=False, eval_dims=(1200, 800))
+  rng = np.random.default_rng(22)
+  P = 40
+  props = synthetic.make_proposals(rng, 1, P, 160, 208)
+  fm1 = synthetic.make_feature_map(rng, 1, 160, 208)
+  fm2 = synthetic.make_feature_map(rng, 1, 112, 144)
+  ex = {F.num_proposals: dev(np.array([P], np.int32)), F.proposals: dev(props)}
+  p1 = model.build_prediction(dict(ex, **{F.features_to_crop: [dev(fm1)]}))
+  p2 = model.build_prediction(dict(ex, **{F.features_to_crop: [dev(fm2)]}))
+  p12 = model.build_prediction(dict(ex, **{F.features_to_crop: [dev(fm1), dev(fm2)]}))
+  for i in range(4):
+    k = 'oicr_proposal_scores_at_%d' % i
+    np.testing.assert_allclose(p12[k].cpu().numpy(), (p1[k].cpu().numpy() + p2[k].cpu().numpy()) / 2, rtol=1e-6, atol=1e-9)
+  assert p12['detection_boxes_at_3'].shape == (1, 300, 4)
+  with pytest.raises(ValueError):
+    cap2det_model.Model(config.PostProcess())
+  with pytest.raises(NotImplementedError):
+    model.build_prediction({F.num_proposals: ex[F.num_proposals], F.proposals: ex[F.proposals], F.image: None})
+
+
+def test_full_size_properties_P2000():
+  """BASELINE sizes (P=2000, C=80): size-independent properties of the OICR / NMS / MIDN kernels."""
+  from cap2det_b200 import ops, synthetic
+  rng = np.random.default_rng(23)
+  B, P, C = 2, 2000, 80
+  props = synthetic.make_proposals(rng, B, P)
+  npr = np.array([P, 1873], np.int32)
+  logits = dev(rng.standard_normal((B, P, 2 * C)).astype(np.float32))
+  cl, sc, pr = ops.midn(logits, 0, C, C, dev(npr))
+  np.testing.assert_allclose(pr.sum(dim=1).cpu().numpy(), 1.0, rtol=1e-5)
+  assert torch.all(pr[1, 1873:] == 0)
+  labels = (rng.uniform(size=(B, C)) < 0.04).astype(np.float32); labels[:, 0] = 1
+  ind, pl, status = ops.oicr_assign(dev(labels), dev(npr), dev(props), pr, 0.6)
+  assert int(status.item()) == 0
+  s = pl.sum(dim=-1).cpu().numpy()
+  assert np.all(np.abs(s - 1) < 1e-6)                                   # the reference's tf.Assert
+  assert torch.all(ind[1] < 1873) and torch.all(ind >= 0)
+  plc = pl.cpu().numpy()
+  assert np.all(plc[:, :, 1:][:, :, labels[0] == 0][0] == 0)
+  seeds = ind.cpu().numpy()
+  for c in np.nonzero(labels[0])[0]:
+    assert plc[0, seeds[0, c], 1 + c] > 0                               # IoU(seed, seed) == 1 >= thr
+  # idempotence: same inputs -> identical outputs
+  ind2, pl2, _ = ops.oicr_assign(dev(labels), dev(npr), dev(props), pr, 0.6)
+  assert torch.equal(ind, ind2) and torch.equal(pl, pl2)
+  n, b, s_, c_, k = ops.multiclass_nms(dev(props), sc, 1e-5, 0.4, 100, 300)
+  sn = s_.cpu().numpy(); kn = k.cpu().numpy(); nn_ = n.cpu().numpy()
+  for bi in range(B):
+    assert np.all(np.diff(sn[bi, :nn_[bi]]) <= 0)                       # sorted by score
+    assert np.all(kn[bi, nn_[bi]:] == -1) and np.all(sn[bi, nn_[bi]:] == 0)
+    cls = c_.cpu().numpy()[bi, :nn_[bi]]
+    for cc in np.unique(cls):
+      assert (cls == cc).sum() <= 100
