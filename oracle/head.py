@@ -51,8 +51,10 @@ def _t(x):
   return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
 
 
-def _conv_bn_relu(x, p, name, k, stride):
-  """x NCHW.  p[name] = dict(weights OHWI, gamma, beta, mean, var)."""
+def _conv_bn_relu(x, p, name, k, stride, collect=None):
+  """x NCHW.  p[name] = dict(weights OHWI, gamma, beta, mean, var).
+  `collect` (dict) receives the pre-activation of every conv (tests use it to find ReLU inputs that
+  sit within rounding noise of zero, where the backward mask is implementation-defined)."""
   q = p[name]
   w = _t(q['weights']).permute(0, 3, 1, 2)          # OHWI -> OIHW
   pad = (k - 1) // 2                                 # SAME: symmetric for all shapes on this path
@@ -60,13 +62,16 @@ def _conv_bn_relu(x, p, name, k, stride):
   inv = torch.rsqrt(_t(q['var']) + BN_EPS)
   scale = _t(q['gamma']) * inv
   shift = _t(q['beta']) - _t(q['mean']) * scale
-  return torch.relu(z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+  u = z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+  if collect is not None:
+    collect[name] = u.detach()
+  return torch.relu(u)
 
 
-def head_mixed5(x_nhwc, p):
+def head_mixed5(x_nhwc, p, collect=None):
   """x [N,7,7,576] (torch or numpy) -> [N,4,4,1024] torch tensor (NHWC)."""
   x = _t(x_nhwc).permute(0, 3, 1, 2)
-  c = lambda t, n: _conv_bn_relu(t, p, n, *[(s[1], s[4]) for s in HEAD_CONVS if s[0] == n][0])
+  c = lambda t, n: _conv_bn_relu(t, p, n, *[(s[1], s[4]) for s in HEAD_CONVS if s[0] == n][0], collect=collect)
   # Mixed_5a
   b0 = c(c(x, 'Mixed_5a/Branch_0/Conv2d_0a_1x1'), 'Mixed_5a/Branch_0/Conv2d_1a_3x3')
   b1 = c(c(c(x, 'Mixed_5a/Branch_1/Conv2d_0a_1x1'), 'Mixed_5a/Branch_1/Conv2d_0b_3x3'),
