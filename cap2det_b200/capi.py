@@ -41,6 +41,9 @@ SIGNATURES = {
     'c2d_head_workspace_bytes': (_c_sz, [_c_int, _c_int]),
     'c2d_head_mixed5_fwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p]),
     'c2d_head_mixed5_bwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p]),
+    'c2d_conv_bf16_fwd': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _p, _c_int, _p, _c_int, _p]),
+    'c2d_conv_bf16_dgrad': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _p]),
+    'c2d_conv_bf16_wgrad': (_c_int, [_p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p]),
     'c2d_fc_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int]),
     'c2d_fc_fwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_int, _p, _c_int, _c_int, _p, _c_sz, _p]),
     'c2d_fc_bwd': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _p, _c_int, _p, _p, _p, _c_int, _p, _c_sz, _p]),

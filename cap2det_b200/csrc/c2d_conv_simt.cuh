@@ -6,6 +6,7 @@
 // outputs are written straight into their channel slice of the Inception concat buffers.
 #pragma once
 #include "c2d_common.cuh"
+#include "c2d_head_plan.h"
 
 namespace c2d {
 
@@ -133,7 +134,7 @@ igemm_f32_kernel(const float* __restrict__ A, int lda, int Kc, ConvGeom g, const
 
 // dW[co, tap*Kc + ci] += sum_m dY[m, co] * X[src(m,tap), ci]     (atomic split over m)
 //   grid.x = ceil(Kc/64) * ceil(N/64), grid.y = taps, grid.z = row splits.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 wgrad_f32_kernel(const float* __restrict__ dY, int ldy, int N, const float* __restrict__ X, int ldx, int Kc,
                  ConvGeom g, int M, int rows_per_split, float* __restrict__ dW) {
   __shared__ float Ys[16][64 + 4];
@@ -238,7 +239,7 @@ __global__ void relu_bwd_colsum_kernel(T* __restrict__ dy, const T* __restrict__
 }
 
 // Column sums of a [M, N] fp32 matrix (bias gradient): out[n] += sum_m x[m, n].
-__global__ void colsum_f32_kernel(const float* __restrict__ x, int ld, int M, int N, int rows_per_cta,
+static __global__ void colsum_f32_kernel(const float* __restrict__ x, int ld, int M, int N, int rows_per_cta,
                                   float* __restrict__ out) {
   __shared__ float red[8][32];
   const int n = blockIdx.x * 32 + threadIdx.x;
@@ -376,5 +377,49 @@ __global__ void avgpool_dropout_bwd_kernel(const float* __restrict__ dfeat, cons
   g = g / (float)hw;
   for (int i = 0; i < hw; ++i) Elem<T>::st(dx + ((size_t)n * hw + i) * C + c, g);
 }
+
+// ---- weight folding / unfolding ------------------------------------------------------------
+// one warp per output channel
+static __global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ mean,
+                               const float* __restrict__ var, int cout, int taps, int cin, float* __restrict__ ws,
+                               float* __restrict__ wt, float* __restrict__ shift) {
+  int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (co >= cout) return;
+  float s = gamma[co] * rsqrtf(var[co] + kBnEps);
+  if (lane == 0) shift[co] = beta[co] - mean[co] * s;
+  int K = taps * cin;
+  for (int k = lane; k < K; k += 32) {
+    float v = w[(size_t)co * K + k] * s;
+    ws[(size_t)co * K + k] = v;
+    int tap = k / cin, ci = k - tap * cin;
+    wt[((size_t)ci * taps + tap) * cout + co] = v;     // [cin][tap][cout] for the data gradient
+  }
+}
+static __global__ void unfold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
+                                 const float* __restrict__ mean, const float* __restrict__ var, int cout, int K,
+                                 const float* __restrict__ dws, const float* __restrict__ dshift,
+                                 float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                 float* __restrict__ dmean, float* __restrict__ dvar) {
+  int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (co >= cout) return;
+  float inv = rsqrtf(var[co] + kBnEps);
+  float s = gamma[co] * inv;
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float g = dws[(size_t)co * K + k];
+    dot += w[(size_t)co * K + k] * g;
+    dw[(size_t)co * K + k] = g * s;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    float dt = dshift[co];
+    dgamma[co] = inv * (dot - mean[co] * dt);
+    dbeta[co] = dt;
+    dmean[co] = 0.f;   // frozen moving statistics
+    dvar[co] = 0.f;
+  }
+}
+
 
 }  // namespace c2d

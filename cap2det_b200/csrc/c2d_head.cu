@@ -13,49 +13,6 @@
 
 namespace c2d {
 
-// ---- weight folding / unfolding ------------------------------------------------------------
-// one warp per output channel
-__global__ void fold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, const float* __restrict__ mean,
-                               const float* __restrict__ var, int cout, int taps, int cin, float* __restrict__ ws,
-                               float* __restrict__ wt, float* __restrict__ shift) {
-  int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (co >= cout) return;
-  float s = gamma[co] * rsqrtf(var[co] + kBnEps);
-  if (lane == 0) shift[co] = beta[co] - mean[co] * s;
-  int K = taps * cin;
-  for (int k = lane; k < K; k += 32) {
-    float v = w[(size_t)co * K + k] * s;
-    ws[(size_t)co * K + k] = v;
-    int tap = k / cin, ci = k - tap * cin;
-    wt[((size_t)ci * taps + tap) * cout + co] = v;     // [cin][tap][cout] for the data gradient
-  }
-}
-__global__ void unfold_bn_kernel(const float* __restrict__ w, const float* __restrict__ gamma,
-                                 const float* __restrict__ mean, const float* __restrict__ var, int cout, int K,
-                                 const float* __restrict__ dws, const float* __restrict__ dshift,
-                                 float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                 float* __restrict__ dmean, float* __restrict__ dvar) {
-  int co = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (co >= cout) return;
-  float inv = rsqrtf(var[co] + kBnEps);
-  float s = gamma[co] * inv;
-  float dot = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    float g = dws[(size_t)co * K + k];
-    dot += w[(size_t)co * K + k] * g;
-    dw[(size_t)co * K + k] = g * s;
-  }
-  dot = warp_sum(dot);
-  if (lane == 0) {
-    float dt = dshift[co];
-    dgamma[co] = inv * (dot - mean[co] * dt);
-    dbeta[co] = dt;
-    dmean[co] = 0.f;   // frozen moving statistics
-    dvar[co] = 0.f;
-  }
-}
-
 static ConvGeom geom_fwd(const HeadConv& c) {
   ConvGeom g;
   g.Hrow = g.Wrow = c.hout; g.Hsrc = g.Wsrc = c.hin; g.k = c.k; g.stride = c.stride; g.pad = (c.k - 1) / 2; g.mode = 0;

@@ -1,19 +1,479 @@
-// bf16 tcgen05 path of the box-classifier head (placeholder until the tensor-core kernels land).
-#include "c2d_common.cuh"
+// bf16 tensor-core path (tcgen05 + TMEM + TMA) of the box-classifier head: host-side tensor-map
+// construction, per-layer launch descriptors and the forward / backward orchestration.
+// Reference semantics: models/utils.py:165-177 (see c2d_head.cu for the BN folding algebra).
+#include <cuda.h>
+
+#include "c2d_conv_simt.cuh"
+#include "c2d_gemm_tc.cuh"
 #include "c2d_head_plan.h"
+
+namespace c2d {
+
+using bf16 = __nv_bfloat16;
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed) --------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor with dims (innermost first) d[0..3], element strides es[1..3] (es[0] == 1), box b[0..3].
+static bool make_map(CUtensorMap* m, const void* base, const long long d[4], const long long es[4], const int b[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled entry point not available"); return false; }
+  cuuint64_t gdim[4] = {(cuuint64_t)d[0], (cuuint64_t)d[1], (cuuint64_t)d[2], (cuuint64_t)d[3]};
+  cuuint64_t gstr[3] = {(cuuint64_t)es[1] * 2, (cuuint64_t)es[2] * 2, (cuuint64_t)es[3] * 2};
+  cuuint32_t box[4] = {(cuuint32_t)b[0], (cuuint32_t)b[1], (cuuint32_t)b[2], (cuuint32_t)b[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): dims %lld %lld %lld %lld strides %lld %lld %lld box %d %d %d %d",
+              (int)r, d[0], d[1], d[2], d[3], es[1], es[2], es[3], b[0], b[1], b[2], b[3]);
+    return false;
+  }
+  return true;
+}
+// [rows, C] row-major matrix with leading dimension ld (elements); box = (64, box_rows).
+static bool make_map_flat(CUtensorMap* m, const void* base, long long C, long long rows, long long ld, int box_rows) {
+  long long d[4] = {C, rows, 1, 1};
+  long long es[4] = {1, ld, ld * rows, ld * rows};
+  int b[4] = {64, box_rows, 1, 1};
+  return make_map(m, base, d, es, b);
+}
+// NHWC activation [n, h, h, C] (leading dimension ld); box = (64, bw, bh, bn).
+static bool make_map_nhwc(CUtensorMap* m, const void* base, long long C, int h, long long n, long long ld, int bw,
+                          int bh, int bn) {
+  long long d[4] = {C, h, h, n};
+  long long es[4] = {1, ld, ld * h, ld * h * h};
+  int b[4] = {64, bw, bh, bn};
+  return make_map(m, base, d, es, b);
+}
+// Parity view (py, px) of a [n, 7, 7, C] tensor: element (q_x, q_y) = pixel (2*q_y + py, 2*q_x + px).
+static bool make_map_parity(CUtensorMap* m, const bf16* base, long long C, long long n, long long ld, int py, int px,
+                            int bn) {
+  long long d[4] = {C, px ? 3 : 4, py ? 3 : 4, n};
+  long long es[4] = {1, 2 * ld, 2 * 7 * ld, 49 * ld};
+  int b[4] = {64, 4, 4, bn};
+  return make_map(m, base + (py * 7 + px) * ld, d, es, b);
+}
+
+static int pick_tiles(int n, int max_tile, int* tile) {
+  int t = (n + max_tile - 1) / max_tile;
+  while (true) {
+    int w = (n + t - 1) / t;
+    w = (w + 15) / 16 * 16;
+    if (w <= max_tile) { *tile = w; return t; }
+    ++t;
+  }
+}
+
+static bool g_attr_done = false;
+static int tc_prepare() {
+  if (!g_attr_done) {
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    g_attr_done = true;
+  }
+  return C2D_OK;
+}
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Description of one convolution operand set (all bf16, NHWC with leading dimensions).
+struct ConvDesc {
+  int n;              // ROIs
+  int k, stride;      // 1 or 3 ; 1 or 2
+  int hin, hout;      // 7/7, 7/4 (stride 2) or 4/4
+  int cin, cout;
+  const bf16* x; int ldx;        // input activation  [n, hin, hin, cin]
+  bf16* y; int ldy;              // output activation [n, hout, hout, cout]   (forward)
+};
+
+static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::ConvGemmParams& p, cudaStream_t st) {
+  int rc = tc_prepare();
+  if (rc != C2D_OK) return rc;
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  if (grid <= 0) return C2D_OK;
+  tc::conv_gemm_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+// Forward: y = act(conv(x, w) + shift).  w16: [cout][k*k][cin] bf16 (K-major).
+static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, cudaStream_t st) {
+  tc::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4], mapB;
+  const int taps = c.k * c.k;
+  p.kc = c.cin;
+  p.chunks_per_tap = (c.cin + 63) / 64;
+  p.num_n_tiles = pick_tiles(c.cout, 256, &p.n_tile);
+  p.n_total = c.cout;
+  p.shift = shift; p.out = c.y; p.ldo = c.ldy; p.out_f32 = 0; p.relu = relu; p.accum = 0;
+  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, c.cout, (long long)taps * c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  if (c.k == 1) {
+    const long long M = (long long)c.n * c.hin * c.hin;
+    p.taps = 1; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
+    p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
+    if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
+    maps[1] = maps[2] = maps[3] = maps[0];
+  } else {
+    p.taps = 9; p.flat = 0;
+    p.pos_per_roi = c.hout * c.hout; p.box_w = c.hout;
+    p.rois_per_tile = 256 / p.pos_per_roi;
+    p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
+    p.a_box_bytes = p.rows_per_tile * 128;
+    p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+    p.Hf = p.Wf = c.hout; p.sy = p.sx = 1; p.oy = p.ox = 0;
+    if (c.stride == 1) {
+      if (!make_map_nhwc(&maps[0], c.x, c.cin, c.hin, c.n, c.ldx, c.hin, c.hin, p.rois_per_tile)) return C2D_ERR_CUDA;
+      maps[1] = maps[2] = maps[3] = maps[0];
+      for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_b[t] = t; p.tap_map[t] = 0; }
+    } else {
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          if (!make_map_parity(&maps[py * 2 + px], c.x, c.cin, c.n, c.ldx, py, px, p.rois_per_tile)) return C2D_ERR_CUDA;
+      for (int t = 0; t < 9; ++t) {
+        int dy = t / 3, dx = t % 3;
+        int py = dy == 1 ? 0 : 1, px = dx == 1 ? 0 : 1;
+        p.tap_y[t] = dy == 0 ? -1 : 0; p.tap_x[t] = dx == 0 ? -1 : 0;
+        p.tap_b[t] = t; p.tap_map[t] = py * 2 + px;
+      }
+    }
+  }
+  return launch_conv(maps, mapB, p, st);
+}
+
+// Data gradient: dx (+)= conv_transpose(du, w).  wt16: [cin][k*k][cout] bf16.  du: [n,hout,hout,cout] (ld lddu).
+static int conv_dgrad_tc(const ConvDesc& c, const bf16* du, int lddu, const bf16* wt16, bf16* dx, int lddx, int accum,
+                         cudaStream_t st) {
+  const int taps = c.k * c.k;
+  tc::ConvGemmParams base;
+  memset(&base, 0, sizeof(base));
+  base.kc = c.cout;
+  base.chunks_per_tap = (c.cout + 63) / 64;
+  base.num_n_tiles = pick_tiles(c.cin, 256, &base.n_tile);
+  base.n_total = c.cin;
+  base.shift = nullptr; base.out = dx; base.ldo = lddx; base.out_f32 = 0; base.relu = 0; base.accum = accum;
+  CUtensorMap maps[4], mapB;
+  if (!make_map_flat(&mapB, wt16, (long long)taps * c.cout, c.cin, (long long)taps * c.cout, base.n_tile)) return C2D_ERR_CUDA;
+  if (c.k == 1) {
+    tc::ConvGemmParams p = base;
+    const long long M = (long long)c.n * c.hin * c.hin;
+    p.taps = 1; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
+    p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
+    if (!make_map_flat(&maps[0], du, c.cout, M, lddu, 256)) return C2D_ERR_CUDA;
+    maps[1] = maps[2] = maps[3] = maps[0];
+    return launch_conv(maps, mapB, p, st);
+  }
+  if (c.stride == 1) {
+    tc::ConvGemmParams p = base;
+    p.taps = 9; p.flat = 0;
+    p.pos_per_roi = c.hin * c.hin; p.box_w = c.hin;
+    p.rois_per_tile = 256 / p.pos_per_roi;
+    p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
+    p.a_box_bytes = p.rows_per_tile * 128;
+    p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+    p.Hf = p.Wf = c.hin; p.sy = p.sx = 1; p.oy = p.ox = 0;
+    if (!make_map_nhwc(&maps[0], du, c.cout, c.hout, c.n, lddu, c.hout, c.hout, p.rois_per_tile)) return C2D_ERR_CUDA;
+    maps[1] = maps[2] = maps[3] = maps[0];
+    // dx[y,x] = sum_{dy,dx} du[y + 1 - dy, x + 1 - dx] * w[dy,dx]
+    for (int t = 0; t < 9; ++t) { p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_b[t] = t; p.tap_map[t] = 0; }
+    return launch_conv(maps, mapB, p, st);
+  }
+  // stride 2 (7x7 <- 4x4): one launch per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      tc::ConvGemmParams p = base;
+      const int nh = py ? 3 : 4, nw = px ? 3 : 4;
+      p.flat = 0;
+      p.pos_per_roi = nh * nw; p.box_w = nw;
+      p.rois_per_tile = 256 / p.pos_per_roi;
+      p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
+      p.a_box_bytes = p.rows_per_tile * 128;
+      p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+      p.Hf = p.Wf = 7; p.sy = p.sx = 2; p.oy = py; p.ox = px;
+      if (!make_map_nhwc(&maps[0], du, c.cout, 4, c.n, lddu, nw, nh, p.rois_per_tile)) return C2D_ERR_CUDA;
+      maps[1] = maps[2] = maps[3] = maps[0];
+      // even coordinate: tap 1 reads o = j ; odd coordinate: tap 0 reads o = j + 1, tap 2 reads o = j
+      int ty[2], oyv[2], nty = 0, tx[2], oxv[2], ntx = 0;
+      if (py == 0) { ty[0] = 1; oyv[0] = 0; nty = 1; } else { ty[0] = 0; oyv[0] = 1; ty[1] = 2; oyv[1] = 0; nty = 2; }
+      if (px == 0) { tx[0] = 1; oxv[0] = 0; ntx = 1; } else { tx[0] = 0; oxv[0] = 1; tx[1] = 2; oxv[1] = 0; ntx = 2; }
+      int t = 0;
+      for (int a = 0; a < nty; ++a)
+        for (int b = 0; b < ntx; ++b) {
+          p.tap_y[t] = oyv[a]; p.tap_x[t] = oxv[b]; p.tap_b[t] = ty[a] * 3 + tx[b]; p.tap_map[t] = 0;
+          ++t;
+        }
+      p.taps = t;
+      int rc = launch_conv(maps, mapB, p, st);
+      if (rc != C2D_OK) return rc;
+    }
+  return C2D_OK;
+}
+
+// Weight gradient: dw[cout][k*k][cin] (fp32, pre-zeroed by the caller) += du^T * x.
+static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaStream_t st) {
+  int rc = tc_prepare();
+  if (rc != C2D_OK) return rc;
+  tc::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap mapY, mapX[4];
+  p.taps = c.k * c.k; p.taps_total = p.taps;
+  p.cout = c.cout; p.cin = c.cin; p.dw = dw;
+  p.co_tiles = (c.cout + 127) / 128;
+  p.ci_tiles = pick_tiles(c.cin, 256, &p.ci_tile);
+  p.ci_groups = (p.ci_tile + 63) / 64;
+  if (c.k == 1) {
+    const long long M = (long long)c.n * c.hin * c.hin;
+    p.flat = 1; p.total_steps = (int)((M + 63) / 64);
+    if (!make_map_flat(&mapY, du, c.cout, M, lddu, 64)) return C2D_ERR_CUDA;
+    if (!make_map_flat(&mapX[0], c.x, c.cin, M, c.ldx, 64)) return C2D_ERR_CUDA;
+    mapX[1] = mapX[2] = mapX[3] = mapX[0];
+    p.tap_b[0] = 0; p.tap_map[0] = 0;
+  } else {
+    p.flat = 0;
+    if (c.hout == 7) {          // 49 valid rows padded to an 8x8 box: the out-of-range rows are TMA zero fill
+      p.rois_per_step = 1;
+      if (!make_map_nhwc(&mapY, du, c.cout, 7, c.n, lddu, 8, 8, 1)) return C2D_ERR_CUDA;
+    } else {
+      p.rois_per_step = 4;
+      if (!make_map_nhwc(&mapY, du, c.cout, 4, c.n, lddu, 4, 4, 4)) return C2D_ERR_CUDA;
+    }
+    p.total_steps = (c.n + p.rois_per_step - 1) / p.rois_per_step;
+    if (c.stride == 1) {
+      const int bw = c.hin == 7 ? 8 : 4;
+      if (!make_map_nhwc(&mapX[0], c.x, c.cin, c.hin, c.n, c.ldx, bw, bw, p.rois_per_step)) return C2D_ERR_CUDA;
+      mapX[1] = mapX[2] = mapX[3] = mapX[0];
+      for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_b[t] = t; p.tap_map[t] = 0; }
+    } else {
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px)
+          if (!make_map_parity(&mapX[py * 2 + px], c.x, c.cin, c.n, c.ldx, py, px, 4)) return C2D_ERR_CUDA;
+      for (int t = 0; t < 9; ++t) {
+        int dy = t / 3, dx = t % 3;
+        p.tap_y[t] = dy == 0 ? -1 : 0; p.tap_x[t] = dx == 0 ? -1 : 0;
+        p.tap_b[t] = t; p.tap_map[t] = (dy == 1 ? 0 : 1) * 2 + (dx == 1 ? 0 : 1);
+      }
+    }
+  }
+  const int base_items = p.taps * p.co_tiles * p.ci_tiles;
+  int splits = (2 * num_sms() + base_items - 1) / base_items;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_steps) splits = p.total_steps;
+  p.steps_per_split = (p.total_steps + splits - 1) / splits;
+  p.num_splits = (p.total_steps + p.steps_per_split - 1) / p.steps_per_split;
+  const int items = base_items * p.num_splits;
+  if (items <= 0 || p.total_steps <= 0) return C2D_OK;
+  const int grid = items < num_sms() ? items : num_sms();
+  tc::wgrad_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+// ---- small helpers ----------------------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    st4(y + i, *reinterpret_cast<const float4*>(x + i));
+  } else {
+    for (; i < n; ++i) y[i] = __float2bfloat16_rn(x[i]);
+  }
+}
+static void launch_cast(const float* x, bf16* y, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  cast_f32_bf16_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(x, y, n);
+  count_launch();
+}
+
+
+static ConvDesc head_conv_desc(int i, int n, bf16* const act[]) {
+  const HeadConv& c = kHeadConvs[i];
+  ConvDesc d;
+  d.n = n; d.k = c.k; d.stride = c.stride; d.hin = c.hin; d.hout = c.hout; d.cin = c.cin; d.cout = c.cout;
+  d.x = act[c.src] + c.src_off; d.ldx = kHeadBufs[c.src].ch;
+  d.y = act[c.dst] + c.dst_off; d.ldy = kHeadBufs[c.dst].ch;
+  return d;
+}
+
+}  // namespace c2d
 
 using namespace c2d;
 
 extern "C" {
-int c2d_has_tensor_core_head(void) { return 0; }
-int c2d_head_mixed5_fwd_bf16(const void*, int, const float*, const HeadPlan&, char*, const float*, float, float*,
-                             cudaStream_t) {
-  set_error("head: bf16 tcgen05 path not built yet");
-  return C2D_ERR_UNSUPPORTED;
+
+int c2d_has_tensor_core_head(void) { return 1; }
+
+static int check_conv_args(int n, int hin, int cin, int cout, int k, int stride, int ldx, int ldy) {
+  C2D_CHECK_ARG(n >= 0 && (hin == 7 || hin == 4) && (k == 1 || k == 3), "conv_bf16: hin must be 7 or 4, k 1 or 3");
+  C2D_CHECK_ARG(stride == 1 || (stride == 2 && hin == 7 && k == 3), "conv_bf16: stride 2 needs hin 7, k 3");
+  C2D_CHECK_ARG(cin >= 16 && cin % 16 == 0 && cout >= 16 && cout % 16 == 0, "conv_bf16: channels must be multiples of 16");
+  C2D_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv_bf16: leading dims must be multiples of 8");
+  return C2D_OK;
 }
-int c2d_head_mixed5_bwd_bf16(const void*, int, const float*, const HeadPlan&, char*, const float*, float,
-                             const float*, float*, void*, cudaStream_t) {
-  set_error("head: bf16 tcgen05 path not built yet");
-  return C2D_ERR_UNSUPPORTED;
+static ConvDesc make_desc(const void* x, int ldx, int n, int hin, int cin, int cout, int k, int stride, void* y, int ldy) {
+  ConvDesc d;
+  d.n = n; d.k = k; d.stride = stride; d.hin = hin; d.hout = stride == 2 ? 4 : hin; d.cin = cin; d.cout = cout;
+  d.x = reinterpret_cast<const bf16*>(x); d.ldx = ldx; d.y = reinterpret_cast<bf16*>(y); d.ldy = ldy;
+  return d;
 }
+
+int c2d_conv_bf16_fwd(const void* x, int ldx, int n, int hin, int cin, const void* w16, int cout, int k, int stride,
+                      const float* shift, int relu, void* y, int ldy, c2d_stream_t stream) {
+  int rc = check_conv_args(n, hin, cin, cout, k, stride, ldx, ldy);
+  if (rc != C2D_OK || n == 0) return rc;
+  return conv_fwd_tc(make_desc(x, ldx, n, hin, cin, cout, k, stride, y, ldy), reinterpret_cast<const bf16*>(w16), shift,
+                     relu, (cudaStream_t)stream);
 }
+int c2d_conv_bf16_dgrad(const void* dy, int lddy, int n, int hin, int cin, const void* wt16, int cout, int k,
+                        int stride, void* dx, int lddx, int accumulate, c2d_stream_t stream) {
+  int rc = check_conv_args(n, hin, cin, cout, k, stride, lddx, lddy);
+  if (rc != C2D_OK || n == 0) return rc;
+  return conv_dgrad_tc(make_desc(nullptr, lddx, n, hin, cin, cout, k, stride, nullptr, lddy),
+                       reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(wt16),
+                       reinterpret_cast<bf16*>(dx), lddx, accumulate, (cudaStream_t)stream);
+}
+int c2d_conv_bf16_wgrad(const void* x, int ldx, const void* dy, int lddy, int n, int hin, int cin, int cout, int k,
+                        int stride, float* dw, c2d_stream_t stream) {
+  int rc = check_conv_args(n, hin, cin, cout, k, stride, ldx, lddy);
+  if (rc != C2D_OK || n == 0) return rc;
+  return conv_wgrad_tc(make_desc(x, ldx, n, hin, cin, cout, k, stride, nullptr, lddy),
+                       reinterpret_cast<const bf16*>(dy), lddy, dw, (cudaStream_t)stream);
+}
+
+int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const HeadPlan& pl, char* ws,
+                             const float* keep_mask, float keep_prob, float* feat, cudaStream_t st) {
+  bf16* act[NBUF];
+  act[X0] = reinterpret_cast<bf16*>(const_cast<void*>(x0));
+  for (int b = 1; b < NBUF; ++b) act[b] = reinterpret_cast<bf16*>(ws + pl.act_off[b]);
+  float* wsf = reinterpret_cast<float*>(ws + pl.ws_off);
+  float* wtf = reinterpret_cast<float*>(ws + pl.wt_off);
+  float* shf = reinterpret_cast<float*>(ws + pl.shift_off);
+  bf16* ws16 = reinterpret_cast<bf16*>(ws + pl.ws16_off);
+  bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
+  for (int i = 0; i < kNumHeadConvs; ++i) {
+    const HeadConv& c = kHeadConvs[i];
+    const HeadParamOff& o = pl.poff[i];
+    fold_bn_kernel<<<cdiv(c.cout * 32, 256), 256, 0, st>>>(params + o.w, params + o.gamma, params + o.beta,
+                                                          params + o.mean, params + o.var, c.cout, c.k * c.k, c.cin,
+                                                          wsf + o.w_only, wtf + o.w_only, shf + o.ch);
+    count_launch();
+  }
+  launch_cast(wsf, ws16, pl.w_only_total, st);
+  launch_cast(wtf, wt16, pl.w_only_total, st);
+  for (int i = 0; i < kNumHeadConvs; ++i) {
+    if (i == 5) {
+      pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
+      count_launch();
+    }
+    if (i == 11) {
+      pool3x3_fwd_kernel<bf16, 4, 1, 1><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
+      count_launch();
+    }
+    if (i == 18) {
+      pool3x3_fwd_kernel<bf16, 4, 1, 0><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
+      count_launch();
+    }
+    const HeadParamOff& o = pl.poff[i];
+    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, st);
+    if (rc != C2D_OK) return rc;
+  }
+  avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const HeadPlan& pl, char* ws,
+                             const float* keep_mask, float keep_prob, const float* dfeat, float* dparams, void* dx0,
+                             cudaStream_t st) {
+  bf16* act[NBUF];
+  bf16* grad[NBUF];
+  act[X0] = reinterpret_cast<bf16*>(const_cast<void*>(x0));
+  grad[X0] = reinterpret_cast<bf16*>(dx0);
+  for (int b = 1; b < NBUF; ++b) {
+    act[b] = reinterpret_cast<bf16*>(ws + pl.act_off[b]);
+    grad[b] = reinterpret_cast<bf16*>(ws + pl.grad_off[b]);
+  }
+  bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
+  float* dwsf = reinterpret_cast<float*>(ws + pl.dws_off);
+  float* dshf = reinterpret_cast<float*>(ws + pl.dshift_off);
+  C2D_CUDA_OK(cudaMemsetAsync(dwsf, 0, pl.w_only_total * sizeof(float), st));
+  C2D_CUDA_OK(cudaMemsetAsync(dshf, 0, pl.ch_total * sizeof(float), st));
+  bool written[NBUF] = {false};
+  avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n);
+  count_launch();
+  written[X3] = true;
+  for (int i = kNumHeadConvs - 1; i >= 0; --i) {
+    const HeadConv& c = kHeadConvs[i];
+    const HeadParamOff& o = pl.poff[i];
+    const int M = n * c.hout * c.hout;
+    bf16* dy = grad[c.dst] + c.dst_off;
+    const int ldd = kHeadBufs[c.dst].ch;
+    relu_bwd_colsum_kernel<bf16><<<dim3(cdiv(c.cout / 4, 32), cdiv(M, 512)), dim3(32, 8), 0, st>>>(
+        dy, act[c.dst] + c.dst_off, ldd, M, c.cout, 512, dshf + o.ch);
+    count_launch();
+    ConvDesc d = head_conv_desc(i, n, act);
+    int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st);
+    if (rc != C2D_OK) return rc;
+    if (!(c.src == X0 && dx0 == nullptr)) {
+      rc = conv_dgrad_tc(d, dy, ldd, wt16 + o.w_only, grad[c.src] + c.src_off, kHeadBufs[c.src].ch,
+                         written[c.src] ? 1 : 0, st);
+      if (rc != C2D_OK) return rc;
+      written[c.src] = true;
+    }
+    if (i == 18) {
+      pool3x3_bwd_kernel<bf16, 4, 1, 0, false><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(
+          act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
+      count_launch();
+      written[X2] = true;
+    }
+    if (i == 11) {
+      pool3x3_bwd_kernel<bf16, 4, 1, 1, false><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(
+          act[X1], 1024, grad[P1], 1024, grad[X1], 1024, n, 1024);
+      count_launch();
+      written[X1] = true;
+    }
+    if (i == 5 && dx0 != nullptr) {
+      pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576, 128), n), 128, 0, st>>>(
+          act[X0], 576, grad[X1] + 448, 1024, grad[X0], 576, n, 576);
+      count_launch();
+      written[X0] = true;
+    }
+  }
+  for (int i = 0; i < kNumHeadConvs; ++i) {
+    const HeadConv& c = kHeadConvs[i];
+    const HeadParamOff& o = pl.poff[i];
+    unfold_bn_kernel<<<cdiv(c.cout * 32, 256), 256, 0, st>>>(
+        params + o.w, params + o.gamma, params + o.mean, params + o.var, c.cout, c.k * c.k * c.cin, dwsf + o.w_only,
+        dshf + o.ch, dparams + o.w, dparams + o.gamma, dparams + o.beta, dparams + o.mean, dparams + o.var);
+    count_launch();
+  }
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+}  // extern "C"

@@ -101,6 +101,19 @@ int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* para
                         size_t workspace_bytes, const float* keep_mask, float keep_prob,
                         const float* dfeat, float* dparams, void* dx0, c2d_stream_t stream);
 
+/* Building blocks of the bf16 (tcgen05/TMEM/TMA) head path, exposed for the parity tests: SAME-padded
+ * k x k convolution (the slim.conv2d inside Mixed_5a-c) on [n, hin, hin, cin] NHWC bf16 maps with leading
+ * dimension ldx; hin is 7 or 4, k is 1 or 3, stride 1 (or 2 with hin 7, k 3).  fp32 accumulation.
+ *   fwd  : y = act(conv(x, w16) + shift),        w16  [cout][k*k][cin] bf16
+ *   dgrad: dx (+)= conv_transpose(dy, wt16),     wt16 [cin][k*k][cout] bf16
+ *   wgrad: dw [cout][k*k][cin] fp32 += dy^T x    (caller zeroes dw) */
+int c2d_conv_bf16_fwd(const void* x, int ldx, int n, int hin, int cin, const void* w16, int cout, int k, int stride,
+                      const float* shift, int relu, void* y, int ldy, c2d_stream_t stream);
+int c2d_conv_bf16_dgrad(const void* dy, int lddy, int n, int hin, int cin, const void* wt16, int cout, int k,
+                        int stride, void* dx, int lddx, int accumulate, c2d_stream_t stream);
+int c2d_conv_bf16_wgrad(const void* x, int ldx, const void* dy, int lddy, int n, int hin, int cin, int cout, int k,
+                        int stride, float* dw, c2d_stream_t stream);
+
 /* ---- K4: slim.fully_connected(activation_fn=None), models/cap2det_model.py:79-88,190-197.
  * The 2 MIDN + K OICR layers run as ONE product: y[M,ldy] = x[M,D] . w[N,D]^T + b[N]. */
 size_t c2d_fc_workspace_bytes(int M, int D, int N, int dtype);
