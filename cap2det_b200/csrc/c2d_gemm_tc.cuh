@@ -96,7 +96,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
             if (p.flat) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
             else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, p.tap_x[t], p.tap_y[t], mt * p.rois_per_tile);
-            tma_load_2d(sB, &mapB, &pipe->full[stage], p.tap_b[t] * p.kc + c * 64, nt * p.n_tile);
+            tma_load_4d(sB, &mapB, &pipe->full[stage], p.tap_b[t] * p.kc + c * 64, nt * p.n_tile, 0, 0);   // rank-4 map
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }

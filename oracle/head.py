@@ -51,7 +51,29 @@ def _t(x):
   return x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
 
 
-def _conv_bn_relu(x, p, name, k, stride, collect=None):
+class _RoundBF16(torch.autograd.Function):
+  """Round to bf16 (straight-through gradient).  Used to emulate the storage precision of the bf16
+  tensor-core path: folded weights, activations and activation gradients are stored in bf16 while every
+  accumulation stays fp32."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).float()
+
+  @staticmethod
+  def backward(ctx, g):
+    return g
+
+
+def _store_bf16(x):
+  """bf16 storage of an activation: forward value AND the gradient that flows back are rounded."""
+  y = _RoundBF16.apply(x)
+  if y.requires_grad:
+    y.register_hook(lambda g: g.to(torch.bfloat16).float())
+  return y
+
+
+def _conv_bn_relu(x, p, name, k, stride, collect=None, emulate_bf16=False):
   """x NCHW.  p[name] = dict(weights OHWI, gamma, beta, mean, var).
   `collect` (dict) receives the pre-activation of every conv (tests use it to find ReLU inputs that
   sit within rounding noise of zero, where the backward mask is implementation-defined)."""
@@ -62,16 +84,27 @@ def _conv_bn_relu(x, p, name, k, stride, collect=None):
   inv = torch.rsqrt(_t(q['var']) + BN_EPS)
   scale = _t(q['gamma']) * inv
   shift = _t(q['beta']) - _t(q['mean']) * scale
+  if emulate_bf16:
+    wf = _RoundBF16.apply(w * scale.view(-1, 1, 1, 1))       # BN scale folded into bf16 weights
+    u = TF_.conv2d(x, wf, None, stride=stride, padding=pad) + shift.view(1, -1, 1, 1)
+    return _store_bf16(torch.relu(u))
   u = z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
   if collect is not None:
     collect[name] = u.detach()
   return torch.relu(u)
 
 
-def head_mixed5(x_nhwc, p, collect=None):
-  """x [N,7,7,576] (torch or numpy) -> [N,4,4,1024] torch tensor (NHWC)."""
+def head_mixed5(x_nhwc, p, collect=None, emulate_bf16=False):
+  """x [N,7,7,576] (torch or numpy) -> [N,4,4,1024] torch tensor (NHWC).
+
+  emulate_bf16=True mirrors the storage precision of the bf16 tensor-core path (bf16 folded weights,
+  bf16 activations and activation gradients, fp32 accumulation) so that gradient parity can be checked
+  on identical ReLU masks; the plain fp32 path stays the reference for the forward tolerance."""
   x = _t(x_nhwc).permute(0, 3, 1, 2)
-  c = lambda t, n: _conv_bn_relu(t, p, n, *[(s[1], s[4]) for s in HEAD_CONVS if s[0] == n][0], collect=collect)
+  if emulate_bf16:
+    x = _store_bf16(x)
+  c = lambda t, n: _conv_bn_relu(t, p, n, *[(s[1], s[4]) for s in HEAD_CONVS if s[0] == n][0], collect=collect,
+                                 emulate_bf16=emulate_bf16)
   # Mixed_5a
   b0 = c(c(x, 'Mixed_5a/Branch_0/Conv2d_0a_1x1'), 'Mixed_5a/Branch_0/Conv2d_1a_3x3')
   b1 = c(c(c(x, 'Mixed_5a/Branch_1/Conv2d_0a_1x1'), 'Mixed_5a/Branch_1/Conv2d_0b_3x3'),
@@ -87,6 +120,8 @@ def head_mixed5(x_nhwc, p, collect=None):
       b3 = TF_.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
     else:
       b3 = TF_.max_pool2d(x, 3, stride=1, padding=1)
+    if emulate_bf16:
+      b3 = _store_bf16(b3)
     b3 = c(b3, blk + '/Branch_3/Conv2d_0b_1x1')
     x = torch.cat([b0, b1, b2, b3], dim=1)
   return x.permute(0, 2, 3, 1)
