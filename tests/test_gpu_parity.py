@@ -487,11 +487,11 @@ def test_model_train_step_end_to_end_fp32():
   # Gradients that pass through the 17 ReLUs of the head: with 96 ROIs (~6M ReLU inputs) a handful of
   # pre-activations sit within fp32 rounding noise of zero, where the mask is implementation-defined
   # (see _unambiguous_head_setup; strict 5e-5 parity is asserted there).  Here: relative L2 error and
-  # the fraction of elements off by more than 1e-4 of the tensor's max.
+  # the fraction of elements off by more than 1e-3 of the tensor's max.
   def close_up_to_relu_flips(got, ref, name):
     got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
     l2 = np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30)
-    frac = float((np.abs(got - ref) > 1e-4 * np.abs(ref).max()).mean())
+    frac = float((np.abs(got - ref) > 1e-3 * np.abs(ref).max()).mean())
     assert l2 < 5e-3 and frac < 0.02, (name, l2, frac)
 
   close_up_to_relu_flips(fm.grad.cpu().numpy(), want['dfmap'], 'dfmap')
