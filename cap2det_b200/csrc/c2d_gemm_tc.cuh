@@ -18,26 +18,34 @@
 namespace c2d {
 namespace tc {
 
-constexpr int kStages = 3;
+constexpr int kStages = 4;
 constexpr int kStageABytes = 32768;              // 256 rows x 64 bf16
-constexpr int kStageBBytes = 32768;              // <= 256 rows x 64 bf16
+constexpr int kStageBBytes = 16384;              // <= 128 rows x 64 bf16
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kTcThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int kTmemCols = 512;
+constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
+constexpr int kMaxTaps = 9;
 
 struct ConvGemmParams {
-  int taps, chunks_per_tap, kc;
-  int tap_x[9], tap_y[9], tap_b[9], tap_map[9];
+  int taps;                       // K-loop segments: 3x3 taps, or the sources of a merged 1x1 group
+  int tap_chunks[kMaxTaps];       // 64-channel chunks of segment t
+  int tap_koff[kMaxTaps];         // offset of segment t on the K axis of the B (weight) matrix
+  int tap_x[kMaxTaps], tap_y[kMaxTaps], tap_map[kMaxTaps];
   int flat;                 // 1: A rows are flat [rows, C]; box = (64, 256)
   int rois_per_tile, pos_per_roi, box_w;
   int rows_per_tile;        // valid rows per M tile (<= 256)
   int a_box_bytes;          // bytes one A box transfers
-  int num_m_tiles, num_n_tiles, n_tile;
+  int num_m_tiles, num_n_tiles, n_tile;   // n_tile = UMMA N (<= 128, multiple of 16)
   int m_total;              // flat: total rows; geometric: total ROIs
-  int n_total;              // valid output columns
-  const float* shift;       // per-column addend (BN shift / bias) or null
-  void* out; int ldo; int out_f32; int relu; int accum;
+  int n_total;              // valid output columns (multiple of 16)
+  const float* shift;       // per-column addend (BN shift / bias), n_total entries, or null
+  // output column segments: columns [seg_begin[s], seg_begin[s+1]) go to seg_out[s] (leading dim seg_ld[s])
+  int nseg;
+  int seg_begin[4];
+  void* seg_out[3];
+  int seg_ld[3];
+  int out_f32, relu, accum;
   // geometric output row mapping: pixel = (n*Hf + jy*sy + oy)*Wf + jx*sx + ox
   int Hf, Wf, sy, sx, oy, ox;
 };
@@ -45,8 +53,8 @@ struct ConvGemmParams {
 struct TcPipe {
   uint64_t full[kStages];
   uint64_t empty[kStages];
-  uint64_t tmem_full;
-  uint64_t tmem_empty;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
 
@@ -66,8 +74,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
-    mbar_init(&pipe->tmem_full, 1);
-    mbar_init(&pipe->tmem_empty, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 4); }
     fence_barrier_init();
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
   }
@@ -78,7 +85,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   const uint32_t tmem_base = pipe->tmem_base;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int ksteps = p.taps * p.chunks_per_tap;
   const uint32_t stage_tx = (uint32_t)p.a_box_bytes + (uint32_t)p.n_tile * 128u;
 
   if (warp == 0) {
@@ -88,15 +94,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
         for (int t = 0; t < p.taps; ++t) {
-          const CUtensorMap* mA = p.tap_map[t] == 0 ? &mapA0 : (p.tap_map[t] == 1 ? &mapA1 : (p.tap_map[t] == 2 ? &mapA2 : &mapA3));
-          for (int c = 0; c < p.chunks_per_tap; ++c) {
+          const int tm = p.tap_map[t];
+          const CUtensorMap* mA = tm == 0 ? &mapA0 : (tm == 1 ? &mapA1 : (tm == 2 ? &mapA2 : &mapA3));
+          const int nchunks = p.tap_chunks[t], koff = p.tap_koff[t], tx = p.tap_x[t], ty = p.tap_y[t];
+          for (int c = 0; c < nchunks; ++c) {
             mbar_wait(&pipe->empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * kStageBytes;
             uint8_t* sB = sA + kStageABytes;
             mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
             if (p.flat) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
-            else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, p.tap_x[t], p.tap_y[t], mt * p.rois_per_tile);
-            tma_load_4d(sB, &mapB, &pipe->full[stage], p.tap_b[t] * p.kc + c * 64, nt * p.n_tile, 0, 0);   // rank-4 map
+            else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, tx, ty, mt * p.rois_per_tile);
+            tma_load_4d(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile, 0, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -105,10 +113,16 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   } else if (warp == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
-    int stage = 0; uint32_t phase = 0; uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      mbar_wait(&pipe->tmem_empty, tphase ^ 1);
+    int ksteps = 0;
+    for (int t = 0; t < p.taps; ++t) ksteps += p.tap_chunks[t];
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;                       // accumulator stage (TMEM double buffering)
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&pipe->tmem_empty[as], aphase ^ 1);
       tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
@@ -119,24 +133,25 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           for (int kk = 0; kk < 4; ++kk) {
             const uint64_t bdesc = make_smem_desc(sB + kk * 32, 16, 1024);
             const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(tmem_base, make_smem_desc(sA + kk * 32, 16, 1024), bdesc, idesc, acc);
-            umma_f16(tmem_base + 256, make_smem_desc(sA + 16384 + kk * 32, 16, 1024), bdesc, idesc, acc);
+            umma_f16(acc0, make_smem_desc(sA + kk * 32, 16, 1024), bdesc, idesc, acc);
+            umma_f16(acc0 + 128, make_smem_desc(sA + 16384 + kk * 32, 16, 1024), bdesc, idesc, acc);
           }
           umma_commit(&pipe->empty[stage]);
-          if (ks == ksteps - 1) umma_commit(&pipe->tmem_full);
+          if (ks == ksteps - 1) umma_commit(&pipe->tmem_full[as]);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      tphase ^= 1;
     }
   } else {
     // ===== epilogue (warps 2..5): TMEM -> registers -> (+shift, relu, accumulate) -> global =====
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    uint32_t tphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
-      mbar_wait(&pipe->tmem_full, tphase);
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
 #pragma unroll 1
       for (int a = 0; a < 2; ++a) {
@@ -155,63 +170,69 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             }
           }
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * 128);
 #pragma unroll 1
         for (int j = 0; j < p.n_tile; j += 16) {
+          const int col0 = nt * p.n_tile + j;
+          if (col0 >= p.n_total) break;               // warp-uniform
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
           if (orow >= 0) {
-            const int col0 = nt * p.n_tile + j;
+            int sgm = 0;
+            if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
+            if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+            const int scol = col0 - p.seg_begin[sgm];
+            const long long ooff = orow * p.seg_ld[sgm] + scol;
             float f[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              f[i] = __uint_as_float(v[i]);
-              if (p.shift != nullptr && col0 + i < p.n_total) f[i] += p.shift[col0 + i];
-              if (p.relu) f[i] = fmaxf(f[i], 0.f);
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.shift != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 s4 = __ldg(sp + i);
+                f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.seg_out[sgm]) + ooff);
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (col0 + i < p.n_total) o[i] = p.accum ? o[i] + f[i] : f[i];
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
-              if (col0 + 16 <= p.n_total) {
-                if (p.accum) {
-                  uint4 o0 = *reinterpret_cast<uint4*>(o), o1 = *reinterpret_cast<uint4*>(o + 8);
-                  const uint32_t old[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&old[i]);
-                    float2 ff = __bfloat1622float2(b2);
-                    f[2 * i] += ff.x; f[2 * i + 1] += ff.y;
-                  }
-                }
-                uint4 w0, w1;
-                w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
-                w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
-                w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
-                w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
-                *reinterpret_cast<uint4*>(o) = w0;
-                *reinterpret_cast<uint4*>(o + 8) = w1;
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (col0 + i < p.n_total) {
-                    float x = f[i];
-                    if (p.accum) x += __bfloat162float(o[i]);
-                    o[i] = __float2bfloat16_rn(x);
-                  }
+              for (int i = 0; i < 4; ++i) {
+                float4 w = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                if (p.accum) { float4 old = o[i]; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+                o[i] = w;
               }
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
+              if (p.accum) {
+                uint4 o0 = *reinterpret_cast<uint4*>(o), o1 = *reinterpret_cast<uint4*>(o + 8);
+                const uint32_t old[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&old[i]);
+                  float2 ff = __bfloat1622float2(b2);
+                  f[2 * i] += ff.x; f[2 * i + 1] += ff.y;
+                }
+              }
+              uint4 w0, w1;
+              w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
+              w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
+              w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
+              w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
+              *reinterpret_cast<uint4*>(o) = w0;
+              *reinterpret_cast<uint4*>(o + 8) = w1;
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pipe->tmem_empty);
-      tphase ^= 1;
+      if (lane == 0) mbar_arrive(&pipe->tmem_empty[as]);
     }
   }
   tc_fence_before();
@@ -251,8 +272,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
-    mbar_init(&pipe->tmem_full, 1);
-    mbar_init(&pipe->tmem_empty, 4);
+    mbar_init(&pipe->tmem_full[0], 1);
+    mbar_init(&pipe->tmem_empty[0], 4);
     fence_barrier_init();
     prefetch_tmap(&mapY); prefetch_tmap(&mapX0);
   }
@@ -280,7 +301,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
         for (int s = s0; s < s1; ++s) {
           mbar_wait(&pipe->empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kStageBytes;
-          uint8_t* sB = sA + kStageABytes;
+          uint8_t* sB = sA + 16384;        // A' = 2 groups x 8 KB, B' = up to 4 groups x 8 KB
           mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
           for (int g = 0; g < 2; ++g) {
             if (p.flat) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 128 + g * 64, s * 64, 0, 0);
@@ -302,25 +323,25 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       const int split = item % p.num_splits;
       const int s0 = split * p.steps_per_split;
       const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-      mbar_wait(&pipe->tmem_empty, tphase ^ 1);
+      mbar_wait(&pipe->tmem_empty[0], tphase ^ 1);
       tc_fence_after();
       for (int s = s0; s < s1; ++s) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sB = sA + kStageABytes;
+          const uint32_t sB = sA + 16384;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)     // 16 reduction rows per MMA = two 8-row swizzle atoms
             umma_f16(tmem_base, make_smem_desc(sA + kk * 2048, 8192, 1024), make_smem_desc(sB + kk * 2048, 8192, 1024),
                      idesc, (s > s0 || kk > 0) ? 1u : 0u);
           umma_commit(&pipe->empty[stage]);
-          if (s == s1 - 1) umma_commit(&pipe->tmem_full);
+          if (s == s1 - 1) umma_commit(&pipe->tmem_full[0]);
         }
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
-      if (s1 <= s0 && lane == 0) umma_commit(&pipe->tmem_full);   // empty split (never scheduled by the host)
+      if (s1 <= s0 && lane == 0) umma_commit(&pipe->tmem_full[0]);   // empty split (never scheduled by the host)
       tphase ^= 1;
     }
   } else {
@@ -334,7 +355,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       const int t = rem;
       const int s0 = split * p.steps_per_split;
       const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-      mbar_wait(&pipe->tmem_full, tphase);
+      mbar_wait(&pipe->tmem_full[0], tphase);
       tc_fence_after();
       const int co = cot * 128 + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -352,7 +373,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pipe->tmem_empty);
+      if (lane == 0) mbar_arrive(&pipe->tmem_empty[0]);
       tphase ^= 1;
     }
   }

@@ -121,21 +121,38 @@ static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::C
   return C2D_OK;
 }
 
-// Forward: y = act(conv(x, w) + shift).  w16: [cout][k*k][cin] bf16 (K-major).
-static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, cudaStream_t st) {
+struct OutSeg { void* out; int ld; int cols; };      // destination of a column range
+struct InSeg { const bf16* du; int ld; int cols; };  // one source of a merged 1x1 data gradient
+
+static void set_segments(tc::ConvGemmParams& p, const OutSeg* segs, int nseg) {
+  p.nseg = nseg;
+  int begin = 0;
+  for (int s = 0; s < nseg; ++s) {
+    p.seg_begin[s] = begin; p.seg_out[s] = segs[s].out; p.seg_ld[s] = segs[s].ld;
+    begin += segs[s].cols;
+  }
+  for (int s = nseg; s < 4; ++s) p.seg_begin[s] = begin;
+  p.n_total = begin;
+}
+
+// Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift) with the output columns split over `segs`.
+//   w16: [sum cols][k*k][cin] bf16 (K-major); shift: [sum cols] or null.
+static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
+                       int out_f32, cudaStream_t st) {
   tc::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4], mapB;
   const int taps = c.k * c.k;
-  p.kc = c.cin;
-  p.chunks_per_tap = (c.cin + 63) / 64;
-  p.num_n_tiles = pick_tiles(c.cout, 256, &p.n_tile);
-  p.n_total = c.cout;
-  p.shift = shift; p.out = c.y; p.ldo = c.ldy; p.out_f32 = 0; p.relu = relu; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, c.cout, (long long)taps * c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  set_segments(p, segs, nseg);
+  const int cout = p.n_total;
+  p.num_n_tiles = pick_tiles(cout, 128, &p.n_tile);
+  p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
+  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, cout, (long long)taps * c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  const int chunks = (c.cin + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
-    p.taps = 1; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
+    p.taps = 1; p.tap_chunks[0] = chunks; p.tap_koff[0] = 0; p.tap_map[0] = 0;
+    p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
     p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
     if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
     maps[1] = maps[2] = maps[3] = maps[0];
@@ -147,10 +164,11 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
     p.a_box_bytes = p.rows_per_tile * 128;
     p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
     p.Hf = p.Wf = c.hout; p.sy = p.sx = 1; p.oy = p.ox = 0;
+    for (int t = 0; t < 9; ++t) { p.tap_chunks[t] = chunks; p.tap_koff[t] = t * c.cin; }
     if (c.stride == 1) {
       if (!make_map_nhwc(&maps[0], c.x, c.cin, c.hin, c.n, c.ldx, c.hin, c.hin, p.rois_per_tile)) return C2D_ERR_CUDA;
       maps[1] = maps[2] = maps[3] = maps[0];
-      for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_b[t] = t; p.tap_map[t] = 0; }
+      for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_map[t] = 0; }
     } else {
       for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px)
@@ -159,35 +177,46 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
         int dy = t / 3, dx = t % 3;
         int py = dy == 1 ? 0 : 1, px = dx == 1 ? 0 : 1;
         p.tap_y[t] = dy == 0 ? -1 : 0; p.tap_x[t] = dx == 0 ? -1 : 0;
-        p.tap_b[t] = t; p.tap_map[t] = py * 2 + px;
+        p.tap_map[t] = py * 2 + px;
       }
     }
   }
   return launch_conv(maps, mapB, p, st);
 }
 
-// Data gradient: dx (+)= conv_transpose(du, w).  wt16: [cin][k*k][cout] bf16.  du: [n,hout,hout,cout] (ld lddu).
-static int conv_dgrad_tc(const ConvDesc& c, const bf16* du, int lddu, const bf16* wt16, bf16* dx, int lddx, int accum,
-                         cudaStream_t st) {
+// Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).
+//   k == 1: up to 3 sources (a merged sibling group), wt16 = [cin][sum cols] bf16.
+//   k == 3: one source, wt16 = [cin][9][cols] bf16.
+static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16* wt16, void* dx, int lddx,
+                         int accum, int out_f32, cudaStream_t st) {
   const int taps = c.k * c.k;
+  int ksum = 0;
+  for (int s = 0; s < nsrc; ++s) ksum += srcs[s].cols;
   tc::ConvGemmParams base;
   memset(&base, 0, sizeof(base));
-  base.kc = c.cout;
-  base.chunks_per_tap = (c.cout + 63) / 64;
-  base.num_n_tiles = pick_tiles(c.cin, 256, &base.n_tile);
-  base.n_total = c.cin;
-  base.shift = nullptr; base.out = dx; base.ldo = lddx; base.out_f32 = 0; base.relu = 0; base.accum = accum;
+  OutSeg oseg = {dx, lddx, c.cin};
+  set_segments(base, &oseg, 1);
+  base.num_n_tiles = pick_tiles(c.cin, 128, &base.n_tile);
+  base.shift = nullptr; base.out_f32 = out_f32; base.relu = 0; base.accum = accum;
   CUtensorMap maps[4], mapB;
-  if (!make_map_flat(&mapB, wt16, (long long)taps * c.cout, c.cin, (long long)taps * c.cout, base.n_tile)) return C2D_ERR_CUDA;
+  if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, base.n_tile)) return C2D_ERR_CUDA;
   if (c.k == 1) {
     tc::ConvGemmParams p = base;
     const long long M = (long long)c.n * c.hin * c.hin;
-    p.taps = 1; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
+    p.taps = nsrc; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
     p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
-    if (!make_map_flat(&maps[0], du, c.cout, M, lddu, 256)) return C2D_ERR_CUDA;
-    maps[1] = maps[2] = maps[3] = maps[0];
+    int koff = 0;
+    for (int s = 0; s < nsrc; ++s) {
+      if (!make_map_flat(&maps[s], srcs[s].du, srcs[s].cols, M, srcs[s].ld, 256)) return C2D_ERR_CUDA;
+      p.tap_chunks[s] = (srcs[s].cols + 63) / 64; p.tap_koff[s] = koff; p.tap_map[s] = s;
+      koff += srcs[s].cols;
+    }
+    for (int s = nsrc; s < 4; ++s) maps[s] = maps[0];
     return launch_conv(maps, mapB, p, st);
   }
+  const bf16* du = srcs[0].du;
+  const int lddu = srcs[0].ld;
+  const int chunks = (c.cout + 63) / 64;
   if (c.stride == 1) {
     tc::ConvGemmParams p = base;
     p.taps = 9; p.flat = 0;
@@ -200,7 +229,9 @@ static int conv_dgrad_tc(const ConvDesc& c, const bf16* du, int lddu, const bf16
     if (!make_map_nhwc(&maps[0], du, c.cout, c.hout, c.n, lddu, c.hout, c.hout, p.rois_per_tile)) return C2D_ERR_CUDA;
     maps[1] = maps[2] = maps[3] = maps[0];
     // dx[y,x] = sum_{dy,dx} du[y + 1 - dy, x + 1 - dx] * w[dy,dx]
-    for (int t = 0; t < 9; ++t) { p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_b[t] = t; p.tap_map[t] = 0; }
+    for (int t = 0; t < 9; ++t) {
+      p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_koff[t] = t * c.cout; p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
+    }
     return launch_conv(maps, mapB, p, st);
   }
   // stride 2 (7x7 <- 4x4): one launch per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
@@ -223,8 +254,9 @@ static int conv_dgrad_tc(const ConvDesc& c, const bf16* du, int lddu, const bf16
       if (px == 0) { tx[0] = 1; oxv[0] = 0; ntx = 1; } else { tx[0] = 0; oxv[0] = 1; tx[1] = 2; oxv[1] = 0; ntx = 2; }
       int t = 0;
       for (int a = 0; a < nty; ++a)
-        for (int b = 0; b < ntx; ++b) {
-          p.tap_y[t] = oyv[a]; p.tap_x[t] = oxv[b]; p.tap_b[t] = ty[a] * 3 + tx[b]; p.tap_map[t] = 0;
+        for (int b2 = 0; b2 < ntx; ++b2) {
+          p.tap_y[t] = oyv[a]; p.tap_x[t] = oxv[b2]; p.tap_koff[t] = (ty[a] * 3 + tx[b2]) * c.cout;
+          p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
           ++t;
         }
       p.taps = t;
@@ -309,6 +341,77 @@ static void launch_cast(const float* x, bf16* y, long long n, cudaStream_t st) {
   count_launch();
 }
 
+// All 19 convolutions folded / unfolded by ONE launch each (grid.y = convolution).
+struct FoldEntry {
+  long long w, gamma, beta, mean, var, w_only, ch, wt_base;
+  int cout, taps, cin, wt_ld, wt_coloff;
+};
+struct FoldTable { FoldEntry e[kNumHeadConvs]; };
+
+static FoldTable make_fold_table(const HeadPlan& pl) {
+  FoldTable t;
+  for (int i = 0; i < kNumHeadConvs; ++i) {
+    const HeadConv& c = kHeadConvs[i];
+    FoldEntry& e = t.e[i];
+    e.w = pl.poff[i].w; e.gamma = pl.poff[i].gamma; e.beta = pl.poff[i].beta; e.mean = pl.poff[i].mean;
+    e.var = pl.poff[i].var; e.w_only = pl.poff[i].w_only; e.ch = pl.poff[i].ch;
+    e.cout = c.cout; e.taps = c.k * c.k; e.cin = c.cin;
+    e.wt_base = pl.poff[i].w_only; e.wt_ld = c.cout; e.wt_coloff = 0;
+  }
+  for (int g = 0; g < 3; ++g) {       // merged sibling groups: wt = [cin][sum cout]
+    int first = kHeadGroups[g].first, total = 0;
+    for (int j = 0; j < kHeadGroups[g].size; ++j) total += kHeadConvs[first + j].cout;
+    int off = 0;
+    for (int j = 0; j < kHeadGroups[g].size; ++j) {
+      FoldEntry& e = t.e[first + j];
+      e.wt_base = pl.poff[first].w_only; e.wt_ld = total; e.wt_coloff = off;
+      off += kHeadConvs[first + j].cout;
+    }
+  }
+  return t;
+}
+
+// ws16[co][k] = W[co][k] * s(co);  wt16 = transposed copy for the data gradient;  shift = beta - mean * s.
+__global__ void fold_bn_bf16_kernel(const float* __restrict__ params, const FoldTable tab, bf16* __restrict__ ws16,
+                                    bf16* __restrict__ wt16, float* __restrict__ shift) {
+  const FoldEntry& e = tab.e[blockIdx.y];
+  const int co = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (co >= e.cout) return;
+  const float s = params[e.gamma + co] * rsqrtf(params[e.var + co] + kBnEps);
+  if (lane == 0) shift[e.ch + co] = params[e.beta + co] - params[e.mean + co] * s;
+  const int K = e.taps * e.cin;
+  const float* w = params + e.w + (long long)co * K;
+  for (int k = lane; k < K; k += 32) {
+    const bf16 v = __float2bfloat16_rn(w[k] * s);
+    ws16[e.w_only + (long long)co * K + k] = v;
+    const int tap = k / e.cin, ci = k - tap * e.cin;
+    wt16[e.wt_base + ((long long)ci * e.taps + tap) * e.wt_ld + e.wt_coloff + co] = v;
+  }
+}
+__global__ void unfold_bn_all_kernel(const float* __restrict__ params, const FoldTable tab,
+                                     const float* __restrict__ dws, const float* __restrict__ dshift,
+                                     float* __restrict__ dparams) {
+  const FoldEntry& e = tab.e[blockIdx.y];
+  const int co = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (co >= e.cout) return;
+  const float inv = rsqrtf(params[e.var + co] + kBnEps);
+  const float s = params[e.gamma + co] * inv;
+  const int K = e.taps * e.cin;
+  float dot = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float g = dws[e.w_only + (long long)co * K + k];
+    dot += params[e.w + (long long)co * K + k] * g;
+    dparams[e.w + (long long)co * K + k] = g * s;
+  }
+  dot = warp_sum(dot);
+  if (lane == 0) {
+    const float dt = dshift[e.ch + co];
+    dparams[e.gamma + co] = inv * (dot - params[e.mean + co] * dt);
+    dparams[e.beta + co] = dt;
+    dparams[e.mean + co] = 0.f;
+    dparams[e.var + co] = 0.f;
+  }
+}
 
 static ConvDesc head_conv_desc(int i, int n, bf16* const act[]) {
   const HeadConv& c = kHeadConvs[i];
@@ -345,16 +448,17 @@ int c2d_conv_bf16_fwd(const void* x, int ldx, int n, int hin, int cin, const voi
                       const float* shift, int relu, void* y, int ldy, c2d_stream_t stream) {
   int rc = check_conv_args(n, hin, cin, cout, k, stride, ldx, ldy);
   if (rc != C2D_OK || n == 0) return rc;
+  OutSeg seg = {y, ldy, cout};
   return conv_fwd_tc(make_desc(x, ldx, n, hin, cin, cout, k, stride, y, ldy), reinterpret_cast<const bf16*>(w16), shift,
-                     relu, (cudaStream_t)stream);
+                     relu, &seg, 1, 0, (cudaStream_t)stream);
 }
 int c2d_conv_bf16_dgrad(const void* dy, int lddy, int n, int hin, int cin, const void* wt16, int cout, int k,
                         int stride, void* dx, int lddx, int accumulate, c2d_stream_t stream) {
   int rc = check_conv_args(n, hin, cin, cout, k, stride, lddx, lddy);
   if (rc != C2D_OK || n == 0) return rc;
-  return conv_dgrad_tc(make_desc(nullptr, lddx, n, hin, cin, cout, k, stride, nullptr, lddy),
-                       reinterpret_cast<const bf16*>(dy), lddy, reinterpret_cast<const bf16*>(wt16),
-                       reinterpret_cast<bf16*>(dx), lddx, accumulate, (cudaStream_t)stream);
+  InSeg src = {reinterpret_cast<const bf16*>(dy), lddy, cout};
+  return conv_dgrad_tc(make_desc(nullptr, lddx, n, hin, cin, cout, k, stride, nullptr, lddy), &src, 1,
+                       reinterpret_cast<const bf16*>(wt16), dx, lddx, accumulate, 0, (cudaStream_t)stream);
 }
 int c2d_conv_bf16_wgrad(const void* x, int ldx, const void* dy, int lddy, int n, int hin, int cin, int cout, int k,
                         int stride, float* dw, c2d_stream_t stream) {
@@ -369,21 +473,11 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   bf16* act[NBUF];
   act[X0] = reinterpret_cast<bf16*>(const_cast<void*>(x0));
   for (int b = 1; b < NBUF; ++b) act[b] = reinterpret_cast<bf16*>(ws + pl.act_off[b]);
-  float* wsf = reinterpret_cast<float*>(ws + pl.ws_off);
-  float* wtf = reinterpret_cast<float*>(ws + pl.wt_off);
   float* shf = reinterpret_cast<float*>(ws + pl.shift_off);
   bf16* ws16 = reinterpret_cast<bf16*>(ws + pl.ws16_off);
   bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
-  for (int i = 0; i < kNumHeadConvs; ++i) {
-    const HeadConv& c = kHeadConvs[i];
-    const HeadParamOff& o = pl.poff[i];
-    fold_bn_kernel<<<cdiv(c.cout * 32, 256), 256, 0, st>>>(params + o.w, params + o.gamma, params + o.beta,
-                                                          params + o.mean, params + o.var, c.cout, c.k * c.k, c.cin,
-                                                          wsf + o.w_only, wtf + o.w_only, shf + o.ch);
-    count_launch();
-  }
-  launch_cast(wsf, ws16, pl.w_only_total, st);
-  launch_cast(wtf, wt16, pl.w_only_total, st);
+  fold_bn_bf16_kernel<<<dim3(cdiv(352, 8), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), ws16, wt16, shf);
+  count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
     if (i == 5) {
       pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
@@ -397,8 +491,16 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       pool3x3_fwd_kernel<bf16, 4, 1, 0><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
       count_launch();
     }
+    if (head_in_group_tail(i)) continue;          // computed together with the first member of its group
     const HeadParamOff& o = pl.poff[i];
-    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, st);
+    int gsz = head_group_size(i);
+    if (gsz == 0) gsz = 1;
+    OutSeg segs[3];
+    for (int j = 0; j < gsz; ++j) {
+      const HeadConv& cj = kHeadConvs[i + j];
+      segs[j].out = act[cj.dst] + cj.dst_off; segs[j].ld = kHeadBufs[cj.dst].ch; segs[j].cols = cj.cout;
+    }
+    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, segs, gsz, 0, st);
     if (rc != C2D_OK) return rc;
   }
   avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
@@ -439,9 +541,17 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
     ConvDesc d = head_conv_desc(i, n, act);
     int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st);
     if (rc != C2D_OK) return rc;
-    if (!(c.src == X0 && dx0 == nullptr)) {
-      rc = conv_dgrad_tc(d, dy, ldd, wt16 + o.w_only, grad[c.src] + c.src_off, kHeadBufs[c.src].ch,
-                         written[c.src] ? 1 : 0, st);
+    // data gradient: a sibling group is reduced by ONE GEMM once its first (lowest) member is reached
+    if (!head_in_group_tail(i) && !(c.src == X0 && dx0 == nullptr)) {
+      int gsz = head_group_size(i);
+      if (gsz == 0) gsz = 1;
+      InSeg srcs[3];
+      for (int j = 0; j < gsz; ++j) {
+        const HeadConv& cj = kHeadConvs[i + j];
+        srcs[j].du = grad[cj.dst] + cj.dst_off; srcs[j].ld = kHeadBufs[cj.dst].ch; srcs[j].cols = cj.cout;
+      }
+      rc = conv_dgrad_tc(d, srcs, gsz, wt16 + o.w_only, grad[c.src] + c.src_off, kHeadBufs[c.src].ch,
+                         written[c.src] ? 1 : 0, 0, st);
       if (rc != C2D_OK) return rc;
       written[c.src] = true;
     }
@@ -464,14 +574,8 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       written[X0] = true;
     }
   }
-  for (int i = 0; i < kNumHeadConvs; ++i) {
-    const HeadConv& c = kHeadConvs[i];
-    const HeadParamOff& o = pl.poff[i];
-    unfold_bn_kernel<<<cdiv(c.cout * 32, 256), 256, 0, st>>>(
-        params + o.w, params + o.gamma, params + o.mean, params + o.var, c.cout, c.k * c.k * c.cin, dwsf + o.w_only,
-        dshf + o.ch, dparams + o.w, dparams + o.gamma, dparams + o.beta, dparams + o.mean, dparams + o.var);
-    count_launch();
-  }
+  unfold_bn_all_kernel<<<dim3(cdiv(352, 8), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), dwsf, dshf, dparams);
+  count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
 }

@@ -25,29 +25,43 @@ struct HeadConv {
 
 constexpr int kNumHeadConvs = 19;
 static const HeadConv kHeadConvs[kNumHeadConvs] = {
+    // Sibling 1x1 convolutions that read the same tensor are adjacent: the bf16 path runs each group as
+    // ONE GEMM (forward: concatenated output columns; dgrad: concatenated reduction axis).
     {"Mixed_5a/Branch_0/Conv2d_0a_1x1", 1, 576, 128, 1, X0, 0, A1, 0, 7, 7},
-    {"Mixed_5a/Branch_0/Conv2d_1a_3x3", 3, 128, 192, 2, A1, 0, X1, 0, 7, 4},
     {"Mixed_5a/Branch_1/Conv2d_0a_1x1", 1, 576, 192, 1, X0, 0, A2, 0, 7, 7},
+    {"Mixed_5a/Branch_0/Conv2d_1a_3x3", 3, 128, 192, 2, A1, 0, X1, 0, 7, 4},
     {"Mixed_5a/Branch_1/Conv2d_0b_3x3", 3, 192, 256, 1, A2, 0, A3, 0, 7, 7},
     {"Mixed_5a/Branch_1/Conv2d_1a_3x3", 3, 256, 256, 2, A3, 0, X1, 192, 7, 4},
     // Mixed_5a/Branch_2/MaxPool_1a_3x3 (stride 2): X0 -> X1[448:1024)
     {"Mixed_5b/Branch_0/Conv2d_0a_1x1", 1, 1024, 352, 1, X1, 0, X2, 0, 4, 4},
     {"Mixed_5b/Branch_1/Conv2d_0a_1x1", 1, 1024, 192, 1, X1, 0, T1, 0, 4, 4},
-    {"Mixed_5b/Branch_1/Conv2d_0b_3x3", 3, 192, 320, 1, T1, 0, X2, 352, 4, 4},
     {"Mixed_5b/Branch_2/Conv2d_0a_1x1", 1, 1024, 160, 1, X1, 0, T2, 0, 4, 4},
+    {"Mixed_5b/Branch_1/Conv2d_0b_3x3", 3, 192, 320, 1, T1, 0, X2, 352, 4, 4},
     {"Mixed_5b/Branch_2/Conv2d_0b_3x3", 3, 160, 224, 1, T2, 0, T3, 0, 4, 4},
     {"Mixed_5b/Branch_2/Conv2d_0c_3x3", 3, 224, 224, 1, T3, 0, X2, 672, 4, 4},
     // Mixed_5b/Branch_3/AvgPool_0a_3x3: X1 -> P1
     {"Mixed_5b/Branch_3/Conv2d_0b_1x1", 1, 1024, 128, 1, P1, 0, X2, 896, 4, 4},
     {"Mixed_5c/Branch_0/Conv2d_0a_1x1", 1, 1024, 352, 1, X2, 0, X3, 0, 4, 4},
     {"Mixed_5c/Branch_1/Conv2d_0a_1x1", 1, 1024, 192, 1, X2, 0, U1, 0, 4, 4},
-    {"Mixed_5c/Branch_1/Conv2d_0b_3x3", 3, 192, 320, 1, U1, 0, X3, 352, 4, 4},
     {"Mixed_5c/Branch_2/Conv2d_0a_1x1", 1, 1024, 192, 1, X2, 0, U2, 0, 4, 4},
+    {"Mixed_5c/Branch_1/Conv2d_0b_3x3", 3, 192, 320, 1, U1, 0, X3, 352, 4, 4},
     {"Mixed_5c/Branch_2/Conv2d_0b_3x3", 3, 192, 224, 1, U2, 0, U3, 0, 4, 4},
     {"Mixed_5c/Branch_2/Conv2d_0c_3x3", 3, 224, 224, 1, U3, 0, X3, 672, 4, 4},
     // Mixed_5c/Branch_3/MaxPool_0a_3x3: X2 -> P2
     {"Mixed_5c/Branch_3/Conv2d_0b_1x1", 1, 1024, 128, 1, P2, 0, X3, 896, 4, 4},
 };
+
+// Sibling groups (first member, size); every other convolution is its own group.
+struct HeadGroup { int first, size; };
+static const HeadGroup kHeadGroups[3] = {{0, 2}, {5, 3}, {12, 3}};
+static inline int head_group_size(int first) {
+  for (int g = 0; g < 3; ++g) if (kHeadGroups[g].first == first) return kHeadGroups[g].size;
+  return 0;
+}
+static inline bool head_in_group_tail(int i) {   // member of a group but not its first element
+  for (int g = 0; g < 3; ++g) if (i > kHeadGroups[g].first && i < kHeadGroups[g].first + kHeadGroups[g].size) return true;
+  return false;
+}
 
 struct HeadParamOff {
   long long w, gamma, beta, mean, var;   // offsets (floats) into the packed parameter buffer
