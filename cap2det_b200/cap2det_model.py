@@ -144,7 +144,7 @@ class Model(ModelBase):
     feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
                            need_dx0=features_to_crop.requires_grad)
     # models/cap2det_model.py:79-88,190-197: the five FC layers as one product
-    logits_all = ops.fc_concat(feat, self.fc_weights, self.fc_biases).view(B, P, -1)
+    logits_all = ops.fc_concat(feat, self.fc_weights, self.fc_biases, compute_dtype=self._head_dtype).view(B, P, -1)
     midn_class_logits, midn_proposal_scores, midn_proba_r_given_c = ops.midn(
         logits_all, self._col_r, self._col_c, C, num_proposals)
     predictions = {}

@@ -251,8 +251,14 @@ int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* para
 }
 
 // ---- K4 fully connected -------------------------------------------------------------------
+size_t c2d_fc_workspace_bytes_bf16(int M, int D, int N);
+int c2d_fc_fwd_bf16(const float* x, int M, int D, const float* w, const float* b, int N, float* y, int ldy,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st);
+int c2d_fc_bwd_bf16(const float* x, int M, int D, const float* w, int N, const float* dy, int ldy, float* dx,
+                    float* dw, float* db, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 size_t c2d_fc_workspace_bytes(int M, int D, int N, int dtype) {
-  (void)M; (void)dtype;
+  if (dtype == C2D_BF16) return c2d_fc_workspace_bytes_bf16(M, D, N);
   // transposed weights [D][ld16(N)] for the data gradient
   size_t ldn = (size_t)((N + 15) / 16) * 16;
   return ldn * (size_t)D * sizeof(float) + 256;
@@ -268,10 +274,10 @@ __global__ void transpose_pad_kernel(const float* __restrict__ w, int N, int D, 
 
 int c2d_fc_fwd(const float* x, int M, int D, const float* w, const float* b, int N, float* y, int ldy, int dtype,
                void* workspace, size_t workspace_bytes, c2d_stream_t stream) {
-  (void)workspace; (void)workspace_bytes;
   C2D_CHECK_ARG(M >= 0 && D >= 16 && D % 16 == 0 && N >= 1 && ldy >= N, "fc_fwd: bad shape M=%d D=%d N=%d ldy=%d", M, D, N, ldy);
-  C2D_CHECK_ARG(dtype == C2D_F32, "fc_fwd: only fp32 compute is implemented for the FC layers");
+  C2D_CHECK_ARG(dtype == C2D_F32 || dtype == C2D_BF16, "fc_fwd: bad dtype %d", dtype);
   if (M == 0) return C2D_OK;
+  if (dtype == C2D_BF16) return c2d_fc_fwd_bf16(x, M, D, w, b, N, y, ldy, workspace, workspace_bytes, (cudaStream_t)stream);
   ConvGeom g{1, 1, 1, 1, 1, 1, 0, 0};
   launch_igemm<false, false>(x, D, D, g, w, b, y, ldy, M, N, (cudaStream_t)stream);
   C2D_LAUNCH_OK();
@@ -282,7 +288,9 @@ int c2d_fc_bwd(const float* x, int M, int D, const float* w, int N, const float*
                float* db, int dtype, void* workspace, size_t workspace_bytes, c2d_stream_t stream) {
   C2D_CHECK_ARG(M >= 0 && D >= 16 && D % 16 == 0 && N >= 1, "fc_bwd: bad shape");
   C2D_CHECK_ARG(ldy % 16 == 0 && ldy >= N, "fc_bwd: dy leading dimension must be a multiple of 16 (got %d)", ldy);
-  C2D_CHECK_ARG(dtype == C2D_F32, "fc_bwd: only fp32 compute is implemented for the FC layers");
+  C2D_CHECK_ARG(dtype == C2D_F32 || dtype == C2D_BF16, "fc_bwd: bad dtype %d", dtype);
+  if (dtype == C2D_BF16)
+    return c2d_fc_bwd_bf16(x, M, D, w, N, dy, ldy, dx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream);
   C2D_CHECK_ARG(workspace_bytes >= (size_t)ldy * D * sizeof(float), "fc_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (dw) C2D_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)N * D * sizeof(float), st));

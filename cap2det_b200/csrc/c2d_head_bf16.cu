@@ -184,6 +184,26 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
   return launch_conv(maps, mapB, p, st);
 }
 
+// Flat (1x1) forward whose weight matrix has only `w_rows` valid rows while the output is padded to
+// seg->cols columns (FC layers: N = 403 -> 416); the missing rows are TMA zero fill.  fp32 output.
+static int conv_fwd_tc_rows(const ConvDesc& c, const bf16* w16, int w_rows, const float* shift, const OutSeg* seg,
+                            cudaStream_t st) {
+  tc::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4], mapB;
+  set_segments(p, seg, 1);
+  p.num_n_tiles = pick_tiles(p.n_total, 128, &p.n_tile);
+  p.shift = shift; p.out_f32 = 1; p.relu = 0; p.accum = 0;
+  if (!make_map_flat(&mapB, w16, c.cin, w_rows, c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  const long long M = c.n;
+  p.taps = 1; p.tap_chunks[0] = (c.cin + 63) / 64; p.tap_koff[0] = 0; p.tap_map[0] = 0;
+  p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
+  p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
+  if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  return launch_conv(maps, mapB, p, st);
+}
+
 // Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).
 //   k == 1: up to 3 sources (a merged sibling group), wt16 = [cin][sum cols] bf16.
 //   k == 3: one source, wt16 = [cin][9][cols] bf16.
@@ -429,6 +449,81 @@ using namespace c2d;
 extern "C" {
 
 int c2d_has_tensor_core_head(void) { return 1; }
+
+// ---- K4 on the tensor cores: y = x . w^T + b as a flat conv GEMM (bf16 operands, fp32 accumulate/out) ----
+struct FcWs { bf16* x16; bf16* w16; bf16* wt16; bf16* dy16; float* bias; size_t total; };
+static FcWs fc_ws(void* base, int M, int D, int N) {
+  const size_t ld = (size_t)((N + 15) / 16) * 16;
+  FcWs w;
+  size_t off = 0;
+  char* p = (char*)base;
+  w.x16 = (bf16*)(p + off); off += align_up((size_t)M * D * 2, 1024);
+  w.w16 = (bf16*)(p + off); off += align_up((size_t)N * D * 2, 1024);
+  w.wt16 = (bf16*)(p + off); off += align_up((size_t)D * ld * 2, 1024);
+  w.dy16 = (bf16*)(p + off); off += align_up((size_t)M * ld * 2, 1024);
+  w.bias = (float*)(p + off); off += align_up(ld * 4, 1024);
+  w.total = off + 1024;
+  return w;
+}
+size_t c2d_fc_workspace_bytes_bf16(int M, int D, int N) { return fc_ws(nullptr, M, D, N).total; }
+
+__global__ void transpose_pad_bf16_kernel(const float* __restrict__ w, int N, int D, int ldn, bf16* __restrict__ wt) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;     // wt[d][n] = w[n][d], zero for n >= N
+  if (idx >= D * ldn) return;
+  int d = idx / ldn, n = idx - d * ldn;
+  wt[idx] = __float2bfloat16_rn(n < N ? w[(size_t)n * D + d] : 0.f);
+}
+
+int c2d_fc_fwd_bf16(const float* x, int M, int D, const float* w, const float* b, int N, float* y, int ldy,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int ld = (N + 15) / 16 * 16;
+  C2D_CHECK_ARG(D % 64 == 0 && ldy == ld, "fc_fwd(bf16): D must be a multiple of 64 and ldy == ld16(N)");
+  FcWs ws = fc_ws(workspace, M, D, N);
+  C2D_CHECK_ARG(workspace != nullptr && workspace_bytes >= ws.total, "fc_fwd(bf16): workspace too small");
+  launch_cast(x, ws.x16, (long long)M * D, st);
+  launch_cast(w, ws.w16, (long long)N * D, st);
+  C2D_CUDA_OK(cudaMemsetAsync(ws.bias, 0, ld * sizeof(float), st));
+  C2D_CUDA_OK(cudaMemcpyAsync(ws.bias, b, N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  ConvDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n = M; d.k = 1; d.stride = 1; d.hin = d.hout = 1; d.cin = D; d.cout = N; d.x = ws.x16; d.ldx = D;
+  OutSeg seg = {y, ld, ld};
+  // weight rows >= N are TMA zero fill (the tensor map has N rows) => padded output columns equal bias pad = 0
+  return conv_fwd_tc_rows(d, ws.w16, N, ws.bias, &seg, st);
+}
+
+int c2d_fc_bwd_bf16(const float* x, int M, int D, const float* w, int N, const float* dy, int ldy, float* dx,
+                    float* dw, float* db, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int ld = (N + 15) / 16 * 16;
+  C2D_CHECK_ARG(D % 64 == 0 && ldy == ld, "fc_bwd(bf16): D must be a multiple of 64 and ldy == ld16(N)");
+  FcWs ws = fc_ws(workspace, M, D, N);
+  C2D_CHECK_ARG(workspace != nullptr && workspace_bytes >= ws.total, "fc_bwd(bf16): workspace too small");
+  if (dw) C2D_CUDA_OK(cudaMemsetAsync(dw, 0, (size_t)N * D * sizeof(float), st));
+  if (db) C2D_CUDA_OK(cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st));
+  if (M == 0) return C2D_OK;
+  launch_cast(dy, ws.dy16, (long long)M * ld, st);
+  ConvDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n = M; d.k = 1; d.stride = 1; d.hin = d.hout = 1; d.cin = D; d.cout = N; d.x = ws.x16; d.ldx = D;
+  if (dx) {
+    transpose_pad_bf16_kernel<<<cdiv((long long)D * ld, 256), 256, 0, st>>>(w, N, D, ld, ws.wt16);
+    count_launch();
+    InSeg src = {ws.dy16, ld, ld};
+    int rc = conv_dgrad_tc(d, &src, 1, ws.wt16, dx, D, 0, 1, st);
+    if (rc != C2D_OK) return rc;
+  }
+  if (dw) {
+    launch_cast(x, ws.x16, (long long)M * D, st);
+    int rc = conv_wgrad_tc(d, ws.dy16, ld, dw, st);
+    if (rc != C2D_OK) return rc;
+  }
+  if (db) {
+    colsum_f32_kernel<<<dim3(cdiv(N, 32), cdiv(M, 512)), dim3(32, 8), 0, st>>>(dy, ldy, M, N, 512, db);
+    count_launch();
+  }
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
 
 static int check_conv_args(int n, int hin, int cin, int cout, int k, int stride, int ldx, int ldy) {
   C2D_CHECK_ARG(n >= 0 && (hin == 7 || hin == 4) && (k == 1 || k == 3), "conv_bf16: hin must be 7 or 4, k 1 or 3");

@@ -148,14 +148,19 @@ def _ld16(n):
 class _FcConcat(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, x, w, b):
+  def forward(ctx, x, w, b, dtype_code):
     require_cuda(x, w, b)
     M, D = x.shape
     N = w.shape[0]
     ld = _ld16(N)
     y = torch.zeros((M, ld), dtype=torch.float32, device=x.device)
-    call('c2d_fc_fwd', ptr(x), M, D, ptr(w), ptr(b), N, ptr(y), ld, capi.C2D_F32, None, 0, stream())
+    ws, nbytes = None, 0
+    if dtype_code == capi.C2D_BF16:
+      nbytes = capi.load().c2d_fc_workspace_bytes(M, D, N, dtype_code)
+      ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
+    call('c2d_fc_fwd', ptr(x), M, D, ptr(w), ptr(b), N, ptr(y), ld, dtype_code, ptr(ws), nbytes, stream())
     ctx.save_for_backward(x, w)
+    ctx.dtype_code = dtype_code
     return y
 
   @staticmethod
@@ -166,19 +171,20 @@ class _FcConcat(torch.autograd.Function):
     ld = _ld16(N)
     dy = dy.contiguous()
     lib = capi.load()
-    nbytes = lib.c2d_fc_workspace_bytes(M, D, N, capi.C2D_F32)
+    nbytes = lib.c2d_fc_workspace_bytes(M, D, N, ctx.dtype_code)
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=x.device)
     dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
     dw = torch.empty_like(w)
     db = torch.empty((N,), dtype=torch.float32, device=x.device)
-    call('c2d_fc_bwd', ptr(x), M, D, ptr(w), N, ptr(dy), ld, ptr(dx), ptr(dw), ptr(db), capi.C2D_F32, ptr(ws),
+    call('c2d_fc_bwd', ptr(x), M, D, ptr(w), N, ptr(dy), ld, ptr(dx), ptr(dw), ptr(db), ctx.dtype_code, ptr(ws),
          nbytes, stream())
-    return dx, dw, db
+    return dx, dw, db, None
 
 
-def fc_concat(x, w, b):
-  """x [M,D] . w [N,D]^T + b [N] -> y [M, ld16(N)] (columns >= N are zero padding)."""
-  return _FcConcat.apply(x.contiguous(), w.contiguous(), b.contiguous())
+def fc_concat(x, w, b, compute_dtype=torch.float32):
+  """x [M,D] . w [N,D]^T + b [N] -> y [M, ld16(N)] fp32 (columns >= N are zero padding).
+  compute_dtype bfloat16 runs the product on the tensor cores (bf16 operands, fp32 accumulation)."""
+  return _FcConcat.apply(x.contiguous(), w.contiguous(), b.contiguous(), capi.dtype_code(compute_dtype))
 
 
 # ---------------------------------------------------------------------------------------------

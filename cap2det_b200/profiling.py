@@ -93,9 +93,9 @@ def kernel_table(model, example, peaks, head_dtype):
 
   ncat = model.fc_weights.shape[0]
   fw, fb = model.fc_weights.detach(), model.fc_biases.detach()
-  ms = _time(lambda: ops.fc_concat(feat, fw, fb), flush)
+  ms = _time(lambda: ops.fc_concat(feat, fw, fb, compute_dtype=dt), flush)
   add('K4 fc_concat_fwd', ms, 'tensor', 2.0 * n * 1024 * ncat, head_peak)
-  logits = ops.fc_concat(feat, fw, fb).view(B, P, -1)
+  logits = ops.fc_concat(feat, fw, fb, compute_dtype=dt).view(B, P, -1)
   ms = _time(lambda: ops.midn(logits, 0, C, C, npr), flush)
   add('K5 midn_fwd', ms, 'hbm', B * (4 * P * C * 4 + C * 4), None)
   cl, sc, pr = ops.midn(logits, 0, C, C, npr)

@@ -145,3 +145,25 @@ def test_head_mixed5_bf16_forward_backward():
     assert cos(w, g32[name]['weights'].numpy()) > 0.98, name
     assert l2(dflat[off['gamma']:off['gamma'] + cout], tp[name]['gamma'].grad.numpy()) < 4e-2, (name, report)
     assert l2(dflat[off['beta']:off['beta'] + cout], tp[name]['beta'].grad.numpy()) < 4e-2, (name, report)
+
+
+def test_fc_concat_bf16_tensor_core():
+  from cap2det_b200 import ops
+  rng = np.random.default_rng(41)
+  M, D, N = 700, 1024, 403
+  x = _bf(rng.standard_normal((M, D)).astype(np.float32)).float().numpy()
+  w = _bf((rng.standard_normal((N, D)) * 0.05).astype(np.float32)).float().numpy()
+  b = rng.standard_normal(N).astype(np.float32)
+  dy = _bf(rng.standard_normal((M, N)).astype(np.float32)).float().numpy()
+  xd = torch.from_numpy(x).cuda().requires_grad_(True)
+  wd = torch.from_numpy(w).cuda().requires_grad_(True)
+  bd = torch.from_numpy(b).cuda().requires_grad_(True)
+  y = ops.fc_concat(xd, wd, bd, compute_dtype=torch.bfloat16)
+  assert y.shape == (M, 416) and torch.all(y[:, N:] == 0)
+  want = x.astype(np.float64) @ w.T.astype(np.float64) + b
+  assert rel_err(y[:, :N].detach().cpu().numpy(), want) < 1e-5          # bf16-exact operands, fp32 accumulation
+  dyp = torch.zeros_like(y); dyp[:, :N] = torch.from_numpy(dy).cuda()
+  y.backward(dyp)
+  assert rel_err(xd.grad.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64)) < 1e-5
+  assert rel_err(wd.grad.cpu().numpy(), dy.T.astype(np.float64) @ x.astype(np.float64)) < 1e-5
+  assert rel_err(bd.grad.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
