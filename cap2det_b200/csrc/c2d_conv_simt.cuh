@@ -366,16 +366,23 @@ __global__ void avgpool_dropout_fwd_kernel(const T* __restrict__ x, int hw, int 
   feat[(size_t)n * C + c] = s;
 }
 // dx[n, hw, c] = dfeat[n, c] * keep_mask / keep_prob / hw  (broadcast over hw)
+// With `y` (the forward activation) the ReLU backward mask is fused: dx = (y > 0) ? g : 0.
 template <typename T>
 __global__ void avgpool_dropout_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ keep_mask,
-                                           float keep_prob, int hw, int C, T* __restrict__ dx, int n_rois) {
+                                           float keep_prob, int hw, int C, T* __restrict__ dx, int n_rois,
+                                           const T* __restrict__ y = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (c >= C || n >= n_rois) return;
   float g = dfeat[(size_t)n * C + c];
   if (keep_mask) g = g / keep_prob * keep_mask[(size_t)n * C + c];
   g = g / (float)hw;
-  for (int i = 0; i < hw; ++i) Elem<T>::st(dx + ((size_t)n * hw + i) * C + c, g);
+  for (int i = 0; i < hw; ++i) {
+    const size_t idx = ((size_t)n * hw + i) * C + c;
+    float v = g;
+    if (y != nullptr && !(Elem<T>::ld(y + idx) > 0.f)) v = 0.f;
+    Elem<T>::st(dx + idx, v);
+  }
 }
 
 // ---- weight folding / unfolding ------------------------------------------------------------

@@ -22,7 +22,8 @@ constexpr int kStages = 4;
 constexpr int kStageABytes = 32768;              // 256 rows x 64 bf16
 constexpr int kStageBBytes = 16384;              // <= 128 rows x 64 bf16
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kWgThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
 constexpr int kMaxTaps = 9;
@@ -46,6 +47,9 @@ struct ConvGemmParams {
   void* seg_out[3];
   int seg_ld[3];
   int out_f32, relu, accum;
+  // fused ReLU backward: out = (y > 0) ? out : 0 for columns < mask_cols; y = bf16 activation with the
+  // same row mapping as the (single) output segment.  Used by the LAST writer of a gradient buffer.
+  const __nv_bfloat16* mask; int mask_ld; int mask_cols;
   // geometric output row mapping: pixel = (n*Hf + jy*sy + oy)*Wf + jx*sx + ox
   int Hf, Wf, sy, sx, oy, ox;
 };
@@ -74,7 +78,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 8); }
     fence_barrier_init();
     prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
   }
@@ -144,8 +148,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       }
     }
   } else {
-    // ===== epilogue (warps 2..5): TMEM -> registers -> (+shift, relu, accumulate) -> global =====
+    // ===== epilogue (warps 2..9): TMEM -> registers -> (+shift, relu, accumulate, mask) -> global =====
+    // Two warps per TMEM lane quarter, one per accumulator.  Global operands of the epilogue (previous
+    // value for accumulation, activation for the fused ReLU mask) are fetched four chunks ahead so that
+    // their latency overlaps the TMEM reads instead of serialising with them.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int a = (warp - 2) >> 2;           // accumulator (rows a*128 ..) handled by this warp
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -153,28 +161,49 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
-#pragma unroll 1
-      for (int a = 0; a < 2; ++a) {
-        const int r = a * 128 + q * 32 + lane;       // row inside the tile
-        long long orow = -1;
-        if (r < p.rows_per_tile) {
-          if (p.flat) {
-            long long m = (long long)mt * p.rows_per_tile + r;
-            if (m < p.m_total) orow = m;
-          } else {
-            int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
-            int n = mt * p.rois_per_tile + rn;
-            if (n < p.m_total) {
-              int jy = pos / p.box_w, jx = pos - jy * p.box_w;
-              orow = ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
-            }
+      const int r = a * 128 + q * 32 + lane;       // row inside the tile
+      long long orow = -1;
+      if (r < p.rows_per_tile) {
+        if (p.flat) {
+          long long m = (long long)mt * p.rows_per_tile + r;
+          if (m < p.m_total) orow = m;
+        } else {
+          int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
+          int n = mt * p.rois_per_tile + rn;
+          if (n < p.m_total) {
+            int jy = pos / p.box_w, jx = pos - jy * p.box_w;
+            orow = ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
           }
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * 128);
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * 128);
+      const bool bf16_rmw = !p.out_f32 && p.accum;
 #pragma unroll 1
-        for (int j = 0; j < p.n_tile; j += 16) {
+      for (int j0 = 0; j0 < p.n_tile; j0 += 64) {
+        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
+        uint4 oldv[4][2], mskv[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int col0 = nt * p.n_tile + j0 + u * 16;
+          const bool live = orow >= 0 && j0 + u * 16 < p.n_tile && col0 < p.n_total;
+          oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);
+          mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+          if (live && bf16_rmw) {     // single output segment when accumulating
+            const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
+            oldv[u][0] = *reinterpret_cast<const uint4*>(o);
+            oldv[u][1] = *reinterpret_cast<const uint4*>(o + 8);
+          }
+          if (live && p.mask != nullptr && col0 < p.mask_cols) {
+            const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
+            mskv[u][0] = *reinterpret_cast<const uint4*>(y);
+            mskv[u][1] = *reinterpret_cast<const uint4*>(y + 8);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 16;
           const int col0 = nt * p.n_tile + j;
-          if (col0 >= p.n_total) break;               // warp-uniform
+          if (j >= p.n_tile || col0 >= p.n_total) break;            // warp-uniform
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
@@ -209,15 +238,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               }
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
-              if (p.accum) {
-                uint4 o0 = *reinterpret_cast<uint4*>(o), o1 = *reinterpret_cast<uint4*>(o + 8);
-                const uint32_t old[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+              const uint32_t old[8] = {oldv[u][0].x, oldv[u][0].y, oldv[u][0].z, oldv[u][0].w,
+                                       oldv[u][1].x, oldv[u][1].y, oldv[u][1].z, oldv[u][1].w};
+              const uint32_t yy[8] = {mskv[u][0].x, mskv[u][0].y, mskv[u][0].z, mskv[u][0].w,
+                                      mskv[u][1].x, mskv[u][1].y, mskv[u][1].z, mskv[u][1].w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&old[i]);
-                  float2 ff = __bfloat1622float2(b2);
-                  f[2 * i] += ff.x; f[2 * i + 1] += ff.y;
-                }
+              for (int i = 0; i < 8; ++i) {
+                float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
+                float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]));
+                f[2 * i] += fo.x; f[2 * i + 1] += fo.y;                 // zeros unless accumulating
+                if (!(fy.x > 0.f)) f[2 * i] = 0.f;                      // ones unless masking
+                if (!(fy.y > 0.f)) f[2 * i + 1] = 0.f;
               }
               uint4 w0, w1;
               w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
@@ -244,11 +275,18 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
-// Weight gradient.  Work item = (tap, co tile of 128, ci tile <= 256, row split).
-//   A' (M = co, MN-major): two boxes [64 rows][64 co]          (16 KB / stage)
-//   B' (N = ci, MN-major): ceil(ci_tile/64) boxes [64 rows][64 ci]
-// Each k-step covers 64 reduction rows = one TMA box per 64-channel group.
+// Weight gradient.  Work item = (tap, co tile of 256, ci tile <= 240, row split).
+//   A' (M = co, MN-major): four boxes [64 rows][64 co]  (32 KB / stage, two accumulators of 128 co)
+//   B' (N = ci, MN-major): ceil(ci_tile/64) boxes [64 rows][64 ci]   (<= 32 KB / stage)
+// Each k-step covers 64 reduction rows.  The BN-shift gradient dshift[co] = sum_rows du[row, co] falls out
+// of the same pipeline as one extra N=16 MMA against a constant block of ones (items with tap 0, ci tile 0).
 // ---------------------------------------------------------------------------------------------
+constexpr int kWgStages = 3;
+constexpr int kWgStageBytes = 65536;
+constexpr int kWgOnesBytes = 8192;
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + kWgOnesBytes + 1024 + 256;
+constexpr int kWgOnesCol = 240;                 // TMEM column (per accumulator) of the ones product
+
 struct WgradParams {
   int taps;
   int tap_x[9], tap_y[9], tap_b[9], tap_map[9];
@@ -256,35 +294,46 @@ struct WgradParams {
   int rois_per_step;          // geometric: ROIs per k-step (box N dim)
   int total_steps;            // k-steps over the whole tensor
   int steps_per_split, num_splits;
-  int co_tiles, ci_tiles, ci_tile, ci_groups;   // ci_tile = UMMA N (<= 256), ci_groups = ceil(ci_tile/64)
+  int co_tiles, ci_tiles, ci_tile, ci_groups;   // co tile = 256; ci_tile = UMMA N (<= 240)
   int cout, cin;              // valid extents
   int taps_total;             // taps in the dW layout [co][taps_total][cin]
   float* dw;
+  float* dshift;              // [cout] or null
 };
 
-__global__ void __launch_bounds__(kTcThreads, 1)
+struct WgPipe {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t tmem_full;
+  uint64_t tmem_empty;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX0,
                 const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
                 const __grid_constant__ CUtensorMap mapX3, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  TcPipe* pipe = reinterpret_cast<TcPipe*>(smem + kStages * kStageBytes);
+  uint8_t* ones = smem + kWgStages * kWgStageBytes;
+  WgPipe* pipe = reinterpret_cast<WgPipe*>(ones + kWgOnesBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;          // bf16 1.0 pairs
+  fence_proxy_async();
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
-    mbar_init(&pipe->tmem_full[0], 1);
-    mbar_init(&pipe->tmem_empty[0], 4);
+    for (int s = 0; s < kWgStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
+    mbar_init(&pipe->tmem_full, 1);
+    mbar_init(&pipe->tmem_empty, 4);
     fence_barrier_init();
     prefetch_tmap(&mapY); prefetch_tmap(&mapX0);
   }
-  if (warp == 1) tmem_alloc(&pipe->tmem_base, 256);
+  if (warp == 1) tmem_alloc(&pipe->tmem_base, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = pipe->tmem_base;
-
   const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.num_splits;
-  const uint32_t stage_tx = (uint32_t)(2 + p.ci_groups) * 8192u;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -295,53 +344,73 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
         const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
         const int cot = rem % p.co_tiles; rem /= p.co_tiles;
         const int t = rem;
-        const CUtensorMap* mX = p.tap_map[t] == 0 ? &mapX0 : (p.tap_map[t] == 1 ? &mapX1 : (p.tap_map[t] == 2 ? &mapX2 : &mapX3));
+        const int a_groups = (p.cout - cot * 256) > 128 ? 4 : 2;
+        const uint32_t stage_tx = (uint32_t)(a_groups + p.ci_groups) * 8192u;
+        const int tm = p.tap_map[t];
+        const CUtensorMap* mX = tm == 0 ? &mapX0 : (tm == 1 ? &mapX1 : (tm == 2 ? &mapX2 : &mapX3));
         const int s0 = split * p.steps_per_split;
         const int s1 = min(p.total_steps, s0 + p.steps_per_split);
         for (int s = s0; s < s1; ++s) {
           mbar_wait(&pipe->empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kStageBytes;
-          uint8_t* sB = sA + 16384;        // A' = 2 groups x 8 KB, B' = up to 4 groups x 8 KB
+          uint8_t* sA = smem + stage * kWgStageBytes;
+          uint8_t* sB = sA + 32768;
           mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
-          for (int g = 0; g < 2; ++g) {
-            if (p.flat) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 128 + g * 64, s * 64, 0, 0);
-            else tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 128 + g * 64, 0, 0, s * p.rois_per_step);
+          for (int g = 0; g < a_groups; ++g) {
+            if (p.flat) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, s * 64, 0, 0);
+            else tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, 0, 0, s * p.rois_per_step);
           }
           for (int g = 0; g < p.ci_groups; ++g) {
             const int c0 = cit * p.ci_tile + g * 64;
             if (p.flat) tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, s * 64, 0, 0);
             else tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, p.tap_x[t], p.tap_y[t], s * p.rois_per_step);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, p.ci_tile, 1, 1);
+    const uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 1);
+    const uint32_t s_ones = smem_u32(ones);
     int stage = 0; uint32_t phase = 0; uint32_t tphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      const int split = item % p.num_splits;
+      int rem = item;
+      const int split = rem % p.num_splits; rem /= p.num_splits;
+      const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
+      const int cot = rem % p.co_tiles; rem /= p.co_tiles;
+      const int t = rem;
+      const bool two = (p.cout - cot * 256) > 128;
+      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
       const int s0 = split * p.steps_per_split;
       const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-      mbar_wait(&pipe->tmem_empty[0], tphase ^ 1);
+      mbar_wait(&pipe->tmem_empty, tphase ^ 1);
       tc_fence_after();
       for (int s = s0; s < s1; ++s) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sB = sA + 16384;
+          const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
+          const uint32_t sB = sA + 32768;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)     // 16 reduction rows per MMA = two 8-row swizzle atoms
-            umma_f16(tmem_base, make_smem_desc(sA + kk * 2048, 8192, 1024), make_smem_desc(sB + kk * 2048, 8192, 1024),
-                     idesc, (s > s0 || kk > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {   // 16 reduction rows per MMA = two 8-row swizzle atoms
+            const uint32_t acc = (s > s0 || kk > 0) ? 1u : 0u;
+            const uint64_t bdesc = make_smem_desc(sB + kk * 2048, 8192, 1024);
+            const uint64_t a0 = make_smem_desc(sA + kk * 2048, 8192, 1024);
+            const uint64_t a1 = make_smem_desc(sA + 16384 + kk * 2048, 8192, 1024);
+            umma_f16(tmem_base, a0, bdesc, idesc, acc);
+            if (two) umma_f16(tmem_base + 256, a1, bdesc, idesc, acc);
+            if (want_shift) {
+              const uint64_t odesc = make_smem_desc(s_ones + kk * 2048, 8192, 1024);
+              umma_f16(tmem_base + kWgOnesCol, a0, odesc, idesc_ones, acc);
+              if (two) umma_f16(tmem_base + 256 + kWgOnesCol, a1, odesc, idesc_ones, acc);
+            }
+          }
           umma_commit(&pipe->empty[stage]);
-          if (s == s1 - 1) umma_commit(&pipe->tmem_full[0]);
+          if (s == s1 - 1) umma_commit(&pipe->tmem_full);
         }
         __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
-      if (s1 <= s0 && lane == 0) umma_commit(&pipe->tmem_full[0]);   // empty split (never scheduled by the host)
       tphase ^= 1;
     }
   } else {
@@ -349,31 +418,42 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       int rem = item;
-      const int split = rem % p.num_splits; rem /= p.num_splits;
+      rem /= p.num_splits;
       const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
       const int cot = rem % p.co_tiles; rem /= p.co_tiles;
       const int t = rem;
-      const int s0 = split * p.steps_per_split;
-      const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-      mbar_wait(&pipe->tmem_full[0], tphase);
+      const bool two = (p.cout - cot * 256) > 128;
+      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
+      mbar_wait(&pipe->tmem_full, tphase);
       tc_fence_after();
-      const int co = cot * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int a = 0; a < (two ? 2 : 1); ++a) {
+        const int co = cot * 256 + a * 128 + q * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
 #pragma unroll 1
-      for (int j = 0; j < p.ci_tile; j += 16) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + j, v);
-        tmem_ld_wait();
-        if (co < p.cout && s1 > s0) {
-          float* o = p.dw + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin + cit * p.ci_tile + j;
+        for (int j = 0; j < p.ci_tile; j += 16) {
+          if (cit * p.ci_tile + j >= p.cin) break;
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + j, v);
+          tmem_ld_wait();
+          if (co < p.cout) {   // cin and ci_tile are multiples of 16 => the whole chunk is in range, 16 B aligned
+            float4* o = reinterpret_cast<float4*>(p.dw + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin +
+                                                  cit * p.ci_tile + j);
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (cit * p.ci_tile + j + i < p.cin) atomicAdd(o + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 4; ++i)     // red.global.add.v4.f32: one L2 atomic per 16 bytes
+              atomicAdd(o + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+          }
+        }
+        if (want_shift) {
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + kWgOnesCol, v);
+          tmem_ld_wait();
+          if (co < p.cout) atomicAdd(p.dshift + co, __uint_as_float(v[0]));
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pipe->tmem_empty[0]);
+      if (lane == 0) mbar_arrive(&pipe->tmem_empty);
       tphase ^= 1;
     }
   }
@@ -381,7 +461,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

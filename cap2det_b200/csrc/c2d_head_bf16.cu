@@ -83,7 +83,7 @@ static bool g_attr_done = false;
 static int tc_prepare() {
   if (!g_attr_done) {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
-    C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
     g_attr_done = true;
   }
   return C2D_OK;
@@ -208,7 +208,7 @@ static int conv_fwd_tc_rows(const ConvDesc& c, const bf16* w16, int w_rows, cons
 //   k == 1: up to 3 sources (a merged sibling group), wt16 = [cin][sum cols] bf16.
 //   k == 3: one source, wt16 = [cin][9][cols] bf16.
 static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16* wt16, void* dx, int lddx,
-                         int accum, int out_f32, cudaStream_t st) {
+                         int accum, int out_f32, cudaStream_t st, const bf16* mask = nullptr, int mask_cols = 0) {
   const int taps = c.k * c.k;
   int ksum = 0;
   for (int s = 0; s < nsrc; ++s) ksum += srcs[s].cols;
@@ -218,6 +218,7 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
   set_segments(base, &oseg, 1);
   base.num_n_tiles = pick_tiles(c.cin, 128, &base.n_tile);
   base.shift = nullptr; base.out_f32 = out_f32; base.relu = 0; base.accum = accum;
+  base.mask = mask; base.mask_ld = lddx; base.mask_cols = mask_cols;
   CUtensorMap maps[4], mapB;
   if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, base.n_tile)) return C2D_ERR_CUDA;
   if (c.k == 1) {
@@ -287,16 +288,17 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
 }
 
 // Weight gradient: dw[cout][k*k][cin] (fp32, pre-zeroed by the caller) += du^T * x.
-static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaStream_t st) {
+static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaStream_t st,
+                         float* dshift = nullptr) {
   int rc = tc_prepare();
   if (rc != C2D_OK) return rc;
   tc::WgradParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap mapY, mapX[4];
   p.taps = c.k * c.k; p.taps_total = p.taps;
-  p.cout = c.cout; p.cin = c.cin; p.dw = dw;
-  p.co_tiles = (c.cout + 127) / 128;
-  p.ci_tiles = pick_tiles(c.cin, 256, &p.ci_tile);
+  p.cout = c.cout; p.cin = c.cin; p.dw = dw; p.dshift = dshift;
+  p.co_tiles = (c.cout + 255) / 256;
+  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile);
   p.ci_groups = (p.ci_tile + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
@@ -332,7 +334,7 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
     }
   }
   const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  int splits = (2 * num_sms() + base_items - 1) / base_items;
+  int splits = num_sms() / base_items;       // one wave of items; every extra split is a dW-sized atomic pass
   if (splits < 1) splits = 1;
   if (splits > p.total_steps) splits = p.total_steps;
   p.steps_per_split = (p.total_steps + splits - 1) / splits;
@@ -340,7 +342,7 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
   const int items = base_items * p.num_splits;
   if (items <= 0 || p.total_steps <= 0) return C2D_OK;
   const int grid = items < num_sms() ? items : num_sms();
-  tc::wgrad_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -621,7 +623,10 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
   C2D_CUDA_OK(cudaMemsetAsync(dwsf, 0, pl.w_only_total * sizeof(float), st));
   C2D_CUDA_OK(cudaMemsetAsync(dshf, 0, pl.ch_total * sizeof(float), st));
   bool written[NBUF] = {false};
-  avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n);
+  // every gradient buffer is written as du = dy * (y > 0) by its LAST writer (fused ReLU backward);
+  // the BN-shift gradients come out of the weight-gradient kernel (ones-vector MMA).
+  avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n,
+                                                                              act[X3]);
   count_launch();
   written[X3] = true;
   for (int i = kNumHeadConvs - 1; i >= 0; --i) {
@@ -630,11 +635,9 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
     const int M = n * c.hout * c.hout;
     bf16* dy = grad[c.dst] + c.dst_off;
     const int ldd = kHeadBufs[c.dst].ch;
-    relu_bwd_colsum_kernel<bf16><<<dim3(cdiv(c.cout / 4, 32), cdiv(M, 512)), dim3(32, 8), 0, st>>>(
-        dy, act[c.dst] + c.dst_off, ldd, M, c.cout, 512, dshf + o.ch);
-    count_launch();
+    (void)M;
     ConvDesc d = head_conv_desc(i, n, act);
-    int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st);
+    int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st, dshf + o.ch);
     if (rc != C2D_OK) return rc;
     // data gradient: a sibling group is reduced by ONE GEMM once its first (lowest) member is reached
     if (!head_in_group_tail(i) && !(c.src == X0 && dx0 == nullptr)) {
@@ -645,8 +648,17 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
         const HeadConv& cj = kHeadConvs[i + j];
         srcs[j].du = grad[cj.dst] + cj.dst_off; srcs[j].ld = kHeadBufs[cj.dst].ch; srcs[j].cols = cj.cout;
       }
+      // the destination is complete after this GEMM (pool backward into X1/X2 runs BEFORE the merged
+      // sibling dgrad), so it applies the ReLU mask of the convolutions that produced the buffer:
+      // all columns for conv outputs, [0,448) for X1 (the rest is the max-pool branch), none for X0 / P*.
+      const bf16* mask = nullptr;
+      int mask_cols = 0;
+      if (c.src != X0 && c.src != P1 && c.src != P2) {
+        mask = act[c.src] + c.src_off;
+        mask_cols = c.src == X1 ? 448 : kHeadBufs[c.src].ch;
+      }
       rc = conv_dgrad_tc(d, srcs, gsz, wt16 + o.w_only, grad[c.src] + c.src_off, kHeadBufs[c.src].ch,
-                         written[c.src] ? 1 : 0, 0, st);
+                         written[c.src] ? 1 : 0, 0, st, mask, mask_cols);
       if (rc != C2D_OK) return rc;
       written[c.src] = true;
     }
