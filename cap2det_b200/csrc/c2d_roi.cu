@@ -106,17 +106,31 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
   return k;
 }
 
-__device__ __forceinline__ void scatter_one(float* __restrict__ dimg, const RoiCoords& sc, int cy, int cx, int Wf,
-                                            int Cf, int ch, float g) {
-  if (g == 0.0f || !(sc.valid[0][cy] & sc.valid[1][cx])) return;
+// Scatter the gradient of crop sample (cy,cx) for a channel quad: g holds the 4 channel gradients,
+// already zeroed for the channels whose max-pool arg-max is a different sample.  One 16-byte
+// red.global.add.v4.f32 per corner instead of four scalar atomics (the SM issues ~1 atomic lane-op
+// per cycle regardless of width, so the vector form is what bounds this kernel).
+__device__ __forceinline__ void scatter_quad(float* __restrict__ dimg, const RoiCoords& sc, int cy, int cx, int Wf,
+                                             int Cf, int ch, float4 g) {
+  if (!(sc.valid[0][cy] & sc.valid[1][cx])) return;
+  if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) return;
   int t = sc.lo[0][cy], b = sc.hi[0][cy], l = sc.lo[1][cx], r = sc.hi[1][cx];
   float yl = sc.lerp[0][cy], xl = sc.lerp[1][cx];
-  float dtop = (1.0f - yl) * g, dbot = yl * g;   // CropAndResizeGradImage order
+  // CropAndResizeGradImage order: dtop = (1-yl)*g ; dTL = (1-xl)*dtop ...
+  float wt = 1.0f - yl, wl = 1.0f - xl;
   float w;
-  w = (1.0f - xl) * dtop; if (w != 0.f) atomicAdd(dimg + ((size_t)t * Wf + l) * Cf + ch, w);
-  w = xl * dtop;          if (w != 0.f) atomicAdd(dimg + ((size_t)t * Wf + r) * Cf + ch, w);
-  w = (1.0f - xl) * dbot; if (w != 0.f) atomicAdd(dimg + ((size_t)b * Wf + l) * Cf + ch, w);
-  w = xl * dbot;          if (w != 0.f) atomicAdd(dimg + ((size_t)b * Wf + r) * Cf + ch, w);
+  w = wl * wt;
+  if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(dimg + ((size_t)t * Wf + l) * Cf + ch),
+                          make_float4(wl * (wt * g.x), wl * (wt * g.y), wl * (wt * g.z), wl * (wt * g.w)));
+  w = xl * wt;
+  if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(dimg + ((size_t)t * Wf + r) * Cf + ch),
+                          make_float4(xl * (wt * g.x), xl * (wt * g.y), xl * (wt * g.z), xl * (wt * g.w)));
+  w = wl * yl;
+  if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(dimg + ((size_t)b * Wf + l) * Cf + ch),
+                          make_float4(wl * (yl * g.x), wl * (yl * g.y), wl * (yl * g.z), wl * (yl * g.w)));
+  w = xl * yl;
+  if (w != 0.f) atomicAdd(reinterpret_cast<float4*>(dimg + ((size_t)b * Wf + r) * Cf + ch),
+                          make_float4(xl * (yl * g.x), xl * (yl * g.y), xl * (yl * g.z), xl * (yl * g.w)));
 }
 
 template <typename GradT>
@@ -142,15 +156,15 @@ roi_crop_maxpool_bwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int 
     float4 v01 = roi_sample(img4, sc, 2 * py, 2 * px + 1, Wf, C4, q);
     float4 v10 = roi_sample(img4, sc, 2 * py + 1, 2 * px, Wf, C4, q);
     float4 v11 = roi_sample(img4, sc, 2 * py + 1, 2 * px + 1, Wf, C4, q);
-    int k;
-    k = argmax4(v00.x, v01.x, v10.x, v11.x);
-    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 0, g.x);
-    k = argmax4(v00.y, v01.y, v10.y, v11.y);
-    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 1, g.y);
-    k = argmax4(v00.z, v01.z, v10.z, v11.z);
-    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 2, g.z);
-    k = argmax4(v00.w, v01.w, v10.w, v11.w);
-    scatter_one(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q + 3, g.w);
+    const int kx = argmax4(v00.x, v01.x, v10.x, v11.x);
+    const int ky = argmax4(v00.y, v01.y, v10.y, v11.y);
+    const int kz = argmax4(v00.z, v01.z, v10.z, v11.z);
+    const int kw = argmax4(v00.w, v01.w, v10.w, v11.w);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 gk = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f, kw == k ? g.w : 0.f);
+      scatter_quad(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q, gk);
+    }
   }
 }
 
