@@ -290,6 +290,8 @@ def main():
       out['kernels'] = table['kernels']
       out['roofline'] = table['dominant']
       out['hbm_group'] = table['hbm_group']
+      if head_dtype == 'bf16':
+        out['roofline'] = profiling.dominant_kernel_roofline(lambda i: run_resident(i), peaks, ROOT)
     if not args.no_cpu_baseline and world == 1:
       out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=96, steps=2)
     print(json.dumps(out))

@@ -21,6 +21,9 @@ SIGNATURES = {
     'c2d_version': (_c_int, []),
     'c2d_last_error': (ctypes.c_char_p, []),
     'c2d_has_tensor_core_head': (_c_int, []),
+    'c2d_profile_enable': (None, [_c_int]),
+    'c2d_profile_reset': (None, []),
+    'c2d_profile_read': (_c_int, [_c_int, _p, _p, _p]),
     'c2d_launch_count': (_c_ll, []),
     'c2d_reset_launch_count': (None, []),
     'c2d_box_area': (_c_int, [_p, _c_int, _p, _p]),

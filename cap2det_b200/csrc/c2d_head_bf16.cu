@@ -3,6 +3,8 @@
 // Reference semantics: models/utils.py:165-177 (see c2d_head.cu for the BN folding algebra).
 #include <cuda.h>
 
+#include <vector>
+
 #include "c2d_conv_simt.cuh"
 #include "c2d_gemm_tc.cuh"
 #include "c2d_head_plan.h"
@@ -79,6 +81,23 @@ static int pick_tiles(int n, int max_tile, int* tile) {
   }
 }
 
+// ---- optional per-launch timing of the tensor-core kernels (bench.py roofline of the dominant kernel) ----
+struct ProfRec { cudaEvent_t a, b; int kind; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  cudaStream_t st; int idx;
+  ProfScope(cudaStream_t s, int kind, double flops) : st(s), idx(-1) {
+    if (!g_prof_on || g_prof.size() >= 8192) return;
+    ProfRec r; r.kind = kind; r.flops = flops;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+    idx = (int)g_prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
+};
+
 static bool g_attr_done = false;
 static int tc_prepare() {
   if (!g_attr_done) {
@@ -109,12 +128,14 @@ struct ConvDesc {
   bf16* y; int ldy;              // output activation [n, hout, hout, cout]   (forward)
 };
 
-static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::ConvGemmParams& p, cudaStream_t st) {
+static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::ConvGemmParams& p, cudaStream_t st,
+                       double flops = 0.0) {
   int rc = tc_prepare();
   if (rc != C2D_OK) return rc;
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
   if (grid <= 0) return C2D_OK;
+  ProfScope prof(st, 0, flops);
   tc::conv_gemm_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
   count_launch();
   C2D_LAUNCH_OK();
@@ -181,7 +202,7 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
       }
     }
   }
-  return launch_conv(maps, mapB, p, st);
+  return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * (double)taps * c.cin * cout);
 }
 
 // Flat (1x1) forward whose weight matrix has only `w_rows` valid rows while the output is padded to
@@ -201,7 +222,7 @@ static int conv_fwd_tc_rows(const ConvDesc& c, const bf16* w16, int w_rows, cons
   p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
   if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
   maps[1] = maps[2] = maps[3] = maps[0];
-  return launch_conv(maps, mapB, p, st);
+  return launch_conv(maps, mapB, p, st, 2.0 * M * (double)c.cin * w_rows);
 }
 
 // Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).
@@ -233,7 +254,7 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
       koff += srcs[s].cols;
     }
     for (int s = nsrc; s < 4; ++s) maps[s] = maps[0];
-    return launch_conv(maps, mapB, p, st);
+    return launch_conv(maps, mapB, p, st, 2.0 * M * (double)ksum * c.cin);
   }
   const bf16* du = srcs[0].du;
   const int lddu = srcs[0].ld;
@@ -253,7 +274,7 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
     for (int t = 0; t < 9; ++t) {
       p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_koff[t] = t * c.cout; p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
     }
-    return launch_conv(maps, mapB, p, st);
+    return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * 9.0 * c.cin * c.cout);
   }
   // stride 2 (7x7 <- 4x4): one launch per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
   for (int py = 0; py < 2; ++py)
@@ -281,7 +302,8 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
           ++t;
         }
       p.taps = t;
-      int rc = launch_conv(maps, mapB, p, st);
+      // the four parity classes together do the work of one stride-2 convolution (9 taps x 16 outputs)
+      int rc = launch_conv(maps, mapB, p, st, 2.0 * c.n * (double)(nh * nw) * t * c.cin * c.cout);
       if (rc != C2D_OK) return rc;
     }
   return C2D_OK;
@@ -342,6 +364,7 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
   const int items = base_items * p.num_splits;
   if (items <= 0 || p.total_steps <= 0) return C2D_OK;
   const int grid = items < num_sms() ? items : num_sms();
+  ProfScope prof(st, 1, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout);
   tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
   count_launch();
   C2D_LAUNCH_OK();
@@ -451,6 +474,28 @@ using namespace c2d;
 extern "C" {
 
 int c2d_has_tensor_core_head(void) { return 1; }
+
+void c2d_profile_enable(int on) { g_prof_on = on != 0; }
+void c2d_profile_reset(void) {
+  for (size_t i = 0; i < g_prof.size(); ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
+  g_prof.clear();
+}
+int c2d_profile_read(int kind, double* ms_total, long long* launches, double* flops_total) {
+  C2D_CHECK_ARG(kind == 0 || kind == 1, "profile_read: kind 0 = conv_gemm_tc_kernel, 1 = wgrad_tc_kernel");
+  double ms = 0.0, fl = 0.0;
+  long long n = 0;
+  for (size_t i = 0; i < g_prof.size(); ++i) {
+    if (g_prof[i].kind != kind) continue;
+    C2D_CUDA_OK(cudaEventSynchronize(g_prof[i].b));
+    float t = 0.f;
+    C2D_CUDA_OK(cudaEventElapsedTime(&t, g_prof[i].a, g_prof[i].b));
+    ms += t; fl += g_prof[i].flops; ++n;
+  }
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  if (flops_total) *flops_total = fl;
+  return C2D_OK;
+}
 
 // ---- K4 on the tensor cores: y = x . w^T + b as a flat conv GEMM (bf16 operands, fp32 accumulate/out) ----
 struct FcWs { bf16* x16; bf16* w16; bf16* wt16; bf16* dy16; float* bias; size_t total; };

@@ -117,3 +117,45 @@ def kernel_table(model, example, peaks, head_dtype):
              frac=dominant['frac'], traffic=None, kernel=dominant['kernel'],
              peak_source='%s (MEASURED_PEAKS.json)' % peaks['source'] if peaks['source'] == 'measured' else 'fallback')
   return dict(kernels=rows, dominant=dom, hbm_group=hbm_group)
+
+
+def dominant_kernel_roofline(run_step, peaks, root, steps=3):
+  """Roofline of the single kernel that takes most of the step, measured LIVE: every launch of the two
+  tensor-core kernels is bracketed by CUDA events on its own stream inside real training steps
+  (c2d_profile_*).  achieved = algorithmic FLOPs (2*rows*K*N, padding excluded) / summed launch time;
+  peak = sustained bf16 figure of MEASURED_PEAKS.json (kernels timed inside a long step).
+  `traffic` = average DRAM bytes per launch from the committed ncu --set full capture, if present."""
+  import ctypes
+  import json
+  import os
+  from cap2det_b200 import capi
+  lib = capi.load()
+  for i in range(2):
+    run_step(i)
+  torch.cuda.synchronize()
+  lib.c2d_profile_reset()
+  lib.c2d_profile_enable(1)
+  for i in range(steps):
+    run_step(i)
+  torch.cuda.synchronize()
+  lib.c2d_profile_enable(0)
+  stats = {}
+  for kind, name in ((0, 'conv_gemm_tc_kernel'), (1, 'wgrad_tc_kernel')):
+    ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    capi.check(lib.c2d_profile_read(kind, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+    stats[name] = dict(ms_per_step=ms.value / steps, launches_per_step=n.value / steps, flops_per_step=fl.value / steps)
+  lib.c2d_profile_reset()
+  name = max(stats, key=lambda k: stats[k]['ms_per_step'])
+  st = stats[name]
+  achieved = st['flops_per_step'] / (st['ms_per_step'] * 1e-3) / 1e12
+  peak = peaks['bf16_tflops_sustained']
+  traffic = None
+  path = os.path.join(root, 'profiles', 'ncu_tc_traffic.json')
+  if os.path.exists(path):
+    with open(path) as fid:
+      traffic = json.load(fid).get(name, {}).get('dram_bytes_per_launch')
+  return dict(bound='tensor', kernel=name, achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+              traffic=traffic, avg_launch_ms=st['ms_per_step'] / max(st['launches_per_step'], 1),
+              launches_per_step=st['launches_per_step'], algorithmic_flops_per_launch=st['flops_per_step'] /
+              max(st['launches_per_step'], 1), peak_source='%s bf16_tflops_sustained (MEASURED_PEAKS.json)' % peaks['source'],
+              per_kernel=stats)

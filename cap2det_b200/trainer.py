@@ -8,7 +8,8 @@ larger-batch run of the reference; the reference itself trains with an asynchron
 (train_wsod.sh:46-88), which has no deterministic equivalent.
 """
 import torch
-import torch.distributed as dist
+
+from cap2det_b200 import dist as c2d_dist
 
 from cap2det_b200 import capi
 from cap2det_b200.capi import call, ptr, stream
@@ -73,8 +74,7 @@ class TrainStep(object):
       total = v if total is None else total + v
     total.backward()
     if self.world_size > 1:
-      for v in model.get_variables_to_train():
-        dist.all_reduce(v.grad, op=dist.ReduceOp.SUM)
+      c2d_dist.allreduce_sum([v.grad for v in model.get_variables_to_train()])
     self.opt.step(grad_scale=1.0 / self.world_size)
     self.last_loss_dict = loss_dict
     return total.detach() + self.regularization_loss()

@@ -49,6 +49,12 @@ const char* c2d_last_error(void);
 /* Kernels launched by this library since the last reset (all threads). */
 /* 1 when the bf16 tcgen05/TMEM/TMA head path is compiled into this library. */
 int c2d_has_tensor_core_head(void);
+/* Optional per-launch CUDA-event timing of the two tensor-core kernels (kind 0 = conv_gemm_tc_kernel,
+ * 1 = wgrad_tc_kernel) on the stream they are launched on; read returns the sums since the last reset
+ * (duration, launches, algorithmic FLOPs = 2*rows*K*N of the convolutions, padding excluded). */
+void c2d_profile_enable(int on);
+void c2d_profile_reset(void);
+int c2d_profile_read(int kind, double* ms_total, long long* launches, double* flops_total);
 long long c2d_launch_count(void);
 void c2d_reset_launch_count(void);
 
