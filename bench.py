@@ -195,7 +195,9 @@ def main():
   assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
   torch.cuda.set_device(local_rank)
   if world > 1:
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    import datetime
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
+                            timeout=datetime.timedelta(seconds=120))
   dev = torch.device('cuda', local_rank)
   capi.load()
   head_dtype = args.head_dtype
@@ -282,16 +284,21 @@ def main():
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                       ms_per_step=e2e_ms / args.steps))
+  peaks = load_peaks()
+  dominant = None
+  if not args.no_kernel_table and head_dtype == 'bf16':
+    # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
+    from cap2det_b200 import profiling
+    dominant = profiling.dominant_kernel_roofline(lambda i: run_resident(i), peaks, ROOT)
   if rank == 0:
-    peaks = load_peaks()
     if not args.no_kernel_table:
       from cap2det_b200 import profiling
       table = profiling.kernel_table(model, resident[0], peaks, head_dtype)
       out['kernels'] = table['kernels']
       out['roofline'] = table['dominant']
       out['hbm_group'] = table['hbm_group']
-      if head_dtype == 'bf16':
-        out['roofline'] = profiling.dominant_kernel_roofline(lambda i: run_resident(i), peaks, ROOT)
+      if dominant is not None:
+        out['roofline'] = dominant
     if not args.no_cpu_baseline and world == 1:
       out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=96, steps=2)
     print(json.dumps(out))
