@@ -275,6 +275,238 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a cluster of two CTAs (one SM pair) computes one 256 x n_tile tile.
+// Each CTA stages ITS 128 rows of A and ITS half of the B tile (n_tile/2 weight rows); the leader CTA
+// issues tcgen05.mma.cta_group::2 (M = 256), which reads both halves, so per SM the shared-memory read
+// traffic per MMA and the TMA fill traffic are halved w.r.t. two independent 128-row MMAs -- the
+// single-CTA kernel above is bound by shared-memory bandwidth (128 B/clk/SM), not by the tensor pipe.
+// Accumulators: 128 lanes x n_tile columns per CTA, double buffered (2 x 256 TMEM columns).
+//   params: rows_per_tile / rois_per_tile / a_box_bytes are PER CTA (<= 128 rows); n_tile <= 256, % 32 == 0.
+// ---------------------------------------------------------------------------------------------
+constexpr int k2Stages = 6;
+constexpr int k2StageABytes = 16384;
+constexpr int k2StageBBytes = 16384;
+constexpr int k2StageBytes = k2StageABytes + k2StageBBytes;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+
+struct Tc2Pipe {
+  uint64_t full[k2Stages];
+  uint64_t empty[k2Stages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                     const __grid_constant__ CUtensorMap mapB, const ConvGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Tc2Pipe* pipe = reinterpret_cast<Tc2Pipe*>(smem + k2Stages * k2StageBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < k2Stages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 16); }
+    fence_barrier_init();
+    prefetch_tmap(&mapA0); prefetch_tmap(&mapB);
+  }
+  if (warp == 1) tmem_alloc_2cta(&pipe->tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                // barriers of BOTH CTAs initialised before any remote signal
+  tc_fence_after();
+  const uint32_t tmem_base = pipe->tmem_base;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int n_half = p.n_tile >> 1;
+  const uint32_t pair_tx = 2u * ((uint32_t)p.a_box_bytes + (uint32_t)n_half * 128u);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs; completion is credited to the leader's full barrier) =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+        for (int t = 0; t < p.taps; ++t) {
+          const int tm = p.tap_map[t];
+          const CUtensorMap* mA = tm == 0 ? &mapA0 : (tm == 1 ? &mapA1 : (tm == 2 ? &mapA2 : &mapA3));
+          const int nchunks = p.tap_chunks[t], koff = p.tap_koff[t], tx = p.tap_x[t], ty = p.tap_y[t];
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&pipe->empty[stage], phase ^ 1);
+            uint8_t* sA = smem + stage * k2StageBytes;
+            uint8_t* sB = sA + k2StageABytes;
+            if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
+            if (p.flat) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, (2 * mt + (int)rank) * p.rows_per_tile, 0, 0);
+            else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, (2 * mt + (int)rank) * p.rois_per_tile);
+            tma_load_4d_2cta(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile + (int)rank * n_half, 0, 0);
+            if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, p.n_tile, 0, 0);
+      int ksteps = 0;
+      for (int t = 0; t < p.taps; ++t) ksteps += p.tap_chunks[t];
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&pipe->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&pipe->full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_u32(smem + stage * k2StageBytes);
+            const uint32_t sB = sA + k2StageABytes;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_f16_2cta(acc0, make_smem_desc(sA + kk * 32, 16, 1024), make_smem_desc(sB + kk * 32, 16, 1024), idesc,
+                            (ks > 0 || kk > 0) ? 1u : 0u);
+            umma_commit_2cta(&pipe->empty[stage], 3);                 // frees the slot in BOTH CTAs
+            if (ks == ksteps - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
+          }
+          __syncwarp();
+          if (++stage == k2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (warps 2..9 of both CTAs): this CTA's 128 rows; warp group g handles half the columns =====
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int col_lo = g * n_half, col_hi = col_lo + n_half;
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
+      const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&pipe->tmem_full[as], aphase);
+      tc_fence_after();
+      const int r = q * 32 + lane;                  // row inside this CTA's half tile
+      long long orow = -1;
+      if (r < p.rows_per_tile) {
+        if (p.flat) {
+          long long m = (long long)(2 * mt + (int)rank) * p.rows_per_tile + r;
+          if (m < p.m_total) orow = m;
+        } else {
+          int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
+          int n = (2 * mt + (int)rank) * p.rois_per_tile + rn;
+          if (n < p.m_total) {
+            int jy = pos / p.box_w, jx = pos - jy * p.box_w;
+            orow = ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
+          }
+        }
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+      const bool bf16_rmw = !p.out_f32 && p.accum;
+#pragma unroll 1
+      for (int j0 = col_lo; j0 < col_hi; j0 += 64) {
+        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
+        uint4 oldv[4][2], mskv[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int col0 = nt * p.n_tile + j0 + u * 16;
+          const bool live = orow >= 0 && j0 + u * 16 < col_hi && col0 < p.n_total;
+          oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);
+          mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+          if (live && bf16_rmw) {
+            const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
+            oldv[u][0] = *reinterpret_cast<const uint4*>(o);
+            oldv[u][1] = *reinterpret_cast<const uint4*>(o + 8);
+          }
+          if (live && p.mask != nullptr && col0 < p.mask_cols) {
+            const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
+            mskv[u][0] = *reinterpret_cast<const uint4*>(y);
+            mskv[u][1] = *reinterpret_cast<const uint4*>(y + 8);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 16;
+          const int col0 = nt * p.n_tile + j;
+          if (j >= col_hi || col0 >= p.n_total) break;              // warp-uniform
+          uint32_t v[16];
+          tmem_ld_32x16(taddr + j, v);
+          tmem_ld_wait();
+          if (orow >= 0) {
+            int sgm = 0;
+            if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
+            if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+            const int scol = col0 - p.seg_begin[sgm];
+            const long long ooff = orow * p.seg_ld[sgm] + scol;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.shift != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 s4 = __ldg(sp + i);
+                f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            if (p.out_f32) {
+              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.seg_out[sgm]) + ooff);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float4 w = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                if (p.accum) { float4 old = o[i]; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+                o[i] = w;
+              }
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
+              const uint32_t old[8] = {oldv[u][0].x, oldv[u][0].y, oldv[u][0].z, oldv[u][0].w,
+                                       oldv[u][1].x, oldv[u][1].y, oldv[u][1].z, oldv[u][1].w};
+              const uint32_t yy[8] = {mskv[u][0].x, mskv[u][0].y, mskv[u][0].z, mskv[u][0].w,
+                                      mskv[u][1].x, mskv[u][1].y, mskv[u][1].z, mskv[u][1].w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
+                float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]));
+                f[2 * i] += fo.x; f[2 * i + 1] += fo.y;
+                if (!(fy.x > 0.f)) f[2 * i] = 0.f;
+                if (!(fy.y > 0.f)) f[2 * i + 1] = 0.f;
+              }
+              uint4 w0, w1;
+              w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
+              w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
+              w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
+              w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
+              *reinterpret_cast<uint4*>(o) = w0;
+              *reinterpret_cast<uint4*>(o + 8) = w1;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);      // 8 warps x 2 CTAs arrive on the leader
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // the peer must not exit / free TMEM while the pair is busy
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Weight gradient.  Work item = (tap, co tile of 256, ci tile <= 240, row split).
 //   A' (M = co, MN-major): four boxes [64 rows][64 co]  (32 KB / stage, two accumulators of 128 co)
 //   B' (N = ci, MN-major): ceil(ci_tile/64) boxes [64 rows][64 ci]   (<= 32 KB / stage)

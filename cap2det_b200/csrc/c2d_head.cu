@@ -72,11 +72,11 @@ static int head_fwd_f32(const float* x0, int n, const float* params, const HeadP
   auto pool = [&](int which) {
     dim3 blk(128);
     if (which == 0) {        // Mixed_5a Branch_2 MaxPool_1a_3x3 /2 : X0 -> X1[448:1024)
-      pool3x3_fwd_kernel<float, 7, 2, 0><<<dim3(cdiv(576, 128), n), blk, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
+      pool3x3_fwd_kernel<float, 7, 2, 0><<<dim3(cdiv(576 / 2, 128), n), blk, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
     } else if (which == 1) { // Mixed_5b Branch_3 AvgPool_0a_3x3 : X1 -> P1
-      pool3x3_fwd_kernel<float, 4, 1, 1><<<dim3(cdiv(1024, 128), n), blk, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
+      pool3x3_fwd_kernel<float, 4, 1, 1><<<dim3(cdiv(1024 / 2, 128), n), blk, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
     } else {                 // Mixed_5c Branch_3 MaxPool_0a_3x3 : X2 -> P2
-      pool3x3_fwd_kernel<float, 4, 1, 0><<<dim3(cdiv(1024, 128), n), blk, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
+      pool3x3_fwd_kernel<float, 4, 1, 0><<<dim3(cdiv(1024 / 2, 128), n), blk, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
     }
     count_launch();
   };
@@ -121,15 +121,15 @@ static int head_bwd_f32(const float* x0, int n, const float* params, const HeadP
   auto pool_bwd = [&](int which) {
     dim3 blk(128);
     if (which == 2) {   // X2 <- P2 (first writer of grad[X2])
-      pool3x3_bwd_kernel<float, 4, 1, 0, false><<<dim3(cdiv(1024, 128), n), blk, 0, st>>>(
+      pool3x3_bwd_kernel<float, 4, 1, 0, false><<<dim3(cdiv(1024 / 2, 128), n), blk, 0, st>>>(
           act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
       written[X2] = true;
     } else if (which == 1) {   // X1 <- P1 (first writer of grad[X1])
-      pool3x3_bwd_kernel<float, 4, 1, 1, false><<<dim3(cdiv(1024, 128), n), blk, 0, st>>>(
+      pool3x3_bwd_kernel<float, 4, 1, 1, false><<<dim3(cdiv(1024 / 2, 128), n), blk, 0, st>>>(
           act[X1], 1024, grad[P1], 1024, grad[X1], 1024, n, 1024);
       written[X1] = true;
     } else {                   // X0 <- X1[448:1024) (first writer of grad[X0])
-      pool3x3_bwd_kernel<float, 7, 2, 0, false><<<dim3(cdiv(576, 128), n), blk, 0, st>>>(
+      pool3x3_bwd_kernel<float, 7, 2, 0, false><<<dim3(cdiv(576 / 2, 128), n), blk, 0, st>>>(
           act[X0], 576, grad[X1] + 448, 1024, grad[X0], 576, n, 576);
       written[X0] = true;
     }

@@ -3,6 +3,7 @@
 // Reference semantics: models/utils.py:165-177 (see c2d_head.cu for the BN folding algebra).
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <vector>
 
 #include "c2d_conv_simt.cuh"
@@ -71,14 +72,24 @@ static bool make_map_parity(CUtensorMap* m, const bf16* base, long long C, long 
   return make_map(m, base + (py * 7 + px) * ld, d, es, b);
 }
 
-static int pick_tiles(int n, int max_tile, int* tile) {
+static int pick_tiles(int n, int max_tile, int* tile, int align = 16) {
   int t = (n + max_tile - 1) / max_tile;
   while (true) {
     int w = (n + t - 1) / t;
-    w = (w + 15) / 16 * 16;
+    w = (w + align - 1) / align * align;
     if (w <= max_tile) { *tile = w; return t; }
     ++t;
   }
+}
+
+// The 2-CTA (cta_group::2) kernel is used whenever a CTA's 128-row half tile is well filled: flat rows and
+// 4x4 / parity-class geometries.  7x7 stride-1 boxes (49 rows per ROI) keep the single-CTA 245-row tile.
+static bool use_2cta(bool flat, int pos_per_roi) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("C2D_DISABLE_2CTA"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (disabled) return false;
+  if (flat) return true;
+  return (128 / pos_per_roi) * pos_per_roi >= 112;
 }
 
 // ---- optional per-launch timing of the tensor-core kernels (bench.py roofline of the dominant kernel) ----
@@ -102,6 +113,7 @@ static bool g_attr_done = false;
 static int tc_prepare() {
   if (!g_attr_done) {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
     g_attr_done = true;
   }
@@ -129,14 +141,20 @@ struct ConvDesc {
 };
 
 static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::ConvGemmParams& p, cudaStream_t st,
-                       double flops = 0.0) {
+                       double flops, bool two) {
   int rc = tc_prepare();
   if (rc != C2D_OK) return rc;
   int tiles = p.num_m_tiles * p.num_n_tiles;
-  int grid = tiles < num_sms() ? tiles : num_sms();
-  if (grid <= 0) return C2D_OK;
+  if (tiles <= 0) return C2D_OK;
   ProfScope prof(st, 0, flops);
-  tc::conv_gemm_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  if (two) {
+    int pairs = num_sms() / 2;
+    if (tiles < pairs) pairs = tiles;
+    tc::conv_gemm_tc2_kernel<<<2 * pairs, tc::kTcThreads, tc::k2SmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  } else {
+    int grid = tiles < num_sms() ? tiles : num_sms();
+    tc::conv_gemm_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+  }
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -156,6 +174,25 @@ static void set_segments(tc::ConvGemmParams& p, const OutSeg* segs, int nseg) {
   p.n_total = begin;
 }
 
+// ---- tile geometry (single-CTA 256-row tiles or 2-CTA pairs of 128-row half tiles) ----------------
+static void set_flat_tiles(tc::ConvGemmParams& p, long long M, bool two) {
+  const int rows = two ? 128 : 256;
+  p.flat = 1; p.rows_per_tile = rows; p.a_box_bytes = rows * 128;
+  p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
+}
+static void set_geo_tiles(tc::ConvGemmParams& p, int n, int pos_per_roi, int box_w, bool two) {
+  p.flat = 0; p.pos_per_roi = pos_per_roi; p.box_w = box_w;
+  p.rois_per_tile = (two ? 128 : 256) / pos_per_roi;
+  p.rows_per_tile = p.rois_per_tile * pos_per_roi;
+  p.a_box_bytes = p.rows_per_tile * 128;
+  const int per_tile = p.rois_per_tile * (two ? 2 : 1);
+  p.num_m_tiles = (n + per_tile - 1) / per_tile; p.m_total = n;
+}
+static void set_n_tiles(tc::ConvGemmParams& p, bool two) {
+  p.num_n_tiles = two ? pick_tiles(p.n_total, 256, &p.n_tile, 32) : pick_tiles(p.n_total, 128, &p.n_tile, 16);
+}
+static int b_box_rows(const tc::ConvGemmParams& p, bool two) { return two ? p.n_tile / 2 : p.n_tile; }
+
 // Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift) with the output columns split over `segs`.
 //   w16: [sum cols][k*k][cin] bf16 (K-major); shift: [sum cols] or null.
 static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
@@ -164,26 +201,22 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4], mapB;
   const int taps = c.k * c.k;
+  const bool two = use_2cta(c.k == 1, c.hout * c.hout);
   set_segments(p, segs, nseg);
   const int cout = p.n_total;
-  p.num_n_tiles = pick_tiles(cout, 128, &p.n_tile);
+  set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, cout, (long long)taps * c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, cout, (long long)taps * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const int chunks = (c.cin + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
     p.taps = 1; p.tap_chunks[0] = chunks; p.tap_koff[0] = 0; p.tap_map[0] = 0;
-    p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
-    p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
-    if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
+    set_flat_tiles(p, M, two);
+    if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, p.rows_per_tile)) return C2D_ERR_CUDA;
     maps[1] = maps[2] = maps[3] = maps[0];
   } else {
-    p.taps = 9; p.flat = 0;
-    p.pos_per_roi = c.hout * c.hout; p.box_w = c.hout;
-    p.rois_per_tile = 256 / p.pos_per_roi;
-    p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
-    p.a_box_bytes = p.rows_per_tile * 128;
-    p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+    p.taps = 9;
+    set_geo_tiles(p, c.n, c.hout * c.hout, c.hout, two);
     p.Hf = p.Wf = c.hout; p.sy = p.sx = 1; p.oy = p.ox = 0;
     for (int t = 0; t < 9; ++t) { p.tap_chunks[t] = chunks; p.tap_koff[t] = t * c.cin; }
     if (c.stride == 1) {
@@ -202,7 +235,7 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
       }
     }
   }
-  return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * (double)taps * c.cin * cout);
+  return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * (double)taps * c.cin * cout, two);
 }
 
 // Flat (1x1) forward whose weight matrix has only `w_rows` valid rows while the output is padded to
@@ -212,17 +245,17 @@ static int conv_fwd_tc_rows(const ConvDesc& c, const bf16* w16, int w_rows, cons
   tc::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4], mapB;
+  const bool two = use_2cta(true, 1);
   set_segments(p, seg, 1);
-  p.num_n_tiles = pick_tiles(p.n_total, 128, &p.n_tile);
+  set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = 1; p.relu = 0; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, c.cin, w_rows, c.cin, p.n_tile)) return C2D_ERR_CUDA;
+  if (!make_map_flat(&mapB, w16, c.cin, w_rows, c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const long long M = c.n;
   p.taps = 1; p.tap_chunks[0] = (c.cin + 63) / 64; p.tap_koff[0] = 0; p.tap_map[0] = 0;
-  p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
-  p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
-  if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, 256)) return C2D_ERR_CUDA;
+  set_flat_tiles(p, M, two);
+  if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, p.rows_per_tile)) return C2D_ERR_CUDA;
   maps[1] = maps[2] = maps[3] = maps[0];
-  return launch_conv(maps, mapB, p, st, 2.0 * M * (double)c.cin * w_rows);
+  return launch_conv(maps, mapB, p, st, 2.0 * M * (double)c.cin * w_rows, two);
 }
 
 // Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).
@@ -237,36 +270,36 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
   memset(&base, 0, sizeof(base));
   OutSeg oseg = {dx, lddx, c.cin};
   set_segments(base, &oseg, 1);
-  base.num_n_tiles = pick_tiles(c.cin, 128, &base.n_tile);
   base.shift = nullptr; base.out_f32 = out_f32; base.relu = 0; base.accum = accum;
   base.mask = mask; base.mask_ld = lddx; base.mask_cols = mask_cols;
   CUtensorMap maps[4], mapB;
-  if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, base.n_tile)) return C2D_ERR_CUDA;
   if (c.k == 1) {
     tc::ConvGemmParams p = base;
+    const bool two = use_2cta(true, 1);
+    set_n_tiles(p, two);
+    if (!make_map_flat(&mapB, wt16, ksum, c.cin, ksum, b_box_rows(p, two))) return C2D_ERR_CUDA;
     const long long M = (long long)c.n * c.hin * c.hin;
-    p.taps = nsrc; p.flat = 1; p.rows_per_tile = 256; p.a_box_bytes = 256 * 128;
-    p.num_m_tiles = (int)((M + 255) / 256); p.m_total = (int)M;
+    p.taps = nsrc;
+    set_flat_tiles(p, M, two);
     int koff = 0;
     for (int s = 0; s < nsrc; ++s) {
-      if (!make_map_flat(&maps[s], srcs[s].du, srcs[s].cols, M, srcs[s].ld, 256)) return C2D_ERR_CUDA;
+      if (!make_map_flat(&maps[s], srcs[s].du, srcs[s].cols, M, srcs[s].ld, p.rows_per_tile)) return C2D_ERR_CUDA;
       p.tap_chunks[s] = (srcs[s].cols + 63) / 64; p.tap_koff[s] = koff; p.tap_map[s] = s;
       koff += srcs[s].cols;
     }
     for (int s = nsrc; s < 4; ++s) maps[s] = maps[0];
-    return launch_conv(maps, mapB, p, st, 2.0 * M * (double)ksum * c.cin);
+    return launch_conv(maps, mapB, p, st, 2.0 * M * (double)ksum * c.cin, two);
   }
   const bf16* du = srcs[0].du;
   const int lddu = srcs[0].ld;
   const int chunks = (c.cout + 63) / 64;
   if (c.stride == 1) {
     tc::ConvGemmParams p = base;
-    p.taps = 9; p.flat = 0;
-    p.pos_per_roi = c.hin * c.hin; p.box_w = c.hin;
-    p.rois_per_tile = 256 / p.pos_per_roi;
-    p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
-    p.a_box_bytes = p.rows_per_tile * 128;
-    p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+    const bool two = use_2cta(false, c.hin * c.hin);
+    set_n_tiles(p, two);
+    if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, b_box_rows(p, two))) return C2D_ERR_CUDA;
+    p.taps = 9;
+    set_geo_tiles(p, c.n, c.hin * c.hin, c.hin, two);
     p.Hf = p.Wf = c.hin; p.sy = p.sx = 1; p.oy = p.ox = 0;
     if (!make_map_nhwc(&maps[0], du, c.cout, c.hout, c.n, lddu, c.hout, c.hout, p.rois_per_tile)) return C2D_ERR_CUDA;
     maps[1] = maps[2] = maps[3] = maps[0];
@@ -274,19 +307,17 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
     for (int t = 0; t < 9; ++t) {
       p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_koff[t] = t * c.cout; p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
     }
-    return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * 9.0 * c.cin * c.cout);
+    return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * 9.0 * c.cin * c.cout, two);
   }
   // stride 2 (7x7 <- 4x4): one launch per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       tc::ConvGemmParams p = base;
       const int nh = py ? 3 : 4, nw = px ? 3 : 4;
-      p.flat = 0;
-      p.pos_per_roi = nh * nw; p.box_w = nw;
-      p.rois_per_tile = 256 / p.pos_per_roi;
-      p.rows_per_tile = p.rois_per_tile * p.pos_per_roi;
-      p.a_box_bytes = p.rows_per_tile * 128;
-      p.num_m_tiles = (c.n + p.rois_per_tile - 1) / p.rois_per_tile; p.m_total = c.n;
+      const bool two = use_2cta(false, nh * nw);
+      set_n_tiles(p, two);
+      if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, b_box_rows(p, two))) return C2D_ERR_CUDA;
+      set_geo_tiles(p, c.n, nh * nw, nw, two);
       p.Hf = p.Wf = 7; p.sy = p.sx = 2; p.oy = py; p.ox = px;
       if (!make_map_nhwc(&maps[0], du, c.cout, 4, c.n, lddu, nw, nh, p.rois_per_tile)) return C2D_ERR_CUDA;
       maps[1] = maps[2] = maps[3] = maps[0];
@@ -303,7 +334,7 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
         }
       p.taps = t;
       // the four parity classes together do the work of one stride-2 convolution (9 taps x 16 outputs)
-      int rc = launch_conv(maps, mapB, p, st, 2.0 * c.n * (double)(nh * nw) * t * c.cin * c.cout);
+      int rc = launch_conv(maps, mapB, p, st, 2.0 * c.n * (double)(nh * nw) * t * c.cin * c.cout, two);
       if (rc != C2D_OK) return rc;
     }
   return C2D_OK;
@@ -622,15 +653,15 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
     if (i == 5) {
-      pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
+      pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
       count_launch();
     }
     if (i == 11) {
-      pool3x3_fwd_kernel<bf16, 4, 1, 1><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
+      pool3x3_fwd_kernel<bf16, 4, 1, 1><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
       count_launch();
     }
     if (i == 18) {
-      pool3x3_fwd_kernel<bf16, 4, 1, 0><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
+      pool3x3_fwd_kernel<bf16, 4, 1, 0><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
       count_launch();
     }
     if (head_in_group_tail(i)) continue;          // computed together with the first member of its group
@@ -708,19 +739,19 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       written[c.src] = true;
     }
     if (i == 18) {
-      pool3x3_bwd_kernel<bf16, 4, 1, 0, false><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(
+      pool3x3_bwd_kernel<bf16, 4, 1, 0, false><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(
           act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
       count_launch();
       written[X2] = true;
     }
     if (i == 11) {
-      pool3x3_bwd_kernel<bf16, 4, 1, 1, false><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(
+      pool3x3_bwd_kernel<bf16, 4, 1, 1, false><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(
           act[X1], 1024, grad[P1], 1024, grad[X1], 1024, n, 1024);
       count_launch();
       written[X1] = true;
     }
     if (i == 5 && dx0 != nullptr) {
-      pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576, 128), n), 128, 0, st>>>(
+      pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(
           act[X0], 576, grad[X1] + 448, 1024, grad[X0], 576, n, 576);
       count_launch();
       written[X0] = true;

@@ -10,7 +10,7 @@
 namespace c2d {
 
 constexpr int kColsPerCta = 8;    // classes per CTA
-constexpr int kRowLanes = 32;     // row lanes per class
+constexpr int kRowLanes = 128;    // row lanes per class (P ~ 2000 rows => ~16 rows per thread per pass)
 constexpr int kColThreads = kColsPerCta * kRowLanes;
 
 // Deterministic cross-lane reduction for the (8 classes x 32 row lanes) CTA shape.
