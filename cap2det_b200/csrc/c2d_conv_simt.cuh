@@ -335,11 +335,18 @@ __global__ void pool3x3_bwd_kernel(const T* __restrict__ x, int ldx, const T* __
               if (t.y > by || iy_ < 0) { by = t.y; iy_ = iy * HIN + ix; }
             }
           }
+        // only the (statically known) taps of this window can hold the arg-max
 #pragma unroll
-        for (int i = 0; i < HIN * HIN; ++i) {
-          g[i].x += (i == ix_) ? go.x : 0.f;
-          g[i].y += (i == iy_) ? go.y : 0.f;
-        }
+        for (int dyy = 0; dyy < 3; ++dyy)
+#pragma unroll
+          for (int dxx = 0; dxx < 3; ++dxx) {
+            const int iy = oy * STRIDE + dyy - 1, ix = ox * STRIDE + dxx - 1;
+            if (iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) {
+              const int i = iy * HIN + ix;
+              g[i].x += (i == ix_) ? go.x : 0.f;
+              g[i].y += (i == iy_) ? go.y : 0.f;
+            }
+          }
       } else {
         int cnt = 0;
 #pragma unroll

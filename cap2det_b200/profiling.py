@@ -140,7 +140,7 @@ def dominant_kernel_roofline(run_step, peaks, root, steps=3):
   torch.cuda.synchronize()
   lib.c2d_profile_enable(0)
   stats = {}
-  for kind, name in ((0, 'conv_gemm_tc_kernel'), (1, 'wgrad_tc_kernel')):
+  for kind, name in ((0, 'conv_gemm_tc_kernel'), (1, 'wgrad_tc_kernel')):   # kind 0 = conv_gemm_tc2_kernel (2-CTA) + conv_gemm_tc_kernel
     ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     capi.check(lib.c2d_profile_read(kind, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
     stats[name] = dict(ms_per_step=ms.value / steps, launches_per_step=n.value / steps, flops_per_step=fl.value / steps)
