@@ -167,3 +167,51 @@ def test_fc_concat_bf16_tensor_core():
   assert rel_err(xd.grad.cpu().numpy(), dy.astype(np.float64) @ w.astype(np.float64)) < 1e-5
   assert rel_err(wd.grad.cpu().numpy(), dy.T.astype(np.float64) @ x.astype(np.float64)) < 1e-5
   assert rel_err(bd.grad.cpu().numpy(), dy.astype(np.float64).sum(0)) < 1e-5
+
+
+def test_model_train_step_bf16_against_fp32_oracle():
+  """Whole model with head_dtype=bfloat16 (K1 bf16 output, tcgen05 head + FC): scores / losses within 2e-2 of
+  the fp32 oracle; extracted labels stay exact."""
+  import tempfile
+  from cap2det_b200 import builder, config, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  from oracle import labels as olabels
+  from tests import oracle_model
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  C, K, B, P = 20, 3, 2, 40
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=True)
+  model._head_dtype = torch.bfloat16
+  rng = np.random.default_rng(51)
+  fmap = synthetic.make_feature_map(rng, B, 160, 208)
+  props = synthetic.make_proposals(rng, B, P, 160, 208)
+  npr = np.array([P, P - 7], np.int32)
+  props[1, P - 7:] = 0
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+  ex = {F.features_to_crop: torch.from_numpy(fmap).cuda(), F.num_proposals: torch.from_numpy(npr).cuda(),
+        F.proposals: torch.from_numpy(props).cuda(), F.object_texts: texts,
+        F.dropout_keep_mask: torch.from_numpy(keep).cuda()}
+  pred = model.build_prediction(ex, postprocess=True)
+  loss = model.build_loss(pred, ex)
+  sum(loss.values()).backward()
+  model.raise_if_assert_failed()
+  labels = olabels.groundtruth_extract(classes, texts)
+  np.testing.assert_array_equal(model.last_labels.cpu().numpy(), labels)
+  want = oracle_model.forward_backward(
+      fmap, props, npr, labels, oracle_model.head_params_from_named(model.named_variables()),
+      model.fc_weights.detach().cpu().numpy(), model.fc_biases.detach().cpu().numpy(), keep, 0.5, C, K, 0.6, 1.0, 0.5,
+      want_dfmap=False)
+  assert rel_err(pred['_proposal_features'].detach().cpu().numpy(), want['feat']) < RTOL_BF16
+  assert rel_err(pred['midn_class_logits'].detach().cpu().numpy(), want['class_logits']) < RTOL_BF16
+  assert rel_err(pred['midn_proba_r_given_c'].detach().cpu().numpy(), want['proba']) < RTOL_BF16
+  assert abs(float(loss['midn_cross_entropy_loss']) - want['loss']['midn_cross_entropy_loss']) <= \
+      RTOL_BF16 * abs(want['loss']['midn_cross_entropy_loss'])
+  assert torch.isfinite(model.head_params.grad).all() and torch.isfinite(model.fc_weights.grad).all()
+  assert pred['detection_boxes_at_3'].shape == (B, 300, 4)

@@ -574,3 +574,67 @@ def test_full_size_properties_P2000():
     cls = c_.cpu().numpy()[bi, :nn_[bi]]
     for cc in np.unique(cls):
       assert (cls == cc).sum() <= 100
+
+
+# ---------------------------------------------------------------------------------------------
+def test_adagrad_l2_update_matches_reference_formulas():
+  """train/trainer.py:85-146 + core/training_utils.py:45-50: slim l2_regularizer (scale * sum(w^2) / 2),
+  gradient multiplier, tf.train.AdagradOptimizer (accum0 = 0.1, w -= lr * g / sqrt(accum))."""
+  from cap2det_b200.capi import call, ptr, stream
+  rng = np.random.default_rng(24)
+  n = 100003
+  w = rng.standard_normal(n).astype(np.float32)
+  g = rng.standard_normal(n).astype(np.float32)
+  acc = np.full(n, 0.1, np.float32)
+  lr, mult, l2 = 0.01, 0.5, 1e-3
+  wd, ad, gd = dev(w.copy()), dev(acc.copy()), dev(g)
+  for _ in range(2):
+    call('c2d_adagrad_update', ptr(wd), ptr(ad), ptr(gd), n, lr, mult, l2, stream())
+  w64, a64 = w.astype(np.float64), acc.astype(np.float64)
+  for _ in range(2):
+    gg = g.astype(np.float64) * mult + l2 * w64
+    a64 = a64 + gg * gg
+    w64 = w64 - lr * gg / np.sqrt(a64)
+  assert rel_err(wd.cpu().numpy(), w64) < RTOL_F32
+  assert rel_err(ad.cpu().numpy(), a64) < RTOL_F32
+  out = torch.empty((), dtype=torch.float32, device='cuda')
+  call('c2d_l2_loss', ptr(dev(w)), n, 1e-6, ptr(out), stream())
+  assert abs(float(out) - 1e-6 * float((w.astype(np.float64) ** 2).sum()) / 2) <= 1e-5 * abs(float(out))
+
+
+def test_train_step_updates_variables_like_the_oracle():
+  """One TrainStep (forward, losses, backward, Adagrad with L2 on the FC weights) against the oracle's
+  gradients pushed through the reference update formulas."""
+  from cap2det_b200 import synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  C, K, B, P = 20, 3, 1, 12
+  model = _build_model(C, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)))
+  rng = np.random.default_rng(25)
+  fmap = synthetic.make_feature_map(rng, B, 128, 160)
+  props = synthetic.make_proposals(rng, B, P, 128, 160)
+  npr = np.array([P], np.int32)
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+  fc_w0 = model.fc_weights.detach().cpu().numpy().copy()
+  fc_b0 = model.fc_biases.detach().cpu().numpy().copy()
+  named0 = oracle_model.head_params_from_named(model.named_variables())
+  step = trainer.TrainStep(model, learning_rate=0.01)
+  ex = {F.features_to_crop: dev(fmap), F.num_proposals: dev(npr), F.proposals: dev(props), F.object_texts: texts,
+        F.dropout_keep_mask: dev(keep)}
+  total = step(ex)
+  labels = olabels.groundtruth_extract(classes, texts)
+  want = oracle_model.forward_backward(fmap, props, npr, labels, named0, fc_w0, fc_b0, keep, 0.5, C, K, 0.6, 1.0, 0.5,
+                                       want_dfmap=False)
+  l2 = 1e-6
+  loss_sum = sum(want['loss'].values()) + l2 * float((fc_w0.astype(np.float64) ** 2).sum()) / 2
+  assert abs(float(total) - loss_sum) <= 2e-5 * abs(loss_sum)
+  g = want['dfc_w'].astype(np.float64) + l2 * fc_w0
+  w_new = fc_w0 - 0.01 * g / np.sqrt(0.1 + g * g)
+  np.testing.assert_allclose(model.fc_weights.detach().cpu().numpy(), w_new, rtol=2e-4, atol=2e-6)
+  gb = want['dfc_b'].astype(np.float64)
+  np.testing.assert_allclose(model.fc_biases.detach().cpu().numpy(), fc_b0 - 0.01 * gb / np.sqrt(0.1 + gb * gb),
+                             rtol=2e-4, atol=2e-6)
