@@ -697,5 +697,183 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 2-CTA weight gradient: a CTA pair owns one (tap, 256 co, ci tile <= 240, row split) item.  Each CTA stages
+// ITS 128 output channels of dY (two [64 rows][64 co] boxes) and ITS half of the ci tile of X (ceil(N/2/64)
+// boxes); the leader issues tcgen05.mma.cta_group::2 with both operands MN-major.  Per SM this halves the
+// L2 -> shared-memory traffic of wgrad_tc_kernel for the same MMA work; the accumulator (128 lanes x N
+// columns per CTA, + 16 columns for the ones product) is double buffered so the red.add epilogue of one item
+// overlaps the main loop of the next.
+// ---------------------------------------------------------------------------------------------
+constexpr int kWg2Stages = 6;
+constexpr int kWg2StageBytes = 32768;             // A' 16 KB + B' <= 16 KB
+constexpr int kWg2SmemBytes = kWg2Stages * kWg2StageBytes + kWgOnesBytes + 1024 + 256;
+
+struct Wg2Pipe {
+  uint64_t full[kWg2Stages];
+  uint64_t empty[kWg2Stages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
+wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX0,
+                 const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
+                 const __grid_constant__ CUtensorMap mapX3, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + kWg2Stages * kWg2StageBytes;
+  Wg2Pipe* pipe = reinterpret_cast<Wg2Pipe*>(ones + kWgOnesBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;          // bf16 1.0 pairs
+  fence_proxy_async();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWg2Stages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 8); }
+    fence_barrier_init();
+    prefetch_tmap(&mapY); prefetch_tmap(&mapX0);
+  }
+  if (warp == 1) tmem_alloc_2cta(&pipe->tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = pipe->tmem_base;
+  const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.num_splits;
+  const int n_half = p.ci_tile >> 1;                 // ci columns staged by each CTA
+  const int b_groups = (n_half + 63) / 64;
+  const uint32_t pair_tx = 2u * (uint32_t)(2 + b_groups) * 8192u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = pair; item < num_items; item += num_pairs) {
+        int rem = item;
+        const int split = rem % p.num_splits; rem /= p.num_splits;
+        const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
+        const int cot = rem % p.co_tiles; rem /= p.co_tiles;
+        const int t = rem;
+        const int tm = p.tap_map[t];
+        const CUtensorMap* mX = tm == 0 ? &mapX0 : (tm == 1 ? &mapX1 : (tm == 2 ? &mapX2 : &mapX3));
+        const int s0 = split * p.steps_per_split;
+        const int s1 = min(p.total_steps, s0 + p.steps_per_split);
+        const int co0 = cot * 256 + (int)rank * 128;
+        const int ci0 = cit * p.ci_tile + (int)rank * n_half;
+        for (int s = s0; s < s1; ++s) {
+          mbar_wait(&pipe->empty[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * kWg2StageBytes;
+          uint8_t* sB = sA + 16384;
+          if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
+          for (int g = 0; g < 2; ++g) {
+            if (p.flat) tma_load_4d_2cta(sA + g * 8192, &mapY, &pipe->full[stage], co0 + g * 64, s * 64, 0, 0);
+            else tma_load_4d_2cta(sA + g * 8192, &mapY, &pipe->full[stage], co0 + g * 64, 0, 0, s * p.rois_per_step);
+          }
+          for (int g = 0; g < b_groups; ++g) {
+            if (p.flat) tma_load_4d_2cta(sB + g * 8192, mX, &pipe->full[stage], ci0 + g * 64, s * 64, 0, 0);
+            else tma_load_4d_2cta(sB + g * 8192, mX, &pipe->full[stage], ci0 + g * 64, p.tap_x[t], p.tap_y[t],
+                                  s * p.rois_per_step);
+          }
+          if (++stage == kWg2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, p.ci_tile, 1, 1);
+      const uint32_t idesc_ones = make_idesc_bf16(256, 16, 1, 1);
+      const uint32_t s_ones = smem_u32(ones);
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = pair; item < num_items; item += num_pairs, ++it) {
+        int rem = item;
+        const int split = rem % p.num_splits; rem /= p.num_splits;
+        const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
+        rem /= p.co_tiles;
+        const int t = rem;
+        const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
+        const int s0 = split * p.steps_per_split;
+        const int s1 = min(p.total_steps, s0 + p.steps_per_split);
+        const int as = it & 1;
+        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&pipe->tmem_empty[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
+        for (int s = s0; s < s1; ++s) {
+          mbar_wait(&pipe->full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sA = smem_u32(smem + stage * kWg2StageBytes);
+            const uint32_t sB = sA + 16384;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t acc = (s > s0 || kk > 0) ? 1u : 0u;
+              const uint64_t adesc = make_smem_desc(sA + kk * 2048, 8192, 1024);
+              umma_f16_2cta(acc0, adesc, make_smem_desc(sB + kk * 2048, 8192, 1024), idesc, acc);
+              if (want_shift)
+                umma_f16_2cta(acc0 + kWgOnesCol, adesc, make_smem_desc(s_ones + kk * 2048, 8192, 1024), idesc_ones, acc);
+            }
+            umma_commit_2cta(&pipe->empty[stage], 3);
+            if (s == s1 - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
+          }
+          __syncwarp();
+          if (++stage == kWg2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int it = 0;
+    for (int item = pair; item < num_items; item += num_pairs, ++it) {
+      int rem = item;
+      rem /= p.num_splits;
+      const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
+      const int cot = rem % p.co_tiles; rem /= p.co_tiles;
+      const int t = rem;
+      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
+      const int as = it & 1;
+      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&pipe->tmem_full[as], aphase);
+      tc_fence_after();
+      const int co = cot * 256 + (int)rank * 128 + q * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+#pragma unroll 1
+      for (int j = 0; j < p.ci_tile; j += 16) {
+        if (cit * p.ci_tile + j >= p.cin) break;
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + j, v);
+        tmem_ld_wait();
+        if (co < p.cout) {
+          float4* o = reinterpret_cast<float4*>(p.dw + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin +
+                                                cit * p.ci_tile + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            atomicAdd(o + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+        }
+      }
+      if (want_shift) {
+        uint32_t v[16];
+        tmem_ld_32x16(taddr + kWgOnesCol, v);
+        tmem_ld_wait();
+        if (co < p.cout) atomicAdd(p.dshift + co, __uint_as_float(v[0]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);     // 4 warps x 2 CTAs
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 }  // namespace tc
 }  // namespace c2d

@@ -114,6 +114,7 @@ static int tc_prepare() {
   if (!g_attr_done) {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWg2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
     g_attr_done = true;
   }
@@ -350,8 +351,14 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
   CUtensorMap mapY, mapX[4];
   p.taps = c.k * c.k; p.taps_total = p.taps;
   p.cout = c.cout; p.cin = c.cin; p.dw = dw; p.dshift = dshift;
+  // The 2-CTA weight gradient (wgrad_tc2_kernel) is correct but measured 6 % SLOWER than the single-CTA
+  // kernel on this layer mix (its fixed M = 256 wastes MMA work on cout = 320 / 352 / 160 / 192, and wgrad is
+  // not shared-memory bound); opt in with C2D_WGRAD_2CTA=1.
+  static int wg2 = -1;
+  if (wg2 < 0) { const char* e = getenv("C2D_WGRAD_2CTA"); wg2 = (e && e[0] == '1') ? 1 : 0; }
+  const bool two = wg2 == 1 && use_2cta(true, 1);
   p.co_tiles = (c.cout + 255) / 256;
-  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile);
+  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, two ? 32 : 16);
   p.ci_groups = (p.ci_tile + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
@@ -387,16 +394,22 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
     }
   }
   const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  int splits = num_sms() / base_items;       // one wave of items; every extra split is a dW-sized atomic pass
+  const int workers = two ? num_sms() / 2 : num_sms();
+  int splits = workers / base_items;         // one wave of items; every extra split is a dW-sized atomic pass
   if (splits < 1) splits = 1;
   if (splits > p.total_steps) splits = p.total_steps;
   p.steps_per_split = (p.total_steps + splits - 1) / splits;
   p.num_splits = (p.total_steps + p.steps_per_split - 1) / p.steps_per_split;
   const int items = base_items * p.num_splits;
   if (items <= 0 || p.total_steps <= 0) return C2D_OK;
-  const int grid = items < num_sms() ? items : num_sms();
   ProfScope prof(st, 1, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout);
-  tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  if (two) {
+    const int pairs = items < workers ? items : workers;
+    tc::wgrad_tc2_kernel<<<2 * pairs, tc::kWgThreads, tc::kWg2SmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  } else {
+    const int grid = items < num_sms() ? items : num_sms();
+    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  }
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -638,3 +638,37 @@ def test_train_step_updates_variables_like_the_oracle():
   gb = want['dfc_b'].astype(np.float64)
   np.testing.assert_allclose(model.fc_biases.detach().cpu().numpy(), fc_b0 - 0.01 * gb / np.sqrt(0.1 + gb * gb),
                              rtol=2e-4, atol=2e-6)
+
+
+def test_eval_predict_full_size_multiscale_nms():
+  """BASELINE configs[4] shape: one image, 2000 proposals, 20 classes, 4 scales, (1+K) NMS passes."""
+  from cap2det_b200 import synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  model = _build_model(20, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)),
+                       is_training=False, eval_dims=(1200, 800, 600, 400))
+  with torch.no_grad():
+    model.fc_weights.mul_(20.0)
+  rng = np.random.default_rng(26)
+  P = 2000
+  props = synthetic.make_proposals(rng, 1, P)
+  fmaps = [dev(synthetic.make_feature_map(rng, 1, h, w)) for (h, w) in ((1200, 2000), (800, 1333), (600, 1000), (400, 667))]
+  ex = {F.features_to_crop: fmaps, F.num_proposals: dev(np.array([P], np.int32)), F.proposals: dev(props)}
+  pred = model.build_prediction(ex)
+  for i in range(4):
+    n = int(pred['num_detections_at_%d' % i][0])
+    s = pred['detection_scores_at_%d' % i][0].cpu().numpy()
+    c = pred['detection_classes_at_%d' % i][0].cpu().numpy()
+    assert 0 < n <= 300 and np.all(np.diff(s[:n]) <= 0) and np.all(s[n:] == 0) and np.all(c[n:] == 1.0)
+    assert np.all((c[:n] >= 1) & (c[:n] <= 20))
+  # stage 0 against the oracle NMS on the SAME averaged scores: keep lists bit-exact
+  s0 = pred['oicr_proposal_scores_at_0'].cpu().numpy()
+  n_o, b_o, s_o, c_o, _ = onms.multiclass_nms(props, s0, 1e-5, 0.4, 100, 300)
+  np.testing.assert_array_equal(pred['num_detections_at_0'].cpu().numpy(), n_o)
+  np.testing.assert_array_equal(pred['detection_boxes_at_0'].cpu().numpy(), b_o)
+  np.testing.assert_array_equal(pred['detection_classes_at_0'].cpu().numpy(), c_o)
+  s3 = box_ops.softmax(pred['oicr_proposal_scores_at_3'].cpu().numpy())[:, :, 1:]
+  n_o, b_o, s_o, c_o, _ = onms.multiclass_nms(props, s3, 1e-5, 0.3, 100, 300)
+  np.testing.assert_array_equal(pred['num_detections_at_3'].cpu().numpy(), n_o)
+  np.testing.assert_array_equal(pred['detection_classes_at_3'].cpu().numpy()[0, :n_o[0]], c_o[0, :n_o[0]])
