@@ -62,6 +62,8 @@ SIGNATURES = {
     'c2d_multiclass_nms': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _c_int, _c_int,
                                     _p, _p, _p, _p, _p, _p, _c_sz, _p]),
     'c2d_label_lut': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _p]),
+    'c2d_text_classifier_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _p, _c_int, _p, _p, _c_int,
+                                           _c_float, _p, _p, _p, _p]),
     'c2d_adagrad_update': (_c_int, [_p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _p]),
     'c2d_l2_loss': (_c_int, [_p, _c_ll, _c_float, _p, _p]),
     'c2d_wordvec_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _c_int, _p, _p, _p, _p]),

@@ -263,6 +263,64 @@ wordvec_match_kernel(const int* __restrict__ tok, int T, const float* __restrict
     }
 }
 
+// ---- TextClassifierMatchExtractor (models/label_extractor.py:363-472) --------------------------------
+// One CTA per image.  hidden[t,h] = emb[tok_t] . W1[:,h] + b1[h]; masked_maximum over tokens (mask = token != OOV,
+// minimum over ALL tokens, core/utils.py:63-79); ReLU; logits = pooled . W2 + b2; label = sigmoid(logit) > thr;
+// overridden by the exact-match labels whenever any exact match exists (:466-472).
+// Dynamic smem: pooled [H] floats.
+__global__ void __launch_bounds__(256)
+text_classifier_match_kernel(const int* __restrict__ tok, int T, const float* __restrict__ emb, int V, int D,
+                             const float* __restrict__ w1, const float* __restrict__ b1, int H,
+                             const float* __restrict__ w2, const float* __restrict__ b2, int C, float threshold,
+                             const int* __restrict__ exact_lut, float* __restrict__ labels,
+                             float* __restrict__ probas) {
+  extern __shared__ float pooled[];
+  __shared__ int s_exact;
+  const int b = blockIdx.x;
+  const int* tk = tok + (size_t)b * T;
+  if (threadIdx.x == 0) s_exact = 0;
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float mn = INFINITY;
+    for (int t = 0; t < T; ++t) {          // pass 1: axis minimum over all tokens
+      const float* e = emb + (size_t)min(max(tk[t], 0), V) * D;
+      float acc = b1[h];
+      for (int d = 0; d < D; ++d) acc = fmaf(e[d], w1[(size_t)d * H + h], acc);
+      mn = fminf(mn, acc);
+    }
+    float mx = -INFINITY;
+    for (int t = 0; t < T; ++t) {          // pass 2: max((x - min) * mask)
+      const float* e = emb + (size_t)min(max(tk[t], 0), V) * D;
+      float acc = b1[h];
+      for (int d = 0; d < D; ++d) acc = fmaf(e[d], w1[(size_t)d * H + h], acc);
+      const float m = (tk[t] != V) ? 1.f : 0.f;
+      mx = fmaxf(mx, __fmul_rn(__fsub_rn(acc, mn), m));
+    }
+    pooled[h] = fmaxf(__fadd_rn(mx, mn), 0.f);      // masked_maximum, then tf.nn.relu
+  }
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int id = tk[t];
+    const int cls = (id >= 0 && id < V) ? exact_lut[id] : C;
+    if (cls >= 0 && cls < C) s_exact = 1;
+  }
+  __syncthreads();
+  const bool exact = s_exact != 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = b2[c];
+    for (int h = 0; h < H; ++h) acc = fmaf(pooled[h], w2[(size_t)h * C + c], acc);
+    const float p = 1.0f / (1.0f + expf(-acc));
+    if (probas) probas[(size_t)b * C + c] = p;
+    labels[(size_t)b * C + c] = exact ? 0.f : (p > threshold ? 1.f : 0.f);
+  }
+  __syncthreads();
+  if (exact)
+    for (int t = threadIdx.x; t < T; t += blockDim.x) {
+      const int id = tk[t];
+      const int cls = (id >= 0 && id < V) ? exact_lut[id] : C;
+      if (cls >= 0 && cls < C) labels[(size_t)b * C + cls] = 1.0f;
+    }
+}
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -338,6 +396,27 @@ int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int 
   }
   C2D_CUDA_OK(cudaFuncSetAttribute(wordvec_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   wordvec_match_kernel<<<B, 256, smem, st>>>(token_ids, T, emb, V, D, class_ids, C, exact_lut, labels, sim_pooled);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_text_classifier_match(const int* token_ids, int B, int T, const float* emb, int V, int D, const float* w1,
+                              const float* b1, int H, const float* w2, const float* b2, int C, float threshold,
+                              const int* exact_lut, float* labels, float* probas, c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 0 && T >= 0 && V >= 1 && D >= 1 && H >= 1 && C >= 1, "text_classifier_match: bad shape");
+  if (B == 0) return C2D_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (T == 0) {   // no tokens: the reference's predicted labels come from an all-masked pool; exact match is empty.
+    // hidden = masked_maximum over an empty axis is undefined in TF; the reference test feeds [] and expects zeros
+    // (models/label_extractor_test.py:215-217) -> zeros.
+    C2D_CUDA_OK(cudaMemsetAsync(labels, 0, (size_t)B * C * sizeof(float), st));
+    if (probas) C2D_CUDA_OK(cudaMemsetAsync(probas, 0, (size_t)B * C * sizeof(float), st));
+    return C2D_OK;
+  }
+  C2D_CHECK_ARG((size_t)H * sizeof(float) <= 48 * 1024, "text_classifier_match: hidden_units too large");
+  text_classifier_match_kernel<<<B, 256, (size_t)H * sizeof(float), st>>>(token_ids, T, emb, V, D, w1, b1, H, w2, b2, C,
+                                                                         threshold, exact_lut, labels, probas);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -194,16 +194,68 @@ class WordVectorMatchExtractor(LabelExtractor):
 
 
 class TextClassifierMatchExtractor(LabelExtractor):
-  """models/label_extractor.py:331-472.  Needs the pre-trained text-classifier checkpoint
-  (zoo/coco_text_classifier, absent from the reference tree); SURVEY.md 8(f) rank 3 ("next")."""
+  """Exact match, else the classes a pre-trained caption classifier predicts (sigmoid > label_threshold)
+  (models/label_extractor.py:331-472).  The classifier is the 2-layer MLP of `_predict` (:363-430):
+  embedding -> FC(hidden_units) -> masked max over tokens -> ReLU -> FC(num_classes).
+
+  `text_classifier_checkpoint_file`: the reference restores a TF checkpoint (:456-458); TensorFlow is not a
+  dependency here, so the four variables are read from a NumPy `.npz` with the TF variable names
+  `text_classifier/layer1/weights` [D,H], `.../layer1/biases` [H], `text_classifier/layer2/weights` [H,C],
+  `.../layer2/biases` [C]  (export once with tf.train.load_checkpoint(path).get_tensor(name) + np.savez)."""
+
+  _VARS = ('text_classifier/layer1/weights', 'text_classifier/layer1/biases',
+           'text_classifier/layer2/weights', 'text_classifier/layer2/biases')
 
   def __init__(self, options, device=None):
     super(TextClassifierMatchExtractor, self).__init__(options, device)
-    raise NotImplementedError(
-        'text_classifier_match_extractor is outside the hot path built so far (SURVEY.md 8(f) rank 3)')
+    self._classes = _read_lines(options.label_file)
+    self._num_classes = len(self._classes)
+    self._open_vocabulary_list = _read_lines(options.open_vocabulary_file)
+    with open(options.open_vocabulary_word_embedding_file, 'rb') as fid:
+      self._open_vocabulary_word_embedding = np.load(fid)
+    self._built = False
 
-  def extract_labels(self, examples):
-    raise NotImplementedError
+  def _build(self):
+    options = self._options
+    path = options.text_classifier_checkpoint_file
+    if not path.endswith('.npz'):
+      raise ValueError('text_classifier_checkpoint_file must be a .npz export of the text_classifier variables '
+                       '(got %r); TensorFlow checkpoints cannot be read without TensorFlow' % path)
+    ckpt = np.load(path)
+    for name in self._VARS:
+      if name not in ckpt:
+        raise ValueError('checkpoint %s lacks variable %s' % (path, name))
+    w1, b1, w2, b2 = [np.asarray(ckpt[n], np.float32) for n in self._VARS]
+    emb = self._open_vocabulary_word_embedding
+    if w1.shape != (emb.shape[-1], options.hidden_units) or w2.shape != (options.hidden_units, self._num_classes):
+      raise ValueError('text classifier shapes %s / %s do not match embedding dims %d, hidden_units %d, classes %d'
+                       % (w1.shape, w2.shape, emb.shape[-1], options.hidden_units, self._num_classes))
+    init_width = 0.03
+    oov_emb = init_width * (np.random.rand(1, emb.shape[-1]) * 2 - 1)                  # :383-384 (unseeded)
+    table = np.concatenate([emb, oov_emb], axis=0).astype(np.float32)
+    dev = self._device
+    self._embedding_weights = torch.from_numpy(table).to(dev)
+    self._w1, self._b1 = torch.from_numpy(w1).to(dev), torch.from_numpy(b1).to(dev)
+    self._w2, self._b2 = torch.from_numpy(w2).to(dev), torch.from_numpy(b2).to(dev)
+    vocab = self._open_vocabulary_list
+    index = {}
+    for i, w in enumerate(vocab):
+      index.setdefault(w, i)
+    # exact match uses the RAW class names here (:466-469), unlike ExactMatch / WordVectorMatch
+    exact = np.full((len(vocab),), self._num_classes, np.int32)
+    for cid, name in enumerate(self._classes):
+      if name in index:
+        exact[index[name]] = cid
+    self._exact_lut = torch.from_numpy(exact).to(dev)
+    self._tok = _Tokenizer(vocab)
+    self._built = True
+
+  def extract_labels(self, examples, return_probas=False):
+    if not self._built:
+      self._build()
+    ids = self._tok(examples[InputDataFields.concat_caption_string], self._device)
+    return ops.text_classifier_match(ids, self._embedding_weights, self._w1, self._b1, self._w2, self._b2,
+                                     self._options.label_threshold, self._exact_lut, return_probas=return_probas)
 
 
 def build_label_extractor(options, device=None):

@@ -366,3 +366,16 @@ def wordvec_match(token_ids, emb, class_ids, exact_lut, return_similarity=False)
   call('c2d_wordvec_match', ptr(token_ids), B, T, ptr(emb), V, D, ptr(class_ids), C, ptr(exact_lut), ptr(labels),
        ptr(sim), stream())
   return (labels, sim) if return_similarity else labels
+
+
+def text_classifier_match(token_ids, emb, w1, b1, w2, b2, threshold, exact_lut, return_probas=False):
+  """models/label_extractor.py:363-472 on pre-tokenised ids; w1 [D,H], w2 [H,C] (TF [in,out] layout)."""
+  require_cuda(token_ids, emb, w1, b1, w2, b2, exact_lut)
+  B, T = token_ids.shape
+  V, D = emb.shape[0] - 1, emb.shape[1]
+  H, C = w1.shape[1], w2.shape[1]
+  labels = torch.empty((B, C), dtype=torch.float32, device=token_ids.device)
+  probas = torch.empty((B, C), dtype=torch.float32, device=token_ids.device) if return_probas else None
+  call('c2d_text_classifier_match', ptr(token_ids), B, T, ptr(emb), V, D, ptr(w1), ptr(b1), H, ptr(w2), ptr(b2), C,
+       float(threshold), ptr(exact_lut), ptr(labels), ptr(probas), stream())
+  return (labels, probas) if return_probas else labels

@@ -188,6 +188,14 @@ int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int 
                       const int* class_ids, int C, const int* exact_lut, float* labels,
                       float* sim_pooled, c2d_stream_t stream);
 
+/* ---- TextClassifierMatchExtractor.extract_labels, models/label_extractor.py:363-472 ----
+ * emb [V+1,D] (row V = OOV); w1 [D,H], b1 [H], w2 [H,C], b2 [C] are the text_classifier/layer{1,2} variables in
+ * TF [in,out] layout.  labels [B,C] = sigmoid(logits) > threshold, overridden by exact-match labels when any
+ * caption token is a class name.  probas [B,C] may be NULL. */
+int c2d_text_classifier_match(const int* token_ids, int B, int T, const float* emb, int V, int D, const float* w1,
+                              const float* b1, int H, const float* w2, const float* b2, int C, float threshold,
+                              const int* exact_lut, float* labels, float* probas, c2d_stream_t stream);
+
 /* ---- trainer numerics around the path, train/trainer.py:85-146 -----
  * One fused update: g = grad * grad_scale + l2_scale * var   (gradient multiplier / 1/G data-parallel
  * averaging; slim l2_regularizer = scale * sum(w^2)/2 => d/dw = scale * w, core/training_utils.py:45-50)

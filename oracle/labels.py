@@ -118,6 +118,32 @@ def word_vector_match_extract(classes, open_vocab, embedding_with_oov, caption_t
   return labels.astype(np.float32), pooled
 
 
+def text_classifier_match_extract(classes, open_vocab, embedding_with_oov, w1, b1, w2, b2, threshold, caption_tokens):
+  """models/label_extractor.py:363-472 (is_training False).  w1 [D,H], w2 [H,C] in TF [in,out] layout.
+  Returns (labels [B,C], probas [B,C]).  **Parity unpinned**: the reference test needs an absent checkpoint
+  (models/label_extractor_test.py:173-219)."""
+  index = {}
+  for i, w in enumerate(open_vocab):
+    index.setdefault(w, i)
+  oov = len(open_vocab)
+  emb = np.asarray(embedding_with_oov, np.float32)
+  B = len(caption_tokens); C = len(classes)
+  T = len(caption_tokens[0]) if B else 0
+  exact = match_labels(caption_tokens, classes)                 # raw class names (:466-469)
+  if T == 0:
+    return np.zeros((B, C), np.float32), np.zeros((B, C), np.float32)
+  ids = np.array([[index.get(t, oov) for t in row] for row in caption_tokens], np.int64)
+  hidden = emb[ids].astype(np.float32) @ np.asarray(w1, np.float32) + np.asarray(b1, np.float32)   # :407-413
+  mask = (ids != oov).astype(np.float32)
+  pooled = box_ops.masked_maximum(hidden, mask[:, :, None], dim=1)[:, 0]                          # :414-416
+  pooled = np.maximum(pooled, F(0))                                                                 # :417
+  logits = pooled @ np.asarray(w2, np.float32) + np.asarray(b2, np.float32)                        # :420-426
+  probas = (F(1) / (F(1) + np.exp(-logits))).astype(np.float32)
+  likely = (probas > F(threshold)).astype(np.float32)                                               # :462-463
+  labels = np.where((exact > 0).any(axis=-1)[:, None], exact, likely)                               # :470-472
+  return labels.astype(np.float32), probas
+
+
 def parse_texts(tokens, offsets, lengths):
   """core/preprocess.py:151-214: (num_texts, padded [n,max_len] strings, lengths)."""
   if len(offsets) != len(lengths):

@@ -672,3 +672,42 @@ def test_eval_predict_full_size_multiscale_nms():
   n_o, b_o, s_o, c_o, _ = onms.multiclass_nms(props, s3, 1e-5, 0.3, 100, 300)
   np.testing.assert_array_equal(pred['num_detections_at_3'].cpu().numpy(), n_o)
   np.testing.assert_array_equal(pred['detection_classes_at_3'].cpu().numpy()[0, :n_o[0]], c_o[0, :n_o[0]])
+
+
+def test_text_classifier_match_extractor():
+  """models/label_extractor.py:331-472 with a synthetic classifier (.npz export) against the oracle."""
+  from cap2det_b200 import config, label_extractor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields
+  d = tempfile.mkdtemp()
+  rng = np.random.default_rng(27)
+  classes = synthetic.COCO_CLASSES
+  vpath, epath, vocab, emb = synthetic.write_open_vocab(d, classes, rng, size=1500, dims=300)
+  H = 400
+  w1 = (rng.standard_normal((300, H)) * 0.1).astype(np.float32); b1 = (rng.standard_normal(H) * 0.1).astype(np.float32)
+  w2 = (rng.standard_normal((H, 80)) * 0.05).astype(np.float32); b2 = (rng.standard_normal(80) * 0.5 - 1.0).astype(np.float32)
+  ck = os.path.join(d, 'text_classifier.npz')
+  np.savez(ck, **{'text_classifier/layer1/weights': w1, 'text_classifier/layer1/biases': b1,
+                  'text_classifier/layer2/weights': w2, 'text_classifier/layer2/biases': b2})
+  opts = config.parse_text(
+      "text_classifier_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+      "open_vocabulary_word_embedding_file: '%s' text_classifier_checkpoint_file: '%s' hidden_units: 400 "
+      "label_threshold: 0.5 }" % (synthetic.write_label_file(d, classes), vpath, epath, ck), config.LabelExtractor)
+  ex = label_extractor.build_label_extractor(opts)
+  assert isinstance(ex, label_extractor.TextClassifierMatchExtractor) and ex.num_classes == 80
+  caps = synthetic.make_captions(rng, 6, vocab, [c for c in classes if ' ' not in c], no_plant_images=(1, 3, 4))
+  caps[4] = ['zzz_oov'] * len(caps[4])
+  f = InputDataFields.concat_caption_string
+  labels, probas = ex.extract_labels({f: caps}, return_probas=True)
+  want, want_p = olabels.text_classifier_match_extract(classes, vocab, ex._embedding_weights.cpu().numpy(), w1, b1, w2, b2,
+                                                       0.5, caps)
+  np.testing.assert_allclose(probas.cpu().numpy(), want_p, rtol=1e-4, atol=1e-6)
+  clear = np.abs(want_p - 0.5) > 1e-4                      # thresholded labels away from the threshold: exact
+  np.testing.assert_array_equal(labels.cpu().numpy()[clear], want[clear])
+  assert (want[0] > 0).any() and want.shape == (6, 80)
+  np.testing.assert_array_equal(ex.extract_labels({f: [[], [], []]}).cpu().numpy(), np.zeros((3, 80)))
+  bad = config.parse_text(
+      "text_classifier_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+      "open_vocabulary_word_embedding_file: '%s' text_classifier_checkpoint_file: 'zoo/model.ckpt-50000' }"
+      % (synthetic.write_label_file(d, classes), vpath, epath), config.LabelExtractor)
+  with pytest.raises(ValueError):
+    label_extractor.build_label_extractor(bad).extract_labels({f: caps})
