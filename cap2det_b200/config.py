@@ -216,18 +216,50 @@ class GradientMultiplier(Message):
 
 
 class AdagradOptimizer(Message):
-  FIELDS = {'initial_accumulator_value': ('float', 0.1)}
+  FIELDS = {'initial_accumulator_value': ('float', 0.1), 'use_locking': ('bool', False)}
+
+
+class GradientDescentOptimizer(Message):
+  FIELDS = {'use_locking': ('bool', False)}
+
+
+class AdamOptimizer(Message):
+  FIELDS = {'beta1': ('float', 0.9), 'beta2': ('float', 0.999), 'epsilon': ('float', 1e-8),
+            'use_locking': ('bool', False)}
+
+
+class RMSPropOptimizer(Message):
+  FIELDS = {'decay': ('float', 0.9), 'momentum': ('float', 0.0), 'epsilon': ('float', 1e-10),
+            'use_locking': ('bool', False), 'centered': ('bool', False)}
+
+
+class MomentumOptimizer(Message):
+  FIELDS = {'momentum': ('float', 0.0), 'use_locking': ('bool', False), 'use_nesterov': ('bool', False)}
 
 
 class Optimizer(Message):
-  FIELDS = {'adagrad': (AdagradOptimizer, None)}
-  ONEOFS = {'optimizer': ['adagrad']}
+  """protos/optimizer.proto:3-11.  Every reference config selects adagrad; the other four parse but the
+  trainer refuses them (no device kernel on this path)."""
+  FIELDS = {'sgd': (GradientDescentOptimizer, None), 'adagrad': (AdagradOptimizer, None),
+            'adam': (AdamOptimizer, None), 'rmsprop': (RMSPropOptimizer, None),
+            'momentum': (MomentumOptimizer, None)}
+  ONEOFS = {'optimizer': ['sgd', 'adagrad', 'adam', 'rmsprop', 'momentum']}
+
+
+class LearningRateDecay(Message):
+  """protos/pipeline.proto:81-90."""
+  FIELDS = {'decay_steps': ('int', 999999999), 'decay_rate': ('float', 1.0), 'staircase': ('bool', True)}
 
 
 class TrainConfig(Message):
-  FIELDS = {'max_steps': ('int', 0), 'learning_rate': ('float', 0.1), 'moving_average_decay': ('float', 0.0),
+  """protos/pipeline.proto:40-79 (the fields train/trainer.py:70-146 reads; the logging / checkpoint
+  cadence fields parse and are ignored)."""
+  FIELDS = {'max_steps': ('int', 0), 'learning_rate': ('float', 0.0), 'moving_average_decay': ('float', 0.999),
             'optimizer': (Optimizer, None), 'gradient_multiplier': ([GradientMultiplier], None),
-            'sync_replicas': ('bool', False), 'max_gradient_norm': ('float', 0.0)}
+            'sync_replicas': ('bool', False), 'max_gradient_norm': ('float', 0.0),
+            'learning_rate_decay': (LearningRateDecay, None), 'save_summary_steps': ('int', 2000),
+            'save_checkpoints_steps': ('int', 2000), 'keep_checkpoint_max': ('int', 5),
+            'log_step_count_steps': ('int', 2000)}
 
 
 class Pipeline(Message):

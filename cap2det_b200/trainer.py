@@ -23,39 +23,180 @@ def l2_regularizer_scale(hyperparams):
   return 0.0
 
 
-class Adagrad(object):
-  """tf.train.AdagradOptimizer(lr, initial_accumulator_value=0.1): accum += g^2; w -= lr*g/sqrt(accum)."""
+def exponential_decay(learning_rate, global_step, decay_steps, decay_rate, staircase):
+  """tf.train.exponential_decay as called at train/trainer.py:75-81: lr * rate^(step/decay_steps), the
+  exponent floored when ``staircase``."""
+  e = float(global_step) / float(decay_steps)
+  if staircase:
+    e = float(int(e))
+  return float(learning_rate) * float(decay_rate) ** e
 
-  def __init__(self, variables, learning_rate, initial_accumulator_value=0.1, l2_scales=None, grad_multipliers=None):
+
+def resolve_gradient_multipliers(variable_names, gradient_multipliers):
+  """train/trainer.py:104-125.  Returns (trainable names in order, {name: multiplier}).
+
+  Every multiplier whose scope is a *prefix* of the variable name applies, later entries overriding earlier
+  ones; a final multiplier <= 0 drops the variable from the train list (and from the multiplier map).
+  Variables no scope matches stay trainable with no multiplier."""
+  trainable, mults = [], {}
+  for name in variable_names:
+    keep = True
+    for m in gradient_multipliers:
+      if name.startswith(m.scope):
+        mults[name] = float(m.multiplier)
+        keep = m.multiplier > 0
+    if keep:
+      trainable.append(name)
+    else:
+      mults.pop(name, None)
+  return trainable, mults
+
+
+class Adagrad(object):
+  """tf.train.AdagradOptimizer(lr, initial_accumulator_value=0.1): accum += g^2; w -= lr*g/sqrt(accum).
+
+  ``variables`` are the packed parameter buffers.  ``segments`` (optional) lists, per buffer, the named
+  sub-ranges ``(name, start, numel, multiplier or None if dropped, l2)``; when every segment of a buffer agrees
+  the whole buffer is one fused launch, otherwise each live segment is its own launch and dropped segments are
+  left untouched (weights and accumulator)."""
+
+  def __init__(self, variables, learning_rate, initial_accumulator_value=0.1, l2_scales=None, grad_multipliers=None,
+               segments=None):
     self.variables = list(variables)
     self.lr = float(learning_rate)
     self.accum = [torch.full_like(v, initial_accumulator_value) for v in self.variables]
     self.l2 = list(l2_scales) if l2_scales is not None else [0.0] * len(self.variables)
     self.mult = list(grad_multipliers) if grad_multipliers is not None else [1.0] * len(self.variables)
+    self.segments = segments
+    self.clip_norm = None       # tf.contrib.training.clip_gradient_norms: per-variable clip_by_norm
+
+  def _update(self, w, a, g, n, scale, l2):
+    call('c2d_adagrad_update', ptr(w), ptr(a), ptr(g), n, self.lr, float(scale), float(l2), stream())
+
+  def _clip_factor(self, w, g, scale, l2):
+    """tf.clip_by_norm on the total gradient scale*g + l2*w of one variable: factor = clip / max(norm, clip).
+    One host sync per variable; no reference config sets max_gradient_norm (train/trainer.py:134)."""
+    if self.clip_norm is None:
+      return 1.0
+    total = g.float() * scale
+    if l2 != 0.0:
+      total = total + l2 * w.float()
+    norm = float(torch.linalg.vector_norm(total))
+    return self.clip_norm / max(norm, self.clip_norm)
 
   def step(self, grad_scale=1.0):
-    for v, a, l2, m in zip(self.variables, self.accum, self.l2, self.mult):
-      if v.grad is None or m == 0.0:      # multiplier 0 => variable dropped from the train list (train/trainer.py:104-125)
+    """The regularisation loss is part of the reference's total loss, so a variable's gradient multiplier
+    scales its L2 term as well: g_total = m * (grad_scale * grad + l2 * w)."""
+    for i, (v, a) in enumerate(zip(self.variables, self.accum)):
+      if v.grad is None:
         continue
-      call('c2d_adagrad_update', ptr(v.data), ptr(a), ptr(v.grad), v.numel(), self.lr, float(grad_scale * m),
-           float(l2), stream())
+      segs = self.segments[i] if self.segments is not None else None
+      uniform = segs is None or len({(m, l2) for _, _, _, m, l2 in segs}) == 1
+      if uniform and self.clip_norm is None:
+        m, l2 = (self.mult[i], self.l2[i]) if segs is None else (segs[0][3], segs[0][4])
+        if m is None or m == 0.0:   # multiplier 0 => variable dropped from the train list (train/trainer.py:104-125)
+          continue
+        self._update(v.data, a, v.grad, v.numel(), grad_scale * m, l2 * m)
+        continue
+      wf, af, gf = v.data.view(-1), a.view(-1), v.grad.view(-1)
+      if segs is None:
+        segs = [('', 0, v.numel(), self.mult[i], self.l2[i])]
+      for _, start, numel, m, l2 in segs:
+        if m is None or m == 0.0 or numel == 0:
+          continue
+        w, g = wf[start:start + numel], gf[start:start + numel]
+        clip = self._clip_factor(w, g, grad_scale * m, l2 * m)
+        self._update(w, af[start:start + numel], g, numel, grad_scale * m * clip, l2 * m * clip)
 
   def zero_grad(self):
     for v in self.variables:
       v.grad = None
 
 
+def build_optimizer(options, variables, learning_rate, **kwargs):
+  """core/training_utils.py:14-70.  Only adagrad has a device kernel on this path (it is what all nine
+  reference configs select, e.g. configs/voc07_groundtruth.pbtxt:108-111)."""
+  which = options.WhichOneof('optimizer')
+  if which == 'adagrad':
+    return Adagrad(variables, learning_rate,
+                   initial_accumulator_value=options.adagrad.initial_accumulator_value, **kwargs)
+  if which in ('sgd', 'momentum', 'adam', 'rmsprop'):
+    raise ValueError('optimizer %r has no sm_100a kernel in cap2det_b200; use adagrad' % which)
+  raise ValueError('Invalid optimizer: {}.'.format(which))
+
+
+def _is_moving_stat(name):
+  return name.endswith('/moving_mean') or name.endswith('/moving_variance')
+
+
+def _variable_segments(model, multipliers, trainable, l2_scale):
+  """Per packed buffer: (name, start, numel, multiplier | None, l2) for every named TF variable inside it.
+
+  The BatchNorm moving statistics live in the head buffer too but are not TF trainable variables
+  (models/model_base.py:60-66); the head backward writes exact zeros for them, which Adagrad maps to "no
+  change", so they are left out of the segment list and never force the per-segment path."""
+  buffers = model.get_variables_to_train()
+  segs = [[] for _ in buffers]
+  live = set(trainable)
+  for name, view in model.named_variables().items():
+    if _is_moving_stat(name):
+      continue
+    for i, b in enumerate(buffers):
+      off = view.data_ptr() - b.data_ptr()
+      if 0 <= off < b.numel() * b.element_size():
+        assert view.is_contiguous()
+        m = multipliers.get(name, 1.0) if name in live else None
+        # slim regularises the FC *weights* only (models/cap2det_model.py:79-88,190-197 under fc_hyperparams)
+        l2 = l2_scale if (b is model.fc_weights and m is not None) else 0.0
+        segs[i].append((name, off // b.element_size(), view.numel(), m, l2))
+        break
+  return segs
+
+
 class TrainStep(object):
   """Runs training steps of a cap2det_b200 Model; data-parallel when torch.distributed is initialised."""
 
-  def __init__(self, model, learning_rate=0.01, world_size=1):
+  def __init__(self, model, learning_rate=0.01, world_size=1, train_config=None):
     self.model = model
     self.world_size = world_size
+    self.global_step = 0
+    self.train_config = train_config
     options = model._model_proto
     l2 = l2_regularizer_scale(options.fc_hyperparams)
-    # slim regularises FC weights only (biases and the conv head have no regulariser on this path)
-    self.opt = Adagrad(model.get_variables_to_train(), learning_rate, l2_scales=[0.0, l2, 0.0])
     self.l2_scale = l2
+    variables = model.get_variables_to_train()
+    if train_config is None:
+      # slim regularises FC weights only (biases and the conv head have no regulariser on this path)
+      self.base_lr = float(learning_rate)
+      self.opt = Adagrad(variables, learning_rate, l2_scales=[0.0, l2, 0.0])
+      return
+    if train_config.sync_replicas:
+      raise ValueError('sync_replicas (SyncReplicasOptimizer over a parameter server, train/trainer.py:90-94) is '
+                       'replaced by the NCCL all-reduce of TrainStep; leave it false')
+    self.base_lr = float(train_config.learning_rate)
+    names = [n for n in model.named_variables().keys() if not _is_moving_stat(n)]
+    trainable, mults = resolve_gradient_multipliers(names, train_config.gradient_multiplier)
+    segs = _variable_segments(model, mults, trainable, l2)
+    self.trainable_names, self.gradient_multipliers = trainable, mults
+    self.opt = build_optimizer(train_config.optimizer, variables, self.base_lr, segments=segs)
+    # MovingAverageOptimizer(decay): every reference config sets 0.0, which makes the shadow copy equal the
+    # variable (train/trainer.py:98-100); any other value would need the shadow set, which this path lacks.
+    if train_config.HasField('moving_average_decay') and train_config.moving_average_decay != 0.0:
+      raise ValueError('moving_average_decay != 0 is not supported on this path')
+    if train_config.HasField('max_gradient_norm'):          # train/trainer.py:134-136
+      self.opt.clip_norm = float(train_config.max_gradient_norm)
+
+  @classmethod
+  def from_pipeline(cls, model, pipeline, world_size=1):
+    """train/trainer.py:66-146 for a parsed Pipeline proto."""
+    return cls(model, world_size=world_size, train_config=pipeline.train_config)
+
+  def learning_rate(self):
+    tc = self.train_config
+    if tc is None or not tc.HasField('learning_rate_decay'):
+      return self.base_lr
+    d = tc.learning_rate_decay
+    return exponential_decay(self.base_lr, self.global_step, d.decay_steps, d.decay_rate, d.staircase)
 
   def regularization_loss(self):
     out = torch.empty((), dtype=torch.float32, device=self.model.fc_weights.device)
@@ -67,6 +208,7 @@ class TrainStep(object):
     """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""
     model = self.model
     self.opt.zero_grad()
+    self.opt.lr = self.learning_rate()
     predictions = model.build_prediction(examples)
     loss_dict = model.build_loss(predictions, examples)
     total = None
@@ -76,5 +218,6 @@ class TrainStep(object):
     if self.world_size > 1:
       c2d_dist.allreduce_sum([v.grad for v in model.get_variables_to_train()])
     self.opt.step(grad_scale=1.0 / self.world_size)
+    self.global_step += 1
     self.last_loss_dict = loss_dict
     return total.detach() + self.regularization_loss()

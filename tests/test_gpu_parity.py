@@ -480,7 +480,7 @@ def test_model_train_step_end_to_end_fp32():
     np.testing.assert_array_equal(ind.cpu().numpy(), want['aux'][i][0])           # pseudo-label seeds: bit-exact
     np.testing.assert_array_equal(pl.cpu().numpy(), want['aux'][i][1])            # soft labels: bit-exact
   for k, v in want['loss'].items():
-    assert abs(float(loss[k]) - v) <= 2e-5 * abs(v), k
+    assert abs(float(loss[k].detach()) - v) <= 2e-5 * abs(v), k
   assert rel_err(model.fc_weights.grad.cpu().numpy(), want['dfc_w']) < 1e-4
   assert rel_err(model.fc_biases.grad.cpu().numpy(), want['dfc_b']) < 1e-4
 
@@ -638,6 +638,82 @@ def test_train_step_updates_variables_like_the_oracle():
   gb = want['dfc_b'].astype(np.float64)
   np.testing.assert_allclose(model.fc_biases.detach().cpu().numpy(), fc_b0 - 0.01 * gb / np.sqrt(0.1 + gb * gb),
                              rtol=2e-4, atol=2e-6)
+
+
+def test_train_step_from_pipeline_applies_scope_multipliers_decay_and_clip():
+  """train/trainer.py:66-146 through TrainStep.from_pipeline: a dropped scope stays untouched (weights and
+  accumulator), a fractional multiplier scales gradient and L2 term, the decayed learning rate is used, and
+  max_gradient_norm clips each variable's total gradient (tf.clip_by_norm)."""
+  from cap2det_b200 import config, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  C, B, P = 20, 1, 12
+  rng = np.random.default_rng(27)
+  fmap = synthetic.make_feature_map(rng, B, 128, 160)
+  props = synthetic.make_proposals(rng, B, P, 128, 160)
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  ex = {F.features_to_crop: dev(fmap), F.num_proposals: dev(np.array([P], np.int32)), F.proposals: dev(props),
+        F.object_texts: texts, F.dropout_keep_mask: dev(keep)}
+
+  def fresh():
+    torch.manual_seed(5)
+    m = _build_model(C, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)))
+    with torch.no_grad():
+      m.fc_weights.mul_(8.0)
+    return m
+
+  # gradients of the un-multiplied step (same seeds => same variables)
+  ref = fresh()
+  pred = ref.build_prediction(ex)
+  sum(ref.build_loss(pred, ex).values()).backward()
+  grads = {n: None for n in ref.named_variables()}
+  flat = {id(v): v.grad.detach().view(-1) for v in ref.get_variables_to_train()}
+  for n, view in ref.named_variables().items():
+    for v in ref.get_variables_to_train():
+      off = view.data_ptr() - v.data_ptr()
+      if 0 <= off < v.numel() * 4:
+        grads[n] = flat[id(v)][off // 4: off // 4 + view.numel()].double().cpu().numpy()
+  w0 = {n: v.double().cpu().numpy().reshape(-1).copy() for n, v in ref.named_variables().items()}
+
+  tc_text = """
+    learning_rate: 0.02 optimizer { adagrad { initial_accumulator_value: 0.2 } } moving_average_decay: 0.0
+    learning_rate_decay { decay_steps: 1 decay_rate: 0.5 staircase: true }
+    gradient_multiplier { scope: 'oicr/iter2' multiplier: 0.0 }
+    gradient_multiplier { scope: 'midn' multiplier: 0.5 }
+    gradient_multiplier { scope: 'second_stage_feature_extraction/InceptionV2/Mixed_5b' multiplier: 0.0 }
+    %s
+  """
+  for clip in (None, 0.05):
+    model = fresh()
+    tc = config.parse_text(tc_text % ('' if clip is None else 'max_gradient_norm: %g' % clip), config.TrainConfig)
+    pipe = config.Pipeline(train_config=tc)
+    step = trainer.TrainStep.from_pipeline(model, pipe)
+    assert 'oicr/iter2/weights' not in step.trainable_names
+    assert step.gradient_multipliers['midn/proba_r_given_c/weights'] == 0.5
+    step.global_step = 2            # lr = 0.02 * 0.5^2
+    step(ex)
+    lr, l2 = 0.02 * 0.25, 1e-6
+    got = {n: v.double().cpu().numpy().reshape(-1) for n, v in model.named_variables().items()}
+    checked = 0
+    for n in got:
+      if n.endswith('moving_mean') or n.endswith('moving_variance') or n.startswith('oicr/iter2') or '/Mixed_5b/' in n:
+        np.testing.assert_array_equal(got[n], w0[n], err_msg=n)
+        continue
+      m = 0.5 if n.startswith('midn') else 1.0
+      reg = l2 if (n.endswith('/weights') and not n.startswith('second_stage')) else 0.0
+      g = m * (grads[n] + reg * w0[n])
+      if clip is not None:
+        g = g * (clip / max(np.linalg.norm(g), clip))
+      want = w0[n] - lr * g / np.sqrt(0.2 + g * g)
+      np.testing.assert_allclose(got[n], want, rtol=3e-5, atol=3e-7, err_msg=n)
+      checked += 1
+    assert checked > 40
+    # the dropped segments' accumulators stay at their initial value
+    acc_fc = step.opt.accum[1].view(-1, 1024)
+    col = model._col_oicr[1]
+    assert torch.all(acc_fc[col:col + C + 1] == 0.2)
 
 
 def test_eval_predict_full_size_multiscale_nms():

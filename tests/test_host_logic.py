@@ -128,3 +128,55 @@ def test_no_cpu_fallback_on_cpu_tensors():
   from cap2det_b200 import box_utils
   with pytest.raises(RuntimeError):
     box_utils.area(torch.zeros(3, 4))
+
+
+# ---- trainer numerics around the path -----------------------------------
+def _mults(*pairs):
+  from cap2det_b200 import config
+  return [config.GradientMultiplier(scope=s, multiplier=m) for s, m in pairs]
+
+
+def test_gradient_multiplier_scopes_follow_the_reference_loop():
+  """train/trainer.py:104-125: prefix match, later entries override, final multiplier <= 0 drops the variable."""
+  from cap2det_b200 import trainer
+  names = ['first_stage_feature_extraction/InceptionV2/Mixed_4d/w', 'first_stage_feature_extraction/InceptionV2/Mixed_4e/w',
+           'second_stage_feature_extraction/InceptionV2/Mixed_5a/w', 'midn/proba_r_given_c/weights', 'oicr/iter1/biases']
+  # the three entries of configs/coco17_groundtruth.pbtxt:112-123
+  m = _mults(('first_stage_feature_extraction', 0.0), ('second_stage_feature_extraction', 1.0),
+             ('first_stage_feature_extraction/InceptionV2/Mixed_4e', 1.0))
+  train, mult = trainer.resolve_gradient_multipliers(names, m)
+  assert train == names[1:]
+  assert mult == {names[1]: 1.0, names[2]: 1.0}          # unmatched variables train without a multiplier
+  # order matters: the broader scope listed last wins
+  train, mult = trainer.resolve_gradient_multipliers(names, list(reversed(m)))
+  assert train == names[2:] and mult == {names[2]: 1.0}
+  # a negative multiplier drops as well (":113 if multiplier.multiplier > 0")
+  train, mult = trainer.resolve_gradient_multipliers(names, _mults(('oicr', -1.0), ('midn', 0.25)))
+  assert train == names[:4] and mult == {names[3]: 0.25}
+  assert trainer.resolve_gradient_multipliers(names, []) == (names, {})
+
+
+def test_exponential_decay_and_optimizer_selection():
+  """train/trainer.py:75-81 and core/training_utils.py:14-70."""
+  from cap2det_b200 import config, trainer
+  assert trainer.exponential_decay(0.01, 250, 100, 0.5, True) == 0.01 * 0.5 ** 2
+  assert abs(trainer.exponential_decay(0.01, 250, 100, 0.5, False) - 0.01 * 0.5 ** 2.5) < 1e-12
+  assert trainer.exponential_decay(0.01, 99999, 100000, 1.0, True) == 0.01      # every reference config
+  tc = config.parse_text("""
+    max_steps: 100000 learning_rate: 0.01
+    learning_rate_decay { decay_steps: 100000 decay_rate: 1.0 staircase: true }
+    moving_average_decay: 0.0
+    optimizer { adagrad { } }
+    sync_replicas: false
+    save_summary_steps: 2000 save_checkpoints_steps: 2000 keep_checkpoint_max: 5 log_step_count_steps: 10
+  """, config.TrainConfig)
+  assert tc.optimizer.WhichOneof('optimizer') == 'adagrad'
+  assert tc.optimizer.adagrad.initial_accumulator_value == pytest.approx(0.1)
+  assert tc.learning_rate_decay.decay_steps == 100000 and tc.HasField('learning_rate_decay')
+  assert not tc.HasField('max_gradient_norm')
+  for other in ('sgd', 'adam', 'rmsprop', 'momentum'):
+    opt = config.parse_text('%s { }' % other, config.Optimizer)
+    with pytest.raises(ValueError, match='no sm_100a kernel'):
+      trainer.build_optimizer(opt, [], 0.01)
+  with pytest.raises(ValueError, match='Invalid optimizer'):
+    trainer.build_optimizer(config.Optimizer(), [], 0.01)
