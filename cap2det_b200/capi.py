@@ -44,6 +44,18 @@ SIGNATURES = {
     'c2d_head_workspace_bytes': (_c_sz, [_c_int, _c_int]),
     'c2d_head_mixed5_fwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p]),
     'c2d_head_mixed5_bwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p]),
+    'c2d_backbone_num_convs': (_c_int, []),
+    'c2d_backbone_conv_spec': (_c_int, [_c_int, _p, _p, _p, _p, _p]),
+    'c2d_backbone_param_floats': (_c_ll, []),
+    'c2d_backbone_param_offsets': (_c_int, [_c_int, _p, _p, _p, _p, _p]),
+    'c2d_backbone_out_dims': (_c_int, [_c_int, _c_int, _p, _p]),
+    'c2d_backbone_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int]),
+    'c2d_backbone_fwd': (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p, _c_sz, _p, _p]),
+    'c2d_backbone_bwd': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p, _p, _c_sz, _p, _p]),
+    'c2d_backbone_mixed4e_input': (_c_int, [_p, _c_int, _c_int, _c_int, _p, _p]),
+    'c2d_conv_img_bf16_fwd': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _p, _c_int, _p, _c_int, _p]),
+    'c2d_conv_img_bf16_dgrad': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _p, _p, _c_int, _p]),
+    'c2d_conv_img_bf16_wgrad': (_c_int, [_p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p, _p]),
     'c2d_conv_bf16_fwd': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _p, _c_int, _p, _c_int, _p]),
     'c2d_conv_bf16_dgrad': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _p]),
     'c2d_conv_bf16_wgrad': (_c_int, [_p, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p]),

@@ -52,7 +52,42 @@ struct ConvGemmParams {
   const __nv_bfloat16* mask; int mask_ld; int mask_cols;
   // geometric output row mapping: pixel = (n*Hf + jy*sy + oy)*Wf + jx*sx + ox
   int Hf, Wf, sy, sx, oy, ox;
+  // flat == 2 (whole feature maps, backbone): a (half) tile is an img_tw x (rows_per_tile / img_tw) patch of
+  // the Hf x Wf output plane of image n; A box = (64, img_tw, th, 1) at (x0 + tap_x, y0 + tap_y, n).
+  int img_tw, img_tiles_x, img_tiles_y;
 };
+
+struct ImgTile { int n, x0, y0; };
+__device__ __forceinline__ ImgTile img_tile(const ConvGemmParams& p, int h) {
+  ImgTile t;
+  const int per_img = p.img_tiles_x * p.img_tiles_y;
+  t.n = h / per_img;
+  const int rem = h - t.n * per_img;
+  const int by = rem / p.img_tiles_x;
+  t.x0 = (rem - by * p.img_tiles_x) * p.img_tw;
+  t.y0 = by * (p.rows_per_tile / p.img_tw);
+  return t;
+}
+// output row of tile-local row r (or -1): shared by both conv kernels; h = (half) tile index
+__device__ __forceinline__ long long conv_out_row(const ConvGemmParams& p, int h, int r) {
+  if (r >= p.rows_per_tile) return -1;
+  if (p.flat == 1) {
+    const long long m = (long long)h * p.rows_per_tile + r;
+    return m < p.m_total ? m : -1;
+  }
+  if (p.flat == 2) {
+    const ImgTile t = img_tile(p, h);
+    const int jy = r / p.img_tw, jx = r - jy * p.img_tw;
+    const int y = t.y0 + jy, x = t.x0 + jx;
+    if (t.n >= p.m_total || y >= p.Hf || x >= p.Wf) return -1;
+    return ((long long)t.n * p.Hf + y) * p.Wf + x;
+  }
+  const int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
+  const int n = h * p.rois_per_tile + rn;
+  if (n >= p.m_total) return -1;
+  const int jy = pos / p.box_w, jx = pos - jy * p.box_w;
+  return ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
+}
 
 struct TcPipe {
   uint64_t full[kStages];
@@ -106,7 +141,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             uint8_t* sA = smem + stage * kStageBytes;
             uint8_t* sB = sA + kStageABytes;
             mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
-            if (p.flat) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
+            if (p.flat == 1) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
+            else if (p.flat == 2) { const ImgTile it = img_tile(p, mt); tma_load_4d(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n); }
             else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, tx, ty, mt * p.rois_per_tile);
             tma_load_4d(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile, 0, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -162,20 +198,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = a * 128 + q * 32 + lane;       // row inside the tile
-      long long orow = -1;
-      if (r < p.rows_per_tile) {
-        if (p.flat) {
-          long long m = (long long)mt * p.rows_per_tile + r;
-          if (m < p.m_total) orow = m;
-        } else {
-          int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
-          int n = mt * p.rois_per_tile + rn;
-          if (n < p.m_total) {
-            int jy = pos / p.box_w, jx = pos - jy * p.box_w;
-            orow = ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
-          }
-        }
-      }
+      const long long orow = conv_out_row(p, mt, r);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * 128);
       const bool bf16_rmw = !p.out_f32 && p.accum;
 #pragma unroll 1
@@ -340,8 +363,10 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             uint8_t* sA = smem + stage * k2StageBytes;
             uint8_t* sB = sA + k2StageABytes;
             if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
-            if (p.flat) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, (2 * mt + (int)rank) * p.rows_per_tile, 0, 0);
-            else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, (2 * mt + (int)rank) * p.rois_per_tile);
+            const int h = 2 * mt + (int)rank;
+            if (p.flat == 1) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, h * p.rows_per_tile, 0, 0);
+            else if (p.flat == 2) { const ImgTile it = img_tile(p, h); tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n); }
+            else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, h * p.rois_per_tile);
             tma_load_4d_2cta(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile + (int)rank * n_half, 0, 0);
             if (++stage == k2Stages) { stage = 0; phase ^= 1; }
           }
@@ -393,20 +418,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = q * 32 + lane;                  // row inside this CTA's half tile
-      long long orow = -1;
-      if (r < p.rows_per_tile) {
-        if (p.flat) {
-          long long m = (long long)(2 * mt + (int)rank) * p.rows_per_tile + r;
-          if (m < p.m_total) orow = m;
-        } else {
-          int rn = r / p.pos_per_roi, pos = r - rn * p.pos_per_roi;
-          int n = (2 * mt + (int)rank) * p.rois_per_tile + rn;
-          if (n < p.m_total) {
-            int jy = pos / p.box_w, jx = pos - jy * p.box_w;
-            orow = ((long long)n * p.Hf + jy * p.sy + p.oy) * p.Wf + jx * p.sx + p.ox;
-          }
-        }
-      }
+      const long long orow = conv_out_row(p, 2 * mt + (int)rank, r);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
       const bool bf16_rmw = !p.out_f32 && p.accum;
 #pragma unroll 1
@@ -523,6 +535,8 @@ struct WgradParams {
   int taps;
   int tap_x[9], tap_y[9], tap_b[9], tap_map[9];
   int flat;                   // 1: rows are flat; k-step j covers rows [64j, 64j+64)
+                              // 2: whole feature maps; k-step j = 8x8 patch (n, by, bx) of the output plane
+  int img_tiles_x, img_tiles_y;
   int rois_per_step;          // geometric: ROIs per k-step (box N dim)
   int total_steps;            // k-steps over the whole tensor
   int steps_per_split, num_splits;
@@ -587,14 +601,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           uint8_t* sA = smem + stage * kWgStageBytes;
           uint8_t* sB = sA + 32768;
           mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
+          int px0 = 0, py0 = 0, pn = s * p.rois_per_step;
+          if (p.flat == 2) {
+            const int per_img = p.img_tiles_x * p.img_tiles_y;
+            pn = s / per_img;
+            const int rem = s - pn * per_img;
+            py0 = rem / p.img_tiles_x;
+            px0 = (rem - py0 * p.img_tiles_x) * 8;
+            py0 *= 8;
+          }
           for (int g = 0; g < a_groups; ++g) {
-            if (p.flat) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, s * 64, 0, 0);
-            else tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, 0, 0, s * p.rois_per_step);
+            if (p.flat == 1) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, s * 64, 0, 0);
+            else tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, px0, py0, pn);
           }
           for (int g = 0; g < p.ci_groups; ++g) {
             const int c0 = cit * p.ci_tile + g * 64;
-            if (p.flat) tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, s * 64, 0, 0);
-            else tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, p.tap_x[t], p.tap_y[t], s * p.rois_per_step);
+            if (p.flat == 1) tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, s * 64, 0, 0);
+            else tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, px0 + p.tap_x[t], py0 + p.tap_y[t], pn);
           }
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "c2d_conv_simt.cuh"
+#include "c2d_conv_tc.h"
 #include "c2d_gemm_tc.cuh"
 #include "c2d_head_plan.h"
 
@@ -160,9 +161,6 @@ static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::C
   C2D_LAUNCH_OK();
   return C2D_OK;
 }
-
-struct OutSeg { void* out; int ld; int cols; };      // destination of a column range
-struct InSeg { const bf16* du; int ld; int cols; };  // one source of a merged 1x1 data gradient
 
 static void set_segments(tc::ConvGemmParams& p, const OutSeg* segs, int nseg) {
   p.nseg = nseg;
@@ -341,6 +339,32 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
   return C2D_OK;
 }
 
+// Splits the reduction rows into one wave of work items and launches the weight-gradient kernel.
+static int launch_wgrad(tc::WgradParams& p, const CUtensorMap& mapY, const CUtensorMap mapX[4], cudaStream_t st,
+                        double flops, bool two) {
+  const int base_items = p.taps * p.co_tiles * p.ci_tiles;
+  const int workers = two ? num_sms() / 2 : num_sms();
+  int splits = workers / base_items;         // one wave of items; every extra split is a dW-sized atomic pass
+  if (splits < 1) splits = 1;
+  if (splits > p.total_steps) splits = p.total_steps;
+  if (p.total_steps <= 0) return C2D_OK;
+  p.steps_per_split = (p.total_steps + splits - 1) / splits;
+  p.num_splits = (p.total_steps + p.steps_per_split - 1) / p.steps_per_split;
+  const int items = base_items * p.num_splits;
+  if (items <= 0) return C2D_OK;
+  ProfScope prof(st, 1, flops);
+  if (two) {
+    const int pairs = items < workers ? items : workers;
+    tc::wgrad_tc2_kernel<<<2 * pairs, tc::kWgThreads, tc::kWg2SmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  } else {
+    const int grid = items < num_sms() ? items : num_sms();
+    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+  }
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
 // Weight gradient: dw[cout][k*k][cin] (fp32, pre-zeroed by the caller) += du^T * x.
 static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaStream_t st,
                          float* dshift = nullptr) {
@@ -393,27 +417,135 @@ static int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw,
       }
     }
   }
-  const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  const int workers = two ? num_sms() / 2 : num_sms();
-  int splits = workers / base_items;         // one wave of items; every extra split is a dW-sized atomic pass
-  if (splits < 1) splits = 1;
-  if (splits > p.total_steps) splits = p.total_steps;
-  p.steps_per_split = (p.total_steps + splits - 1) / splits;
-  p.num_splits = (p.total_steps + p.steps_per_split - 1) / p.steps_per_split;
-  const int items = base_items * p.num_splits;
-  if (items <= 0 || p.total_steps <= 0) return C2D_OK;
-  ProfScope prof(st, 1, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout);
-  if (two) {
-    const int pairs = items < workers ? items : workers;
-    tc::wgrad_tc2_kernel<<<2 * pairs, tc::kWgThreads, tc::kWg2SmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
-  } else {
-    const int grid = items < num_sms() ? items : num_sms();
-    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
-  }
-  count_launch();
-  C2D_LAUNCH_OK();
-  return C2D_OK;
+  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout, two);
 }
+
+// ---- whole-feature-map convolutions (backbone): image-patch tiles, same kernels ----------------------------
+// NHWC activation [n, h, w, C]; box = (64, bw, bh, 1).
+static bool make_map_img(CUtensorMap* m, const void* base, long long C, int h, int w, long long n, long long ld,
+                         int bw, int bh) {
+  long long d[4] = {C, w, h, n};
+  long long es[4] = {1, ld, ld * w, ld * w * h};
+  int b[4] = {64, bw, bh, 1};
+  return make_map(m, base, d, es, b);
+}
+// Parity view (py, px): element (qx, qy) = pixel (2*qy + py, 2*qx + px).
+static bool make_map_img_parity(CUtensorMap* m, const bf16* base, long long C, int h, int w, long long n, long long ld,
+                                int py, int px, int bw, int bh) {
+  const int hq = (h - py + 1) / 2, wq = (w - px + 1) / 2;
+  long long d[4] = {C, wq > 0 ? wq : 1, hq > 0 ? hq : 1, n};
+  long long es[4] = {1, 2 * ld, 2 * ld * w, ld * w * h};
+  int b[4] = {64, bw, bh, 1};
+  return make_map(m, base + ((long long)py * w + px) * ld, d, es, b);
+}
+static void set_img_tiles(tc::ConvGemmParams& p, int n, int H, int W, bool two) {
+  p.flat = 2; p.img_tw = 16;
+  const int th = two ? 8 : 16;
+  p.rows_per_tile = 16 * th; p.a_box_bytes = p.rows_per_tile * 128;
+  p.img_tiles_x = (W + 15) / 16; p.img_tiles_y = (H + th - 1) / th;
+  const long long halves = (long long)n * p.img_tiles_x * p.img_tiles_y;
+  p.num_m_tiles = (int)(two ? (halves + 1) / 2 : halves);
+  p.m_total = n; p.Hf = H; p.Wf = W; p.sy = p.sx = 1; p.oy = p.ox = 0;
+}
+static int same_pad_before(int in, int out, int k, int stride) {
+  int total = (out - 1) * stride + k - in;
+  return total > 0 ? total / 2 : 0;
+}
+static ConvDesc flat_desc(const ImgConv& c, long long rows) {
+  ConvDesc d;
+  memset(&d, 0, sizeof(d));
+  d.n = (int)rows; d.k = 1; d.stride = 1; d.hin = d.hout = 1; d.cin = c.cin; d.cout = c.cout; d.x = c.x; d.ldx = c.ldx;
+  return d;
+}
+
+int conv_img_fwd_tc(const ImgConv& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
+                    int out_f32, cudaStream_t st) {
+  if (c.k == 1) {
+    C2D_CHECK_ARG(c.stride == 1, "conv_img_fwd: 1x1 convolutions are stride 1");
+    return conv_fwd_tc(flat_desc(c, (long long)c.n * c.hin * c.win), w16, shift, relu, segs, nseg, out_f32, st);
+  }
+  C2D_CHECK_ARG(c.k == 3 && (c.stride == 1 || c.stride == 2), "conv_img_fwd: k must be 1 or 3, stride 1 or 2");
+  tc::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4], mapB;
+  const bool two = use_2cta(true, 1);
+  set_segments(p, segs, nseg);
+  const int cout = p.n_total;
+  set_n_tiles(p, two);
+  p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
+  if (!make_map_flat(&mapB, w16, 9LL * c.cin, cout, 9LL * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
+  const int chunks = (c.cin + 63) / 64;
+  p.taps = 9;
+  set_img_tiles(p, c.n, c.hout, c.wout, two);
+  const int th = p.rows_per_tile / 16;
+  for (int t = 0; t < 9; ++t) { p.tap_chunks[t] = chunks; p.tap_koff[t] = t * c.cin; }
+  if (c.stride == 1) {
+    if (!make_map_img(&maps[0], c.x, c.cin, c.hin, c.win, c.n, c.ldx, 16, th)) return C2D_ERR_CUDA;
+    maps[1] = maps[2] = maps[3] = maps[0];
+    for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_map[t] = 0; }
+  } else {
+    // input index = 2*o + d - pad_before: parity (d - pb) & 1 of the parity view, coordinate o + floor((d - pb) / 2)
+    const int pby = same_pad_before(c.hin, c.hout, 3, 2), pbx = same_pad_before(c.win, c.wout, 3, 2);
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px)
+        if (!make_map_img_parity(&maps[py * 2 + px], c.x, c.cin, c.hin, c.win, c.n, c.ldx, py, px, 16, th)) return C2D_ERR_CUDA;
+    for (int t = 0; t < 9; ++t) {
+      const int ey = t / 3 - pby, ex = t % 3 - pbx;          // in {-1, 0, 1, 2}
+      const int py = ey & 1, px = ex & 1;
+      p.tap_y[t] = (ey - py) / 2; p.tap_x[t] = (ex - px) / 2;
+      p.tap_map[t] = py * 2 + px;
+    }
+  }
+  return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.wout * 9.0 * c.cin * cout, two);
+}
+
+int conv_img_dgrad_tc(const ImgConv& c, const bf16* du, int lddu, const bf16* wt16, bf16* dx, int lddx,
+                      const bf16* mask, cudaStream_t st) {
+  C2D_CHECK_ARG(c.k == 3 && c.stride == 1, "conv_img_dgrad: only 3x3 stride-1 convolutions");
+  tc::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap maps[4], mapB;
+  const bool two = use_2cta(true, 1);
+  OutSeg oseg = {dx, lddx, c.cin};
+  set_segments(p, &oseg, 1);
+  set_n_tiles(p, two);
+  p.mask = mask; p.mask_ld = lddx; p.mask_cols = mask ? c.cin : 0;
+  if (!make_map_flat(&mapB, wt16, 9LL * c.cout, c.cin, 9LL * c.cout, b_box_rows(p, two))) return C2D_ERR_CUDA;
+  p.taps = 9;
+  set_img_tiles(p, c.n, c.hin, c.win, two);
+  if (!make_map_img(&maps[0], du, c.cout, c.hout, c.wout, c.n, lddu, 16, p.rows_per_tile / 16)) return C2D_ERR_CUDA;
+  maps[1] = maps[2] = maps[3] = maps[0];
+  const int chunks = (c.cout + 63) / 64;
+  for (int t = 0; t < 9; ++t) {     // dx[y,x] = sum_{dy,dx} du[y + 1 - dy, x + 1 - dx] * w[dy,dx]
+    p.tap_y[t] = 1 - t / 3; p.tap_x[t] = 1 - t % 3; p.tap_koff[t] = t * c.cout; p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
+  }
+  return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.wout * 9.0 * c.cin * c.cout, two);
+}
+
+int conv_img_wgrad_tc(const ImgConv& c, const bf16* du, int lddu, float* dw, float* dshift, cudaStream_t st) {
+  if (c.k == 1) return conv_wgrad_tc(flat_desc(c, (long long)c.n * c.hin * c.win), du, lddu, dw, st, dshift);
+  C2D_CHECK_ARG(c.k == 3 && c.stride == 1, "conv_img_wgrad: only 1x1 and 3x3 stride-1 convolutions");
+  int rc = tc_prepare();
+  if (rc != C2D_OK) return rc;
+  tc::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap mapY, mapX[4];
+  p.taps = 9; p.taps_total = 9;
+  p.cout = c.cout; p.cin = c.cin; p.dw = dw; p.dshift = dshift;
+  p.co_tiles = (c.cout + 255) / 256;
+  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, 16);
+  p.ci_groups = (p.ci_tile + 63) / 64;
+  p.flat = 2;
+  p.img_tiles_x = (c.wout + 7) / 8; p.img_tiles_y = (c.hout + 7) / 8;
+  p.total_steps = c.n * p.img_tiles_x * p.img_tiles_y;
+  if (!make_map_img(&mapY, du, c.cout, c.hout, c.wout, c.n, lddu, 8, 8)) return C2D_ERR_CUDA;
+  if (!make_map_img(&mapX[0], c.x, c.cin, c.hin, c.win, c.n, c.ldx, 8, 8)) return C2D_ERR_CUDA;
+  mapX[1] = mapX[2] = mapX[3] = mapX[0];
+  for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_b[t] = t; p.tap_map[t] = 0; }
+  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.wout * 9.0 * c.cin * c.cout, false);
+}
+
+void launch_cast_f32_bf16(const float* x, bf16* y, long long n, cudaStream_t st);
 
 // ---- small helpers ----------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, long long n) {
@@ -429,6 +561,7 @@ static void launch_cast(const float* x, bf16* y, long long n, cudaStream_t st) {
   cast_f32_bf16_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, st>>>(x, y, n);
   count_launch();
 }
+void launch_cast_f32_bf16(const float* x, bf16* y, long long n, cudaStream_t st) { launch_cast(x, y, n, st); }
 
 // All 19 convolutions folded / unfolded by ONE launch each (grid.y = convolution).
 struct FoldEntry {

@@ -139,6 +139,95 @@ def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True):
 
 
 # ---------------------------------------------------------------------------------------------
+# First stage: Inception-v2 up to Mixed_4e on whole images  (models/utils.py:127-136)
+# ---------------------------------------------------------------------------------------------
+BACKBONE_STEM_SCOPE = 'Conv2d_1a_7x7'
+
+
+def backbone_conv_specs():
+  """[(tf_scope, k, cin, cout, stride, offsets dict)] of the packed first-stage parameter buffer; the
+  separable stem comes first with offsets 'depthwise_weights' [7,7,3,8] and 'pointwise_weights' [64,24]."""
+  import ctypes
+  lib = capi.load()
+  names = ('weights', 'gamma', 'beta', 'moving_mean', 'moving_variance')
+  offs = [ctypes.c_longlong() for _ in range(5)]
+  capi.check(lib.c2d_backbone_param_offsets(-1, *[ctypes.byref(o) for o in offs]))
+  stem = dict(zip(names, [o.value for o in offs]))
+  stem['depthwise_weights'] = stem.pop('weights')
+  stem['pointwise_weights'] = stem['depthwise_weights'] + 7 * 7 * 3 * 8
+  out = [(BACKBONE_STEM_SCOPE, 7, 3, 64, 2, stem)]
+  for i in range(lib.c2d_backbone_num_convs()):
+    k, cin, cout, stride = (ctypes.c_int() for _ in range(4))
+    name = ctypes.c_char_p()
+    capi.check(lib.c2d_backbone_conv_spec(i, ctypes.byref(k), ctypes.byref(cin), ctypes.byref(cout),
+                                          ctypes.byref(stride), ctypes.byref(name)))
+    capi.check(lib.c2d_backbone_param_offsets(i, *[ctypes.byref(o) for o in offs]))
+    out.append((name.value.decode(), k.value, cin.value, cout.value, stride.value,
+                dict(zip(names, [o.value for o in offs]))))
+  return out
+
+
+def backbone_param_floats():
+  return int(capi.load().c2d_backbone_param_floats())
+
+
+def backbone_out_dims(height, width):
+  import ctypes
+  hf, wf = ctypes.c_int(), ctypes.c_int()
+  capi.check(capi.load().c2d_backbone_out_dims(int(height), int(width), ctypes.byref(hf), ctypes.byref(wf)))
+  return hf.value, wf.value
+
+
+class _BackboneInceptionV2(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, image, params):
+    require_cuda(image, params)
+    _f32(image); _f32(params)
+    B, H, W, C = image.shape
+    if C != 3:
+      raise ValueError('backbone expects [B,H,W,3] images, got %s' % (tuple(image.shape),))
+    Hf, Wf = backbone_out_dims(H, W)
+    nbytes = capi.load().c2d_backbone_workspace_bytes(B, H, W)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=image.device)
+    fmap = torch.empty((B, Hf, Wf, BACKBONE_OUT_CH), dtype=torch.float32, device=image.device)
+    call('c2d_backbone_fwd', ptr(image), B, H, W, ptr(params), ptr(ws), nbytes, ptr(fmap), stream())
+    ctx.save_for_backward(params, ws, fmap)
+    ctx.shape = (B, H, W)
+    return fmap
+
+  @staticmethod
+  def backward(ctx, dfmap):
+    params, ws, fmap = ctx.saved_tensors
+    B, H, W = ctx.shape
+    dparams = torch.empty_like(params)
+    call('c2d_backbone_bwd', ptr(dfmap.contiguous()), ptr(fmap), B, H, W, ptr(params), ptr(ws), ws.numel(),
+         ptr(dparams), stream())
+    return None, dparams
+
+
+BACKBONE_OUT_CH = 576
+
+
+def backbone_mixed4e_input(fmap):
+  """Parity-test hook: the Mixed_4e input (bf16 [B,Hf,Wf,576]) of the forward pass that produced ``fmap``."""
+  fn = fmap.grad_fn
+  if fn is None or not hasattr(fn, 'saved_tensors'):
+    raise ValueError('fmap must come from backbone_inception_v2 with a params tensor that requires grad')
+  _, ws, _ = fn.saved_tensors
+  B, H, W = fn.shape
+  x = torch.empty(tuple(fmap.shape), dtype=torch.bfloat16, device=fmap.device)
+  call('c2d_backbone_mixed4e_input', ptr(ws), B, H, W, ptr(x), stream())
+  return x
+
+
+def backbone_inception_v2(image, params):
+  """image [B,H,W,3] fp32 pixel values in [0,255], packed first-stage params fp32 -> features_to_crop
+  [B,ceil(H/16),ceil(W/16),576] fp32.  Backward yields the Mixed_4e variable gradients only."""
+  return _BackboneInceptionV2.apply(image.contiguous(), params)
+
+
+# ---------------------------------------------------------------------------------------------
 # K4: concatenated fully connected layers  (models/cap2det_model.py:79-88,190-197)
 # ---------------------------------------------------------------------------------------------
 def _ld16(n):

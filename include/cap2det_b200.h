@@ -107,6 +107,48 @@ int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* para
                         size_t workspace_bytes, const float* keep_mask, float keep_prob,
                         const float* dfeat, float* dparams, void* dx0, c2d_stream_t stream);
 
+/* ---- first-stage feature extractor, models/utils.py:127-136 ------------------------------
+ * feature_extractor.preprocess ((2/255) x - 1) + extract_proposal_features(scope
+ * 'first_stage_feature_extraction') = slim inception_v2_base up to Mixed_4e (OD-API
+ * faster_rcnn_inception_v2; neither slim nor the OD-API is vendored in the reference).  BN uses the
+ * frozen moving statistics (eps 1e-3).  bf16 activations, fp32 accumulation, fp32 feature map.
+ * Parameters live in ONE packed fp32 buffer: the separable stem Conv2d_1a_7x7 (index -1: depthwise
+ * [7,7,3,8] in TF layout, then pointwise [64,24], then gamma, beta, moving_mean, moving_variance [64])
+ * followed by conv i = weights OHWI [cout,k,k,cin], gamma, beta, moving_mean, moving_variance [cout]. */
+int c2d_backbone_num_convs(void);
+int c2d_backbone_conv_spec(int i, int* k, int* cin, int* cout, int* stride, const char** tf_scope);
+long long c2d_backbone_param_floats(void);
+int c2d_backbone_param_offsets(int i, long long* weights, long long* gamma, long long* beta,
+                               long long* mean, long long* var);
+/* Feature-map size for an H x W image (stride 16, every stage SAME: ceil(ceil(ceil(ceil(H/2)/2)/2)/2)). */
+int c2d_backbone_out_dims(int H, int W, int* Hf, int* Wf);
+size_t c2d_backbone_workspace_bytes(int B, int H, int W);
+/* image [B,H,W,3] fp32 pixel values in [0,255] -> fmap [B,Hf,Wf,576] fp32.  The workspace keeps the
+ * Mixed_4e activations for c2d_backbone_bwd. */
+int c2d_backbone_fwd(const float* image, int B, int H, int W, const float* params, void* workspace,
+                     size_t workspace_bytes, float* fmap, c2d_stream_t stream);
+/* Gradients of the Mixed_4e variables (the only first-stage block any reference config trains,
+ * configs/voc07_groundtruth.pbtxt:112-123); every other entry of dparams is set to 0. */
+int c2d_backbone_bwd(const float* dfmap, const float* fmap, int B, int H, int W, const float* params,
+                     void* workspace, size_t workspace_bytes, float* dparams, c2d_stream_t stream);
+
+/* Parity-test hook: copies the Mixed_4e INPUT (= Mixed_4d output, bf16 [B,Hf,Wf,576]) out of a workspace
+ * c2d_backbone_fwd filled, so the trainable block can be checked on identical inputs. */
+int c2d_backbone_mixed4e_input(const void* workspace, int B, int H, int W, void* x, c2d_stream_t stream);
+
+/* Building blocks of the first stage, exposed for the parity tests: SAME-padded k x k convolution
+ * (slim.conv2d) on whole [n, h, w, c] NHWC bf16 feature maps with leading dimensions; k is 1 or 3,
+ * stride 1 (forward also 2 with k 3; hout = ceil(hin/2), TF pad_before = pad_total / 2).  Same operand
+ * layouts as c2d_conv_bf16_*; dgrad takes an optional ReLU mask (dx = 0 where mask <= 0, same layout
+ * as dx); wgrad accumulates into pre-zeroed dw and, when not NULL, dshift [cout] (column sums of dy). */
+int c2d_conv_img_bf16_fwd(const void* x, int ldx, int n, int hin, int win, int cin, const void* w16,
+                          int cout, int k, int stride, const float* shift, int relu, void* y, int ldy,
+                          c2d_stream_t stream);
+int c2d_conv_img_bf16_dgrad(const void* dy, int lddy, int n, int h, int w, int cin, const void* wt16,
+                            int cout, const void* mask, void* dx, int lddx, c2d_stream_t stream);
+int c2d_conv_img_bf16_wgrad(const void* x, int ldx, const void* dy, int lddy, int n, int h, int w,
+                            int cin, int cout, int k, float* dw, float* dshift, c2d_stream_t stream);
+
 /* Building blocks of the bf16 (tcgen05/TMEM/TMA) head path, exposed for the parity tests: SAME-padded
  * k x k convolution (the slim.conv2d inside Mixed_5a-c) on [n, hin, hin, cin] NHWC bf16 maps with leading
  * dimension ldx; hin is 7 or 4, k is 1 or 3, stride 1 (or 2 with hin 7, k 3).  fp32 accumulation.

@@ -90,3 +90,30 @@ def test_nms_tie_rule_lower_index_first():
 def test_seq_sum_matches_numpy_on_exact_values():
   x = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
   np.testing.assert_array_equal(box_ops.seq_sum(x, 1), x.sum(1, keepdims=True))
+
+
+# ---- first-stage oracle (oracle/backbone.py) ------------------------------------------------------
+def test_backbone_oracle_shapes_and_same_padding():
+  """TF SAME arithmetic and the stride-16 output size; Mixed_4e concat = 96 + 192 + 192 + 96 channels."""
+  import numpy as np
+  import torch
+  from oracle import backbone as ob
+  assert ob.same_pads(7, 3, 2) == (1, 1) and ob.same_pads(8, 3, 2) == (0, 1)
+  assert ob.same_pads(600, 7, 2) == (2, 3) and ob.same_pads(75, 7, 2) == (3, 3)
+  assert ob.same_pads(9, 3, 1) == (1, 1) and ob.same_pads(9, 1, 1) == (0, 0)
+  assert len(ob.BACKBONE_CONVS) == 49
+  chans = {}
+  for name, k, cin, cout, s in ob.BACKBONE_CONVS:
+    chans.setdefault(name.split('/')[0], []).append((name, cout))
+  out_4e = sum(c for n, c in chans['Mixed_4e'] if n.endswith(('Branch_0/Conv2d_0a_1x1', 'Conv2d_0b_3x3', 'Conv2d_0c_3x3',
+                                                              'Branch_3/Conv2d_0b_1x1')) and 'Branch_2/Conv2d_0b' not in n)
+  assert out_4e == 576
+  p = ob.random_backbone_params(seed=1)
+  img = np.random.default_rng(2).uniform(0, 255, size=(1, 49, 66, 3)).astype(np.float32)
+  with torch.no_grad():
+    y = ob.inception_v2_mixed_4e(img, p)
+    y16 = ob.inception_v2_mixed_4e(img, p, emulate_bf16=True)
+  assert tuple(y.shape) == (1, 4, 5, 576)
+  assert bool((y >= 0).all()) and float(y.max()) > 0
+  err = float((y16 - y).norm() / y.norm())
+  assert 0 < err < 3e-2                # bf16 storage emulation stays within bf16 noise of fp32
