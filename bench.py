@@ -50,7 +50,7 @@ def make_host_batch(seed, B, P, vocab, plant):
               captions=synthetic.make_captions(rng, B, vocab, plant, captions_per_image=CONFIG['captions_per_image']))
 
 
-def build_model(workdir, head_dtype, seed=0):
+def build_model(workdir, head_dtype, seed=0, first_stage=False):
   import torch
   from cap2det_b200 import builder, config, synthetic
   classes = synthetic.COCO_CLASSES
@@ -60,7 +60,7 @@ def build_model(workdir, head_dtype, seed=0):
   m = config.Model()
   m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
   dt = torch.bfloat16 if head_dtype == 'bf16' else torch.float32
-  return builder.build(m, is_training=True), classes
+  return builder.build(m, is_training=True, head_dtype=dt, first_stage=first_stage), classes
 
 
 class ClockSampler(object):
@@ -177,6 +177,7 @@ def main():
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--head-dtype', default=os.environ.get('C2D_HEAD_DTYPE', 'auto'), choices=['auto', 'bf16', 'f32'])
+  ap.add_argument('--no-first-stage', action='store_true', help='skip the extra from-images measurement')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-kernel-table', action='store_true')
   args = ap.parse_args()
@@ -207,8 +208,6 @@ def main():
   workdir = tempfile.mkdtemp()
   B, P = CONFIG['images_per_gpu'], CONFIG['proposals']
   model, classes = build_model(workdir, head_dtype)
-  if head_dtype == 'bf16':
-    model._head_dtype = torch.bfloat16
   if world > 1:   # identical replicas
     for v in model.get_variables_to_train():
       dist.broadcast(v.data, src=0)
@@ -304,6 +303,32 @@ def main():
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
                       ms_per_step=e2e_ms / args.steps))
+  if not args.no_first_stage and head_dtype == 'bf16':
+    # the same step fed with IMAGES (600x1000x3 uint8, resident) instead of feature maps:
+    # Inception-v2 first stage forward + Mixed_4e backward in front of / behind the proposal path.
+    model_fs, _ = build_model(workdir, head_dtype, first_stage=True)
+    if world > 1:
+      for v in model_fs.get_variables_to_train():
+        dist.broadcast(v.data, src=0)
+    step_fs = trainer.TrainStep(model_fs, learning_rate=0.01, world_size=world)
+    rng_img = np.random.default_rng(77 + rank)
+    H, W = 600, 1000          # the image size behind the 38x63 stride-16 feature map
+    imgs = [torch.from_numpy(rng_img.integers(0, 256, size=(B, H, W, 3)).astype(np.uint8)).to(dev) for _ in range(2)]
+
+    def run_images(i):
+      ex = dict(resident[i % n_pool])
+      del ex[F.features_to_crop]
+      ex[F.image] = imgs[i % 2]
+      return step_fs(ex)
+
+    fs_ms, fs_launches, _ = timed(run_images, 3, args.steps)
+    model_fs.raise_if_assert_failed()
+    out['with_first_stage'] = dict(
+        workload='same step from images [B,%d,%d,3]: Inception-v2 to Mixed_4e fwd + Mixed_4e bwd added' % (H, W),
+        ms_per_step=fs_ms / args.steps, images_per_sec=world * B / (fs_ms / args.steps / 1e3),
+        proposals_per_sec=props_per_step / (fs_ms / args.steps / 1e3), gpu_launches=fs_launches,
+        first_stage_ms_per_step=(fs_ms - total_ms) / args.steps)
+    del model_fs, step_fs, imgs
   peaks = load_peaks()
   dominant = None
   if not args.no_kernel_table and head_dtype == 'bf16':

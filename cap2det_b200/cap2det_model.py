@@ -8,8 +8,10 @@ models/cap2det_model.py:201-214 and :142-149), ``build_loss(predictions, example
 kernels eagerly on the current CUDA stream and the loss tensors carry autograd history whose
 backward nodes call the fused CUDA backward kernels.
 
-The backbone (first_stage_feature_extraction) is outside this path: callers pass the stride-16
-feature map as ``examples['features_to_crop']`` ([B,Hf,Wf,576] NHWC fp32).
+Inputs of the proposal path: either the stride-16 feature map as ``examples['features_to_crop']``
+([B,Hf,Wf,576] NHWC fp32 -- the hot path of BASELINE.json starts here), or, for a model built with
+``first_stage=True``, the image as ``examples['image']`` ([B,H,W,3], pixel values in [0,255]), which runs
+through the Inception-v2 first stage (models/utils.py:127-136) on the same tensor-core kernels.
 """
 import math
 
@@ -26,6 +28,7 @@ from cap2det_b200.standard_fields import DetectionResultFields
 from cap2det_b200.standard_fields import InputDataFields
 
 _HEAD_SCOPE = 'second_stage_feature_extraction/InceptionV2/'
+_FIRST_STAGE_SCOPE = 'first_stage_feature_extraction/InceptionV2/'
 
 
 def _trunc_normal_(t, std, gen):
@@ -36,7 +39,8 @@ def _trunc_normal_(t, std, gen):
 class Model(ModelBase):
   """Cap2Det model."""
 
-  def __init__(self, model_proto, is_training=False, device=None, head_dtype=torch.float32, seed=0):
+  def __init__(self, model_proto, is_training=False, device=None, head_dtype=torch.float32, seed=0,
+               first_stage=False):
     """Initializes the model.
 
     Args:
@@ -45,6 +49,8 @@ class Model(ModelBase):
       device: CUDA device (default: current).
       head_dtype: torch.float32 (CUDA-core fp32 path, 1e-5 parity) or torch.bfloat16
         (tcgen05 tensor-core path, 2e-2 parity) for the ROI tensor and the Mixed_5 head.
+      first_stage: also own the first-stage (Inception-v2 up to Mixed_4e) variables, so that
+        ``examples['image']`` can replace ``examples['features_to_crop']``.
     """
     super(Model, self).__init__(model_proto, is_training)
     if not isinstance(model_proto, config.Cap2DetModel):
@@ -57,6 +63,9 @@ class Model(ModelBase):
     self._label_extractor = build_label_extractor(options.label_extractor, self._device)
     self._assert_status = None
     self._init_variables(seed)
+    self.backbone_params = None
+    if first_stage:
+      self._init_first_stage(seed + 1)
 
   # ---- variables ------------------------------------------------------------------------------
   def _init_variables(self, seed):
@@ -95,9 +104,31 @@ class Model(ModelBase):
     self._col_r, self._col_c = 0, C
     self._col_oicr = [2 * C + i * (C + 1) for i in range(K)]
 
+  def _init_first_stage(self, seed):
+    """Random first-stage variables (the reference restores them from the ImageNet checkpoint named by
+    frcnn_options.checkpoint_path; use ``named_variables`` to load real weights).  Variance-preserving
+    init so that 20 layers deep the feature map keeps unit scale."""
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(seed)
+    self._backbone_specs = ops.backbone_conv_specs()
+    buf = torch.zeros((ops.backbone_param_floats(),), dtype=torch.float32)
+    for name, k, cin, cout, _, off in self._backbone_specs:
+      if name == ops.BACKBONE_STEM_SCOPE:
+        buf[off['depthwise_weights']:off['depthwise_weights'] + 1176].normal_(0.0, math.sqrt(2.0 / 49), generator=gen)
+        buf[off['pointwise_weights']:off['pointwise_weights'] + 1536].normal_(0.0, math.sqrt(2.0 / 24), generator=gen)
+      else:
+        nw = cout * k * k * cin
+        buf[off['weights']:off['weights'] + nw].normal_(0.0, math.sqrt(2.0 / (k * k * cin)), generator=gen)
+      buf[off['gamma']:off['gamma'] + cout] = 1.0
+      buf[off['moving_variance']:off['moving_variance'] + cout] = 1.0
+    self.backbone_params = buf.to(self._device).requires_grad_(True)
+
   def get_variables_to_train(self):
-    """models/model_base.py:60-66: all trainable variables."""
-    return [self.head_params, self.fc_weights, self.fc_biases]
+    """models/model_base.py:60-66: all trainable variables (the first stage only yields Mixed_4e gradients)."""
+    out = [self.head_params, self.fc_weights, self.fc_biases]
+    if self.backbone_params is not None:
+      out.append(self.backbone_params)
+    return out
 
   def named_variables(self):
     """TF variable name -> view (head weights are OHWI = transposed TF HWIO; FC weights [out,in])."""
@@ -110,6 +141,17 @@ class Model(ModelBase):
       out[scope + '/BatchNorm/beta'] = hp[off['beta']:off['beta'] + cout]
       out[scope + '/BatchNorm/moving_mean'] = hp[off['moving_mean']:off['moving_mean'] + cout]
       out[scope + '/BatchNorm/moving_variance'] = hp[off['moving_variance']:off['moving_variance'] + cout]
+    if self.backbone_params is not None:
+      bp = self.backbone_params.detach()
+      for name, k, cin, cout, _, off in self._backbone_specs:
+        scope = _FIRST_STAGE_SCOPE + name
+        if name == ops.BACKBONE_STEM_SCOPE:     # TF layouts: depthwise HWCM [7,7,3,8]; pointwise here [out,in]
+          out[scope + '/depthwise_weights'] = bp[off['depthwise_weights']:off['depthwise_weights'] + 1176].view(7, 7, 3, 8)
+          out[scope + '/pointwise_weights'] = bp[off['pointwise_weights']:off['pointwise_weights'] + 1536].view(64, 24)
+        else:
+          out[scope + '/weights'] = bp[off['weights']:off['weights'] + cout * k * k * cin].view(cout, k, k, cin)
+        for v in ('gamma', 'beta', 'moving_mean', 'moving_variance'):
+          out[scope + '/BatchNorm/' + v] = bp[off[v]:off[v] + cout]
     C = self._num_classes
     fw, fb = self.fc_weights.detach(), self.fc_biases.detach()
     out['midn/proba_r_given_c/weights'] = fw[0:C]; out['midn/proba_r_given_c/biases'] = fb[0:C]
@@ -180,6 +222,18 @@ class Model(ModelBase):
       results[DetectionResultFields.detection_classes + '_at_{}'.format(i)] = classes
     return results
 
+  def _first_stage(self, images):
+    """models/utils.py:127-136: preprocess + extract_proposal_features.  A list of images (one per entry of
+    eval_min_dimension, already resized) yields a list of feature maps."""
+    if images is None:
+      raise ValueError("examples needs 'features_to_crop' or 'image'")
+    if self.backbone_params is None:
+      raise ValueError("examples['image'] needs a model built with first_stage=True "
+                       "(otherwise pass the stride-16 feature map as examples['features_to_crop'])")
+    if isinstance(images, (list, tuple)):
+      return [self._first_stage(im) for im in images]
+    return ops.backbone_inception_v2(images.to(torch.float32), self.backbone_params)
+
   def build_prediction(self, examples, postprocess=None, **kwargs):
     """models/cap2det_model.py:218-272.
 
@@ -193,9 +247,7 @@ class Model(ModelBase):
       postprocess = not self._is_training
     fmaps = examples.get(InputDataFields.features_to_crop)
     if fmaps is None:
-      raise NotImplementedError(
-          "examples['features_to_crop'] is required: the Inception-v2 backbone (first_stage_feature_extraction) "
-          'is outside the proposal hot path (SURVEY.md 8(f) rank 2)')
+      fmaps = self._first_stage(examples.get(InputDataFields.image))
     if self._is_training or len(options.eval_min_dimension) == 0:
       if isinstance(fmaps, (list, tuple)):
         raise ValueError('a single feature map is expected outside multi-scale evaluation')

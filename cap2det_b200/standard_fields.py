@@ -18,9 +18,9 @@ class InputDataFields(object):
   object_texts = 'object_texts'
   proposals = 'proposals'
   num_proposals = 'number_of_proposals'
-  # Added key: the backbone (first_stage) feature map [B,Hf,Wf,576] NHWC.  The reference computes
-  # it from `image` inside extract_frcnn_feature (models/utils.py:127-136); the backbone is outside
-  # this path, so callers hand the map in directly.
+  # Added key: the first-stage feature map [B,Hf,Wf,576] NHWC, where the hot path of BASELINE.json starts.
+  # The reference computes it from `image` inside extract_frcnn_feature (models/utils.py:127-136); a model
+  # built with first_stage=True does the same when only `image` is given.
   features_to_crop = 'features_to_crop'
   # Added key (tests only): an injected {0,1} dropout keep mask [B*P,1024].
   dropout_keep_mask = 'dropout_keep_mask'

@@ -168,7 +168,7 @@ class TrainStep(object):
     if train_config is None:
       # slim regularises FC weights only (biases and the conv head have no regulariser on this path)
       self.base_lr = float(learning_rate)
-      self.opt = Adagrad(variables, learning_rate, l2_scales=[0.0, l2, 0.0])
+      self.opt = Adagrad(variables, learning_rate, l2_scales=[l2 if v is model.fc_weights else 0.0 for v in variables])
       return
     if train_config.sync_replicas:
       raise ValueError('sync_replicas (SyncReplicasOptimizer over a parameter server, train/trainer.py:90-94) is '

@@ -189,3 +189,58 @@ def test_backbone_full_size_properties():
   one = ops.backbone_inception_v2(img[1:2].contiguous(), p)
   assert torch.equal(one[0], a[1])
   assert float((a > 0).float().mean()) > 0.05
+
+
+def test_model_from_images_trains_mixed_4e_only():
+  """examples['image'] through a first_stage=True model == examples['features_to_crop'] fed with the first-stage
+  output; one TrainStep moves Mixed_4e and the second stage, and nothing below Mixed_4e
+  (configs/voc07_groundtruth.pbtxt:112-123)."""
+  import tempfile
+  from cap2det_b200 import builder, config, ops, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=True, head_dtype=torch.bfloat16, first_stage=True)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+  B, P, H, W = 2, 24, 160, 208
+  rng = np.random.default_rng(51)
+  img = torch.from_numpy(rng.integers(0, 256, size=(B, H, W, 3)).astype(np.uint8)).cuda()
+  props = torch.from_numpy(synthetic.make_proposals(rng, B, P, H, W)).cuda()
+  ex = {F.image: img, F.num_proposals: torch.full((B,), P, dtype=torch.int32, device='cuda'), F.proposals: props,
+        F.object_texts: synthetic.make_object_texts(rng, B, classes),
+        F.dropout_keep_mask: torch.from_numpy((rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)).cuda()}
+  loss_img = model.build_loss(model.build_prediction(ex), ex)
+  fmap = ops.backbone_inception_v2(img.float(), model.backbone_params.detach())
+  assert fmap.shape == (B, 10, 13, 576)
+  ex2 = dict(ex); del ex2[F.image]; ex2[F.features_to_crop] = fmap
+  loss_fm = model.build_loss(model.build_prediction(ex2), ex2)
+  for k in loss_img:
+    # the loss reductions use atomics: equal up to fp32 summation order
+    assert abs(float(loss_img[k].detach()) - float(loss_fm[k].detach())) <= 1e-6 * abs(float(loss_fm[k].detach())), k
+
+  names = model.named_variables()
+  assert 'first_stage_feature_extraction/InceptionV2/Conv2d_1a_7x7/depthwise_weights' in names
+  before = {n: v.clone() for n, v in names.items()}
+  tc = config.parse_text("""
+    learning_rate: 0.01 optimizer { adagrad { } } moving_average_decay: 0.0
+    gradient_multiplier { scope: 'first_stage_feature_extraction' multiplier: 0.0 }
+    gradient_multiplier { scope: 'second_stage_feature_extraction' multiplier: 1.0 }
+    gradient_multiplier { scope: 'first_stage_feature_extraction/InceptionV2/Mixed_4e' multiplier: 1.0 }
+  """, config.TrainConfig)
+  step = trainer.TrainStep.from_pipeline(model, config.Pipeline(train_config=tc))
+  total = step(ex)
+  assert np.isfinite(float(total))
+  moved = {n: bool((model.named_variables()[n] != before[n]).any()) for n in before}
+  for n, mv in moved.items():
+    stat = n.endswith('moving_mean') or n.endswith('moving_variance')
+    if n.startswith('first_stage_feature_extraction/InceptionV2/Mixed_4e') and not stat:
+      assert mv, n
+    elif n.startswith('first_stage_feature_extraction') or stat:
+      assert not mv, n
+  assert moved['second_stage_feature_extraction/InceptionV2/Mixed_5a/Branch_0/Conv2d_0a_1x1/weights']
+  assert moved['midn/proba_r_given_c/weights'] and moved['oicr/iter3/weights']
