@@ -68,17 +68,27 @@ static const BbLayout& bb_layout() {
     L.stem_dw = o; o += kStemDw;
     L.stem_pw = o; o += kStemPw;
     L.stem_gamma = o; o += kStemCh; L.stem_beta = o; o += kStemCh; L.stem_mean = o; o += kStemCh; L.stem_var = o; o += kStemCh;
-    long long w16 = 0, wt16 = 0, ch = 0;
     for (int i = 0; i < kNumBbConvs; ++i) {
       const BbConv& c = kBbConvs[i];
       const long long nw = (long long)c.cout * c.k * c.k * c.cin;
       L.c[i].w = o; o += nw;
       L.c[i].gamma = o; o += c.cout; L.c[i].beta = o; o += c.cout; L.c[i].mean = o; o += c.cout; L.c[i].var = o; o += c.cout;
+    }
+    // Folded bf16 weights / shifts: the 1x1 convolutions that read a block's input sit next to each other
+    // (Branch_0, Branch_1 reducer, Branch_2 reducer) so that they run as ONE GEMM with concatenated columns.
+    long long w16 = 0, wt16 = 0, ch = 0;
+    auto place = [&](int i) {
+      const BbConv& c = kBbConvs[i];
+      const long long nw = (long long)c.cout * c.k * c.k * c.cin;
       L.c[i].w16 = w16; w16 += nw;
       L.c[i].wt16 = -1;
       if (needs_wt(i)) { L.c[i].wt16 = wt16; wt16 += nw; }
       L.c[i].ch = ch; ch += c.cout;
-    }
+    };
+    place(0); place(1);
+    for (int i0 : {kBb3b, kBb3c}) for (int j : {0, 1, 3, 2, 4, 5, 6}) place(i0 + j);
+    for (int j : {0, 2, 1, 3, 4}) place(kBb4a + j);
+    for (int blk = 0; blk < 4; ++blk) for (int j : {0, 1, 3, 2, 4, 5, 6}) place(kBb4b + 7 * blk + j);
     L.param_floats = o; L.w_elems = w16; L.wt_elems = wt16; L.ch_total = ch;
     done = true;
   }
@@ -148,10 +158,12 @@ bb_stem_kernel(const float* __restrict__ img, int H, int W, int H1, int W1, int 
                const float* __restrict__ dw, const float* __restrict__ pw, const float* __restrict__ gamma,
                const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ var,
                bf16* __restrict__ out) {
+  // weights are read as float4 broadcasts (scalar LDS made the first version shared-memory bound, 3100
+  // wavefronts per warp instead of 830)
   __shared__ float s_in[kStemPatch * kStemPatch * 3];
-  __shared__ float s_dw[kStemDw];
-  __shared__ float s_pw[24 * 64];          // [j][o], BN scale folded
-  __shared__ float s_shift[64];
+  __shared__ __align__(16) float s_dw[kStemDw];
+  __shared__ __align__(16) float s_pw[24 * 64];          // [j][o], BN scale folded
+  __shared__ __align__(16) float s_shift[64];
   const int n = blockIdx.z, oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
   const int tid = threadIdx.x;
   for (int i = tid; i < kStemDw; i += 256) s_dw[i] = dw[i];
@@ -181,12 +193,15 @@ bb_stem_kernel(const float* __restrict__ img, int H, int W, int H1, int W1, int 
   for (int ky = 0; ky < 7; ++ky)
     for (int kx = 0; kx < 7; ++kx) {
       const float* pin = s_in + ((2 * ty + ky) * kStemPatch + 2 * tx + kx) * 3;
-      const float* pwt = s_dw + (ky * 7 + kx) * 24;
+      const float4* pwt = reinterpret_cast<const float4*>(s_dw + (ky * 7 + kx) * 24);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float v = pin[c];
-#pragma unroll
-        for (int m = 0; m < 8; ++m) d[c * 8 + m] = fmaf(v, pwt[c * 8 + m], d[c * 8 + m]);
+        const float4 w0 = pwt[2 * c], w1 = pwt[2 * c + 1];
+        d[c * 8 + 0] = fmaf(v, w0.x, d[c * 8 + 0]); d[c * 8 + 1] = fmaf(v, w0.y, d[c * 8 + 1]);
+        d[c * 8 + 2] = fmaf(v, w0.z, d[c * 8 + 2]); d[c * 8 + 3] = fmaf(v, w0.w, d[c * 8 + 3]);
+        d[c * 8 + 4] = fmaf(v, w1.x, d[c * 8 + 4]); d[c * 8 + 5] = fmaf(v, w1.y, d[c * 8 + 5]);
+        d[c * 8 + 6] = fmaf(v, w1.z, d[c * 8 + 6]); d[c * 8 + 7] = fmaf(v, w1.w, d[c * 8 + 7]);
       }
     }
   const int oy = oy0 + ty, ox = ox0 + tx;
@@ -195,12 +210,16 @@ bb_stem_kernel(const float* __restrict__ img, int H, int W, int H1, int W1, int 
 #pragma unroll 1
   for (int o0 = 0; o0 < 64; o0 += 8) {
     float a[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = s_shift[o0 + i];
+    {
+      const float4 s0 = *reinterpret_cast<const float4*>(s_shift + o0), s1 = *reinterpret_cast<const float4*>(s_shift + o0 + 4);
+      a[0] = s0.x; a[1] = s0.y; a[2] = s0.z; a[3] = s0.w; a[4] = s1.x; a[5] = s1.y; a[6] = s1.z; a[7] = s1.w;
+    }
 #pragma unroll
     for (int j = 0; j < 24; ++j) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = fmaf(d[j], s_pw[j * 64 + o0 + i], a[i]);
+      const float4 w0 = *reinterpret_cast<const float4*>(s_pw + j * 64 + o0);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_pw + j * 64 + o0 + 4);
+      a[0] = fmaf(d[j], w0.x, a[0]); a[1] = fmaf(d[j], w0.y, a[1]); a[2] = fmaf(d[j], w0.z, a[2]); a[3] = fmaf(d[j], w0.w, a[3]);
+      a[4] = fmaf(d[j], w1.x, a[4]); a[5] = fmaf(d[j], w1.y, a[5]); a[6] = fmaf(d[j], w1.z, a[6]); a[7] = fmaf(d[j], w1.w, a[7]);
     }
     uint4 v;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(a[0], 0.f), fmaxf(a[1], 0.f));
@@ -327,6 +346,15 @@ struct BbWalk {
     OutSeg seg = {y, ldy, c.cout};
     rc = conv_img_fwd_tc(ic, w16 + L.c[i].w16, shift + L.c[i].ch, 1, &seg, 1, out_f32, st);
   }
+  // Sibling 1x1 convolutions on the same input as one GEMM: conv `first` and the ones whose folded weights
+  // follow it; output columns routed to `segs` (all bf16).
+  void conv1x1_group(int first, int l, const bf16* x, int ldx, const OutSeg* segs, int nseg) {
+    if (!run || rc != C2D_OK) return;
+    int cout = 0;
+    for (int s = 0; s < nseg; ++s) cout += segs[s].cols;
+    ImgConv ic = {B, 1, 1, d.h[l], d.w[l], d.h[l], d.w[l], kBbConvs[first].cin, cout, x, ldx};
+    rc = conv_img_fwd_tc(ic, w16 + L.c[first].w16, shift + L.c[first].ch, 1, segs, nseg, 0, st);
+  }
   void maxpool_s2(int lin, const bf16* x, int C, int ldx, bf16* y, int ldy) {
     if (!run || rc != C2D_OK) return;
     const int H = d.h[lin], W = d.w[lin], Ho = d.h[lin + 1], Wo = d.w[lin + 1];
@@ -356,10 +384,16 @@ struct BbWalk {
     auto col = [&](int off_cols) -> void* {
       return f32 ? (void*)((float*)y + off_cols) : (void*)((bf16*)y + off_cols);
     };
-    conv(i0, l, x, cin, col(0), ctot, f32);
-    conv(i0 + 1, l, x, cin, t1, kBbConvs[i0 + 1].cout, 0);
+    const int c1 = kBbConvs[i0 + 1].cout, c2 = kBbConvs[i0 + 3].cout;
+    if (f32) {                      // Branch_0 writes fp32: only the two reducers share a GEMM
+      conv(i0, l, x, cin, col(0), ctot, 1);
+      OutSeg segs[2] = {{t1, c1, c1}, {t2, c2, c2}};
+      conv1x1_group(i0 + 1, l, x, cin, segs, 2);
+    } else {
+      OutSeg segs[3] = {{y, ctot, a}, {t1, c1, c1}, {t2, c2, c2}};
+      conv1x1_group(i0, l, x, cin, segs, 3);
+    }
     conv(i0 + 2, l, t1, kBbConvs[i0 + 1].cout, col(a), ctot, f32);
-    conv(i0 + 3, l, x, cin, t2, kBbConvs[i0 + 3].cout, 0);
     conv(i0 + 4, l, t2, kBbConvs[i0 + 3].cout, t3, kBbConvs[i0 + 4].cout, 0);
     conv(i0 + 5, l, t3, kBbConvs[i0 + 4].cout, col(a + b), ctot, f32);
     avgpool(l, x, cin, cin, t4);
@@ -426,9 +460,11 @@ static void* bb_forward_walk(BbWalk& w, const float* image, int H, int W, const 
   bf16* t1 = w.act(3, 128);
   bf16* t2 = w.act(3, 64);
   bf16* t3 = w.act(3, 96);
-  w.conv(kBb4a, 3, y3c, 320, t1, 128, 0);
+  {
+    OutSeg segs[2] = {{t1, 128, 128}, {t2, 64, 64}};
+    w.conv1x1_group(kBb4a, 3, y3c, 320, segs, 2);
+  }
   w.conv(kBb4a + 1, 3, t1, 128, y4a, 576, 0);
-  w.conv(kBb4a + 2, 3, y3c, 320, t2, 64, 0);
   w.conv(kBb4a + 3, 3, t2, 64, t3, 96, 0);
   w.conv(kBb4a + 4, 3, t3, 96, y4a + 160, 576, 0);
   w.maxpool_s2(3, y3c, 320, 320, y4a + 256, 576);
@@ -498,9 +534,9 @@ int c2d_backbone_fwd(const float* image, int B, int H, int W, const float* param
   C2D_CHECK_ARG(B >= 0 && H >= 33 && W >= 33, "backbone_fwd: bad shape B=%d H=%d W=%d", B, H, W);
   if (B == 0) return C2D_OK;
   C2D_CHECK_ARG(image && params && fmap, "backbone_fwd: null pointer");
-  C2D_CHECK_ARG(workspace != nullptr && ((uintptr_t)workspace & 1023) == 0 &&
+  C2D_CHECK_ARG(workspace != nullptr && ((uintptr_t)workspace & 255) == 0 &&
                     workspace_bytes >= c2d_backbone_workspace_bytes(B, H, W),
-                "backbone_fwd: workspace must be 1024-byte aligned and >= c2d_backbone_workspace_bytes");
+                "backbone_fwd: workspace must be 256-byte aligned and >= c2d_backbone_workspace_bytes");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = bb_upload_fold_table();
   if (rc != C2D_OK) return rc;
@@ -522,7 +558,7 @@ int c2d_backbone_bwd(const float* dfmap, const float* fmap, int B, int H, int W,
   C2D_CUDA_OK(cudaMemsetAsync(dparams, 0, (size_t)L.param_floats * sizeof(float), st));
   if (B == 0) return C2D_OK;
   C2D_CHECK_ARG(dfmap && fmap && params, "backbone_bwd: null pointer");
-  C2D_CHECK_ARG(workspace != nullptr && ((uintptr_t)workspace & 1023) == 0 &&
+  C2D_CHECK_ARG(workspace != nullptr && ((uintptr_t)workspace & 255) == 0 &&
                     workspace_bytes >= c2d_backbone_workspace_bytes(B, H, W),
                 "backbone_bwd: workspace must be the one c2d_backbone_fwd filled");
   BbWalk w(B, H, W, workspace, false, st);

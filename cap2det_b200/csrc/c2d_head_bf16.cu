@@ -190,6 +190,22 @@ static void set_geo_tiles(tc::ConvGemmParams& p, int n, int pos_per_roi, int box
 static void set_n_tiles(tc::ConvGemmParams& p, bool two) {
   p.num_n_tiles = two ? pick_tiles(p.n_total, 256, &p.n_tile, 32) : pick_tiles(p.n_total, 128, &p.n_tile, 16);
 }
+// Small problems (first-stage maps, FC layers): when the M tiles alone cannot fill the machine, narrow the N tile
+// so that more CTAs (pairs) share the work.  Call after the M tiling is known.  No effect on the head (thousands
+// of M tiles).
+static void rebalance_n_tiles(tc::ConvGemmParams& p, bool two) {
+  const int workers = two ? num_sms() / 2 : num_sms();
+  if (p.num_m_tiles <= 0 || p.num_m_tiles * p.num_n_tiles >= workers) return;
+  const int align = two ? 32 : 16;
+  int want = (workers + p.num_m_tiles - 1) / p.num_m_tiles;
+  const int max_nt = p.n_total / align > 0 ? p.n_total / align : 1;
+  if (want > max_nt) want = max_nt;
+  if (want <= p.num_n_tiles) return;
+  int t = (p.n_total + want - 1) / want;
+  t = (t + align - 1) / align * align;
+  p.n_tile = t;
+  p.num_n_tiles = (p.n_total + t - 1) / t;
+}
 static int b_box_rows(const tc::ConvGemmParams& p, bool two) { return two ? p.n_tile / 2 : p.n_tile; }
 
 // Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift) with the output columns split over `segs`.
@@ -205,12 +221,12 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
   const int cout = p.n_total;
   set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, cout, (long long)taps * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const int chunks = (c.cin + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
     p.taps = 1; p.tap_chunks[0] = chunks; p.tap_koff[0] = 0; p.tap_map[0] = 0;
     set_flat_tiles(p, M, two);
+    rebalance_n_tiles(p, two);
     if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, p.rows_per_tile)) return C2D_ERR_CUDA;
     maps[1] = maps[2] = maps[3] = maps[0];
   } else {
@@ -234,6 +250,7 @@ static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, i
       }
     }
   }
+  if (!make_map_flat(&mapB, w16, (long long)taps * c.cin, cout, (long long)taps * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * (double)taps * c.cin * cout, two);
 }
 
@@ -248,10 +265,11 @@ static int conv_fwd_tc_rows(const ConvDesc& c, const bf16* w16, int w_rows, cons
   set_segments(p, seg, 1);
   set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = 1; p.relu = 0; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, c.cin, w_rows, c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const long long M = c.n;
   p.taps = 1; p.tap_chunks[0] = (c.cin + 63) / 64; p.tap_koff[0] = 0; p.tap_map[0] = 0;
   set_flat_tiles(p, M, two);
+  rebalance_n_tiles(p, two);
+  if (!make_map_flat(&mapB, w16, c.cin, w_rows, c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   if (!make_map_flat(&maps[0], c.x, c.cin, M, c.ldx, p.rows_per_tile)) return C2D_ERR_CUDA;
   maps[1] = maps[2] = maps[3] = maps[0];
   return launch_conv(maps, mapB, p, st, 2.0 * M * (double)c.cin * w_rows, two);
@@ -473,10 +491,11 @@ int conv_img_fwd_tc(const ImgConv& c, const bf16* w16, const float* shift, int r
   const int cout = p.n_total;
   set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
-  if (!make_map_flat(&mapB, w16, 9LL * c.cin, cout, 9LL * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const int chunks = (c.cin + 63) / 64;
   p.taps = 9;
   set_img_tiles(p, c.n, c.hout, c.wout, two);
+  rebalance_n_tiles(p, two);
+  if (!make_map_flat(&mapB, w16, 9LL * c.cin, cout, 9LL * c.cin, b_box_rows(p, two))) return C2D_ERR_CUDA;
   const int th = p.rows_per_tile / 16;
   for (int t = 0; t < 9; ++t) { p.tap_chunks[t] = chunks; p.tap_koff[t] = t * c.cin; }
   if (c.stride == 1) {
@@ -510,9 +529,10 @@ int conv_img_dgrad_tc(const ImgConv& c, const bf16* du, int lddu, const bf16* wt
   set_segments(p, &oseg, 1);
   set_n_tiles(p, two);
   p.mask = mask; p.mask_ld = lddx; p.mask_cols = mask ? c.cin : 0;
-  if (!make_map_flat(&mapB, wt16, 9LL * c.cout, c.cin, 9LL * c.cout, b_box_rows(p, two))) return C2D_ERR_CUDA;
   p.taps = 9;
   set_img_tiles(p, c.n, c.hin, c.win, two);
+  rebalance_n_tiles(p, two);
+  if (!make_map_flat(&mapB, wt16, 9LL * c.cout, c.cin, 9LL * c.cout, b_box_rows(p, two))) return C2D_ERR_CUDA;
   if (!make_map_img(&maps[0], du, c.cout, c.hout, c.wout, c.n, lddu, 16, p.rows_per_tile / 16)) return C2D_ERR_CUDA;
   maps[1] = maps[2] = maps[3] = maps[0];
   const int chunks = (c.cout + 63) / 64;

@@ -537,8 +537,11 @@ def test_model_multiscale_eval_and_errors():
   assert p12['detection_boxes_at_3'].shape == (1, 300, 4)
   with pytest.raises(ValueError):
     cap2det_model.Model(config.PostProcess())
-  with pytest.raises(NotImplementedError):
+  with pytest.raises(ValueError, match="'features_to_crop' or 'image'"):
     model.build_prediction({F.num_proposals: ex[F.num_proposals], F.proposals: ex[F.proposals], F.image: None})
+  with pytest.raises(ValueError, match='first_stage=True'):      # images need the first-stage variables
+    model.build_prediction({F.num_proposals: ex[F.num_proposals], F.proposals: ex[F.proposals],
+                            F.image: torch.zeros((1, 64, 64, 3), device='cuda')})
 
 
 def test_full_size_properties_P2000():
