@@ -18,6 +18,7 @@ import math
 import torch
 
 from cap2det_b200 import config
+from cap2det_b200 import imgproc
 from cap2det_b200 import ops
 from cap2det_b200.label_extractor import build_label_extractor
 from cap2det_b200.model_base import ModelBase
@@ -247,7 +248,14 @@ class Model(ModelBase):
       postprocess = not self._is_training
     fmaps = examples.get(InputDataFields.features_to_crop)
     if fmaps is None:
-      fmaps = self._first_stage(examples.get(InputDataFields.image))
+      images = examples.get(InputDataFields.image)
+      if (not self._is_training and len(options.eval_min_dimension) > 0 and torch.is_tensor(images)):
+        # models/cap2det_model.py:236-247: one resized copy of the (single) image per eval_min_dimension
+        if images.shape[0] != 1:
+          raise ValueError('multi-scale evaluation needs batch size 1 (models/cap2det_model.py:237)')
+        images = [imgproc.resize_image_to_min_dimension(images[0], d)[0].unsqueeze(0)
+                  for d in options.eval_min_dimension]
+      fmaps = self._first_stage(images)
     if self._is_training or len(options.eval_min_dimension) == 0:
       if isinstance(fmaps, (list, tuple)):
         raise ValueError('a single feature map is expected outside multi-scale evaluation')

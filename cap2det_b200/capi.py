@@ -10,7 +10,7 @@ import torch
 
 from cap2det_b200 import build as _build
 
-C2D_F32, C2D_BF16 = 0, 1
+C2D_F32, C2D_BF16, C2D_U8 = 0, 1, 2
 MASKED_MAX, MASKED_MIN, MASKED_SUM, MASKED_AVG, MASKED_ARGMAX, MASKED_ARGMIN = range(6)
 
 _c_int, _c_float, _c_ll, _c_sz, _p = (ctypes.c_int, ctypes.c_float, ctypes.c_longlong,
@@ -44,6 +44,9 @@ SIGNATURES = {
     'c2d_head_workspace_bytes': (_c_sz, [_c_int, _c_int]),
     'c2d_head_mixed5_fwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p]),
     'c2d_head_mixed5_bwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p]),
+    'c2d_resize_bilinear': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _p]),
+    'c2d_image_flip_left_right': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p, _p]),
+    'c2d_box_scale_batch': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p]),
     'c2d_backbone_num_convs': (_c_int, []),
     'c2d_backbone_conv_spec': (_c_int, [_c_int, _p, _p, _p, _p, _p]),
     'c2d_backbone_param_floats': (_c_ll, []),
@@ -150,6 +153,8 @@ def dtype_code(dtype):
     return C2D_F32
   if dtype == torch.bfloat16:
     return C2D_BF16
+  if dtype == torch.uint8:
+    return C2D_U8
   raise ValueError('unsupported dtype %s' % dtype)
 
 

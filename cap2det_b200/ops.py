@@ -139,6 +139,45 @@ def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True):
 
 
 # ---------------------------------------------------------------------------------------------
+# Reader-side image / box contract  (readers/cap2det_reader.py:143-199, core/imgproc.py:300-352)
+# ---------------------------------------------------------------------------------------------
+def resize_bilinear(image, new_height, new_width):
+  """tf.image.resize_images(image, [new_height, new_width]) (bilinear, align_corners False, TF1 sampling).
+  image [B,H,W,C] or [H,W,C], fp32 or uint8 -> fp32."""
+  squeeze = image.dim() == 3
+  x = (image.unsqueeze(0) if squeeze else image).contiguous()
+  require_cuda(x)
+  B, H, W, C = x.shape
+  out = torch.empty((B, int(new_height), int(new_width), C), dtype=torch.float32, device=x.device)
+  call('c2d_resize_bilinear', ptr(x), capi.dtype_code(x.dtype), B, H, W, C, ptr(out), int(new_height), int(new_width),
+       stream())
+  return out[0] if squeeze else out
+
+
+def image_flip_left_right(image, flip=None):
+  """tf.image.flip_left_right; ``flip`` [B] selects the images to flip (None = all)."""
+  squeeze = image.dim() == 3
+  x = (image.unsqueeze(0) if squeeze else image).contiguous()
+  f = None if flip is None else flip.to(torch.int32).contiguous()
+  require_cuda(x, f)
+  B, H, W, C = x.shape
+  out = torch.empty_like(x)
+  call('c2d_image_flip_left_right', ptr(x), capi.dtype_code(x.dtype), B, H, W, C, ptr(f), ptr(out), stream())
+  return out[0] if squeeze else out
+
+
+def box_scale_batch(box, image_hw, pad_h, pad_w):
+  """_batch_scale_box_fn: box [B,P,4] * image_hw[b] / (pad_h, pad_w)."""
+  box = _f32(box).contiguous()
+  hw = image_hw.to(torch.int32).contiguous()
+  require_cuda(box, hw)
+  B, P, _ = box.shape
+  out = torch.empty_like(box)
+  call('c2d_box_scale_batch', ptr(box), ptr(hw), B, P, int(pad_h), int(pad_w), ptr(out), stream())
+  return out
+
+
+# ---------------------------------------------------------------------------------------------
 # First stage: Inception-v2 up to Mixed_4e on whole images  (models/utils.py:127-136)
 # ---------------------------------------------------------------------------------------------
 BACKBONE_STEM_SCOPE = 'Conv2d_1a_7x7'

@@ -31,7 +31,7 @@ enum {
   C2D_ERR_UNSUPPORTED = -3  /* shape / option outside what the path uses */
 };
 
-enum { C2D_F32 = 0, C2D_BF16 = 1 };
+enum { C2D_F32 = 0, C2D_BF16 = 1, C2D_U8 = 2 };
 
 /* masked reductions, core/utils.py:63-214 */
 enum {
@@ -65,6 +65,19 @@ int c2d_box_iou(const float* box1, const float* box2, int n, float* iou, c2d_str
 int c2d_box_flip_left_right(const float* box, int n, float* out, c2d_stream_t stream);               /* :29-41 */
 int c2d_box_scale_to_new_size(const float* box, int n, int img_h, int img_w, int pad_h, int pad_w,
                               float* out, c2d_stream_t stream);                                      /* :9-26 */
+
+/* ---- reader-side image / box contract, readers/cap2det_reader.py:143-199 -------------------
+ * tf.image.resize_images(bilinear, align_corners False, TF1 legacy sampling src = dst * in/out) as used by
+ * _batch_resize_image_fn (:143-171) and core/imgproc.py:300-352 (resize_image_to_min_dimension).
+ * in [B,H,W,C] fp32 or uint8 (C2D_F32 / C2D_U8) -> out [B,H2,W2,C] fp32. */
+int c2d_resize_bilinear(const void* in, int in_dtype, int B, int H, int W, int C, float* out, int H2,
+                        int W2, c2d_stream_t stream);
+/* tf.image.flip_left_right per image: flip [B] of {0,1} (NULL = flip all); out must not alias in. */
+int c2d_image_flip_left_right(const void* in, int dtype, int B, int H, int W, int C, const int* flip,
+                              void* out, c2d_stream_t stream);
+/* _batch_scale_box_fn (:173-199): box [B,P,4] * (img_h, img_w)[b] / (pad_h, pad_w); img_hw [B,2] int32. */
+int c2d_box_scale_batch(const float* box, const int* img_hw, int B, int P, int pad_h, int pad_w,
+                        float* out, c2d_stream_t stream);
 
 /* ---- core/utils.py:63-214.  data [n,m,d], mask [n,m] (broadcast over d), reduce over m.
  * Float results go to out_f [n,d]; ARGMAX/ARGMIN write int64 indices to out_i [n,d]. */

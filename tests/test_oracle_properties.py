@@ -117,3 +117,26 @@ def test_backbone_oracle_shapes_and_same_padding():
   assert bool((y >= 0).all()) and float(y.max()) > 0
   err = float((y16 - y).norm() / y.norm())
   assert 0 < err < 3e-2                # bf16 storage emulation stays within bf16 noise of fp32
+
+
+# ---- reader-side oracle (oracle/image.py) ----------------------------------------------------------
+def test_image_oracle_sizes_and_resize_properties():
+  """Output sizes pinned by core/imgproc_test.py:198-218; bilinear resize: identity at equal size, exact on
+  constant and on linear ramps when upsampling by an integer factor (legacy sampling src = dst * in/out)."""
+  import numpy as np
+  from oracle import image as oi
+  assert oi.min_dimension_size(300, 400, 900) == (900, 1200)
+  assert oi.min_dimension_size(400, 300, 900) == (1200, 900)
+  rng = np.random.default_rng(0)
+  x = rng.uniform(0, 255, size=(2, 6, 9, 3)).astype(np.float32)
+  np.testing.assert_array_equal(oi.resize_bilinear(x, 6, 9), x)
+  c = np.full((1, 4, 5, 2), 7.25, np.float32)
+  np.testing.assert_array_equal(oi.resize_bilinear(c, 9, 3), np.full((1, 9, 3, 2), 7.25, np.float32))
+  ramp = np.arange(8, dtype=np.float32)[None, None, :, None] * np.ones((1, 3, 1, 1), np.float32)
+  up = oi.resize_bilinear(ramp, 3, 16)                # src = dst / 2: exact halves, clamped at the right edge
+  np.testing.assert_array_equal(up[0, 0, :, 0], np.minimum(np.arange(16) / 2.0, 7.0).astype(np.float32))
+  down = oi.resize_bilinear(ramp, 3, 4)               # src = 2 * dst: pure subsampling
+  np.testing.assert_array_equal(down[0, 0, :, 0], np.array([0, 2, 4, 6], np.float32))
+  box = np.array([[[0.5, 0.25, 1.0, 0.75]]], np.float32)
+  got = oi.batch_scale_box(box, np.array([[300, 200, 3]]), 600, 400)
+  np.testing.assert_array_equal(got, np.array([[[0.25, 0.125, 0.5, 0.375]]], np.float32))
