@@ -24,6 +24,7 @@ SIGNATURES = {
     'c2d_profile_enable': (None, [_c_int]),
     'c2d_profile_reset': (None, []),
     'c2d_profile_read': (_c_int, [_c_int, _p, _p, _p]),
+    'c2d_profile_entry': (_c_int, [_c_int, _p, _p, _p]),
     'c2d_launch_count': (_c_ll, []),
     'c2d_reset_launch_count': (None, []),
     'c2d_box_area': (_c_int, [_p, _c_int, _p, _p]),
@@ -37,6 +38,9 @@ SIGNATURES = {
                                           _c_int, _p, _c_int, _p]),
     'c2d_roi_crop_maxpool_bwd': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int,
                                           _c_int, _p, _c_int, _p, _p]),
+    'c2d_roi_argmax_code_bytes': (_c_sz, [_c_int, _c_int, _c_int]),
+    'c2d_roi_crop_maxpool_fwd_codes': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _p, _p]),
+    'c2d_roi_crop_maxpool_bwd_codes': (_c_int, [_c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _c_int, _p, _p]),
     'c2d_head_num_convs': (_c_int, []),
     'c2d_head_conv_spec': (_c_int, [_c_int, _p, _p, _p, _p, _p]),
     'c2d_head_param_floats': (_c_ll, []),

@@ -621,7 +621,7 @@ static int check_img_args(int n, int h, int w, int cin, int cout, int k, int str
   C2D_CHECK_ARG(n >= 0 && h >= 1 && w >= 1 && (k == 1 || k == 3), "conv_img_bf16: k must be 1 or 3");
   C2D_CHECK_ARG(stride == 1 || (stride == 2 && k == 3), "conv_img_bf16: stride 2 needs k 3");
   C2D_CHECK_ARG(cin >= 16 && cin % 16 == 0 && cout >= 16 && cout % 16 == 0, "conv_img_bf16: channels must be multiples of 16");
-  C2D_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv_img_bf16: leading dims must be multiples of 8");
+  C2D_CHECK_ARG(ldx % 16 == 0 && ldy % 16 == 0 && ldx >= cin && ldy >= cout, "conv_img_bf16: leading dims must be multiples of 16 (32-byte rows)");
   return C2D_OK;
 }
 

@@ -97,6 +97,19 @@ struct TcPipe {
   uint32_t tmem_base;
 };
 
+// 32-byte global accesses (sm_100: LDG/STG.256): one full sector per thread and instruction.  The epilogue
+// threads own one output row each, so a 16-column bf16 chunk is exactly one sector.
+__device__ __forceinline__ void ld_global_256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void st_global_256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -213,13 +226,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
           if (live && bf16_rmw) {     // single output segment when accumulating
             const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
-            oldv[u][0] = *reinterpret_cast<const uint4*>(o);
-            oldv[u][1] = *reinterpret_cast<const uint4*>(o + 8);
+            ld_global_256(o, oldv[u][0], oldv[u][1]);
           }
           if (live && p.mask != nullptr && col0 < p.mask_cols) {
             const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
-            mskv[u][0] = *reinterpret_cast<const uint4*>(y);
-            mskv[u][1] = *reinterpret_cast<const uint4*>(y + 8);
+            ld_global_256(y, mskv[u][0], mskv[u][1]);
           }
         }
 #pragma unroll
@@ -252,12 +263,22 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.seg_out[sgm]) + ooff);
+              float* o = reinterpret_cast<float*>(p.seg_out[sgm]) + ooff;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 w = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                if (p.accum) { float4 old = o[i]; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
-                o[i] = w;
+              for (int i = 0; i < 2; ++i) {
+                if (p.accum) {
+                  uint4 a, c;
+                  ld_global_256(o + 8 * i, a, c);
+                  f[8 * i] += __uint_as_float(a.x); f[8 * i + 1] += __uint_as_float(a.y);
+                  f[8 * i + 2] += __uint_as_float(a.z); f[8 * i + 3] += __uint_as_float(a.w);
+                  f[8 * i + 4] += __uint_as_float(c.x); f[8 * i + 5] += __uint_as_float(c.y);
+                  f[8 * i + 6] += __uint_as_float(c.z); f[8 * i + 7] += __uint_as_float(c.w);
+                }
+                st_global_256(o + 8 * i,
+                              make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
+                                         __float_as_uint(f[8 * i + 3])),
+                              make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                                         __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
               }
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
@@ -278,8 +299,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
               w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
               w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
               w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
-              *reinterpret_cast<uint4*>(o) = w0;
-              *reinterpret_cast<uint4*>(o + 8) = w1;
+              st_global_256(o, w0, w1);
             }
           }
         }
@@ -433,13 +453,11 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
           mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
           if (live && bf16_rmw) {
             const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
-            oldv[u][0] = *reinterpret_cast<const uint4*>(o);
-            oldv[u][1] = *reinterpret_cast<const uint4*>(o + 8);
+            ld_global_256(o, oldv[u][0], oldv[u][1]);
           }
           if (live && p.mask != nullptr && col0 < p.mask_cols) {
             const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
-            mskv[u][0] = *reinterpret_cast<const uint4*>(y);
-            mskv[u][1] = *reinterpret_cast<const uint4*>(y + 8);
+            ld_global_256(y, mskv[u][0], mskv[u][1]);
           }
         }
 #pragma unroll
@@ -472,12 +490,22 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
             if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.seg_out[sgm]) + ooff);
+              float* o = reinterpret_cast<float*>(p.seg_out[sgm]) + ooff;
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 w = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                if (p.accum) { float4 old = o[i]; w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
-                o[i] = w;
+              for (int i = 0; i < 2; ++i) {
+                if (p.accum) {
+                  uint4 a, c;
+                  ld_global_256(o + 8 * i, a, c);
+                  f[8 * i] += __uint_as_float(a.x); f[8 * i + 1] += __uint_as_float(a.y);
+                  f[8 * i + 2] += __uint_as_float(a.z); f[8 * i + 3] += __uint_as_float(a.w);
+                  f[8 * i + 4] += __uint_as_float(c.x); f[8 * i + 5] += __uint_as_float(c.y);
+                  f[8 * i + 6] += __uint_as_float(c.z); f[8 * i + 7] += __uint_as_float(c.w);
+                }
+                st_global_256(o + 8 * i,
+                              make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
+                                         __float_as_uint(f[8 * i + 3])),
+                              make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                                         __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
               }
             } else {
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
@@ -498,8 +526,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
               w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
               w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
               w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
-              *reinterpret_cast<uint4*>(o) = w0;
-              *reinterpret_cast<uint4*>(o + 8) = w1;
+              st_global_256(o, w0, w1);
             }
           }
         }

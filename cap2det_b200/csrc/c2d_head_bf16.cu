@@ -694,6 +694,17 @@ int c2d_profile_read(int kind, double* ms_total, long long* launches, double* fl
   return C2D_OK;
 }
 
+int c2d_profile_entry(int index, int* kind, double* ms, double* flops) {
+  if (index < 0 || index >= (int)g_prof.size()) return C2D_ERR_INVALID_ARG;
+  C2D_CUDA_OK(cudaEventSynchronize(g_prof[index].b));
+  float t = 0.f;
+  C2D_CUDA_OK(cudaEventElapsedTime(&t, g_prof[index].a, g_prof[index].b));
+  if (kind) *kind = g_prof[index].kind;
+  if (ms) *ms = t;
+  if (flops) *flops = g_prof[index].flops;
+  return C2D_OK;
+}
+
 // ---- K4 on the tensor cores: y = x . w^T + b as a flat conv GEMM (bf16 operands, fp32 accumulate/out) ----
 struct FcWs { bf16* x16; bf16* w16; bf16* wt16; bf16* dy16; float* bias; size_t total; };
 static FcWs fc_ws(void* base, int M, int D, int N) {
@@ -773,7 +784,7 @@ static int check_conv_args(int n, int hin, int cin, int cout, int k, int stride,
   C2D_CHECK_ARG(n >= 0 && (hin == 7 || hin == 4) && (k == 1 || k == 3), "conv_bf16: hin must be 7 or 4, k 1 or 3");
   C2D_CHECK_ARG(stride == 1 || (stride == 2 && hin == 7 && k == 3), "conv_bf16: stride 2 needs hin 7, k 3");
   C2D_CHECK_ARG(cin >= 16 && cin % 16 == 0 && cout >= 16 && cout % 16 == 0, "conv_bf16: channels must be multiples of 16");
-  C2D_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= cin && ldy >= cout, "conv_bf16: leading dims must be multiples of 8");
+  C2D_CHECK_ARG(ldx % 16 == 0 && ldy % 16 == 0 && ldx >= cin && ldy >= cout, "conv_bf16: leading dims must be multiples of 16 (32-byte rows)");
   return C2D_OK;
 }
 static ConvDesc make_desc(const void* x, int ldx, int n, int hin, int cin, int cout, int k, int stride, void* y, int ldy) {

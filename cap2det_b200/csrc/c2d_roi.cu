@@ -68,10 +68,21 @@ __device__ __forceinline__ float4 roi_sample(const float4* __restrict__ img4, co
   return o;
 }
 
+// first maximum in row-major (dy,dx) window order
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  int k = 0; float m = a;
+  if (b > m) { m = b; k = 1; }
+  if (c > m) { m = c; k = 2; }
+  if (d > m) { m = d; k = 3; }
+  return k;
+}
+
+// `codes` (optional, training): one byte per (bin, channel quad) = the four 2-bit max-pool arg-max indices, so
+// that the backward pass routes gradients without re-sampling the feature map.
 template <typename OutT>
 __global__ void __launch_bounds__(288)
 roi_crop_maxpool_fwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
-                            int P, int crop, OutT* __restrict__ out) {
+                            int P, int crop, OutT* __restrict__ out, unsigned char* __restrict__ codes) {
   __shared__ RoiCoords sc;
   const int roi = blockIdx.x;
   const int b = roi / P;
@@ -94,16 +105,12 @@ roi_crop_maxpool_fwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int 
     m.z = fmaxf(fmaxf(v00.z, v01.z), fmaxf(v10.z, v11.z));
     m.w = fmaxf(fmaxf(v00.w, v01.w), fmaxf(v10.w, v11.w));
     st4(o + (size_t)pos * Cf + 4 * q, m);
+    if (codes != nullptr)
+      codes[(size_t)roi * items + w] = (unsigned char)(argmax4(v00.x, v01.x, v10.x, v11.x) |
+                                                       (argmax4(v00.y, v01.y, v10.y, v11.y) << 2) |
+                                                       (argmax4(v00.z, v01.z, v10.z, v11.z) << 4) |
+                                                       (argmax4(v00.w, v01.w, v10.w, v11.w) << 6));
   }
-}
-
-// first maximum in row-major (dy,dx) window order
-__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
-  int k = 0; float m = a;
-  if (b > m) { m = b; k = 1; }
-  if (c > m) { m = c; k = 2; }
-  if (d > m) { m = d; k = 3; }
-  return k;
 }
 
 // Scatter the gradient of crop sample (cy,cx) for a channel quad: g holds the 4 channel gradients,
@@ -168,6 +175,37 @@ roi_crop_maxpool_bwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int 
   }
 }
 
+// Backward from the arg-max codes of the forward pass: no feature-map reads at all.
+template <typename GradT>
+__global__ void __launch_bounds__(288)
+roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restrict__ boxes, int P, int crop,
+                                  const unsigned char* __restrict__ codes, const GradT* __restrict__ dout,
+                                  float* __restrict__ dfmap) {
+  __shared__ RoiCoords sc;
+  const int roi = blockIdx.x;
+  const int b = roi / P;
+  roi_setup_coords(sc, boxes[roi], Hf, Wf, crop);
+  __syncthreads();
+  const int C4 = Cf >> 2, hp = crop >> 1;
+  float* dimg = dfmap + (size_t)b * Hf * Wf * Cf;
+  const GradT* go = dout + (size_t)roi * hp * hp * Cf;
+  const int items = hp * hp * C4;
+  const unsigned char* cd = codes + (size_t)roi * items;
+  for (int w = threadIdx.x; w < items; w += blockDim.x) {
+    int q = w % C4, pos = w / C4;
+    int py = pos / hp, px = pos - py * hp;
+    float4 g = ld4(go + (size_t)pos * Cf + 4 * q);
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    const int code = cd[w];
+    const int kx = code & 3, ky = (code >> 2) & 3, kz = (code >> 4) & 3, kw = (code >> 6) & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float4 gk = make_float4(kx == k ? g.x : 0.f, ky == k ? g.y : 0.f, kz == k ? g.z : 0.f, kw == k ? g.w : 0.f);
+      scatter_quad(dimg, sc, 2 * py + (k >> 1), 2 * px + (k & 1), Wf, Cf, 4 * q, gk);
+    }
+  }
+}
+
 static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k, int pool_s) {
   C2D_CHECK_ARG(B >= 0 && P >= 0 && Hf >= 1 && Wf >= 1, "roi: bad shape B=%d P=%d Hf=%d Wf=%d", B, P, Hf, Wf);
   C2D_CHECK_ARG(Cf >= 4 && Cf % 4 == 0, "roi: feature depth %d must be a multiple of 4", Cf);
@@ -185,8 +223,20 @@ using namespace c2d;
 
 extern "C" {
 
+size_t c2d_roi_argmax_code_bytes(int n_rois, int Cf, int crop_size) {
+  if (n_rois <= 0 || Cf <= 0 || crop_size <= 0) return 0;
+  return (size_t)n_rois * (crop_size / 2) * (crop_size / 2) * (Cf / 4);
+}
+
 int c2d_roi_crop_maxpool_fwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes, int P,
                              int crop_size, int pool_k, int pool_s, void* out, int out_dtype, c2d_stream_t stream) {
+  return c2d_roi_crop_maxpool_fwd_codes(fmap, B, Hf, Wf, Cf, boxes, P, crop_size, pool_k, pool_s, out, out_dtype,
+                                        nullptr, stream);
+}
+
+int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes, int P,
+                                   int crop_size, int pool_k, int pool_s, void* out, int out_dtype,
+                                   unsigned char* codes, c2d_stream_t stream) {
   int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
   if (rc != C2D_OK) return rc;
   C2D_CHECK_ARG(out_dtype == C2D_F32 || out_dtype == C2D_BF16, "roi: bad dtype %d", out_dtype);
@@ -194,10 +244,10 @@ int c2d_roi_crop_maxpool_fwd(const float* fmap, int B, int Hf, int Wf, int Cf, c
   cudaStream_t st = (cudaStream_t)stream;
   if (out_dtype == C2D_F32)
     roi_crop_maxpool_fwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
-                                                             (float*)out);
+                                                             (float*)out, codes);
   else
     roi_crop_maxpool_fwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
-                                                                     crop_size, (__nv_bfloat16*)out);
+                                                                     crop_size, (__nv_bfloat16*)out, codes);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -219,6 +269,28 @@ int c2d_roi_crop_maxpool_bwd(const float* fmap, int B, int Hf, int Wf, int Cf, c
   else
     roi_crop_maxpool_bwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
                                                                      crop_size, (const __nv_bfloat16*)dout, dfmap);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size, int pool_k,
+                                   int pool_s, const unsigned char* codes, const void* dout, int dout_dtype,
+                                   float* dfmap, c2d_stream_t stream) {
+  int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
+  if (rc != C2D_OK) return rc;
+  C2D_CHECK_ARG(dout_dtype == C2D_F32 || dout_dtype == C2D_BF16, "roi: bad dtype %d", dout_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return C2D_OK;
+  C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
+  if (P == 0) return C2D_OK;
+  C2D_CHECK_ARG(codes != nullptr, "roi_bwd_codes: null codes");
+  if (dout_dtype == C2D_F32)
+    roi_crop_maxpool_bwd_codes_kernel<float><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes,
+                                                                   (const float*)dout, dfmap);
+  else
+    roi_crop_maxpool_bwd_codes_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
+                                                                           codes, (const __nv_bfloat16*)dout, dfmap);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

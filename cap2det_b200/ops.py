@@ -41,6 +41,8 @@ def _f32(t):
 # K1: crop_and_resize + max_pool  (models/utils.py:147-160)
 # ---------------------------------------------------------------------------------------------
 class _RoiCropMaxPool(torch.autograd.Function):
+  """When the feature map needs a gradient the forward also writes the max-pool arg-max codes (1 byte per
+  bin and channel quad) and the backward scatters from them, instead of re-sampling the feature map."""
 
   @staticmethod
   def forward(ctx, fmap, proposals, crop_size, pool_k, pool_s, out_dtype):
@@ -50,21 +52,26 @@ class _RoiCropMaxPool(torch.autograd.Function):
     P = proposals.shape[1]
     hp = crop_size // pool_s
     out = torch.empty((B * P, hp, hp, Cf), dtype=out_dtype, device=fmap.device)
-    call('c2d_roi_crop_maxpool_fwd', ptr(fmap), B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s,
-         ptr(out), capi.dtype_code(out_dtype), stream())
-    ctx.save_for_backward(fmap, proposals)
+    codes = None
+    if ctx.needs_input_grad[0] and B * P > 0:
+      codes = torch.empty((capi.load().c2d_roi_argmax_code_bytes(B * P, Cf, crop_size),), dtype=torch.uint8,
+                          device=fmap.device)
+    call('c2d_roi_crop_maxpool_fwd_codes', ptr(fmap), B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s,
+         ptr(out), capi.dtype_code(out_dtype), ptr(codes), stream())
+    ctx.save_for_backward(proposals, codes)
     ctx.cfg = (crop_size, pool_k, pool_s)
+    ctx.fmap_shape = (B, Hf, Wf, Cf)
     return out
 
   @staticmethod
   def backward(ctx, dout):
-    fmap, proposals = ctx.saved_tensors
+    proposals, codes = ctx.saved_tensors
     crop_size, pool_k, pool_s = ctx.cfg
-    B, Hf, Wf, Cf = fmap.shape
+    B, Hf, Wf, Cf = ctx.fmap_shape
     P = proposals.shape[1]
     dout = dout.contiguous()
-    dfmap = torch.empty_like(fmap)
-    call('c2d_roi_crop_maxpool_bwd', ptr(fmap), B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s,
+    dfmap = torch.empty((B, Hf, Wf, Cf), dtype=torch.float32, device=dout.device)
+    call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
          ptr(dout), capi.dtype_code(dout.dtype), ptr(dfmap), stream())
     return dfmap, None, None, None, None, None
 

@@ -60,17 +60,20 @@ def kernel_table(model, example, peaks, head_dtype):
     rows.append(dict(kernel=name, bound=bound, ms=ms, achieved=achieved, peak=peak, unit=unit,
                      frac=achieved / peak, algorithmic=work))
 
-  with torch.no_grad():
-    x0 = ops.roi_crop_maxpool(fmap, props, out_dtype=dt)
-  ms = _time(lambda: ops.roi_crop_maxpool(fmap, props, out_dtype=dt), flush)
-  add('K1 roi_crop_maxpool_fwd', ms, 'hbm', B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s), None)
-  g0 = torch.randn(x0.shape, device=dev).to(dt)
-  dfm = torch.empty_like(fmap)
   from cap2det_b200.capi import call, ptr, stream
   from cap2det_b200 import capi
-  ms = _time(lambda: call('c2d_roi_crop_maxpool_bwd', ptr(fmap), B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(g0),
+  n_code = capi.load().c2d_roi_argmax_code_bytes(B * P, Cf, 14)
+  codes = torch.empty((n_code,), dtype=torch.uint8, device=dev)
+  x0 = torch.empty((B * P, 7, 7, Cf), dtype=dt, device=dev)
+  # the training-mode pair: forward writes the max-pool arg-max codes, backward scatters from them
+  ms = _time(lambda: call('c2d_roi_crop_maxpool_fwd_codes', ptr(fmap), B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(x0),
+                          capi.dtype_code(dt), ptr(codes), stream()), flush)
+  add('K1 roi_crop_maxpool_fwd', ms, 'hbm', B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s) + n_code, None)
+  g0 = torch.randn(x0.shape, device=dev).to(dt)
+  dfm = torch.empty_like(fmap)
+  ms = _time(lambda: call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
                           capi.dtype_code(dt), ptr(dfm), stream()), flush)
-  add("K1' roi_crop_maxpool_bwd", ms, 'hbm', B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4), None)
+  add("K1' roi_crop_maxpool_bwd", ms, 'hbm', B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4) + n_code, None)
 
   n = B * P
   lib = capi.load()
@@ -144,6 +147,16 @@ def dominant_kernel_roofline(run_step, peaks, root, steps=3):
     ms, n, fl = ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
     capi.check(lib.c2d_profile_read(kind, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
     stats[name] = dict(ms_per_step=ms.value / steps, launches_per_step=n.value / steps, flops_per_step=fl.value / steps)
+  per_launch = None
+  if os.environ.get('C2D_PROFILE_PER_LAUNCH'):       # launch-by-launch table of the last profiled step
+    total = int(sum(s['launches_per_step'] for s in stats.values()) * steps)
+    first = total - total // steps
+    per_launch = []
+    for idx in range(first, total):
+      kind, ms, fl = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+      capi.check(lib.c2d_profile_entry(idx, ctypes.byref(kind), ctypes.byref(ms), ctypes.byref(fl)))
+      per_launch.append(dict(kind=kind.value, us=ms.value * 1e3, gflop=fl.value / 1e9,
+                             tflops=fl.value / max(ms.value, 1e-9) / 1e9))
   lib.c2d_profile_reset()
   name = max(stats, key=lambda k: stats[k]['ms_per_step'])
   st = stats[name]
@@ -158,4 +171,4 @@ def dominant_kernel_roofline(run_step, peaks, root, steps=3):
               traffic=traffic, avg_launch_ms=st['ms_per_step'] / max(st['launches_per_step'], 1),
               launches_per_step=st['launches_per_step'], algorithmic_flops_per_launch=st['flops_per_step'] /
               max(st['launches_per_step'], 1), peak_source='%s bf16_tflops_sustained (MEASURED_PEAKS.json)' % peaks['source'],
-              per_kernel=stats)
+              per_kernel=stats, **({'per_launch': per_launch} if per_launch else {}))

@@ -55,6 +55,8 @@ int c2d_has_tensor_core_head(void);
 void c2d_profile_enable(int on);
 void c2d_profile_reset(void);
 int c2d_profile_read(int kind, double* ms_total, long long* launches, double* flops_total);
+/* One recorded launch (in launch order); C2D_ERR_INVALID_ARG past the end. */
+int c2d_profile_entry(int index, int* kind, double* ms, double* flops);
 long long c2d_launch_count(void);
 void c2d_reset_launch_count(void);
 
@@ -98,6 +100,18 @@ int c2d_roi_crop_maxpool_fwd(const float* fmap, int B, int Hf, int Wf, int Cf, c
 int c2d_roi_crop_maxpool_bwd(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes,
                              int P, int crop_size, int pool_k, int pool_s, const void* dout,
                              int dout_dtype, float* dfmap, c2d_stream_t stream);
+
+/* Training variant: the forward also writes one byte per (ROI, pooled bin, channel quad) holding the four
+ * 2-bit max-pool arg-max indices (first maximum in window order, as MaxPoolGrad routes), and the backward
+ * scatters from those codes without reading the feature map again.  Same results as the pair above.
+ * codes: c2d_roi_argmax_code_bytes(B*P, Cf, crop_size) bytes. */
+size_t c2d_roi_argmax_code_bytes(int n_rois, int Cf, int crop_size);
+int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int Cf, const float* boxes,
+                                   int P, int crop_size, int pool_k, int pool_s, void* out, int out_dtype,
+                                   unsigned char* codes, c2d_stream_t stream);
+int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size,
+                                   int pool_k, int pool_s, const unsigned char* codes, const void* dout,
+                                   int dout_dtype, float* dfmap, c2d_stream_t stream);
 
 /* ---- K2/K3: box-classifier head, models/utils.py:165-177 ---------------------------
  * extract_box_classifier_features (Inception-v2 Mixed_5a..5c, OD-API) -> reduce_mean over

@@ -125,7 +125,28 @@ def test_roi_crop_maxpool_backward():
   out = ops.roi_crop_maxpool(f, dev(props))
   out.backward(dev(g))
   want = oroi.roi_crop_maxpool_bwd(fmap, props, g)
-  assert rel_err(f.grad.cpu().numpy(), want) < RTOL_F32
+  assert rel_err(f.grad.cpu().numpy(), want) < RTOL_F32          # training path: arg-max codes from the forward
+  # the stand-alone ABI pair that re-samples the feature map gives the same gradient
+  from cap2det_b200 import capi
+  from cap2det_b200.capi import call, ptr, stream
+  B, Hf, Wf, C = fmap.shape
+  P = props.shape[1]
+  for dt in (torch.float32, torch.bfloat16):
+    gd = dev(g).to(dt)
+    d1 = torch.empty((B, Hf, Wf, C), dtype=torch.float32, device='cuda')
+    call('c2d_roi_crop_maxpool_bwd', ptr(dev(fmap)), B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(gd),
+         capi.dtype_code(dt), ptr(d1), stream())
+    codes = torch.empty((capi.load().c2d_roi_argmax_code_bytes(B * P, C, 14),), dtype=torch.uint8, device='cuda')
+    out2 = torch.empty((B * P, 7, 7, C), dtype=dt, device='cuda')
+    call('c2d_roi_crop_maxpool_fwd_codes', ptr(dev(fmap)), B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(out2),
+         capi.dtype_code(dt), ptr(codes), stream())
+    d2 = torch.empty_like(d1)
+    call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(codes), ptr(gd),
+         capi.dtype_code(dt), ptr(d2), stream())
+    want_dt = oroi.roi_crop_maxpool_bwd(fmap, props, gd.float().cpu().numpy())
+    assert rel_err(d1.cpu().numpy(), want_dt) < RTOL_F32
+    assert rel_err(d2.cpu().numpy(), want_dt) < RTOL_F32
+    assert int(codes.max()) <= 255 and codes.numel() == B * P * 49 * C // 4
 
 
 def test_roi_rejects_unsupported_options():
