@@ -375,6 +375,130 @@ __global__ void pool3x3_bwd_kernel(const T* __restrict__ x, int ldx, const T* __
   }
 }
 
+// 4x4 stride-1 variants with FOUR channels per thread (8-byte bf16 / 16-byte fp32 accesses): the two-channel
+// kernels above are instruction-issue bound on the 1024-channel Mixed_5b / 5c planes.  The average divides by
+// the (compile-time) tap count; bf16 storage multiplies by the reciprocal instead (the difference, one fp32 ulp,
+// disappears in the bf16 rounding of the result).
+template <typename T> struct PoolDiv {
+  static __device__ __forceinline__ float f(float s, int cnt) { return s / (float)cnt; }
+};
+template <> struct PoolDiv<__nv_bfloat16> {
+  static __device__ __forceinline__ float f(float s, int cnt) { return s * (1.0f / (float)cnt); }
+};
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128)
+pool3x3_s1_4x4_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy, int n_rois, int C) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float4 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = ld4(x + ((size_t)n * 16 + i) * ldx + c);
+#pragma unroll
+  for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      float4 acc = MODE == 0 ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int iy = oy + dy, ix = ox + dx;
+          if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+            const float4 t = v[iy * 4 + ix];
+            if (MODE == 0) { acc.x = fmaxf(acc.x, t.x); acc.y = fmaxf(acc.y, t.y); acc.z = fmaxf(acc.z, t.z); acc.w = fmaxf(acc.w, t.w); }
+            else { acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w; }
+            ++cnt;
+          }
+        }
+      if (MODE == 1) {
+        acc.x = PoolDiv<T>::f(acc.x, cnt); acc.y = PoolDiv<T>::f(acc.y, cnt);
+        acc.z = PoolDiv<T>::f(acc.z, cnt); acc.w = PoolDiv<T>::f(acc.w, cnt);
+      }
+      st4(y + ((size_t)n * 16 + oy * 4 + ox) * ldy + c, acc);
+    }
+}
+
+// Backward (overwrite).  Max routes to the FIRST maximum in row-major window order, as pool3x3_bwd_kernel.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(128)
+pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int ldy, T* __restrict__ dx,
+                          int lddx, int n_rois, int C) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  float v[16][4], g[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (MODE == 0) {
+      const float4 t = ld4(x + ((size_t)n * 16 + i) * ldx + c);
+      v[i][0] = t.x; v[i][1] = t.y; v[i][2] = t.z; v[i][3] = t.w;
+    }
+    g[i][0] = g[i][1] = g[i][2] = g[i][3] = 0.f;
+  }
+#pragma unroll
+  for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      const float4 go4 = ld4(dy + ((size_t)n * 16 + oy * 4 + ox) * ldy + c);
+      const float go[4] = {go4.x, go4.y, go4.z, go4.w};
+      if (MODE == 0) {
+        float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        int arg[4] = {-1, -1, -1, -1};
+#pragma unroll
+        for (int dyy = -1; dyy <= 1; ++dyy)
+#pragma unroll
+          for (int dxx = -1; dxx <= 1; ++dxx) {
+            const int iy = oy + dyy, ix = ox + dxx;
+            if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+              const int i = iy * 4 + ix;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (v[i][k] > best[k] || arg[k] < 0) { best[k] = v[i][k]; arg[k] = i; }
+            }
+          }
+#pragma unroll
+        for (int dyy = -1; dyy <= 1; ++dyy)
+#pragma unroll
+          for (int dxx = -1; dxx <= 1; ++dxx) {
+            const int iy = oy + dyy, ix = ox + dxx;
+            if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+              const int i = iy * 4 + ix;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) g[i][k] += (i == arg[k]) ? go[k] : 0.f;
+            }
+          }
+      } else {
+        int cnt = 0;
+#pragma unroll
+        for (int dyy = -1; dyy <= 1; ++dyy)
+#pragma unroll
+          for (int dxx = -1; dxx <= 1; ++dxx) {
+            const int iy = oy + dyy, ix = ox + dxx;
+            if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) ++cnt;
+          }
+        float share[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) share[k] = PoolDiv<T>::f(go[k], cnt);
+#pragma unroll
+        for (int dyy = -1; dyy <= 1; ++dyy)
+#pragma unroll
+          for (int dxx = -1; dxx <= 1; ++dxx) {
+            const int iy = oy + dyy, ix = ox + dxx;
+            if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) g[iy * 4 + ix][k] += share[k];
+            }
+          }
+      }
+    }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    st4(dx + ((size_t)n * 16 + i) * lddx + c, make_float4(g[i][0], g[i][1], g[i][2], g[i][3]));
+}
+
 // feat[n, c] = mean_{hw} x[n, hw, c] (* keep_mask[n,c] / keep_prob).  models/utils.py:169-174.
 template <typename T>
 __global__ void avgpool_dropout_fwd_kernel(const T* __restrict__ x, int hw, int C, const float* __restrict__ keep_mask,

@@ -134,6 +134,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();                                       // everything above overlapped the previous kernel's tail
   const uint32_t tmem_base = pipe->tmem_base;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -362,6 +364,8 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
   __syncthreads();
   cluster_sync_all();                                // barriers of BOTH CTAs initialised before any remote signal
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = pipe->tmem_base;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -605,6 +609,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = pipe->tmem_base;
   const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.num_splits;
 

@@ -4,6 +4,7 @@
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <utility>
 #include <vector>
 
 #include "c2d_conv_simt.cuh"
@@ -142,6 +143,22 @@ struct ConvDesc {
   bf16* y; int ldy;              // output activation [n, hout, hout, cout]   (forward)
 };
 
+// Launch with programmatic stream serialization (see c2d_tc.cuh: pdl_wait); C2D_DISABLE_PDL=1 falls back to
+// plain stream order.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("C2D_DISABLE_PDL"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = disabled ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::ConvGemmParams& p, cudaStream_t st,
                        double flops, bool two) {
   int rc = tc_prepare();
@@ -152,10 +169,12 @@ static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::C
   if (two) {
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    tc::conv_gemm_tc2_kernel<<<2 * pairs, tc::kTcThreads, tc::k2SmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+    C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc2_kernel, 2 * pairs, tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1],
+                           maps[2], maps[3], mapB, p));
   } else {
     int grid = tiles < num_sms() ? tiles : num_sms();
-    tc::conv_gemm_tc_kernel<<<grid, tc::kTcThreads, tc::kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], mapB, p);
+    C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc_kernel, grid, tc::kTcThreads, tc::kTcSmemBytes, st, maps[0], maps[1], maps[2],
+                           maps[3], mapB, p));
   }
   count_launch();
   C2D_LAUNCH_OK();
@@ -376,7 +395,8 @@ static int launch_wgrad(tc::WgradParams& p, const CUtensorMap& mapY, const CUten
     tc::wgrad_tc2_kernel<<<2 * pairs, tc::kWgThreads, tc::kWg2SmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
   } else {
     const int grid = items < num_sms() ? items : num_sms();
-    tc::wgrad_tc_kernel<<<grid, tc::kWgThreads, tc::kWgSmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
+    C2D_CUDA_OK(launch_pdl(tc::wgrad_tc_kernel, grid, tc::kWgThreads, tc::kWgSmemBytes, st, mapY, mapX[0], mapX[1], mapX[2],
+                           mapX[3], p));
   }
   count_launch();
   C2D_LAUNCH_OK();
@@ -834,11 +854,11 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       count_launch();
     }
     if (i == 11) {
-      pool3x3_fwd_kernel<bf16, 4, 1, 1><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
+      pool3x3_s1_4x4_fwd_kernel<bf16, 1><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
       count_launch();
     }
     if (i == 18) {
-      pool3x3_fwd_kernel<bf16, 4, 1, 0><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
+      pool3x3_s1_4x4_fwd_kernel<bf16, 0><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
       count_launch();
     }
     if (head_in_group_tail(i)) continue;          // computed together with the first member of its group
@@ -916,13 +936,13 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       written[c.src] = true;
     }
     if (i == 18) {
-      pool3x3_bwd_kernel<bf16, 4, 1, 0, false><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(
+      pool3x3_s1_4x4_bwd_kernel<bf16, 0><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
           act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
       count_launch();
       written[X2] = true;
     }
     if (i == 11) {
-      pool3x3_bwd_kernel<bf16, 4, 1, 1, false><<<dim3(cdiv(1024 / 2, 128), n), 128, 0, st>>>(
+      pool3x3_s1_4x4_bwd_kernel<bf16, 1><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
           act[X1], 1024, grad[P1], 1024, grad[X1], 1024, n, 1024);
       count_launch();
       written[X1] = true;

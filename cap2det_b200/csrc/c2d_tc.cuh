@@ -10,6 +10,13 @@
 namespace c2d {
 namespace tc {
 
+// Programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start (barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains; pdl_wait() blocks
+// until the predecessor has completed and its writes are visible.  pdl_launch_dependents() lets the successor
+// be scheduled as soon as this grid's CTAs free their SMs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // ---- mbarrier -------------------------------------------------------------------------------
