@@ -79,26 +79,89 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
 
 // `codes` (optional, training): one byte per (bin, channel quad) = the four 2-bit max-pool arg-max indices, so
 // that the backward pass routes gradients without re-sampling the feature map.
+// The four samples of one pooling window, with the corner loads shared between them.
+// Per axis the two consecutive samples s0, s1 (floor/ceil rows r0 = lo0, r1 = hi0, r2 = lo1, r3 = hi1) fall into
+//   pattern 0: same cell      (lo1 == lo0 && hi1 == hi0)  -> s1 reads rows (r0, r1): 2 distinct rows
+//   pattern 1: adjacent cells (lo1 == hi0)                -> s1 reads rows (r1, r3): 3 distinct rows
+//   pattern 2: anything else                              -> s1 reads rows (r2, r3): 4 rows
+// The pattern depends on the bin only (warp-uniform), so it selects a template instance in which every register
+// index is a compile-time constant: 4 / 6 / 9 / ... / 16 loads instead of always 16.  The kernel is bound by the
+// number of load instructions, not by bytes.  Arithmetic per sample is unchanged (bit-exact).
+__device__ __forceinline__ float4 bilerp(float4 tl, float4 tr, float4 bl, float4 br, float xl, float yl, bool valid) {
+  float4 o;
+  o.x = lerp_rn(lerp_rn(tl.x, tr.x, xl), lerp_rn(bl.x, br.x, xl), yl);
+  o.y = lerp_rn(lerp_rn(tl.y, tr.y, xl), lerp_rn(bl.y, br.y, xl), yl);
+  o.z = lerp_rn(lerp_rn(tl.z, tr.z, xl), lerp_rn(bl.z, br.z, xl), yl);
+  o.w = lerp_rn(lerp_rn(tl.w, tr.w, xl), lerp_rn(bl.w, br.w, xl), yl);
+  return valid ? o : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+template <int YP, int XP>
+__device__ __forceinline__ void roi_window(const float4* __restrict__ img4, const RoiCoords& sc, int py, int px, int Wf,
+                                           int C4, int q, float4& v00, float4& v01, float4& v10, float4& v11) {
+  constexpr int R1T = YP == 0 ? 0 : (YP == 1 ? 1 : 2), R1B = YP == 0 ? 1 : 3;
+  constexpr int C1L = XP == 0 ? 0 : (XP == 1 ? 1 : 2), C1R = XP == 0 ? 1 : 3;
+  const int cy0 = 2 * py, cy1 = cy0 + 1, cx0 = 2 * px, cx1 = cx0 + 1;
+  const int rows[4] = {sc.lo[0][cy0], sc.hi[0][cy0], sc.lo[0][cy1], sc.hi[0][cy1]};
+  const int cols[4] = {sc.lo[1][cx0], sc.hi[1][cx0], sc.lo[1][cx1], sc.hi[1][cx1]};
+  float4 G[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const bool need_r = r < 2 || (r == 2 && YP == 2) || (r == 3 && YP >= 1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool need_c = c < 2 || (c == 2 && XP == 2) || (c == 3 && XP >= 1);
+      if (need_r && need_c) G[r][c] = __ldg(img4 + ((size_t)rows[r] * Wf + cols[c]) * C4 + q);
+    }
+  }
+  const float yl0 = sc.lerp[0][cy0], yl1 = sc.lerp[0][cy1], xl0 = sc.lerp[1][cx0], xl1 = sc.lerp[1][cx1];
+  const bool vy0 = sc.valid[0][cy0], vy1 = sc.valid[0][cy1], vx0 = sc.valid[1][cx0], vx1 = sc.valid[1][cx1];
+  v00 = bilerp(G[0][0], G[0][1], G[1][0], G[1][1], xl0, yl0, vy0 && vx0);
+  v01 = bilerp(G[0][C1L], G[0][C1R], G[1][C1L], G[1][C1R], xl1, yl0, vy0 && vx1);
+  v10 = bilerp(G[R1T][0], G[R1T][1], G[R1B][0], G[R1B][1], xl0, yl1, vy1 && vx0);
+  v11 = bilerp(G[R1T][C1L], G[R1T][C1R], G[R1B][C1L], G[R1B][C1R], xl1, yl1, vy1 && vx1);
+}
+
+__device__ __forceinline__ int axis_pattern(const RoiCoords& sc, int axis, int i0) {
+  const int lo0 = sc.lo[axis][i0], hi0 = sc.hi[axis][i0], lo1 = sc.lo[axis][i0 + 1], hi1 = sc.hi[axis][i0 + 1];
+  if (lo1 == lo0 && hi1 == hi0) return 0;
+  if (lo1 == hi0) return 1;
+  return 2;
+}
+
+// `codes` (optional, training): one byte per (bin, channel quad) = the four 2-bit max-pool arg-max indices, so
+// that the backward pass routes gradients without re-sampling the feature map.
 template <typename OutT>
 __global__ void __launch_bounds__(288)
 roi_crop_maxpool_fwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
                             int P, int crop, OutT* __restrict__ out, unsigned char* __restrict__ codes) {
   __shared__ RoiCoords sc;
+  __shared__ unsigned char pat[kMaxCrop / 2][2];        // [pooled index][axis] -> pattern 0/1/2
   const int roi = blockIdx.x;
   const int b = roi / P;
   roi_setup_coords(sc, boxes[roi], Hf, Wf, crop);
   __syncthreads();
   const int C4 = Cf >> 2, hp = crop >> 1;
+  if (threadIdx.x < 2 * hp) pat[threadIdx.x >> 1][threadIdx.x & 1] = (unsigned char)axis_pattern(sc, threadIdx.x & 1, threadIdx.x & ~1);
+  __syncthreads();
   const float4* img4 = reinterpret_cast<const float4*>(fmap + (size_t)b * Hf * Wf * Cf);
   OutT* o = out + (size_t)roi * hp * hp * Cf;
   const int items = hp * hp * C4;
   for (int w = threadIdx.x; w < items; w += blockDim.x) {
     int q = w % C4, pos = w / C4;
     int py = pos / hp, px = pos - py * hp;
-    float4 v00 = roi_sample(img4, sc, 2 * py, 2 * px, Wf, C4, q);
-    float4 v01 = roi_sample(img4, sc, 2 * py, 2 * px + 1, Wf, C4, q);
-    float4 v10 = roi_sample(img4, sc, 2 * py + 1, 2 * px, Wf, C4, q);
-    float4 v11 = roi_sample(img4, sc, 2 * py + 1, 2 * px + 1, Wf, C4, q);
+    float4 v00, v01, v10, v11;
+    switch (pat[py][0] * 3 + pat[px][1]) {
+      case 0: roi_window<0, 0>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 1: roi_window<0, 1>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 2: roi_window<0, 2>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 3: roi_window<1, 0>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 4: roi_window<1, 1>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 5: roi_window<1, 2>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 6: roi_window<2, 0>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      case 7: roi_window<2, 1>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+      default: roi_window<2, 2>(img4, sc, py, px, Wf, C4, q, v00, v01, v10, v11); break;
+    }
     float4 m;
     m.x = fmaxf(fmaxf(v00.x, v01.x), fmaxf(v10.x, v11.x));
     m.y = fmaxf(fmaxf(v00.y, v01.y), fmaxf(v10.y, v11.y));
