@@ -499,6 +499,42 @@ pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict_
     st4(dx + ((size_t)n * 16 + i) * lddx + c, make_float4(g[i][0], g[i][1], g[i][2], g[i][3]));
 }
 
+// y = relu(avgpool3x3_same(z) + shift) on 4x4 planes: the tail of Mixed_5b/Branch_3 when the 1x1 convolution
+// runs BEFORE the pooling (see kHead5bPoolConv).  z holds raw accumulators (no shift, no ReLU).
+template <typename T>
+__global__ void avgpool_shift_relu_4x4_kernel(const T* __restrict__ z, int ldz, const float* __restrict__ shift,
+                                              T* __restrict__ y, int ldy, int n_rois, int C) {
+  const int c4n = C >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_rois * c4n) return;
+  const int n = (int)(idx / c4n), c = (int)(idx - (long long)n * c4n) * 4;
+  float4 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = ld4(z + ((size_t)n * 16 + i) * ldz + c);
+  const float4 s = *reinterpret_cast<const float4*>(shift + c);
+#pragma unroll
+  for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      int cnt = 0;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int iy = oy + dy, ix = ox + dx;
+          if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+            const float4 t = v[iy * 4 + ix];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            ++cnt;
+          }
+        }
+      acc.x = fmaxf(PoolDiv<T>::f(acc.x, cnt) + s.x, 0.f); acc.y = fmaxf(PoolDiv<T>::f(acc.y, cnt) + s.y, 0.f);
+      acc.z = fmaxf(PoolDiv<T>::f(acc.z, cnt) + s.z, 0.f); acc.w = fmaxf(PoolDiv<T>::f(acc.w, cnt) + s.w, 0.f);
+      st4(y + ((size_t)n * 16 + oy * 4 + ox) * ldy + c, acc);
+    }
+}
+
 // feat[n, c] = mean_{hw} x[n, hw, c] (* keep_mask[n,c] / keep_prob).  models/utils.py:169-174.
 template <typename T>
 __global__ void avgpool_dropout_fwd_kernel(const T* __restrict__ x, int hw, int C, const float* __restrict__ keep_mask,

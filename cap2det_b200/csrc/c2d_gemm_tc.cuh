@@ -43,10 +43,11 @@ struct ConvGemmParams {
   const float* shift;       // per-column addend (BN shift / bias), n_total entries, or null
   // output column segments: columns [seg_begin[s], seg_begin[s+1]) go to seg_out[s] (leading dim seg_ld[s])
   int nseg;
-  int seg_begin[4];
-  void* seg_out[3];
-  int seg_ld[3];
+  int seg_begin[5];
+  void* seg_out[4];
+  int seg_ld[4];
   int out_f32, relu, accum;
+  int act_cols;             // shift and ReLU apply to columns < act_cols; the rest are written as raw accumulators
   // fused ReLU backward: out = (y > 0) ? out : 0 for columns < mask_cols; y = bf16 activation with the
   // same row mapping as the (single) output segment.  Used by the LAST writer of a gradient buffer.
   const __nv_bfloat16* mask; int mask_ld; int mask_cols;
@@ -247,12 +248,14 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             int sgm = 0;
             if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
             if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+            if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
             const int scol = col0 - p.seg_begin[sgm];
             const long long ooff = orow * p.seg_ld[sgm] + scol;
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (p.shift != nullptr) {
+            const bool act = col0 < p.act_cols;
+            if (p.shift != nullptr && act) {
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -260,7 +263,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
             }
-            if (p.relu) {
+            if (p.relu && act) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }
@@ -476,12 +479,14 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
             int sgm = 0;
             if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
             if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+            if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
             const int scol = col0 - p.seg_begin[sgm];
             const long long ooff = orow * p.seg_ld[sgm] + scol;
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            if (p.shift != nullptr) {
+            const bool act = col0 < p.act_cols;
+            if (p.shift != nullptr && act) {
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
@@ -489,7 +494,7 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
             }
-            if (p.relu) {
+            if (p.relu && act) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
             }

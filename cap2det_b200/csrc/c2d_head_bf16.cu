@@ -188,8 +188,9 @@ static void set_segments(tc::ConvGemmParams& p, const OutSeg* segs, int nseg) {
     p.seg_begin[s] = begin; p.seg_out[s] = segs[s].out; p.seg_ld[s] = segs[s].ld;
     begin += segs[s].cols;
   }
-  for (int s = nseg; s < 4; ++s) p.seg_begin[s] = begin;
+  for (int s = nseg; s < 5; ++s) p.seg_begin[s] = begin;
   p.n_total = begin;
+  p.act_cols = begin;
 }
 
 // ---- tile geometry (single-CTA 256-row tiles or 2-CTA pairs of 128-row half tiles) ----------------
@@ -230,13 +231,14 @@ static int b_box_rows(const tc::ConvGemmParams& p, bool two) { return two ? p.n_
 // Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift) with the output columns split over `segs`.
 //   w16: [sum cols][k*k][cin] bf16 (K-major); shift: [sum cols] or null.
 static int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
-                       int out_f32, cudaStream_t st) {
+                       int out_f32, cudaStream_t st, int act_cols = -1) {
   tc::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4], mapB;
   const int taps = c.k * c.k;
   const bool two = use_2cta(c.k == 1, c.hout * c.hout);
   set_segments(p, segs, nseg);
+  if (act_cols >= 0) p.act_cols = act_cols;
   const int cout = p.n_total;
   set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
@@ -630,6 +632,14 @@ static FoldTable make_fold_table(const HeadPlan& pl) {
       off += kHeadConvs[first + j].cout;
     }
   }
+  {   // Mixed_5b/Branch_3's 1x1 runs as a fourth member of the Mixed_5b group (see kHead5bPoolConv)
+    const int first = kHeadGroups[1].first;
+    int total = kHeadConvs[kHead5bPoolConv].cout;
+    for (int j = 0; j < kHeadGroups[1].size; ++j) total += kHeadConvs[first + j].cout;
+    for (int j = 0; j < kHeadGroups[1].size; ++j) t.e[first + j].wt_ld = total;
+    FoldEntry& e = t.e[kHead5bPoolConv];
+    e.wt_base = pl.poff[first].w_only; e.wt_ld = total; e.wt_coloff = total - kHeadConvs[kHead5bPoolConv].cout;
+  }
   return t;
 }
 
@@ -853,25 +863,36 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
       count_launch();
     }
-    if (i == 11) {
-      pool3x3_s1_4x4_fwd_kernel<bf16, 1><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X1], 1024, act[P1], 1024, n, 1024);
-      count_launch();
-    }
     if (i == 18) {
       pool3x3_s1_4x4_fwd_kernel<bf16, 0><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
       count_launch();
     }
-    if (head_in_group_tail(i)) continue;          // computed together with the first member of its group
+    if (head_in_group_tail(i) || i == kHead5bPoolConv) continue;   // computed together with the first member of its group
     const HeadParamOff& o = pl.poff[i];
     int gsz = head_group_size(i);
     if (gsz == 0) gsz = 1;
-    OutSeg segs[3];
+    OutSeg segs[4];
     for (int j = 0; j < gsz; ++j) {
       const HeadConv& cj = kHeadConvs[i + j];
       segs[j].out = act[cj.dst] + cj.dst_off; segs[j].ld = kHeadBufs[cj.dst].ch; segs[j].cols = cj.cout;
     }
-    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, segs, gsz, 0, st);
+    int act_cols = -1;
+    if (i == kHeadGroups[1].first) {
+      // + Mixed_5b/Branch_3's 1x1 applied to X1 itself; its raw result z (P1's memory, [n,16,128]) is pooled below
+      const HeadConv& cp = kHeadConvs[kHead5bPoolConv];
+      act_cols = 0;
+      for (int j = 0; j < gsz; ++j) act_cols += segs[j].cols;
+      segs[gsz].out = act[P1]; segs[gsz].ld = cp.cout; segs[gsz].cols = cp.cout;
+      ++gsz;
+    }
+    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, segs, gsz, 0, st, act_cols);
     if (rc != C2D_OK) return rc;
+    if (i == kHeadGroups[1].first) {
+      const HeadConv& cp = kHeadConvs[kHead5bPoolConv];
+      avgpool_shift_relu_4x4_kernel<bf16><<<cdiv((long long)n * (cp.cout / 4), 128), 128, 0, st>>>(
+          act[P1], cp.cout, shf + pl.poff[kHead5bPoolConv].ch, act[cp.dst] + cp.dst_off, kHeadBufs[cp.dst].ch, n, cp.cout);
+      count_launch();
+    }
   }
   avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
   count_launch();
@@ -910,18 +931,33 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
     const int ldd = kHeadBufs[c.dst].ch;
     (void)M;
     ConvDesc d = head_conv_desc(i, n, act);
+    if (i == kHead5bPoolConv) {
+      // pool the 128-channel gradient first (avg-pool backward is linear and commutes with the 1x1 convolution);
+      // q (P1's gradient memory, [n,16,128]) then acts as the gradient of a 1x1 convolution applied to X1
+      bf16* q = grad[P1];
+      pool3x3_s1_4x4_bwd_kernel<bf16, 1><<<dim3(1, n), 32, 0, st>>>(nullptr, 0, dy, ldd, q, c.cout, n, c.cout);
+      count_launch();
+      d.x = act[X1]; d.ldx = kHeadBufs[X1].ch;
+      int rc = conv_wgrad_tc(d, q, c.cout, dwsf + o.w_only, st, dshf + o.ch);
+      if (rc != C2D_OK) return rc;
+      continue;
+    }
     int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st, dshf + o.ch);
     if (rc != C2D_OK) return rc;
     // data gradient: a sibling group is reduced by ONE GEMM once its first (lowest) member is reached
     if (!head_in_group_tail(i) && !(c.src == X0 && dx0 == nullptr)) {
       int gsz = head_group_size(i);
       if (gsz == 0) gsz = 1;
-      InSeg srcs[3];
+      InSeg srcs[4];
       for (int j = 0; j < gsz; ++j) {
         const HeadConv& cj = kHeadConvs[i + j];
         srcs[j].du = grad[cj.dst] + cj.dst_off; srcs[j].ld = kHeadBufs[cj.dst].ch; srcs[j].cols = cj.cout;
       }
-      // the destination is complete after this GEMM (pool backward into X1/X2 runs BEFORE the merged
+      if (i == kHeadGroups[1].first) {
+        srcs[gsz].du = grad[P1]; srcs[gsz].ld = kHeadConvs[kHead5bPoolConv].cout; srcs[gsz].cols = kHeadConvs[kHead5bPoolConv].cout;
+        ++gsz;
+      }
+      // the destination is complete after this GEMM (the max-pool backward into X2 runs BEFORE the merged
       // sibling dgrad), so it applies the ReLU mask of the convolutions that produced the buffer:
       // all columns for conv outputs, [0,448) for X1 (the rest is the max-pool branch), none for X0 / P*.
       const bf16* mask = nullptr;
@@ -940,12 +976,6 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
           act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
       count_launch();
       written[X2] = true;
-    }
-    if (i == 11) {
-      pool3x3_s1_4x4_bwd_kernel<bf16, 1><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
-          act[X1], 1024, grad[P1], 1024, grad[X1], 1024, n, 1024);
-      count_launch();
-      written[X1] = true;
     }
     if (i == 5 && dx0 != nullptr) {
       pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(

@@ -51,6 +51,13 @@ static const HeadConv kHeadConvs[kNumHeadConvs] = {
     {"Mixed_5c/Branch_3/Conv2d_0b_1x1", 1, 1024, 128, 1, P2, 0, X3, 896, 4, 4},
 };
 
+// Mixed_5b/Branch_3 is AvgPool_0a_3x3 -> Conv2d_0b_1x1.  Average pooling acts on positions, a 1x1 convolution
+// on channels, so they commute: conv(avgpool(X1)) == avgpool(conv(X1)).  The bf16 path therefore runs this
+// convolution as a FOURTH member of the Mixed_5b sibling GEMM on X1 and pools its 128-channel result (instead
+// of pooling the 1024-channel input and running a separate, memory-bound GEMM); backward likewise pools the
+// 128-channel gradient first and feeds it to the merged data / weight gradients.
+constexpr int kHead5bPoolConv = 11;
+
 // Sibling groups (first member, size); every other convolution is its own group.
 struct HeadGroup { int first, size; };
 static const HeadGroup kHeadGroups[3] = {{0, 2}, {5, 3}, {12, 3}};
@@ -93,7 +100,14 @@ static inline HeadPlan make_head_plan(int n_rois, int elt_bytes) {
     p.poff[i].beta = po; po += c.cout;
     p.poff[i].mean = po; po += c.cout;
     p.poff[i].var = po; po += c.cout;
-    p.poff[i].w_only = wo; wo += nw;
+  }
+  // Folded weights / shifts: table order, except that Mixed_5b/Branch_3's 1x1 (conv 11) follows the three
+  // sibling 1x1s of Mixed_5b (5, 6, 7): the bf16 path runs all four as ONE GEMM on X1 (kHead5bPoolConv).
+  static const int order[kNumHeadConvs] = {0, 1, 2, 3, 4, 5, 6, 7, 11, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18};
+  for (int j = 0; j < kNumHeadConvs; ++j) {
+    const int i = order[j];
+    const HeadConv& c = kHeadConvs[i];
+    p.poff[i].w_only = wo; wo += (long long)c.cout * c.k * c.k * c.cin;
     p.poff[i].ch = co; co += c.cout;
   }
   p.param_total = po; p.w_only_total = wo; p.ch_total = co;

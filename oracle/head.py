@@ -116,13 +116,25 @@ def head_mixed5(x_nhwc, p, collect=None, emulate_bf16=False):
     b1 = c(c(x, blk + '/Branch_1/Conv2d_0a_1x1'), blk + '/Branch_1/Conv2d_0b_3x3')
     b2 = c(c(c(x, blk + '/Branch_2/Conv2d_0a_1x1'), blk + '/Branch_2/Conv2d_0b_3x3'),
            blk + '/Branch_2/Conv2d_0c_3x3')
-    if pool == 'avg':
-      b3 = TF_.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
+    if pool == 'avg' and emulate_bf16:
+      # The bf16 CUDA path evaluates AvgPool -> 1x1 conv as 1x1 conv -> AvgPool (they commute: one acts on
+      # positions, the other on channels) and stores the 128-channel intermediate in bf16; mirror its rounding
+      # points so that ReLU masks agree.  The plain fp32 branch below keeps the reference order.
+      q = p[blk + '/Branch_3/Conv2d_0b_1x1']
+      scale = _t(q['gamma']) * torch.rsqrt(_t(q['var']) + BN_EPS)
+      shift = _t(q['beta']) - _t(q['mean']) * scale
+      wf = _RoundBF16.apply(_t(q['weights']).permute(0, 3, 1, 2) * scale.view(-1, 1, 1, 1))
+      z = _store_bf16(TF_.conv2d(x, wf, None))
+      b3 = TF_.avg_pool2d(z, 3, stride=1, padding=1, count_include_pad=False) + shift.view(1, -1, 1, 1)
+      b3 = _store_bf16(torch.relu(b3))
     else:
-      b3 = TF_.max_pool2d(x, 3, stride=1, padding=1)
-    if emulate_bf16:
-      b3 = _store_bf16(b3)
-    b3 = c(b3, blk + '/Branch_3/Conv2d_0b_1x1')
+      if pool == 'avg':
+        b3 = TF_.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
+      else:
+        b3 = TF_.max_pool2d(x, 3, stride=1, padding=1)
+      if emulate_bf16:
+        b3 = _store_bf16(b3)
+      b3 = c(b3, blk + '/Branch_3/Conv2d_0b_1x1')
     x = torch.cat([b0, b1, b2, b3], dim=1)
   return x.permute(0, 2, 3, 1)
 
