@@ -345,16 +345,17 @@ struct Tc2Pipe {
   uint32_t tmem_base;
 };
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
-conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
-                     const __grid_constant__ CUtensorMap mapB, const ConvGemmParams p) {
+// Body shared by the single-problem kernel and the multi-problem kernel below: the CTA pair `pair` of
+// `num_pairs` pairs works through the tiles of problem `p`.
+__device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
+                                                   const CUtensorMap& mapA2, const CUtensorMap& mapA3,
+                                                   const CUtensorMap& mapB, const ConvGemmParams& p, const int pair,
+                                                   const int num_pairs) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Tc2Pipe* pipe = reinterpret_cast<Tc2Pipe*>(smem + k2Stages * k2StageBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < k2Stages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
@@ -552,6 +553,33 @@ conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_con
     tc_fence_after();
     tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                     const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvGemmParams p) {
+  conv_gemm_tc2_body(mapA0, mapA1, mapA2, mapA3, mapB, p, blockIdx.x >> 1, gridDim.x >> 1);
+}
+
+// Up to four independent problems that share the B operand (weights) and the N tiling, each with its own A
+// tensor map (tap_map = its index), run in ONE launch: the CTA pairs are partitioned between the problems in
+// proportion to their work.  Used for the four output-parity classes of a stride-2 data gradient, which as
+// separate launches each left most of the machine idle in their tail.
+struct ConvGemmMulti {
+  int count;
+  int pair_begin[5];          // pairs [pair_begin[c], pair_begin[c+1]) work on problem c
+  ConvGemmParams p[4];
+};
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv_gemm_tc2_multi_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                           const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
+                           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvGemmMulti mp) {
+  const int pair = blockIdx.x >> 1;
+  int cls = 0;
+  while (cls + 1 < mp.count && pair >= mp.pair_begin[cls + 1]) ++cls;
+  conv_gemm_tc2_body(mapA0, mapA1, mapA2, mapA3, mapB, mp.p[cls], pair - mp.pair_begin[cls],
+                     mp.pair_begin[cls + 1] - mp.pair_begin[cls]);
 }
 
 // ---------------------------------------------------------------------------------------------

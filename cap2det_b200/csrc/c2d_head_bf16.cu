@@ -116,6 +116,7 @@ static int tc_prepare() {
   if (!g_attr_done) {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWg2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
     g_attr_done = true;
@@ -347,18 +348,21 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
     }
     return launch_conv(maps, mapB, p, st, 2.0 * c.n * c.hout * c.hout * 9.0 * c.cin * c.cout, two);
   }
-  // stride 2 (7x7 <- 4x4): one launch per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
+  // stride 2 (7x7 <- 4x4): one PROBLEM per output parity class (py, px); y = 2*jy + py, x = 2*jx + px.
+  // The four classes (1, 2, 2 and 4 taps) share the weights and run in one multi-problem launch.
+  tc::ConvGemmMulti mp;
+  memset(&mp, 0, sizeof(mp));
+  double flops = 0.0, work[4];
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
-      tc::ConvGemmParams p = base;
+      const int cls = py * 2 + px;
+      tc::ConvGemmParams& p = mp.p[cls];
+      p = base;
       const int nh = py ? 3 : 4, nw = px ? 3 : 4;
-      const bool two = use_2cta(false, nh * nw);
-      set_n_tiles(p, two);
-      if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, b_box_rows(p, two))) return C2D_ERR_CUDA;
-      set_geo_tiles(p, c.n, nh * nw, nw, two);
+      set_n_tiles(p, true);                     // always the 2-CTA kernel (C2D_DISABLE_2CTA does not apply here)
+      set_geo_tiles(p, c.n, nh * nw, nw, true);
       p.Hf = p.Wf = 7; p.sy = p.sx = 2; p.oy = py; p.ox = px;
-      if (!make_map_nhwc(&maps[0], du, c.cout, 4, c.n, lddu, nw, nh, p.rois_per_tile)) return C2D_ERR_CUDA;
-      maps[1] = maps[2] = maps[3] = maps[0];
+      if (!make_map_nhwc(&maps[cls], du, c.cout, 4, c.n, lddu, nw, nh, p.rois_per_tile)) return C2D_ERR_CUDA;
       // even coordinate: tap 1 reads o = j ; odd coordinate: tap 0 reads o = j + 1, tap 2 reads o = j
       int ty[2], oyv[2], nty = 0, tx[2], oxv[2], ntx = 0;
       if (py == 0) { ty[0] = 1; oyv[0] = 0; nty = 1; } else { ty[0] = 0; oyv[0] = 1; ty[1] = 2; oyv[1] = 0; nty = 2; }
@@ -367,14 +371,38 @@ static int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const b
       for (int a = 0; a < nty; ++a)
         for (int b2 = 0; b2 < ntx; ++b2) {
           p.tap_y[t] = oyv[a]; p.tap_x[t] = oxv[b2]; p.tap_koff[t] = (ty[a] * 3 + tx[b2]) * c.cout;
-          p.tap_chunks[t] = chunks; p.tap_map[t] = 0;
+          p.tap_chunks[t] = chunks; p.tap_map[t] = cls;
           ++t;
         }
       p.taps = t;
       // the four parity classes together do the work of one stride-2 convolution (9 taps x 16 outputs)
-      int rc = launch_conv(maps, mapB, p, st, 2.0 * c.n * (double)(nh * nw) * t * c.cin * c.cout, two);
-      if (rc != C2D_OK) return rc;
+      flops += 2.0 * c.n * (double)(nh * nw) * t * c.cin * c.cout;
+      // a tile costs its k-steps plus a read-modify-write epilogue worth ~16 k-steps (measured: the classes are
+      // epilogue bound, weighting by taps alone starved the one-tap class)
+      work[cls] = (double)p.num_m_tiles * p.num_n_tiles * (t * chunks + 16);
     }
+  if (!make_map_flat(&mapB, wt16, (long long)taps * ksum, c.cin, (long long)taps * ksum, b_box_rows(mp.p[0], true))) return C2D_ERR_CUDA;
+  int rc = tc_prepare();
+  if (rc != C2D_OK) return rc;
+  if (c.n == 0) return C2D_OK;
+  // partition the CTA pairs in proportion to tiles x taps (at least one pair per class)
+  const int pairs = num_sms() / 2;
+  double total = work[0] + work[1] + work[2] + work[3];
+  int given = 0;
+  mp.count = 4;
+  for (int cls = 0; cls < 4; ++cls) {
+    int share = cls == 3 ? pairs - given : (int)(pairs * work[cls] / total + 0.5);
+    if (share < 1) share = 1;
+    if (cls < 3 && given + share > pairs - (3 - cls)) share = pairs - (3 - cls) - given;
+    mp.pair_begin[cls] = given;
+    given += share;
+  }
+  mp.pair_begin[4] = given;
+  ProfScope prof(st, 0, flops);
+  C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc2_multi_kernel, 2 * given, tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1],
+                         maps[2], maps[3], mapB, mp));
+  count_launch();
+  C2D_LAUNCH_OK();
   return C2D_OK;
 }
 
@@ -644,20 +672,39 @@ static FoldTable make_fold_table(const HeadPlan& pl) {
 }
 
 // ws16[co][k] = W[co][k] * s(co);  wt16 = transposed copy for the data gradient;  shift = beta - mean * s.
-__global__ void fold_bn_bf16_kernel(const float* __restrict__ params, const FoldTable tab, bf16* __restrict__ ws16,
-                                    bf16* __restrict__ wt16, float* __restrict__ shift) {
-  const FoldEntry& e = tab.e[blockIdx.y];
-  const int co = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (co >= e.cout) return;
-  const float s = params[e.gamma + co] * rsqrtf(params[e.var + co] + kBnEps);
-  if (lane == 0) shift[e.ch + co] = params[e.beta + co] - params[e.mean + co] * s;
+// One CTA = 32 output channels x 64 reduction indices of one convolution: coalesced fp32 reads and bf16 writes
+// along k, then the tile goes through shared memory so that the transposed copy is written as 16-byte runs
+// along co (the first version scattered 2-byte stores with a stride of cout and took 6x longer).
+__global__ void __launch_bounds__(256)
+fold_bn_bf16_kernel(const float* __restrict__ params, const FoldTable tab, bf16* __restrict__ ws16,
+                    bf16* __restrict__ wt16, float* __restrict__ shift) {
+  const FoldEntry& e = tab.e[blockIdx.z];
   const int K = e.taps * e.cin;
-  const float* w = params + e.w + (long long)co * K;
-  for (int k = lane; k < K; k += 32) {
-    const bf16 v = __float2bfloat16_rn(w[k] * s);
-    ws16[e.w_only + (long long)co * K + k] = v;
+  const int co0 = blockIdx.y * 32, k0 = blockIdx.x * 64;
+  if (co0 >= e.cout || k0 >= K) return;
+  __shared__ bf16 tile[64][32 + 8];        // [k][co], padded against bank conflicts
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {            // warp w handles channels co0 + 4w + r, lanes cover 64 k (2 each)
+    const int col = warp * 4 + r, co = co0 + col;
+    if (co >= e.cout) break;               // cout is a multiple of 32 for every head convolution; kept for safety
+    const float s = params[e.gamma + co] * rsqrtf(params[e.var + co] + kBnEps);
+    if (k0 == 0 && lane == 0) shift[e.ch + co] = params[e.beta + co] - params[e.mean + co] * s;
+    const int k = k0 + 2 * lane;
+    if (k < K) {                           // K is even
+      const float2 w = *reinterpret_cast<const float2*>(params + e.w + (long long)co * K + k);
+      const __nv_bfloat162 v = __floats2bfloat162_rn(w.x * s, w.y * s);
+      *reinterpret_cast<__nv_bfloat162*>(ws16 + e.w_only + (long long)co * K + k) = v;
+      tile[2 * lane][col] = v.x; tile[2 * lane + 1][col] = v.y;
+    }
+  }
+  __syncthreads();
+  const int kk = threadIdx.x >> 2, cg = (threadIdx.x & 3) * 8;      // 64 k x 4 groups of 8 channels
+  const int k = k0 + kk;
+  if (k < K && co0 + cg < e.cout) {
     const int tap = k / e.cin, ci = k - tap * e.cin;
-    wt16[e.wt_base + ((long long)ci * e.taps + tap) * e.wt_ld + e.wt_coloff + co] = v;
+    const uint4 v = *reinterpret_cast<const uint4*>(&tile[kk][cg]);
+    *reinterpret_cast<uint4*>(wt16 + e.wt_base + ((long long)ci * e.taps + tap) * e.wt_ld + e.wt_coloff + co0 + cg) = v;
   }
 }
 __global__ void unfold_bn_all_kernel(const float* __restrict__ params, const FoldTable tab,
@@ -856,7 +903,7 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   float* shf = reinterpret_cast<float*>(ws + pl.shift_off);
   bf16* ws16 = reinterpret_cast<bf16*>(ws + pl.ws16_off);
   bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
-  fold_bn_bf16_kernel<<<dim3(cdiv(352, 8), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), ws16, wt16, shf);
+  fold_bn_bf16_kernel<<<dim3(cdiv(9 * 256, 64), cdiv(352, 32), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), ws16, wt16, shf);
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
     if (i == 5) {
