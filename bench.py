@@ -197,6 +197,9 @@ def main():
   torch.cuda.set_device(local_rank)
   if world > 1:
     import datetime
+    # NCCL prints its version banner on STDOUT at VERSION level and above; stdout carries exactly one JSON line
+    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+      os.environ['NCCL_DEBUG'] = 'WARN'
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                             timeout=datetime.timedelta(seconds=120))
   dev = torch.device('cuda', local_rank)
