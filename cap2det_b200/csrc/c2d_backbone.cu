@@ -75,7 +75,8 @@ static const BbLayout& bb_layout() {
       L.c[i].gamma = o; o += c.cout; L.c[i].beta = o; o += c.cout; L.c[i].mean = o; o += c.cout; L.c[i].var = o; o += c.cout;
     }
     // Folded bf16 weights / shifts: the 1x1 convolutions that read a block's input sit next to each other
-    // (Branch_0, Branch_1 reducer, Branch_2 reducer) so that they run as ONE GEMM with concatenated columns.
+    // (Branch_0, Branch_1 reducer, Branch_2 reducer, and Branch_3's 1x1, which commutes with its average pool
+    // and is therefore applied to the block input as well) so that they run as ONE GEMM with concatenated columns.
     long long w16 = 0, wt16 = 0, ch = 0;
     auto place = [&](int i) {
       const BbConv& c = kBbConvs[i];
@@ -86,9 +87,9 @@ static const BbLayout& bb_layout() {
       L.c[i].ch = ch; ch += c.cout;
     };
     place(0); place(1);
-    for (int i0 : {kBb3b, kBb3c}) for (int j : {0, 1, 3, 2, 4, 5, 6}) place(i0 + j);
+    for (int i0 : {kBb3b, kBb3c}) for (int j : {0, 1, 3, 6, 2, 4, 5}) place(i0 + j);
     for (int j : {0, 2, 1, 3, 4}) place(kBb4a + j);
-    for (int blk = 0; blk < 4; ++blk) for (int j : {0, 1, 3, 2, 4, 5, 6}) place(kBb4b + 7 * blk + j);
+    for (int blk = 0; blk < 4; ++blk) for (int j : {0, 1, 3, 6, 2, 4, 5}) place(kBb4b + 7 * blk + j);
     L.param_floats = o; L.w_elems = w16; L.wt_elems = wt16; L.ch_total = ch;
     done = true;
   }
@@ -263,9 +264,12 @@ __global__ void bb_maxpool_s2_kernel(const bf16* __restrict__ x, int B, int H, i
   *reinterpret_cast<uint4*>(y + (((long long)n * Ho + oy) * Wo + ox) * ldy + c8 * 8) = o;
 }
 
-// slim.avg_pool2d([3,3], stride 1, SAME): TF divides by the number of in-bounds taps.
-__global__ void bb_avgpool_s1_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, int ldx,
-                                     bf16* __restrict__ y, int ldy) {
+// slim.avg_pool2d([3,3], stride 1, SAME) divides by the number of in-bounds taps.
+// y = relu(avgpool3x3_same(z) + shift): tail of Branch_3 when its 1x1 convolution runs BEFORE the pooling
+// (AvgPool acts on positions, the 1x1 on channels: they commute).  z holds raw accumulators.  OutT = bf16 or float.
+template <typename OutT>
+__global__ void bb_avgpool_shift_relu_kernel(const bf16* __restrict__ z, int B, int H, int W, int C,
+                                             const float* __restrict__ shift, OutT* __restrict__ y, int ldy) {
   const int c8n = C >> 3;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)B * H * W * c8n) return;
@@ -284,7 +288,7 @@ __global__ void bb_avgpool_s1_kernel(const bf16* __restrict__ x, int B, int H, i
     for (int kx = -1; kx <= 1; ++kx) {
       const int ix = ox + kx;
       if (ix < 0 || ix >= W) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + iy) * W + ix) * ldx + c8 * 8);
+      const uint4 v = *reinterpret_cast<const uint4*>(z + (((long long)n * H + iy) * W + ix) * C + c8 * 8);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); s[2 * i] += f.x; s[2 * i + 1] += f.y; }
@@ -292,13 +296,50 @@ __global__ void bb_avgpool_s1_kernel(const bf16* __restrict__ x, int B, int H, i
     }
   }
   const float c = (float)cnt;
+  OutT* o = y + (((long long)n * H + oy) * W + ox) * ldy + c8 * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) Elem<OutT>::st(o + i, fmaxf(__fdiv_rn(s[i], c) + shift[c8 * 8 + i], 0.f));
+}
+
+// Backward of avgpool3x3_same (stride 1): dx[p] = sum over the windows o containing p of dy[o] / cnt[o].
+__global__ void bb_avgpool_bwd_kernel(const bf16* __restrict__ dy, int lddy, int B, int H, int W, int C,
+                                      bf16* __restrict__ dx, int lddx) {
+  const int c8n = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * H * W * c8n) return;
+  const int c8 = (int)(idx % c8n);
+  long long r = idx / c8n;
+  const int x = (int)(r % W); r /= W;
+  const int y = (int)(r % H);
+  const int n = (int)(r / H);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int ky = -1; ky <= 1; ++ky) {
+    const int oy = y + ky;
+    if (oy < 0 || oy >= H) continue;
+    const int ny = (oy > 0) + 1 + (oy < H - 1);
+    for (int kx = -1; kx <= 1; ++kx) {
+      const int ox = x + kx;
+      if (ox < 0 || ox >= W) continue;
+      const int nx = (ox > 0) + 1 + (ox < W - 1);
+      const float inv = (float)(ny * nx);
+      const uint4 v = *reinterpret_cast<const uint4*>(dy + (((long long)n * H + oy) * W + ox) * lddy + c8 * 8);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        s[2 * i] += __fdiv_rn(f.x, inv); s[2 * i + 1] += __fdiv_rn(f.y, inv);
+      }
+    }
+  }
   __nv_bfloat162 h[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(__fdiv_rn(s[2 * i], c), __fdiv_rn(s[2 * i + 1], c));
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(s[2 * i], s[2 * i + 1]);
   uint4 o;
   o.x = *reinterpret_cast<uint32_t*>(&h[0]); o.y = *reinterpret_cast<uint32_t*>(&h[1]);
   o.z = *reinterpret_cast<uint32_t*>(&h[2]); o.w = *reinterpret_cast<uint32_t*>(&h[3]);
-  *reinterpret_cast<uint4*>(y + (((long long)n * H + oy) * W + ox) * ldy + c8 * 8) = o;
+  *reinterpret_cast<uint4*>(dx + (((long long)n * H + y) * W + x) * lddx + c8 * 8) = o;
 }
 
 // du = dfmap * (fmap > 0) as bf16 (ReLU backward of the Mixed_4e output).
@@ -348,12 +389,12 @@ struct BbWalk {
   }
   // Sibling 1x1 convolutions on the same input as one GEMM: conv `first` and the ones whose folded weights
   // follow it; output columns routed to `segs` (all bf16).
-  void conv1x1_group(int first, int l, const bf16* x, int ldx, const OutSeg* segs, int nseg) {
+  void conv1x1_group(int first, int l, const bf16* x, int ldx, const OutSeg* segs, int nseg, int act_cols = -1) {
     if (!run || rc != C2D_OK) return;
     int cout = 0;
     for (int s = 0; s < nseg; ++s) cout += segs[s].cols;
     ImgConv ic = {B, 1, 1, d.h[l], d.w[l], d.h[l], d.w[l], kBbConvs[first].cin, cout, x, ldx};
-    rc = conv_img_fwd_tc(ic, w16 + L.c[first].w16, shift + L.c[first].ch, 1, segs, nseg, 0, st);
+    rc = conv_img_fwd_tc(ic, w16 + L.c[first].w16, shift + L.c[first].ch, 1, segs, nseg, 0, st, act_cols);
   }
   void maxpool_s2(int lin, const bf16* x, int C, int ldx, bf16* y, int ldy) {
     if (!run || rc != C2D_OK) return;
@@ -363,13 +404,9 @@ struct BbWalk {
                                                       pad_before(W, Wo, 3, 2), y, ldy);
     count_launch();
   }
-  void avgpool(int l, const bf16* x, int C, int ldx, bf16* y) {
-    if (!run || rc != C2D_OK) return;
-    const long long n = (long long)B * d.h[l] * d.w[l] * (C / 8);
-    bb_avgpool_s1_kernel<<<cdiv(n, 256), 256, 0, st>>>(x, B, d.h[l], d.w[l], C, ldx, y, C);
-    count_launch();
-  }
   // Mixed block with four branches at one resolution; out = bf16 [.., ctot] or (final block) the fp32 fmap.
+  // Branch_3 (AvgPool -> 1x1) runs as 1x1 -> AvgPool: its convolution joins the sibling GEMM on the block input
+  // (raw accumulators z3, `act_cols`), a small kernel pools + shifts + ReLUs the d-channel result.
   void* mixed(int l, int i0, const bf16* x, void* out_f32_or_null, Bb4eBufs* keep) {
     const int cin = kBbConvs[i0].cin;
     const int a = kBbConvs[i0].cout, b = kBbConvs[i0 + 2].cout, c = kBbConvs[i0 + 5].cout, dd = kBbConvs[i0 + 6].cout;
@@ -379,25 +416,34 @@ struct BbWalk {
     bf16* t1 = act(l, kBbConvs[i0 + 1].cout);
     bf16* t2 = act(l, kBbConvs[i0 + 3].cout);
     bf16* t3 = act(l, kBbConvs[i0 + 4].cout);
-    bf16* t4 = act(l, cin);
-    if (keep) { keep->x = const_cast<bf16*>(x); keep->t1 = t1; keep->t2 = t2; keep->t3 = t3; keep->t4 = t4; }
+    bf16* z3 = act(l, dd);
+    if (keep) { keep->x = const_cast<bf16*>(x); keep->t1 = t1; keep->t2 = t2; keep->t3 = t3; keep->t4 = z3; }
     auto col = [&](int off_cols) -> void* {
       return f32 ? (void*)((float*)y + off_cols) : (void*)((bf16*)y + off_cols);
     };
     const int c1 = kBbConvs[i0 + 1].cout, c2 = kBbConvs[i0 + 3].cout;
-    if (f32) {                      // Branch_0 writes fp32: only the two reducers share a GEMM
+    if (f32) {                      // Branch_0 writes fp32: the two reducers and Branch_3's 1x1 share a GEMM
       conv(i0, l, x, cin, col(0), ctot, 1);
-      OutSeg segs[2] = {{t1, c1, c1}, {t2, c2, c2}};
-      conv1x1_group(i0 + 1, l, x, cin, segs, 2);
+      OutSeg segs[3] = {{t1, c1, c1}, {t2, c2, c2}, {z3, dd, dd}};
+      conv1x1_group(i0 + 1, l, x, cin, segs, 3, c1 + c2);
     } else {
-      OutSeg segs[3] = {{y, ctot, a}, {t1, c1, c1}, {t2, c2, c2}};
-      conv1x1_group(i0, l, x, cin, segs, 3);
+      OutSeg segs[4] = {{y, ctot, a}, {t1, c1, c1}, {t2, c2, c2}, {z3, dd, dd}};
+      conv1x1_group(i0, l, x, cin, segs, 4, a + c1 + c2);
     }
     conv(i0 + 2, l, t1, kBbConvs[i0 + 1].cout, col(a), ctot, f32);
     conv(i0 + 4, l, t2, kBbConvs[i0 + 3].cout, t3, kBbConvs[i0 + 4].cout, 0);
     conv(i0 + 5, l, t3, kBbConvs[i0 + 4].cout, col(a + b), ctot, f32);
-    avgpool(l, x, cin, cin, t4);
-    conv(i0 + 6, l, t4, cin, col(a + b + c), ctot, f32);
+    if (run && rc == C2D_OK) {
+      const long long nthr = (long long)B * d.h[l] * d.w[l] * (dd / 8);
+      const float* sh = shift + L.c[i0 + 6].ch;
+      if (f32)
+        bb_avgpool_shift_relu_kernel<float><<<cdiv(nthr, 256), 256, 0, st>>>(z3, B, d.h[l], d.w[l], dd, sh,
+                                                                           (float*)col(a + b + c), ctot);
+      else
+        bb_avgpool_shift_relu_kernel<bf16><<<cdiv(nthr, 256), 256, 0, st>>>(z3, B, d.h[l], d.w[l], dd, sh,
+                                                                          (bf16*)col(a + b + c), ctot);
+      count_launch();
+    }
     return y;
   }
 };
@@ -419,7 +465,7 @@ static int bb_upload_fold_table() {
 }
 
 // Buffers of the backward pass, placed after everything the forward walk takes.
-struct BbBwdBufs { bf16 *du, *dt1, *dt2, *dt3; float *dws, *dshift; };
+struct BbBwdBufs { bf16 *du, *dt1, *dt2, *dt3, *dq; float *dws, *dshift; };
 static BbBwdBufs bb_bwd_bufs(BbWalk& w) {
   const BbLayout& L = w.L;
   BbBwdBufs b;
@@ -427,6 +473,7 @@ static BbBwdBufs bb_bwd_bufs(BbWalk& w) {
   b.dt1 = w.act(4, kBbConvs[kBb4e + 1].cout);
   b.dt2 = w.act(4, kBbConvs[kBb4e + 3].cout);
   b.dt3 = w.act(4, kBbConvs[kBb4e + 4].cout);
+  b.dq = w.act(4, kBbConvs[kBb4e + 6].cout);
   b.dws = (float*)w.take((size_t)(L.w_elems - L.c[kBb4e].w16) * 4);
   b.dshift = (float*)w.take((size_t)(L.ch_total - L.c[kBb4e].ch) * 4);
   return b;
@@ -597,8 +644,13 @@ int c2d_backbone_bwd(const float* dfmap, const float* fmap, int B, int H, int W,
   C2D_TRY(conv_img_wgrad_tc(ic(i0 + 4, k.t2, c2), b.dt3, c3, dw(i0 + 4), ds(i0 + 4), st));
   C2D_TRY(conv_img_dgrad_tc(ic(i0 + 4, nullptr, c2), b.dt3, c3, w.wt16 + L.c[i0 + 4].wt16, b.dt2, c2, k.t2, st));
   C2D_TRY(conv_img_wgrad_tc(ic(i0 + 3, k.x, 576), b.dt2, c2, dw(i0 + 3), ds(i0 + 3), st));
-  // Branch_3: 1x1 on the average-pooled input
-  C2D_TRY(conv_img_wgrad_tc(ic(i0 + 6, k.t4, 576), b.du + ca + cb + cc, 576, dw(i0 + 6), ds(i0 + 6), st));
+  // Branch_3 (evaluated as 1x1 -> AvgPool): pool the 96-channel gradient, then a 1x1 weight gradient against x
+  {
+    const int c4 = kBbConvs[i0 + 6].cout;
+    bb_avgpool_bwd_kernel<<<cdiv(M * (c4 / 8), 256), 256, 0, st>>>(b.du + ca + cb + cc, 576, B, Hf, Wf, c4, b.dq, c4);
+    count_launch();
+    C2D_TRY(conv_img_wgrad_tc(ic(i0 + 6, k.x, 576), b.dq, c4, dw(i0 + 6), ds(i0 + 6), st));
+  }
 #undef C2D_TRY
   bb_unfold_kernel<<<dim3(cdiv(192, 8), 7), 256, 0, st>>>(params, kBb4e, b.dws, dws_base, b.dshift, ch_base, dparams);
   count_launch();

@@ -22,8 +22,9 @@ struct ImgConv {
 };
 
 // y = act(conv(x, w16) + shift), output columns split over `segs` (sum cols = cout).  w16 [cout][k*k][cin].
+// act_cols >= 0: shift / ReLU only for output columns < act_cols, the rest are raw accumulators (1x1 only).
 int conv_img_fwd_tc(const ImgConv& c, const bf16_t* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
-                    int out_f32, cudaStream_t st);
+                    int out_f32, cudaStream_t st, int act_cols = -1);
 // dx = conv_transpose(du, w) for k == 3, stride 1; wt16 [cin][9][cout]; optional fused ReLU mask (dx *= mask > 0).
 int conv_img_dgrad_tc(const ImgConv& c, const bf16_t* du, int lddu, const bf16_t* wt16, bf16_t* dx, int lddx,
                       const bf16_t* mask, cudaStream_t st);

@@ -527,11 +527,12 @@ static ConvDesc flat_desc(const ImgConv& c, long long rows) {
 }
 
 int conv_img_fwd_tc(const ImgConv& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
-                    int out_f32, cudaStream_t st) {
+                    int out_f32, cudaStream_t st, int act_cols) {
   if (c.k == 1) {
     C2D_CHECK_ARG(c.stride == 1, "conv_img_fwd: 1x1 convolutions are stride 1");
-    return conv_fwd_tc(flat_desc(c, (long long)c.n * c.hin * c.win), w16, shift, relu, segs, nseg, out_f32, st);
+    return conv_fwd_tc(flat_desc(c, (long long)c.n * c.hin * c.win), w16, shift, relu, segs, nseg, out_f32, st, act_cols);
   }
+  C2D_CHECK_ARG(act_cols < 0, "conv_img_fwd: raw output columns are a 1x1 feature");
   C2D_CHECK_ARG(c.k == 3 && (c.stride == 1 || c.stride == 2), "conv_img_fwd: k must be 1 or 3, stride 1 or 2");
   tc::ConvGemmParams p;
   memset(&p, 0, sizeof(p));

@@ -102,8 +102,17 @@ def mixed_block(x, p, blk, emulate_bf16=False, last=False, collect=None):
   t2 = st(c(x, blk + '/Branch_2/Conv2d_0a_1x1'))
   t3 = st(c(t2, blk + '/Branch_2/Conv2d_0b_3x3'))
   b2 = fin(c(t3, blk + '/Branch_2/Conv2d_0c_3x3'))
-  t4 = st(TF_.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False))
-  b3 = fin(c(t4, blk + '/Branch_3/Conv2d_0b_1x1'))
+  if emulate_bf16:
+    # The CUDA path evaluates AvgPool -> 1x1 conv as 1x1 conv -> AvgPool (one acts on positions, the other on
+    # channels: they commute) and stores the narrow intermediate in bf16; mirror its rounding points.
+    q = p[blk + '/Branch_3/Conv2d_0b_1x1']
+    scale, shift = _bn(q)
+    wf = _RoundBF16.apply(_t(q['weights']).permute(0, 3, 1, 2) * scale.view(-1, 1, 1, 1))
+    t4 = st(TF_.conv2d(x, wf, None))
+    b3 = fin(torch.relu(TF_.avg_pool2d(t4, 3, stride=1, padding=1, count_include_pad=False) + shift.view(1, -1, 1, 1)))
+  else:
+    t4 = TF_.avg_pool2d(x, 3, stride=1, padding=1, count_include_pad=False)
+    b3 = c(t4, blk + '/Branch_3/Conv2d_0b_1x1')
   if collect is not None and last:
     collect.update({'x': x, 't1': t1, 't2': t2, 't3': t3, 't4': t4})
   return torch.cat([b0, b1, b2, b3], dim=1)
