@@ -499,6 +499,41 @@ pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict_
     st4(dx + ((size_t)n * 16 + i) * lddx + c, make_float4(g[i][0], g[i][1], g[i][2], g[i][3]));
 }
 
+// Mixed_5a/Branch_2 MaxPool_1a_3x3 (7x7 -> 4x4, stride 2, SAME) on bf16 planes with FOUR channels per thread.
+// max is exact in bf16, so the plane stays packed (49 x 8 bytes = 98 registers) and the windows use __hmax2.
+static __global__ void __launch_bounds__(128)
+maxpool3x3_s2_7x7_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
+                              int n_rois, int C) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  uint2 v[49];
+#pragma unroll
+  for (int i = 0; i < 49; ++i) v[i] = *reinterpret_cast<const uint2*>(x + ((size_t)n * 49 + i) * ldx + c);
+#pragma unroll
+  for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      __nv_bfloat162 m0, m1;
+      bool first = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+          if (iy >= 0 && iy < 7 && ix >= 0 && ix < 7) {
+            const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v[iy * 7 + ix].x);
+            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&v[iy * 7 + ix].y);
+            if (first) { m0 = a; m1 = b2; first = false; }
+            else { m0 = __hmax2(m0, a); m1 = __hmax2(m1, b2); }
+          }
+        }
+      uint2 o;
+      o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
+      *reinterpret_cast<uint2*>(y + ((size_t)n * 16 + oy * 4 + ox) * ldy + c) = o;
+    }
+}
+
 // y = relu(avgpool3x3_same(z) + shift) on 4x4 planes: the tail of Mixed_5b/Branch_3 when the 1x1 convolution
 // runs BEFORE the pooling (see kHead5bPoolConv).  z holds raw accumulators (no shift, no ReLU).
 template <typename T>

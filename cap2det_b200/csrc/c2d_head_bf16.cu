@@ -908,7 +908,7 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
     if (i == 5) {
-      pool3x3_fwd_kernel<bf16, 7, 2, 0><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
+      maxpool3x3_s2_7x7_bf16_kernel<<<dim3(cdiv(576 / 4, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
       count_launch();
     }
     if (i == 18) {
