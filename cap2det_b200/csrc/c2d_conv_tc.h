@@ -11,6 +11,28 @@ typedef __nv_bfloat16 bf16_t;
 struct OutSeg { void* out; int ld; int cols; };            // destination of a column range
 struct InSeg { const bf16_t* du; int ld; int cols; };      // one source of a merged 1x1 data gradient
 
+// One convolution on per-ROI planes (the head): x [n, hin, hin, cin] -> y [n, hout, hout, cout], all bf16 NHWC
+// with leading dimensions; hin/hout = 7/7, 7/4 (stride 2) or 4/4; k in {1, 3}.
+struct ConvDesc {
+  int n;              // ROIs
+  int k, stride;      // 1 or 3 ; 1 or 2
+  int hin, hout;
+  int cin, cout;
+  const bf16_t* x; int ldx;        // input activation  [n, hin, hin, cin]
+  bf16_t* y; int ldy;              // output activation [n, hout, hout, cout]   (forward)
+};
+
+// Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift), output columns split over `segs` (<= 4);
+//   w16 [sum cols][k*k][cin]; act_cols >= 0: shift / ReLU only for columns < act_cols (1x1 only).
+int conv_fwd_tc(const ConvDesc& c, const bf16_t* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
+                int out_f32, cudaStream_t st, int act_cols = -1);
+// Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).  k == 1: up to 4 sources (a merged sibling group),
+//   wt16 [cin][sum cols]; k == 3: one source, wt16 [cin][9][cols].  mask: fused ReLU backward for columns < mask_cols.
+int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16_t* wt16, void* dx, int lddx, int accum,
+                  int out_f32, cudaStream_t st, const bf16_t* mask = nullptr, int mask_cols = 0);
+// Weight gradient: dw [cout][k*k][cin] (fp32, pre-zeroed) += du^T x ; dshift [cout] (optional) += column sums of du.
+int conv_wgrad_tc(const ConvDesc& c, const bf16_t* du, int lddu, float* dw, cudaStream_t st, float* dshift = nullptr);
+
 // One convolution over whole feature maps: x [n, hin, win, cin] -> y [n, hout, wout, cout], NHWC bf16 with
 // leading dimensions (elements per pixel).  k in {1, 3}; stride in {1, 2} (2: k == 3, forward only);
 // TF SAME padding: hout = ceil(hin / stride), pad_before = max((hout-1)*stride + k - hin, 0) / 2.
