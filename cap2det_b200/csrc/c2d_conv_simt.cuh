@@ -571,17 +571,25 @@ __global__ void avgpool_shift_relu_4x4_kernel(const T* __restrict__ z, int ldz, 
 }
 
 // feat[n, c] = mean_{hw} x[n, hw, c] (* keep_mask[n,c] / keep_prob).  models/utils.py:169-174.
+// Four channels per thread (8-byte bf16 / 16-byte fp32 accesses); C must be a multiple of 4.
 template <typename T>
 __global__ void avgpool_dropout_fwd_kernel(const T* __restrict__ x, int hw, int C, const float* __restrict__ keep_mask,
                                            float keep_prob, float* __restrict__ feat, int n_rois) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int n = blockIdx.y;
   if (c >= C || n >= n_rois) return;
-  float s = 0.f;
-  for (int i = 0; i < hw; ++i) s += Elem<T>::ld(x + ((size_t)n * hw + i) * C + c);
-  s = s / (float)hw;
-  if (keep_mask) s = s / keep_prob * keep_mask[(size_t)n * C + c];
-  feat[(size_t)n * C + c] = s;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = 0; i < hw; ++i) {
+    const float4 v = ld4(x + ((size_t)n * hw + i) * C + c);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const float h = (float)hw;
+  s.x = s.x / h; s.y = s.y / h; s.z = s.z / h; s.w = s.w / h;
+  if (keep_mask) {
+    const float4 k = *reinterpret_cast<const float4*>(keep_mask + (size_t)n * C + c);
+    s.x = s.x / keep_prob * k.x; s.y = s.y / keep_prob * k.y; s.z = s.z / keep_prob * k.z; s.w = s.w / keep_prob * k.w;
+  }
+  *reinterpret_cast<float4*>(feat + (size_t)n * C + c) = s;
 }
 // dx[n, hw, c] = dfeat[n, c] * keep_mask / keep_prob / hw  (broadcast over hw)
 // With `y` (the forward activation) the ReLU backward mask is fused: dx = (y > 0) ? g : 0.
@@ -589,17 +597,27 @@ template <typename T>
 __global__ void avgpool_dropout_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ keep_mask,
                                            float keep_prob, int hw, int C, T* __restrict__ dx, int n_rois,
                                            const T* __restrict__ y = nullptr) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int n = blockIdx.y;
   if (c >= C || n >= n_rois) return;
-  float g = dfeat[(size_t)n * C + c];
-  if (keep_mask) g = g / keep_prob * keep_mask[(size_t)n * C + c];
-  g = g / (float)hw;
+  float4 g = *reinterpret_cast<const float4*>(dfeat + (size_t)n * C + c);
+  if (keep_mask) {
+    const float4 k = *reinterpret_cast<const float4*>(keep_mask + (size_t)n * C + c);
+    g.x = g.x / keep_prob * k.x; g.y = g.y / keep_prob * k.y; g.z = g.z / keep_prob * k.z; g.w = g.w / keep_prob * k.w;
+  }
+  const float h = (float)hw;
+  g.x = g.x / h; g.y = g.y / h; g.z = g.z / h; g.w = g.w / h;
   for (int i = 0; i < hw; ++i) {
     const size_t idx = ((size_t)n * hw + i) * C + c;
-    float v = g;
-    if (y != nullptr && !(Elem<T>::ld(y + idx) > 0.f)) v = 0.f;
-    Elem<T>::st(dx + idx, v);
+    float4 v = g;
+    if (y != nullptr) {
+      const float4 a = ld4(y + idx);
+      if (!(a.x > 0.f)) v.x = 0.f;
+      if (!(a.y > 0.f)) v.y = 0.f;
+      if (!(a.z > 0.f)) v.z = 0.f;
+      if (!(a.w > 0.f)) v.w = 0.f;
+    }
+    st4(dx + idx, v);
   }
 }
 

@@ -90,7 +90,7 @@ static int head_fwd_f32(const float* x0, int n, const float* params, const HeadP
     launch_igemm<true, false>(act[c.src] + c.src_off, kHeadBufs[c.src].ch, c.cin, geom_fwd(c), wsf + o.w_only,
                               shf + o.ch, act[c.dst] + c.dst_off, kHeadBufs[c.dst].ch, M, c.cout, st);
   }
-  avgpool_dropout_fwd_kernel<float><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob,
+  avgpool_dropout_fwd_kernel<float><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob,
                                                                              feat, n);
   count_launch();
   C2D_LAUNCH_OK();
@@ -114,7 +114,7 @@ static int head_bwd_f32(const float* x0, int n, const float* params, const HeadP
   C2D_CUDA_OK(cudaMemsetAsync(dwsf, 0, pl.w_only_total * sizeof(float), st));
   C2D_CUDA_OK(cudaMemsetAsync(dshf, 0, pl.ch_total * sizeof(float), st));
   bool written[NBUF] = {false};
-  avgpool_dropout_bwd_kernel<float><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024,
+  avgpool_dropout_bwd_kernel<float><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024,
                                                                              grad[X3], n);
   count_launch();
   written[X3] = true;

@@ -173,7 +173,7 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       count_launch();
     }
   }
-  avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
+  avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -198,7 +198,7 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
   bool written[NBUF] = {false};
   // every gradient buffer is written as du = dy * (y > 0) by its LAST writer (fused ReLU backward);
   // the BN-shift gradients come out of the weight-gradient kernel (ones-vector MMA).
-  avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n,
+  avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n,
                                                                               act[X3]);
   count_launch();
   written[X3] = true;
