@@ -811,3 +811,50 @@ def test_text_classifier_match_extractor():
       % (synthetic.write_label_file(d, classes), vpath, epath), config.LabelExtractor)
   with pytest.raises(ValueError):
     label_extractor.build_label_extractor(bad).extract_labels({f: caps})
+
+
+# ---------------------------------------------------------------------------------------------
+def test_edge_cases_empty_and_degenerate_inputs():
+  """Empty batches / zero proposals pass through every op without a launch error; an image without positive
+  labels gets all-background pseudo labels; NMS with nothing above the score threshold returns zero detections;
+  all-padding proposal rows (zero boxes) never survive NMS."""
+  from cap2det_b200 import ops, synthetic
+  rng = np.random.default_rng(61)
+  fmap = dev(synthetic.make_feature_map(rng, 1, 128, 160))
+  # P = 0 and B = 0
+  x0 = ops.roi_crop_maxpool(fmap, torch.zeros((1, 0, 4), device='cuda'))
+  assert tuple(x0.shape) == (0, 7, 7, 576)
+  x0b = ops.roi_crop_maxpool(torch.zeros((0, 8, 10, 576), device='cuda'), torch.zeros((0, 5, 4), device='cuda'),
+                             out_dtype=torch.bfloat16)
+  assert tuple(x0b.shape) == (0, 7, 7, 576)
+  hp = torch.zeros((ops.head_param_floats(),), device='cuda')
+  for dt in (torch.float32, torch.bfloat16):
+    feat = ops.head_mixed5(torch.zeros((0, 7, 7, 576), dtype=dt, device='cuda'), hp)
+    assert tuple(feat.shape) == (0, 1024)
+  y = ops.fc_concat(torch.zeros((0, 1024), device='cuda'), torch.zeros((43, 1024), device='cuda'),
+                    torch.zeros((43,), device='cuda'))
+  assert y.shape[0] == 0
+  torch.cuda.synchronize()
+  # no positive label: every valid proposal is background with weight 1 (models/utils.py:61-90)
+  B, P, C = 2, 33, 7
+  props = synthetic.make_proposals(rng, B, P)
+  npr = np.array([P, P - 5], np.int32)
+  s0 = rng.uniform(0, 1, (B, P, C)).astype(np.float32)
+  labels = np.zeros((B, C), np.float32)
+  labels[1, 3] = 1
+  ind_o, pl_o, ok = midn_oicr.oicr_assign(labels, npr, props, np.concatenate([np.zeros((B, P, 1), np.float32), s0], -1), 0.6)
+  ind, pl, status = ops.oicr_assign(dev(labels), dev(npr), dev(props), dev(s0), 0.6)
+  np.testing.assert_array_equal(ind.cpu().numpy(), ind_o)
+  np.testing.assert_array_equal(pl.cpu().numpy(), pl_o)
+  assert np.all(pl_o[0, :, 0] == 1) and np.all(pl_o[0, :, 1:] == 0) and ok and int(status.item()) == 0
+  # NMS: nothing above the threshold in image 0; only zero-area boxes in image 1
+  scores = rng.uniform(0.5, 1, (B, P, C)).astype(np.float32)
+  scores[0] = 1e-6
+  props2 = props.copy(); props2[1] = 0
+  n_o, b_o, s_o, c_o, k_o = onms.multiclass_nms(props2, scores, 1e-5, 0.4, 100, 300)
+  n, b, s, c, k = ops.multiclass_nms(dev(props2), dev(scores), 1e-5, 0.4, 100, 300)
+  assert n_o.tolist() == [0, 0]
+  np.testing.assert_array_equal(n.cpu().numpy(), n_o)
+  np.testing.assert_array_equal(b.cpu().numpy(), b_o)
+  np.testing.assert_array_equal(s.cpu().numpy(), s_o)
+  np.testing.assert_array_equal(c.cpu().numpy(), c_o)
