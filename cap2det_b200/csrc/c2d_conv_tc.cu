@@ -116,7 +116,6 @@ static int tc_prepare() {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
-    C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWg2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
     g_attr_done = true;
   }
@@ -396,11 +395,11 @@ int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16* wt
 }
 
 // Splits the reduction rows into one wave of work items and launches the weight-gradient kernel.
+// (A 2-CTA variant of this kernel was measured 6 % slower on this layer mix and removed)
 static int launch_wgrad(tc::WgradParams& p, const CUtensorMap& mapY, const CUtensorMap mapX[4], cudaStream_t st,
-                        double flops, bool two) {
+                        double flops) {
   const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  const int workers = two ? num_sms() / 2 : num_sms();
-  int splits = workers / base_items;         // one wave of items; every extra split is a dW-sized atomic pass
+  int splits = num_sms() / base_items;       // one wave of items; every extra split is a dW-sized atomic pass
   if (splits < 1) splits = 1;
   if (splits > p.total_steps) splits = p.total_steps;
   if (p.total_steps <= 0) return C2D_OK;
@@ -409,36 +408,36 @@ static int launch_wgrad(tc::WgradParams& p, const CUtensorMap& mapY, const CUten
   const int items = base_items * p.num_splits;
   if (items <= 0) return C2D_OK;
   ProfScope prof(st, 1, flops);
-  if (two) {
-    const int pairs = items < workers ? items : workers;
-    tc::wgrad_tc2_kernel<<<2 * pairs, tc::kWgThreads, tc::kWg2SmemBytes, st>>>(mapY, mapX[0], mapX[1], mapX[2], mapX[3], p);
-  } else {
-    const int grid = items < num_sms() ? items : num_sms();
-    C2D_CUDA_OK(launch_pdl(tc::wgrad_tc_kernel, grid, tc::kWgThreads, tc::kWgSmemBytes, st, mapY, mapX[0], mapX[1], mapX[2],
-                           mapX[3], p));
-  }
+  const int grid = items < num_sms() ? items : num_sms();
+  C2D_CUDA_OK(launch_pdl(tc::wgrad_tc_kernel, grid, tc::kWgThreads, tc::kWgSmemBytes, st, mapY, mapX[0], mapX[1], mapX[2],
+                         mapX[3], p));
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
 }
 
+// One member (the usual case): groups of 64 output channels in order, all from mapY.
+static void set_single_member(tc::WgradParams& p, int cout, float* dw, float* dshift) {
+  p.ngroups = (cout + 63) / 64;
+  for (int g = 0; g < p.ngroups; ++g) { p.g_map[g] = 0; p.g_member[g] = 0; p.g_co[g] = (short)(g * 64); }
+  p.m_cout[0] = cout; p.m_dw[0] = dw; p.m_dshift[0] = dshift;
+  p.any_dshift = dshift != nullptr;
+  p.cout = p.ngroups * 64;
+  p.co_tiles = (p.ngroups + 3) / 4;
+}
+
 // Weight gradient: dw[cout][k*k][cin] (fp32, pre-zeroed by the caller) += du^T * x.
 int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaStream_t st, float* dshift) {
+  C2D_CHECK_ARG(c.cout <= 1024, "conv_wgrad: at most 1024 output channels per launch");
   int rc = tc_prepare();
   if (rc != C2D_OK) return rc;
   tc::WgradParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap mapY, mapX[4];
   p.taps = c.k * c.k; p.taps_total = p.taps;
-  p.cout = c.cout; p.cin = c.cin; p.dw = dw; p.dshift = dshift;
-  // The 2-CTA weight gradient (wgrad_tc2_kernel) is correct but measured 6 % SLOWER than the single-CTA
-  // kernel on this layer mix (its fixed M = 256 wastes MMA work on cout = 320 / 352 / 160 / 192, and wgrad is
-  // not shared-memory bound); opt in with C2D_WGRAD_2CTA=1.
-  static int wg2 = -1;
-  if (wg2 < 0) { const char* e = getenv("C2D_WGRAD_2CTA"); wg2 = (e && e[0] == '1') ? 1 : 0; }
-  const bool two = wg2 == 1 && use_2cta(true, 1);
-  p.co_tiles = (c.cout + 255) / 256;
-  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, two ? 32 : 16);
+  p.cin = c.cin;
+  set_single_member(p, c.cout, dw, dshift);
+  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, 16);
   p.ci_groups = (p.ci_tile + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;
@@ -473,7 +472,43 @@ int conv_wgrad_tc(const ConvDesc& c, const bf16* du, int lddu, float* dw, cudaSt
       }
     }
   }
-  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout, two);
+  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.hout * (double)p.taps * c.cin * c.cout);
+}
+
+// Weight gradients of up to four sibling 1x1 convolutions that read the same input x (c.x, c.cin; c.cout unused)
+// in ONE launch: member m has gradient srcs[m] (du pointer, leading dim, cout) and outputs dw[m], dshift[m].
+int conv_wgrad_group_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, float* const dw[], float* const dshift[],
+                        cudaStream_t st) {
+  C2D_CHECK_ARG(c.k == 1 && nsrc >= 1 && nsrc <= 4, "conv_wgrad_group: 1x1 convolutions, 1..4 members");
+  int rc = tc_prepare();
+  if (rc != C2D_OK) return rc;
+  tc::WgradParams p;
+  memset(&p, 0, sizeof(p));
+  CUtensorMap mapY[4], mapX[4];
+  p.taps = 1; p.taps_total = 1; p.cin = c.cin;
+  const long long M = (long long)c.n * c.hin * c.hin;
+  p.flat = 1; p.total_steps = (int)((M + 63) / 64);
+  double cout_sum = 0;
+  for (int m = 0; m < nsrc; ++m) {
+    if (!make_map_flat(&mapY[m], srcs[m].du, srcs[m].cols, M, srcs[m].ld, 64)) return C2D_ERR_CUDA;
+    p.m_cout[m] = srcs[m].cols; p.m_dw[m] = dw[m]; p.m_dshift[m] = dshift ? dshift[m] : nullptr;
+    if (p.m_dshift[m] != nullptr) p.any_dshift = 1;
+    for (int g = 0; g * 64 < srcs[m].cols; ++g) {
+      C2D_CHECK_ARG(p.ngroups < 16, "conv_wgrad_group: more than 16 groups of 64 output channels");
+      p.g_map[p.ngroups] = (unsigned char)m; p.g_member[p.ngroups] = (unsigned char)m; p.g_co[p.ngroups] = (short)(g * 64);
+      ++p.ngroups;
+    }
+    cout_sum += srcs[m].cols;
+  }
+  for (int m = nsrc; m < 4; ++m) mapY[m] = mapY[0];
+  p.cout = p.ngroups * 64;
+  p.co_tiles = (p.ngroups + 3) / 4;
+  p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, 16);
+  p.ci_groups = (p.ci_tile + 63) / 64;
+  if (!make_map_flat(&mapX[0], c.x, c.cin, M, c.ldx, 64)) return C2D_ERR_CUDA;
+  mapX[1] = mapY[1]; mapX[2] = mapY[2]; mapX[3] = mapY[3];     // a flat problem reads X through mapX0 only
+  p.tap_b[0] = 0; p.tap_map[0] = 0;
+  return launch_wgrad(p, mapY[0], mapX, st, 2.0 * M * (double)c.cin * cout_sum);
 }
 
 // ---- whole-feature-map convolutions (backbone): image-patch tiles, same kernels ----------------------------
@@ -590,8 +625,8 @@ int conv_img_wgrad_tc(const ImgConv& c, const bf16* du, int lddu, float* dw, flo
   memset(&p, 0, sizeof(p));
   CUtensorMap mapY, mapX[4];
   p.taps = 9; p.taps_total = 9;
-  p.cout = c.cout; p.cin = c.cin; p.dw = dw; p.dshift = dshift;
-  p.co_tiles = (c.cout + 255) / 256;
+  p.cin = c.cin;
+  set_single_member(p, c.cout, dw, dshift);
   p.ci_tiles = pick_tiles(c.cin, 240, &p.ci_tile, 16);
   p.ci_groups = (p.ci_tile + 63) / 64;
   p.flat = 2;
@@ -601,7 +636,7 @@ int conv_img_wgrad_tc(const ImgConv& c, const bf16* du, int lddu, float* dw, flo
   if (!make_map_img(&mapX[0], c.x, c.cin, c.hin, c.win, c.n, c.ldx, 8, 8)) return C2D_ERR_CUDA;
   mapX[1] = mapX[2] = mapX[3] = mapX[0];
   for (int t = 0; t < 9; ++t) { p.tap_y[t] = t / 3 - 1; p.tap_x[t] = t % 3 - 1; p.tap_b[t] = t; p.tap_map[t] = 0; }
-  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.wout * 9.0 * c.cin * c.cout, false);
+  return launch_wgrad(p, mapY, mapX, st, 2.0 * c.n * c.hout * c.wout * 9.0 * c.cin * c.cout);
 }
 
 // ---- small helpers ----------------------------------------------------------------------------

@@ -33,6 +33,11 @@ int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16_t* 
 // Weight gradient: dw [cout][k*k][cin] (fp32, pre-zeroed) += du^T x ; dshift [cout] (optional) += column sums of du.
 int conv_wgrad_tc(const ConvDesc& c, const bf16_t* du, int lddu, float* dw, cudaStream_t st, float* dshift = nullptr);
 
+// Weight gradients of up to four sibling 1x1 convolutions on the same input x (c.x, c.ldx, c.cin, c.n, c.hin) in one
+// launch: member m has gradient srcs[m] (pointer, leading dim, cout) and outputs dw[m] / dshift[m] (may be null).
+int conv_wgrad_group_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, float* const dw[], float* const dshift[],
+                        cudaStream_t st);
+
 // One convolution over whole feature maps: x [n, hin, win, cin] -> y [n, hout, wout, cout], NHWC bf16 with
 // leading dimensions (elements per pixel).  k in {1, 3}; stride in {1, 2} (2: k == 3, forward only);
 // TF SAME padding: hout = ceil(hin / stride), pad_before = max((hout-1)*stride + k - hin, 0) / 2.

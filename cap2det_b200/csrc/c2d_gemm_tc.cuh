@@ -605,10 +605,20 @@ struct WgradParams {
   int total_steps;            // k-steps over the whole tensor
   int steps_per_split, num_splits;
   int co_tiles, ci_tiles, ci_tile, ci_groups;   // co tile = 256; ci_tile = UMMA N (<= 240)
-  int cout, cin;              // valid extents
+  int cout, cin;              // valid extents (cout = A rows incl. the padding of partial 64-channel groups)
   int taps_total;             // taps in the dW layout [co][taps_total][cin]
-  float* dw;
-  float* dshift;              // [cout] or null
+  // The A operand (dY^T) is addressed in groups of 64 output channels.  Group g comes from tensor map g_map[g]
+  // (0 = mapY, 1..3 = mapX1..mapX3, which a flat 1x1 problem does not need for X) at channel offset g_co[g] and
+  // belongs to member g_member[g]: sibling 1x1 convolutions that read the same input run as ONE weight-gradient
+  // launch (the input, e.g. 131 MB of X1, is then read once instead of once per member).  A member's last
+  // group may be partial: its extra rows hold whatever the map returns and are never written.
+  int ngroups;
+  int any_dshift;             // some member wants the BN-shift gradient (the ones-block MMA)
+  unsigned char g_map[16], g_member[16];
+  short g_co[16];
+  int m_cout[4];
+  float* m_dw[4];
+  float* m_dshift[4];         // [cout] or null
 };
 
 struct WgPipe {
@@ -656,12 +666,24 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
         const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
         const int cot = rem % p.co_tiles; rem /= p.co_tiles;
         const int t = rem;
-        const int a_groups = (p.cout - cot * 256) > 128 ? 4 : 2;
+        const int a_groups = (p.ngroups - cot * 4) > 2 ? 4 : 2;
         const uint32_t stage_tx = (uint32_t)(a_groups + p.ci_groups) * 8192u;
         const int tm = p.tap_map[t];
         const CUtensorMap* mX = tm == 0 ? &mapX0 : (tm == 1 ? &mapX1 : (tm == 2 ? &mapX2 : &mapX3));
         const int s0 = split * p.steps_per_split;
         const int s1 = min(p.total_steps, s0 + p.steps_per_split);
+        // A-operand groups of this item (hoisted out of the k loop: the producer is a single latency-bound thread);
+        // a group past the last one reads at a channel coordinate outside every map => TMA zero fill
+        const CUtensorMap* gmap[4];
+        int gco[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int gg = cot * 4 + g;
+          const bool in = gg < p.ngroups;
+          const int gm = in ? p.g_map[gg] : 0;
+          gmap[g] = gm == 0 ? &mapY : (gm == 1 ? &mapX1 : (gm == 2 ? &mapX2 : &mapX3));
+          gco[g] = in ? (int)p.g_co[gg] : 4096;   // past every map (cout <= 1024 per member)
+        }
         for (int s = s0; s < s1; ++s) {
           mbar_wait(&pipe->empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kWgStageBytes;
@@ -676,9 +698,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
             px0 = (rem - py0 * p.img_tiles_x) * 8;
             py0 *= 8;
           }
-          for (int g = 0; g < a_groups; ++g) {
-            if (p.flat == 1) tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, s * 64, 0, 0);
-            else tma_load_4d(sA + g * 8192, &mapY, &pipe->full[stage], cot * 256 + g * 64, px0, py0, pn);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g >= a_groups) break;
+            if (p.flat == 1) tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], s * 64, 0, 0);
+            else tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], px0, py0, pn);
           }
           for (int g = 0; g < p.ci_groups; ++g) {
             const int c0 = cit * p.ci_tile + g * 64;
@@ -700,8 +724,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
       const int cot = rem % p.co_tiles; rem /= p.co_tiles;
       const int t = rem;
-      const bool two = (p.cout - cot * 256) > 128;
-      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
+      const bool two = (p.ngroups - cot * 4) > 2;
+      const bool want_shift = p.any_dshift != 0 && t == 0 && cit == 0;
       const int s0 = split * p.steps_per_split;
       const int s1 = min(p.total_steps, s0 + p.steps_per_split);
       mbar_wait(&pipe->tmem_empty, tphase ^ 1);
@@ -743,12 +767,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
       const int cot = rem % p.co_tiles; rem /= p.co_tiles;
       const int t = rem;
-      const bool two = (p.cout - cot * 256) > 128;
-      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
+      const bool two = (p.ngroups - cot * 4) > 2;
+      const bool want_shift = p.any_dshift != 0 && t == 0 && cit == 0;
       mbar_wait(&pipe->tmem_full, tphase);
       tc_fence_after();
       for (int a = 0; a < (two ? 2 : 1); ++a) {
-        const int co = cot * 256 + a * 128 + q * 32 + lane;
+        const int r = a * 128 + q * 32 + lane;              // row of the 256-row co tile
+        const int gg = cot * 4 + (r >> 6);
+        const bool in_group = gg < p.ngroups;
+        const int mem = in_group ? p.g_member[gg] : 0;
+        const int co = in_group ? p.g_co[gg] + (r & 63) : 0;
+        const bool live = in_group && co < p.m_cout[mem];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * 256);
 #pragma unroll 1
         for (int j = 0; j < p.ci_tile; j += 16) {
@@ -756,8 +785,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
-          if (co < p.cout) {   // cin and ci_tile are multiples of 16 => the whole chunk is in range, 16 B aligned
-            float4* o = reinterpret_cast<float4*>(p.dw + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin +
+          if (live) {   // cin and ci_tile are multiples of 16 => the whole chunk is in range, 16 B aligned
+            float4* o = reinterpret_cast<float4*>(p.m_dw[mem] + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin +
                                                   cit * p.ci_tile + j);
 #pragma unroll
             for (int i = 0; i < 4; ++i)     // red.global.add.v4.f32: one L2 atomic per 16 bytes
@@ -769,7 +798,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           uint32_t v[16];
           tmem_ld_32x16(taddr + kWgOnesCol, v);
           tmem_ld_wait();
-          if (co < p.cout) atomicAdd(p.dshift + co, __uint_as_float(v[0]));
+          if (live && p.m_dshift[mem] != nullptr) atomicAdd(p.m_dshift[mem] + co, __uint_as_float(v[0]));
         }
       }
       tc_fence_before();
@@ -783,184 +812,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 2-CTA weight gradient: a CTA pair owns one (tap, 256 co, ci tile <= 240, row split) item.  Each CTA stages
-// ITS 128 output channels of dY (two [64 rows][64 co] boxes) and ITS half of the ci tile of X (ceil(N/2/64)
-// boxes); the leader issues tcgen05.mma.cta_group::2 with both operands MN-major.  Per SM this halves the
-// L2 -> shared-memory traffic of wgrad_tc_kernel for the same MMA work; the accumulator (128 lanes x N
-// columns per CTA, + 16 columns for the ones product) is double buffered so the red.add epilogue of one item
-// overlaps the main loop of the next.
-// ---------------------------------------------------------------------------------------------
-constexpr int kWg2Stages = 6;
-constexpr int kWg2StageBytes = 32768;             // A' 16 KB + B' <= 16 KB
-constexpr int kWg2SmemBytes = kWg2Stages * kWg2StageBytes + kWgOnesBytes + 1024 + 256;
-
-struct Wg2Pipe {
-  uint64_t full[kWg2Stages];
-  uint64_t empty[kWg2Stages];
-  uint64_t tmem_full[2];
-  uint64_t tmem_empty[2];
-  uint32_t tmem_base;
-};
-
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kWgThreads, 1)
-wgrad_tc2_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant__ CUtensorMap mapX0,
-                 const __grid_constant__ CUtensorMap mapX1, const __grid_constant__ CUtensorMap mapX2,
-                 const __grid_constant__ CUtensorMap mapX3, const WgradParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ones = smem + kWg2Stages * kWg2StageBytes;
-  Wg2Pipe* pipe = reinterpret_cast<Wg2Pipe*>(ones + kWgOnesBytes);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x)
-    reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;          // bf16 1.0 pairs
-  fence_proxy_async();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kWg2Stages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&pipe->tmem_full[s], 1); mbar_init(&pipe->tmem_empty[s], 8); }
-    fence_barrier_init();
-    prefetch_tmap(&mapY); prefetch_tmap(&mapX0);
-  }
-  if (warp == 1) tmem_alloc_2cta(&pipe->tmem_base, 512);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  tc_fence_after();
-  const uint32_t tmem_base = pipe->tmem_base;
-  const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.num_splits;
-  const int n_half = p.ci_tile >> 1;                 // ci columns staged by each CTA
-  const int b_groups = (n_half + 63) / 64;
-  const uint32_t pair_tx = 2u * (uint32_t)(2 + b_groups) * 8192u;
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int item = pair; item < num_items; item += num_pairs) {
-        int rem = item;
-        const int split = rem % p.num_splits; rem /= p.num_splits;
-        const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-        const int cot = rem % p.co_tiles; rem /= p.co_tiles;
-        const int t = rem;
-        const int tm = p.tap_map[t];
-        const CUtensorMap* mX = tm == 0 ? &mapX0 : (tm == 1 ? &mapX1 : (tm == 2 ? &mapX2 : &mapX3));
-        const int s0 = split * p.steps_per_split;
-        const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-        const int co0 = cot * 256 + (int)rank * 128;
-        const int ci0 = cit * p.ci_tile + (int)rank * n_half;
-        for (int s = s0; s < s1; ++s) {
-          mbar_wait(&pipe->empty[stage], phase ^ 1);
-          uint8_t* sA = smem + stage * kWg2StageBytes;
-          uint8_t* sB = sA + 16384;
-          if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
-          for (int g = 0; g < 2; ++g) {
-            if (p.flat) tma_load_4d_2cta(sA + g * 8192, &mapY, &pipe->full[stage], co0 + g * 64, s * 64, 0, 0);
-            else tma_load_4d_2cta(sA + g * 8192, &mapY, &pipe->full[stage], co0 + g * 64, 0, 0, s * p.rois_per_step);
-          }
-          for (int g = 0; g < b_groups; ++g) {
-            if (p.flat) tma_load_4d_2cta(sB + g * 8192, mX, &pipe->full[stage], ci0 + g * 64, s * 64, 0, 0);
-            else tma_load_4d_2cta(sB + g * 8192, mX, &pipe->full[stage], ci0 + g * 64, p.tap_x[t], p.tap_y[t],
-                                  s * p.rois_per_step);
-          }
-          if (++stage == kWg2Stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      const uint32_t idesc = make_idesc_bf16(256, p.ci_tile, 1, 1);
-      const uint32_t idesc_ones = make_idesc_bf16(256, 16, 1, 1);
-      const uint32_t s_ones = smem_u32(ones);
-      int stage = 0; uint32_t phase = 0;
-      int it = 0;
-      for (int item = pair; item < num_items; item += num_pairs, ++it) {
-        int rem = item;
-        const int split = rem % p.num_splits; rem /= p.num_splits;
-        const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-        rem /= p.co_tiles;
-        const int t = rem;
-        const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
-        const int s0 = split * p.steps_per_split;
-        const int s1 = min(p.total_steps, s0 + p.steps_per_split);
-        const int as = it & 1;
-        const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(&pipe->tmem_empty[as], aphase ^ 1);
-        tc_fence_after();
-        const uint32_t acc0 = tmem_base + (uint32_t)(as * 256);
-        for (int s = s0; s < s1; ++s) {
-          mbar_wait(&pipe->full[stage], phase);
-          tc_fence_after();
-          if (lane == 0) {
-            const uint32_t sA = smem_u32(smem + stage * kWg2StageBytes);
-            const uint32_t sB = sA + 16384;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-              const uint32_t acc = (s > s0 || kk > 0) ? 1u : 0u;
-              const uint64_t adesc = make_smem_desc(sA + kk * 2048, 8192, 1024);
-              umma_f16_2cta(acc0, adesc, make_smem_desc(sB + kk * 2048, 8192, 1024), idesc, acc);
-              if (want_shift)
-                umma_f16_2cta(acc0 + kWgOnesCol, adesc, make_smem_desc(s_ones + kk * 2048, 8192, 1024), idesc_ones, acc);
-            }
-            umma_commit_2cta(&pipe->empty[stage], 3);
-            if (s == s1 - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
-          }
-          __syncwarp();
-          if (++stage == kWg2Stages) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    int it = 0;
-    for (int item = pair; item < num_items; item += num_pairs, ++it) {
-      int rem = item;
-      rem /= p.num_splits;
-      const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-      const int cot = rem % p.co_tiles; rem /= p.co_tiles;
-      const int t = rem;
-      const bool want_shift = p.dshift != nullptr && t == 0 && cit == 0;
-      const int as = it & 1;
-      const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(&pipe->tmem_full[as], aphase);
-      tc_fence_after();
-      const int co = cot * 256 + (int)rank * 128 + q * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-#pragma unroll 1
-      for (int j = 0; j < p.ci_tile; j += 16) {
-        if (cit * p.ci_tile + j >= p.cin) break;
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + j, v);
-        tmem_ld_wait();
-        if (co < p.cout) {
-          float4* o = reinterpret_cast<float4*>(p.dw + ((size_t)co * p.taps_total + p.tap_b[t]) * p.cin +
-                                                cit * p.ci_tile + j);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            atomicAdd(o + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                         __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
-        }
-      }
-      if (want_shift) {
-        uint32_t v[16];
-        tmem_ld_32x16(taddr + kWgOnesCol, v);
-        tmem_ld_wait();
-        if (co < p.cout) atomicAdd(p.dshift + co, __uint_as_float(v[0]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);     // 4 warps x 2 CTAs
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 

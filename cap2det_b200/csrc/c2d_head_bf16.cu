@@ -213,15 +213,33 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
     if (i == kHead5bPoolConv) {
       // pool the 128-channel gradient first (avg-pool backward is linear and commutes with the 1x1 convolution);
       // q (P1's gradient memory, [n,16,128]) then acts as the gradient of a 1x1 convolution applied to X1
-      bf16* q = grad[P1];
-      pool3x3_s1_4x4_bwd_kernel<bf16, 1><<<dim3(1, n), 32, 0, st>>>(nullptr, 0, dy, ldd, q, c.cout, n, c.cout);
+      pool3x3_s1_4x4_bwd_kernel<bf16, 1><<<dim3(1, n), 32, 0, st>>>(nullptr, 0, dy, ldd, grad[P1], c.cout, n, c.cout);
       count_launch();
-      d.x = act[X1]; d.ldx = kHeadBufs[X1].ch;
-      int rc = conv_wgrad_tc(d, q, c.cout, dwsf + o.w_only, st, dshf + o.ch);
-      if (rc != C2D_OK) return rc;
-      continue;
+      continue;      // its weight gradient joins the Mixed_5b sibling launch below
     }
-    int rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st, dshf + o.ch);
+    int rc = C2D_OK;
+    const int gsz0 = head_group_size(i);
+    if (gsz0 > 0) {
+      // sibling 1x1 convolutions: ONE weight-gradient launch for the group (the shared input is read once)
+      InSeg members[4];
+      float* mdw[4];
+      float* mds[4];
+      int nm = 0;
+      for (int j = 0; j < gsz0; ++j, ++nm) {
+        const HeadConv& cj = kHeadConvs[i + j];
+        members[nm].du = grad[cj.dst] + cj.dst_off; members[nm].ld = kHeadBufs[cj.dst].ch; members[nm].cols = cj.cout;
+        mdw[nm] = dwsf + pl.poff[i + j].w_only; mds[nm] = dshf + pl.poff[i + j].ch;
+      }
+      if (i == kHeadGroups[1].first) {
+        const HeadConv& cp = kHeadConvs[kHead5bPoolConv];
+        members[nm].du = grad[P1]; members[nm].ld = cp.cout; members[nm].cols = cp.cout;
+        mdw[nm] = dwsf + pl.poff[kHead5bPoolConv].w_only; mds[nm] = dshf + pl.poff[kHead5bPoolConv].ch;
+        ++nm;
+      }
+      rc = conv_wgrad_group_tc(d, members, nm, mdw, mds, st);
+    } else if (!head_in_group_tail(i)) {
+      rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st, dshf + o.ch);
+    }
     if (rc != C2D_OK) return rc;
     // data gradient: a sibling group is reduced by ONE GEMM once its first (lowest) member is reached
     if (!head_in_group_tail(i) && !(c.src == X0 && dx0 == nullptr)) {
