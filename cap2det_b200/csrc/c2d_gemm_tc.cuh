@@ -148,6 +148,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+        ImgTile it = {0, 0, 0};
+        if (p.flat == 2) it = img_tile(p, mt);        // once per tile: the producer is one latency-bound thread
         for (int t = 0; t < p.taps; ++t) {
           const int tm = p.tap_map[t];
           const CUtensorMap* mA = tm == 0 ? &mapA0 : (tm == 1 ? &mapA1 : (tm == 2 ? &mapA2 : &mapA3));
@@ -158,7 +160,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             uint8_t* sB = sA + kStageABytes;
             mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
             if (p.flat == 1) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
-            else if (p.flat == 2) { const ImgTile it = img_tile(p, mt); tma_load_4d(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n); }
+            else if (p.flat == 2) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
             else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, tx, ty, mt * p.rois_per_tile);
             tma_load_4d(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile, 0, 0);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -382,6 +384,9 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
+        const int h = 2 * mt + (int)rank;
+        ImgTile it = {0, 0, 0};
+        if (p.flat == 2) it = img_tile(p, h);         // once per tile: the producer is one latency-bound thread
         for (int t = 0; t < p.taps; ++t) {
           const int tm = p.tap_map[t];
           const CUtensorMap* mA = tm == 0 ? &mapA0 : (tm == 1 ? &mapA1 : (tm == 2 ? &mapA2 : &mapA3));
@@ -391,9 +396,8 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             uint8_t* sA = smem + stage * k2StageBytes;
             uint8_t* sB = sA + k2StageABytes;
             if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
-            const int h = 2 * mt + (int)rank;
             if (p.flat == 1) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, h * p.rows_per_tile, 0, 0);
-            else if (p.flat == 2) { const ImgTile it = img_tile(p, h); tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n); }
+            else if (p.flat == 2) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
             else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, h * p.rois_per_tile);
             tma_load_4d_2cta(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile + (int)rank * n_half, 0, 0);
             if (++stage == k2Stages) { stage = 0; phase ^= 1; }
