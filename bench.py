@@ -365,7 +365,7 @@ def main():
       if dominant is not None:
         out['roofline'] = dominant
     if not args.no_cpu_baseline and world == 1:
-      out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=96, steps=2)
+      out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=960, steps=1)   # ~10-30 s of host work
     print(json.dumps(out))
   if world > 1:
     dist.barrier()
