@@ -1,16 +1,19 @@
-// bf16 tensor-core GEMM kernels for the box-classifier head and FC layers (sm_100a):
-// TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared memory ring -> tcgen05.mma (accumulators in
-// TMEM) -> tcgen05.ld epilogue.  One persistent CTA per SM, warp specialised:
-//   warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue.
+// bf16 tensor-core GEMM kernels (sm_100a) for the box-classifier head, the FC layers and the first stage:
+// TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma (accumulators in TMEM) ->
+// tcgen05.ld epilogue.  Persistent CTAs (one per SM, or one cluster of two per SM pair), warp specialised:
+//   warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2.. = epilogue.
 //
-// conv_gemm_tc_kernel : implicit-GEMM convolution / plain GEMM with K-major operands.
+// conv_gemm_tc_kernel        : implicit-GEMM convolution / plain GEMM, K-major operands, one CTA per 256-row tile.
 //     D[256 rows, n_tile] = sum_{tap, 64-channel chunk} A_box(tap, chunk) * W[n, tap, chunk]^T
-//   The A rows of one tap are ONE TMA box over the NHWC activation tensor, shifted by the tap
-//   offset; out-of-bounds coordinates are zero-filled by TMA, which implements SAME padding (and
-//   the ragged last tile) without an im2col buffer.  Stride-2 convolutions use four parity views
-//   of the input (one tensor map per (y parity, x parity)).
-// wgrad_tc_kernel     : weight gradient, dW[co, tap, ci] += sum_rows dY[row, co] * X[row(tap), ci]
-//   with MN-major operands (the reduction runs over rows, data is contiguous along channels).
+//   The A rows of one tap are ONE TMA box over the NHWC activation tensor, shifted by the tap offset;
+//   out-of-bounds coordinates are zero-filled by TMA, which implements SAME padding (and the ragged last
+//   tile) without an im2col buffer.  Stride-2 convolutions read four parity views of the input (one tensor
+//   map per (y parity, x parity)).  Three row geometries: flat rows, per-ROI planes, whole feature maps.
+// conv_gemm_tc2_kernel       : the same on a CTA pair (cta_group::2, M = 256 across two SMs).
+// conv_gemm_tc2_multi_kernel : up to four such problems that share the weights in one launch.
+// wgrad_tc_kernel            : weight gradient, dW[co, tap, ci] += sum_rows dY[row, co] * X[row(tap), ci] with
+//   MN-major operands (the reduction runs over rows, data is contiguous along channels); the dY rows may come
+//   from up to four gradient buffers (sibling convolutions on one input).
 #pragma once
 #include "c2d_common.cuh"
 #include "c2d_tc.cuh"
