@@ -220,3 +220,47 @@ def test_model_train_step_bf16_against_fp32_oracle():
       RTOL_BF16 * abs(want['loss']['midn_cross_entropy_loss'])
   assert torch.isfinite(model.head_params.grad).all() and torch.isfinite(model.fc_weights.grad).all()
   assert pred['detection_boxes_at_3'].shape == (B, 300, 4)
+
+
+def test_configuration_spread_trains_and_predicts_finite():
+  """Shapes beyond the bench workload on the bf16 path: VOC (20 classes) and COCO (80), batch 1..4, ragged proposal
+  counts, odd proposal numbers, feature-map and image inputs of several sizes, single- and multi-scale
+  evaluation: two training steps (or one prediction) each, everything stays finite and no kernel reports an error."""
+  import tempfile
+  from cap2det_b200 import builder, config, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  def run(B, P, classes, H, W, first_stage, train=True, eval_dims=()):
+    text = synthetic.model_options_text(extractor='groundtruth_extractor', eval_min_dimension=eval_dims,
+                                        extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+    m = config.Model(); m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+    model = builder.build(m, is_training=train, head_dtype=torch.bfloat16, first_stage=first_stage)
+    with torch.no_grad(): model.fc_weights.mul_(8.0)
+    rng = np.random.default_rng(B * 1000 + P)
+    props = torch.from_numpy(synthetic.make_proposals(rng, B, P, H, W)).cuda()
+    npr = torch.from_numpy(rng.integers(max(1, P // 2), P + 1, size=B).astype(np.int32)).cuda()
+    ex = {F.num_proposals: npr, F.proposals: props, F.object_texts: synthetic.make_object_texts(rng, B, classes)}
+    if first_stage:
+      ex[F.image] = torch.from_numpy(rng.integers(0, 256, size=(B, H, W, 3)).astype(np.uint8)).cuda()
+    else:
+      ex[F.features_to_crop] = torch.from_numpy(synthetic.make_feature_map(rng, B, H, W)).cuda().requires_grad_(True)
+    if train:
+      step = trainer.TrainStep(model, learning_rate=0.01)
+      for _ in range(2): total = step(ex)
+      model.raise_if_assert_failed()
+      torch.cuda.synchronize()
+      assert np.isfinite(float(total)), total
+      for v in model.get_variables_to_train(): assert bool(torch.isfinite(v).all())
+      return float(total)
+    pred = model.build_prediction(ex)
+    torch.cuda.synchronize()
+    n = pred['num_detections_at_3']
+    assert bool(torch.isfinite(pred['detection_scores_at_3']).all())
+    return n.tolist()
+  assert np.isfinite(run(1, 2000, synthetic.VOC_CLASSES, 600, 1000, False))
+  assert np.isfinite(run(3, 1500, synthetic.COCO_CLASSES, 480, 640, False))
+  assert np.isfinite(run(1, 1999, synthetic.VOC_CLASSES, 333, 500, True))
+  assert np.isfinite(run(4, 300, synthetic.COCO_CLASSES, 224, 224, True))
+  assert all(0 <= n <= 300 for n in run(1, 2000, synthetic.VOC_CLASSES, 600, 900, True, train=False, eval_dims=(480, 600)))
+  assert all(0 <= n <= 300 for n in run(2, 500, synthetic.COCO_CLASSES, 600, 1000, False, train=False))
+
