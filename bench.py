@@ -180,6 +180,8 @@ def main():
   ap.add_argument('--no-first-stage', action='store_true', help='skip the extra from-images measurement')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-kernel-table', action='store_true')
+  ap.add_argument('--no-cuda-graph', action='store_true', help='run every step eagerly (default: replay the step as a '
+                  'CUDA graph on one GPU, eager under torchrun)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
   if args.impl == 'reference':
@@ -195,6 +197,7 @@ def main():
   local_rank = int(os.environ.get('LOCAL_RANK', '0'))
   assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
   torch.cuda.set_device(local_rank)
+  torch.cuda.set_stream(torch.cuda.Stream())      # keep off the legacy default stream (CUDA-graph capture needs it)
   if world > 1:
     import datetime
     # NCCL prints its version banner on STDOUT at VERSION level and above; stdout carries exactly one JSON line
@@ -232,10 +235,44 @@ def main():
       dist.barrier()
       torch.cuda.synchronize()
 
-  def run_resident(i):
+  def run_eager(i):
     ex = resident[i % n_pool]
     ex[F.features_to_crop].grad = None
     return step(ex)
+
+  # One GPU: the step is captured once into a CUDA graph (trainer.GraphedTrainStep, part of the public API) and
+  # replayed; inputs are copied into its static buffers every step.  Falls back to eager steps if capture fails.
+  graphed = None
+  if world == 1 and not args.no_cuda_graph:
+    try:
+      graphed = trainer.GraphedTrainStep(step, resident[0])
+    except Exception as e:      # noqa: BLE001 - any capture problem means: measure the eager path
+      sys.stderr.write('CUDA-graph capture failed (%s); running eager steps\n' % str(e).split('\n')[0])
+      graphed = None
+      torch.cuda.synchronize()
+
+  # Graph mode: label extraction (host tokenisation + a pageable H2D copy of the token ids) runs one step ahead on
+  # the copy stream, like a data loader would, so that the host never waits on the compute stream before a replay.
+  label_stream = torch.cuda.Stream(device=dev)
+  pre_labels = {}
+
+  def prefetch_labels(i, ex):
+    with torch.cuda.stream(label_stream):
+      lab = graphed.extract_labels(ex)
+      ev = torch.cuda.Event()
+      ev.record(label_stream)
+    pre_labels[i] = (lab, ev)
+
+  def run_resident(i):
+    if graphed is None:
+      return run_eager(i)
+    if i not in pre_labels:
+      prefetch_labels(i, resident[i % n_pool])
+    lab, ev = pre_labels.pop(i)
+    prefetch_labels(i + 1, resident[(i + 1) % n_pool])
+    torch.cuda.current_stream().wait_event(ev)
+    lab.record_stream(torch.cuda.current_stream())
+    return graphed(resident[i % n_pool], labels=lab)
 
   # end to end: every step copies its inputs from pinned host memory (on a copy stream, one step ahead, so the
   # PCIe transfer of step i+1 overlaps the kernels of step i) and reads the step's loss back to the host.
@@ -251,6 +288,8 @@ def main():
       ex = {F.features_to_crop: p['fmap'].to(dev, non_blocking=True),
             F.proposals: p['proposals'].to(dev, non_blocking=True),
             F.num_proposals: p['num_proposals'].to(dev, non_blocking=True), F.concat_caption_string: p['captions']}
+      if graphed is not None:
+        ex['_labels'] = graphed.extract_labels(ex)
       ev = torch.cuda.Event()
       ev.record(copy_stream)
     staged[i] = (ex, ev)
@@ -264,8 +303,11 @@ def main():
     for t in ex.values():
       if torch.is_tensor(t):
         t.record_stream(torch.cuda.current_stream())
-    ex[F.features_to_crop].requires_grad_(True)
-    total = step(ex)
+    if graphed is not None:
+      total = graphed(ex, labels=ex['_labels'])
+    else:
+      ex[F.features_to_crop].requires_grad_(True)
+      total = step(ex)
     # device -> host read of the step's loss: an async copy into pinned memory every step; the host blocks on the
     # PREVIOUS step's copy only, so it keeps one step of launches queued ahead of the GPU
     slot = i & 1
@@ -300,6 +342,8 @@ def main():
 
   sampler = ClockSampler(local_rank) if rank == 0 else None
   total_ms, launches, wall = timed(run_resident, args.warmup, args.steps)
+  if graphed is not None:     # a replay launches the kernels recorded at capture; the host-side counter saw them once
+    launches += graphed.launches_per_step * args.steps
   clocks = sampler.stop() if sampler else None
   e2e_ms, _, _ = timed(run_e2e, 2, args.steps)
   for slot in range(2):
@@ -319,6 +363,7 @@ def main():
              steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
              scaling='weak', vs_baseline=None, dtype=head_dtype, data='synthetic',
              config=dict(CONFIG, global_batch_images=world * B, parallelism='dp%d (by image)' % world,
+                         step_launch='CUDA graph replay (trainer.GraphedTrainStep)' if graphed is not None else 'eager',
                          l2_handling='256 MB L2 flush between timed iterations', head_dtype=head_dtype),
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
@@ -354,7 +399,7 @@ def main():
   if not args.no_kernel_table and head_dtype == 'bf16':
     # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
     from cap2det_b200 import profiling
-    dominant = profiling.dominant_kernel_roofline(lambda i: run_resident(i), peaks, ROOT)
+    dominant = profiling.dominant_kernel_roofline(lambda i: run_eager(i), peaks, ROOT)   # per-launch events need eager launches
   if rank == 0:
     if not args.no_kernel_table:
       from cap2det_b200 import profiling

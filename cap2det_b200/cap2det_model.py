@@ -287,7 +287,9 @@ class Model(ModelBase):
     """models/cap2det_model.py:274-330."""
     options = self._model_proto
     loss_dict = {}
-    labels = self._label_extractor.extract_labels(examples)
+    labels = examples.get('_labels')            # precomputed image-level labels (GraphedTrainStep), else extract
+    if labels is None:
+      labels = self._label_extractor.extract_labels(examples)
     loss_dict['midn_cross_entropy_loss'] = ops.sigmoid_ce_mean(
         labels, predictions[Cap2DetPredictions.midn_class_logits], options.midn_loss_weight)
     num_proposals = predictions[DetectionResultFields.num_proposals]

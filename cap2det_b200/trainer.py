@@ -221,3 +221,58 @@ class TrainStep(object):
     self.global_step += 1
     self.last_loss_dict = loss_dict
     return total.detach() + self.regularization_loss()
+
+
+class GraphedTrainStep(object):
+  """A TrainStep captured once into a CUDA graph and replayed: the ~140 kernel launches of a step (and the gaps
+  between dependent launches) collapse into one graph launch.  Fixed shapes only: every step must bring tensors
+  of the shapes seen at construction.  Label extraction (host-side tokenisation) stays outside the graph; its
+  [B, C] result and the input tensors are copied into static buffers before each replay.  The learning rate is
+  baked in at capture time (every reference config keeps it constant, learning_rate_decay.decay_rate 1.0).
+  Single process only (world_size 1)."""
+
+  def __init__(self, train_step, examples):
+    if train_step.world_size != 1:
+      raise ValueError('GraphedTrainStep supports world_size 1')
+    self.step = train_step
+    model = train_step.model
+    self._extract = model._label_extractor.extract_labels
+    self.static = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in examples.items() if torch.is_tensor(v)}
+    self.static_labels = self._extract(examples).clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+      for _ in range(3):
+        self._run_static()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    before = capi.launch_count()
+    self.graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(self.graph):
+      self.static_total = self._run_static()
+    self.launches_per_step = capi.launch_count() - before
+    self._status = model._assert_status
+
+  def _run_static(self):
+    for v in self.static.values():
+      v.grad = None
+    ex = dict(self.static)
+    ex['_labels'] = self.static_labels
+    return self.step(ex)
+
+  def extract_labels(self, examples):
+    """The image-level labels of a batch (host tokenisation + one small kernel).  Call it ahead of time on a side
+    stream and pass the result to __call__ to keep it off the step's critical path."""
+    return self._extract(examples)
+
+  def __call__(self, examples, labels=None):
+    self.static_labels.copy_(labels if labels is not None else self._extract(examples), non_blocking=True)
+    for k, v in self.static.items():
+      v.detach().copy_(examples[k], non_blocking=True)
+    self.graph.replay()
+    self.step.model._assert_status = self._status
+    return self.static_total
+
+  def input_grad(self, key):
+    """Gradient w.r.t. a static input tensor of the last replay (e.g. features_to_crop)."""
+    return self.static[key].grad
