@@ -166,10 +166,20 @@ def run_reference(args):
              cpu_baseline=dict(value=value, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
                                sample=base['sample']),
              e2e=dict(value=value, unit='proposals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-  print(json.dumps(out))
+  emit(out)
 
 
 # ---------------------------------------------------------------------------------------------
+_STDOUT_FD = None
+
+
+def emit(obj):
+  """Writes the result line to the real stdout (see main)."""
+  sys.stdout.flush()
+  line = (json.dumps(obj) + '\n').encode()
+  os.write(_STDOUT_FD if _STDOUT_FD is not None else 1, line)
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -183,6 +193,12 @@ def main():
   ap.add_argument('--no-cuda-graph', action='store_true', help='run every step eagerly (default: replay the step as a '
                   'CUDA graph on one GPU, eager under torchrun)')
   args = ap.parse_args()
+  # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner) is sent to
+  # stderr by pointing fd 1 at fd 2 until the result is written
+  sys.stdout.flush()
+  global _STDOUT_FD
+  _STDOUT_FD = os.dup(1)
+  os.dup2(2, 1)
   args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
   if args.impl == 'reference':
     return run_reference(args)
@@ -200,9 +216,6 @@ def main():
   torch.cuda.set_stream(torch.cuda.Stream())      # keep off the legacy default stream (CUDA-graph capture needs it)
   if world > 1:
     import datetime
-    # NCCL prints its version banner on STDOUT at VERSION level and above; stdout carries exactly one JSON line
-    if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
-      os.environ['NCCL_DEBUG'] = 'WARN'
     dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank),
                             timeout=datetime.timedelta(seconds=120))
   dev = torch.device('cuda', local_rank)
@@ -411,7 +424,7 @@ def main():
         out['roofline'] = dominant
     if not args.no_cpu_baseline and world == 1:
       out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=960, steps=1)   # ~10-30 s of host work
-    print(json.dumps(out))
+    emit(out)
   if world > 1:
     dist.barrier()
     dist.destroy_process_group()
