@@ -126,3 +126,46 @@ def test_multiscale_eval_from_one_image():
   for i in range(4):
     k = 'oicr_proposal_scores_at_%d' % i
     assert torch.equal(pred[k], pred2[k])
+
+
+def test_tfrecord_to_training_step(tmp_path):
+  """Disk to gradients: a TFRecord written in the reference's tf.Example schema -> tfrecord.read_examples ->
+  reader.make_batch (flip, pad, batch rescale, box rescale) -> one training step from images."""
+  import io
+  import tempfile
+  from PIL import Image
+  from cap2det_b200 import builder, config, reader, synthetic, tfrecord, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  rng = np.random.default_rng(11)
+  classes = synthetic.VOC_CLASSES
+  records = []
+  for i, (h, w, n) in enumerate(((96, 128, 9), (120, 90, 14), (100, 100, 5))):
+    buf = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)).save(buf, format='JPEG')
+    props = np.sort(rng.uniform(0, 1, size=(n, 2, 2)), axis=1).reshape(n, 4).astype(np.float32)
+    ex = {'image/source_id': [('%06d.jpg' % i).encode()], 'image/encoded': [buf.getvalue()],
+          'image/caption/string': [classes[i]], 'image/caption/offset': [0], 'image/caption/length': [1],
+          'image/object/class/text': [classes[i]], 'image/object/bbox/ymin': [0.1], 'image/object/bbox/xmin': [0.1],
+          'image/object/bbox/ymax': [0.9], 'image/object/bbox/xmax': [0.8]}
+    for j, k in enumerate(('ymin', 'xmin', 'ymax', 'xmax')):
+      ex['image/proposal/bbox/' + k] = props[:, j]
+    records.append(tfrecord.encode_example(ex))
+  path = str(tmp_path / 'train.record')
+  tfrecord.write_records(path, records)
+  examples = list(tfrecord.read_examples(path))
+  assert [e[F.image_id] for e in examples] == ['000000.jpg', '000001.jpg', '000002.jpg']
+  batch = reader.make_batch(examples, max_num_proposals=12, batch_resize_scale_value=(1.2, 0.8), rng=rng,
+                            flip_probability=0.5)
+  assert batch[F.proposals].shape == (3, 12, 4) and batch[F.num_proposals].tolist() == [9, 12, 5]
+  assert batch[F.image].shape[0] == 3 and batch[F.object_texts] == [[classes[0]], [classes[1]], [classes[2]]]
+  d = tempfile.mkdtemp()
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=True, head_dtype=torch.bfloat16, first_stage=True)
+  step = trainer.TrainStep(model, learning_rate=0.01)
+  total = step(batch)
+  model.raise_if_assert_failed()
+  assert np.isfinite(float(total))
+  assert model.last_labels.sum(dim=1).tolist() == [1.0, 1.0, 1.0]          # one ground-truth class per image
