@@ -258,3 +258,66 @@ def test_tfrecord_decode_example_mirrors_parse_fn(tmp_path):
   assert e[F.concat_caption_string] == ['a', 'dog', 'runs', 'two', 'cats'] and e[F.concat_caption_length] == 5
   no_img = tfrecord.decode_example(tfrecord.encode_example(ex), decode_image=False)
   assert F.image not in no_img
+
+
+# ---- Pascal VOC metric (train/predict.py:325-420; OD-API PascalDetectionEvaluator restated) -----------------
+def test_pascal_evaluator_known_answers():
+  import numpy as np
+  from cap2det_b200 import evaluation
+  cats = [{'id': 1, 'name': 'cat'}, {'id': 2, 'name': 'dog'}, {'id': 3, 'name': 'bird'}]
+  ev = evaluation.PascalDetectionEvaluator(cats)
+  # image A: two cats; detections: hit (0.9), miss (0.8), hit (0.7), duplicate of the first cat (0.6)
+  ev.add_single_ground_truth_image_info('A', {'groundtruth_boxes': np.array([[0, 0, 10, 10], [20, 20, 40, 40]], float),
+                                            'groundtruth_classes': np.array([1, 1])})
+  ev.add_single_detected_image_info('A', {
+      'detection_boxes': np.array([[0, 0, 10, 9], [50, 50, 60, 60], [21, 20, 40, 41], [0, 1, 10, 10]], float),
+      'detection_scores': np.array([0.9, 0.8, 0.7, 0.6]), 'detection_classes': np.array([1, 1, 1, 1])})
+  # image B: one dog (difficult) + one dog; the detection on the difficult one is ignored, the other is found
+  ev.add_single_ground_truth_image_info('B', {'groundtruth_boxes': np.array([[0, 0, 10, 10], [30, 30, 50, 50]], float),
+                                            'groundtruth_classes': np.array([2, 2]),
+                                            'groundtruth_difficult': np.array([True, False])})
+  ev.add_single_detected_image_info('B', {
+      'detection_boxes': np.array([[0, 0, 10, 10], [30, 30, 50, 49]], float),
+      'detection_scores': np.array([0.95, 0.5]), 'detection_classes': np.array([2, 2])})
+  m = ev.evaluate()
+  # cat: tp fp tp fp -> precision 1, 1/2, 2/3, 2/4 ; recall .5 .5 1 1 -> AP = .5*1 + .5*(2/3)
+  assert m['PascalBoxes_PerformanceByCategory/AP@0.5IOU/cat'] == pytest.approx(0.5 + 0.5 * 2 / 3)
+  assert m['PascalBoxes_PerformanceByCategory/AP@0.5IOU/dog'] == pytest.approx(1.0)
+  assert np.isnan(m['PascalBoxes_PerformanceByCategory/AP@0.5IOU/bird'])          # no ground truth: skipped
+  assert m['PascalBoxes_Precision/mAP@0.5IOU'] == pytest.approx((0.5 + 1 / 3 + 1.0) / 2)
+  assert evaluation.compute_average_precision(None, None) != evaluation.compute_average_precision(None, None)  # NaN
+  assert evaluation.compute_average_precision([1.0, 0.5], [0.5, 0.5]) == pytest.approx(0.5)
+  # a class with ground truth but no detection scores 0
+  ev.clear()
+  ev.add_single_ground_truth_image_info('C', {'groundtruth_boxes': np.array([[0, 0, 5, 5]], float), 'groundtruth_classes': np.array([3])})
+  ev.add_single_detected_image_info('C', {'detection_boxes': np.zeros((0, 4)), 'detection_scores': np.zeros(0), 'detection_classes': np.zeros(0)})
+  assert ev.evaluate()['PascalBoxes_Precision/mAP@0.5IOU'] == 0.0
+
+
+def test_pascal_evaluator_add_batch_from_prediction_dict():
+  """The loop of train/predict.py:346-412 over a batch: normalised boxes -> pixels, 1-based classes, one
+  evaluator per OICR stage."""
+  import numpy as np
+  from cap2det_b200 import evaluation
+  from cap2det_b200.standard_fields import InputDataFields as F
+  names = ['cat', 'dog']
+  category_to_id = {n: i + 1 for i, n in enumerate(names)}
+  cats = [{'id': i + 1, 'name': n} for i, n in enumerate(names)]
+  evs = [evaluation.PascalDetectionEvaluator(cats) for _ in range(2)]
+  examples = {F.image_id: ['x', 'y'], F.image_height: np.array([100, 200]), F.image_width: np.array([200, 100]),
+              F.num_objects: np.array([1, 2]), F.object_texts: [['cat', ''], ['dog', 'cat']],
+              F.object_boxes: np.array([[[0.1, 0.1, 0.5, 0.5], [0, 0, 0, 0]], [[0.0, 0.0, 0.5, 0.5], [0.5, 0.5, 1, 1]]], np.float32)}
+  det = np.zeros((2, 3, 4), np.float32)
+  det[0, 0] = [0.1, 0.1, 0.5, 0.5]; det[1, 0] = [0.0, 0.0, 0.5, 0.5]; det[1, 1] = [0.5, 0.5, 1, 1]
+  pred = {}
+  for i, cls in enumerate(([[1, 0, 0], [2, 1, 0]], [[2, 0, 0], [2, 2, 0]])):       # stage 1 is wrong on purpose
+    pred['num_detections_at_%d' % i] = np.array([1, 2])
+    pred['detection_boxes_at_%d' % i] = det
+    pred['detection_scores_at_%d' % i] = np.array([[0.9, 0, 0], [0.8, 0.7, 0]], np.float32)
+    pred['detection_classes_at_%d' % i] = np.array(cls, np.float32)
+  evaluation.add_batch(evs, examples, pred, category_to_id)
+  assert evs[0].evaluate()['PascalBoxes_Precision/mAP@0.5IOU'] == pytest.approx(1.0)
+  m1 = evs[1].evaluate()
+  assert m1['PascalBoxes_PerformanceByCategory/AP@0.5IOU/cat'] == 0.0
+  # dog detections by score: 0.9 on the cat box of image x (fp), 0.8 on the dog (tp), 0.7 on the cat of image y (fp)
+  assert m1['PascalBoxes_PerformanceByCategory/AP@0.5IOU/dog'] == pytest.approx(0.5)
