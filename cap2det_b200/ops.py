@@ -247,7 +247,8 @@ class _BackboneInceptionV2(torch.autograd.Function):
     params, ws, fmap = ctx.saved_tensors
     B, H, W = ctx.shape
     dparams = torch.empty_like(params)
-    call('c2d_backbone_bwd', ptr(dfmap.contiguous()), ptr(fmap), B, H, W, ptr(params), ptr(ws), ws.numel(),
+    dfmap = dfmap.contiguous()              # named: ptr() of a temporary would dangle
+    call('c2d_backbone_bwd', ptr(dfmap), ptr(fmap), B, H, W, ptr(params), ptr(ws), ws.numel(),
          ptr(dparams), stream())
     return None, dparams
 

@@ -87,7 +87,8 @@ def test_conv_img_bf16_fwd_dgrad_wgrad(n, h, w, cin, cout, k, stride):
   assert torch.all(dxd[..., cin:] == 7.0)
   # fused ReLU mask: dx = 0 where the activation (same layout as dx) is <= 0
   mask = _bf(rng.standard_normal((n, h, w, ldx)).astype(np.float32))
-  call('c2d_conv_img_bf16_dgrad', ptr(dyd), ldy, n, h, w, cin, ptr(wt), cout, ptr(mask.cuda()), ptr(dxd), ldx, stream())
+  mask_d = mask.cuda()
+  call('c2d_conv_img_bf16_dgrad', ptr(dyd), ldy, n, h, w, cin, ptr(wt), cout, ptr(mask_d), ptr(dxd), ldx, stream())
   torch.cuda.synchronize()
   want_m = want_dx * (mask[..., :cin].float().numpy() > 0)
   assert l2_err(dxd[..., :cin].float().cpu().numpy(), want_m) < 3e-3

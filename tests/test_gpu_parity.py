@@ -131,17 +131,18 @@ def test_roi_crop_maxpool_backward():
   from cap2det_b200.capi import call, ptr, stream
   B, Hf, Wf, C = fmap.shape
   P = props.shape[1]
+  fm, pr = dev(fmap), dev(props)       # keep the device tensors alive: ptr() of a temporary would dangle
   for dt in (torch.float32, torch.bfloat16):
     gd = dev(g).to(dt)
     d1 = torch.empty((B, Hf, Wf, C), dtype=torch.float32, device='cuda')
-    call('c2d_roi_crop_maxpool_bwd', ptr(dev(fmap)), B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(gd),
+    call('c2d_roi_crop_maxpool_bwd', ptr(fm), B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(gd),
          capi.dtype_code(dt), ptr(d1), stream())
     codes = torch.empty((capi.load().c2d_roi_argmax_code_bytes(B * P, C, 14),), dtype=torch.uint8, device='cuda')
     out2 = torch.empty((B * P, 7, 7, C), dtype=dt, device='cuda')
-    call('c2d_roi_crop_maxpool_fwd_codes', ptr(dev(fmap)), B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(out2),
+    call('c2d_roi_crop_maxpool_fwd_codes', ptr(fm), B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(out2),
          capi.dtype_code(dt), ptr(codes), stream())
     d2 = torch.empty_like(d1)
-    call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, C, ptr(dev(props)), P, 14, 2, 2, ptr(codes), ptr(gd),
+    call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd),
          capi.dtype_code(dt), ptr(d2), stream())
     want_dt = oroi.roi_crop_maxpool_bwd(fmap, props, gd.float().cpu().numpy())
     assert rel_err(d1.cpu().numpy(), want_dt) < RTOL_F32
@@ -622,7 +623,8 @@ def test_adagrad_l2_update_matches_reference_formulas():
   assert rel_err(wd.cpu().numpy(), w64) < RTOL_F32
   assert rel_err(ad.cpu().numpy(), a64) < RTOL_F32
   out = torch.empty((), dtype=torch.float32, device='cuda')
-  call('c2d_l2_loss', ptr(dev(w)), n, 1e-6, ptr(out), stream())
+  w_dev = dev(w)
+  call('c2d_l2_loss', ptr(w_dev), n, 1e-6, ptr(out), stream())
   assert abs(float(out) - 1e-6 * float((w.astype(np.float64) ** 2).sum()) / 2) <= 1e-5 * abs(float(out))
 
 
