@@ -160,6 +160,12 @@ class TrainStep(object):
     self.model = model
     self.world_size = world_size
     self.global_step = 0
+    self._pending = []
+    if world_size > 1 and hasattr(torch.Tensor, 'register_post_accumulate_grad_hook'):
+      # Start the all-reduce of a gradient buffer the moment autograd has finished it: the head's 24 MB buffer
+      # is complete before the ROI backward (and the first-stage backward) run, so NCCL overlaps with them.
+      for v in model.get_variables_to_train():
+        v.register_post_accumulate_grad_hook(self._reduce_when_ready)
     self.train_config = train_config
     options = model._model_proto
     l2 = l2_regularizer_scale(options.fc_hyperparams)
@@ -185,6 +191,11 @@ class TrainStep(object):
       raise ValueError('moving_average_decay != 0 is not supported on this path')
     if train_config.HasField('max_gradient_norm'):          # train/trainer.py:134-136
       self.opt.clip_norm = float(train_config.max_gradient_norm)
+
+  def _reduce_when_ready(self, param):
+    import torch.distributed as dist
+    if param.grad is not None and dist.is_available() and dist.is_initialized():
+      self._pending.append((param, dist.all_reduce(param.grad, op=dist.ReduceOp.SUM, async_op=True)))
 
   @classmethod
   def from_pipeline(cls, model, pipeline, world_size=1):
@@ -214,9 +225,14 @@ class TrainStep(object):
     total = None
     for v in loss_dict.values():
       total = v if total is None else total + v
+    self._pending = []
     total.backward()
     if self.world_size > 1:
-      c2d_dist.allreduce_sum([v.grad for v in model.get_variables_to_train()])
+      # gradient buffers whose hook fired are already being reduced (see _reduce_when_ready); reduce the rest
+      started = {id(v) for v, _ in self._pending}
+      c2d_dist.allreduce_sum([v.grad for v in model.get_variables_to_train() if v.grad is not None and id(v) not in started])
+      for _, work in self._pending:
+        work.wait()
     self.opt.step(grad_scale=1.0 / self.world_size)
     self.global_step += 1
     self.last_loss_dict = loss_dict
