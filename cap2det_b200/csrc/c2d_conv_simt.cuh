@@ -304,7 +304,7 @@ __global__ void pool3x3_fwd_kernel(const T* __restrict__ x, int ldx, T* __restri
 // Backward of the above.  Max routes to the FIRST maximum in row-major window order.
 // dx (+)= ...; ACCUM selects accumulate vs overwrite of the destination.
 template <typename T, int HIN, int STRIDE, int MODE, bool ACCUM>
-__global__ void pool3x3_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int ldy,
+__global__ void __launch_bounds__(128, 4) pool3x3_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int ldy,
                                    T* __restrict__ dx, int lddx, int n_rois, int C) {
   constexpr int HOUT = (HIN + STRIDE - 1) / STRIDE;
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
@@ -423,7 +423,7 @@ pool3x3_s1_4x4_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, i
 
 // Backward (overwrite).  Max routes to the FIRST maximum in row-major window order, as pool3x3_bwd_kernel.
 template <typename T, int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int ldy, T* __restrict__ dx,
                           int lddx, int n_rois, int C) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
