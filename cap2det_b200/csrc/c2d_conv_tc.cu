@@ -398,14 +398,33 @@ int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16* wt
 // (A 2-CTA variant of this kernel was measured 6 % slower on this layer mix and removed)
 static int launch_wgrad(tc::WgradParams& p, const CUtensorMap& mapY, const CUtensorMap mapX[4], cudaStream_t st,
                         double flops) {
-  const int base_items = p.taps * p.co_tiles * p.ci_tiles;
-  int splits = num_sms() / base_items;       // one wave of items; every extra split is a dW-sized atomic pass
-  if (splits < 1) splits = 1;
-  if (splits > p.total_steps) splits = p.total_steps;
   if (p.total_steps <= 0) return C2D_OK;
-  p.steps_per_split = (p.total_steps + splits - 1) / splits;
-  p.num_splits = (p.total_steps + p.steps_per_split - 1) / p.steps_per_split;
-  const int items = base_items * p.num_splits;
+  C2D_CHECK_ARG(p.co_tiles >= 1 && p.co_tiles <= 4, "wgrad: at most 1024 output channels (4 co tiles) per launch");
+  // One wave of work items (every extra split is another dW-sized pass of vector atomics).  The time of a k-step
+  // follows the bytes it stages, (A groups + ci groups) x 8 KB, plus a fixed part (barrier round trip, MMA issue)
+  // worth about twenty more groups -- measured: a 2-group tail tile costs ~0.93 of a full one -- so tail tiles get
+  // slightly fewer splits: greedily give the next split to the tile whose items are currently the longest.
+  const int per_tile = p.taps * p.ci_tiles;
+  int cost[4], splits[4];
+  for (int c = 0; c < p.co_tiles; ++c) {
+    cost[c] = ((p.ngroups - c * 4) > 2 ? 4 : 2) + p.ci_groups + 20;
+    splits[c] = 1;
+  }
+  int used = p.co_tiles;
+  while ((used + 1) * per_tile <= num_sms()) {
+    int best = -1;
+    for (int c = 0; c < p.co_tiles; ++c)
+      if (splits[c] < p.total_steps && (best < 0 || (long long)cost[c] * splits[best] > (long long)cost[best] * splits[c])) best = c;
+    if (best < 0) break;
+    ++splits[best]; ++used;
+  }
+  p.splits_sum = 0;
+  for (int c = 0; c < p.co_tiles; ++c) {
+    p.tile_steps[c] = (p.total_steps + splits[c] - 1) / splits[c];
+    p.tile_splits[c] = (p.total_steps + p.tile_steps[c] - 1) / p.tile_steps[c];
+    p.splits_sum += p.tile_splits[c];
+  }
+  const int items = per_tile * p.splits_sum;
   if (items <= 0) return C2D_OK;
   ProfScope prof(st, 1, flops);
   const int grid = items < num_sms() ? items : num_sms();

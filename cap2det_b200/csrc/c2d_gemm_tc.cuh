@@ -610,7 +610,9 @@ struct WgradParams {
   int img_tiles_x, img_tiles_y;
   int rois_per_step;          // geometric: ROIs per k-step (box N dim)
   int total_steps;            // k-steps over the whole tensor
-  int steps_per_split, num_splits;
+  // Row splits per co tile (<= 4 tiles): a 2-group tail tile stages fewer bytes per k-step than a full one, so it
+  // gets fewer, longer splits -- every work item then takes about the same time.  splits_sum = sum over co tiles.
+  int tile_splits[4], tile_steps[4], splits_sum;
   int co_tiles, ci_tiles, ci_tile, ci_groups;   // co tile = 256; ci_tile = UMMA N (<= 240)
   int cout, cin;              // valid extents (cout = A rows incl. the padding of partial 64-channel groups)
   int taps_total;             // taps in the dW layout [co][taps_total][cin]
@@ -627,6 +629,20 @@ struct WgradParams {
   float* m_dw[4];
   float* m_dshift[4];         // [cout] or null
 };
+
+struct WgItem { int t, cot, cit, s0, s1; };
+__device__ __forceinline__ WgItem wg_decode(const WgradParams& p, int item) {
+  WgItem w;
+  int rem = item % p.splits_sum;                 // (co tile, split) pair
+  item /= p.splits_sum;
+  w.cit = item % p.ci_tiles;
+  w.t = item / p.ci_tiles;
+  w.cot = 0;
+  while (w.cot + 1 < p.co_tiles && rem >= p.tile_splits[w.cot]) { rem -= p.tile_splits[w.cot]; ++w.cot; }
+  w.s0 = rem * p.tile_steps[w.cot];
+  w.s1 = min(p.total_steps, w.s0 + p.tile_steps[w.cot]);
+  return w;
+}
 
 struct WgPipe {
   uint64_t full[kWgStages];
@@ -662,23 +678,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_base = pipe->tmem_base;
-  const int num_items = p.taps * p.co_tiles * p.ci_tiles * p.num_splits;
+  const int num_items = p.taps * p.ci_tiles * p.splits_sum;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-        int rem = item;
-        const int split = rem % p.num_splits; rem /= p.num_splits;
-        const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-        const int cot = rem % p.co_tiles; rem /= p.co_tiles;
-        const int t = rem;
+        const WgItem wi = wg_decode(p, item);
+        const int cit = wi.cit, cot = wi.cot, t = wi.t;
         const int a_groups = (p.ngroups - cot * 4) > 2 ? 4 : 2;
         const uint32_t stage_tx = (uint32_t)(a_groups + p.ci_groups) * 8192u;
         const int tm = p.tap_map[t];
         const CUtensorMap* mX = tm == 0 ? &mapX0 : (tm == 1 ? &mapX1 : (tm == 2 ? &mapX2 : &mapX3));
-        const int s0 = split * p.steps_per_split;
-        const int s1 = min(p.total_steps, s0 + p.steps_per_split);
+        const int s0 = wi.s0, s1 = wi.s1;
         // A-operand groups of this item (hoisted out of the k loop: the producer is a single latency-bound thread);
         // a group past the last one reads at a channel coordinate outside every map => TMA zero fill
         const CUtensorMap* gmap[4];
@@ -726,15 +738,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
     const uint32_t s_ones = smem_u32(ones);
     int stage = 0; uint32_t phase = 0; uint32_t tphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int rem = item;
-      const int split = rem % p.num_splits; rem /= p.num_splits;
-      const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-      const int cot = rem % p.co_tiles; rem /= p.co_tiles;
-      const int t = rem;
+      const WgItem wi = wg_decode(p, item);
+      const int cit = wi.cit, cot = wi.cot, t = wi.t;
       const bool two = (p.ngroups - cot * 4) > 2;
       const bool want_shift = p.any_dshift != 0 && t == 0 && cit == 0;
-      const int s0 = split * p.steps_per_split;
-      const int s1 = min(p.total_steps, s0 + p.steps_per_split);
+      const int s0 = wi.s0, s1 = wi.s1;
       mbar_wait(&pipe->tmem_empty, tphase ^ 1);
       tc_fence_after();
       for (int s = s0; s < s1; ++s) {
@@ -769,11 +777,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
     const int q = warp & 3;
     uint32_t tphase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
-      int rem = item;
-      rem /= p.num_splits;
-      const int cit = rem % p.ci_tiles; rem /= p.ci_tiles;
-      const int cot = rem % p.co_tiles; rem /= p.co_tiles;
-      const int t = rem;
+      const WgItem wi = wg_decode(p, item);
+      const int cit = wi.cit, cot = wi.cot, t = wi.t;
       const bool two = (p.ngroups - cot * 4) > 2;
       const bool want_shift = p.any_dshift != 0 && t == 0 && cit == 0;
       mbar_wait(&pipe->tmem_full, tphase);
