@@ -303,8 +303,9 @@ def main():
       ex = {F.features_to_crop: p['fmap'].to(dev, non_blocking=True),
             F.proposals: p['proposals'].to(dev, non_blocking=True),
             F.num_proposals: p['num_proposals'].to(dev, non_blocking=True), F.concat_caption_string: p['captions']}
-      if graphed is not None:
-        ex['_labels'] = graphed.extract_labels(ex)
+      # image-level labels (host tokenisation + a small kernel) are prepared with the batch, one step ahead, as a
+      # data loader would; Model.build_loss takes them from the example dict
+      ex['_labels'] = model._label_extractor.extract_labels(ex)
       ev = torch.cuda.Event()
       ev.record(copy_stream)
     staged[i] = (ex, ev)
