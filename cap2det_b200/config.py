@@ -262,8 +262,57 @@ class TrainConfig(Message):
             'log_step_count_steps': ('int', 2000)}
 
 
+# ---- protos/image_resizer.proto, protos/preprocess.proto, protos/reader.proto -----------------------
+class DefaultResizer(Message):
+  FIELDS = {}
+
+
+class FixedShapeResizer(Message):
+  FIELDS = {'height': ('int', 300), 'width': ('int', 300)}
+
+
+class KeepAspectRatioResizer(Message):
+  FIELDS = {'min_dimension': ('int', 600)}
+
+
+class ImageResizer(Message):
+  """protos/image_resizer.proto:3-10 (random_scale_resizer is commented out in core/builder.py:113-126 and
+  is rejected there; it parses and is rejected here as well)."""
+  FIELDS = {'default_resizer': (DefaultResizer, None), 'fixed_shape_resizer': (FixedShapeResizer, None),
+            'keep_aspect_ratio_resizer': (KeepAspectRatioResizer, None)}
+  ONEOFS = {'image_resizer_oneof': ['default_resizer', 'fixed_shape_resizer', 'keep_aspect_ratio_resizer']}
+
+
+class Preprocess(Message):
+  """protos/preprocess.proto:3-5: the one field readers/cap2det_reader.py uses (preprocess_image_v2)."""
+  FIELDS = {'random_flip_left_right_prob': ('float', 0.0)}
+
+
+class Cap2DetReader(Message):
+  """protos/reader.proto:12-52."""
+  FIELDS = {'input_pattern': (['string'], None), 'interleave_cycle_length': ('int', 2),
+            'is_training': ('bool', False), 'shuffle_buffer_size': ('int', 1000),
+            'map_num_parallel_calls': ('int', 1), 'prefetch_buffer_size': ('int', 200),
+            'batch_size': ('int', 32), 'decode_image': ('bool', True), 'image_resizer': (ImageResizer, None),
+            'preprocess_options': (Preprocess, None), 'max_num_proposals': ('int', 500),
+            'batch_resize_scale_value': (['float'], None), 'shard_indicator': ('string', '')}
+
+
+class Reader(Message):
+  """protos/reader.proto:6-10."""
+  FIELDS = {'cap2det_reader': (Cap2DetReader, None)}
+  ONEOFS = {'reader_oneof': ['cap2det_reader']}
+
+
+class EvalConfig(Message):
+  """protos/pipeline.proto:27-38."""
+  FIELDS = {'steps': ('int', 0), 'start_delay_secs': ('int', 60), 'throttle_secs': ('int', 120)}
+
+
 class Pipeline(Message):
-  FIELDS = {'model': (Model, None), 'train_config': (TrainConfig, None)}
+  """protos/pipeline.proto:7-25."""
+  FIELDS = {'train_reader': (Reader, None), 'eval_reader': (Reader, None), 'model': (Model, None),
+            'model_dir': ('string', ''), 'train_config': (TrainConfig, None), 'eval_config': (EvalConfig, None)}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -17,8 +17,10 @@ from cap2det_b200 import ops
 from cap2det_b200.standard_fields import InputDataFields as F
 
 
-def parse_example(example, max_num_proposals, flip_left_right=False, device='cuda'):
-  """:104-140: truncate proposals to max_num_proposals, optional left-right flip of image and boxes."""
+def parse_example(example, max_num_proposals, flip_left_right=False, device='cuda', resize_fn=None):
+  """:85-140: optional left-right flip of image and boxes, per-image resize (``resize_fn`` from
+  imgproc.build_image_resizer; image_height / image_width stay the pre-resize size, image_shape is the resized
+  one, :93-101), proposals truncated to max_num_proposals."""
   out = dict(example)
   image = torch.as_tensor(example[F.image]).to(device)
   proposals = torch.as_tensor(np.asarray(example[F.proposals], np.float32)[:max_num_proposals]).to(device)
@@ -28,7 +30,10 @@ def parse_example(example, max_num_proposals, flip_left_right=False, device='cud
     proposals = box_utils.flip_left_right(proposals) if proposals.numel() else proposals
     objects = box_utils.flip_left_right(objects) if objects.numel() else objects
   h, w, c = image.shape
-  out.update({F.image: image, F.image_height: h, F.image_width: w, F.image_shape: [h, w, c],
+  shape = [h, w, c]
+  if resize_fn is not None:
+    image, shape = resize_fn(image)
+  out.update({F.image: image, F.image_height: h, F.image_width: w, F.image_shape: [int(v) for v in shape],
               F.proposals: proposals, F.num_proposals: int(proposals.shape[0]),
               F.object_boxes: objects, F.num_objects: int(objects.shape[0])})
   return out
@@ -104,13 +109,111 @@ def batch_scale_box_fn(examples):
   return out
 
 
+_U64 = (1 << 64) - 1
+
+
+def hash64(data, seed=0xDECAFCAFFE):
+  """``tensorflow::Hash64`` (core/lib/hash/hash.cc): the 64-bit Murmur-style hash behind the legacy
+  ``StringToHashBucket`` op, i.e. ``tf.strings.to_hash_bucket`` as called at readers/cap2det_reader.py:210.
+  Little-endian 8-byte blocks, multiplier 0xc6a4a7935bd1e995, shift 47, the tail bytes folded in as one
+  little-endian integer.  Pinned on TensorFlow's documented example (tests/test_host_logic.py)."""
+  data = data.encode('utf-8') if isinstance(data, str) else bytes(data)
+  m, r, n = 0xc6a4a7935bd1e995, 47, len(data)
+  h = (seed ^ (n * m)) & _U64
+  full = n - n % 8
+  for i in range(0, full, 8):
+    k = (int.from_bytes(data[i:i + 8], 'little') * m) & _U64
+    k = ((k ^ (k >> r)) * m) & _U64
+    h = ((h ^ k) * m) & _U64
+  if n > full:
+    h = ((h ^ int.from_bytes(data[full:], 'little')) * m) & _U64
+  h = ((h ^ (h >> r)) * m) & _U64
+  return h ^ (h >> r)
+
+
+def to_hash_bucket(string, num_buckets):
+  return hash64(string) % int(num_buckets)
+
+
+def shard_filter(shard_indicator):
+  """_filter_fn (readers/cap2det_reader.py:201-211): 'numer/denom' -> predicate over examples that keeps the
+  images whose id hashes into bucket ``numer`` of ``denom``.  Same assertions as the reference."""
+  numer, denom = shard_indicator.split('/')
+  assert numer.isdigit() and denom.isdigit()
+  numer, denom = int(numer), int(denom)
+  assert 0 <= numer < denom
+  return lambda example: to_hash_bucket(example[F.image_id], denom) == numer
+
+
 def make_batch(raw_examples, max_num_proposals, batch_resize_scale_value=(), rng=None, flip_probability=0.0,
-               device='cuda'):
-  """_input_fn (:213-262) for in-memory examples: parse (+flip) -> padded_batch -> batch resize -> box rescale."""
+               device='cuda', resize_fn=None):
+  """_input_fn (:213-262) for in-memory examples: parse (+flip, +resize) -> padded_batch -> batch resize ->
+  box rescale."""
   rng = rng if rng is not None else np.random.default_rng()
-  parsed = [parse_example(e, max_num_proposals, flip_left_right=bool(rng.uniform() < flip_probability), device=device)
+  parsed = [parse_example(e, max_num_proposals, flip_left_right=bool(rng.uniform() < flip_probability), device=device,
+                          resize_fn=resize_fn)
             for e in raw_examples]
   batch = padded_batch(parsed, max_num_proposals)
   if len(batch_resize_scale_value) > 0:
     batch = batch_resize_image_fn(batch, batch_resize_scale_value, int(rng.integers(0, len(batch_resize_scale_value))))
   return batch_scale_box_fn(batch)
+
+
+def get_input_fn(options, device='cuda', seed=None):
+  """readers/cap2det_reader.py:16-264 (get_input_fn): Cap2DetReader options -> a function returning an iterator
+  of batches read from the TFRecord files of ``input_pattern``.
+
+  Order of the stages as in _input_fn: list files (shuffled when training) -> records -> parse -> shard filter ->
+  padded batches of ``batch_size`` (remainder dropped) -> batch resize -> box rescale.  Training repeats forever
+  and shuffles through a buffer of ``shuffle_buffer_size`` records; interleave / parallel-map / prefetch sizes
+  only affect scheduling in the reference and are not modelled."""
+  import glob
+  from cap2det_b200 import config, imgproc, tfrecord
+  if not isinstance(options, config.Cap2DetReader):
+    raise ValueError('options has to be an instance of Reader.')
+  if not options.decode_image:
+    raise ValueError('decode_image=false (text classifier training) is outside the detection path.')
+  resize_fn = imgproc.build_image_resizer(options.image_resizer)
+  keep = shard_filter(options.shard_indicator) if options.shard_indicator else None
+  flip = options.preprocess_options.random_flip_left_right_prob if options.HasField('preprocess_options') else 0.0
+
+  def _records(rng):
+    files = sorted(f for pattern in options.input_pattern for f in glob.glob(pattern))
+    if not files:
+      raise IOError('no file matches %r' % list(options.input_pattern))
+    while True:
+      if options.is_training:
+        files = [files[i] for i in rng.permutation(len(files))]
+      for path in files:
+        for record in tfrecord.read_records(path):
+          yield record
+      if not options.is_training:
+        return
+
+  def _shuffled(records, rng):
+    buf = []
+    for record in records:
+      buf.append(record)
+      if len(buf) >= options.shuffle_buffer_size:
+        yield buf.pop(int(rng.integers(0, len(buf))))
+    while buf:
+      yield buf.pop(int(rng.integers(0, len(buf))))
+
+  def _input_fn():
+    rng = np.random.default_rng(seed)
+    records = _records(rng)
+    if options.is_training:
+      records = _shuffled(records, rng)
+    pending = []
+    for record in records:
+      if keep is not None and not keep(tfrecord.decode_example(record, decode_image=False)):
+        continue                                           # skip the JPEG decode of other shards' images
+      example = tfrecord.decode_example(record)
+      pending.append(example)
+      if len(pending) == options.batch_size:
+        yield make_batch(pending, options.max_num_proposals,
+                         batch_resize_scale_value=list(options.batch_resize_scale_value), rng=rng,
+                         flip_probability=flip, device=device, resize_fn=resize_fn)
+        pending = []
+
+  return _input_fn

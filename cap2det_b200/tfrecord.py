@@ -212,7 +212,7 @@ def decode_jpeg(encoded):
   """tf.image.decode_jpeg(channels=3) -> uint8 [H, W, 3] (RGB)."""
   from PIL import Image
   with Image.open(io.BytesIO(encoded)) as im:
-    return np.asarray(im.convert('RGB'), np.uint8)
+    return np.array(im.convert('RGB'), np.uint8)           # own, writable buffer
 
 
 def decode_example(data, decode_image=True):

@@ -169,3 +169,75 @@ def test_tfrecord_to_training_step(tmp_path):
   model.raise_if_assert_failed()
   assert np.isfinite(float(total))
   assert model.last_labels.sum(dim=1).tolist() == [1.0, 1.0, 1.0]          # one ground-truth class per image
+
+
+def test_get_input_fn_reads_sharded_tfrecords(tmp_path):
+  """readers/cap2det_reader.py:16-264 end to end: Cap2DetReader options -> files -> shard filter -> per-image
+  resizer -> padded batches (remainder dropped) -> box rescale; training repeats and shuffles."""
+  import io
+  import itertools
+  from PIL import Image
+  from cap2det_b200 import config, imgproc, reader, tfrecord
+  from cap2det_b200.standard_fields import InputDataFields as F
+  from oracle import image as oi
+  rng = np.random.default_rng(21)
+  ids, decoded = [], {}
+  for f in range(2):
+    records = []
+    for i in range(5):
+      h, w, n = int(rng.integers(40, 90)), int(rng.integers(40, 90)), int(rng.integers(3, 9))
+      buf = io.BytesIO()
+      Image.fromarray(rng.integers(0, 256, size=(h, w, 3)).astype(np.uint8)).save(buf, format='JPEG')
+      props = np.sort(rng.uniform(0, 1, size=(n, 2, 2)), axis=1).reshape(n, 4).astype(np.float32)
+      image_id = '%06d.jpg' % (5 * f + i)
+      ex = {'image/source_id': [image_id.encode()], 'image/encoded': [buf.getvalue()],
+            'image/caption/string': ['a', 'dog'], 'image/caption/offset': [0], 'image/caption/length': [2],
+            'image/object/class/text': ['dog'], 'image/object/bbox/ymin': [0.1], 'image/object/bbox/xmin': [0.1],
+            'image/object/bbox/ymax': [0.9], 'image/object/bbox/xmax': [0.8]}
+      for j, k in enumerate(('ymin', 'xmin', 'ymax', 'xmax')):
+        ex['image/proposal/bbox/' + k] = props[:, j]
+      records.append(tfrecord.encode_example(ex))
+      ids.append(image_id)
+      decoded[image_id] = (tfrecord.decode_jpeg(buf.getvalue()), props)
+    tfrecord.write_records(str(tmp_path / ('val.record-%05d-of-00002' % f)), records)
+
+  text = '''input_pattern: "%s/val.record*"  batch_size: 2  max_num_proposals: 6  shard_indicator: "%%d/2"
+            image_resizer { keep_aspect_ratio_resizer { min_dimension: 64 } }''' % tmp_path
+  seen = []
+  for k in range(2):
+    options = config.parse_text(text % k, config.Cap2DetReader)
+    mine = [i for i in ids if reader.to_hash_bucket(i, 2) == k]
+    batches = list(reader.get_input_fn(options)())
+    assert len(batches) == len(mine) // 2                                  # drop_remainder=True
+    got = sum((b[F.image_id] for b in batches), [])
+    assert got == mine[:len(got)]                                          # file order, only this shard
+    seen += got
+    for b in batches:
+      pad_h, pad_w = b[F.image].shape[1:3]
+      for j, image_id in enumerate(b[F.image_id]):
+        img, props = decoded[image_id]
+        h, w = img.shape[:2]
+        nh, nw = imgproc.compute_new_size(h, w, 64)
+        assert min(nh, nw) == 64
+        assert b[F.image_height][j].item() == h and b[F.image_width][j].item() == w      # pre-resize size (:93-101)
+        assert b[F.image_shape][j].tolist() == [nh, nw, 3]
+        np.testing.assert_array_equal(b[F.image][j, :nh, :nw].cpu().numpy(), oi.resize_bilinear(img[None], nh, nw)[0])
+        assert float(b[F.image][j, nh:].abs().sum()) == 0 and float(b[F.image][j, :, nw:].abs().sum()) == 0
+        n = min(len(props), 6)
+        assert b[F.num_proposals][j].item() == n
+        want = oi.batch_scale_box(props[None, :n], np.array([[nh, nw, 3]], np.int32), pad_h, pad_w)[0]
+        np.testing.assert_array_equal(b[F.proposals][j, :n].cpu().numpy(), want)
+  assert len(set(seen)) == len(seen)
+
+  train = config.parse_text('''input_pattern: "%s/val.record*"  batch_size: 3  max_num_proposals: 6  is_training: true
+      shuffle_buffer_size: 4  preprocess_options { random_flip_left_right_prob: 0.5 }
+      image_resizer { fixed_shape_resizer { height: 48 width: 80 } }
+      batch_resize_scale_value: 1.2 batch_resize_scale_value: 0.5''' % tmp_path, config.Cap2DetReader)
+  batches = list(itertools.islice(reader.get_input_fn(train, seed=3)(), 9))          # 27 examples > 10: repeats
+  assert len(batches) == 9
+  assert {tuple(b[F.image].shape[1:3]) for b in batches} <= {(58, 96), (24, 40)}
+  assert len({i for b in batches for i in b[F.image_id]}) == 10
+  assert [b[F.image_id] for b in batches] == [b[F.image_id] for b in
+                                              itertools.islice(reader.get_input_fn(train, seed=3)(), 9)]
+  with pytest.raises(ValueError, match='Invalid resizer'):
+    reader.get_input_fn(config.parse_text('input_pattern: "x"', config.Cap2DetReader))

@@ -321,3 +321,140 @@ def test_pascal_evaluator_add_batch_from_prediction_dict():
   assert m1['PascalBoxes_PerformanceByCategory/AP@0.5IOU/cat'] == 0.0
   # dog detections by score: 0.9 on the cat box of image x (fp), 0.8 on the dog (tp), 0.7 on the cat of image y (fp)
   assert m1['PascalBoxes_PerformanceByCategory/AP@0.5IOU/dog'] == pytest.approx(0.5)
+
+
+# ---- COCO metric (train/predict.py:570-573; pycocotools COCOeval restated, parity unpinned) --------------------
+def _coco_names():
+  from cap2det_b200 import evaluation
+  return ['DetectionBoxes_' + n for n in evaluation.CocoDetectionEvaluator.METRICS]
+
+
+def test_coco_evaluator_perfect_detections():
+  import numpy as np
+  from cap2det_b200 import evaluation
+  ev = evaluation.CocoDetectionEvaluator([{'id': 1, 'name': 'cat'}, {'id': 2, 'name': 'dog'}, {'id': 3, 'name': 'bird'}])
+  medium, large = [10., 10., 60., 60.], [0., 0., 100., 100.]               # areas 2500 and 10000
+  ev.add_single_ground_truth_image_info('a', {'groundtruth_boxes': np.array([medium]), 'groundtruth_classes': np.array([1])})
+  ev.add_single_detected_image_info('a', {'detection_boxes': np.array([medium]), 'detection_scores': np.array([0.9]),
+                                          'detection_classes': np.array([1])})
+  ev.add_single_ground_truth_image_info('b', {'groundtruth_boxes': np.array([large, medium]),
+                                              'groundtruth_classes': np.array([1, 2])})
+  ev.add_single_detected_image_info('b', {'detection_boxes': np.array([medium, large]),
+                                          'detection_scores': np.array([0.5, 0.7]), 'detection_classes': np.array([2, 1])})
+  m = ev.evaluate()
+  assert list(m) == _coco_names()
+  for name, v in m.items():
+    assert v == pytest.approx(-1.0 if '(small)' in name else 1.0), name
+  with pytest.raises(ValueError, match='Missing groundtruth'):
+    ev.add_single_detected_image_info('zzz', {'detection_boxes': np.zeros((0, 4)), 'detection_scores': np.zeros(0),
+                                              'detection_classes': np.zeros(0)})
+  ev.clear()
+  ev.add_single_ground_truth_image_info('a', {'groundtruth_boxes': np.array([medium]), 'groundtruth_classes': np.array([1])})
+  m = ev.evaluate()                                                          # ground truth, no detections at all
+  assert m['DetectionBoxes_Precision/mAP'] == 0.0 and m['DetectionBoxes_Recall/AR@100'] == 0.0
+
+
+def test_coco_evaluator_hand_computed_curve():
+  """Two large ground-truth boxes; detections: exact hit (0.9), miss (0.8), IoU-0.62 hit (0.7).  At IoU thresholds
+  .50/.55/.60 the third detection is a true positive: precision (1, 2/3, 2/3) at recall (.5, .5, 1) -> 51 recall
+  thresholds at 1 and 50 at 2/3; at the other seven it is a false positive -> 51 thresholds at 1, the rest 0."""
+  import numpy as np
+  from cap2det_b200 import evaluation
+  ev = evaluation.CocoDetectionEvaluator([{'id': 1, 'name': 'cat'}], include_metrics_per_category=True)
+  A, B = [0., 0., 100., 100.], [200., 200., 300., 300.]
+  ev.add_single_ground_truth_image_info(7, {'groundtruth_boxes': np.array([A, B]), 'groundtruth_classes': np.array([1, 1])})
+  ev.add_single_detected_image_info(7, {
+      'detection_boxes': np.array([[200., 200., 300., 262.], A, [500., 500., 600., 600.]]),
+      'detection_scores': np.array([0.7, 0.9, 0.8]), 'detection_classes': np.array([1, 1, 1])})
+  m = ev.evaluate()
+  lo, hi = (51 + 50 * 2 / 3) / 101, 51 / 101
+  assert m['DetectionBoxes_Precision/mAP@.50IOU'] == pytest.approx(lo)
+  assert m['DetectionBoxes_Precision/mAP@.75IOU'] == pytest.approx(hi)
+  assert m['DetectionBoxes_Precision/mAP'] == pytest.approx((3 * lo + 7 * hi) / 10)
+  assert m['DetectionBoxes_PerformanceByCategory/mAP/cat'] == pytest.approx((3 * lo + 7 * hi) / 10)
+  # 'large': the 6200-pixel detection is outside the range -> ignored where unmatched, counted where matched
+  assert m['DetectionBoxes_Precision/mAP (large)'] == pytest.approx((3 * lo + 7 * hi) / 10)
+  assert m['DetectionBoxes_Precision/mAP (medium)'] == -1.0 and m['DetectionBoxes_Precision/mAP (small)'] == -1.0
+  assert m['DetectionBoxes_Recall/AR@1'] == pytest.approx(0.5)
+  assert m['DetectionBoxes_Recall/AR@10'] == pytest.approx(0.65)
+  assert m['DetectionBoxes_Recall/AR@100'] == pytest.approx(0.65)
+  assert m['DetectionBoxes_Recall/AR@100 (large)'] == pytest.approx(0.65)
+
+
+def test_coco_evaluator_crowd_and_area_ranges():
+  import numpy as np
+  from cap2det_b200 import evaluation
+  ev = evaluation.CocoDetectionEvaluator([{'id': 1, 'name': 'cat'}, {'id': 2, 'name': 'dog'}])
+  crowd, regular = [0., 0., 200., 200.], [300., 300., 320., 320.]            # regular: 400 px = small
+  ev.add_single_ground_truth_image_info('x', {
+      'groundtruth_boxes': np.array([crowd, regular, crowd]), 'groundtruth_classes': np.array([1, 1, 2]),
+      'groundtruth_is_crowd': np.array([True, False, True])})
+  ev.add_single_detected_image_info('x', {
+      # two detections inside the crowd region (both absorbed by it, not false positives), one on the small box
+      'detection_boxes': np.array([[10., 10., 60., 60.], [100., 100., 150., 150.], regular, [20., 20., 80., 80.]]),
+      'detection_scores': np.array([0.95, 0.9, 0.5, 0.99]), 'detection_classes': np.array([1, 1, 1, 2])})
+  m = ev.evaluate()
+  assert m['DetectionBoxes_Precision/mAP'] == pytest.approx(1.0)             # class 2 has only crowd ground truth: skipped
+  assert m['DetectionBoxes_Precision/mAP (small)'] == pytest.approx(1.0)
+  assert m['DetectionBoxes_Precision/mAP (medium)'] == -1.0
+  assert m['DetectionBoxes_Recall/AR@1'] == pytest.approx(0.0)               # the top-scoring detection is a crowd match
+  assert m['DetectionBoxes_Recall/AR@10'] == pytest.approx(1.0)
+
+
+def test_convert_coco_result_to_voc():
+  import numpy as np
+  from cap2det_b200 import evaluation
+  boxes = np.arange(16, dtype=np.float64).reshape(4, 4)
+  b, s, c = evaluation.convert_coco_result_to_voc(boxes, np.array([.9, .8, .7, .6]), np.array([1., 8., 63., 5.]))
+  np.testing.assert_array_equal(b, boxes[[0, 2, 3]])
+  assert s.tolist() == [.9, .7, .6] and c.tolist() == [15, 20, 1]              # person, tvmonitor, aeroplane
+  b, s, c = evaluation.convert_coco_result_to_voc(boxes[:1], np.array([.9]), np.array([8.]))
+  assert b.shape == (0, 4) and s.shape == (0,) and c.dtype == np.int64
+  assert len(evaluation.COCO_TO_VOC) == 20 and sorted(evaluation.COCO_TO_VOC.values()) == list(range(1, 21))
+
+
+# ---- shard filter (readers/cap2det_reader.py:201-211) and reader options ---------------------------------------
+def test_to_hash_bucket_matches_tensorflow_documented_values():
+  """The example in the TensorFlow documentation of tf.strings.to_hash_bucket:
+  to_hash_bucket(["Hello", "TensorFlow", "2.x"], 3) == [2, 0, 1]."""
+  from cap2det_b200 import reader
+  assert [reader.to_hash_bucket(s, 3) for s in ('Hello', 'TensorFlow', '2.x')] == [2, 0, 1]
+  assert reader.hash64(b'') == reader.hash64('') and 0 <= reader.hash64('x' * 23) < 1 << 64
+
+
+def test_shard_filter_partitions_the_image_ids():
+  from cap2det_b200 import reader
+  from cap2det_b200.standard_fields import InputDataFields as F
+  ids = ['%06d.jpg' % i for i in range(500)]
+  shards = [[i for i in ids if reader.shard_filter('%d/3' % k)({F.image_id: i})] for k in range(3)]
+  assert sorted(sum(shards, [])) == ids and all(len(s) > 100 for s in shards)
+  for bad in ('3/3', 'a/3', '1/b'):
+    with pytest.raises(AssertionError):
+      reader.shard_filter(bad)
+
+
+def test_pipeline_reader_options_parse_like_the_reference_configs():
+  from cap2det_b200 import config
+  text = '''
+    train_reader { cap2det_reader {
+      input_pattern: "output/coco17_train.record*"  interleave_cycle_length: 1  is_training: true
+      shuffle_buffer_size: 2000  batch_size: 2
+      image_resizer { keep_aspect_ratio_resizer { min_dimension: 1000 } }
+      preprocess_options { random_flip_left_right_prob: 0.5 }
+      max_num_proposals: 500  batch_resize_scale_value: 1.2  batch_resize_scale_value: 0.8 } }
+    eval_reader { cap2det_reader { input_pattern: "output/coco17_val.record*"  batch_size: 1  shard_indicator: "1/4"
+      image_resizer { fixed_shape_resizer { height: 448 } } } }
+    model_dir: "logs/x"
+    eval_config { steps: 500 }'''
+  p = config.parse_text(text, config.Pipeline)
+  r = p.train_reader.cap2det_reader
+  assert p.train_reader.WhichOneof('reader_oneof') == 'cap2det_reader'
+  assert list(r.input_pattern) == ['output/coco17_train.record*'] and r.is_training and r.batch_size == 2
+  assert r.image_resizer.WhichOneof('image_resizer_oneof') == 'keep_aspect_ratio_resizer'
+  assert r.image_resizer.keep_aspect_ratio_resizer.min_dimension == 1000
+  assert r.HasField('preprocess_options') and r.preprocess_options.random_flip_left_right_prob == 0.5
+  assert list(r.batch_resize_scale_value) == [1.2, 0.8] and r.decode_image and r.prefetch_buffer_size == 200
+  e = p.eval_reader.cap2det_reader
+  assert e.shard_indicator == '1/4' and not e.HasField('preprocess_options') and not e.is_training
+  assert e.image_resizer.fixed_shape_resizer.height == 448 and e.image_resizer.fixed_shape_resizer.width == 300
+  assert p.model_dir == 'logs/x' and p.eval_config.steps == 500 and p.eval_config.throttle_secs == 120
