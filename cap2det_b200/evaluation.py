@@ -341,3 +341,72 @@ def add_batch(evaluators, examples, predictions, category_to_id, eval_coco_on_vo
         det_boxes, det_scores, det_classes = convert_coco_result_to_voc(det_boxes, det_scores, det_classes)
       evaluator.add_single_detected_image_info(image_id, {
           'detection_boxes': det_boxes, 'detection_scores': det_scores, 'detection_classes': det_classes})
+
+
+def build_evaluators(evaluator, label_file_lines, number_of_evaluators=1):
+  """train/predict.py:550-575: category list (1-based ids in label-file order) and one evaluator per OICR stage.
+  Returns (evaluators, categories, category_to_id)."""
+  names = [line.strip('\n') for line in label_file_lines]
+  categories = [{'id': 1 + i, 'name': n} for i, n in enumerate(names)]
+  category_to_id = {n: 1 + i for i, n in enumerate(names)}
+  n = max(1, int(number_of_evaluators))
+  if evaluator.lower() == 'pascal':
+    return [PascalDetectionEvaluator(categories) for _ in range(n)], categories, category_to_id
+  if evaluator.lower() == 'coco':
+    return [CocoDetectionEvaluator(categories) for _ in range(n)], categories, category_to_id
+  raise ValueError('Invalid evaluator {}.'.format(evaluator))
+
+
+def detection_results(image_id, boxes_abs, scores, classes, class_labels):
+  """train/predict.py:462-478: one image's detections as COCO result records (integer-truncated pixel corners,
+  [x, y, w, h], score rounded to 5 digits, category = the label-file name of the 1-based class)."""
+  out = []
+  for (ymin, xmin, ymax, xmax), score, cls in zip(boxes_abs, scores, classes):
+    ymin, xmin, ymax, xmax = int(ymin), int(xmin), int(ymax), int(xmax)
+    out.append({'image_id': int(image_id), 'category_id': class_labels[int(cls - 1)],
+                'bbox': [xmin, ymin, xmax - xmin, ymax - ymin], 'score': round(float(score), 5)})
+  return out
+
+
+def run_evaluation(model, batches, evaluators, category_to_id, max_eval_examples=None, eval_coco_on_voc=False,
+                   detection_result_dir=None):
+  """train/predict.py:328-531 (_run_evaluation) without the visualisation / summary side: every batch of
+  ``batches`` goes through ``model.build_prediction``, evaluator i scores the detections of OICR stage i, all
+  evaluators are evaluated and cleared.  Returns (list of metric dicts, one per stage; headline) where the
+  headline is the last stage's 'PascalBoxes_Precision/mAP@0.5IOU', else 'DetectionBoxes_Precision/mAP' (:529-531).
+  Like the reference, ``max_eval_examples`` is checked after a whole batch.  ``detection_result_dir`` receives
+  '<image_id>.json' per image for the LAST stage (the loop variable the reference's writer reads, :462-485)."""
+  import json
+  import os
+  eval_count = 0
+  last = len(evaluators) - 1
+
+  def host(x):
+    return x.detach().cpu().numpy() if hasattr(x, 'detach') else np.asarray(x)
+  for examples in batches:
+    predictions = model.build_prediction(examples)
+    add_batch(evaluators, examples, predictions, category_to_id, eval_coco_on_voc=eval_coco_on_voc)
+    batch_size = len(examples[InputDataFields.image_id])
+    if detection_result_dir:
+      class_labels = list(predictions[DetectionResultFields.class_labels])
+      heights, widths = host(examples[InputDataFields.image_height]), host(examples[InputDataFields.image_width])
+      for b, image_id in enumerate(examples[InputDataFields.image_id]):
+        nd = int(host(predictions[DetectionResultFields.num_detections + '_at_%d' % last])[b])
+        boxes = box_utils.py_coord_norm_to_abs(
+            host(predictions[DetectionResultFields.detection_boxes + '_at_%d' % last])[b, :nd], heights[b], widths[b])
+        results = detection_results(
+            image_id, boxes, host(predictions[DetectionResultFields.detection_scores + '_at_%d' % last])[b, :nd],
+            host(predictions[DetectionResultFields.detection_classes + '_at_%d' % last])[b, :nd], class_labels)
+        with open(os.path.join(detection_result_dir, '{}.json'.format(int(image_id))), 'w') as fid:
+          fid.write(json.dumps(results, indent=2))
+    eval_count += batch_size
+    if max_eval_examples is not None and eval_count > max_eval_examples:
+      break
+  all_metrics = []
+  for evaluator in evaluators:
+    all_metrics.append(evaluator.evaluate())
+    evaluator.clear()
+  metrics = all_metrics[-1]
+  if 'PascalBoxes_Precision/mAP@0.5IOU' in metrics:
+    return all_metrics, metrics['PascalBoxes_Precision/mAP@0.5IOU']
+  return all_metrics, metrics['DetectionBoxes_Precision/mAP']

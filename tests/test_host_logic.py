@@ -458,3 +458,40 @@ def test_pipeline_reader_options_parse_like_the_reference_configs():
   assert e.shard_indicator == '1/4' and not e.HasField('preprocess_options') and not e.is_training
   assert e.image_resizer.fixed_shape_resizer.height == 448 and e.image_resizer.fixed_shape_resizer.width == 300
   assert p.model_dir == 'logs/x' and p.eval_config.steps == 500 and p.eval_config.throttle_secs == 120
+
+
+def test_run_evaluation_loop_with_a_stub_model(tmp_path):
+  """train/predict.py:328-531: batches -> build_prediction -> one evaluator per OICR stage -> headline metric of the
+  last stage; detection files in COCO result format for the last stage."""
+  import json
+  import numpy as np
+  from cap2det_b200 import evaluation
+  from cap2det_b200.standard_fields import InputDataFields as F
+  evs, cats, category_to_id = evaluation.build_evaluators('pascal', ['cat\n', 'dog\n'], number_of_evaluators=2)
+  assert cats == [{'id': 1, 'name': 'cat'}, {'id': 2, 'name': 'dog'}] and category_to_id == {'cat': 1, 'dog': 2}
+  assert isinstance(evaluation.build_evaluators('COCO', ['a'])[0][0], evaluation.CocoDetectionEvaluator)
+  with pytest.raises(ValueError, match='Invalid evaluator'):
+    evaluation.build_evaluators('kitti', ['a'])
+
+  class Stub(object):
+    def build_prediction(self, examples):
+      B = len(examples[F.image_id])
+      pred = {'class_labels': ['cat', 'dog']}
+      for i in range(2):
+        pred['num_detections_at_%d' % i] = np.full([B], 1)
+        pred['detection_boxes_at_%d' % i] = examples[F.object_boxes][:, :1]          # the ground-truth box itself
+        pred['detection_scores_at_%d' % i] = np.full([B, 1], 0.123456789, np.float32)
+        pred['detection_classes_at_%d' % i] = np.full([B, 1], 1.0 if i == 1 else 2.0, np.float32)
+      return pred
+
+  def batch(ids):
+    return {F.image_id: ids, F.image_height: np.array([100] * len(ids)), F.image_width: np.array([200] * len(ids)),
+            F.num_objects: np.array([1] * len(ids)), F.object_texts: [['cat']] * len(ids),
+            F.object_boxes: np.tile(np.array([[[0.105, 0.1, 0.5, 0.5]]], np.float32), (len(ids), 1, 1))}
+  per_stage, headline = evaluation.run_evaluation(Stub(), [batch(['1', '2']), batch(['3', '4']), batch(['5', '6'])], evs,
+                                                  category_to_id, max_eval_examples=3, detection_result_dir=str(tmp_path))
+  assert headline == pytest.approx(1.0) and per_stage[0]['PascalBoxes_Precision/mAP@0.5IOU'] == 0.0
+  assert sorted(p.name for p in tmp_path.iterdir()) == ['1.json', '2.json', '3.json', '4.json']   # stopped after 4 > 3
+  rec = json.loads((tmp_path / '3.json').read_text())
+  assert rec == [{'image_id': 3, 'category_id': 'cat', 'bbox': [20, 10, 80, 40], 'score': 0.12346}]
+  assert np.isnan(evs[1].evaluate()['PascalBoxes_Precision/mAP@0.5IOU'])             # evaluators were cleared
