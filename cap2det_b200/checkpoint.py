@@ -1,0 +1,117 @@
+"""Variable exchange and resume for the path's variables (train/trainer.py:147-171 restores
+``first_stage_feature_extraction/*`` and ``second_stage_feature_extraction/*`` from the ImageNet checkpoint named
+by ``frcnn_options.checkpoint_path``; tf.estimator saves / restores everything else).
+
+TensorFlow's checkpoint files cannot be read without TensorFlow, so the container format here is NumPy ``.npz``
+keyed by the reference's variable names IN TF LAYOUTS, i.e. what
+
+    reader = tf.train.load_checkpoint(path)
+    np.savez(out, **{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()})
+
+writes: conv ``weights`` HWIO ``[k,k,in,out]``, ``depthwise_weights`` ``[7,7,3,8]``, ``pointwise_weights``
+``[1,1,24,64]``, FC ``weights`` ``[in,out]``, everything else 1-D.  The packed CUDA buffers keep OHWI / ``[out,in]``
+(INTEGRATION.md); the transposes happen here.  Optimizer slots use TF's slot naming ``<variable>/Adagrad``.
+"""
+import numpy as np
+import torch
+
+GLOBAL_STEP = 'global_step'
+_SLOT = '/Adagrad'
+
+
+def _to_tf(name, t):
+  """Packed-buffer view -> TF layout (torch tensor, not necessarily contiguous)."""
+  if name.endswith('/pointwise_weights'):
+    return t.t().reshape(1, 1, t.shape[1], t.shape[0])
+  if name.endswith('/weights'):
+    return t.permute(1, 2, 3, 0) if t.dim() == 4 else t.t()
+  return t
+
+
+def _from_tf(name, a, like):
+  """TF-layout array -> tensor shaped like the packed-buffer view ``like``; raises on a shape mismatch."""
+  a = torch.as_tensor(np.asarray(a, np.float32))
+  want = tuple(_to_tf(name, like).shape)
+  if tuple(a.shape) != want:
+    raise ValueError('variable %s has shape %s in the checkpoint, the model expects %s' % (name, tuple(a.shape), want))
+  if name.endswith('/pointwise_weights'):
+    return a.reshape(a.shape[2], a.shape[3]).t()
+  if name.endswith('/weights'):
+    return a.permute(3, 0, 1, 2) if a.dim() == 4 else a.t()
+  return a
+
+
+def export_variables(model):
+  """{TF variable name: np.float32 array in TF layout} of every variable of the model."""
+  return {name: _to_tf(name, view).contiguous().cpu().numpy() for name, view in model.named_variables().items()}
+
+
+def import_variables(model, variables, include_scopes=None, strict=True):
+  """Copies ``variables`` (dict or path of an .npz, TF names and layouts) into the model's packed buffers.
+
+  ``include_scopes``: optional name prefixes to restore (the reference restores only the two feature-extractor
+  scopes from the ImageNet checkpoint, train/trainer.py:147-171).  ``strict``: every selected model variable
+  must be present.  Returns the list of restored names."""
+  if isinstance(variables, str):
+    with np.load(variables) as data:
+      variables = {k: data[k] for k in data.files}
+  restored, missing = [], []
+  with torch.no_grad():
+    for name, view in model.named_variables().items():
+      if include_scopes is not None and not any(name.startswith(s) for s in include_scopes):
+        continue
+      if name not in variables:
+        missing.append(name)
+        continue
+      view.copy_(_from_tf(name, variables[name], view).to(view.device))
+      restored.append(name)
+  if strict and missing:
+    raise KeyError('checkpoint lacks %d variable(s), first: %s' % (len(missing), missing[0]))
+  return restored
+
+
+def _slot_views(model, train_step):
+  """TF variable name -> view into the Adagrad accumulator of the packed buffer that holds the variable."""
+  buffers = model.get_variables_to_train()
+  accum = {id(v): a for v, a in zip(train_step.opt.variables, train_step.opt.accum)}
+  out = {}
+  for name, view in model.named_variables().items():
+    for b in buffers:
+      off = view.data_ptr() - b.data_ptr()
+      if 0 <= off < b.numel() * b.element_size() and id(b) in accum:
+        start = off // b.element_size()
+        out[name] = accum[id(b)].view(-1)[start:start + view.numel()].view(view.shape)
+        break
+  return out
+
+
+def _is_moving_stat(name):
+  return name.endswith('/moving_mean') or name.endswith('/moving_variance')
+
+
+def save_checkpoint(path, train_step):
+  """Variables + Adagrad accumulators (``<name>/Adagrad``) + ``global_step`` -> one .npz (resume point)."""
+  model = train_step.model
+  out = export_variables(model)
+  for name, view in _slot_views(model, train_step).items():
+    if not _is_moving_stat(name):                      # not trainable in TF: no slot
+      out[name + _SLOT] = _to_tf(name, view).contiguous().cpu().numpy()
+  out[GLOBAL_STEP] = np.asarray(train_step.global_step, np.int64)
+  path = path if path.endswith('.npz') else path + '.npz'
+  np.savez(path, **out)
+  return path
+
+
+def load_checkpoint(path, train_step, strict=True):
+  """Inverse of save_checkpoint: restores variables, accumulators (where present) and the global step."""
+  with np.load(path) as data:
+    variables = {k: data[k] for k in data.files}
+  model = train_step.model
+  restored = import_variables(model, variables, strict=strict)
+  with torch.no_grad():
+    for name, view in _slot_views(model, train_step).items():
+      if name + _SLOT in variables:
+        view.copy_(_from_tf(name, variables[name + _SLOT], view).to(view.device))
+  if GLOBAL_STEP in variables:
+    train_step.global_step = int(variables[GLOBAL_STEP])
+  return restored

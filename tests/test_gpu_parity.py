@@ -860,3 +860,42 @@ def test_edge_cases_empty_and_degenerate_inputs():
   np.testing.assert_array_equal(b.cpu().numpy(), b_o)
   np.testing.assert_array_equal(s.cpu().numpy(), s_o)
   np.testing.assert_array_equal(c.cpu().numpy(), c_o)
+
+
+def test_checkpoint_resume_continues_training_identically(tmp_path):
+  """Two steps, save, third step  ==  fresh model + load_checkpoint + third step (variables, Adagrad accumulators
+  and the decayed learning rate's global step all come back)."""
+  from cap2det_b200 import checkpoint, config, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  C, B, P = 20, 1, 16
+  extractor = ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes))
+  rng = np.random.default_rng(41)
+  fmap = synthetic.make_feature_map(rng, B, 128, 160)
+  batches = []
+  for _ in range(3):
+    batches.append({F.features_to_crop: dev(fmap), F.num_proposals: dev(np.array([P], np.int32)),
+                    F.proposals: dev(synthetic.make_proposals(rng, B, P, 128, 160)),
+                    F.object_texts: synthetic.make_object_texts(rng, B, classes),
+                    F.dropout_keep_mask: dev((rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32))})
+  tc = config.parse_text('''learning_rate: 0.05  optimizer { adagrad { } }
+      learning_rate_decay { decay_steps: 1 decay_rate: 0.5 staircase: true }''', config.TrainConfig)
+  model = _build_model(C, extractor)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+  step = trainer.TrainStep(model, train_config=tc)
+  step(batches[0]); step(batches[1])
+  path = checkpoint.save_checkpoint(str(tmp_path / 'model.ckpt-2'), step)
+  loss3 = float(step(batches[2]))
+
+  other = _build_model(C, extractor)
+  resumed = trainer.TrainStep(other, train_config=tc)
+  checkpoint.load_checkpoint(path, resumed)
+  assert resumed.global_step == 2 and resumed.learning_rate() == pytest.approx(0.05 * 0.25)
+  loss3_resumed = float(resumed(batches[2]))
+  assert abs(loss3 - loss3_resumed) <= 1e-5 * abs(loss3)
+  for va, vb in zip(model.get_variables_to_train(), other.get_variables_to_train()):
+    assert rel_err(vb.detach().cpu().numpy(), va.detach().cpu().numpy()) < RTOL_F32
+  for aa, ab in zip(step.opt.accum, resumed.opt.accum):
+    assert rel_err(ab.cpu().numpy(), aa.cpu().numpy()) < RTOL_F32

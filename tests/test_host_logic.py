@@ -495,3 +495,96 @@ def test_run_evaluation_loop_with_a_stub_model(tmp_path):
   rec = json.loads((tmp_path / '3.json').read_text())
   assert rec == [{'image_id': 3, 'category_id': 'cat', 'bbox': [20, 10, 80, 40], 'score': 0.12346}]
   assert np.isnan(evs[1].evaluate()['PascalBoxes_Precision/mAP@0.5IOU'])             # evaluators were cleared
+
+
+# ---- variable exchange / resume (train/trainer.py:147-171; TF names and layouts in .npz) -----------------------
+def _cpu_model(seed, first_stage=True):
+  import tempfile
+  from cap2det_b200 import builder, config, synthetic
+  d = tempfile.mkdtemp()
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, synthetic.VOC_CLASSES))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  return builder.build(m, is_training=True, device='cpu', first_stage=first_stage, seed=seed)
+
+
+def test_checkpoint_variables_use_tf_names_and_layouts(tmp_path):
+  import numpy as np
+  import torch
+  from cap2det_b200 import checkpoint
+  a, b = _cpu_model(0), _cpu_model(1)
+  with torch.no_grad():
+    a.fc_weights.normal_(); a.fc_biases.normal_()
+  tf_vars = checkpoint.export_variables(a)
+  ours = a.named_variables()
+  n = 'second_stage_feature_extraction/InceptionV2/Mixed_5a/Branch_1/Conv2d_0b_3x3/weights'
+  assert tf_vars[n].shape == (3, 3, 192, 256)                                # HWIO
+  assert tf_vars[n][2, 0, 5, 7] == ours[n][7, 2, 0, 5].item()                # ours: OHWI
+  assert tf_vars['midn/proba_r_given_c/weights'].shape == (1024, 20)         # [in, out]
+  assert tf_vars['oicr/iter2/weights'].shape == (1024, 21) and tf_vars['oicr/iter2/biases'].shape == (21,)
+  assert tf_vars['midn/proba_r_given_c/weights'][3, 4] == ours['midn/proba_r_given_c/weights'][4, 3].item()
+  fs = 'first_stage_feature_extraction/InceptionV2/'
+  assert tf_vars[fs + 'Conv2d_1a_7x7/depthwise_weights'].shape == (7, 7, 3, 8)
+  assert tf_vars[fs + 'Conv2d_1a_7x7/pointwise_weights'].shape == (1, 1, 24, 64)
+  assert tf_vars[fs + 'Conv2d_1a_7x7/pointwise_weights'][0, 0, 5, 9] == ours[fs + 'Conv2d_1a_7x7/pointwise_weights'][9, 5].item()
+  assert tf_vars[fs + 'Mixed_4e/Branch_2/Conv2d_0c_3x3/BatchNorm/moving_variance'].shape == (192,)
+
+  path = str(tmp_path / 'vars.npz')
+  np.savez(path, **tf_vars)
+  before = {k: v.clone() for k, v in b.named_variables().items()}
+  # the reference's restore: feature extractors only (train/trainer.py:147-171)
+  got = checkpoint.import_variables(b, path, include_scopes=('first_stage_feature_extraction', 'second_stage_feature_extraction'))
+  assert len(got) == len([k for k in before if 'feature_extraction' in k]) and not any(k.startswith('midn') for k in got)
+  after = b.named_variables()
+  for k, v in a.named_variables().items():
+    if 'feature_extraction' in k:
+      assert torch.equal(after[k], v), k
+    else:
+      assert torch.equal(after[k], before[k]), k
+  checkpoint.import_variables(b, path)
+  for k, v in a.named_variables().items():
+    assert torch.equal(b.named_variables()[k], v), k
+  assert torch.equal(b.head_params, a.head_params) and torch.equal(b.backbone_params, a.backbone_params)
+
+  partial = {k: v for k, v in tf_vars.items() if not k.startswith('oicr/iter3')}
+  with pytest.raises(KeyError, match='lacks 2 variable'):
+    checkpoint.import_variables(b, partial)
+  assert len(checkpoint.import_variables(b, partial, strict=False)) == len(tf_vars) - 2
+  bad = dict(tf_vars)
+  bad[n] = np.transpose(bad[n], (3, 0, 1, 2))                                # OHWI handed in as if it were TF's
+  with pytest.raises(ValueError, match='has shape'):
+    checkpoint.import_variables(b, bad)
+
+
+def test_checkpoint_resume_restores_accumulators_and_step(tmp_path):
+  import numpy as np
+  import torch
+  from cap2det_b200 import checkpoint, trainer
+  a, b = _cpu_model(0, first_stage=False), _cpu_model(5, first_stage=False)
+  sa, sb = trainer.TrainStep(a, learning_rate=0.01), trainer.TrainStep(b, learning_rate=0.01)
+  gen = torch.Generator().manual_seed(3)
+  for acc in sa.opt.accum:
+    acc.copy_(torch.rand(acc.shape, generator=gen) + 0.1)
+  sa.global_step = 1234
+  path = checkpoint.save_checkpoint(str(tmp_path / 'model.ckpt-1234'), sa)
+  assert path.endswith('model.ckpt-1234.npz')
+  with np.load(path) as data:
+    assert int(data['global_step']) == 1234
+    assert data['oicr/iter1/weights/Adagrad'].shape == (1024, 21)            # TF slot naming and layout
+    assert not any(k.endswith('moving_mean/Adagrad') for k in data.files)    # not trainable: no slot in TF
+  checkpoint.load_checkpoint(path, sb)
+  assert sb.global_step == 1234
+  for va, vb in zip(a.get_variables_to_train(), b.get_variables_to_train()):
+    assert torch.equal(va, vb)
+  stats = torch.zeros_like(a.head_params, dtype=torch.bool)
+  for k, v in a.named_variables().items():
+    if k.endswith('/moving_mean') or k.endswith('/moving_variance'):
+      off = (v.data_ptr() - a.head_params.data_ptr()) // 4
+      stats[off:off + v.numel()] = True
+  for acc_a, acc_b, v in zip(sa.opt.accum, sb.opt.accum, a.get_variables_to_train()):
+    if v is a.head_params:
+      assert torch.equal(acc_a[~stats], acc_b[~stats])
+      assert bool((acc_b[stats] == 0.1).all())                               # untouched initial accumulator
+    else:
+      assert torch.equal(acc_a, acc_b)
