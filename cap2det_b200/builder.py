@@ -2,6 +2,7 @@
 from cap2det_b200 import config
 from cap2det_b200.registry import get_registered_model_classes
 import cap2det_b200.cap2det_model  # noqa: F401  (registers the class, models/builder.py:9)
+import cap2det_b200.text_model     # noqa: F401  (models/builder.py:10)
 
 
 def build(options, is_training=False, **model_kwargs):

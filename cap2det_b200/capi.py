@@ -33,6 +33,7 @@ SIGNATURES = {
     'c2d_box_flip_left_right': (_c_int, [_p, _c_int, _p, _p]),
     'c2d_box_scale_to_new_size': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p]),
     'c2d_masked_reduce': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p]),
+    'c2d_masked_max_bwd': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p, _p, _p]),
     'c2d_masked_softmax': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _p, _p]),
     'c2d_roi_crop_maxpool_fwd': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int,
                                           _c_int, _p, _c_int, _p]),

@@ -192,8 +192,14 @@ class Cap2DetModel(Message):
 
 
 # ---- protos/model.proto: a bag of extensions -----------------------------------------------------
+class TextModel(Message):
+  """protos/cap2det_model.proto:48-57: the caption classifier trained by models/text_model.py."""
+  ext = 'TextModel.ext'         # extension id on Model (field 1453)
+  FIELDS = {'label_extractor': (GroundtruthExtractor, None), 'text_classifier': (TextClassifierMatchExtractor, None)}
+
+
 class Model(Message):
-  EXTENSIONS = {Cap2DetModel.ext: Cap2DetModel}
+  EXTENSIONS = {Cap2DetModel.ext: Cap2DetModel, TextModel.ext: TextModel}
 
   def __init__(self, **kwargs):
     object.__setattr__(self, '_values', {})

@@ -101,6 +101,41 @@ __global__ void masked_reduce_kernel(const float* __restrict__ data, const float
   }
 }
 
+// Gradient of masked_maximum along m with TensorFlow's tie rule (equal shares); one warp per (n, d) column.
+__global__ void masked_max_bwd_kernel(const float* __restrict__ data, const float* __restrict__ mask, int n, int m,
+                                      int d, const float* __restrict__ dy, float* __restrict__ ddata) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n * d) return;
+  int in = warp / d, id = warp % d;
+  const float* col = data + (size_t)in * m * d + id;
+  float* dcol = ddata + (size_t)in * m * d + id;
+  const float* mk = mask + (size_t)in * m;
+  float lo = INFINITY;
+  for (int j = lane; j < m; j += 32) lo = fminf(lo, col[(size_t)j * d]);
+  lo = warp_min(lo);
+  float best = -INFINITY;
+  for (int j = lane; j < m; j += 32) best = fmaxf(best, __fmul_rn(__fsub_rn(col[(size_t)j * d], lo), mk[j]));
+  best = warp_max(best);
+  float n_lo = 0.f, n_best = 0.f, mask_best = 0.f;
+  for (int j = lane; j < m; j += 32) {
+    const float x = col[(size_t)j * d];
+    if (x == lo) n_lo += 1.f;
+    if (__fmul_rn(__fsub_rn(x, lo), mk[j]) == best) { n_best += 1.f; mask_best += mk[j]; }
+  }
+  n_lo = warp_sum(n_lo); n_best = warp_sum(n_best); mask_best = warp_sum(mask_best);
+  const float g = dy[warp];
+  const float g_best = __fdiv_rn(g, n_best);                                  // share of each tied maximum
+  const float g_lo = __fdiv_rn(__fmul_rn(g, __fsub_rn(1.f, __fdiv_rn(mask_best, n_best))), n_lo);
+  for (int j = lane; j < m; j += 32) {
+    const float x = col[(size_t)j * d];
+    float r = 0.f;
+    if (__fmul_rn(__fsub_rn(x, lo), mk[j]) == best) r = __fmul_rn(g_best, mk[j]);
+    if (x == lo) r = __fadd_rn(r, g_lo);
+    dcol[(size_t)j * d] = r;
+  }
+}
+
 // masked softmax along m: one warp per (n, d) column; three passes (max, sum, write).
 __global__ void masked_softmax_kernel(const float* __restrict__ data, const float* __restrict__ mask, int n,
                                       int m, int d, float* __restrict__ out) {
@@ -198,6 +233,18 @@ int c2d_masked_reduce(const float* data, const float* mask, int n, int m, int d,
   if (n == 0) return C2D_OK;
   long long threads = (long long)n * d * 32;
   masked_reduce_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(data, mask, n, m, d, op, out_f, out_i);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_masked_max_bwd(const float* data, const float* mask, int n, int m, int d, const float* dy, float* ddata,
+                       c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0 && m >= 1 && d >= 1, "masked_max_bwd: bad shape n=%d m=%d d=%d", n, m, d);
+  C2D_CHECK_ARG(data && mask && dy && ddata, "masked_max_bwd: null buffer");
+  if (n == 0) return C2D_OK;
+  long long threads = (long long)n * d * 32;
+  masked_max_bwd_kernel<<<cdiv(threads, 256), 256, 0, (cudaStream_t)stream>>>(data, mask, n, m, d, dy, ddata);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

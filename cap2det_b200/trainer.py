@@ -129,7 +129,16 @@ def _is_moving_stat(name):
   return name.endswith('/moving_mean') or name.endswith('/moving_variance')
 
 
-def _variable_segments(model, multipliers, trainable, l2_scale):
+def regularization_terms(model):
+  """[(packed variable, slim l2_regularizer scale)]: the variables built under a weights_regularizer.  Models may
+  provide their own list; for Cap2DetModel it is the five FC weight matrices under fc_hyperparams
+  (models/cap2det_model.py:79-88,190-197 - biases and the conv head have no regulariser on this path)."""
+  if hasattr(model, 'regularization_terms'):
+    return list(model.regularization_terms())
+  return [(model.fc_weights, l2_regularizer_scale(model._model_proto.fc_hyperparams))]
+
+
+def _variable_segments(model, multipliers, trainable, l2_scales):
   """Per packed buffer: (name, start, numel, multiplier | None, l2) for every named TF variable inside it.
 
   The BatchNorm moving statistics live in the head buffer too but are not TF trainable variables
@@ -146,8 +155,7 @@ def _variable_segments(model, multipliers, trainable, l2_scale):
       if 0 <= off < b.numel() * b.element_size():
         assert view.is_contiguous()
         m = multipliers.get(name, 1.0) if name in live else None
-        # slim regularises the FC *weights* only (models/cap2det_model.py:79-88,190-197 under fc_hyperparams)
-        l2 = l2_scale if (b is model.fc_weights and m is not None) else 0.0
+        l2 = l2_scales.get(id(b), 0.0) if m is not None else 0.0
         segs[i].append((name, off // b.element_size(), view.numel(), m, l2))
         break
   return segs
@@ -167,14 +175,12 @@ class TrainStep(object):
       for v in model.get_variables_to_train():
         v.register_post_accumulate_grad_hook(self._reduce_when_ready)
     self.train_config = train_config
-    options = model._model_proto
-    l2 = l2_regularizer_scale(options.fc_hyperparams)
-    self.l2_scale = l2
+    self.reg_terms = regularization_terms(model)
+    l2 = {id(v): float(scale) for v, scale in self.reg_terms}
     variables = model.get_variables_to_train()
     if train_config is None:
-      # slim regularises FC weights only (biases and the conv head have no regulariser on this path)
       self.base_lr = float(learning_rate)
-      self.opt = Adagrad(variables, learning_rate, l2_scales=[l2 if v is model.fc_weights else 0.0 for v in variables])
+      self.opt = Adagrad(variables, learning_rate, l2_scales=[l2.get(id(v), 0.0) for v in variables])
       return
     if train_config.sync_replicas:
       raise ValueError('sync_replicas (SyncReplicasOptimizer over a parameter server, train/trainer.py:90-94) is '
@@ -210,10 +216,13 @@ class TrainStep(object):
     return exponential_decay(self.base_lr, self.global_step, d.decay_steps, d.decay_rate, d.staircase)
 
   def regularization_loss(self):
-    out = torch.empty((), dtype=torch.float32, device=self.model.fc_weights.device)
-    call('c2d_l2_loss', ptr(self.model.fc_weights.data), self.model.fc_weights.numel(), self.l2_scale, ptr(out),
-         stream())
-    return out
+    """sum of slim l2_regularizer terms, scale * sum(w^2) / 2 each (core/training_utils.py:45-50)."""
+    total = None
+    for v, scale in self.reg_terms:
+      out = torch.empty((), dtype=torch.float32, device=v.device)
+      call('c2d_l2_loss', ptr(v.data), v.numel(), float(scale), ptr(out), stream())
+      total = out if total is None else total + out
+    return total
 
   def __call__(self, examples):
     """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""
@@ -236,7 +245,8 @@ class TrainStep(object):
     self.opt.step(grad_scale=1.0 / self.world_size)
     self.global_step += 1
     self.last_loss_dict = loss_dict
-    return total.detach() + self.regularization_loss()
+    reg = self.regularization_loss()
+    return total.detach() + reg if reg is not None else total.detach()
 
 
 class GraphedTrainStep(object):

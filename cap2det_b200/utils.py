@@ -35,8 +35,30 @@ def _reduce(data, mask, dim, op):
   return out.reshape(n, 1, d) if data.dim() == 3 else out.reshape(n, 1)
 
 
+class _MaskedMaximum(torch.autograd.Function):
+  """masked_maximum with TensorFlow's gradient (tied maxima / minima share it equally): c2d_masked_max_bwd."""
+
+  @staticmethod
+  def forward(ctx, data, mask, dim):
+    out = _reduce(data, mask, dim, capi.MASKED_MAX)
+    ctx.save_for_backward(data, mask)
+    ctx.dim = dim
+    return out
+
+  @staticmethod
+  def backward(ctx, dy):
+    data, mask = ctx.saved_tensors
+    data3, mask2, n, m, d = _prep(data, mask, ctx.dim)
+    ddata = torch.empty_like(data3)
+    dy = dy.contiguous()
+    call('c2d_masked_max_bwd', ptr(data3), ptr(mask2), n, m, d, ptr(dy), ptr(ddata), stream())
+    return ddata.view(data.shape), None, None
+
+
 def masked_maximum(data, mask, dim=1):
-  """core/utils.py:63-79."""
+  """core/utils.py:63-79 (differentiable with respect to ``data``)."""
+  if data.requires_grad and torch.is_grad_enabled():
+    return _MaskedMaximum.apply(data, mask, dim)
   return _reduce(data, mask, dim, capi.MASKED_MAX)
 
 

@@ -85,6 +85,12 @@ int c2d_box_scale_batch(const float* box, const int* img_hw, int B, int P, int p
  * Float results go to out_f [n,d]; ARGMAX/ARGMIN write int64 indices to out_i [n,d]. */
 int c2d_masked_reduce(const float* data, const float* mask, int n, int m, int d, int op,
                       float* out_f, long long* out_i, c2d_stream_t stream);
+/* Gradient of masked_maximum (core/utils.py:63-79: max((data - min) * mask) + min over axis m) with respect to
+ * data, as TensorFlow differentiates it: reduce_max / reduce_min share the gradient EQUALLY among tied elements,
+ * and the axis minimum receives dy * (1 - sum of the mask over the tied maxima / their count).  dy [n,d],
+ * ddata [n,m,d].  Used by the caption classifier of models/text_model.py (label_extractor.py:410-412). */
+int c2d_masked_max_bwd(const float* data, const float* mask, int n, int m, int d, const float* dy,
+                       float* ddata, c2d_stream_t stream);
 /* core/utils.py:172-184 masked_softmax over axis m: softmax(data - 1e10*(1-mask)). */
 int c2d_masked_softmax(const float* data, const float* mask, int n, int m, int d, float* out,
                        c2d_stream_t stream);

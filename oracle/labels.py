@@ -154,3 +154,33 @@ def parse_texts(tokens, offsets, lengths):
     row = list(tokens[o:o + l])
     rows.append(row + [''] * (max_len - len(row)))
   return len(offsets), rows, list(lengths)
+
+
+def text_model_forward_backward(classes, open_vocab, embedding_with_oov, w1, b1, w2, b2, caption_tokens, labels,
+                                keep_mask=None, keep_prob=1.0):
+  """models/text_model.py:53-83 (training graph): _predict (models/label_extractor.py:363-430) with dropout, then
+  reduce_mean(sigmoid_cross_entropy_with_logits).  w1 [D,H], w2 [H,C] in TF [in,out] layout.  fp64 torch autograd
+  of the reference formulas; amax / amin share the gradient equally among ties, as tf.reduce_max / reduce_min do.
+  Returns dict(logits, loss, dw1, db1, dw2, db2).  **Parity unpinned** (no reference test runs this graph)."""
+  import torch
+  index = {}
+  for i, w in enumerate(open_vocab):
+    index.setdefault(w, i)
+  oov = len(open_vocab)
+  ids = torch.tensor([[index.get(t, oov) for t in row] for row in caption_tokens], dtype=torch.long)
+  emb = torch.tensor(np.asarray(embedding_with_oov, np.float64))
+  v = [torch.tensor(np.asarray(a, np.float64), requires_grad=True) for a in (w1, b1, w2, b2)]
+  tw1, tb1, tw2, tb2 = v
+  hidden = emb[ids] @ tw1 + tb1                                                   # [B,T,H]
+  mask = (ids != oov).to(torch.float64)[:, :, None]
+  lo = hidden.amin(dim=1, keepdim=True)                                           # core/utils.py:75-79
+  pooled = ((hidden - lo) * mask).amax(dim=1, keepdim=True) + lo
+  pooled = torch.relu(pooled[:, 0])
+  if keep_mask is not None:
+    pooled = pooled / keep_prob * torch.tensor(np.asarray(keep_mask, np.float64))  # TF1 slim.dropout
+  logits = pooled @ tw2 + tb2
+  y = torch.tensor(np.asarray(labels, np.float64))
+  loss = (torch.clamp(logits, min=0) - logits * y + torch.log1p(torch.exp(-logits.abs()))).mean()
+  loss.backward()
+  return dict(logits=logits.detach().numpy(), loss=float(loss.detach()), dw1=tw1.grad.numpy(), db1=tb1.grad.numpy(),
+              dw2=tw2.grad.numpy(), db2=tb2.grad.numpy())

@@ -899,3 +899,125 @@ def test_checkpoint_resume_continues_training_identically(tmp_path):
     assert rel_err(vb.detach().cpu().numpy(), va.detach().cpu().numpy()) < RTOL_F32
   for aa, ab in zip(step.opt.accum, resumed.opt.accum):
     assert rel_err(ab.cpu().numpy(), aa.cpu().numpy()) < RTOL_F32
+
+
+# ---------------------------------------------------------------------------------------------
+# models/text_model.py: the caption classifier behind TextClassifierMatch
+# ---------------------------------------------------------------------------------------------
+def test_masked_maximum_gradient_shares_ties_like_tensorflow():
+  """d/d(data) of max((data - min) * mask) + min: tied maxima / minima share dy equally (tf.reduce_max / reduce_min
+  gradients); the minimum also receives dy * (1 - mask share of the maxima).  Against torch amax / amin autograd."""
+  from cap2det_b200 import utils
+  rng = np.random.default_rng(71)
+  n, m, d = 5, 9, 33
+  data = rng.standard_normal((n, m, d)).astype(np.float32)
+  data[0, 2] = data[0, 5]                                      # tied rows (maxima for some columns)
+  data[1] = np.round(data[1])                                  # many ties, incl. tied minima
+  data[2, :, :] = 0.25                                         # everything tied
+  mask = (rng.uniform(size=(n, m)) < 0.7).astype(np.float32)
+  mask[3] = 0                                                  # nothing selected: the gradient goes to the minimum
+  mask[4] = 1
+  dy = rng.standard_normal((n, 1, d)).astype(np.float32)
+  x = dev(data).requires_grad_(True)
+  out = utils.masked_maximum(x, dev(mask).unsqueeze(-1), dim=1)
+  out.backward(dev(dy))
+  xr = torch.tensor(data, dtype=torch.float64, requires_grad=True)
+  mk = torch.tensor(mask, dtype=torch.float64)[:, :, None]
+  lo = xr.amin(dim=1, keepdim=True)
+  ref = ((xr - lo) * mk).amax(dim=1, keepdim=True) + lo
+  ref.backward(torch.tensor(dy, dtype=torch.float64))
+  np.testing.assert_allclose(out.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-6, atol=1e-6)
+  np.testing.assert_allclose(x.grad.cpu().numpy(), xr.grad.numpy(), rtol=1e-5, atol=1e-6)
+  assert abs(float(x.grad[2].sum()) - float(dy[2].sum())) < 1e-4            # shares add up to dy
+
+
+def _text_model(d, rng, classes, hidden_units, dims, keep=0.5, is_training=True):
+  from cap2det_b200 import builder, config, synthetic
+  vpath, epath, vocab, emb = synthetic.write_open_vocab(d, classes, rng, size=600, dims=dims)
+  label_file = synthetic.write_label_file(d, classes)
+  m = config.parse_text(
+      "[TextModel.ext] { label_extractor { label_file: '%s' } text_classifier { label_file: '%s' "
+      "open_vocabulary_file: '%s' open_vocabulary_word_embedding_file: '%s' hidden_units: %d "
+      "dropout_keep_proba: %g regularizer: 1e-5 label_threshold: 0.7 } }" % (label_file, label_file, vpath, epath,
+                                                                             hidden_units, keep), config.Model)
+  return builder.build(m, is_training=is_training), vocab, (label_file, vpath, epath)
+
+
+@pytest.mark.parametrize('hidden_units,dims', [(400, 300), (300, 64)])
+def test_text_model_forward_backward_matches_oracle(hidden_units, dims):
+  """models/text_model.py:53-83 through c2d_fc_*, c2d_masked_reduce / c2d_masked_max_bwd and c2d_sigmoid_ce_mean
+  (embedding / hidden sizes that are not multiples of 16 are zero-padded for the FC kernels)."""
+  from cap2det_b200 import synthetic, text_model
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  rng = np.random.default_rng(73)
+  classes = synthetic.VOC_CLASSES
+  model, vocab, _ = _text_model(d, rng, classes, hidden_units, dims)
+  assert isinstance(model, text_model.Model)
+  B = 5
+  caps = synthetic.make_captions(rng, B, vocab, [c for c in classes if ' ' not in c], no_plant_images=(1,))
+  caps[3] = ['zzz_oov'] * len(caps[3])                                    # nothing in vocabulary
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B, hidden_units)) < 0.5).astype(np.float32)
+  with torch.no_grad():
+    model.layer1_biases.normal_(0, 0.1); model.layer2_biases.normal_(0, 0.5)
+  ex = {F.concat_caption_string: caps, F.object_texts: texts, F.dropout_keep_mask: dev(keep)}
+  pred = model.build_prediction(ex)
+  loss = model.build_loss(pred, ex)
+  assert list(loss) == ['text_cross_entropy_loss'] and tuple(pred['logits'].shape) == (B, len(classes))
+  loss['text_cross_entropy_loss'].backward()
+  tf_vars = {k: v.cpu().numpy() for k, v in model.named_variables().items()}
+  w1, w2 = tf_vars['text_classifier/layer1/weights'].T, tf_vars['text_classifier/layer2/weights'].T
+  want = olabels.text_model_forward_backward(
+      classes, vocab, model.embedding_weights.cpu().numpy()[:, :dims], w1, tf_vars['text_classifier/layer1/biases'], w2,
+      tf_vars['text_classifier/layer2/biases'], caps, olabels.groundtruth_extract(classes, texts), keep, 0.5)
+  np.testing.assert_allclose(pred['logits'].detach().cpu().numpy(), want['logits'], rtol=1e-4, atol=1e-5)
+  assert abs(float(loss['text_cross_entropy_loss']) - want['loss']) <= 1e-5 * abs(want['loss'])
+  assert rel_err(model.layer2_weights.grad.cpu().numpy(), want['dw2'].T) < 1e-4
+  assert rel_err(model.layer2_biases.grad.cpu().numpy(), want['db2']) < 1e-4
+  assert rel_err(model.layer1_weights.grad.cpu().numpy(), want['dw1'].T) < 1e-4
+  assert rel_err(model.layer1_biases.grad.cpu().numpy(), want['db1']) < 1e-4
+
+
+def test_text_model_trains_and_feeds_the_text_classifier_extractor(tmp_path):
+  """configs/coco17_text.pbtxt in miniature: Adagrad steps from the pipeline's train_config reduce the loss (L2 on
+  both FC layers), evaluation metrics accumulate, and the exported .npz is what TextClassifierMatchExtractor reads."""
+  from cap2det_b200 import checkpoint, config, label_extractor, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  rng = np.random.default_rng(75)
+  classes = synthetic.VOC_CLASSES
+  model, vocab, (label_file, vpath, epath) = _text_model(d, rng, classes, 64, 48, keep=0.5)
+  single = [c for c in classes if ' ' not in c]
+  tc = config.parse_text('learning_rate: 0.1  optimizer { adagrad { } }  moving_average_decay: 0.0', config.TrainConfig)
+  step = trainer.TrainStep(model, train_config=tc)
+  assert [s for _, s in step.reg_terms] == [1e-5, 1e-5]
+  batches = []
+  for b in range(8):                                           # the caption names the object: learnable
+    names = [single[(16 * b + i) % len(single)] for i in range(16)]
+    batches.append({F.concat_caption_string: [['a', n, 'zzz_oov'] for n in names], F.object_texts: [[n] for n in names]})
+  w1_before = model.layer1_weights.detach().clone()
+  losses = [float(step(batches[i % 8])) for i in range(300)]
+  assert losses[-1] < 0.3 * losses[0] and not torch.equal(w1_before, model.layer1_weights.detach())
+  reg = 1e-5 * 0.5 * float((model.layer1_weights.double() ** 2).sum() + (model.layer2_weights.double() ** 2).sum())
+  assert abs(float(step.regularization_loss()) - reg) <= 1e-5 * reg
+
+  model._is_training = False
+  for n in single[:6]:
+    ex = {F.concat_caption_string: [['a', n]], F.object_texts: [[n]]}
+    metrics = model.build_evaluation(model.build_prediction(ex), ex)
+  assert metrics['metrics/recall_at_5'] >= 0.8 and metrics['metrics/precision_at_1'] >= 0.5
+  assert set(metrics) == {'metrics/%s_at_%s' % (a, b) for a in ('precision', 'recall') for b in (0.3, 0.5, 0.7, 1, 5)}
+
+  ck = str(tmp_path / 'text_classifier.npz')
+  np.savez(ck, **checkpoint.export_variables(model))
+  opts = config.parse_text(
+      "text_classifier_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+      "open_vocabulary_word_embedding_file: '%s' text_classifier_checkpoint_file: '%s' hidden_units: 64 "
+      "label_threshold: 0.7 }" % (label_file, vpath, epath, ck), config.LabelExtractor)
+  extractor = label_extractor.build_label_extractor(opts)
+  caps = [['a', 'zzz_oov', n] for n in single[:6]]
+  labels, probas = extractor.extract_labels({F.concat_caption_string: caps}, return_probas=True)
+  logits = model.build_prediction({F.concat_caption_string: caps})['logits']
+  # same network, same variables (only the out-of-vocabulary embedding row is drawn independently - masked out)
+  np.testing.assert_allclose(probas.cpu().numpy(), torch.sigmoid(logits).detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
