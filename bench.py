@@ -293,48 +293,66 @@ def main():
   # PCIe transfer of step i+1 overlaps the kernels of step i) and reads the step's loss back to the host.
   copy_stream = torch.cuda.Stream(device=dev)
   staged = {}
-  loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-  loss_events = [None, None]
+  LOSS_DEPTH = 4                         # loss read-backs in flight: the host may queue this many steps ahead
+  loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(LOSS_DEPTH)]
+  loss_events = [None] * LOSS_DEPTH
   losses = []
+  host_wait = [0.0]                      # seconds the host spent blocked on loss read-backs (e2e diagnostics)
+  host_busy = [0.0]                      # seconds the host spent issuing e2e steps, blocking excluded
+
+  # device-side staging ring: fixed buffers reused every RING steps, so the timed region never touches the allocator
+  RING = LOSS_DEPTH + 1
+  ring = [{k: torch.empty_like(v.detach()) for k, v in resident[0].items() if torch.is_tensor(v)} for _ in range(RING)]
+  consumed = [None] * RING
 
   def stage(i):
-    p = pinned[i % n_pool]
+    p, k = pinned[i % n_pool], i % RING
+    buf = ring[k]
     with torch.cuda.stream(copy_stream):
-      ex = {F.features_to_crop: p['fmap'].to(dev, non_blocking=True),
-            F.proposals: p['proposals'].to(dev, non_blocking=True),
-            F.num_proposals: p['num_proposals'].to(dev, non_blocking=True), F.concat_caption_string: p['captions']}
-      # image-level labels (host tokenisation + a small kernel) are prepared with the batch, one step ahead, as a
-      # data loader would; Model.build_loss takes them from the example dict
+      if consumed[k] is not None:        # the step that last read this ring entry must be done with it
+        copy_stream.wait_event(consumed[k])
+      buf[F.features_to_crop].detach().copy_(p['fmap'], non_blocking=True)
+      buf[F.proposals].copy_(p['proposals'], non_blocking=True)
+      buf[F.num_proposals].copy_(p['num_proposals'], non_blocking=True)
+      ex = dict(buf)
+      ex[F.concat_caption_string] = p['captions']
+      # image-level labels (host tokenisation + a small kernel) are prepared with the batch, ahead of the step, as
+      # a data loader would; Model.build_loss takes them from the example dict
       ex['_labels'] = model._label_extractor.extract_labels(ex)
       ev = torch.cuda.Event()
       ev.record(copy_stream)
-    staged[i] = (ex, ev)
+    staged[i] = (ex, ev, k)
 
   def run_e2e(i):
+    t_in, waited = time.perf_counter(), host_wait[0]
     if i not in staged:
       stage(i)
-    ex, ev = staged.pop(i)
-    for j in (i + 1, i + 2):           # two steps of inputs in flight: absorbs host jitter on a busy box
+    ex, ev, k = staged.pop(i)
+    for j in range(i + 1, i + LOSS_DEPTH):      # inputs of the next steps in flight: absorbs host jitter on a busy box
       if j not in staged:
         stage(j)
     torch.cuda.current_stream().wait_event(ev)
-    for t in ex.values():
-      if torch.is_tensor(t):
-        t.record_stream(torch.cuda.current_stream())
+    ex['_labels'].record_stream(torch.cuda.current_stream())
     if graphed is not None:
       total = graphed(ex, labels=ex['_labels'])
     else:
+      ex[F.features_to_crop].grad = None
       ex[F.features_to_crop].requires_grad_(True)
       total = step(ex)
+    consumed[k] = torch.cuda.Event()
+    consumed[k].record()
     # device -> host read of the step's loss: an async copy into pinned memory every step; the host blocks on the
-    # PREVIOUS step's copy only, so it keeps one step of launches queued ahead of the GPU
-    slot = i & 1
+    # copy of LOSS_DEPTH steps ago only, so it keeps a few steps of launches queued ahead of the GPU
+    slot = i % LOSS_DEPTH
     if loss_events[slot] is not None:
+      t_wait = time.perf_counter()
       loss_events[slot].synchronize()
+      host_wait[0] += time.perf_counter() - t_wait
       losses.append(float(loss_host[slot]))
     loss_host[slot].copy_(total, non_blocking=True)
     loss_events[slot] = torch.cuda.Event()
     loss_events[slot].record()
+    host_busy[0] += (time.perf_counter() - t_in) - (host_wait[0] - waited)
     return None
 
   def timed(fn, n_warm, n_steps, count_launches=False):
@@ -363,12 +381,18 @@ def main():
   if graphed is not None:     # a replay launches the kernels recorded at capture; the host-side counter saw them once
     launches += graphed.launches_per_step * args.steps
   clocks = sampler.stop() if sampler else None
-  e2e_ms, _, _ = timed(run_e2e, 2, args.steps)
-  for slot in range(2):
+  e2e_warm = 3
+  for i in range(e2e_warm):              # reach the allocator's steady state before the timed region
+    run_e2e(i)
+  host_busy[0] = 0.0
+  e2e_ms, _, _ = timed(lambda i: run_e2e(e2e_warm + i), 0, args.steps)
+  e2e_host_busy = host_busy[0]
+  for k in range(LOSS_DEPTH):            # oldest first
+    slot = (e2e_warm + args.steps + k) % LOSS_DEPTH
     if loss_events[slot] is not None:
       loss_events[slot].synchronize()
       losses.append(float(loss_host[slot]))
-  assert len(losses) == args.steps + 2 and all(np.isfinite(v) for v in losses), 'e2e losses must all reach the host'
+  assert len(losses) == args.steps + e2e_warm and all(np.isfinite(v) for v in losses), 'e2e losses must all reach the host'
   model.raise_if_assert_failed()
 
   props_per_step = world * B * P
@@ -385,7 +409,8 @@ def main():
                          l2_handling='256 MB L2 flush between timed iterations', head_dtype=head_dtype),
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                      ms_per_step=e2e_ms / args.steps))
+                      ms_per_step=e2e_ms / args.steps, loss_readbacks_in_flight=LOSS_DEPTH,
+                      host_busy_ms_per_step=e2e_host_busy / args.steps * 1e3))
   if not args.no_first_stage and head_dtype == 'bf16':
     # the same step fed with IMAGES (600x1000x3 uint8, resident) instead of feature maps:
     # Inception-v2 first stage forward + Mixed_4e backward in front of / behind the proposal path.
