@@ -79,6 +79,39 @@ def padded_batch(examples, max_num_proposals):
   return batch
 
 
+def padded_text_batch(examples, max_num_proposals):
+  """padded_batch for ``decode_image: false`` readers (text classifier training, configs/coco17_text.pbtxt):
+  the string / box fields of :231-240 on the host (strings padded with '', boxes as NumPy), no image, and hence
+  none of the image-dependent stages."""
+  B = len(examples)
+  T = max(len(e[F.concat_caption_string]) for e in examples)
+  max_obj = max(len(e[F.object_texts]) for e in examples)
+  max_caps = max(int(e[F.num_captions]) for e in examples)
+  max_len = max([len(c) for e in examples for c in e[F.caption_strings]] + [0])
+  proposals = np.zeros((B, max_num_proposals, 4), np.float32)
+  objects = np.zeros((B, max_obj, 4), np.float32)
+  num_proposals = np.zeros((B,), np.int32)
+  for b, e in enumerate(examples):
+    p = np.asarray(e[F.proposals], np.float32).reshape(-1, 4)[:max_num_proposals]
+    proposals[b, :len(p)] = p
+    num_proposals[b] = len(p)
+    o = np.asarray(e[F.object_boxes], np.float32).reshape(-1, 4)
+    objects[b, :len(o)] = o
+  return {
+      F.image_id: [e[F.image_id] for e in examples],
+      F.num_captions: np.array([e[F.num_captions] for e in examples], np.int32),
+      F.caption_strings: [[list(c) + [''] * (max_len - len(c)) for c in e[F.caption_strings]] +
+                          [[''] * max_len] * (max_caps - int(e[F.num_captions])) for e in examples],
+      F.caption_lengths: [list(e[F.caption_lengths]) + [0] * (max_caps - int(e[F.num_captions])) for e in examples],
+      F.concat_caption_string: [list(e[F.concat_caption_string]) + [''] * (T - len(e[F.concat_caption_string]))
+                                for e in examples],
+      F.concat_caption_length: [len(e[F.concat_caption_string]) for e in examples],
+      F.num_proposals: num_proposals, F.proposals: proposals,
+      F.num_objects: np.array([len(e[F.object_texts]) for e in examples], np.int32), F.object_boxes: objects,
+      F.object_texts: [list(e[F.object_texts]) + [''] * (max_obj - len(e[F.object_texts])) for e in examples],
+  }
+
+
 def _round_scaled(scale, value):
   """tf.to_int32(tf.round(scale * tf.to_float(value))) in fp32 (round half to even)."""
   return np.rint(np.float32(scale) * np.asarray(value, np.float32)).astype(np.int32)
@@ -171,9 +204,7 @@ def get_input_fn(options, device='cuda', seed=None):
   from cap2det_b200 import config, imgproc, tfrecord
   if not isinstance(options, config.Cap2DetReader):
     raise ValueError('options has to be an instance of Reader.')
-  if not options.decode_image:
-    raise ValueError('decode_image=false (text classifier training) is outside the detection path.')
-  resize_fn = imgproc.build_image_resizer(options.image_resizer)
+  resize_fn = imgproc.build_image_resizer(options.image_resizer) if options.decode_image else None
   keep = shard_filter(options.shard_indicator) if options.shard_indicator else None
   flip = options.preprocess_options.random_flip_left_right_prob if options.HasField('preprocess_options') else 0.0
 
@@ -208,9 +239,12 @@ def get_input_fn(options, device='cuda', seed=None):
     for record in records:
       if keep is not None and not keep(tfrecord.decode_example(record, decode_image=False)):
         continue                                           # skip the JPEG decode of other shards' images
-      example = tfrecord.decode_example(record)
+      example = tfrecord.decode_example(record, decode_image=options.decode_image)
       pending.append(example)
-      if len(pending) == options.batch_size:
+      if len(pending) == options.batch_size and not options.decode_image:
+        yield padded_text_batch(pending, options.max_num_proposals)      # :251-262 are skipped without images
+        pending = []
+      elif len(pending) == options.batch_size:
         yield make_batch(pending, options.max_num_proposals,
                          batch_resize_scale_value=list(options.batch_resize_scale_value), rng=rng,
                          flip_probability=flip, device=device, resize_fn=resize_fn)

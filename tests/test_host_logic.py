@@ -588,3 +588,39 @@ def test_checkpoint_resume_restores_accumulators_and_step(tmp_path):
       assert bool((acc_b[stats] == 0.1).all())                               # untouched initial accumulator
     else:
       assert torch.equal(acc_a, acc_b)
+
+
+def test_get_input_fn_without_images_feeds_the_text_model(tmp_path):
+  """configs/coco17_text.pbtxt reads with decode_image: false: string fields only, padded per batch, sharded."""
+  import numpy as np
+  from cap2det_b200 import config, reader, tfrecord
+  from cap2det_b200.standard_fields import InputDataFields as F
+  records = []
+  for i in range(7):
+    caps = [['a', 'dog'], ['two', 'cats', 'sleep']][: 1 + i % 2]
+    tokens = sum(caps, [])
+    ex = {'image/source_id': [('%06d' % i).encode()], 'image/encoded': [b'not a jpeg'],
+          'image/caption/string': tokens, 'image/caption/offset': [0, 2][:len(caps)],
+          'image/caption/length': [len(c) for c in caps], 'image/object/class/text': ['dog', 'cat'][: 1 + i % 2]}
+    for k in ('ymin', 'xmin', 'ymax', 'xmax'):
+      ex['image/object/bbox/' + k] = [0.1] * (1 + i % 2)
+      ex['image/proposal/bbox/' + k] = [0.2] * 3
+    records.append(tfrecord.encode_example(ex))
+  tfrecord.write_records(str(tmp_path / 'train.record-00000-of-00001'), records)
+  options = config.parse_text('input_pattern: "%s/train.record*" batch_size: 2 decode_image: false max_num_proposals: 2'
+                              % tmp_path, config.Cap2DetReader)
+  batches = list(reader.get_input_fn(options)())
+  assert len(batches) == 3 and [b[F.image_id] for b in batches] == [['000000', '000001'], ['000002', '000003'],
+                                                                   ['000004', '000005']]
+  b = batches[0]
+  assert F.image not in b
+  assert b[F.concat_caption_string] == [['a', 'dog', '', '', ''], ['a', 'dog', 'two', 'cats', 'sleep']]
+  assert b[F.concat_caption_length] == [2, 5] and b[F.object_texts] == [['dog', ''], ['dog', 'cat']]
+  assert b[F.caption_strings] == [[['a', 'dog', ''], ['', '', '']], [['a', 'dog', ''], ['two', 'cats', 'sleep']]]
+  assert b[F.caption_lengths] == [[2, 0], [2, 3]] and b[F.num_captions].tolist() == [1, 2]
+  assert b[F.proposals].shape == (2, 2, 4) and b[F.num_proposals].tolist() == [2, 2]
+  assert b[F.object_boxes].shape == (2, 2, 4) and b[F.num_objects].tolist() == [1, 2]
+  sharded = config.parse_text('input_pattern: "%s/train.record*" batch_size: 1 decode_image: false shard_indicator: "0/2"'
+                              % tmp_path, config.Cap2DetReader)
+  ids = [b[F.image_id][0] for b in reader.get_input_fn(sharded)()]
+  assert ids == [i for i in ('%06d' % k for k in range(7)) if reader.to_hash_bucket(i, 2) == 0]
