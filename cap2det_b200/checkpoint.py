@@ -2,8 +2,8 @@
 ``first_stage_feature_extraction/*`` and ``second_stage_feature_extraction/*`` from the ImageNet checkpoint named
 by ``frcnn_options.checkpoint_path``; tf.estimator saves / restores everything else).
 
-TensorFlow's checkpoint files cannot be read without TensorFlow, so the container format here is NumPy ``.npz``
-keyed by the reference's variable names IN TF LAYOUTS, i.e. what
+The container format written here is NumPy ``.npz`` keyed by the reference's variable names IN TF LAYOUTS (reading
+also accepts a TensorFlow V2 checkpoint prefix through cap2det_b200.tf_checkpoint - parity unpinned, see there), i.e. what
 
     reader = tf.train.load_checkpoint(path)
     np.savez(out, **{n: reader.get_tensor(n) for n in reader.get_variable_to_shape_map()})
@@ -12,6 +12,8 @@ writes: conv ``weights`` HWIO ``[k,k,in,out]``, ``depthwise_weights`` ``[7,7,3,8
 ``[1,1,24,64]``, FC ``weights`` ``[in,out]``, everything else 1-D.  The packed CUDA buffers keep OHWI / ``[out,in]``
 (INTEGRATION.md); the transposes happen here.  Optimizer slots use TF's slot naming ``<variable>/Adagrad``.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -41,6 +43,16 @@ def _from_tf(name, a, like):
   return a
 
 
+def read_variables(path):
+  """{name: array} from an ``.npz`` file or from a TensorFlow V2 checkpoint prefix (``<path>.index`` +
+  ``<path>.data-*``, read by cap2det_b200.tf_checkpoint without TensorFlow)."""
+  if not path.endswith('.npz') and os.path.exists(path + '.index'):
+    from cap2det_b200 import tf_checkpoint
+    return tf_checkpoint.load_variables(path)
+  with np.load(path) as data:
+    return {k: data[k] for k in data.files}
+
+
 def export_variables(model):
   """{TF variable name: np.float32 array in TF layout} of every variable of the model."""
   return {name: _to_tf(name, view).contiguous().cpu().numpy() for name, view in model.named_variables().items()}
@@ -53,8 +65,7 @@ def import_variables(model, variables, include_scopes=None, strict=True):
   scopes from the ImageNet checkpoint, train/trainer.py:147-171).  ``strict``: every selected model variable
   must be present.  Returns the list of restored names."""
   if isinstance(variables, str):
-    with np.load(variables) as data:
-      variables = {k: data[k] for k in data.files}
+    variables = read_variables(variables)
   restored, missing = [], []
   with torch.no_grad():
     for name, view in model.named_variables().items():
@@ -104,8 +115,7 @@ def save_checkpoint(path, train_step):
 
 def load_checkpoint(path, train_step, strict=True):
   """Inverse of save_checkpoint: restores variables, accumulators (where present) and the global step."""
-  with np.load(path) as data:
-    variables = {k: data[k] for k in data.files}
+  variables = read_variables(path)
   model = train_step.model
   restored = import_variables(model, variables, strict=strict)
   with torch.no_grad():

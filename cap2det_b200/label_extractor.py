@@ -8,6 +8,7 @@ L2 normalisation, cosine similarity, masked max / arg-max and exact-match overri
 of {0,1}, like the reference.
 """
 import abc
+import os
 
 import numpy as np
 import torch
@@ -218,10 +219,14 @@ class TextClassifierMatchExtractor(LabelExtractor):
   def _build(self):
     options = self._options
     path = options.text_classifier_checkpoint_file
-    if not path.endswith('.npz'):
-      raise ValueError('text_classifier_checkpoint_file must be a .npz export of the text_classifier variables '
-                       '(got %r); TensorFlow checkpoints cannot be read without TensorFlow' % path)
-    ckpt = np.load(path)
+    if path.endswith('.npz'):
+      ckpt = np.load(path)
+    elif os.path.exists(path + '.index'):            # TensorFlow V2 checkpoint prefix (cap2det_b200.tf_checkpoint)
+      from cap2det_b200 import tf_checkpoint
+      ckpt = tf_checkpoint.load_variables(path, names=[n for n in self._VARS])
+    else:
+      raise ValueError('text_classifier_checkpoint_file must be a .npz export of the text_classifier variables or '
+                       'the prefix of a TensorFlow V2 checkpoint (got %r)' % path)
     for name in self._VARS:
       if name not in ckpt:
         raise ValueError('checkpoint %s lacks variable %s' % (path, name))

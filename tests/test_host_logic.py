@@ -624,3 +624,83 @@ def test_get_input_fn_without_images_feeds_the_text_model(tmp_path):
                               % tmp_path, config.Cap2DetReader)
   ids = [b[F.image_id][0] for b in reader.get_input_fn(sharded)()]
   assert ids == [i for i in ('%06d' % k for k in range(7)) if reader.to_hash_bucket(i, 2) == 0]
+
+
+# ---- TensorFlow V2 checkpoint files without TensorFlow (parity unpinned: format restated, no real file here) ----
+def test_snappy_decompress_literals_and_copies():
+  from cap2det_b200 import tf_checkpoint as tfc
+  # "abcabcabcabcX": literal "abc", copy(len 9, offset 3) that overlaps its own output, literal "X"
+  stream = bytes([13]) + bytes([(3 - 1) << 2]) + b'abc' + bytes([((9 - 4) << 2) | 1 | (0 << 5), 3]) + bytes([0]) + b'X'
+  assert tfc.snappy_decompress(stream) == b'abcabcabcabcX'
+  # 2-byte-offset copy and a long literal (length in an extra byte)
+  lit = bytes(range(200))
+  stream = bytes([0xD0, 0x01]) + bytes([60 << 2, 199]) + lit + bytes([((8 - 1) << 2) | 2, 200, 0])
+  assert tfc.snappy_decompress(stream) == lit + lit[:8]
+  assert tfc.snappy_decompress(tfc._snappy_literals(lit * 700)) == lit * 700            # > 64 KiB: several elements
+  with pytest.raises(ValueError, match='bad copy offset'):
+    tfc.snappy_decompress(bytes([4]) + bytes([((4 - 4) << 2) | 1, 9]))
+  with pytest.raises(ValueError, match='length mismatch'):
+    tfc.snappy_decompress(bytes([5]) + bytes([(3 - 1) << 2]) + b'abc')
+
+
+@pytest.mark.parametrize('snappy', [False, True])
+def test_tf_checkpoint_round_trip_and_model_restore(tmp_path, snappy):
+  import numpy as np
+  import torch
+  from cap2det_b200 import checkpoint, tf_checkpoint as tfc
+  a, b = _cpu_model(0, first_stage=False), _cpu_model(3, first_stage=False)
+  variables = checkpoint.export_variables(a)
+  variables['global_step'] = np.asarray(77, np.int64)
+  variables['some/half'] = np.arange(6, dtype=np.float16).reshape(2, 3)
+  variables['some/empty'] = np.zeros((0, 4), np.float32)
+  prefix = tfc.write_checkpoint(str(tmp_path / 'model.ckpt-77'), variables, entries_per_block=5, snappy=snappy)
+  header, entries = tfc.read_index(prefix)
+  assert header['num_shards'] == 1 and len(entries) == len(variables)                 # many blocks, prefix-compressed keys
+  listed = dict(tfc.list_variables(prefix))
+  assert listed['midn/proba_r_given_c/weights'] == [1024, 20] and listed['global_step'] == []
+  got = tfc.load_variables(prefix, verify_crc=True)
+  assert sorted(got) == sorted(variables)
+  for k, v in variables.items():
+    assert got[k].dtype == v.dtype and got[k].shape == v.shape, k
+    np.testing.assert_array_equal(got[k], v)
+  some = tfc.load_variables(prefix, names=['oicr/iter1/biases'])
+  assert list(some) == ['oicr/iter1/biases']
+  with pytest.raises(KeyError, match='lacks variable'):
+    tfc.load_variables(prefix, names=['nope'])
+  # the model restores straight from the checkpoint prefix (train/trainer.py:147-171)
+  restored = checkpoint.import_variables(b, prefix)
+  assert len(restored) == len(a.named_variables())
+  for va, vb in zip(a.get_variables_to_train(), b.get_variables_to_train()):
+    assert torch.equal(va, vb)
+
+
+def test_tf_checkpoint_rejects_damaged_files(tmp_path):
+  import numpy as np
+  from cap2det_b200 import tf_checkpoint as tfc
+  prefix = tfc.write_checkpoint(str(tmp_path / 'm'), {'a/b': np.arange(5, dtype=np.float32), 'a/c': np.ones((2, 2), np.int32)})
+  raw = bytearray(open(prefix + '.index', 'rb').read())
+  bad = bytes(raw[:-1]) + bytes([raw[-1] ^ 1])
+  open(str(tmp_path / 'bad.index'), 'wb').write(bad)
+  with pytest.raises(IOError, match='bad magic'):
+    tfc.read_index(str(tmp_path / 'bad'))
+  raw[3] ^= 0x40                                                                        # inside the first data block
+  open(str(tmp_path / 'crc.index'), 'wb').write(bytes(raw))
+  with pytest.raises(IOError, match='checksum mismatch'):
+    tfc.read_index(str(tmp_path / 'crc'))
+  data = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+  data[0] ^= 1
+  open(str(tmp_path / 'm2.index'), 'wb').write(open(prefix + '.index', 'rb').read())
+  open(str(tmp_path / 'm2.data-00000-of-00001'), 'wb').write(bytes(data))
+  assert tfc.load_variables(str(tmp_path / 'm2'))['a/c'].tolist() == [[1, 1], [1, 1]]
+  with pytest.raises(IOError, match='checksum mismatch for a/b'):
+    tfc.load_variables(str(tmp_path / 'm2'), verify_crc=True)
+
+
+def test_crc32c_chunked_path_equals_the_byte_loop():
+  import numpy as np
+  from cap2det_b200 import tfrecord
+  assert tfrecord.crc32c(b'123456789') == 0xE3069283                                   # the CRC-32C check value
+  rng = np.random.default_rng(0)
+  for n in (0, 1, 4095, 65535, 65536, 65537, 200001):
+    data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+    assert tfrecord.crc32c(data) == tfrecord._crc_scalar(0xFFFFFFFF, data) ^ 0xFFFFFFFF, n
