@@ -1,4 +1,4 @@
-"""Variable exchange and resume for the path's variables (train/trainer.py:147-171 restores
+"""Variable exchange and resume for the path's variables (models/utils.py:179-186 restores
 ``first_stage_feature_extraction/*`` and ``second_stage_feature_extraction/*`` from the ImageNet checkpoint named
 by ``frcnn_options.checkpoint_path``; tf.estimator saves / restores everything else).
 
@@ -62,7 +62,7 @@ def import_variables(model, variables, include_scopes=None, strict=True):
   """Copies ``variables`` (dict or path of an .npz, TF names and layouts) into the model's packed buffers.
 
   ``include_scopes``: optional name prefixes to restore (the reference restores only the two feature-extractor
-  scopes from the ImageNet checkpoint, train/trainer.py:147-171).  ``strict``: every selected model variable
+  scopes from the ImageNet checkpoint, models/utils.py:179-186).  ``strict``: every selected model variable
   must be present.  Returns the list of restored names."""
   if isinstance(variables, str):
     variables = read_variables(variables)
@@ -78,6 +78,40 @@ def import_variables(model, variables, include_scopes=None, strict=True):
       restored.append(name)
   if strict and missing:
     raise KeyError('checkpoint lacks %d variable(s), first: %s' % (len(missing), missing[0]))
+  return restored
+
+
+FEATURE_EXTRACTOR_SCOPES = ('first_stage_feature_extraction/', 'second_stage_feature_extraction/')
+
+
+def init_from_checkpoint(model, checkpoint_path=None, scopes=FEATURE_EXTRACTOR_SCOPES, missing='raise'):
+  """models/utils.py:179-186: ``tf.train.init_from_checkpoint(options.checkpoint_path, {"/": scope})`` for the two
+  feature-extractor scopes - checkpoint tensor ``InceptionV2/...`` initialises BOTH
+  ``first_stage_feature_extraction/InceptionV2/...`` and ``second_stage_feature_extraction/InceptionV2/...``
+  (the ImageNet network's Mixed_5a-c become the box-classifier head).
+
+  ``checkpoint_path``: .npz, TensorFlow V2 prefix or a dict; default ``frcnn_options.checkpoint_path`` of the model.
+  Like TensorFlow, a model variable of a mapped scope that the checkpoint lacks raises ValueError; ``missing='keep'``
+  leaves such variables at their initial value instead (slim's ImageNet Inception-v2 was trained without the
+  BatchNorm scale, so ``BatchNorm/gamma`` may be absent: it then stays 1).  Returns the restored model names."""
+  if missing not in ('raise', 'keep'):
+    raise ValueError("missing must be 'raise' or 'keep'")
+  if checkpoint_path is None:
+    checkpoint_path = model._model_proto.frcnn_options.checkpoint_path
+  ckpt = read_variables(checkpoint_path) if isinstance(checkpoint_path, str) else checkpoint_path
+  restored = []
+  with torch.no_grad():
+    for name, view in model.named_variables().items():
+      for scope in scopes:
+        if not name.startswith(scope):
+          continue
+        key = name[len(scope):]
+        if key not in ckpt:
+          if missing == 'raise':
+            raise ValueError('Tensor %s (%s in %s) is not found in the checkpoint' % (key, name, scope))
+          continue
+        view.copy_(_from_tf(name, ckpt[key], view).to(view.device))
+        restored.append(name)
   return restored
 
 

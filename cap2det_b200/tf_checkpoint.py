@@ -1,7 +1,7 @@
 """TensorFlow V2 checkpoints ("tensor bundles") read without TensorFlow.
 
 The reference restores ``zoo/inception_v2_2016_08_28/inception_v2.ckpt`` (V1 single file, which ``tf.train.Saver``
-users re-save as V2) into the two feature-extractor scopes (train/trainer.py:147-171) and a text-classifier
+users re-save as V2) into the two feature-extractor scopes (models/utils.py:179-186) and a text-classifier
 checkpoint into ``text_classifier/`` (models/label_extractor.py:456-458).  TensorFlow is not installable here, so
 this module restates the two published container formats a V2 checkpoint ``<prefix>`` is made of:
 

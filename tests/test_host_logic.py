@@ -497,7 +497,7 @@ def test_run_evaluation_loop_with_a_stub_model(tmp_path):
   assert np.isnan(evs[1].evaluate()['PascalBoxes_Precision/mAP@0.5IOU'])             # evaluators were cleared
 
 
-# ---- variable exchange / resume (train/trainer.py:147-171; TF names and layouts in .npz) -----------------------
+# ---- variable exchange / resume (models/utils.py:179-186; TF names and layouts in .npz) -----------------------
 def _cpu_model(seed, first_stage=True):
   import tempfile
   from cap2det_b200 import builder, config, synthetic
@@ -533,7 +533,7 @@ def test_checkpoint_variables_use_tf_names_and_layouts(tmp_path):
   path = str(tmp_path / 'vars.npz')
   np.savez(path, **tf_vars)
   before = {k: v.clone() for k, v in b.named_variables().items()}
-  # the reference's restore: feature extractors only (train/trainer.py:147-171)
+  # the reference's restore: feature extractors only (models/utils.py:179-186)
   got = checkpoint.import_variables(b, path, include_scopes=('first_stage_feature_extraction', 'second_stage_feature_extraction'))
   assert len(got) == len([k for k in before if 'feature_extraction' in k]) and not any(k.startswith('midn') for k in got)
   after = b.named_variables()
@@ -667,7 +667,7 @@ def test_tf_checkpoint_round_trip_and_model_restore(tmp_path, snappy):
   assert list(some) == ['oicr/iter1/biases']
   with pytest.raises(KeyError, match='lacks variable'):
     tfc.load_variables(prefix, names=['nope'])
-  # the model restores straight from the checkpoint prefix (train/trainer.py:147-171)
+  # the model restores straight from the checkpoint prefix (models/utils.py:179-186)
   restored = checkpoint.import_variables(b, prefix)
   assert len(restored) == len(a.named_variables())
   for va, vb in zip(a.get_variables_to_train(), b.get_variables_to_train()):
@@ -704,3 +704,33 @@ def test_crc32c_chunked_path_equals_the_byte_loop():
   for n in (0, 1, 4095, 65535, 65536, 65537, 200001):
     data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
     assert tfrecord.crc32c(data) == tfrecord._crc_scalar(0xFFFFFFFF, data) ^ 0xFFFFFFFF, n
+
+
+def test_init_from_checkpoint_maps_the_imagenet_scope_onto_both_extractors(tmp_path):
+  """models/utils.py:179-186: {"/": "first_stage_feature_extraction/"} and {"/": "second_stage_feature_extraction/"}."""
+  import numpy as np
+  import torch
+  from cap2det_b200 import checkpoint, tf_checkpoint
+  src, dst = _cpu_model(0), _cpu_model(9)
+  imagenet = {}
+  for name, arr in checkpoint.export_variables(src).items():
+    for scope in checkpoint.FEATURE_EXTRACTOR_SCOPES:
+      if name.startswith(scope):
+        imagenet[name[len(scope):]] = arr                                  # 'InceptionV2/...': one network, Mixed_5* included
+  assert 'InceptionV2/Conv2d_1a_7x7/depthwise_weights' in imagenet and 'InceptionV2/Mixed_5c/Branch_0/Conv2d_0a_1x1/weights' in imagenet
+  prefix = tf_checkpoint.write_checkpoint(str(tmp_path / 'inception_v2.ckpt'), imagenet)
+  dst._model_proto.frcnn_options.checkpoint_path = prefix                  # as in configs/*.pbtxt:56
+  fc_before = dst.fc_weights.detach().clone()
+  restored = checkpoint.init_from_checkpoint(dst)
+  assert len(restored) == len(imagenet)
+  assert torch.equal(dst.head_params, src.head_params) and torch.equal(dst.backbone_params, src.backbone_params)
+  assert torch.equal(dst.fc_weights, fc_before)                            # midn / oicr are not in the mapped scopes
+  # slim's ImageNet checkpoint has no BatchNorm scale: TensorFlow raises, 'keep' leaves gamma at its initial value
+  no_gamma = {k: v for k, v in imagenet.items() if not k.endswith('/gamma')}
+  with pytest.raises(ValueError, match='BatchNorm/gamma .* is not found'):
+    checkpoint.init_from_checkpoint(_cpu_model(9), no_gamma)
+  other = _cpu_model(9)
+  n = checkpoint.init_from_checkpoint(other, no_gamma, missing='keep')
+  assert len(n) == len(no_gamma)
+  gamma = other.named_variables()['second_stage_feature_extraction/InceptionV2/Mixed_5a/Branch_0/Conv2d_0a_1x1/BatchNorm/gamma']
+  assert bool((gamma == 1).all())
