@@ -44,13 +44,13 @@ def _from_tf(name, a, like):
 
 
 def read_variables(path):
-  """{name: array} from an ``.npz`` file or from a TensorFlow V2 checkpoint prefix (``<path>.index`` +
-  ``<path>.data-*``, read by cap2det_b200.tf_checkpoint without TensorFlow)."""
-  if not path.endswith('.npz') and os.path.exists(path + '.index'):
-    from cap2det_b200 import tf_checkpoint
-    return tf_checkpoint.load_variables(path)
-  with np.load(path) as data:
-    return {k: data[k] for k in data.files}
+  """{name: array} from an ``.npz`` file, a TensorFlow V2 checkpoint prefix (``<path>.index`` + ``<path>.data-*``)
+  or a V1 single-file checkpoint such as ``inception_v2.ckpt`` (cap2det_b200.tf_checkpoint, no TensorFlow)."""
+  if path.endswith('.npz'):
+    with np.load(path) as data:
+      return {k: data[k] for k in data.files}
+  from cap2det_b200 import tf_checkpoint
+  return tf_checkpoint.load_variables(path)
 
 
 def export_variables(model):

@@ -221,7 +221,7 @@ class TextClassifierMatchExtractor(LabelExtractor):
     path = options.text_classifier_checkpoint_file
     if path.endswith('.npz'):
       ckpt = np.load(path)
-    elif os.path.exists(path + '.index'):            # TensorFlow V2 checkpoint prefix (cap2det_b200.tf_checkpoint)
+    elif os.path.exists(path + '.index') or os.path.isfile(path):     # TensorFlow V2 prefix / V1 file (tf_checkpoint)
       from cap2det_b200 import tf_checkpoint
       ckpt = tf_checkpoint.load_variables(path, names=[n for n in self._VARS])
     else:

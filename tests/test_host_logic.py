@@ -734,3 +734,28 @@ def test_init_from_checkpoint_maps_the_imagenet_scope_onto_both_extractors(tmp_p
   assert len(n) == len(no_gamma)
   gamma = other.named_variables()['second_stage_feature_extraction/InceptionV2/Mixed_5a/Branch_0/Conv2d_0a_1x1/BatchNorm/gamma']
   assert bool((gamma == 1).all())
+
+
+@pytest.mark.parametrize('snappy', [False, True])
+def test_tf_v1_checkpoint_single_file(tmp_path, snappy):
+  """The format of zoo/inception_v2_2016_08_28/inception_v2.ckpt: one table, tensors inside SavedSlice protos."""
+  import numpy as np
+  from cap2det_b200 import checkpoint, tf_checkpoint as tfc
+  rng = np.random.default_rng(4)
+  variables = {'InceptionV2/Conv2d_1a_7x7/depthwise_weights': rng.standard_normal((7, 7, 3, 8)).astype(np.float32),
+               'InceptionV2/Conv2d_1a_7x7/BatchNorm/beta': rng.standard_normal(64).astype(np.float32),
+               'InceptionV2/Mixed_3b/Branch_0/Conv2d_0a_1x1/weights': rng.standard_normal((1, 1, 192, 64)).astype(np.float32),
+               'global_step': np.asarray(-3, np.int64), 'counts': np.arange(-2, 5, dtype=np.int32),
+               'doubles': rng.standard_normal((2, 2))}
+  path = tfc.write_v1_checkpoint(str(tmp_path / 'inception_v2.ckpt'), variables, snappy=snappy)
+  assert tfc.is_v1_checkpoint(path)
+  got = tfc.load_variables(path)
+  assert sorted(got) == sorted(variables)
+  for k, v in variables.items():
+    assert got[k].dtype == v.dtype and got[k].shape == v.shape, k
+    np.testing.assert_array_equal(got[k], v)
+  assert dict(tfc.list_variables(path))['InceptionV2/Conv2d_1a_7x7/depthwise_weights'] == [7, 7, 3, 8]
+  assert list(tfc.load_variables(path, names=['counts'])) == ['counts']
+  with pytest.raises(KeyError, match='lacks variable'):
+    tfc.load_variables(path, names=['nope'])
+  assert sorted(checkpoint.read_variables(path)) == sorted(variables)       # what init_from_checkpoint reads
