@@ -218,7 +218,9 @@ def encode_example(features):
     if isinstance(v, (bytes, str)):
       v = [v]
     v = list(v) if not isinstance(v, np.ndarray) else v
-    if len(v) > 0 and isinstance(v[0], (bytes, str)):
+    if len(v) == 0 and not isinstance(v, np.ndarray):
+      feature = b''                              # no kind set: TensorFlow reads it as an empty list of any type
+    elif len(v) > 0 and isinstance(v[0], (bytes, str)):
       lst = b''.join(_enc_field(1, x.encode('utf-8') if isinstance(x, str) else x) for x in v)
       feature = _enc_field(1, lst)
     elif isinstance(v, np.ndarray) and v.dtype.kind == 'f' or (len(v) > 0 and isinstance(v[0], float)):
@@ -279,3 +281,48 @@ def read_examples(paths, decode_image=True):
   for path in ([paths] if isinstance(paths, str) else paths):
     for record in read_records(path):
       yield decode_example(record, decode_image=decode_image)
+
+
+# ---- dataset-tools/create_pascal_tf_record.py:80-193 (dict_to_tf_example) ----------------------------------------
+def pascal_example(encoded_jpg, filename, objects, proposals, label_map_dict, ignore_difficult_instances=False):
+  """The tf.Example the reference writes per VOC image: ``objects`` = the annotation's object dicts (name, bndbox
+  in pixels, difficult, truncated, pose), ``proposals`` = the ``<image_id>.npy`` array [n,4] of normalised
+  (ymin, xmin, ymax, xmax) boxes, or its path.  Boxes are normalised by the decoded image size; the class names
+  double as the caption (offset [0], length [#objects]), as in :172-177.  Returns the serialized record."""
+  import hashlib
+  from PIL import Image
+  with Image.open(io.BytesIO(encoded_jpg)) as image:
+    if image.format != 'JPEG':
+      raise ValueError('Image format not JPEG')
+    height, width = image.height, image.width
+  if isinstance(proposals, str):
+    with open(proposals, 'rb') as fid:
+      proposals = np.load(fid)
+  proposals = np.asarray(proposals, np.float32).reshape(-1, 4)
+  xmin, ymin, xmax, ymax, classes, classes_text, truncated, poses, difficult_obj = [], [], [], [], [], [], [], [], []
+  for obj in objects:
+    difficult = bool(int(obj.get('difficult', 0)))
+    if ignore_difficult_instances and difficult:
+      continue
+    difficult_obj.append(int(difficult))
+    xmin.append(float(obj['bndbox']['xmin']) / width)
+    ymin.append(float(obj['bndbox']['ymin']) / height)
+    xmax.append(float(obj['bndbox']['xmax']) / width)
+    ymax.append(float(obj['bndbox']['ymax']) / height)
+    classes_text.append(obj['name'])
+    classes.append(int(label_map_dict[obj['name']]))
+    truncated.append(int(obj.get('truncated', 0)))
+    poses.append(obj.get('pose', 'Unspecified'))
+  f32 = lambda v: np.asarray(v, np.float32)
+  i64 = lambda v: np.asarray(v, np.int64)
+  return encode_example({
+      'image/height': i64([height]), 'image/width': i64([width]), 'image/filename': [filename],
+      IMAGE_ID: [filename], 'image/key/sha256': [hashlib.sha256(encoded_jpg).hexdigest()],
+      IMAGE_ENCODED: [encoded_jpg], 'image/format': ['jpeg'],
+      OBJECT_BOX + '/xmin': f32(xmin), OBJECT_BOX + '/xmax': f32(xmax), OBJECT_BOX + '/ymin': f32(ymin),
+      OBJECT_BOX + '/ymax': f32(ymax), OBJECT_TEXT: classes_text, OBJECT_LABEL: i64(classes),
+      'image/object/difficult': i64(difficult_obj), 'image/object/truncated': i64(truncated),
+      'image/object/view': poses, CAPTION_STRING: classes_text, CAPTION_OFFSET: i64([0]),
+      CAPTION_LENGTH: i64([len(classes_text)]),
+      PROPOSAL_BOX + '/ymin': proposals[:, 0], PROPOSAL_BOX + '/xmin': proposals[:, 1],
+      PROPOSAL_BOX + '/ymax': proposals[:, 2], PROPOSAL_BOX + '/xmax': proposals[:, 3]})

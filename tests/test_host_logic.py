@@ -759,3 +759,41 @@ def test_tf_v1_checkpoint_single_file(tmp_path, snappy):
   with pytest.raises(KeyError, match='lacks variable'):
     tfc.load_variables(path, names=['nope'])
   assert sorted(checkpoint.read_variables(path)) == sorted(variables)       # what init_from_checkpoint reads
+
+
+def test_pascal_example_mirrors_dict_to_tf_example(tmp_path):
+  """dataset-tools/create_pascal_tf_record.py:80-193: annotation dict + <image_id>.npy proposals -> the record that
+  readers/cap2det_reader.py parses (class names double as the caption)."""
+  import io
+  import numpy as np
+  from PIL import Image
+  from cap2det_b200 import tfrecord
+  from cap2det_b200.standard_fields import InputDataFields as F
+  buf = io.BytesIO()
+  Image.fromarray(np.zeros((50, 100, 3), np.uint8)).save(buf, format='JPEG')
+  props = np.array([[0.1, 0.2, 0.5, 0.6], [0.0, 0.0, 1.0, 1.0]], np.float32)
+  np.save(str(tmp_path / '000007.npy'), props)
+  objects = [{'name': 'dog', 'bndbox': {'xmin': '10', 'ymin': '5', 'xmax': '60', 'ymax': '45'}, 'difficult': '0',
+              'truncated': '1', 'pose': 'Left'},
+             {'name': 'cat', 'bndbox': {'xmin': '0', 'ymin': '0', 'xmax': '100', 'ymax': '50'}, 'difficult': '1'}]
+  label_map = {'cat': 8, 'dog': 12}
+  rec = tfrecord.pascal_example(buf.getvalue(), '000007.jpg', objects, str(tmp_path / '000007.npy'), label_map)
+  raw = tfrecord.parse_example(rec)
+  assert raw['image/height'].tolist() == [50] and raw['image/width'].tolist() == [100]
+  assert raw['image/object/class/label'].tolist() == [12, 8] and raw['image/object/difficult'].tolist() == [0, 1]
+  assert raw['image/format'] == [b'jpeg'] and len(raw['image/key/sha256'][0]) == 64
+  e = tfrecord.decode_example(rec)
+  assert e[F.image_id] == '000007.jpg' and e[F.image].shape == (50, 100, 3)
+  np.testing.assert_array_equal(e[F.proposals], props)
+  np.testing.assert_allclose(e[F.object_boxes], [[0.1, 0.1, 0.9, 0.6], [0.0, 0.0, 1.0, 1.0]], rtol=1e-6)
+  assert e[F.object_texts] == ['dog', 'cat'] and e[F.caption_strings] == [['dog', 'cat']] and e[F.num_captions] == 1
+  easy = tfrecord.decode_example(tfrecord.pascal_example(buf.getvalue(), '000007.jpg', objects, props, label_map,
+                                                         ignore_difficult_instances=True), decode_image=False)
+  assert easy[F.object_texts] == ['dog']
+  none = tfrecord.decode_example(tfrecord.pascal_example(buf.getvalue(), '000007.jpg', [], props, label_map),
+                                 decode_image=False)
+  assert none[F.object_texts] == [] and none[F.object_boxes].shape == (0, 4) and none[F.caption_strings] == [[]]
+  png = io.BytesIO()
+  Image.fromarray(np.zeros((4, 4, 3), np.uint8)).save(png, format='PNG')
+  with pytest.raises(ValueError, match='not JPEG'):
+    tfrecord.pascal_example(png.getvalue(), 'x.png', [], props, label_map)
