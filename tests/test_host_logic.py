@@ -797,3 +797,43 @@ def test_pascal_example_mirrors_dict_to_tf_example(tmp_path):
   Image.fromarray(np.zeros((4, 4, 3), np.uint8)).save(png, format='PNG')
   with pytest.raises(ValueError, match='not JPEG'):
     tfrecord.pascal_example(png.getvalue(), 'x.png', [], props, label_map)
+
+
+def test_detection_metrics_are_order_invariant_and_ignore_trailing_false_positives():
+  """Properties both evaluators must have: the order images / detections are added in does not matter (distinct
+  scores), and a false positive scored below every true positive leaves AP unchanged."""
+  import numpy as np
+  from cap2det_b200 import evaluation
+  rng = np.random.default_rng(17)
+  cats = [{'id': 1, 'name': 'a'}, {'id': 2, 'name': 'b'}]
+  images = []
+  for i in range(12):
+    n = int(rng.integers(1, 4))
+    corner = rng.uniform(0, 300, size=(n, 2))
+    size = rng.uniform(20, 150, size=(n, 2))
+    gt = np.concatenate([corner, corner + size], axis=1)
+    det = np.concatenate([gt + rng.normal(0, 6, size=gt.shape), rng.uniform(0, 400, size=(2, 4))], axis=0)
+    det[:, 2:] = np.maximum(det[:, 2:], det[:, :2] + 1)
+    cls = rng.integers(1, 3, size=n)
+    images.append((i, gt, cls, det, np.concatenate([cls, rng.integers(1, 3, size=2)]), rng.permutation(100)[:n + 2] / 100 + 0.001 * i))
+
+  def run(make, order, det_perm, extra_fp=False):
+    ev = make()
+    for k in order:
+      i, gt, cls, det, dcls, score = images[k]
+      p = det_perm(len(det))
+      det, dcls, score = det[p], dcls[p], score[p]
+      if extra_fp:
+        det = np.concatenate([det, [[900., 900., 950., 950.]]]); dcls = np.append(dcls, 1); score = np.append(score, 1e-6)
+      ev.add_single_ground_truth_image_info(i, {'groundtruth_boxes': gt, 'groundtruth_classes': cls})
+      ev.add_single_detected_image_info(i, {'detection_boxes': det, 'detection_scores': score, 'detection_classes': dcls})
+    return ev.evaluate()
+  for make in (lambda: evaluation.PascalDetectionEvaluator(cats), lambda: evaluation.CocoDetectionEvaluator(cats)):
+    base = run(make, range(12), np.arange)
+    shuffled = run(make, rng.permutation(12), rng.permutation)
+    with_fp = run(make, range(12), np.arange, extra_fp=True)
+    for k, v in base.items():
+      assert shuffled[k] == pytest.approx(v, nan_ok=True), k
+      if 'Recall/AR@1' not in k and 'AR@10' not in k or 'AR@100' in k:
+        assert with_fp[k] == pytest.approx(v, nan_ok=True), k
+    assert 0 < [v for k, v in base.items() if k.endswith('mAP') or 'mAP@0.5IOU' in k][0] < 1
