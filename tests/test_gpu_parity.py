@@ -972,7 +972,7 @@ def test_text_model_forward_backward_matches_oracle(hidden_units, dims):
       classes, vocab, model.embedding_weights.cpu().numpy()[:, :dims], w1, tf_vars['text_classifier/layer1/biases'], w2,
       tf_vars['text_classifier/layer2/biases'], caps, olabels.groundtruth_extract(classes, texts), keep, 0.5)
   np.testing.assert_allclose(pred['logits'].detach().cpu().numpy(), want['logits'], rtol=1e-4, atol=1e-5)
-  assert abs(float(loss['text_cross_entropy_loss']) - want['loss']) <= 1e-5 * abs(want['loss'])
+  assert abs(float(loss['text_cross_entropy_loss'].detach()) - want['loss']) <= 1e-5 * abs(want['loss'])
   assert rel_err(model.layer2_weights.grad.cpu().numpy(), want['dw2'].T) < 1e-4
   assert rel_err(model.layer2_biases.grad.cpu().numpy(), want['db2']) < 1e-4
   assert rel_err(model.layer1_weights.grad.cpu().numpy(), want['dw1'].T) < 1e-4
