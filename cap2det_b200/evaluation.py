@@ -325,18 +325,22 @@ def add_batch(evaluators, examples, predictions, category_to_id, eval_coco_on_vo
   heights, widths = host(examples[InputDataFields.image_height]), host(examples[InputDataFields.image_width])
   num_objects, object_boxes = host(examples[InputDataFields.num_objects]), host(examples[InputDataFields.object_boxes])
   object_texts = examples[InputDataFields.object_texts]
+  # one device -> host copy per prediction tensor and batch (not per image)
+  stages = []
+  for i in range(len(evaluators)):
+    stages.append([host(predictions[key + '_at_%d' % i]) for key in (
+        DetectionResultFields.num_detections, DetectionResultFields.detection_boxes,
+        DetectionResultFields.detection_scores, DetectionResultFields.detection_classes)])
   for b, image_id in enumerate(image_ids):
     n = int(num_objects[b])
     gt = {'groundtruth_boxes': box_utils.py_coord_norm_to_abs(object_boxes[b, :n], heights[b], widths[b]),
           'groundtruth_classes': np.array([category_to_id[t] for t in object_texts[b][:n]], np.int64),
           'groundtruth_difficult': np.zeros([n], bool)}
-    for i, evaluator in enumerate(evaluators):
-      nd = int(host(predictions[DetectionResultFields.num_detections + '_at_%d' % i])[b])
+    for evaluator, (num, boxes, scores, classes) in zip(evaluators, stages):
+      nd = int(num[b])
       evaluator.add_single_ground_truth_image_info(image_id, gt)
-      det_boxes = box_utils.py_coord_norm_to_abs(
-          host(predictions[DetectionResultFields.detection_boxes + '_at_%d' % i])[b, :nd], heights[b], widths[b])
-      det_scores = host(predictions[DetectionResultFields.detection_scores + '_at_%d' % i])[b, :nd]
-      det_classes = host(predictions[DetectionResultFields.detection_classes + '_at_%d' % i])[b, :nd]
+      det_boxes = box_utils.py_coord_norm_to_abs(boxes[b, :nd], heights[b], widths[b])
+      det_scores, det_classes = scores[b, :nd], classes[b, :nd]
       if eval_coco_on_voc:
         det_boxes, det_scores, det_classes = convert_coco_result_to_voc(det_boxes, det_scores, det_classes)
       evaluator.add_single_detected_image_info(image_id, {
