@@ -140,3 +140,34 @@ def test_image_oracle_sizes_and_resize_properties():
   box = np.array([[[0.5, 0.25, 1.0, 0.75]]], np.float32)
   got = oi.batch_scale_box(box, np.array([[300, 200, 3]]), 600, 400)
   np.testing.assert_array_equal(got, np.array([[[0.25, 0.125, 0.5, 0.375]]], np.float32))
+
+
+def test_crop_and_resize_reproduces_tensorflows_published_examples():
+  """The 2x2 cases of TensorFlow's own kernel test (tensorflow/python/kernel_tests/crop_and_resize_op_test.py:
+  2x2To1x1, 2x2To1x1Flipped, 2x2To3x3, 2x2To3x3Flipped, 2x2To3x3Extrapolated), restated here as known answers
+  for SURVEY.md Appendix A.1; the reference calls the op with its default extrapolation value 0."""
+  img = np.array([[1, 2], [3, 4]], np.float32).reshape(1, 2, 2, 1)
+  crop = lambda box, size: roi.crop_and_resize(img, np.array([box], np.float32), [0], size)[0, :, :, 0]
+  np.testing.assert_array_equal(crop([0, 0, 1, 1], (1, 1)), [[2.5]])
+  np.testing.assert_array_equal(crop([1, 1, 0, 0], (1, 1)), [[2.5]])
+  np.testing.assert_array_equal(crop([0, 0, 1, 1], (3, 3)), [[1, 1.5, 2], [2, 2.5, 3], [3, 3.5, 4]])
+  np.testing.assert_array_equal(crop([1, 1, 0, 0], (3, 3)), [[4, 3.5, 3], [3, 2.5, 2], [2, 1.5, 1]])
+  np.testing.assert_array_equal(crop([-1, -1, 1, 1], (3, 3)), [[0, 0, 0], [0, 1, 2], [0, 3, 4]])
+  np.testing.assert_array_equal(crop([0, 0, 1, 1], (2, 2)), [[1, 2], [3, 4]])
+
+
+def test_greedy_nms_reproduces_tensorflows_published_examples():
+  """tensorflow/python/kernel_tests/non_max_suppression_op_test.py: three clusters (also with flipped corner order,
+  one output only, ten outputs requested, a single box, no box) - the known answers behind SURVEY.md Appendix A.4."""
+  boxes = np.array([[0, 0, 1, 1], [0, 0.1, 1, 1.1], [0, -0.1, 1, 0.9], [0, 10, 1, 11], [0, 10.1, 1, 11.1],
+                    [0, 100, 1, 101]], np.float32)
+  scores = np.array([0.9, 0.75, 0.6, 0.95, 0.5, 0.3], np.float32)
+  cand = np.arange(6)
+  assert list(nms.greedy_nms(boxes, scores, cand, 3, 0.5)) == [3, 0, 5]
+  flipped = np.array([[1, 1, 0, 0], [0, 0.1, 1, 1.1], [0, .9, 1, -0.1], [0, 10, 1, 11], [1, 10.1, 0, 11.1],
+                      [1, 101, 0, 100]], np.float32)
+  assert list(nms.greedy_nms(flipped, scores, cand, 3, 0.5)) == [3, 0, 5]
+  assert list(nms.greedy_nms(boxes, scores, cand, 1, 0.5)) == [3]
+  assert list(nms.greedy_nms(boxes, scores, cand, 10, 0.5)) == [3, 0, 5]
+  assert list(nms.greedy_nms(boxes[:1], scores[:1], np.arange(1), 3, 0.5)) == [0]
+  assert list(nms.greedy_nms(boxes[:0], scores[:0], np.arange(0), 3, 0.5)) == []
