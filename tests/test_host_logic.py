@@ -837,3 +837,37 @@ def test_detection_metrics_are_order_invariant_and_ignore_trailing_false_positiv
       if 'Recall/AR@1' not in k and 'AR@10' not in k or 'AR@100' in k:
         assert with_fp[k] == pytest.approx(v, nan_ok=True), k
     assert 0 < [v for k, v in base.items() if k.endswith('mAP') or 'mAP@0.5IOU' in k][0] < 1
+
+
+def test_tf_example_codec_round_trips_random_feature_dicts():
+  """Property: parse_example(encode_example(x)) == x for random bytes / float / int64 features (packed lists, negative
+  and 64-bit integers, empty lists, non-ASCII keys), and the framing survives arbitrary record sizes."""
+  import numpy as np
+  from hypothesis import given, settings, strategies as st
+  from cap2det_b200 import tfrecord
+  keys = st.text(min_size=1, max_size=12)
+  value = st.one_of(
+      st.lists(st.binary(max_size=40), min_size=1, max_size=5),
+      st.lists(st.floats(width=32, allow_nan=False, allow_infinity=False), max_size=8).map(lambda v: np.asarray(v, np.float32)),
+      st.lists(st.integers(-2**63, 2**63 - 1), max_size=8).map(lambda v: np.asarray(v, np.int64)))
+
+  @settings(max_examples=60, deadline=None)
+  @given(st.dictionaries(keys, value, max_size=6))
+  def check(features):
+    got = tfrecord.parse_example(tfrecord.encode_example(features))
+    assert set(got) == set(features)
+    for k, v in features.items():
+      if isinstance(v, list):
+        assert got[k] == v
+      else:
+        assert got[k].dtype == v.dtype and got[k].tolist() == v.tolist()
+  check()
+
+  @settings(max_examples=20, deadline=None)
+  @given(st.lists(st.binary(max_size=300), max_size=6))
+  def framing(records):
+    import os, tempfile
+    path = os.path.join(tempfile.mkdtemp(), 'r')
+    tfrecord.write_records(path, records)
+    assert list(tfrecord.read_records(path, verify_data_crc=True)) == records
+  framing()
