@@ -192,14 +192,40 @@ def make_batch(raw_examples, max_num_proposals, batch_resize_scale_value=(), rng
   return batch_scale_box_fn(batch)
 
 
+def parallel_map(fn, iterable, workers, window):
+  """dataset.map(num_parallel_calls=workers).prefetch(window) for host work: results in input order, at most
+  ``window`` items in flight, the source iterated on the calling thread, exceptions re-raised at their position."""
+  if workers <= 1:
+    for item in iterable:
+      yield fn(item)
+    return
+  import collections
+  from concurrent.futures import ThreadPoolExecutor
+  pool = ThreadPoolExecutor(max_workers=workers)
+  in_flight = collections.deque()
+  try:
+    for item in iterable:
+      in_flight.append(pool.submit(fn, item))
+      if len(in_flight) >= window:
+        yield in_flight.popleft().result()
+    while in_flight:
+      yield in_flight.popleft().result()
+  finally:
+    for f in in_flight:
+      f.cancel()
+    pool.shutdown(wait=True)
+
+
 def get_input_fn(options, device='cuda', seed=None):
   """readers/cap2det_reader.py:16-264 (get_input_fn): Cap2DetReader options -> a function returning an iterator
   of batches read from the TFRecord files of ``input_pattern``.
 
   Order of the stages as in _input_fn: list files (shuffled when training) -> records -> parse -> shard filter ->
   padded batches of ``batch_size`` (remainder dropped) -> batch resize -> box rescale.  Training repeats forever
-  and shuffles through a buffer of ``shuffle_buffer_size`` records; interleave / parallel-map / prefetch sizes
-  only affect scheduling in the reference and are not modelled."""
+  and shuffles through a buffer of ``shuffle_buffer_size`` records.  ``map_num_parallel_calls`` decodes records
+  (protobuf + JPEG, PIL releases the GIL) on that many host threads, in order, up to ``prefetch_buffer_size``
+  examples ahead of the consumer, so decoding overlaps the GPU step; ``interleave_cycle_length`` only changes the
+  file read order in the reference and is not modelled."""
   import glob
   from cap2det_b200 import config, imgproc, tfrecord
   if not isinstance(options, config.Cap2DetReader):
@@ -235,11 +261,13 @@ def get_input_fn(options, device='cuda', seed=None):
     records = _records(rng)
     if options.is_training:
       records = _shuffled(records, rng)
+    if keep is not None:                                   # skip the JPEG decode of other shards' images
+      records = (r for r in records if keep(tfrecord.decode_example(r, decode_image=False)))
+    workers = max(1, int(options.map_num_parallel_calls))
+    window = max(1, min(int(options.prefetch_buffer_size), 4 * workers * max(1, int(options.batch_size))))
+    decode = lambda record: tfrecord.decode_example(record, decode_image=options.decode_image)
     pending = []
-    for record in records:
-      if keep is not None and not keep(tfrecord.decode_example(record, decode_image=False)):
-        continue                                           # skip the JPEG decode of other shards' images
-      example = tfrecord.decode_example(record, decode_image=options.decode_image)
+    for example in parallel_map(decode, records, workers, window):
       pending.append(example)
       if len(pending) == options.batch_size and not options.decode_image:
         yield padded_text_batch(pending, options.max_num_proposals)      # :251-262 are skipped without images

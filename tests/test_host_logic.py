@@ -871,3 +871,66 @@ def test_tf_example_codec_round_trips_random_feature_dicts():
     tfrecord.write_records(path, records)
     assert list(tfrecord.read_records(path, verify_data_crc=True)) == records
   framing()
+
+
+def test_parallel_map_keeps_order_bounds_the_window_and_propagates_errors():
+  import threading
+  import time
+  from cap2det_b200 import reader
+  peak, live, lock = [0], [0], threading.Lock()
+
+  def work(x):
+    with lock:
+      live[0] += 1
+      peak[0] = max(peak[0], live[0])
+    time.sleep(0.002 * (x % 3))
+    with lock:
+      live[0] -= 1
+    if x == 37:
+      raise KeyError('record 37')
+    return x * x
+  assert list(reader.parallel_map(work, range(30), 4, 8)) == [x * x for x in range(30)]
+  assert 2 <= peak[0] <= 4
+  assert list(reader.parallel_map(work, range(5), 1, 8)) == [0, 1, 4, 9, 16]
+  got = []
+  with pytest.raises(KeyError, match='record 37'):
+    for y in reader.parallel_map(work, range(100), 4, 8):
+      got.append(y)
+  assert got == [x * x for x in range(37)]                      # everything before the failing record was delivered
+  consumed = []
+
+  def source():
+    for i in range(1000):
+      consumed.append(i)
+      yield i
+  gen = reader.parallel_map(lambda x: x, source(), 3, 5)
+  assert [next(gen) for _ in range(4)] == [0, 1, 2, 3]
+  gen.close()                                                   # consumer stops early: the pool shuts down
+  assert len(consumed) <= 4 + 5
+  assert threading.active_count() < 8
+
+
+def test_get_input_fn_parallel_decode_equals_sequential(tmp_path):
+  from cap2det_b200 import config, reader, tfrecord
+  from cap2det_b200.standard_fields import InputDataFields as F
+  records = []
+  for i in range(23):
+    ex = {'image/source_id': [('%06d' % i).encode()], 'image/caption/string': ['w%d' % i], 'image/caption/offset': [0],
+          'image/caption/length': [1], 'image/object/class/text': ['dog']}
+    for k in ('ymin', 'xmin', 'ymax', 'xmax'):
+      ex['image/object/bbox/' + k] = [0.1]
+      ex['image/proposal/bbox/' + k] = [0.2] * 2
+    records.append(tfrecord.encode_example(ex))
+  tfrecord.write_records(str(tmp_path / 'a.record'), records[:12])
+  tfrecord.write_records(str(tmp_path / 'b.record'), records[12:])
+  text = ('input_pattern: "%s/*.record" batch_size: 3 decode_image: false is_training: %%s shuffle_buffer_size: 5 '
+          'map_num_parallel_calls: %%d prefetch_buffer_size: 7 shard_indicator: "0/2"' % tmp_path)
+  import itertools
+  for training in ('false', 'true'):
+    runs = []
+    for workers in (1, 6):
+      options = config.parse_text(text % (training, workers), config.Cap2DetReader)
+      it = reader.get_input_fn(options, seed=5)()
+      runs.append([b[F.image_id] for b in itertools.islice(it, 6)])
+      it.close()
+    assert runs[0] == runs[1] and len(runs[0]) > 0
