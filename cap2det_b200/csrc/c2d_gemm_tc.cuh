@@ -26,6 +26,17 @@ constexpr int kStageABytes = 32768;              // 256 rows x 64 bf16
 constexpr int kStageBBytes = 16384;              // <= 128 rows x 64 bf16
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+
+// EXPERIMENT (off by default, not yet validated on a GPU): warp-uniform issue loops.  With the role decided from
+// `threadIdx.x >> 5` and the issuing thread picked by `lane == 0`, ptxas cannot prove that the operands of
+// UTMALDG / UTCHMMA are warp-uniform and wraps every one of them in a waterfall (ELECT + R2UR.BROADCAST x4-8 +
+// BRA.U.ANY): 150-240 SASS instructions per k-step on the MMA warp, which the r1 profile shows to be ~90 % busy
+// ISSUING while the tensor pipe idles ~45 % (profiles/r1_tc_issue_analysis.md).  The variant below makes the warp
+// index uniform (__shfl_sync), lets all 32 lanes walk the uniform control flow and predicates only the issue
+// instructions on elect.sync, so the operands live in uniform registers.  Build with -DC2D_UNIFORM_ISSUE=1.
+#ifndef C2D_UNIFORM_ISSUE
+#define C2D_UNIFORM_ISSUE 0
+#endif
 constexpr int kWgThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
@@ -126,7 +137,11 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcPipe* pipe = reinterpret_cast<TcPipe*>(smem + kStages * kStageBytes);
+#if C2D_UNIFORM_ISSUE
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+#else
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
@@ -147,7 +162,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
   if (warp == 0) {
     // ===== TMA producer =====
+#if C2D_UNIFORM_ISSUE
+    const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
+    {
+#else
+    const bool issuer = true;
     if (lane == 0) {
+#endif
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -161,11 +182,13 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             mbar_wait(&pipe->empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * kStageBytes;
             uint8_t* sB = sA + kStageABytes;
-            mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
-            if (p.flat == 1) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
-            else if (p.flat == 2) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
-            else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, tx, ty, mt * p.rois_per_tile);
-            tma_load_4d(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile, 0, 0);
+            if (issuer) {
+              mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
+              if (p.flat == 1) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, mt * p.rows_per_tile, 0, 0);
+              else if (p.flat == 2) tma_load_4d(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
+              else tma_load_4d(sA, mA, &pipe->full[stage], c * 64, tx, ty, mt * p.rois_per_tile);
+              tma_load_4d(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile, 0, 0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -173,6 +196,9 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
+#if C2D_UNIFORM_ISSUE
+    const bool mma_issuer = elect_one_sync();
+#endif
     const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
     int ksteps = 0;
     for (int t = 0; t < p.taps; ++t) ksteps += p.tap_chunks[t];
@@ -187,6 +213,24 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
+#if C2D_UNIFORM_ISSUE
+        {
+          // descriptors built in warp-uniform code; +2 in the low word = +32 bytes (one UMMA_K of bf16)
+          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc0 = make_smem_desc(sA, 16, 1024), adesc1 = make_smem_desc(sA + 16384, 16, 1024);
+          const uint64_t bdesc0 = make_smem_desc(sA + kStageABytes, 16, 1024);
+          if (mma_issuer) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
+              umma_f16(acc0, adesc0 + (uint64_t)(2 * kk), bdesc0 + (uint64_t)(2 * kk), idesc, acc);
+              umma_f16(acc0 + 128, adesc1 + (uint64_t)(2 * kk), bdesc0 + (uint64_t)(2 * kk), idesc, acc);
+            }
+            umma_commit(&pipe->empty[stage]);
+            if (ks == ksteps - 1) umma_commit(&pipe->tmem_full[as]);
+          }
+        }
+#else
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + stage * kStageBytes);
           const uint32_t sB = sA + kStageABytes;
@@ -200,6 +244,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           umma_commit(&pipe->empty[stage]);
           if (ks == ksteps - 1) umma_commit(&pipe->tmem_full[as]);
         }
+#endif
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -359,7 +404,11 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Tc2Pipe* pipe = reinterpret_cast<Tc2Pipe*>(smem + k2Stages * k2StageBytes);
+#if C2D_UNIFORM_ISSUE
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+#else
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
 
   if (threadIdx.x == 0) {
@@ -383,7 +432,13 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; completion is credited to the leader's full barrier) =====
+#if C2D_UNIFORM_ISSUE
+    const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
+    {
+#else
+    const bool issuer = true;
     if (lane == 0) {
+#endif
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -398,11 +453,13 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             mbar_wait(&pipe->empty[stage], phase ^ 1);
             uint8_t* sA = smem + stage * k2StageBytes;
             uint8_t* sB = sA + k2StageABytes;
-            if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
-            if (p.flat == 1) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, h * p.rows_per_tile, 0, 0);
-            else if (p.flat == 2) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
-            else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, h * p.rois_per_tile);
-            tma_load_4d_2cta(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile + (int)rank * n_half, 0, 0);
+            if (issuer) {
+              if (rank == 0) mbar_arrive_expect_tx(&pipe->full[stage], pair_tx);
+              if (p.flat == 1) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, h * p.rows_per_tile, 0, 0);
+              else if (p.flat == 2) tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, it.x0 + tx, it.y0 + ty, it.n);
+              else tma_load_4d_2cta(sA, mA, &pipe->full[stage], c * 64, tx, ty, h * p.rois_per_tile);
+              tma_load_4d_2cta(sB, &mapB, &pipe->full[stage], koff + c * 64, nt * p.n_tile + (int)rank * n_half, 0, 0);
+            }
             if (++stage == k2Stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -410,6 +467,9 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
+#if C2D_UNIFORM_ISSUE
+    const bool mma_issuer = elect_one_sync();
+#endif
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(256, p.n_tile, 0, 0);
       int ksteps = 0;
@@ -425,6 +485,21 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&pipe->full[stage], phase);
           tc_fence_after();
+#if C2D_UNIFORM_ISSUE
+          {
+            // descriptors built in warp-uniform code; +2 in the low word = +32 bytes (one UMMA_K of bf16)
+            const uint32_t sA = smem_u32(smem + stage * k2StageBytes);
+            const uint64_t adesc = make_smem_desc(sA, 16, 1024), bdesc = make_smem_desc(sA + k2StageABytes, 16, 1024);
+            if (mma_issuer) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk)
+                umma_f16_2cta(acc0, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc,
+                              (ks > 0 || kk > 0) ? 1u : 0u);
+              umma_commit_2cta(&pipe->empty[stage], 3);               // frees the slot in BOTH CTAs
+              if (ks == ksteps - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
+            }
+          }
+#else
           if (lane == 0) {
             const uint32_t sA = smem_u32(smem + stage * k2StageBytes);
             const uint32_t sB = sA + k2StageABytes;
@@ -435,6 +510,7 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             umma_commit_2cta(&pipe->empty[stage], 3);                 // frees the slot in BOTH CTAs
             if (ks == ksteps - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
           }
+#endif
           __syncwarp();
           if (++stage == k2Stages) { stage = 0; phase ^= 1; }
         }
@@ -660,7 +736,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + kWgStages * kWgStageBytes;
   WgPipe* pipe = reinterpret_cast<WgPipe*>(ones + kWgOnesBytes);
+#if C2D_UNIFORM_ISSUE
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+#else
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#endif
   for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;          // bf16 1.0 pairs
   fence_proxy_async();
@@ -681,7 +761,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   const int num_items = p.taps * p.ci_tiles * p.splits_sum;
 
   if (warp == 0) {
+#if C2D_UNIFORM_ISSUE
+    const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
+    {
+#else
+    const bool issuer = true;
     if (lane == 0) {
+#endif
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const WgItem wi = wg_decode(p, item);
@@ -707,7 +793,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           mbar_wait(&pipe->empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kWgStageBytes;
           uint8_t* sB = sA + 32768;
+#if !C2D_UNIFORM_ISSUE
           mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
+#endif
           int px0 = 0, py0 = 0, pn = s * p.rois_per_step;
           if (p.flat == 2) {
             const int per_img = p.img_tiles_x * p.img_tiles_y;
@@ -717,22 +805,30 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
             px0 = (rem - py0 * p.img_tiles_x) * 8;
             py0 *= 8;
           }
+          if (issuer) {
+#if C2D_UNIFORM_ISSUE
+            mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
+#endif
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (g >= a_groups) break;
-            if (p.flat == 1) tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], s * 64, 0, 0);
-            else tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], px0, py0, pn);
-          }
-          for (int g = 0; g < p.ci_groups; ++g) {
-            const int c0 = cit * p.ci_tile + g * 64;
-            if (p.flat == 1) tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, s * 64, 0, 0);
-            else tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, px0 + p.tap_x[t], py0 + p.tap_y[t], pn);
+            for (int g = 0; g < 4; ++g) {
+              if (g >= a_groups) break;
+              if (p.flat == 1) tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], s * 64, 0, 0);
+              else tma_load_4d(sA + g * 8192, gmap[g], &pipe->full[stage], gco[g], px0, py0, pn);
+            }
+            for (int g = 0; g < p.ci_groups; ++g) {
+              const int c0 = cit * p.ci_tile + g * 64;
+              if (p.flat == 1) tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, s * 64, 0, 0);
+              else tma_load_4d(sB + g * 8192, mX, &pipe->full[stage], c0, px0 + p.tap_x[t], py0 + p.tap_y[t], pn);
+            }
           }
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
+#if C2D_UNIFORM_ISSUE
+    const bool mma_issuer = elect_one_sync();
+#endif
     const uint32_t idesc = make_idesc_bf16(128, p.ci_tile, 1, 1);
     const uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 1);
     const uint32_t s_ones = smem_u32(ones);
@@ -748,6 +844,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       for (int s = s0; s < s1; ++s) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
+#if C2D_UNIFORM_ISSUE
+        {
+          // descriptors built in warp-uniform code; +128 in the low word = +2048 bytes (16 reduction rows)
+          const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
+          const uint64_t a0d = make_smem_desc(sA, 8192, 1024), a1d = make_smem_desc(sA + 16384, 8192, 1024);
+          const uint64_t bd = make_smem_desc(sA + 32768, 8192, 1024), od = make_smem_desc(s_ones, 8192, 1024);
+          if (mma_issuer) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t acc = (s > s0 || kk > 0) ? 1u : 0u;
+              const uint64_t step = (uint64_t)(128 * kk);
+              umma_f16(tmem_base, a0d + step, bd + step, idesc, acc);
+              if (two) umma_f16(tmem_base + 256, a1d + step, bd + step, idesc, acc);
+              if (want_shift) {
+                umma_f16(tmem_base + kWgOnesCol, a0d + step, od + step, idesc_ones, acc);
+                if (two) umma_f16(tmem_base + 256 + kWgOnesCol, a1d + step, od + step, idesc_ones, acc);
+              }
+            }
+            umma_commit(&pipe->empty[stage]);
+            if (s == s1 - 1) umma_commit(&pipe->tmem_full);
+          }
+        }
+#else
         if (lane == 0) {
           const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
           const uint32_t sB = sA + 32768;
@@ -768,6 +887,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           umma_commit(&pipe->empty[stage]);
           if (s == s1 - 1) umma_commit(&pipe->tmem_full);
         }
+#endif
         __syncwarp();
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }
