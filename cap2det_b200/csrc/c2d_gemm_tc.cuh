@@ -37,6 +37,12 @@ constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps
 #ifndef C2D_UNIFORM_ISSUE
 #define C2D_UNIFORM_ISSUE 0
 #endif
+// EXPERIMENT (off by default, not yet validated on a GPU): issue the BN-shift loads of a 16-column chunk BEFORE the
+// tcgen05.ld of its accumulators, so that their latency overlaps the TMEM read instead of following it
+// (profiles/r1_tc_issue_analysis.md: the FADDs consuming them hold ~12 % of the samples as long_scoreboard).
+#ifndef C2D_EPILOGUE_EARLY_SHIFT
+#define C2D_EPILOGUE_EARLY_SHIFT 0
+#endif
 constexpr int kWgThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
@@ -291,6 +297,17 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int j = j0 + u * 16;
           const int col0 = nt * p.n_tile + j;
           if (j >= p.n_tile || col0 >= p.n_total) break;            // warp-uniform
+#if C2D_EPILOGUE_EARLY_SHIFT
+          float4 sh[4];
+          if (p.shift != nullptr && col0 < p.act_cols) {
+            const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh[i] = __ldg(sp + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#endif
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
@@ -306,12 +323,19 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             const bool act = col0 < p.act_cols;
             if (p.shift != nullptr && act) {
+#if C2D_EPILOGUE_EARLY_SHIFT
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[4 * i] += sh[i].x; f[4 * i + 1] += sh[i].y; f[4 * i + 2] += sh[i].z; f[4 * i + 3] += sh[i].w;
+              }
+#else
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float4 s4 = __ldg(sp + i);
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
+#endif
             }
             if (p.relu && act) {
 #pragma unroll
@@ -556,6 +580,17 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
           const int j = j0 + u * 16;
           const int col0 = nt * p.n_tile + j;
           if (j >= col_hi || col0 >= p.n_total) break;              // warp-uniform
+#if C2D_EPILOGUE_EARLY_SHIFT
+          float4 sh[4];
+          if (p.shift != nullptr && col0 < p.act_cols) {
+            const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh[i] = __ldg(sp + i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#endif
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
@@ -571,12 +606,19 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             const bool act = col0 < p.act_cols;
             if (p.shift != nullptr && act) {
+#if C2D_EPILOGUE_EARLY_SHIFT
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                f[4 * i] += sh[i].x; f[4 * i + 1] += sh[i].y; f[4 * i + 2] += sh[i].z; f[4 * i + 3] += sh[i].w;
+              }
+#else
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float4 s4 = __ldg(sp + i);
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
+#endif
             }
             if (p.relu && act) {
 #pragma unroll
