@@ -43,6 +43,14 @@ constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps
 #ifndef C2D_EPILOGUE_EARLY_SHIFT
 #define C2D_EPILOGUE_EARLY_SHIFT 0
 #endif
+// EXPERIMENT (off by default, not yet validated on a GPU; 2-CTA kernel only): rolling prefetch of the epilogue's
+// global operands (previous bf16 value for accumulation, activation for the fused ReLU mask).  The first 64-column
+// block of a tile is requested BEFORE the wait for its accumulator, and the registers of a consumed chunk are
+// refilled at once with the same chunk of the next block, so that a memory latency is no longer exposed per block
+// (profiles/r1_tc_issue_analysis.md, finding 2).
+#ifndef C2D_EPILOGUE_PREFETCH
+#define C2D_EPILOGUE_PREFETCH 0
+#endif
 constexpr int kWgThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
@@ -550,6 +558,33 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+#if C2D_EPILOGUE_PREFETCH
+      const int r = q * 32 + lane;                  // row inside this CTA's half tile
+      const long long orow = conv_out_row(p, 2 * mt + (int)rank, r);
+      const bool bf16_rmw = !p.out_f32 && p.accum;
+      uint4 oldv[4][2], mskv[4][2];
+      // chunk u of the 64-column block that starts at column jb of this tile -> oldv[u], mskv[u]
+#define C2D_FETCH_CHUNK(jb, u)                                                                                    \
+      {                                                                                                           \
+        const int fc0 = nt * p.n_tile + (jb) + (u) * 16;                                                          \
+        const bool flive = orow >= 0 && (jb) + (u) * 16 < col_hi && fc0 < p.n_total;                              \
+        oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);                                                     \
+        mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);                 \
+        if (flive && bf16_rmw)                                                                                    \
+          ld_global_256(reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + fc0,          \
+                        oldv[u][0], oldv[u][1]);                                                                  \
+        if (flive && p.mask != nullptr && fc0 < p.mask_cols)                                                      \
+          ld_global_256(p.mask + orow * p.mask_ld + fc0, mskv[u][0], mskv[u][1]);                                 \
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) C2D_FETCH_CHUNK(col_lo, u)      // in flight while the accumulator completes
+      mbar_wait(&pipe->tmem_full[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+#pragma unroll 1
+      for (int j0 = col_lo; j0 < col_hi; j0 += 64) {
+        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
+#else
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = q * 32 + lane;                  // row inside this CTA's half tile
@@ -575,6 +610,7 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             ld_global_256(y, mskv[u][0], mskv[u][1]);
           }
         }
+#endif
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + u * 16;
@@ -664,8 +700,14 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
               st_global_256(o, w0, w1);
             }
           }
+#if C2D_EPILOGUE_PREFETCH
+          if (j0 + 64 < col_hi) C2D_FETCH_CHUNK(j0 + 64, u)         // chunk u consumed: refill with the next block's
+#endif
         }
       }
+#if C2D_EPILOGUE_PREFETCH
+#undef C2D_FETCH_CHUNK
+#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);      // 8 warps x 2 CTAs arrive on the leader
