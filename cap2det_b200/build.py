@@ -16,13 +16,6 @@ LIB_PATH = os.path.join(LIB_DIR, 'libcap2det_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
-# experiment switches of csrc/c2d_gemm_tc.cuh (warp-uniform TMA / MMA issue loops, early BN-shift loads in the
-# epilogue; profiles/r1_tc_issue_analysis.md);
-# off unless the environment asks for it, so the default library is the measured one
-for _switch in ('C2D_UNIFORM_ISSUE', 'C2D_EPILOGUE_EARLY_SHIFT', 'C2D_EPILOGUE_PREFETCH'):
-  if os.environ.get(_switch, '0') == '1':
-    FLAGS = FLAGS + ['-D%s=1' % _switch]
-
 
 def _sources():
   return sorted(f for f in os.listdir(CSRC) if f.endswith('.cu'))

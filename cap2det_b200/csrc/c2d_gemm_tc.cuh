@@ -27,30 +27,15 @@ constexpr int kStageBBytes = 16384;              // <= 128 rows x 64 bf16
 constexpr int kStageBytes = kStageABytes + kStageBBytes;
 constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
-// EXPERIMENT (off by default, not yet validated on a GPU): warp-uniform issue loops.  With the role decided from
-// `threadIdx.x >> 5` and the issuing thread picked by `lane == 0`, ptxas cannot prove that the operands of
-// UTMALDG / UTCHMMA are warp-uniform and wraps every one of them in a waterfall (ELECT + R2UR.BROADCAST x4-8 +
-// BRA.U.ANY): 150-240 SASS instructions per k-step on the MMA warp, which the r1 profile shows to be ~90 % busy
-// ISSUING while the tensor pipe idles ~45 % (profiles/r1_tc_issue_analysis.md).  The variant below makes the warp
-// index uniform (__shfl_sync), lets all 32 lanes walk the uniform control flow and predicates only the issue
-// instructions on elect.sync, so the operands live in uniform registers.  Build with -DC2D_UNIFORM_ISSUE=1.
-#ifndef C2D_UNIFORM_ISSUE
-#define C2D_UNIFORM_ISSUE 0
-#endif
-// EXPERIMENT (off by default, not yet validated on a GPU): issue the BN-shift loads of a 16-column chunk BEFORE the
-// tcgen05.ld of its accumulators, so that their latency overlaps the TMEM read instead of following it
-// (profiles/r1_tc_issue_analysis.md: the FADDs consuming them hold ~12 % of the samples as long_scoreboard).
-#ifndef C2D_EPILOGUE_EARLY_SHIFT
-#define C2D_EPILOGUE_EARLY_SHIFT 0
-#endif
-// EXPERIMENT (off by default, not yet validated on a GPU; 2-CTA kernel only): rolling prefetch of the epilogue's
-// global operands (previous bf16 value for accumulation, activation for the fused ReLU mask).  The first 64-column
-// block of a tile is requested BEFORE the wait for its accumulator, and the registers of a consumed chunk are
-// refilled at once with the same chunk of the next block, so that a memory latency is no longer exposed per block
-// (profiles/r1_tc_issue_analysis.md, finding 2).
-#ifndef C2D_EPILOGUE_PREFETCH
-#define C2D_EPILOGUE_PREFETCH 0
-#endif
+// Warp-uniform issue loops.  With the role decided from `threadIdx.x >> 5` and the issuing thread picked by
+// `lane == 0`, ptxas cannot prove that the operands of UTMALDG / UTCHMMA are warp-uniform and wraps every one of
+// them in a waterfall (ELECT + R2UR.BROADCAST x4-8 + BRA.U.ANY): 150-240 SASS instructions per k-step on the MMA
+// warp, which the r1 profile showed ~90 % busy ISSUING while the tensor pipe idled ~45 %
+// (profiles/r1_tc_issue_analysis.md).  The kernels therefore make the warp index uniform (__shfl_sync), let all 32
+// lanes walk the uniform control flow and predicate only the issue instructions on elect.sync, so the operands
+// live in uniform registers.  Measured on B200 (round 2, profiles/r2_tc_switches.md): conv fwd+dgrad 2.28 -> 1.93 ms
+// and wgrad 1.28 -> 1.18 ms per step.  The two epilogue experiments prepared with it (BN-shift loads before the
+// TMEM read; rolling prefetch of the accumulate / mask operands) measured no change and were removed.
 constexpr int kWgThreads = 192;
 constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
@@ -151,11 +136,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   TcPipe* pipe = reinterpret_cast<TcPipe*>(smem + kStages * kStageBytes);
-#if C2D_UNIFORM_ISSUE
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-#else
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&pipe->full[s], 1); mbar_init(&pipe->empty[s], 1); }
@@ -176,13 +157,8 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
 
   if (warp == 0) {
     // ===== TMA producer =====
-#if C2D_UNIFORM_ISSUE
     const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
     {
-#else
-    const bool issuer = true;
-    if (lane == 0) {
-#endif
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -210,9 +186,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-#if C2D_UNIFORM_ISSUE
     const bool mma_issuer = elect_one_sync();
-#endif
     const uint32_t idesc = make_idesc_bf16(128, p.n_tile, 0, 0);
     int ksteps = 0;
     for (int t = 0; t < p.taps; ++t) ksteps += p.tap_chunks[t];
@@ -227,7 +201,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
-#if C2D_UNIFORM_ISSUE
         {
           // descriptors built in warp-uniform code; +2 in the low word = +32 bytes (one UMMA_K of bf16)
           const uint32_t sA = smem_u32(smem + stage * kStageBytes);
@@ -244,21 +217,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             if (ks == ksteps - 1) umma_commit(&pipe->tmem_full[as]);
           }
         }
-#else
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * kStageBytes);
-          const uint32_t sB = sA + kStageABytes;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bdesc = make_smem_desc(sB + kk * 32, 16, 1024);
-            const uint32_t acc = (ks > 0 || kk > 0) ? 1u : 0u;
-            umma_f16(acc0, make_smem_desc(sA + kk * 32, 16, 1024), bdesc, idesc, acc);
-            umma_f16(acc0 + 128, make_smem_desc(sA + 16384 + kk * 32, 16, 1024), bdesc, idesc, acc);
-          }
-          umma_commit(&pipe->empty[stage]);
-          if (ks == ksteps - 1) umma_commit(&pipe->tmem_full[as]);
-        }
-#endif
         __syncwarp();
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -305,17 +263,6 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
           const int j = j0 + u * 16;
           const int col0 = nt * p.n_tile + j;
           if (j >= p.n_tile || col0 >= p.n_total) break;            // warp-uniform
-#if C2D_EPILOGUE_EARLY_SHIFT
-          float4 sh[4];
-          if (p.shift != nullptr && col0 < p.act_cols) {
-            const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sh[i] = __ldg(sp + i);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#endif
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
@@ -331,19 +278,12 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             const bool act = col0 < p.act_cols;
             if (p.shift != nullptr && act) {
-#if C2D_EPILOGUE_EARLY_SHIFT
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[4 * i] += sh[i].x; f[4 * i + 1] += sh[i].y; f[4 * i + 2] += sh[i].z; f[4 * i + 3] += sh[i].w;
-              }
-#else
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float4 s4 = __ldg(sp + i);
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
-#endif
             }
             if (p.relu && act) {
 #pragma unroll
@@ -436,11 +376,7 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Tc2Pipe* pipe = reinterpret_cast<Tc2Pipe*>(smem + k2Stages * k2StageBytes);
-#if C2D_UNIFORM_ISSUE
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-#else
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#endif
   const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
 
   if (threadIdx.x == 0) {
@@ -464,13 +400,8 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs; completion is credited to the leader's full barrier) =====
-#if C2D_UNIFORM_ISSUE
     const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
     {
-#else
-    const bool issuer = true;
-    if (lane == 0) {
-#endif
       int stage = 0; uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
@@ -499,9 +430,7 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
     }
   } else if (warp == 1) {
     // ===== MMA issuer (leader CTA only) =====
-#if C2D_UNIFORM_ISSUE
     const bool mma_issuer = elect_one_sync();
-#endif
     if (rank == 0) {
       const uint32_t idesc = make_idesc_bf16(256, p.n_tile, 0, 0);
       int ksteps = 0;
@@ -517,7 +446,6 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
         for (int ks = 0; ks < ksteps; ++ks) {
           mbar_wait(&pipe->full[stage], phase);
           tc_fence_after();
-#if C2D_UNIFORM_ISSUE
           {
             // descriptors built in warp-uniform code; +2 in the low word = +32 bytes (one UMMA_K of bf16)
             const uint32_t sA = smem_u32(smem + stage * k2StageBytes);
@@ -531,18 +459,6 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
               if (ks == ksteps - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
             }
           }
-#else
-          if (lane == 0) {
-            const uint32_t sA = smem_u32(smem + stage * k2StageBytes);
-            const uint32_t sB = sA + k2StageABytes;
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_f16_2cta(acc0, make_smem_desc(sA + kk * 32, 16, 1024), make_smem_desc(sB + kk * 32, 16, 1024), idesc,
-                            (ks > 0 || kk > 0) ? 1u : 0u);
-            umma_commit_2cta(&pipe->empty[stage], 3);                 // frees the slot in BOTH CTAs
-            if (ks == ksteps - 1) umma_commit_2cta(&pipe->tmem_full[as], 3);
-          }
-#endif
           __syncwarp();
           if (++stage == k2Stages) { stage = 0; phase ^= 1; }
         }
@@ -558,33 +474,6 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-#if C2D_EPILOGUE_PREFETCH
-      const int r = q * 32 + lane;                  // row inside this CTA's half tile
-      const long long orow = conv_out_row(p, 2 * mt + (int)rank, r);
-      const bool bf16_rmw = !p.out_f32 && p.accum;
-      uint4 oldv[4][2], mskv[4][2];
-      // chunk u of the 64-column block that starts at column jb of this tile -> oldv[u], mskv[u]
-#define C2D_FETCH_CHUNK(jb, u)                                                                                    \
-      {                                                                                                           \
-        const int fc0 = nt * p.n_tile + (jb) + (u) * 16;                                                          \
-        const bool flive = orow >= 0 && (jb) + (u) * 16 < col_hi && fc0 < p.n_total;                              \
-        oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);                                                     \
-        mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);                 \
-        if (flive && bf16_rmw)                                                                                    \
-          ld_global_256(reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + fc0,          \
-                        oldv[u][0], oldv[u][1]);                                                                  \
-        if (flive && p.mask != nullptr && fc0 < p.mask_cols)                                                      \
-          ld_global_256(p.mask + orow * p.mask_ld + fc0, mskv[u][0], mskv[u][1]);                                 \
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) C2D_FETCH_CHUNK(col_lo, u)      // in flight while the accumulator completes
-      mbar_wait(&pipe->tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-#pragma unroll 1
-      for (int j0 = col_lo; j0 < col_hi; j0 += 64) {
-        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
-#else
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = q * 32 + lane;                  // row inside this CTA's half tile
@@ -610,23 +499,11 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             ld_global_256(y, mskv[u][0], mskv[u][1]);
           }
         }
-#endif
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int j = j0 + u * 16;
           const int col0 = nt * p.n_tile + j;
           if (j >= col_hi || col0 >= p.n_total) break;              // warp-uniform
-#if C2D_EPILOGUE_EARLY_SHIFT
-          float4 sh[4];
-          if (p.shift != nullptr && col0 < p.act_cols) {
-            const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sh[i] = __ldg(sp + i);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sh[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#endif
           uint32_t v[16];
           tmem_ld_32x16(taddr + j, v);
           tmem_ld_wait();
@@ -642,19 +519,12 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
             const bool act = col0 < p.act_cols;
             if (p.shift != nullptr && act) {
-#if C2D_EPILOGUE_EARLY_SHIFT
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[4 * i] += sh[i].x; f[4 * i + 1] += sh[i].y; f[4 * i + 2] += sh[i].z; f[4 * i + 3] += sh[i].w;
-              }
-#else
               const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 float4 s4 = __ldg(sp + i);
                 f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
               }
-#endif
             }
             if (p.relu && act) {
 #pragma unroll
@@ -700,14 +570,8 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
               st_global_256(o, w0, w1);
             }
           }
-#if C2D_EPILOGUE_PREFETCH
-          if (j0 + 64 < col_hi) C2D_FETCH_CHUNK(j0 + 64, u)         // chunk u consumed: refill with the next block's
-#endif
         }
       }
-#if C2D_EPILOGUE_PREFETCH
-#undef C2D_FETCH_CHUNK
-#endif
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);      // 8 warps x 2 CTAs arrive on the leader
@@ -820,11 +684,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + kWgStages * kWgStageBytes;
   WgPipe* pipe = reinterpret_cast<WgPipe*>(ones + kWgOnesBytes);
-#if C2D_UNIFORM_ISSUE
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-#else
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#endif
   for (int i = threadIdx.x; i < kWgOnesBytes / 4; i += blockDim.x)
     reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;          // bf16 1.0 pairs
   fence_proxy_async();
@@ -845,13 +705,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
   const int num_items = p.taps * p.ci_tiles * p.splits_sum;
 
   if (warp == 0) {
-#if C2D_UNIFORM_ISSUE
     const bool issuer = elect_one_sync();            // all lanes walk the loops, this one issues
     {
-#else
-    const bool issuer = true;
-    if (lane == 0) {
-#endif
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         const WgItem wi = wg_decode(p, item);
@@ -877,9 +732,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
           mbar_wait(&pipe->empty[stage], phase ^ 1);
           uint8_t* sA = smem + stage * kWgStageBytes;
           uint8_t* sB = sA + 32768;
-#if !C2D_UNIFORM_ISSUE
-          mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
-#endif
           int px0 = 0, py0 = 0, pn = s * p.rois_per_step;
           if (p.flat == 2) {
             const int per_img = p.img_tiles_x * p.img_tiles_y;
@@ -890,9 +742,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
             py0 *= 8;
           }
           if (issuer) {
-#if C2D_UNIFORM_ISSUE
             mbar_arrive_expect_tx(&pipe->full[stage], stage_tx);
-#endif
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               if (g >= a_groups) break;
@@ -910,9 +760,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-#if C2D_UNIFORM_ISSUE
     const bool mma_issuer = elect_one_sync();
-#endif
     const uint32_t idesc = make_idesc_bf16(128, p.ci_tile, 1, 1);
     const uint32_t idesc_ones = make_idesc_bf16(128, 16, 1, 1);
     const uint32_t s_ones = smem_u32(ones);
@@ -928,7 +776,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
       for (int s = s0; s < s1; ++s) {
         mbar_wait(&pipe->full[stage], phase);
         tc_fence_after();
-#if C2D_UNIFORM_ISSUE
         {
           // descriptors built in warp-uniform code; +128 in the low word = +2048 bytes (16 reduction rows)
           const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
@@ -950,28 +797,6 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapY, const __grid_constant_
             if (s == s1 - 1) umma_commit(&pipe->tmem_full);
           }
         }
-#else
-        if (lane == 0) {
-          const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
-          const uint32_t sB = sA + 32768;
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {   // 16 reduction rows per MMA = two 8-row swizzle atoms
-            const uint32_t acc = (s > s0 || kk > 0) ? 1u : 0u;
-            const uint64_t bdesc = make_smem_desc(sB + kk * 2048, 8192, 1024);
-            const uint64_t a0 = make_smem_desc(sA + kk * 2048, 8192, 1024);
-            const uint64_t a1 = make_smem_desc(sA + 16384 + kk * 2048, 8192, 1024);
-            umma_f16(tmem_base, a0, bdesc, idesc, acc);
-            if (two) umma_f16(tmem_base + 256, a1, bdesc, idesc, acc);
-            if (want_shift) {
-              const uint64_t odesc = make_smem_desc(s_ones + kk * 2048, 8192, 1024);
-              umma_f16(tmem_base + kWgOnesCol, a0, odesc, idesc_ones, acc);
-              if (two) umma_f16(tmem_base + 256 + kWgOnesCol, a1, odesc, idesc_ones, acc);
-            }
-          }
-          umma_commit(&pipe->empty[stage]);
-          if (s == s1 - 1) umma_commit(&pipe->tmem_full);
-        }
-#endif
         __syncwarp();
         if (++stage == kWgStages) { stage = 0; phase ^= 1; }
       }

@@ -936,23 +936,14 @@ def test_get_input_fn_parallel_decode_equals_sequential(tmp_path):
     assert runs[0] == runs[1] and len(runs[0]) > 0
 
 
-def test_default_build_has_no_experimental_switches():
-  """The kernels measured in profiles/ are the default build; the prepared experiments of csrc/c2d_gemm_tc.cuh
-  (profiles/r1_tc_issue_analysis.md) only compile in when their environment switch is set."""
-  import importlib
+def test_build_has_no_experimental_switches():
+  """One library: the round-1 experiment switches were measured (profiles/r2_tc_switches.md), the uniform-issue
+  variant became THE code and the two epilogue variants were deleted -- no -D switch, no #if variant left."""
   import os
   from cap2det_b200 import build
-  saved = {k: os.environ.pop(k, None) for k in ('C2D_UNIFORM_ISSUE', 'C2D_EPILOGUE_EARLY_SHIFT', 'C2D_EPILOGUE_PREFETCH')}
-  try:
-    assert not [f for f in importlib.reload(build).FLAGS if f.startswith('-DC2D_')]
-    os.environ['C2D_UNIFORM_ISSUE'] = '1'
-    assert '-DC2D_UNIFORM_ISSUE=1' in importlib.reload(build).FLAGS
-  finally:
-    os.environ.pop('C2D_UNIFORM_ISSUE', None)
-    for k, v in saved.items():
-      if v is not None:
-        os.environ[k] = v
-    importlib.reload(build)
-  text = open(os.path.join(os.path.dirname(build.__file__), 'csrc', 'c2d_gemm_tc.cuh')).read()
-  for macro in ('C2D_UNIFORM_ISSUE', 'C2D_EPILOGUE_EARLY_SHIFT', 'C2D_EPILOGUE_PREFETCH'):
-    assert '#define %s 0' % macro in text
+  assert not [f for f in build.FLAGS if f.startswith('-D')]
+  csrc = os.path.join(os.path.dirname(build.__file__), 'csrc')
+  for name in os.listdir(csrc):
+    text = open(os.path.join(csrc, name)).read()
+    for macro in ('C2D_UNIFORM_ISSUE', 'C2D_EPILOGUE_EARLY_SHIFT', 'C2D_EPILOGUE_PREFETCH'):
+      assert macro not in text.replace('-D' + macro, ''), (name, macro)
