@@ -7,6 +7,7 @@
 // (no FMA contraction), so floor/ceil/in-range decisions match the oracle bit for bit.
 // The [N,14,14,C] crop tensor (903 MB / image in the TF graph) is never materialised:
 // HBM traffic is the feature map (L2 resident, 5.5 MB) + the pooled output.
+#include <stdlib.h>
 #include "c2d_common.cuh"
 
 namespace c2d {
@@ -176,6 +177,215 @@ roi_crop_maxpool_fwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1, round 2: separable, row-rolling forward.
+//
+// TF's kernel interpolates along x first (top = TL + (TR - TL) * xl, bottom likewise) and then along y, so the
+// x-interpolated value H(row, cx) of a feature-map row depends on the row and the sample column only.  Consecutive
+// sample rows of a proposal mostly touch the SAME feature rows (half of all proposals have a sample spacing below
+// one feature pixel), so H is computed once per DISTINCT row and kept in registers while cy advances: per channel
+// 3 * (14 * distinct_rows + 196) rounded operations instead of 9 * 196, and distinct_rows * (2..4) loads per pooled
+// column instead of 4..16 per pooling window (394 -> 245 sixteen-byte loads per proposal and channel quad on the
+// benchmark boxes).  Every sample is still t + (b - t) * yl of the same two correctly rounded x-lerps, so the
+// result is bit-identical to the oracle.
+//
+// Work item = (pooled column px, channel quad): two sample columns, whose corner columns fall into one of three
+// patterns (same cell / adjacent cells / disjoint) -> a template parameter, hoisted out of the row loop.  The row
+// pattern of every sample row (re-use both rows / previous bottom row becomes the top row / load both) is
+// precomputed per proposal in shared memory and is warp-uniform.  The subtraction and the multiplication use the
+// sm_100 packed fp32 instructions (FFMA2 / FMUL2, each lane IEEE round-to-nearest): same results as the scalar
+// sequence in two thirds of the issue slots (profiles/r2/microbench_pipes.txt).
+// All items of a proposal run in ONE CTA (7 x 144 = 1008 threads for 576 channels), so the corner columns that
+// neighbouring pooled columns share are served by L1.
+// ---------------------------------------------------------------------------------------------
+// Per sample row, resolved once per proposal: the two cached x-interpolated feature rows live in the register sets
+// A and B of every thread; the plan says which feature row (float4 offset) to load into which set before this
+// sample row is interpolated, and which set is the top row -- so "the previous bottom row becomes the top row"
+// moves no registers and costs no decision in the inner loop.
+enum { kRowLoadA = 1, kRowLoadB = 2, kRowTopIsB = 4, kRowCopy = 8, kRowValid = 16 };
+struct RowPlan { int off_a, off_b; float yl; int flags; };
+
+struct RoiPlan {
+  RoiCoords sc;
+  RowPlan row[kMaxCrop + 1];           // one 16-byte shared-memory load per sample row (+1: the loop prefetches one ahead)
+  unsigned char xpat[kMaxCrop / 2];    // axis_pattern of the two sample columns of a pooled column
+  int all_valid;                       // every sample of the proposal lies inside the map (the usual case)
+};
+
+__device__ __forceinline__ void roi_setup_plan(RoiPlan& pl, float4 box, int Hf, int Wf, int C4, int crop) {
+  roi_setup_coords(pl.sc, box, Hf, Wf, crop);
+  __syncthreads();
+  const int t = threadIdx.x;
+  if (t == 0) {
+    // sequential over <= 32 sample rows: which register set holds which feature row
+    int row_a = -1, row_b = -1, top_is_b = 0, ok = 1;
+    for (int cy = 0; cy < crop; ++cy) {
+      const int lo = pl.sc.lo[0][cy], hi = pl.sc.hi[0][cy];
+      int flags = pl.sc.valid[0][cy] ? kRowValid : 0;
+      ok &= pl.sc.valid[0][cy] & pl.sc.valid[1][cy];
+      RowPlan r;
+      r.off_a = r.off_b = 0;
+      const int cur_top = top_is_b ? row_b : row_a, cur_bot = top_is_b ? row_a : row_b;
+      if (!(lo == cur_top && hi == cur_bot)) {
+        if (lo == cur_bot && lo != cur_top) top_is_b ^= 1;           // previous bottom row is the new top row
+        else {                                                       // new top row
+          if (top_is_b) { row_b = lo; flags |= kRowLoadB; r.off_b = lo * Wf * C4; }
+          else { row_a = lo; flags |= kRowLoadA; r.off_a = lo * Wf * C4; }
+        }
+        if (hi == lo) flags |= kRowCopy;                             // integer coordinate: bottom = top (copied)
+        else if (top_is_b) { flags |= kRowLoadA; r.off_a = hi * Wf * C4; }
+        else { flags |= kRowLoadB; r.off_b = hi * Wf * C4; }
+        if (top_is_b) row_a = hi; else row_b = hi;
+      }
+      if (top_is_b) flags |= kRowTopIsB;
+      r.yl = pl.sc.lerp[0][cy];
+      r.flags = flags;
+      pl.row[cy] = r;
+    }
+    pl.row[crop] = pl.row[crop - 1];
+    pl.all_valid = ok;
+  } else if (t >= 32 && t < 32 + (crop >> 1)) {
+    pl.xpat[t - 32] = (unsigned char)axis_pattern(pl.sc, 1, 2 * (t - 32));
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float2 lerp2_rn(float2 a, float2 b, float2 t) {
+  // a + (b - a) * t, three separately rounded operations per lane.  fma(a, -1, b) is the correctly rounded b - a.
+  // The final addition is scalar ON PURPOSE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
+  // (even with --fmad=false), which would change the rounding; FMUL2 followed by two FADDs is left alone
+  // (checked in the SASS and by the bit-exact parity test against the oracle).
+  const float2 p = __fmul2_rn(__ffma2_rn(a, make_float2(-1.f, -1.f), b), t);
+  return make_float2(__fadd_rn(a.x, p.x), __fadd_rn(a.y, p.y));
+}
+__device__ __forceinline__ float4 lerp4_rn(float4 a, float4 b, float2 t) {
+  const float2 lo = lerp2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), t);
+  const float2 hi = lerp2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), t);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// The ALU pipe (integer add / logic / compare / min-max, 16 lanes per SM sub-partition) is what bounds this kernel
+// (profiles/r2_roi_kernels.md), the FMA pipe has room: addresses are formed with ONE mad.wide.u32 each (FMA pipe).
+__device__ __forceinline__ const float4* roi_addr(const float4* base, unsigned idx) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(idx), "l"(reinterpret_cast<unsigned long long>(base)));
+  return reinterpret_cast<const float4*>(r);
+}
+// x-interpolated values of one feature row at the two sample columns of a pooled column.  row = the feature row of
+// the image as float4; c0..c3 = float4 index of this thread's channel quad at the corner columns (l0, r0, l1, r1).
+template <int XP>
+__device__ __forceinline__ void roi_xrow(const float4* __restrict__ row, unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+                                         float2 xl0, float2 xl1, float4& h0, float4& h1) {
+  if (XP == 0) {
+    const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1));
+    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(a, b, xl1);
+  } else if (XP == 1) {
+    const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1)), c = __ldg(roi_addr(row, c3));
+    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(b, c, xl1);
+  } else {
+    const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1)), c = __ldg(roi_addr(row, c2)),
+                 d = __ldg(roi_addr(row, c3));
+    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(c, d, xl1);
+  }
+}
+
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+  return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+// 2-bit arg-max index of one channel, shifted to its place in the code byte: bit 0 = column of the winning sample
+// (taken from the winning row), bit 1 = its row.  A later sample wins only when STRICTLY greater (first maximum).
+template <int SH>
+__device__ __forceinline__ unsigned code_field(float v00, float v01, float v10, float v11, float a, float b) {
+  const bool s = b > a;
+  const bool col = s ? (v11 > v10) : (v01 > v00);
+  return (col ? (1u << SH) : 0u) + (s ? (2u << SH) : 0u);
+}
+
+// One work item: pooled column px of channel quad q, all pooled rows.
+template <int XP, bool CODES, bool ALL_VALID, typename OutT>
+__device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const RoiPlan& pl, int px, int q, int C4, int crop,
+                                          OutT* __restrict__ o, unsigned char* __restrict__ cd) {
+  const int cx0 = 2 * px, cx1 = cx0 + 1, hp = crop >> 1;
+  const unsigned c0 = pl.sc.lo[1][cx0] * C4 + q, c1 = pl.sc.hi[1][cx0] * C4 + q, c2 = pl.sc.lo[1][cx1] * C4 + q,
+                 c3 = pl.sc.hi[1][cx1] * C4 + q;
+  const float xa = pl.sc.lerp[1][cx0], xb = pl.sc.lerp[1][cx1];
+  const float2 xl0 = make_float2(xa, xa), xl1 = make_float2(xb, xb);
+  const bool vx0 = pl.sc.valid[1][cx0] != 0, vx1 = pl.sc.valid[1][cx1] != 0;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 A0 = zero, A1 = zero, B0 = zero, B1 = zero;
+  RowPlan rp = pl.row[0];
+  for (int py = 0; py < hp; ++py) {
+    float4 a, b, t0, t1, u0, u1;           // t = the two samples of the top sample row, u = of the bottom one
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int cy = 2 * py + r;
+      const RowPlan nx = pl.row[cy + 1];                          // next row's plan: its latency hides behind this row
+      const int f = rp.flags;
+      if (__builtin_expect((f & (kRowLoadA | kRowLoadB)) != 0, 0)) {        // warp-uniform; most sample rows re-use both rows
+        if ((f & (kRowLoadA | kRowLoadB)) == (kRowLoadA | kRowLoadB)) {      // all loads of both rows in flight together
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, A0, A1);
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, B0, B1);
+        } else if (f & kRowLoadA) {
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, A0, A1);
+        } else {
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, B0, B1);
+        }
+      }
+      if (__builtin_expect((f & kRowCopy) != 0, 0)) { if (f & kRowTopIsB) { A0 = B0; A1 = B1; } else { B0 = A0; B1 = A1; } }
+      const float2 yl2 = make_float2(rp.yl, rp.yl);
+      float4 v0, v1;
+      if (f & kRowTopIsB) { v0 = lerp4_rn(B0, A0, yl2); v1 = lerp4_rn(B1, A1, yl2); }
+      else { v0 = lerp4_rn(A0, B0, yl2); v1 = lerp4_rn(A1, B1, yl2); }
+      if (!ALL_VALID) {
+        const bool vy = (f & kRowValid) != 0;
+        if (!(vy && vx0)) v0 = zero;
+        if (!(vy && vx1)) v1 = zero;
+      }
+      if (r == 0) { a = max4(v0, v1); t0 = v0; t1 = v1; }
+      else { b = max4(v0, v1); u0 = v0; u1 = v1; }
+      rp = nx;
+    }
+    st4(o + (size_t)py * hp * (4 * C4), max4(a, b));
+    if (CODES) {
+      const unsigned code = code_field<0>(t0.x, t1.x, u0.x, u1.x, a.x, b.x) + code_field<2>(t0.y, t1.y, u0.y, u1.y, a.y, b.y) +
+                            code_field<4>(t0.z, t1.z, u0.z, u1.z, a.z, b.z) + code_field<6>(t0.w, t1.w, u0.w, u1.w, a.w, b.w);
+      cd[(size_t)py * hp * C4] = (unsigned char)code;
+    }
+  }
+}
+
+template <bool CODES, typename OutT>
+__global__ void __launch_bounds__(448, 2)
+roi_crop_maxpool_fwd_rows_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
+                                 int P, int crop, OutT* __restrict__ out, unsigned char* __restrict__ codes) {
+  __shared__ RoiPlan pl;
+  const int roi = blockIdx.x;
+  const int b = roi / P;
+  const int C4 = Cf >> 2, hp = crop >> 1;
+  roi_setup_plan(pl, boxes[roi], Hf, Wf, C4, crop);
+  const float4* img4 = reinterpret_cast<const float4*>(fmap + (size_t)b * Hf * Wf * Cf);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = (blockDim.x >> 5) / hp;
+  const int px = warp / W;
+  if (px >= hp) return;
+  OutT* oroi = out + (size_t)roi * hp * hp * Cf + (size_t)px * Cf;
+  unsigned char* croi = CODES ? codes + (size_t)roi * hp * hp * C4 + px * C4 : nullptr;
+  const int xp = pl.xpat[px];
+  const bool all_valid = pl.all_valid != 0;
+  for (int q = (warp - px * W) * 32 + lane; q < C4; q += 32 * W) {
+    OutT* o = oroi + 4 * q;
+    unsigned char* cd = CODES ? croi + q : nullptr;
+    if (all_valid) {
+      if (xp == 0) roi_strip<0, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
+      else if (xp == 1) roi_strip<1, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
+      else roi_strip<2, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
+    } else {
+      if (xp == 0) roi_strip<0, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
+      else if (xp == 1) roi_strip<1, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
+      else roi_strip<2, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
+    }
+  }
+}
+
 // Scatter the gradient of crop sample (cy,cx) for a channel quad: g holds the 4 channel gradients,
 // already zeroed for the channels whose max-pool arg-max is a different sample.  One 16-byte
 // red.global.add.v4.f32 per corner instead of four scalar atomics (the SM issues ~1 atomic lane-op
@@ -320,6 +530,153 @@ roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1', round 2: backward from the arg-max codes with the gradient PRE-REDUCED PER PROPOSAL AND PIXEL.
+//
+// Measured (profiles/r2/microbench_l2.txt): the L2 adds fp32 at ~6 TB/s of addends whatever issues them (lane
+// red.global.add.v4.f32: 6.0-6.3 TB/s, TMA cp.reduce.async.bulk: 5.7 TB/s), and the round-1 kernel, 7.1 vector
+// atomics per (pooling window, channel quad) = 3.2 GB of addends per step, ran at exactly that limit.  So the only
+// lever is FEWER ADDENDS: a proposal touches rows x cols distinct pixels (167 on average on the benchmark boxes,
+// against 348 atomics per channel quad before), and one addend per distinct pixel is the minimum a per-proposal
+// scatter can send.
+//
+// One thread owns one channel quad of one proposal and walks the proposal's distinct feature rows in ascending
+// order.  For a row it first gathers dH[cx] = sum over the sample rows cy whose top / bottom row this is of
+// wy(cy) * G(cy, cx), G = the pooled gradient where the arg-max code selects sample (cy, cx), else 0 -- 14 float4
+// accumulators with compile-time indices -- and then walks the 14 sample columns, whose left corner columns are
+// non-decreasing, with two rolling accumulators (pixel `cur` and `cur + 1`): an accumulator is sent with ONE
+// red.global.add.v4.f32 when the walk leaves its pixel.  All control flow depends on the proposal only
+// (warp-uniform).  (row, sample row, weight) events are sorted once per CTA in shared memory.
+// The weights are applied as wx * (wy * g) like CropAndResizeGradImage, but sums over samples are formed before
+// the atomic, so results differ from the round-1 kernel by fp32 summation order only (the atomics never had one).
+// ---------------------------------------------------------------------------------------------
+struct RoiBwdPlan {
+  RoiCoords sc;
+  int n_ev;
+  int ev_row[2 * kMaxCrop];      // feature row
+  int ev_cy[2 * kMaxCrop];       // sample row
+  float ev_w[2 * kMaxCrop];      // 1 - yl (top row) or yl (bottom row)
+  int key[2 * kMaxCrop];
+};
+
+__device__ __forceinline__ void roi_setup_events(RoiBwdPlan& pl, float4 box, int Hf, int Wf, int crop) {
+  roi_setup_coords(pl.sc, box, Hf, Wf, crop);
+  __syncthreads();
+  const int e = threadIdx.x;
+  int key = 0x7fffffff;
+  if (e < 2 * crop) {
+    const int cy = e >> 1;
+    const float yl = pl.sc.lerp[0][cy];
+    const bool live = pl.sc.valid[0][cy] && ((e & 1) == 0 || yl != 0.f);   // a zero weight adds nothing
+    if (live) key = ((e & 1) ? pl.sc.hi[0][cy] : pl.sc.lo[0][cy]) * 64 + e;
+    pl.key[e] = key;
+  }
+  __syncthreads();
+  if (e < 2 * crop && key != 0x7fffffff) {
+    int rank = 0;
+    for (int f = 0; f < 2 * crop; ++f) rank += pl.key[f] < key ? 1 : 0;
+    const int cy = e >> 1;
+    const float yl = pl.sc.lerp[0][cy];
+    pl.ev_row[rank] = key >> 6; pl.ev_cy[rank] = cy; pl.ev_w[rank] = (e & 1) ? yl : 1.0f - yl;
+  }
+  if (e == 0) {
+    int n = 0;
+    for (int f = 0; f < 2 * crop; ++f) n += pl.key[f] != 0x7fffffff ? 1 : 0;
+    pl.n_ev = n;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+  if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(p), v);
+}
+
+template <int HP, typename GradT>
+__global__ void __launch_bounds__(160)
+roi_crop_maxpool_bwd_rows_kernel(int Hf, int Wf, int Cf, const float4* __restrict__ boxes, int P,
+                                 const unsigned char* __restrict__ codes, const GradT* __restrict__ dout,
+                                 float* __restrict__ dfmap) {
+  constexpr int CROP = 2 * HP;
+  __shared__ RoiBwdPlan pl;
+  const int roi = blockIdx.x;
+  const int b = roi / P;
+  roi_setup_events(pl, boxes[roi], Hf, Wf, CROP);
+  const int C4 = Cf >> 2;
+  const int n_ev = pl.n_ev;
+  if (n_ev == 0) return;
+  const GradT* go = dout + (size_t)roi * HP * HP * Cf;
+  const unsigned char* cd = codes + (size_t)roi * HP * HP * C4;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = threadIdx.x; q < C4; q += blockDim.x) {
+    float* dimg = dfmap + (size_t)b * Hf * Wf * Cf + 4 * q;
+    float4 dH[CROP];
+#pragma unroll
+    for (int i = 0; i < CROP; ++i) dH[i] = zero;
+    int cur_row = pl.ev_row[0];
+    for (int e = 0; e <= n_ev; ++e) {
+      const int row = e < n_ev ? pl.ev_row[e] : -1;
+      if (row != cur_row) {
+        // ---- send row cur_row: walk the sample columns with two rolling pixel accumulators ----
+        float* drow = dimg + (size_t)cur_row * Wf * Cf;
+        float4 accL = zero, accR = zero;
+        int cur = -2;
+        bool usedR = false;
+#pragma unroll
+        for (int cx = 0; cx < CROP; ++cx) {
+          if (pl.sc.valid[1][cx]) {                                   // warp-uniform
+            const int l = pl.sc.lo[1][cx];
+            const float xl = pl.sc.lerp[1][cx];
+            if (l != cur) {
+              if (cur >= 0) {
+                red_add4(drow + (size_t)cur * Cf, accL);
+                if (l == cur + 1) accL = accR;
+                else { if (usedR) red_add4(drow + (size_t)(cur + 1) * Cf, accR); accL = zero; }
+              }
+              accR = zero; usedR = false; cur = l;
+            }
+            const float wl = 1.0f - xl;
+            const float4 h = dH[cx];
+            accL.x += wl * h.x; accL.y += wl * h.y; accL.z += wl * h.z; accL.w += wl * h.w;
+            if (xl != 0.f) {
+              accR.x += xl * h.x; accR.y += xl * h.y; accR.z += xl * h.z; accR.w += xl * h.w;
+              usedR = true;
+            }
+          }
+          dH[cx] = zero;
+        }
+        if (cur >= 0) {
+          red_add4(drow + (size_t)cur * Cf, accL);
+          if (usedR) red_add4(drow + (size_t)(cur + 1) * Cf, accR);
+        }
+        cur_row = row;
+      }
+      if (e == n_ev) break;
+      // ---- gather sample row cy into dH with weight w ----
+      const int cy = pl.ev_cy[e];
+      const float w = pl.ev_w[e];
+      const int py = cy >> 1;
+      const unsigned rsel = (unsigned)(cy & 1) << 1;                 // codes 2r, 2r+1 belong to this sample row
+      const GradT* gp = go + (size_t)py * HP * Cf + 4 * q;
+      const unsigned char* cp = cd + (size_t)py * HP * C4 + q;
+      float4 g[HP];
+      unsigned code[HP];
+#pragma unroll
+      for (int px = 0; px < HP; ++px) { g[px] = ld4(gp + (size_t)px * Cf); code[px] = cp[px * C4]; }
+#pragma unroll
+      for (int px = 0; px < HP; ++px) {
+        const unsigned k = code[px] ^ (rsel * 0x55u);                // per channel: 0 / 1 now mean "left / right sample of this row"
+        const float gx = w * g[px].x, gy = w * g[px].y, gz = w * g[px].z, gw = w * g[px].w;
+        float4& d0 = dH[2 * px];
+        float4& d1 = dH[2 * px + 1];
+        d0.x += (k & 0x03u) == 0u ? gx : 0.f;  d1.x += (k & 0x03u) == 1u ? gx : 0.f;
+        d0.y += (k & 0x0cu) == 0u ? gy : 0.f;  d1.y += (k & 0x0cu) == 0x04u ? gy : 0.f;
+        d0.z += (k & 0x30u) == 0u ? gz : 0.f;  d1.z += (k & 0x30u) == 0x10u ? gz : 0.f;
+        d0.w += (k & 0xc0u) == 0u ? gw : 0.f;  d1.w += (k & 0xc0u) == 0x40u ? gw : 0.f;
+      }
+    }
+  }
+}
+
 static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k, int pool_s) {
   C2D_CHECK_ARG(B >= 0 && P >= 0 && Hf >= 1 && Wf >= 1, "roi: bad shape B=%d P=%d Hf=%d Wf=%d", B, P, Hf, Wf);
   C2D_CHECK_ARG(Cf >= 4 && Cf % 4 == 0, "roi: feature depth %d must be a multiple of 4", Cf);
@@ -356,12 +713,27 @@ int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int
   C2D_CHECK_ARG(out_dtype == C2D_F32 || out_dtype == C2D_BF16, "roi: bad dtype %d", out_dtype);
   if (B * P == 0) return C2D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (out_dtype == C2D_F32)
-    roi_crop_maxpool_fwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
-                                                             (float*)out, codes);
-  else
-    roi_crop_maxpool_fwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
-                                                                     crop_size, (__nv_bfloat16*)out, codes);
+  static const char* impl = getenv("C2D_ROI_FWD");            // TEMPORARY A/B switch: "old" = round-1 kernel
+  if ((impl != nullptr && strcmp(impl, "old") == 0) || crop_size > 28) {
+    if (out_dtype == C2D_F32)
+      roi_crop_maxpool_fwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
+                                                               (float*)out, codes);
+    else
+      roi_crop_maxpool_fwd_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,
+                                                                       crop_size, (__nv_bfloat16*)out, codes);
+  } else {
+    // one CTA per proposal: (crop / 2) pooled columns x W warps, lanes = channel quads
+    const int hp = crop_size / 2, C4 = Cf / 4;
+    int W = (C4 + 95) / 96;                       // <= 3 quads per lane; 2 warps per column at 576 channels
+    while (W > 1 && hp * W * 32 > 448) --W;
+    const int threads = hp * W * 32;
+#define C2D_ROI_FWD_LAUNCH(CODES, T)                                                                                  \
+    roi_crop_maxpool_fwd_rows_kernel<CODES, T><<<B * P, threads, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,   \
+                                                                          crop_size, (T*)out, codes)
+    if (out_dtype == C2D_F32) { if (codes) C2D_ROI_FWD_LAUNCH(true, float); else C2D_ROI_FWD_LAUNCH(false, float); }
+    else { if (codes) C2D_ROI_FWD_LAUNCH(true, __nv_bfloat16); else C2D_ROI_FWD_LAUNCH(false, __nv_bfloat16); }
+#undef C2D_ROI_FWD_LAUNCH
+  }
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -399,7 +771,19 @@ int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* b
   C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
   if (P == 0) return C2D_OK;
   C2D_CHECK_ARG(codes != nullptr, "roi_bwd_codes: null codes");
-  if (dout_dtype == C2D_F32)
+  static const char* impl = getenv("C2D_ROI_BWD");            // TEMPORARY A/B switch: "old" = round-1 kernel
+  const bool rows = crop_size == 14 && impl != nullptr && strcmp(impl, "rows") == 0;   // opt-in: measured slower (0.90 vs 0.61 ms)
+  if (rows) {
+    const int C4 = Cf / 4;
+    int threads = ((C4 + 31) / 32) * 32;
+    threads = threads < 64 ? 64 : (threads > 160 ? 160 : threads);
+    if (dout_dtype == C2D_F32)
+      roi_crop_maxpool_bwd_rows_kernel<7, float><<<B * P, threads, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, codes,
+                                                                           (const float*)dout, dfmap);
+    else
+      roi_crop_maxpool_bwd_rows_kernel<7, __nv_bfloat16><<<B * P, threads, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, codes,
+                                                                                   (const __nv_bfloat16*)dout, dfmap);
+  } else if (dout_dtype == C2D_F32)
     roi_crop_maxpool_bwd_codes_kernel<float><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes,
                                                                    (const float*)dout, dfmap);
   else

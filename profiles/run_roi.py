@@ -26,6 +26,8 @@ def main():
   ap.add_argument('--images', type=int, default=2)
   ap.add_argument('--proposals', type=int, default=2000)
   ap.add_argument('--dtype', default='bf16', choices=['bf16', 'f32'])
+  ap.add_argument('--dump', default=None, help='save forward output, codes and backward output to this file')
+  ap.add_argument('--compare', default=None, help='compare them with a file written by --dump (other kernel version)')
   ap.add_argument('--check', action='store_true', help='compare the forward with the CPU oracle (first 64 ROIs / image)')
   args = ap.parse_args()
   from cap2det_b200 import capi, synthetic
@@ -34,6 +36,7 @@ def main():
   torch.cuda.set_device(0)
   B, P, Cf = args.images, args.proposals, 576
   rng = np.random.default_rng(1000)
+  torch.manual_seed(1000)
   fmap = torch.from_numpy(synthetic.make_feature_map(rng, B)).to(dev)
   props = torch.from_numpy(synthetic.make_proposals(rng, B, P)).to(dev)
   _, Hf, Wf, _ = fmap.shape
@@ -42,7 +45,7 @@ def main():
   n_code = capi.load().c2d_roi_argmax_code_bytes(B * P, Cf, 14)
   codes = torch.empty((n_code,), dtype=torch.uint8, device=dev)
   x0 = torch.empty((B * P, 7, 7, Cf), dtype=dt, device=dev)
-  g0 = (torch.randn(x0.shape, device=dev) * (torch.rand(x0.shape, device=dev) < 0.5)).to(dt)   # post-ReLU-like: half zeros
+  g0 = torch.randn(x0.shape, device=dev).to(dt)          # dense, like the data gradient the head hands back
   dfm = torch.empty_like(fmap)
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
   fwd = lambda: call('c2d_roi_crop_maxpool_fwd_codes', ptr(fmap), B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(x0),
@@ -75,6 +78,14 @@ def main():
     out[name] = dict(ms=ms, all_ms=all_ms, algorithmic_bytes=nbytes, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / peak)
     total_ms += ms; total_bytes += nbytes
   out['group'] = dict(ms=total_ms, gbs=total_bytes / total_ms / 1e6, frac=total_bytes / total_ms / 1e6 / peak)
+  if args.dump:
+    fwd(); bwd(); torch.cuda.synchronize()
+    torch.save(dict(x0=x0.cpu(), codes=codes.cpu(), dfm=dfm.cpu()), args.dump)
+  if args.compare:
+    fwd(); bwd(); torch.cuda.synchronize()
+    ref = torch.load(args.compare)
+    out['vs_dump'] = dict(x0_equal=bool(torch.equal(ref['x0'], x0.cpu())), codes_equal=bool(torch.equal(ref['codes'], codes.cpu())),
+                          dfm_max_abs_diff=float((ref['dfm'] - dfm.cpu()).abs().max()), dfm_max_abs=float(ref['dfm'].abs().max()))
   if args.check:
     from oracle import roi as oroi
     n = min(64, P)
