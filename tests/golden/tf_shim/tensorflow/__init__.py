@@ -367,7 +367,11 @@ def _crop_and_resize(image, boxes, box_ind, crop_size, method='bilinear', extrap
   return Tensor(np.asarray(out, np.float32))
 
 
-image = _module('image', crop_and_resize=_crop_and_resize)
+class _ResizeMethod(object):
+  BILINEAR, NEAREST_NEIGHBOR, BICUBIC, AREA = 0, 1, 2, 3
+
+
+image = _module('image', crop_and_resize=_crop_and_resize, ResizeMethod=_ResizeMethod)
 
 # ---- no-op services ----
 summary = _module('summary', histogram=lambda *a, **k: None, scalar=lambda *a, **k: None, image=lambda *a, **k: None)
