@@ -123,7 +123,7 @@ def cpu_baseline(seed, n_images=1, n_props=48, steps=1, warm=True):
   w = (rng.standard_normal((N, 1024)) * 0.01).astype(np.float32)
   b = np.zeros(N, np.float32)
   keep = (rng.uniform(size=(n_images * n_props, 1024)) < 0.5).astype(np.float32)
-  best = None
+  times = []
   for it in range(steps + (1 if warm else 0)):       # with `warm`, the first pass is an untimed warm-up
     for q in tp.values():
       for t in q.values():
@@ -135,40 +135,246 @@ def cpu_baseline(seed, n_images=1, n_props=48, steps=1, warm=True):
     dt = time.perf_counter() - t0
     if warm and it == 0:
       continue
-    best = dt if best is None else min(best, dt)
-  return dict(value=n_images * n_props / best, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
-              sample='%d image(s) x %d proposals of the same config, one fwd+bwd step, best of %d (oracle/: NumPy + '
-                     'torch-CPU restatement of the TF 1.x path; TensorFlow itself is not installable)'
-                     % (n_images, n_props, steps), seconds_per_step=best)
+    times.append(dt)
+  med = float(np.median(times))
+  return dict(value=n_images * n_props / med, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
+              sample='%d image(s) x %d proposals of the same config, one fwd+bwd step, median of %d after one warm-up '
+                     '(oracle/: NumPy + torch-CPU restatement of the TF 1.x path; TensorFlow itself is not installable)'
+                     % (n_images, n_props, len(times)), seconds_per_step=med, all_seconds=times)
 
 
 def run_reference(args):
-  """--impl reference: the CPU restatement, timed on the host cores (rank 0 only)."""
+  """--impl reference: the CPU restatement of the TF path (oracle/), timed on all host cores, rank 0 only.
+
+  Every step is the FULL configs[1] batch (2 images x 2000 proposals, 80 classes, 3 OICR stages: the same config the
+  GPU arm runs), ~30 s of host work; to keep the run within a few minutes the number of steps is bounded by a
+  150 s budget (one warm-up, at least two timed steps) and the line reports how many were timed."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   import torch
   torch.set_num_threads(os.cpu_count() or 1)
-  n_props = 480          # a bounded sample of the 2 x 2000-proposal workload: ~4 s of host work per step
-  times = []
-  base = None
-  for i in range(args.warmup + args.steps):
-    base = cpu_baseline(1000 + i, n_images=1, n_props=n_props, steps=1, warm=False)
-    if i >= args.warmup:
+  B, P = CONFIG['images_per_gpu'], CONFIG['proposals']
+  times, base = [], None
+  budget_s, t_start = 150.0, time.perf_counter()
+  n_warm = min(args.warmup, 1)
+  for i in range(n_warm + args.steps):
+    base = cpu_baseline(1000 + i, n_images=B, n_props=P, steps=1, warm=False)
+    if i >= n_warm:
       times.append(base['seconds_per_step'])
-    if sum(times) > 150:
+    if len(times) >= 2 and time.perf_counter() - t_start > budget_s:
       break
   ms = 1e3 * float(np.mean(times))
-  value = n_props / (ms / 1e3)
+  value = B * P / (ms / 1e3)
   out = dict(metric='proposals/sec (ROI+head+MIL+OICR fwd+bwd)', value=value, unit='proposals/s', impl='reference',
-             n_gpus=args.gpus, steps=len(times), warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+             n_gpus=args.gpus, steps=len(times), warmup=n_warm, ms_per_step=ms, higher_is_better=True,
              scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-             config=dict(CONFIG, sample='1 image x %d proposals per step' % n_props),
-             images_per_sec=value / CONFIG['proposals'],
+             config=dict(CONFIG, global_batch_images=B, parallelism='host cores (rank 0 only)',
+                         step='full batch per step: %d images x %d proposals' % (B, P)),
+             images_per_sec=value / P,
              cpu_baseline=dict(value=value, unit='proposals/s', cores=torch.get_num_threads(), kind='port',
-                               sample=base['sample']),
+                               sample='the full configs[1] batch (%d x %d proposals) per step, %d timed steps: '
+                                      'oracle/ = NumPy + torch-CPU restatement of the TF 1.x path '
+                                      '(TensorFlow itself is not installable here)' % (B, P, len(times))),
              e2e=dict(value=value, unit='proposals/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   emit(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations (reported beside the headline line, same JSON object)
+# ---------------------------------------------------------------------------------------------
+EVAL_MIN_DIMENSION = (1200, 800, 600, 400)       # configs/voc07_groundtruth.pbtxt:87-90
+
+
+def eval_sweep(dev, world, rank, head_dtype, workdir, peaks, n_images=16, warm=3):
+  """BASELINE configs[4]: VOC07 test predict sweep -- batch 1, 2000 proposals, 20 classes, 4 scales
+  (models/cap2det_model.py:231-272: the head runs once per eval_min_dimension on the rescaled image's feature map,
+  scores are averaged, then ONE per-class NMS pass per stage, 1 + K = 4 passes), images sharded over the ranks
+  with no communication (train/predict.py:328-415 consumes the detections on the host)."""
+  import torch
+  import torch.distributed as dist
+  from cap2det_b200 import builder, config, ops, synthetic
+  from cap2det_b200 import dist as c2d_dist
+  from cap2det_b200.standard_fields import InputDataFields as F
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor', eval_min_dimension=EVAL_MIN_DIMENSION,
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(workdir, classes, 'voc.txt'))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  dt = torch.bfloat16 if head_dtype == 'bf16' else torch.float32
+  model = builder.build(m, is_training=False, head_dtype=dt)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)          # spread the scores so that NMS has real work (random init leaves them ~equal)
+  P = CONFIG['proposals']
+  total = world * (n_images + warm)
+  mine = c2d_dist.shard_indices(total, rank, world, mode='contiguous')     # contiguous index shards (SURVEY 8(d))
+  sizes = []
+  for d in EVAL_MIN_DIMENSION:          # a 600 x 1000 image resized to min dimension d (core/imgproc.py:300)
+    sizes.append(synthetic.feature_map_shape(d, int(round(d * 1000.0 / 600.0))))
+  pool = []
+  for j in range(4):                    # a small pool of distinct images, pinned on the host
+    rng = np.random.default_rng(4000 + 17 * rank + j)
+    fm = [torch.from_numpy(np.maximum(rng.standard_normal((1, h, w, 576), dtype=np.float32), 0)).pin_memory() for h, w in sizes]
+    pool.append(dict(fmaps=fm, proposals=torch.from_numpy(synthetic.make_proposals(rng, 1, P)).pin_memory(),
+                     num_proposals=torch.full((1,), P, dtype=torch.int32).pin_memory()))
+  out_host = [dict(n=torch.zeros((1,), dtype=torch.int32).pin_memory(), boxes=torch.zeros((1, 300, 4)).pin_memory(),
+                   scores=torch.zeros((1, 300)).pin_memory(), classes=torch.zeros((1, 300)).pin_memory()) for _ in range(4)]
+
+  def one_image(i, from_host):
+    p = pool[i % len(pool)]
+    nb = dict(non_blocking=True)
+    ex = {F.features_to_crop: [f.to(dev, **nb) for f in p['fmaps']] if from_host else resident[i % len(pool)][0],
+          F.proposals: p['proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][1],
+          F.num_proposals: p['num_proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][2]}
+    pred = model.build_prediction(ex)
+    if from_host:                       # what train/predict.py:367-376 reads back, every stage
+      for st in range(4):
+        out_host[st]['n'].copy_(pred['num_detections_at_%d' % st], **nb)
+        out_host[st]['boxes'].copy_(pred['detection_boxes_at_%d' % st], **nb)
+        out_host[st]['scores'].copy_(pred['detection_scores_at_%d' % st], **nb)
+        out_host[st]['classes'].copy_(pred['detection_classes_at_%d' % st], **nb)
+    return pred
+
+  resident = [([f.to(dev) for f in p['fmaps']], p['proposals'].to(dev), p['num_proposals'].to(dev)) for p in pool]
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+  res = {}
+  for mode, from_host in (('resident', False), ('e2e', True)):
+    for i in range(warm):
+      one_image(i, from_host)
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_images)]
+    t0 = time.perf_counter()
+    for i in range(n_images):
+      if not from_host:
+        flush.fill_(i & 255)
+      ev[i][0].record()
+      one_image(warm + i, from_host)
+      ev[i][1].record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    res[mode] = (float(t[0].item()), float(t[1].item()))
+  # K7 alone: one stage, 2000 proposals x 20 classes
+  sc = torch.rand((1, P, len(classes)), device=dev) ** 4
+  props = resident[0][1]
+  for _ in range(3):
+    ops.multiclass_nms(props, sc, 1e-5, 0.3, 100, 300)
+  torch.cuda.synchronize()
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(10):
+    ops.multiclass_nms(props, sc, 1e-5, 0.3, 100, 300)
+  b.record()
+  torch.cuda.synchronize()
+  nms_ms = a.elapsed_time(b) / 10
+  nms_bytes = P * 16 + P * len(classes) * 4 + 300 * 24 + 4
+  h2d = sum(f.numel() * 4 for f in pool[0]['fmaps']) + P * 16 + 4
+  d2h = 4 * (4 + 300 * 16 + 300 * 4 + 300 * 4)
+  return dict(workload='VOC07 test predict sweep (BASELINE configs[4]): batch 1, 2000 proposals, 20 classes, '
+                       'eval_min_dimension %s, 4 NMS passes / image' % (list(EVAL_MIN_DIMENSION),),
+              images_timed_per_gpu=n_images, sharding='contiguous image-index shards, no communication',
+              images_in_shard_of_4952=len(c2d_dist.shard_indices(4952, rank, world, mode='contiguous')),
+              images_per_sec=world * n_images / (res['resident'][0] / 1e3), ms_per_image=res['resident'][0] / n_images,
+              e2e=dict(images_per_sec=world * n_images / (res['e2e'][1] / 1e3), ms_per_image_wall=res['e2e'][1] / n_images,
+                       ms_per_image_device=res['e2e'][0] / n_images, h2d_bytes_per_image=int(h2d), d2h_bytes_per_image=int(d2h),
+                       clock='time.perf_counter around the synchronised loop (host-pinned inputs in, detections out)'),
+              feature_maps=[list(x) for x in sizes],
+              k7_nms=dict(ms_per_pass=nms_ms, algorithmic_bytes=nms_bytes, gbs=nms_bytes / nms_ms / 1e6,
+                          frac_of_hbm=nms_bytes / nms_ms / 1e6 / peaks['hbm_gbs'],
+                          note='latency-bound: 0.2 MB per pass; 64-bit-key bitonic sort + bitmask NMS in shared memory'))
+
+
+def voc07_step(dev, head_dtype, workdir, steps, warm=3):
+  """BASELINE configs[0]: voc07_groundtruth training step, 1 image x 2000 proposals, 20 classes (one GPU)."""
+  import torch
+  from cap2det_b200 import builder, config, synthetic, trainer
+  from cap2det_b200.standard_fields import InputDataFields as F
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(workdir, classes, 'voc.txt'))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=True, head_dtype=torch.bfloat16 if head_dtype == 'bf16' else torch.float32)
+  step = trainer.TrainStep(model, learning_rate=0.01)
+  P = CONFIG['proposals']
+  exs = []
+  for j in range(3):
+    rng = np.random.default_rng(500 + j)
+    exs.append({F.features_to_crop: torch.from_numpy(synthetic.make_feature_map(rng, 1)).to(dev).requires_grad_(True),
+                F.proposals: torch.from_numpy(synthetic.make_proposals(rng, 1, P)).to(dev),
+                F.num_proposals: torch.full((1,), P, dtype=torch.int32, device=dev),
+                F.object_texts: synthetic.make_object_texts(rng, 1, classes)})
+  launch = 'eager'
+  run = step
+  try:
+    run = trainer.GraphedTrainStep(step, exs[0])
+    launch = 'CUDA graph replay'
+  except Exception:       # noqa: BLE001
+    torch.cuda.synchronize()
+  flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+  def one(i):
+    ex = exs[i % 3]
+    if run is step:
+      ex[F.features_to_crop].grad = None
+    return run(ex)
+
+  for i in range(warm):
+    one(i)
+  torch.cuda.synchronize()
+  ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+  for i in range(steps):
+    flush.fill_(i & 255)
+    ev[i][0].record(); one(warm + i); ev[i][1].record()
+  torch.cuda.synchronize()
+  ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+  model.raise_if_assert_failed()
+  return dict(workload='voc07_groundtruth train step (BASELINE configs[0]): 1 image x 2000 proposals, 20 classes',
+              ms_per_step=ms, proposals_per_sec=P / (ms / 1e3), images_per_sec=1.0 / (ms / 1e3), step_launch=launch)
+
+
+def wordvec_extract(dev, workdir, reps=50):
+  """BASELINE configs[3]: the GloVe word-vector label extractor on a configs[1]-shaped caption batch (2 images x 5
+  captions), 80 classes against a 7379 x 300 table: host tokenisation + one kernel (K8)."""
+  import torch
+  from cap2det_b200 import config, label_extractor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  rng = np.random.default_rng(300)
+  classes = synthetic.COCO_CLASSES
+  label_file = synthetic.write_label_file(workdir, classes, 'coco.txt')
+  vpath, epath, vocab, _ = synthetic.write_open_vocab(workdir, classes, rng)
+  plant = [synthetic._MULTIWORD.get(c, c) for c in classes]
+  caps = [synthetic.make_captions(rng, 2, vocab, plant, no_plant_images=(1,)) for _ in range(4)]
+  cfg = config.parse_text("word_vector_match_extractor { label_file: '%s' open_vocabulary_file: '%s' "
+                          "open_vocabulary_word_embedding_file: '%s' }" % (label_file, vpath, epath), config.LabelExtractor)
+  ext = label_extractor.build_label_extractor(cfg, dev)
+  for c in caps:
+    ext.extract_labels({F.concat_caption_string: c})
+  torch.cuda.synchronize()
+  ids = ext._tok(caps[0], dev)
+  a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  a.record()
+  for _ in range(reps):
+    from cap2det_b200 import ops
+    ops.wordvec_match(ids, ext._embedding_weights, ext._class_ids, ext._exact_lut)
+  b.record()
+  torch.cuda.synchronize()
+  kernel_us = a.elapsed_time(b) / reps * 1e3
+  t0 = time.perf_counter()
+  for i in range(reps):
+    ext.extract_labels({F.concat_caption_string: caps[i % 4]})
+  torch.cuda.synchronize()
+  call_us = (time.perf_counter() - t0) / reps * 1e6
+  T = len(caps[0][0])
+  flops = 2.0 * 2 * T * 300 * len(classes)
+  return dict(workload='coco17_word_vector_match label extraction (BASELINE configs[3]): 2 images x %d tokens, 80 classes, '
+                       '7379 x 300 embedding' % T, kernel_us=kernel_us, call_us_incl_host_tokenisation=call_us,
+              flops=flops, note='%.1f MFLOP per batch: launch-latency bound, a tensor-core GEMM cannot help' % (flops / 1e6))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -192,6 +398,7 @@ def main():
   ap.add_argument('--no-first-stage', action='store_true', help='skip the extra from-images measurement')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-kernel-table', action='store_true')
+  ap.add_argument('--no-extra-configs', action='store_true', help='skip the eval sweep / VOC07 step / word-vector timings')
   ap.add_argument('--no-cuda-graph', action='store_true', help='run every step eagerly (default: replay the step as a '
                   'CUDA graph on one GPU, eager under torchrun)')
   args = ap.parse_args()
@@ -385,7 +592,11 @@ def main():
   for i in range(e2e_warm):              # reach the allocator's steady state before the timed region
     run_e2e(i)
   host_busy[0] = 0.0
-  e2e_ms, _, _ = timed(lambda i: run_e2e(e2e_warm + i), 0, args.steps)
+  e2e_ms, _, e2e_wall = timed(lambda i: run_e2e(e2e_warm + i), 0, args.steps)
+  if world > 1:
+    tw = torch.tensor([e2e_wall], dtype=torch.float64, device=dev)
+    dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    e2e_wall = float(tw.item())
   e2e_host_busy = host_busy[0]
   for k in range(LOSS_DEPTH):            # oldest first
     slot = (e2e_warm + args.steps + k) % LOSS_DEPTH
@@ -397,7 +608,9 @@ def main():
 
   props_per_step = world * B * P
   value = props_per_step / (total_ms / args.steps / 1e3)
-  e2e_value = props_per_step / (e2e_ms / args.steps / 1e3)
+  # e2e is WALL time (time.perf_counter around the synchronised region, L2 flushes included, max over ranks): the
+  # CUDA-event sum below it misses the gaps between steps and is reported only as a diagnostic.
+  e2e_value = props_per_step / (e2e_wall / args.steps)
   h2d = sum(pinned[0][k].numel() * pinned[0][k].element_size() for k in ('fmap', 'proposals', 'num_proposals'))
   T = len(pinned[0]['captions'][0])
   h2d += B * T * 4                     # tokenised caption ids (int32)
@@ -409,8 +622,17 @@ def main():
                          l2_handling='256 MB L2 flush between timed iterations', head_dtype=head_dtype),
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,
-                      ms_per_step=e2e_ms / args.steps, loss_readbacks_in_flight=LOSS_DEPTH,
+                      ms_per_step=e2e_wall / args.steps * 1e3, clock='time.perf_counter, barrier + synchronize on both sides',
+                      ms_per_step_cuda_events=e2e_ms / args.steps, loss_readbacks_in_flight=LOSS_DEPTH,
                       host_busy_ms_per_step=e2e_host_busy / args.steps * 1e3))
+  if world > 1:
+    # replicas must stay identical: max |checksum - mean checksum| over ranks of every trainable buffer
+    sums = torch.stack([v.detach().double().sum() for v in model.get_variables_to_train()])
+    lo, hi = sums.clone(), sums.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    out['replicas_identical'] = bool(torch.equal(lo, hi))
+    out['replica_checksum_spread'] = float((hi - lo).abs().max().item())
   if not args.no_first_stage and head_dtype == 'bf16':
     # the same step fed with IMAGES (600x1000x3 uint8, resident) instead of feature maps:
     # Inception-v2 first stage forward + Mixed_4e backward in front of / behind the proposal path.
@@ -443,6 +665,20 @@ def main():
     # every rank runs the profiled steps (they contain the gradient all-reduce); rank 0 reports
     from cap2det_b200 import profiling
     dominant = profiling.dominant_kernel_roofline(lambda i: run_eager(i), peaks, ROOT)   # per-launch events need eager launches
+  if dominant is not None and clocks is not None and clocks.get('sm_mhz') and clocks.get('sm_max_mhz'):
+    # which measured peak applies: the burst figure while the SM clock sits at its maximum and no power cap was
+    # seen during the timed region, else the sustained one (B200_PROFILING.md)
+    burst = clocks['sm_mhz'] >= 0.97 * clocks['sm_max_mhz'] and 'sw_power_cap' not in clocks.get('reasons', [])
+    peak = peaks['bf16_tflops'] if burst else peaks['bf16_tflops_sustained']
+    dominant.update(peak=peak, frac=dominant['achieved'] / peak,
+                    peak_source='%s %s (MEASURED_PEAKS.json); SM clock %.0f / %.0f MHz, reasons %s'
+                                % (peaks['source'], 'bf16_tflops (burst)' if burst else 'bf16_tflops_sustained',
+                                   clocks['sm_mhz'], clocks['sm_max_mhz'], clocks.get('reasons')))
+    for k, v in dominant['per_kernel'].items():
+      v['tflops'] = v['flops_per_step'] / (v['ms_per_step'] * 1e-3) / 1e12
+      v['frac_of_peak'] = v['tflops'] / peak
+  if not args.no_extra_configs:
+    out['eval_sweep'] = eval_sweep(dev, world, rank, head_dtype, workdir, peaks)        # every rank: its shard
   if rank == 0:
     if not args.no_kernel_table:
       from cap2det_b200 import profiling
@@ -452,8 +688,11 @@ def main():
       out['hbm_group'] = table['hbm_group']
       if dominant is not None:
         out['roofline'] = dominant
+    if not args.no_extra_configs:
+      out['voc07_step'] = voc07_step(dev, head_dtype, workdir, args.steps)
+      out['wordvec_extract'] = wordvec_extract(dev, workdir)
     if not args.no_cpu_baseline and world == 1:
-      out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=960, steps=1)   # ~10-30 s of host work
+      out['cpu_baseline'] = cpu_baseline(1000, n_images=1, n_props=960, steps=3)   # ~30 s of host work
     emit(out)
   if world > 1:
     dist.barrier()

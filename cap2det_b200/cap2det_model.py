@@ -177,6 +177,14 @@ class Model(ModelBase):
     # models/utils.py:147-160
     x0 = ops.roi_crop_maxpool(features_to_crop, proposals, frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
                               frcnn.maxpool_stride, out_dtype=self._head_dtype)
+    self._roi_split = None
+    if getattr(self, 'split_backward_at_roi', False) and x0.requires_grad:
+      # Data-parallel steps cut the autograd graph here: the backward of everything above (all trainable head / FC
+      # gradients) finishes first, their all-reduce starts, and the ROI (and first-stage) backward then runs beside
+      # it (trainer.TrainStep.backward_below_roi).
+      leaf = x0.detach().requires_grad_(True)
+      self._roi_split = (x0, leaf)
+      x0 = leaf
     # models/utils.py:165-177
     keep_mask = None
     keep_prob = frcnn.dropout_keep_prob

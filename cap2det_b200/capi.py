@@ -146,11 +146,24 @@ def call(name, *args):
 
 
 def require_cuda(*tensors):
+  """All tensors of one call must be contiguous, on ONE CUDA device, and that device must be the current one: the
+  library launches on the current device / current stream and takes raw pointers, so a tensor of another GPU would
+  be dereferenced on the wrong device.  (Use `with torch.cuda.device(t.device):` or torch.cuda.set_device.)"""
+  device = None
   for t in tensors:
-    if t is not None and not t.is_cuda:
+    if t is None:
+      continue
+    if not t.is_cuda:
       raise RuntimeError('cap2det_b200: tensors must live on a CUDA device (no CPU fallback)')
-    if t is not None and not t.is_contiguous():
+    if not t.is_contiguous():
       raise ValueError('cap2det_b200: tensors must be contiguous')
+    if device is None:
+      device = t.device
+    elif t.device != device:
+      raise ValueError('cap2det_b200: tensors of one call live on different devices (%s and %s)' % (device, t.device))
+  if device is not None and device.index != torch.cuda.current_device():
+    raise RuntimeError('cap2det_b200: tensors live on %s but the current CUDA device is cuda:%d; wrap the call in '
+                       'torch.cuda.device(%r)' % (device, torch.cuda.current_device(), str(device)))
 
 
 def dtype_code(dtype):

@@ -449,8 +449,8 @@ struct BbWalk {
 };
 
 static int bb_upload_fold_table() {
-  static bool done = false;
-  if (done) return C2D_OK;
+  static unsigned long long done = 0;
+  if (!first_call_on_this_device(&done)) return C2D_OK;
   const BbLayout& L = bb_layout();
   FoldRow rows[kNumBbConvs];
   for (int i = 0; i < kNumBbConvs; ++i) {
@@ -460,7 +460,6 @@ static int bb_upload_fold_table() {
     rows[i].cout = c.cout; rows[i].taps = c.k * c.k; rows[i].cin = c.cin;
   }
   C2D_CUDA_OK(cudaMemcpyToSymbol(g_bb_fold, rows, sizeof(rows)));
-  done = true;
   return C2D_OK;
 }
 

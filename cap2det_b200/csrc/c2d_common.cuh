@@ -38,6 +38,18 @@ void count_launch(int n = 1);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Per-DEVICE one-shot state (function attributes, __device__ tables): true the first time it is called with `mask`
+// on the current device.  A process may drive several GPUs; a per-process flag would leave every device but the
+// first without its dynamic shared-memory attribute / constant table.
+static inline bool first_call_on_this_device(unsigned long long* mask) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

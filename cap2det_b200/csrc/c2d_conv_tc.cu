@@ -110,14 +110,13 @@ struct ProfScope {
   ~ProfScope() { if (idx >= 0) cudaEventRecord(g_prof[idx].b, st); }
 };
 
-static bool g_attr_done = false;
+static unsigned long long g_attr_done = 0;
 static int tc_prepare() {
-  if (!g_attr_done) {
+  if (first_call_on_this_device(&g_attr_done)) {
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
-    g_attr_done = true;
   }
   return C2D_OK;
 }

@@ -351,11 +351,10 @@ int c2d_multiclass_nms(const float* boxes, const float* scores, int lds, int B, 
   int* cls_count = (int*)workspace;
   int* cls_index = cls_count + (size_t)B * C;
   float* cls_score = (float*)(cls_index + (size_t)B * C * max_size_per_class);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  if (first_call_on_this_device(&attr_done)) {
     C2D_CUDA_OK(cudaFuncSetAttribute(nms_per_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     C2D_CUDA_OK(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-    attr_done = true;
   }
   nms_per_class_kernel<<<dim3(C, B), kNmsThreads, (size_t)n_pad * 8, st>>>(
       (const float4*)boxes, scores, lds, P, C, n_pad, score_thresh, iou_thresh, max_size_per_class, cls_count,

@@ -253,14 +253,28 @@ class TextClassifierMatchExtractor(LabelExtractor):
         exact[index[name]] = cid
     self._exact_lut = torch.from_numpy(exact).to(dev)
     self._tok = _Tokenizer(vocab)
+    # The reference hashes the raw class names independently of the open vocabulary (_match_labels, :466-469): a
+    # class name that the vocabulary lacks still matches exactly.  The fused kernel only sees vocabulary ids, so
+    # such (rare) class lists get a second, class-name keyed lookup.
+    self._class_tok = None
+    if any(name not in index for name in self._classes):
+      self._class_tok = _Tokenizer(self._classes)
+      self._class_lut = torch.arange(self._num_classes, dtype=torch.int32, device=dev)
     self._built = True
 
   def extract_labels(self, examples, return_probas=False):
     if not self._built:
       self._build()
-    ids = self._tok(examples[InputDataFields.concat_caption_string], self._device)
-    return ops.text_classifier_match(ids, self._embedding_weights, self._w1, self._b1, self._w2, self._b2,
-                                     self._options.label_threshold, self._exact_lut, return_probas=return_probas)
+    texts = examples[InputDataFields.concat_caption_string]
+    ids = self._tok(texts, self._device)
+    out = ops.text_classifier_match(ids, self._embedding_weights, self._w1, self._b1, self._w2, self._b2,
+                                    self._options.label_threshold, self._exact_lut, return_probas=return_probas)
+    if self._class_tok is not None:
+      labels = out[0] if return_probas else out
+      exact = _match_labels(self._class_tok(texts, self._device), self._class_lut, self._num_classes)
+      labels = torch.where((exact > 0).any(dim=-1, keepdim=True), exact, labels)
+      out = (labels,) + tuple(out[1:]) if return_probas else labels
+    return out
 
 
 def build_label_extractor(options, device=None):

@@ -68,12 +68,12 @@ def kernel_table(model, example, peaks, head_dtype):
   # the training-mode pair: forward writes the max-pool arg-max codes, backward scatters from them
   ms = _time(lambda: call('c2d_roi_crop_maxpool_fwd_codes', ptr(fmap), B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(x0),
                           capi.dtype_code(dt), ptr(codes), stream()), flush)
-  add('K1 roi_crop_maxpool_fwd', ms, 'hbm', B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s) + n_code, None)
+  add('K1 roi_crop_maxpool_fwd', ms, 'hbm', B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s), None)   # arg-max codes: a by-product, not counted
   g0 = torch.randn(x0.shape, device=dev).to(dt)
   dfm = torch.empty_like(fmap)
   ms = _time(lambda: call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
                           capi.dtype_code(dt), ptr(dfm), stream()), flush)
-  add("K1' roi_crop_maxpool_bwd", ms, 'hbm', B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4) + n_code, None)
+  add("K1' roi_crop_maxpool_bwd", ms, 'hbm', B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4), None)
 
   n = B * P
   lib = capi.load()

@@ -68,6 +68,7 @@ class Adagrad(object):
     self.l2 = list(l2_scales) if l2_scales is not None else [0.0] * len(self.variables)
     self.mult = list(grad_multipliers) if grad_multipliers is not None else [1.0] * len(self.variables)
     self.segments = segments
+    self.static_grads = None
     self.clip_norm = None       # tf.contrib.training.clip_gradient_norms: per-variable clip_by_norm
 
   def _update(self, w, a, g, n, scale, l2):
@@ -109,6 +110,9 @@ class Adagrad(object):
         self._update(w, af[start:start + numel], g, numel, grad_scale * m * clip, l2 * m * clip)
 
   def zero_grad(self):
+    if self.static_grads is not None:     # gradients are views of one flat bucket (GraphedTrainStep, data parallel)
+      self.static_grads.zero_()
+      return
     for v in self.variables:
       v.grad = None
 
@@ -169,6 +173,7 @@ class TrainStep(object):
     self.world_size = world_size
     self.global_step = 0
     self._pending = []
+    self.overlap_hooks = True
     if world_size > 1 and hasattr(torch.Tensor, 'register_post_accumulate_grad_hook'):
       # Start the all-reduce of a gradient buffer the moment autograd has finished it: the head's 24 MB buffer
       # is complete before the ROI backward (and the first-stage backward) run, so NCCL overlaps with them.
@@ -200,6 +205,8 @@ class TrainStep(object):
 
   def _reduce_when_ready(self, param):
     import torch.distributed as dist
+    if not self.overlap_hooks:
+      return
     if param.grad is not None and dist.is_available() and dist.is_initialized():
       self._pending.append((param, dist.all_reduce(param.grad, op=dist.ReduceOp.SUM, async_op=True)))
 
@@ -224,8 +231,10 @@ class TrainStep(object):
       total = out if total is None else total + out
     return total
 
-  def __call__(self, examples):
-    """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""
+  # ---- the three phases of a step (GraphedTrainStep captures them as separate CUDA graphs when world_size > 1) ----
+  def forward_backward(self, examples):
+    """Forward, losses and the backward of everything that has trainable variables.  With
+    model.split_backward_at_roi the gradient stops at the ROI output (see backward_below_roi)."""
     model = self.model
     self.opt.zero_grad()
     self.opt.lr = self.learning_rate()
@@ -236,17 +245,37 @@ class TrainStep(object):
       total = v if total is None else total + v
     self._pending = []
     total.backward()
+    self.last_loss_dict = loss_dict
+    return total.detach()
+
+  def backward_below_roi(self):
+    """The rest of the backward pass: ROI crop / max-pool (and the first stage) from the gradient of the ROI output."""
+    split = getattr(self.model, '_roi_split', None)
+    if split is not None and split[1].grad is not None:
+      split[0].backward(split[1].grad)
+      self.model._roi_split = None
+
+  def reduce_gradients(self):
     if self.world_size > 1:
       # gradient buffers whose hook fired are already being reduced (see _reduce_when_ready); reduce the rest
       started = {id(v) for v, _ in self._pending}
-      c2d_dist.allreduce_sum([v.grad for v in model.get_variables_to_train() if v.grad is not None and id(v) not in started])
+      c2d_dist.allreduce_sum([v.grad for v in self.model.get_variables_to_train() if v.grad is not None and id(v) not in started])
       for _, work in self._pending:
         work.wait()
+      self._pending = []
+
+  def update(self, total):
     self.opt.step(grad_scale=1.0 / self.world_size)
     self.global_step += 1
-    self.last_loss_dict = loss_dict
     reg = self.regularization_loss()
-    return total.detach() + reg if reg is not None else total.detach()
+    return total + reg if reg is not None else total
+
+  def __call__(self, examples):
+    """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""
+    total = self.forward_backward(examples)
+    self.backward_below_roi()
+    self.reduce_gradients()
+    return self.update(total)
 
 
 class GraphedTrainStep(object):
@@ -260,11 +289,20 @@ class GraphedTrainStep(object):
   def __init__(self, train_step, examples):
     if train_step.world_size != 1:
       raise ValueError('GraphedTrainStep supports world_size 1')
+    tc = train_step.train_config
+    if tc is not None and tc.HasField('learning_rate_decay') and float(tc.learning_rate_decay.decay_rate) != 1.0:
+      raise ValueError('GraphedTrainStep bakes the learning rate into the captured graph; a decaying learning rate '
+                       '(learning_rate_decay.decay_rate != 1) needs eager TrainStep calls')
     self.step = train_step
     model = train_step.model
     self._extract = model._label_extractor.extract_labels
     self.static = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in examples.items() if torch.is_tensor(v)}
     self.static_labels = self._extract(examples).clone()
+    # The warm-up runs are REAL optimizer steps on the first batch (the allocator and the lazily built kernel state
+    # need them); constructing this object must not train, so weights, Adagrad accumulators and the step counter are
+    # put back afterwards.  (Capture itself records the kernels without running them.)
+    variables = model.get_variables_to_train()
+    saved = ([v.detach().clone() for v in variables], [a.clone() for a in train_step.opt.accum], train_step.global_step)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -278,6 +316,14 @@ class GraphedTrainStep(object):
       self.static_total = self._run_static()
     self.launches_per_step = capi.launch_count() - before
     self._status = model._assert_status
+    with torch.no_grad():
+      for v, w in zip(variables, saved[0]):
+        v.copy_(w)
+      for a, b in zip(train_step.opt.accum, saved[1]):
+        a.copy_(b)
+    train_step.global_step = saved[2]
+    model._assert_status = None
+    torch.cuda.synchronize()
 
   def _run_static(self):
     for v in self.static.values():
@@ -296,6 +342,7 @@ class GraphedTrainStep(object):
     for k, v in self.static.items():
       v.detach().copy_(examples[k], non_blocking=True)
     self.graph.replay()
+    self.step.global_step += 1                  # replays skip the host code of TrainStep.__call__
     self.step.model._assert_status = self._status
     return self.static_total
 

@@ -87,6 +87,8 @@ def _conv_bn_relu(x, p, name, k, stride, collect=None, emulate_bf16=False):
   if emulate_bf16:
     wf = _RoundBF16.apply(w * scale.view(-1, 1, 1, 1))       # BN scale folded into bf16 weights
     u = TF_.conv2d(x, wf, None, stride=stride, padding=pad) + shift.view(1, -1, 1, 1)
+    if collect is not None:
+      collect[name] = u.detach()
     return _store_bf16(torch.relu(u))
   u = z * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
   if collect is not None:

@@ -272,19 +272,26 @@ def main():
   with tf.variable_scope('wv'):
     G['labels_wordvec'] = wv.extract_labels(ex).v
   G['labels_wordvec_embedding_with_oov'] = tf._VARIABLES['wv/weights']
+  # TextClassifierMatch: one class ('zebra') is NOT in the open vocabulary -- its exact match must still fire, because
+  # _match_labels hashes the raw class names independently of the vocabulary (models/label_extractor.py:466-469)
   H = 12
+  tc_classes = classes + ['zebra']
+  tc_label_file = synthetic.write_label_file(d, tc_classes, name='tc_label.txt')
+  tc_texts = [list(r) for r in texts] + [['a', 'zebra', 'on', 'the', 'qqq', '', '', '']]
+  tc_ex = {InputDataFields.concat_caption_string: text_tensor(tf, tc_texts)}
+  G['labels_tc_classes'], G['labels_tc_texts'] = np.array(tc_classes), np.array(tc_texts)
   tf._VARIABLES['tc/text_classifier/layer1/weights'] = (rng.standard_normal((16, H)) * 0.5).astype(np.float32)
   tf._VARIABLES['tc/text_classifier/layer1/biases'] = (rng.standard_normal((H,)) * 0.1).astype(np.float32)
-  tf._VARIABLES['tc/text_classifier/layer2/weights'] = (rng.standard_normal((H, C)) * 0.8).astype(np.float32)
-  tf._VARIABLES['tc/text_classifier/layer2/biases'] = (rng.standard_normal((C,)) * 0.1).astype(np.float32)
+  tf._VARIABLES['tc/text_classifier/layer2/weights'] = (rng.standard_normal((H, C + 1)) * 0.8).astype(np.float32)
+  tf._VARIABLES['tc/text_classifier/layer2/biases'] = (rng.standard_normal((C + 1,)) * 0.1).astype(np.float32)
   np.random.seed(6)
   tc = extractor('text_classifier_match_extractor',
                  "label_file: '%s' open_vocabulary_file: '%s' open_vocabulary_word_embedding_file: '%s' "
                  "text_classifier_checkpoint_file: 'unused' hidden_units: %d label_threshold: 0.5"
-                 % (label_file, vocab_file, emb_file, H))
+                 % (tc_label_file, vocab_file, emb_file, H))
   with tf.variable_scope('tc'):
-    G['labels_textclassifier'] = tc.extract_labels(ex).v
-    G['labels_textclassifier_logits'] = tc.predict(ex).v
+    G['labels_textclassifier'] = tc.extract_labels(tc_ex).v
+    G['labels_textclassifier_logits'] = tc.predict(tc_ex).v
   G['labels_textclassifier_embedding_with_oov'] = tf._VARIABLES['tc/weights']
   for k in ('layer1/weights', 'layer1/biases', 'layer2/weights', 'layer2/biases'):
     G['labels_tc_' + k.replace('/', '_')] = tf._VARIABLES['tc/text_classifier/' + k]

@@ -83,73 +83,76 @@ def test_conv_bf16_fwd_dgrad_wgrad(n, hin, cin, cout, k, stride):
   assert l2_err(dw.cpu().numpy(), wo.grad.permute(0, 2, 3, 1).numpy()) < 1e-5
 
 
-def test_head_mixed5_bf16_forward_backward():
-  from cap2det_b200 import ops
+def _head_gradients_cpu(p, x0, keep, dfeat, emulate_bf16):
+  """Oracle forward + backward of the head; returns (feat, {name: grad}, pre-activations)."""
   from oracle import head as ohead
+  tp = {k: {kk: torch.from_numpy(v).requires_grad_(kk in ('weights', 'gamma', 'beta')) for kk, v in q.items()}
+        for k, q in p.items()}
+  xt = torch.from_numpy(x0).requires_grad_(True)
+  col = {}
+  feat = ohead.avgpool_dropout(ohead.head_mixed5(xt, tp, emulate_bf16=emulate_bf16, collect=col), 0.5, keep)
+  feat.backward(torch.from_numpy(dfeat))
+  g = {'x': xt.grad.numpy()}
+  for n, q in tp.items():
+    for k in ('weights', 'gamma', 'beta'):
+      g[n + '/' + k] = q[k].grad.numpy()
+  return feat.detach().numpy(), g, {k: v.numpy() for k, v in col.items()}
+
+
+def test_head_mixed5_bf16_forward_backward():
+  """bf16 tensor-core head against the CPU oracle.
+
+  Forward: 2e-2 (max-relative) against the PLAIN fp32 oracle -- the north-star bar.
+  Gradients: a 17-layer ReLU network stored in bf16 cannot be within 2e-2 of its fp32 gradient, whoever computes it:
+  rounding the activations to bf16 flips ~0.1 % of the ReLU decisions, and a flipped unit switches its whole gradient
+  path on or off.  This is measured HERE on the CPU oracle alone (fp32 arithmetic, bf16 storage vs fp32 storage:
+  `floor`, 4-9 % in L2 and in max-norm) and asserted, so the claim is checked and not just written down.  The kernels
+  are therefore compared with the oracle that stores what they store (same rounding points, `emulate_bf16=True`): most
+  gradient tensors are within 2e-2 (L2) of it (the median must be); two bf16 runs with different fp32 accumulation
+  orders still flip some decisions against each other, so a tensor above 2e-2 must at least be NO FURTHER from the
+  storage-precision oracle than that oracle is from fp32 (its own floor).  A wrong mask or a missing term shows up as
+  tens of percent; the arithmetic itself is held to 3e-3 / 1e-5 per layer in test_conv_bf16_fwd_dgrad_wgrad.
+  The flipped fraction and the worst tensor are printed."""
+  from cap2det_b200 import ops
   from tests.test_gpu_parity import _head_setup
-  p, flat, x0 = _head_setup(n=21, seed=31)
+  p, flat, x0 = _head_setup(n=42, seed=31)
   n = x0.shape[0]
   rng = np.random.default_rng(32)
   keep = (rng.uniform(size=(n, 1024)) < 0.5).astype(np.float32)
   dfeat = rng.standard_normal((n, 1024)).astype(np.float32)
   x0 = _bf(x0).float().numpy()
-  tp = {k: {kk: torch.from_numpy(v).requires_grad_(kk in ('weights', 'gamma', 'beta')) for kk, v in q.items()}
-        for k, q in p.items()}
-  xt = torch.from_numpy(x0).requires_grad_(True)
-  feat_o = ohead.avgpool_dropout(ohead.head_mixed5(xt, tp), 0.5, keep)       # plain fp32 oracle
-  feat_o.backward(torch.from_numpy(dfeat))
-  g32 = dict(x=xt.grad.clone(), **{n: {k: v.grad.clone() for k, v in q.items() if v.grad is not None}
-                                   for n, q in tp.items()})
-  for q in tp.values():
-    for v in q.values():
-      v.grad = None
-  xt.grad = None
-  # oracle with the storage precision of the tensor-core path (same ReLU masks): gradient reference
-  feat_e = ohead.avgpool_dropout(ohead.head_mixed5(xt, tp, emulate_bf16=True), 0.5, keep)
-  feat_e.backward(torch.from_numpy(dfeat))
+  feat32, g32, u32 = _head_gradients_cpu(p, x0, keep, dfeat, emulate_bf16=False)
+  feat16, g16, u16 = _head_gradients_cpu(p, x0, keep, dfeat, emulate_bf16=True)
   xd = torch.from_numpy(x0).cuda().to(torch.bfloat16).requires_grad_(True)
   pd = torch.from_numpy(flat).cuda().requires_grad_(True)
   feat = ops.head_mixed5(xd, pd, torch.from_numpy(keep).cuda(), 0.5)
-  assert rel_err(feat.detach().cpu().numpy(), feat_o.detach().numpy()) < RTOL_BF16
+  assert rel_err(feat.detach().cpu().numpy(), feat32) < RTOL_BF16          # forward: the north-star bar, vs plain fp32
+  assert rel_err(feat.detach().cpu().numpy(), feat16) < 5e-3
   feat.backward(torch.from_numpy(dfeat).cuda())
-
-  def l2(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+  got = {'x': xd.grad.float().cpu().numpy()}
+  dflat = pd.grad.cpu().numpy()
+  for name, k, cin, cout, _, off in ops.head_conv_specs():
+    got[name + '/weights'] = dflat[off['weights']:off['weights'] + cout * k * k * cin].reshape(cout, k, k, cin)
+    got[name + '/gamma'] = dflat[off['gamma']:off['gamma'] + cout]
+    got[name + '/beta'] = dflat[off['beta']:off['beta'] + cout]
 
   def cos(a, b):
     a = np.asarray(a, np.float64).ravel(); b = np.asarray(b, np.float64).ravel()
     return float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
 
-  report = {'feat_vs_emul': rel_err(feat.detach().cpu().numpy(), feat_e.detach().numpy()),
-            'dx_l2_emul': l2(xd.grad.float().cpu().numpy(), xt.grad.numpy()),
-            'dx_cos_f32': cos(xd.grad.float().cpu().numpy(), g32['x'].numpy())}
-  dflat_ = pd.grad.cpu().numpy()
-  for name, k, cin, cout, _, off in ops.head_conv_specs():
-    w_ = dflat_[off['weights']:off['weights'] + cout * k * k * cin].reshape(cout, k, k, cin)
-    report[name] = (round(l2(w_, tp[name]['weights'].grad.numpy()), 4), round(cos(w_, g32[name]['weights'].numpy()), 4),
-                    round(l2(dflat_[off['gamma']:off['gamma'] + cout], tp[name]['gamma'].grad.numpy()), 4),
-                    round(l2(dflat_[off['beta']:off['beta'] + cout], tp[name]['beta'].grad.numpy()), 4))
-  print(report)
-  assert rel_err(feat.detach().cpu().numpy(), feat_e.detach().numpy()) < 5e-3
-  # Gradients: rounding activations to bf16 flips ~0.3% of the ReLU masks w.r.t. an fp32 forward, which
-  # alone moves gradients by several percent in L2 -- so (a) against the oracle that stores what the
-  # kernels store (bf16 weights / activations / activation gradients, fp32 accumulation) the tolerance
-  # is the north-star 2e-2, and (b) against the plain fp32 oracle the direction must agree.
-  # Noise floor of this comparison, measured on the CPU oracle itself: perturbing the BN shifts by one fp32 ulp
-  # (1e-7 relative) moves the oracle's own dx by 1.1e-2 .. 1.3e-2 in L2, a 1e-6 perturbation (the size of a
-  # different fp32 accumulation order on the tensor cores) by 2.1e-2 .. 2.7e-2, because values that sit on a
-  # bf16 rounding boundary or a ReLU threshold flip.  3e-2 is therefore the tightest meaningful bar for a
-  # gradient that crosses all 17 layers; the per-layer building blocks above are held to 3e-3.
-  assert l2(xd.grad.float().cpu().numpy(), xt.grad.numpy()) < 3e-2
-  assert cos(xd.grad.float().cpu().numpy(), g32['x'].numpy()) > 0.98
-  dflat = pd.grad.cpu().numpy()
-  for name, k, cin, cout, _, off in ops.head_conv_specs():
-    w = dflat[off['weights']:off['weights'] + cout * k * k * cin].reshape(cout, k, k, cin)
-    assert l2(w, tp[name]['weights'].grad.numpy()) < 4e-2, (name, report)   # measured 0.6e-2 .. 2.6e-2 (grows ~0.8e-2 per chained conv)
-    assert cos(w, g32[name]['weights'].numpy()) > 0.98, name
-    assert l2(dflat[off['gamma']:off['gamma'] + cout], tp[name]['gamma'].grad.numpy()) < 4e-2, (name, report)
-    assert l2(dflat[off['beta']:off['beta'] + cout], tp[name]['beta'].grad.numpy()) < 4e-2, (name, report)
+  flipped = float(np.mean([((u32[k] > 0) != (u16[k] > 0)).mean() for k in u32 if k in u16]))
+  floor = {k: l2_err(g16[k], g32[k]) for k in g32}              # CPU only: what bf16 STORAGE does to this gradient
+  err = {k: l2_err(got[k], g16[k]) for k in g32}
+  worst = max(err, key=lambda k: err[k] / max(RTOL_BF16, floor[k]))
+  print(dict(relu_decisions_flipped_by_bf16_storage=flipped, dx_floor=floor['x'], dx_err=err['x'],
+             weights_err_max=max(v for k, v in err.items() if k.endswith('weights')),
+             within_2e2=sum(1 for v in err.values() if v < RTOL_BF16), tensors=len(err), worst=(worst, err[worst], floor[worst])))
+  assert 1e-4 < flipped < 3e-3
+  assert floor['x'] > RTOL_BF16             # bf16 storage ALONE moves dx by more than the bar (no CUDA code involved)
+  assert float(np.median(list(err.values()))) < RTOL_BF16
+  for k in err:
+    assert err[k] < max(RTOL_BF16, floor[k]), (k, err[k], floor[k])
+    assert cos(got[k], g32[k]) > 0.98, k     # and the direction agrees with the fp32 gradient
 
 
 def test_fc_concat_bf16_tensor_core():
@@ -176,7 +179,7 @@ def test_fc_concat_bf16_tensor_core():
 
 def test_model_train_step_bf16_against_fp32_oracle():
   """Whole model with head_dtype=bfloat16 (K1 bf16 output, tcgen05 head + FC): scores / losses within 2e-2 of
-  the fp32 oracle; extracted labels stay exact."""
+  the fp32 oracle; extracted labels and (given the path's own scores) OICR seeds / soft labels stay exact."""
   import tempfile
   from cap2det_b200 import builder, config, synthetic
   from cap2det_b200.standard_fields import InputDataFields as F
@@ -218,6 +221,31 @@ def test_model_train_step_bf16_against_fp32_oracle():
   assert rel_err(pred['midn_proba_r_given_c'].detach().cpu().numpy(), want['proba']) < RTOL_BF16
   assert abs(float(loss['midn_cross_entropy_loss']) - want['loss']['midn_cross_entropy_loss']) <= \
       RTOL_BF16 * abs(want['loss']['midn_cross_entropy_loss'])
+  # OICR: the pseudo-labelling is a DISCRETE function of the scores (arg-max seed, IoU threshold).  (1) Given the
+  # scores the bf16 path itself produced, seeds, soft labels and the three losses must be what the oracle derives
+  # from those same scores -- indices / labels bit-exact, losses 1e-5.
+  from oracle import midn_oicr
+  stages = [pred['oicr_proposal_scores_at_%d' % (i + 1)].detach().cpu().numpy() for i in range(K)]
+  with np.errstate(invalid='ignore', divide='ignore'):
+    o_loss, o_aux = midn_oicr.build_loss(pred['midn_class_logits'].detach().cpu().numpy(),
+                                         pred['midn_proba_r_given_c'].detach().cpu().numpy(), stages, labels, npr, props,
+                                         1.0, 0.5, 0.6)
+  for i in range(K):
+    np.testing.assert_array_equal(model.last_oicr_assignments[i][0].cpu().numpy(), o_aux[i][0])
+    np.testing.assert_array_equal(model.last_oicr_assignments[i][1].cpu().numpy(), o_aux[i][1])
+    key = 'oicr_cross_entropy_loss_at_%d' % (i + 1)
+    assert abs(float(loss[key]) - float(o_loss[key])) <= 1e-5 * abs(float(o_loss[key])), key
+  # (2) Against the end-to-end fp32 oracle: wherever the bf16 scores pick the same seeds as the fp32 scores, the
+  # stage loss is within the 2e-2 bar; a stage whose seeds differ (a near-tie decided the other way) is reported.
+  agree = []
+  for i in range(K):
+    same = np.array_equal(o_aux[i][0], want['aux'][i][0]) and np.array_equal(o_aux[i][1], want['aux'][i][1])
+    agree.append(bool(same))
+    key = 'oicr_cross_entropy_loss_at_%d' % (i + 1)
+    if same:
+      assert abs(float(loss[key]) - want['loss'][key]) <= RTOL_BF16 * abs(want['loss'][key]), key
+  print('OICR stages whose seeds / labels agree between bf16 and fp32 scores:', agree)
+  assert agree[0]            # stage 1 is seeded by the MIDN scores, which are within 2e-2; this data has no near-tie
   assert torch.isfinite(model.head_params.grad).all() and torch.isfinite(model.fc_weights.grad).all()
   assert pred['detection_boxes_at_3'].shape == (B, 300, 4)
 
@@ -297,21 +325,21 @@ def test_graphed_train_step_matches_eager_steps():
       with torch.no_grad():
         model.fc_weights.mul_(8.0)
       step = trainer.TrainStep(model, learning_rate=0.01)
+      init = [v.detach().clone() for v in model.get_variables_to_train()]
       run = trainer.GraphedTrainStep(step, batches[0]) if graphed else step
-      if graphed:       # construction ran warm-up steps on batch 0: restore the initial state
-        with torch.no_grad():
-          for v, v0 in zip(model.get_variables_to_train(), models[0]['init']):
-            v.copy_(v0)
-          for a in step.opt.accum:
-            a.fill_(0.1)
+      if graphed:       # construction warms up and captures, but must not train: state and step counter untouched
+        for v, v0 in zip(model.get_variables_to_train(), init):
+          assert torch.equal(v.detach(), v0)
+        assert all(bool((a == 0.1).all()) for a in step.opt.accum) and step.global_step == 0
       else:
-        models.append({'init': [v.detach().clone() for v in model.get_variables_to_train()]})
+        models.append({'init': init})
       out = []
       for ex in batches:
         if not graphed:
           ex[F.features_to_crop].grad = None
         out.append(float(run(ex)))
       model.raise_if_assert_failed()
+      assert step.global_step == len(batches)
       totals.append(out)
       models[-1 if graphed else 0]['final' if not graphed else 'final_g'] = [v.detach().clone() for v in model.get_variables_to_train()]
     assert run.launches_per_step > 50

@@ -171,3 +171,32 @@ def test_greedy_nms_reproduces_tensorflows_published_examples():
   assert list(nms.greedy_nms(boxes, scores, cand, 10, 0.5)) == [3, 0, 5]
   assert list(nms.greedy_nms(boxes[:1], scores[:1], np.arange(1), 3, 0.5)) == [0]
   assert list(nms.greedy_nms(boxes[:0], scores[:0], np.arange(0), 3, 0.5)) == []
+
+
+def test_bf16_storage_alone_moves_relu_network_gradients_past_2e2():
+  """Why the bf16 head's gradients are not checked at 2e-2 against the fp32 oracle: on the CPU oracle ALONE (fp32
+  arithmetic everywhere, only the STORAGE of weights / activations / activation gradients rounded to bf16 as the
+  tensor-core path stores them), ~0.1 % of the ReLU decisions flip and the gradients move by several percent.
+  No kernel is involved: any bf16 implementation of this 17-layer network inherits this floor."""
+  import torch
+  from oracle import head as ohead
+  rng = np.random.default_rng(5)
+  n = 6
+  p = ohead.random_head_params(31)
+  x0 = torch.from_numpy(np.maximum(rng.standard_normal((n, 7, 7, 576)).astype(np.float32), 0)).to(torch.bfloat16).float().numpy()
+  keep = (rng.uniform(size=(n, 1024)) < 0.5).astype(np.float32)
+  dfeat = rng.standard_normal((n, 1024)).astype(np.float32)
+  res = []
+  for emulate in (False, True):
+    tp = {k: {kk: torch.from_numpy(v).requires_grad_(kk == 'weights') for kk, v in q.items()} for k, q in p.items()}
+    xt = torch.from_numpy(x0).requires_grad_(True)
+    col = {}
+    feat = ohead.avgpool_dropout(ohead.head_mixed5(xt, tp, emulate_bf16=emulate, collect=col), 0.5, keep)
+    feat.backward(torch.from_numpy(dfeat))
+    res.append((feat.detach().numpy(), xt.grad.numpy(), {k: v.numpy() for k, v in col.items()}))
+  (f32, dx32, u32), (f16, dx16, u16) = res
+  flipped = float(np.mean([((u32[k] > 0) != (u16[k] > 0)).mean() for k in u32 if k in u16]))
+  rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))
+  assert np.abs(f16 - f32).max() / np.abs(f32).max() < 2e-2       # the FORWARD stays inside the bar
+  assert 1e-4 < flipped < 3e-3
+  assert rel(dx16, dx32) > 2e-2                                    # the gradient does not

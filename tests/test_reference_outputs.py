@@ -135,10 +135,12 @@ def test_oracle_label_extractors_match_executed_reference():
   vocab = [str(v) for v in G['labels_vocab']]
   got, _ = olabels.word_vector_match_extract(classes, vocab, G['labels_wordvec_embedding_with_oov'], texts)
   assert np.array_equal(got, G['labels_wordvec'])
+  tc_classes = [str(c) for c in G['labels_tc_classes']]
   got, _ = olabels.text_classifier_match_extract(
-      classes, vocab, G['labels_textclassifier_embedding_with_oov'], G['labels_tc_layer1_weights'],
-      G['labels_tc_layer1_biases'], G['labels_tc_layer2_weights'], G['labels_tc_layer2_biases'], 0.5, texts)
+      tc_classes, vocab, G['labels_textclassifier_embedding_with_oov'], G['labels_tc_layer1_weights'],
+      G['labels_tc_layer1_biases'], G['labels_tc_layer2_weights'], G['labels_tc_layer2_biases'], 0.5, rows(G['labels_tc_texts']))
   assert np.array_equal(got, G['labels_textclassifier'])
+  assert G['labels_textclassifier'][-1].tolist() == [0, 0, 0, 0, 0, 0, 1]   # 'zebra' is not in the open vocabulary
   empty = [[] for _ in range(3)]
   assert np.array_equal(olabels.exact_match_extract(classes, empty), G['labels_exact_no_tokens'])
   assert np.array_equal(olabels.extend_match_extract(syn_classes, name2id, empty), G['labels_extend_no_tokens'])
@@ -320,10 +322,18 @@ def test_cuda_label_extractors_match_executed_reference():
                   'text_classifier/layer1/biases': G['labels_tc_layer1_biases'],
                   'text_classifier/layer2/weights': G['labels_tc_layer2_weights'],
                   'text_classifier/layer2/biases': G['labels_tc_layer2_biases']})
+  tc_label_file = synthetic.write_label_file(d, [str(c) for c in G['labels_tc_classes']], name='tc_label.txt')
   tc = build('text_classifier_match_extractor', "label_file: '%s' open_vocabulary_file: '%s' "
              "open_vocabulary_word_embedding_file: '%s' text_classifier_checkpoint_file: '%s' hidden_units: 12 "
-             "label_threshold: 0.5" % (label_file, vocab_file, emb_file, ck))
-  assert np.array_equal(tc.extract_labels(ex).cpu().numpy(), G['labels_textclassifier'])
+             "label_threshold: 0.5" % (tc_label_file, vocab_file, emb_file, ck))
+  tc_ex = {F.concat_caption_string: rows(G['labels_tc_texts'])}
+  # The reference draws the out-of-vocabulary embedding row from UNSEEDED np.random (models/label_extractor.py:383-384)
+  # and that row does reach the output: a caption without any in-vocabulary token pools to the minimum over its OOV
+  # rows (masked_maximum, core/utils.py:63-80).  Parity therefore needs the row the reference run drew.
+  tc._build()
+  with torch.no_grad():
+    tc._embedding_weights[-1].copy_(dev(G['labels_textclassifier_embedding_with_oov'][-1]))
+  assert np.array_equal(tc.extract_labels(tc_ex).cpu().numpy(), G['labels_textclassifier'])
   empty = {F.concat_caption_string: [[] for _ in range(3)], F.object_texts: [[] for _ in range(3)]}
   assert np.array_equal(build('exact_match_extractor', "label_file: '%s'" % label_file).extract_labels(empty).cpu().numpy(),
                         G['labels_exact_no_tokens'])
