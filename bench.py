@@ -465,7 +465,7 @@ def main():
   # One GPU: the step is captured once into a CUDA graph (trainer.GraphedTrainStep, part of the public API) and
   # replayed; inputs are copied into its static buffers every step.  Falls back to eager steps if capture fails.
   graphed = None
-  if world == 1 and not args.no_cuda_graph:
+  if not args.no_cuda_graph:
     try:
       graphed = trainer.GraphedTrainStep(step, resident[0])
     except Exception as e:      # noqa: BLE001 - any capture problem means: measure the eager path
@@ -618,7 +618,7 @@ def main():
              steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
              scaling='weak', vs_baseline=None, dtype=head_dtype, data='synthetic',
              config=dict(CONFIG, global_batch_images=world * B, parallelism='dp%d (by image)' % world,
-                         step_launch='CUDA graph replay (trainer.GraphedTrainStep)' if graphed is not None else 'eager',
+                         step_launch=('CUDA graph replay (trainer.GraphedTrainStep)' if world == 1 else 'CUDA graphs (3 per step) + one eager NCCL all-reduce between them (trainer.GraphedTrainStep)') if graphed is not None else 'eager',
                          l2_handling='256 MB L2 flush between timed iterations', head_dtype=head_dtype),
              images_per_sec=value / P, clocks=clocks, gpu_launches=launches,
              e2e=dict(value=e2e_value, unit='proposals/s', h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4,

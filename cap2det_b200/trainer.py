@@ -270,6 +270,45 @@ class TrainStep(object):
     reg = self.regularization_loss()
     return total + reg if reg is not None else total
 
+  # ---- the phases of a step (GraphedTrainStep captures them as separate CUDA graphs when world_size > 1) ----
+  def forward_backward(self, examples):
+    """Forward, losses and the backward of everything that has trainable variables.  With
+    model.split_backward_at_roi the gradient stops at the ROI output (see backward_below_roi)."""
+    model = self.model
+    self.opt.zero_grad()
+    self.opt.lr = self.learning_rate()
+    predictions = model.build_prediction(examples)
+    loss_dict = model.build_loss(predictions, examples)
+    total = None
+    for v in loss_dict.values():
+      total = v if total is None else total + v
+    self._pending = []
+    total.backward()
+    self.last_loss_dict = loss_dict
+    return total.detach()
+
+  def backward_below_roi(self):
+    """The rest of the backward pass: ROI crop / max-pool (and the first stage) from the gradient of the ROI output."""
+    split = getattr(self.model, '_roi_split', None)
+    if split is not None and split[1].grad is not None:
+      split[0].backward(split[1].grad)
+      self.model._roi_split = None
+
+  def reduce_gradients(self):
+    if self.world_size > 1:
+      # gradient buffers whose hook fired are already being reduced (see _reduce_when_ready); reduce the rest
+      started = {id(v) for v, _ in self._pending}
+      c2d_dist.allreduce_sum([v.grad for v in self.model.get_variables_to_train() if v.grad is not None and id(v) not in started])
+      for _, work in self._pending:
+        work.wait()
+      self._pending = []
+
+  def update(self, total):
+    self.opt.step(grad_scale=1.0 / self.world_size)
+    self.global_step += 1
+    reg = self.regularization_loss()
+    return total + reg if reg is not None else total
+
   def __call__(self, examples):
     """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""
     total = self.forward_backward(examples)
@@ -279,21 +318,29 @@ class TrainStep(object):
 
 
 class GraphedTrainStep(object):
-  """A TrainStep captured once into a CUDA graph and replayed: the ~140 kernel launches of a step (and the gaps
-  between dependent launches) collapse into one graph launch.  Fixed shapes only: every step must bring tensors
-  of the shapes seen at construction.  Label extraction (host-side tokenisation) stays outside the graph; its
-  [B, C] result and the input tensors are copied into static buffers before each replay.  The learning rate is
-  baked in at capture time (every reference config keeps it constant, learning_rate_decay.decay_rate 1.0).
-  Single process only (world_size 1)."""
+  """A TrainStep captured once into CUDA graphs and replayed: the ~140 kernel launches of a step (and the gaps
+  between dependent launches) collapse into one graph launch -- or, data parallel, into three with the NCCL
+  all-reduce issued between them.  Fixed shapes only: every step must bring tensors of the shapes seen at
+  construction.  Label extraction (host-side tokenisation) stays outside the graph; its [B, C] result and the input
+  tensors are copied into static buffers before each replay.  The learning rate is baked in at capture time (every
+  reference config keeps it constant, learning_rate_decay.decay_rate 1.0).
 
-  def __init__(self, train_step, examples):
-    if train_step.world_size != 1:
-      raise ValueError('GraphedTrainStep supports world_size 1')
+  world_size > 1 (one process per GPU, torch.distributed initialised): NCCL calls are NOT captured (capturing them
+  hung in round 1).  The step is cut where the data path allows it:
+      graph A  forward, losses, backward down to the ROI output -> every trainable gradient is complete
+      eager    ONE all-reduce of the flat gradient bucket on a side stream
+      graph B  ROI crop / max-pool (and first-stage) backward, concurrently with the all-reduce
+      graph C  Adagrad update (x 1/world) after the all-reduce, regularisation loss
+  so the collective overlaps the ~0.6 ms of ROI backward exactly as the eager hooks arrange it, and the host issues
+  3 graph launches + 1 NCCL call per step.  `split_graphs=True` forces this form in a single process (tests)."""
+
+  def __init__(self, train_step, examples, split_graphs=None):
     tc = train_step.train_config
     if tc is not None and tc.HasField('learning_rate_decay') and float(tc.learning_rate_decay.decay_rate) != 1.0:
       raise ValueError('GraphedTrainStep bakes the learning rate into the captured graph; a decaying learning rate '
                        '(learning_rate_decay.decay_rate != 1) needs eager TrainStep calls')
     self.step = train_step
+    self.world_size = train_step.world_size
     model = train_step.model
     self._extract = model._label_extractor.extract_labels
     self.static = {k: v.detach().clone().requires_grad_(v.requires_grad) for k, v in examples.items() if torch.is_tensor(v)}
@@ -303,17 +350,52 @@ class GraphedTrainStep(object):
     # put back afterwards.  (Capture itself records the kernels without running them.)
     variables = model.get_variables_to_train()
     saved = ([v.detach().clone() for v in variables], [a.clone() for a in train_step.opt.accum], train_step.global_step)
+    self.split = self.world_size > 1 if split_graphs is None else bool(split_graphs)
+    if self.split:
+      # gradients live in ONE flat bucket (a single all-reduce); autograd accumulates into the views in place
+      n = sum(v.numel() for v in variables)
+      self.bucket = torch.zeros((n,), dtype=torch.float32, device=variables[0].device)
+      off = 0
+      for v in variables:
+        v.grad = self.bucket[off:off + v.numel()].view_as(v)
+        off += v.numel()
+      train_step.opt.static_grads = self.bucket
+      train_step.overlap_hooks = False
+      model.split_backward_at_roi = True
+      self.comm_stream = torch.cuda.Stream()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
       for _ in range(3):
-        self._run_static()
+        self._run_static_eager()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
+    # The warm-up steps left their tf.Assert status chain in the model.  A capture that OR-ed its own status onto it
+    # would bake the address of an EAGER tensor into the graph, and that tensor dies as soon as the chain is
+    # replaced (found the hard way: the next capture's empty_cache() unmapped it -> illegal address at replay).
+    model._assert_status = None
     before = capi.launch_count()
-    self.graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(self.graph):
-      self.static_total = self._run_static()
+    if not self.split:
+      self.graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph):
+        self.static_total = self._run_static_eager()
+    else:
+      # thread_local: the NCCL watchdog thread of torch.distributed keeps polling its events while we capture
+      mode = dict(capture_error_mode='thread_local')
+      self.graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph, **mode):
+        for v in self.static.values():
+          if v.requires_grad:
+            v.grad = None
+        self._partial_total = train_step.forward_backward(self._static_examples())
+      self.graph_b = None
+      if getattr(model, '_roi_split', None) is not None:      # nothing below the ROI needs a gradient otherwise
+        self.graph_b = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph_b, pool=self.graph.pool(), **mode):
+          train_step.backward_below_roi()
+      self.graph_c = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(self.graph_c, pool=self.graph.pool(), **mode):
+        self.static_total = train_step.update(self._partial_total)
     self.launches_per_step = capi.launch_count() - before
     self._status = model._assert_status
     with torch.no_grad():
@@ -325,12 +407,28 @@ class GraphedTrainStep(object):
     model._assert_status = None
     torch.cuda.synchronize()
 
-  def _run_static(self):
-    for v in self.static.values():
-      v.grad = None
+  def _static_examples(self):
     ex = dict(self.static)
     ex['_labels'] = self.static_labels
-    return self.step(ex)
+    return ex
+
+  def _run_static_eager(self):
+    for v in self.static.values():
+      v.grad = None
+    if not self.split:
+      return self.step(self._static_examples())
+    total = self.step.forward_backward(self._static_examples())
+    self._all_reduce_bucket()
+    self.step.backward_below_roi()
+    torch.cuda.current_stream().wait_stream(self.comm_stream)
+    return self.step.update(total)
+
+  def _all_reduce_bucket(self):
+    import torch.distributed as dist
+    self.comm_stream.wait_stream(torch.cuda.current_stream())
+    if self.world_size > 1:
+      with torch.cuda.stream(self.comm_stream):
+        dist.all_reduce(self.bucket, op=dist.ReduceOp.SUM)
 
   def extract_labels(self, examples):
     """The image-level labels of a batch (host tokenisation + one small kernel).  Call it ahead of time on a side
@@ -341,8 +439,16 @@ class GraphedTrainStep(object):
     self.static_labels.copy_(labels if labels is not None else self._extract(examples), non_blocking=True)
     for k, v in self.static.items():
       v.detach().copy_(examples[k], non_blocking=True)
-    self.graph.replay()
-    self.step.global_step += 1                  # replays skip the host code of TrainStep.__call__
+    if not self.split:
+      self.graph.replay()
+    else:
+      self.graph.replay()                       # forward + backward of everything trainable
+      self._all_reduce_bucket()                 # side stream; overlaps graph B
+      if self.graph_b is not None:
+        self.graph_b.replay()                   # ROI (and first-stage) backward
+      torch.cuda.current_stream().wait_stream(self.comm_stream)
+      self.graph_c.replay()                     # Adagrad on the reduced gradients
+    self.step.global_step += 1                  # replays skip the host code of TrainStep
     self.step.model._assert_status = self._status
     return self.static_total
 

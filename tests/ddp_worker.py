@@ -47,6 +47,49 @@ def main():
   dist.all_reduce(flag, op=dist.ReduceOp.MIN)
   if rank == 0:
     print('DDP_REPLICAS_IDENTICAL' if int(flag.item()) == 1 else 'DDP_REPLICAS_DIVERGED')
+
+  # The CUDA-graph step (three graphs + one eager all-reduce of the flat gradient bucket) against eager steps of an
+  # identically initialised model on the same per-rank data: same losses, replicas identical.
+  torch.cuda.set_stream(torch.cuda.Stream())
+  results = []
+  for graphed in (False, True):
+    model = builder.build(m, is_training=True, head_dtype=torch.bfloat16, seed=3)
+    with torch.no_grad():
+      model.fc_weights.mul_(8.0)
+    for v in model.get_variables_to_train():
+      dist.broadcast(v.data, src=0)
+    step = trainer.TrainStep(model, learning_rate=0.01, world_size=world)
+    rng = np.random.default_rng(200 + rank)
+    B, P = 1, 48
+
+    def batch():
+      return {F.features_to_crop: torch.from_numpy(synthetic.make_feature_map(rng, B, 160, 208)).cuda().requires_grad_(True),
+              F.proposals: torch.from_numpy(synthetic.make_proposals(rng, B, P, 160, 208)).cuda(),
+              F.num_proposals: torch.full((B,), P, dtype=torch.int32, device='cuda'),
+              F.object_texts: synthetic.make_object_texts(rng, B, classes),
+              F.dropout_keep_mask: torch.from_numpy((rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)).cuda()}
+
+    batches = [batch() for _ in range(3)]
+    run = trainer.GraphedTrainStep(step, batches[0]) if graphed else step
+    losses = []
+    for ex in batches:
+      if not graphed:
+        ex[F.features_to_crop].grad = None
+      losses.append(float(run(ex)))
+    model.raise_if_assert_failed()
+    same = True
+    for v in model.get_variables_to_train():
+      ref = v.detach().clone()
+      dist.broadcast(ref, src=0)
+      same = same and bool(torch.equal(ref, v.detach()))
+    results.append((losses, same, [v.detach().clone() for v in model.get_variables_to_train()]))
+  (l_e, same_e, w_e), (l_g, same_g, w_g) = results
+  close = all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l_e, l_g))
+  drift = max(float((a - b).norm() / a.norm()) for a, b in zip(w_e, w_g))
+  flag = torch.tensor([1 if (same_e and same_g and close and drift < 3e-3) else 0], device='cuda')
+  dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+  if rank == 0:
+    print('DDP_GRAPHED_OK' if int(flag.item()) == 1 else 'DDP_GRAPHED_BAD', l_e, l_g, same_e, same_g, drift)
   dist.barrier()
   dist.destroy_process_group()
 

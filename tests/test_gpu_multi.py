@@ -15,5 +15,6 @@ def test_two_ranks_stay_identical():
   root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
          '--master-port', '29561', os.path.join(root, 'tests', 'ddp_worker.py')]
-  out = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=root)
+  out = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=root)
   assert 'DDP_REPLICAS_IDENTICAL' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+  assert 'DDP_GRAPHED_OK' in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
