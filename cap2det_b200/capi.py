@@ -86,7 +86,8 @@ SIGNATURES = {
                                            _c_float, _p, _p, _p, _p]),
     'c2d_adagrad_update': (_c_int, [_p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _p]),
     'c2d_l2_loss': (_c_int, [_p, _c_ll, _c_float, _p, _p]),
-    'c2d_wordvec_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _c_int, _p, _p, _p, _p]),
+    'c2d_wordvec_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int]),
+    'c2d_wordvec_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _c_int, _p, _p, _p, _p, _p]),
 }
 
 _lib = None

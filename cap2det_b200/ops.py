@@ -499,8 +499,9 @@ def wordvec_match(token_ids, emb, class_ids, exact_lut, return_similarity=False)
   C = class_ids.numel()
   labels = torch.empty((B, C), dtype=torch.float32, device=token_ids.device)
   sim = torch.empty((B, C), dtype=torch.float32, device=token_ids.device) if return_similarity else None
+  ws = torch.empty((max(1, capi.load().c2d_wordvec_workspace_bytes(B, T, C)),), dtype=torch.uint8, device=token_ids.device)
   call('c2d_wordvec_match', ptr(token_ids), B, T, ptr(emb), V, D, ptr(class_ids), C, ptr(exact_lut), ptr(labels),
-       ptr(sim), stream())
+       ptr(sim), ptr(ws), stream())
   return (labels, sim) if return_similarity else labels
 
 

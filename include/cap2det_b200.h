@@ -258,10 +258,12 @@ int c2d_label_lut(const int* token_ids, int B, int T, const int* lut, int V, int
                   c2d_stream_t stream);
 /* ---- K8: WordVectorMatchExtractor.extract_labels, models/label_extractor.py:251-328 ------
  * emb [V+1,D] (row V = OOV), class_ids [C] rows of the classes, exact_lut as c2d_label_lut.
- * sim_pooled [B,C] may be NULL. */
+ * sim_pooled [B,C] may be NULL.  workspace: c2d_wordvec_workspace_bytes(B, T, C) bytes (the [B,T,C] cosine
+ * matrix, models/label_extractor.py:232-249: it is spread over (token tile, image) CTAs, then reduced per image). */
+size_t c2d_wordvec_workspace_bytes(int B, int T, int C);
 int c2d_wordvec_match(const int* token_ids, int B, int T, const float* emb, int V, int D,
                       const int* class_ids, int C, const int* exact_lut, float* labels,
-                      float* sim_pooled, c2d_stream_t stream);
+                      float* sim_pooled, void* workspace, c2d_stream_t stream);
 
 /* ---- TextClassifierMatchExtractor.extract_labels, models/label_extractor.py:363-472 ----
  * emb [V+1,D] (row V = OOV); w1 [D,H], b1 [H], w2 [H,C], b2 [C] are the text_classifier/layer{1,2} variables in

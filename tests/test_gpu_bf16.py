@@ -320,13 +320,13 @@ def test_graphed_train_step_matches_eager_steps():
 
     batches = [batch() for _ in range(3)]
     models, totals = [], []
-    for graphed in (False, True):
+    for graphed in (False, True, 'split'):       # 'split': the three-graph form data-parallel steps use, on one GPU
       model = builder.build(m, is_training=True, head_dtype=torch.bfloat16)
       with torch.no_grad():
         model.fc_weights.mul_(8.0)
       step = trainer.TrainStep(model, learning_rate=0.01)
       init = [v.detach().clone() for v in model.get_variables_to_train()]
-      run = trainer.GraphedTrainStep(step, batches[0]) if graphed else step
+      run = trainer.GraphedTrainStep(step, batches[0], split_graphs=(graphed == 'split')) if graphed else step
       if graphed:       # construction warms up and captures, but must not train: state and step counter untouched
         for v, v0 in zip(model.get_variables_to_train(), init):
           assert torch.equal(v.detach(), v0)
@@ -341,10 +341,11 @@ def test_graphed_train_step_matches_eager_steps():
       model.raise_if_assert_failed()
       assert step.global_step == len(batches)
       totals.append(out)
-      models[-1 if graphed else 0]['final' if not graphed else 'final_g'] = [v.detach().clone() for v in model.get_variables_to_train()]
+      models[0]['final' if not graphed else 'final_g_%s' % graphed] = [v.detach().clone() for v in model.get_variables_to_train()]
     assert run.launches_per_step > 50
     np.testing.assert_allclose(totals[1], totals[0], rtol=2e-3)
-    for a, b in zip(models[0]['final'], models[0]['final_g']):
+    np.testing.assert_allclose(totals[2], totals[0], rtol=2e-3)
+    for a, b in list(zip(models[0]['final'], models[0]['final_g_True'])) + list(zip(models[0]['final'], models[0]['final_g_split'])):
       # identical kernels; only the order of floating-point atomics (ROI backward, weight gradients) differs, which
       # the bf16 roundings downstream amplify (measured: 1e-4 of the norm for the weights, 8e-4 for the biases, which
       # start at zero and move by Adagrad's normalised steps)
