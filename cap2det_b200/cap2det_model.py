@@ -40,6 +40,8 @@ def _trunc_normal_(t, std, gen):
 class Model(ModelBase):
   """Cap2Det model."""
 
+  fold_pool_backward = True      # see ops.PoolFold; False keeps the head's own max-pool backward kernel (tests compare both)
+
   def __init__(self, model_proto, is_training=False, device=None, head_dtype=torch.float32, seed=0,
                first_stage=False):
     """Initializes the model.
@@ -175,8 +177,13 @@ class Model(ModelBase):
     if frcnn.dropout_on_feature_map:
       raise NotImplementedError('dropout_on_feature_map is off in every reference config (configs/*.pbtxt:55)')
     # models/utils.py:147-160
+    # bf16 training: the backward of the head's first max-pool is applied inside the ROI backward (ops.PoolFold)
+    fold = None
+    if (self.fold_pool_backward and self._head_dtype == torch.bfloat16 and features_to_crop.requires_grad
+        and frcnn.initial_crop_size == 14 and torch.is_grad_enabled()):
+      fold = ops.PoolFold()
     x0 = ops.roi_crop_maxpool(features_to_crop, proposals, frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
-                              frcnn.maxpool_stride, out_dtype=self._head_dtype)
+                              frcnn.maxpool_stride, out_dtype=self._head_dtype, fold=fold)
     self._roi_split = None
     if getattr(self, 'split_backward_at_roi', False) and x0.requires_grad:
       # Data-parallel steps cut the autograd graph here: the backward of everything above (all trainable head / FC
@@ -193,7 +200,7 @@ class Model(ModelBase):
       if keep_mask is None:   # TF1 slim.dropout: floor(keep_prob + uniform[0,1))
         keep_mask = torch.floor(keep_prob + torch.rand((B * P, ops.HEAD_FEATURE_DIMS), device=x0.device))
     feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
-                           need_dx0=features_to_crop.requires_grad)
+                           need_dx0=features_to_crop.requires_grad, fold=fold)
     # models/cap2det_model.py:79-88,190-197: the five FC layers as one product
     logits_all = ops.fc_concat(feat, self.fc_weights, self.fc_biases, compute_dtype=self._head_dtype).view(B, P, -1)
     midn_class_logits, midn_proposal_scores, midn_proba_r_given_c = ops.midn(

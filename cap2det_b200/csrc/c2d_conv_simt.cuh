@@ -501,9 +501,12 @@ pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict_
 
 // Mixed_5a/Branch_2 MaxPool_1a_3x3 (7x7 -> 4x4, stride 2, SAME) on bf16 planes with FOUR channels per thread.
 // max is exact in bf16, so the plane stays packed (49 x 8 bytes = 98 registers) and the windows use __hmax2.
+// `codes` (optional, [n,16,C] bytes): tap index dy*3+dx of the FIRST maximum of every window in row-major window
+// order (the element TF routes the gradient to); the ROI backward uses it to apply this pool's backward on the fly
+// (c2d_roi_crop_maxpool_bwd_codes_fold), which removes a 226 MB read-modify-write pass over dX0.
 static __global__ void __launch_bounds__(128)
 maxpool3x3_s2_7x7_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ y, int ldy,
-                              int n_rois, int C) {
+                              int n_rois, int C, unsigned char* __restrict__ codes) {
   const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   const int n = blockIdx.y;
   if (c >= C || n >= n_rois) return;
@@ -531,6 +534,30 @@ maxpool3x3_s2_7x7_bf16_kernel(const __nv_bfloat16* __restrict__ x, int ldx, __nv
       uint2 o;
       o.x = *reinterpret_cast<uint32_t*>(&m0); o.y = *reinterpret_cast<uint32_t*>(&m1);
       *reinterpret_cast<uint2*>(y + ((size_t)n * 16 + oy * 4 + ox) * ldy + c) = o;
+      if (codes != nullptr) {
+        // first tap (row-major) whose value equals the window maximum, per channel; scanned backwards so that the
+        // earliest match is the one that stays
+        const unsigned short mx[4] = {(unsigned short)(o.x & 0xffffu), (unsigned short)(o.x >> 16),
+                                      (unsigned short)(o.y & 0xffffu), (unsigned short)(o.y >> 16)};
+        unsigned code = 0;
+#pragma unroll
+        for (int dy = 1; dy >= -1; --dy)
+#pragma unroll
+          for (int dx = 1; dx >= -1; --dx) {
+            const int iy = 2 * oy + dy, ix = 2 * ox + dx;
+            if (iy >= 0 && iy < 7 && ix >= 0 && ix < 7) {
+              const uint2 t = v[iy * 7 + ix];
+              const unsigned tap = (unsigned)((dy + 1) * 3 + (dx + 1));
+              const unsigned short e[4] = {(unsigned short)(t.x & 0xffffu), (unsigned short)(t.x >> 16),
+                                           (unsigned short)(t.y & 0xffffu), (unsigned short)(t.y >> 16)};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (__heq(__ushort_as_bfloat16(e[k]), __ushort_as_bfloat16(mx[k])))
+                  code = (code & ~(0xffu << (8 * k))) | (tap << (8 * k));
+            }
+          }
+        *reinterpret_cast<unsigned*>(codes + ((size_t)n * 16 + oy * 4 + ox) * C + c) = code;
+      }
     }
 }
 

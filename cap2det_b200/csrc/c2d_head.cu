@@ -211,7 +211,7 @@ size_t c2d_head_workspace_bytes(int n_rois, int dtype) {
 }
 
 int c2d_head_mixed5_bwd_bf16(const void*, int, const float*, const HeadPlan&, char*, const float*, float,
-                             const float*, float*, void*, cudaStream_t);
+                             const float*, float*, void*, int, cudaStream_t);
 int c2d_head_mixed5_fwd_bf16(const void*, int, const float*, const HeadPlan&, char*, const float*, float, float*,
                              cudaStream_t);
 
@@ -232,11 +232,12 @@ int c2d_head_mixed5_fwd(const void* x0, int n_rois, int dtype, const float* para
                                   (cudaStream_t)stream);
 }
 
-int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
-                        size_t workspace_bytes, const float* keep_mask, float keep_prob, const float* dfeat,
-                        float* dparams, void* dx0, c2d_stream_t stream) {
+static int head_bwd_dispatch(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                             size_t workspace_bytes, const float* keep_mask, float keep_prob, const float* dfeat,
+                             float* dparams, void* dx0, int fold_pool5a, c2d_stream_t stream) {
   C2D_CHECK_ARG(n_rois >= 0, "head_bwd: n_rois must be >= 0");
   C2D_CHECK_ARG(dtype == C2D_F32 || dtype == C2D_BF16, "head_bwd: bad dtype %d", dtype);
+  C2D_CHECK_ARG(!fold_pool5a || dtype == C2D_BF16, "head_bwd: the folded max-pool backward exists on the bf16 path only");
   HeadPlan pl = make_head_plan(n_rois, dtype == C2D_F32 ? 4 : 2);
   C2D_CHECK_ARG(workspace_bytes >= pl.total_bytes, "head_bwd: workspace too small");
   if (n_rois == 0) {
@@ -247,7 +248,31 @@ int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* para
     return head_bwd_f32((const float*)x0, n_rois, params, pl, (char*)workspace, keep_mask, keep_prob, dfeat, dparams,
                         (float*)dx0, (cudaStream_t)stream);
   return c2d_head_mixed5_bwd_bf16(x0, n_rois, params, pl, (char*)workspace, keep_mask, keep_prob, dfeat, dparams, dx0,
-                                  (cudaStream_t)stream);
+                                  fold_pool5a, (cudaStream_t)stream);
+}
+
+int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                        size_t workspace_bytes, const float* keep_mask, float keep_prob, const float* dfeat,
+                        float* dparams, void* dx0, c2d_stream_t stream) {
+  return head_bwd_dispatch(x0, n_rois, dtype, params, workspace, workspace_bytes, keep_mask, keep_prob, dfeat, dparams,
+                           dx0, 0, stream);
+}
+
+int c2d_head_mixed5_bwd_fold(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                             size_t workspace_bytes, const float* keep_mask, float keep_prob, const float* dfeat,
+                             float* dparams, void* dx0_partial, const unsigned char** pool_codes,
+                             const void** pool_grad, int* pool_grad_ld, c2d_stream_t stream) {
+  C2D_CHECK_ARG(pool_codes != nullptr && pool_grad != nullptr && pool_grad_ld != nullptr && dx0_partial != nullptr,
+                "head_bwd_fold: null output");
+  int rc = head_bwd_dispatch(x0, n_rois, dtype, params, workspace, workspace_bytes, keep_mask, keep_prob, dfeat,
+                             dparams, dx0_partial, 1, stream);
+  if (rc != C2D_OK) return rc;
+  HeadPlan pl = make_head_plan(n_rois, 2);
+  char* ws = (char*)workspace;
+  *pool_codes = reinterpret_cast<const unsigned char*>(ws + pl.pool5a_code_off);
+  *pool_grad = reinterpret_cast<const __nv_bfloat16*>(ws + pl.grad_off[X1]) + 448;     // dX1[:, :, :, 448:1024)
+  *pool_grad_ld = kHeadBufs[X1].ch;
+  return C2D_OK;
 }
 
 // ---- K4 fully connected -------------------------------------------------------------------

@@ -139,7 +139,8 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
     if (i == 5) {
-      maxpool3x3_s2_7x7_bf16_kernel<<<dim3(cdiv(576 / 4, 128), n), 128, 0, st>>>(act[X0], 576, act[X1] + 448, 1024, n, 576);
+      maxpool3x3_s2_7x7_bf16_kernel<<<dim3(cdiv(576 / 4, 128), n), 128, 0, st>>>(
+          act[X0], 576, act[X1] + 448, 1024, n, 576, reinterpret_cast<unsigned char*>(ws + pl.pool5a_code_off));
       count_launch();
     }
     if (i == 18) {
@@ -179,9 +180,11 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   return C2D_OK;
 }
 
+// fold_pool5a != 0: the backward of Mixed_5a/Branch_2's max-pool is NOT applied here; dx0 then lacks that term and the
+// ROI backward adds it on the fly from the pool's arg-max codes and its output gradient (both stay in `ws`).
 int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const HeadPlan& pl, char* ws,
                              const float* keep_mask, float keep_prob, const float* dfeat, float* dparams, void* dx0,
-                             cudaStream_t st) {
+                             int fold_pool5a, cudaStream_t st) {
   bf16* act[NBUF];
   bf16* grad[NBUF];
   act[X0] = reinterpret_cast<bf16*>(const_cast<void*>(x0));
@@ -274,7 +277,7 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       count_launch();
       written[X2] = true;
     }
-    if (i == 5 && dx0 != nullptr) {
+    if (i == 5 && dx0 != nullptr && !fold_pool5a) {
       pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(
           act[X0], 576, grad[X1] + 448, 1024, grad[X0], 576, n, 576);
       count_launch();

@@ -460,11 +460,16 @@ roi_crop_maxpool_bwd_kernel(const float* __restrict__ fmap, int Hf, int Wf, int 
 constexpr int kBinsMax = 49;            // crop 14 -> 7x7 pooled bins; larger crops use the un-merged loop
 struct BinPixel { int off; float wy[4]; float wx[4]; };
 
-template <typename GradT>
+// FOLD: dout lacks the backward of the head's first max-pool (Mixed_5a/Branch_2, 3x3 / stride 2 / SAME on the 7x7
+// ROI tensor); it is applied here: position (y, x) lies in 1, 2 or 4 windows -- an even coordinate is the centre tap
+// of window y/2, an odd one the last tap of (y-1)/2 and the first tap of (y+1)/2 -- and receives a window's output
+// gradient where that window's arg-max code names it.
+template <typename GradT, bool FOLD>
 __global__ void __launch_bounds__(288)
 roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restrict__ boxes, int P, int crop,
                                   const unsigned char* __restrict__ codes, const GradT* __restrict__ dout,
-                                  float* __restrict__ dfmap) {
+                                  float* __restrict__ dfmap, const unsigned char* __restrict__ pool_codes,
+                                  const GradT* __restrict__ pool_grad, int pool_ld) {
   __shared__ RoiCoords sc;
   __shared__ BinPixel tab[kBinsMax][16];
   __shared__ int tab_n[kBinsMax];
@@ -508,6 +513,27 @@ roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restri
     int q = w % C4, pos = w / C4;
     int py = pos / hp, px = pos - py * hp;
     float4 g = ld4(go + (size_t)pos * Cf + 4 * q);
+    if (FOLD) {
+      const int ny = (py & 1) ? 2 : 1, nx = (px & 1) ? 2 : 1;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (a >= ny) break;
+        const int oy = (py & 1) ? ((py - 1) >> 1) + a : (py >> 1), ty = (py & 1) ? (a == 0 ? 2 : 0) : 1;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c >= nx) break;
+          const int ox = (px & 1) ? ((px - 1) >> 1) + c : (px >> 1), tx = (px & 1) ? (c == 0 ? 2 : 0) : 1;
+          const size_t o = (size_t)roi * 16 + oy * 4 + ox;
+          const unsigned pc = *reinterpret_cast<const unsigned*>(pool_codes + o * Cf + 4 * q);
+          const float4 dp = ld4(pool_grad + o * pool_ld + 4 * q);
+          const unsigned tap = (unsigned)(ty * 3 + tx);
+          g.x += (pc & 0xffu) == tap ? dp.x : 0.f;
+          g.y += ((pc >> 8) & 0xffu) == tap ? dp.y : 0.f;
+          g.z += ((pc >> 16) & 0xffu) == tap ? dp.z : 0.f;
+          g.w += (pc >> 24) == tap ? dp.w : 0.f;
+        }
+      }
+    }
     if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
     const int code = cd[w];
     const int kx = code & 3, ky = (code >> 2) & 3, kz = (code >> 4) & 3, kw = (code >> 6) & 3;
@@ -784,11 +810,32 @@ int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* b
       roi_crop_maxpool_bwd_rows_kernel<7, __nv_bfloat16><<<B * P, threads, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, codes,
                                                                                    (const __nv_bfloat16*)dout, dfmap);
   } else if (dout_dtype == C2D_F32)
-    roi_crop_maxpool_bwd_codes_kernel<float><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes,
-                                                                   (const float*)dout, dfmap);
+    roi_crop_maxpool_bwd_codes_kernel<float, false><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes,
+                                                                          (const float*)dout, dfmap, nullptr, nullptr, 0);
   else
-    roi_crop_maxpool_bwd_codes_kernel<__nv_bfloat16><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
-                                                                           codes, (const __nv_bfloat16*)dout, dfmap);
+    roi_crop_maxpool_bwd_codes_kernel<__nv_bfloat16, false><<<B * P, 288, 0, st>>>(
+        Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes, (const __nv_bfloat16*)dout, dfmap, nullptr, nullptr, 0);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size,
+                                        int pool_k, int pool_s, const unsigned char* codes, const void* dout_partial,
+                                        const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,
+                                        float* dfmap, c2d_stream_t stream) {
+  int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
+  if (rc != C2D_OK) return rc;
+  C2D_CHECK_ARG(crop_size == 14, "roi_bwd_fold: the folded max-pool backward is built for a 7x7 ROI tensor (crop 14)");
+  C2D_CHECK_ARG(codes != nullptr && pool_codes != nullptr && pool_grad != nullptr && pool_grad_ld >= Cf,
+                "roi_bwd_fold: null / short operand");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return C2D_OK;
+  C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
+  if (P == 0) return C2D_OK;
+  roi_crop_maxpool_bwd_codes_kernel<__nv_bfloat16, true><<<B * P, 288, 0, st>>>(
+      Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes, (const __nv_bfloat16*)dout_partial, dfmap, pool_codes,
+      (const __nv_bfloat16*)pool_grad, pool_grad_ld);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -40,13 +40,31 @@ def _f32(t):
 # ---------------------------------------------------------------------------------------------
 # K1: crop_and_resize + max_pool  (models/utils.py:147-160)
 # ---------------------------------------------------------------------------------------------
+class PoolFold(object):
+  """Links one roi_crop_maxpool call with the head_mixed5 call that consumes its output (bf16 path, training): the
+  head's backward then leaves the backward of its first max-pool (Mixed_5a/Branch_2) out of dx0 and hands the
+  pool's arg-max codes and output gradient to the ROI backward, which applies that term while it scatters
+  (c2d_head_mixed5_bwd_fold / c2d_roi_crop_maxpool_bwd_codes_fold).  Pass the SAME object to both calls."""
+
+  def __init__(self):
+    self.ws = None            # keeps the head workspace alive until the ROI backward has run
+    self.pool_codes = None
+    self.pool_grad = None
+    self.pool_grad_ld = 0
+
+  @property
+  def ready(self):
+    return self.ws is not None
+
+
 class _RoiCropMaxPool(torch.autograd.Function):
   """When the feature map needs a gradient the forward also writes the max-pool arg-max codes (1 byte per
   bin and channel quad) and the backward scatters from them, instead of re-sampling the feature map."""
 
   @staticmethod
-  def forward(ctx, fmap, proposals, crop_size, pool_k, pool_s, out_dtype):
+  def forward(ctx, fmap, proposals, crop_size, pool_k, pool_s, out_dtype, fold):
     require_cuda(fmap, proposals)
+    ctx.fold = fold
     _f32(fmap); _f32(proposals)
     B, Hf, Wf, Cf = fmap.shape
     P = proposals.shape[1]
@@ -71,14 +89,20 @@ class _RoiCropMaxPool(torch.autograd.Function):
     P = proposals.shape[1]
     dout = dout.contiguous()
     dfmap = torch.empty((B, Hf, Wf, Cf), dtype=torch.float32, device=dout.device)
-    call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
-         ptr(dout), capi.dtype_code(dout.dtype), ptr(dfmap), stream())
-    return dfmap, None, None, None, None, None
+    fold = ctx.fold
+    if fold is not None and fold.ready:
+      call('c2d_roi_crop_maxpool_bwd_codes_fold', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
+           ptr(dout), fold.pool_codes, fold.pool_grad, fold.pool_grad_ld, ptr(dfmap), stream())
+      fold.ws = None
+    else:
+      call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
+           ptr(dout), capi.dtype_code(dout.dtype), ptr(dfmap), stream())
+    return dfmap, None, None, None, None, None, None
 
 
-def roi_crop_maxpool(fmap, proposals, crop_size=14, pool_k=2, pool_s=2, out_dtype=torch.float32):
-  """fmap [B,Hf,Wf,C] fp32, proposals [B,P,4] normalised -> [B*P, crop/2, crop/2, C]."""
-  return _RoiCropMaxPool.apply(fmap.contiguous(), proposals.contiguous(), crop_size, pool_k, pool_s, out_dtype)
+def roi_crop_maxpool(fmap, proposals, crop_size=14, pool_k=2, pool_s=2, out_dtype=torch.float32, fold=None):
+  """fmap [B,Hf,Wf,C] fp32, proposals [B,P,4] normalised -> [B*P, crop/2, crop/2, C].  `fold`: see PoolFold."""
+  return _RoiCropMaxPool.apply(fmap.contiguous(), proposals.contiguous(), crop_size, pool_k, pool_s, out_dtype, fold)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -109,8 +133,9 @@ def head_param_floats():
 class _HeadMixed5(torch.autograd.Function):
 
   @staticmethod
-  def forward(ctx, x0, params, keep_mask, keep_prob, need_dx0):
+  def forward(ctx, x0, params, keep_mask, keep_prob, need_dx0, fold):
     require_cuda(x0, params, keep_mask)
+    ctx.fold = fold
     _f32(params)
     n = x0.shape[0]
     if tuple(x0.shape[1:]) != (HEAD_IN_HW, HEAD_IN_HW, HEAD_IN_CH):
@@ -135,14 +160,23 @@ class _HeadMixed5(torch.autograd.Function):
     dfeat = dfeat.contiguous()
     dparams = torch.empty_like(params)
     dx0 = torch.empty_like(x0) if (ctx.need_dx0 and ctx.needs_input_grad[0]) else None
-    call('c2d_head_mixed5_bwd', ptr(x0), n, dt, ptr(params), ptr(ws), ws.numel(), ptr(keep_mask), ctx.keep_prob,
-         ptr(dfeat), ptr(dparams), ptr(dx0), stream())
-    return dx0, dparams, None, None, None
+    fold = ctx.fold
+    if fold is not None and dx0 is not None and x0.dtype == torch.bfloat16:
+      import ctypes
+      codes, grad, ld = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int()
+      call('c2d_head_mixed5_bwd_fold', ptr(x0), n, dt, ptr(params), ptr(ws), ws.numel(), ptr(keep_mask), ctx.keep_prob,
+           ptr(dfeat), ptr(dparams), ptr(dx0), ctypes.byref(codes), ctypes.byref(grad), ctypes.byref(ld), stream())
+      fold.ws, fold.pool_codes, fold.pool_grad, fold.pool_grad_ld = ws, codes, grad, ld.value
+    else:
+      call('c2d_head_mixed5_bwd', ptr(x0), n, dt, ptr(params), ptr(ws), ws.numel(), ptr(keep_mask), ctx.keep_prob,
+           ptr(dfeat), ptr(dparams), ptr(dx0), stream())
+    return dx0, dparams, None, None, None, None
 
 
-def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True):
-  """x0 [N,7,7,576] (fp32 or bf16), packed params fp32 -> proposal features [N,1024] fp32."""
-  return _HeadMixed5.apply(x0.contiguous(), params, keep_mask, keep_prob, need_dx0)
+def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True, fold=None):
+  """x0 [N,7,7,576] (fp32 or bf16), packed params fp32 -> proposal features [N,1024] fp32.  `fold`: see PoolFold
+  (only when x0 is exactly the tensor roi_crop_maxpool returned for the same PoolFold object)."""
+  return _HeadMixed5.apply(x0.contiguous(), params, keep_mask, keep_prob, need_dx0, fold)
 
 
 # ---------------------------------------------------------------------------------------------

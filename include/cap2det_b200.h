@@ -118,6 +118,13 @@ int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int
 int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size,
                                    int pool_k, int pool_s, const unsigned char* codes, const void* dout,
                                    int dout_dtype, float* dfmap, c2d_stream_t stream);
+/* As above with dout = the partial dX0 of c2d_head_mixed5_bwd_fold (bf16, crop_size 14, Cf 576): the gradient of
+ * every 7x7 position additionally receives pool_grad[roi, window, c] of the (up to four) 3x3 / stride-2 windows
+ * whose arg-max code names that position. */
+int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size,
+                                        int pool_k, int pool_s, const unsigned char* codes, const void* dout_partial,
+                                        const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,
+                                        float* dfmap, c2d_stream_t stream);
 
 /* ---- K2/K3: box-classifier head, models/utils.py:165-177 ---------------------------
  * extract_box_classifier_features (Inception-v2 Mixed_5a..5c, OD-API) -> reduce_mean over
@@ -139,6 +146,16 @@ int c2d_head_mixed5_fwd(const void* x0, int n_rois, int dtype, const float* para
 int c2d_head_mixed5_bwd(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
                         size_t workspace_bytes, const float* keep_mask, float keep_prob,
                         const float* dfeat, float* dparams, void* dx0, c2d_stream_t stream);
+/* bf16 only.  As c2d_head_mixed5_bwd, but the backward of Mixed_5a/Branch_2's 3x3 / stride-2 max-pool (X0 ->
+ * X1[:, 448:1024)) is left out of dx0_partial: *pool_codes ([n,16,576] u8, tap dy*3+dx of the first maximum of every
+ * window), *pool_grad (bf16 gradient of the pool's output, leading dimension *pool_grad_ld) point into the
+ * workspace, and c2d_roi_crop_maxpool_bwd_codes_fold applies that term while it scatters -- one 226 MB
+ * read-modify-write pass over dX0 and one kernel less.  The workspace must stay alive until that call. */
+int c2d_head_mixed5_bwd_fold(const void* x0, int n_rois, int dtype, const float* params, void* workspace,
+                             size_t workspace_bytes, const float* keep_mask, float keep_prob,
+                             const float* dfeat, float* dparams, void* dx0_partial,
+                             const unsigned char** pool_codes, const void** pool_grad, int* pool_grad_ld,
+                             c2d_stream_t stream);
 
 /* ---- first-stage feature extractor, models/utils.py:127-136 ------------------------------
  * feature_extractor.preprocess ((2/255) x - 1) + extract_proposal_features(scope

@@ -352,3 +352,42 @@ def test_graphed_train_step_matches_eager_steps():
       assert float((a - b).norm() / a.norm()) < 3e-3
   finally:
     torch.cuda.set_stream(torch.cuda.default_stream())
+
+
+def test_pool_backward_folded_into_roi_backward_matches_separate_kernel():
+  """ops.PoolFold: the backward of Mixed_5a/Branch_2's max-pool applied inside the ROI scatter == the head's own
+  max-pool backward kernel + read-modify-write of dX0 (same terms; the folded form adds the pool term in fp32 instead
+  of rounding the sum to bf16 once more)."""
+  import tempfile
+  from cap2det_b200 import builder, config, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  rng = np.random.default_rng(91)
+  B, P = 2, 96
+  fmap = synthetic.make_feature_map(rng, B, 160, 208)
+  props = synthetic.make_proposals(rng, B, P, 160, 208)
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  grads, losses = [], []
+  for fold in (True, False):
+    model = builder.build(m, is_training=True, head_dtype=torch.bfloat16)
+    model.fold_pool_backward = fold
+    with torch.no_grad():
+      model.fc_weights.mul_(8.0)
+    fm = torch.from_numpy(fmap).cuda().requires_grad_(True)
+    ex = {F.features_to_crop: fm, F.num_proposals: torch.full((B,), P, dtype=torch.int32, device='cuda'),
+          F.proposals: torch.from_numpy(props).cuda(), F.object_texts: texts, F.dropout_keep_mask: torch.from_numpy(keep).cuda()}
+    loss = model.build_loss(model.build_prediction(ex), ex)
+    sum(loss.values()).backward()
+    model.raise_if_assert_failed()
+    grads.append((fm.grad.cpu().numpy(), model.head_params.grad.cpu().numpy()))
+    losses.append(float(sum(loss.values())))
+  assert losses[0] == losses[1]
+  assert np.abs(grads[0][0]).max() > 0
+  assert l2_err(grads[0][0], grads[1][0]) < 5e-3, l2_err(grads[0][0], grads[1][0])
+  assert l2_err(grads[0][1], grads[1][1]) < 1e-5      # the head's own gradients do not depend on the fold (fp32 atomics order only)
