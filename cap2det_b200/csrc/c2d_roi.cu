@@ -557,152 +557,13 @@ roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1', round 2: backward from the arg-max codes with the gradient PRE-REDUCED PER PROPOSAL AND PIXEL.
-//
-// Measured (profiles/r2/microbench_l2.txt): the L2 adds fp32 at ~6 TB/s of addends whatever issues them (lane
-// red.global.add.v4.f32: 6.0-6.3 TB/s, TMA cp.reduce.async.bulk: 5.7 TB/s), and the round-1 kernel, 7.1 vector
-// atomics per (pooling window, channel quad) = 3.2 GB of addends per step, ran at exactly that limit.  So the only
-// lever is FEWER ADDENDS: a proposal touches rows x cols distinct pixels (167 on average on the benchmark boxes,
-// against 348 atomics per channel quad before), and one addend per distinct pixel is the minimum a per-proposal
-// scatter can send.
-//
-// One thread owns one channel quad of one proposal and walks the proposal's distinct feature rows in ascending
-// order.  For a row it first gathers dH[cx] = sum over the sample rows cy whose top / bottom row this is of
-// wy(cy) * G(cy, cx), G = the pooled gradient where the arg-max code selects sample (cy, cx), else 0 -- 14 float4
-// accumulators with compile-time indices -- and then walks the 14 sample columns, whose left corner columns are
-// non-decreasing, with two rolling accumulators (pixel `cur` and `cur + 1`): an accumulator is sent with ONE
-// red.global.add.v4.f32 when the walk leaves its pixel.  All control flow depends on the proposal only
-// (warp-uniform).  (row, sample row, weight) events are sorted once per CTA in shared memory.
-// The weights are applied as wx * (wy * g) like CropAndResizeGradImage, but sums over samples are formed before
-// the atomic, so results differ from the round-1 kernel by fp32 summation order only (the atomics never had one).
+// K1' note (round 2).  Measured (profiles/r2/microbench_l2.txt): the L2 adds fp32 at ~6 TB/s of addends whatever
+// issues them (lane red.global.add.v4.f32: 6.0-6.3 TB/s, TMA cp.reduce.async.bulk: 5.7 TB/s), and
+// roi_crop_maxpool_bwd_codes_kernel -- 7.1 vector atomics per (pooling window, channel quad) = 3.2 GB of addends per
+// step -- runs at that limit.  A variant that pre-reduced the gradient per proposal and distinct pixel (one addend
+// per pixel, 1.48 GB) was built, verified and measured at 0.90 ms against 0.61 ms (406 M warp instructions, 144
+// registers): removed again, see profiles/r2_roi_kernels.md section 3 and commit 10c67a5 for the code.
 // ---------------------------------------------------------------------------------------------
-struct RoiBwdPlan {
-  RoiCoords sc;
-  int n_ev;
-  int ev_row[2 * kMaxCrop];      // feature row
-  int ev_cy[2 * kMaxCrop];       // sample row
-  float ev_w[2 * kMaxCrop];      // 1 - yl (top row) or yl (bottom row)
-  int key[2 * kMaxCrop];
-};
-
-__device__ __forceinline__ void roi_setup_events(RoiBwdPlan& pl, float4 box, int Hf, int Wf, int crop) {
-  roi_setup_coords(pl.sc, box, Hf, Wf, crop);
-  __syncthreads();
-  const int e = threadIdx.x;
-  int key = 0x7fffffff;
-  if (e < 2 * crop) {
-    const int cy = e >> 1;
-    const float yl = pl.sc.lerp[0][cy];
-    const bool live = pl.sc.valid[0][cy] && ((e & 1) == 0 || yl != 0.f);   // a zero weight adds nothing
-    if (live) key = ((e & 1) ? pl.sc.hi[0][cy] : pl.sc.lo[0][cy]) * 64 + e;
-    pl.key[e] = key;
-  }
-  __syncthreads();
-  if (e < 2 * crop && key != 0x7fffffff) {
-    int rank = 0;
-    for (int f = 0; f < 2 * crop; ++f) rank += pl.key[f] < key ? 1 : 0;
-    const int cy = e >> 1;
-    const float yl = pl.sc.lerp[0][cy];
-    pl.ev_row[rank] = key >> 6; pl.ev_cy[rank] = cy; pl.ev_w[rank] = (e & 1) ? yl : 1.0f - yl;
-  }
-  if (e == 0) {
-    int n = 0;
-    for (int f = 0; f < 2 * crop; ++f) n += pl.key[f] != 0x7fffffff ? 1 : 0;
-    pl.n_ev = n;
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void red_add4(float* p, float4 v) {
-  if (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f) atomicAdd(reinterpret_cast<float4*>(p), v);
-}
-
-template <int HP, typename GradT>
-__global__ void __launch_bounds__(160)
-roi_crop_maxpool_bwd_rows_kernel(int Hf, int Wf, int Cf, const float4* __restrict__ boxes, int P,
-                                 const unsigned char* __restrict__ codes, const GradT* __restrict__ dout,
-                                 float* __restrict__ dfmap) {
-  constexpr int CROP = 2 * HP;
-  __shared__ RoiBwdPlan pl;
-  const int roi = blockIdx.x;
-  const int b = roi / P;
-  roi_setup_events(pl, boxes[roi], Hf, Wf, CROP);
-  const int C4 = Cf >> 2;
-  const int n_ev = pl.n_ev;
-  if (n_ev == 0) return;
-  const GradT* go = dout + (size_t)roi * HP * HP * Cf;
-  const unsigned char* cd = codes + (size_t)roi * HP * HP * C4;
-  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = threadIdx.x; q < C4; q += blockDim.x) {
-    float* dimg = dfmap + (size_t)b * Hf * Wf * Cf + 4 * q;
-    float4 dH[CROP];
-#pragma unroll
-    for (int i = 0; i < CROP; ++i) dH[i] = zero;
-    int cur_row = pl.ev_row[0];
-    for (int e = 0; e <= n_ev; ++e) {
-      const int row = e < n_ev ? pl.ev_row[e] : -1;
-      if (row != cur_row) {
-        // ---- send row cur_row: walk the sample columns with two rolling pixel accumulators ----
-        float* drow = dimg + (size_t)cur_row * Wf * Cf;
-        float4 accL = zero, accR = zero;
-        int cur = -2;
-        bool usedR = false;
-#pragma unroll
-        for (int cx = 0; cx < CROP; ++cx) {
-          if (pl.sc.valid[1][cx]) {                                   // warp-uniform
-            const int l = pl.sc.lo[1][cx];
-            const float xl = pl.sc.lerp[1][cx];
-            if (l != cur) {
-              if (cur >= 0) {
-                red_add4(drow + (size_t)cur * Cf, accL);
-                if (l == cur + 1) accL = accR;
-                else { if (usedR) red_add4(drow + (size_t)(cur + 1) * Cf, accR); accL = zero; }
-              }
-              accR = zero; usedR = false; cur = l;
-            }
-            const float wl = 1.0f - xl;
-            const float4 h = dH[cx];
-            accL.x += wl * h.x; accL.y += wl * h.y; accL.z += wl * h.z; accL.w += wl * h.w;
-            if (xl != 0.f) {
-              accR.x += xl * h.x; accR.y += xl * h.y; accR.z += xl * h.z; accR.w += xl * h.w;
-              usedR = true;
-            }
-          }
-          dH[cx] = zero;
-        }
-        if (cur >= 0) {
-          red_add4(drow + (size_t)cur * Cf, accL);
-          if (usedR) red_add4(drow + (size_t)(cur + 1) * Cf, accR);
-        }
-        cur_row = row;
-      }
-      if (e == n_ev) break;
-      // ---- gather sample row cy into dH with weight w ----
-      const int cy = pl.ev_cy[e];
-      const float w = pl.ev_w[e];
-      const int py = cy >> 1;
-      const unsigned rsel = (unsigned)(cy & 1) << 1;                 // codes 2r, 2r+1 belong to this sample row
-      const GradT* gp = go + (size_t)py * HP * Cf + 4 * q;
-      const unsigned char* cp = cd + (size_t)py * HP * C4 + q;
-      float4 g[HP];
-      unsigned code[HP];
-#pragma unroll
-      for (int px = 0; px < HP; ++px) { g[px] = ld4(gp + (size_t)px * Cf); code[px] = cp[px * C4]; }
-#pragma unroll
-      for (int px = 0; px < HP; ++px) {
-        const unsigned k = code[px] ^ (rsel * 0x55u);                // per channel: 0 / 1 now mean "left / right sample of this row"
-        const float gx = w * g[px].x, gy = w * g[px].y, gz = w * g[px].z, gw = w * g[px].w;
-        float4& d0 = dH[2 * px];
-        float4& d1 = dH[2 * px + 1];
-        d0.x += (k & 0x03u) == 0u ? gx : 0.f;  d1.x += (k & 0x03u) == 1u ? gx : 0.f;
-        d0.y += (k & 0x0cu) == 0u ? gy : 0.f;  d1.y += (k & 0x0cu) == 0x04u ? gy : 0.f;
-        d0.z += (k & 0x30u) == 0u ? gz : 0.f;  d1.z += (k & 0x30u) == 0x10u ? gz : 0.f;
-        d0.w += (k & 0xc0u) == 0u ? gw : 0.f;  d1.w += (k & 0xc0u) == 0x40u ? gw : 0.f;
-      }
-    }
-  }
-}
-
 static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k, int pool_s) {
   C2D_CHECK_ARG(B >= 0 && P >= 0 && Hf >= 1 && Wf >= 1, "roi: bad shape B=%d P=%d Hf=%d Wf=%d", B, P, Hf, Wf);
   C2D_CHECK_ARG(Cf >= 4 && Cf % 4 == 0, "roi: feature depth %d must be a multiple of 4", Cf);
@@ -739,8 +600,7 @@ int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int
   C2D_CHECK_ARG(out_dtype == C2D_F32 || out_dtype == C2D_BF16, "roi: bad dtype %d", out_dtype);
   if (B * P == 0) return C2D_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static const char* impl = getenv("C2D_ROI_FWD");            // TEMPORARY A/B switch: "old" = round-1 kernel
-  if ((impl != nullptr && strcmp(impl, "old") == 0) || crop_size > 28) {
+  if (crop_size > 28) {                           // the row-rolling kernel keeps crop / 2 <= 14 pooled columns per CTA
     if (out_dtype == C2D_F32)
       roi_crop_maxpool_fwd_kernel<float><<<B * P, 288, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P, crop_size,
                                                                (float*)out, codes);
@@ -752,7 +612,7 @@ int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int
     const int hp = crop_size / 2, C4 = Cf / 4;
     int W = (C4 + 95) / 96;                       // <= 3 quads per lane; 2 warps per column at 576 channels
     while (W > 1 && hp * W * 32 > 448) --W;
-    const int threads = hp * W * 32;
+    const int threads = hp * W * 32 < 64 ? 64 : hp * W * 32;   // the plan set-up uses warps 0 (y) and 1 (x)
 #define C2D_ROI_FWD_LAUNCH(CODES, T)                                                                                  \
     roi_crop_maxpool_fwd_rows_kernel<CODES, T><<<B * P, threads, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,   \
                                                                           crop_size, (T*)out, codes)
@@ -797,19 +657,7 @@ int c2d_roi_crop_maxpool_bwd_codes(int B, int Hf, int Wf, int Cf, const float* b
   C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
   if (P == 0) return C2D_OK;
   C2D_CHECK_ARG(codes != nullptr, "roi_bwd_codes: null codes");
-  static const char* impl = getenv("C2D_ROI_BWD");            // TEMPORARY A/B switch: "old" = round-1 kernel
-  const bool rows = crop_size == 14 && impl != nullptr && strcmp(impl, "rows") == 0;   // opt-in: measured slower (0.90 vs 0.61 ms)
-  if (rows) {
-    const int C4 = Cf / 4;
-    int threads = ((C4 + 31) / 32) * 32;
-    threads = threads < 64 ? 64 : (threads > 160 ? 160 : threads);
-    if (dout_dtype == C2D_F32)
-      roi_crop_maxpool_bwd_rows_kernel<7, float><<<B * P, threads, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, codes,
-                                                                           (const float*)dout, dfmap);
-    else
-      roi_crop_maxpool_bwd_rows_kernel<7, __nv_bfloat16><<<B * P, threads, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, codes,
-                                                                                   (const __nv_bfloat16*)dout, dfmap);
-  } else if (dout_dtype == C2D_F32)
+  if (dout_dtype == C2D_F32)
     roi_crop_maxpool_bwd_codes_kernel<float, false><<<B * P, 288, 0, st>>>(Hf, Wf, Cf, (const float4*)boxes, P, crop_size, codes,
                                                                           (const float*)dout, dfmap, nullptr, nullptr, 0);
   else

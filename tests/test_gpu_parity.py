@@ -150,6 +150,20 @@ def test_roi_crop_maxpool_backward():
     assert int(codes.max()) <= 255 and codes.numel() == B * P * 49 * C // 4
 
 
+@pytest.mark.parametrize('crop', [2, 6, 10, 28, 32])
+def test_roi_other_crop_sizes(crop):
+  """initial_crop_size other than 14: <= 28 runs the row-rolling kernel, 30 / 32 the per-window kernel."""
+  from cap2det_b200 import ops
+  fmap, props = _roi_inputs(40 + crop, C=40)
+  want = oroi.roi_crop_maxpool_fwd(fmap, props, crop=crop)
+  f = dev(fmap).requires_grad_(True)
+  out = ops.roi_crop_maxpool(f, dev(props), crop_size=crop)
+  np.testing.assert_array_equal(out.detach().cpu().numpy(), want)
+  g = np.random.default_rng(crop).standard_normal(want.shape).astype(np.float32)
+  out.backward(dev(g))
+  assert rel_err(f.grad.cpu().numpy(), oroi.roi_crop_maxpool_bwd(fmap, props, g, crop=crop)) < RTOL_F32
+
+
 def test_roi_rejects_unsupported_options():
   from cap2det_b200 import ops, capi
   fmap, props = _roi_inputs(5)
