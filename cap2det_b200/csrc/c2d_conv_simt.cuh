@@ -499,6 +499,117 @@ pool3x3_s1_4x4_bwd_kernel(const T* __restrict__ x, int ldx, const T* __restrict_
     st4(dx + ((size_t)n * 16 + i) * lddx + c, make_float4(g[i][0], g[i][1], g[i][2], g[i][3]));
 }
 
+// Mixed_5c/Branch_3 MaxPool_0a_3x3 (4x4, stride 1, SAME) on the bf16 path, with the routing decided in the forward
+// pass.  `codes` [n,16,C]: per window (= position, stride 1) and channel one byte
+//   bits 0..3  tap index (dy+1)*3+(dx+1) of the FIRST maximum in row-major window order
+//   0x80       that maximum is not positive  (the input is a ReLU output: its ReLU backward zeroes the gradient)
+//   0x40       the value AT this position is not positive (ReLU mask of the position itself)
+// so the backward needs neither the input plane nor an arg-max search (the search made the generic kernel issue
+// bound: ~3000 instructions per thread, 126 us per step).  It is the LAST writer of dx: the merged data-gradient GEMM
+// of the block's 1x1 convolutions has stored its un-masked result there (store-only epilogue), this kernel adds the
+// routed pool gradient and applies the ReLU mask to the sum.
+// Forward arithmetic stays packed (bf16 max and equality are exact): HMNMX2 + HSET2 + LOP3 per tap and channel pair.
+__device__ __forceinline__ unsigned bf2_max(unsigned a, unsigned b) {
+  const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const unsigned*>(&r);
+}
+__device__ __forceinline__ unsigned bf2_eq_mask(unsigned a, unsigned b) {
+  return __heq2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ unsigned bf2_gt0_mask(unsigned a) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&a), z);
+}
+
+// C = row stride of x, y, dy, dx and codes in elements (compile-time: every access is base + immediate offset).
+template <int C>
+static __global__ void __launch_bounds__(128)
+maxpool3x3_s1_4x4_codes_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n_rois,
+                                   unsigned char* __restrict__ codes) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  x += (size_t)n * 16 * C + c; y += (size_t)n * 16 * C + c; codes += (size_t)n * 16 * C + c;
+  uint2 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = *reinterpret_cast<const uint2*>(x + i * C);
+#pragma unroll
+  for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+    for (int ox = 0; ox < 4; ++ox) {
+      uint2 best = v[oy * 4 + ox];
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int iy = oy + dy, ix = ox + dx;
+          if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) { best.x = bf2_max(best.x, v[iy * 4 + ix].x); best.y = bf2_max(best.y, v[iy * 4 + ix].y); }
+        }
+      uint2 tap = make_uint2(0u, 0u);                       // 16-bit lanes; walked backwards so that the first maximum wins
+#pragma unroll
+      for (int dy = 1; dy >= -1; --dy)
+#pragma unroll
+        for (int dx = 1; dx >= -1; --dx) {
+          const int iy = oy + dy, ix = ox + dx;
+          if (iy >= 0 && iy < 4 && ix >= 0 && ix < 4) {
+            const unsigned code = (unsigned)((dy + 1) * 3 + dx + 1) * 0x00010001u;
+            const unsigned ex = bf2_eq_mask(v[iy * 4 + ix].x, best.x), ey = bf2_eq_mask(v[iy * 4 + ix].y, best.y);
+            tap.x = (ex & code) | (~ex & tap.x);
+            tap.y = (ey & code) | (~ey & tap.y);
+          }
+        }
+      tap.x |= (~bf2_gt0_mask(best.x) & 0x00800080u) | (~bf2_gt0_mask(v[oy * 4 + ox].x) & 0x00400040u);
+      tap.y |= (~bf2_gt0_mask(best.y) & 0x00800080u) | (~bf2_gt0_mask(v[oy * 4 + ox].y) & 0x00400040u);
+      *reinterpret_cast<uint2*>(y + (oy * 4 + ox) * C) = best;
+      *reinterpret_cast<unsigned*>(codes + (oy * 4 + ox) * C) = __byte_perm(tap.x, tap.y, 0x6420);
+    }
+}
+
+template <int C>
+static __global__ void __launch_bounds__(128)
+maxpool3x3_s1_4x4_codes_bwd_kernel(const unsigned char* __restrict__ codes, const __nv_bfloat16* __restrict__ dy,
+                                   __nv_bfloat16* __restrict__ dx, int n_rois) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  codes += (size_t)n * 16 * C + c; dy += (size_t)n * 16 * C + c; dx += (size_t)n * 16 * C + c;
+  unsigned code[16];
+  float4 go[16];
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    code[w] = *reinterpret_cast<const unsigned*>(codes + w * C);
+    go[w] = ld4(dy + w * C);
+  }
+#pragma unroll
+  for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 4; ++ix) {
+      __nv_bfloat16* o = dx + (iy * 4 + ix) * C;
+      float4 g = ld4(o);
+#pragma unroll
+      for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+        for (int ox = 0; ox < 4; ++ox) {
+          if (oy - iy > 1 || iy - oy > 1 || ox - ix > 1 || ix - ox > 1) continue;       // compile-time
+          const unsigned tap = (unsigned)((iy - oy + 1) * 3 + (ix - ox + 1));
+          // channel k of window (oy, ox) routes here iff its code byte, the 0x40 flag aside, equals the tap (0x80 set =
+          // dead window, never equal): one LOP3 with a predicate result + one predicated FADD per channel
+          const unsigned cw = code[oy * 4 + ox];
+          const float4 gw = go[oy * 4 + ox];
+          if (((cw ^ tap) & 0x000000bfu) == 0u) g.x += gw.x;
+          if (((cw ^ (tap << 8)) & 0x0000bf00u) == 0u) g.y += gw.y;
+          if (((cw ^ (tap << 16)) & 0x00bf0000u) == 0u) g.z += gw.z;
+          if (((cw ^ (tap << 24)) & 0xbf000000u) == 0u) g.w += gw.w;
+        }
+      const unsigned dead = code[iy * 4 + ix];
+      if (dead & 0x00000040u) g.x = 0.f;
+      if (dead & 0x00004000u) g.y = 0.f;
+      if (dead & 0x00400000u) g.z = 0.f;
+      if (dead & 0x40000000u) g.w = 0.f;
+      st4(o, g);
+    }
+}
+
 // Mixed_5a/Branch_2 MaxPool_1a_3x3 (7x7 -> 4x4, stride 2, SAME) on bf16 planes with FOUR channels per thread.
 // max is exact in bf16, so the plane stays packed (49 x 8 bytes = 98 registers) and the windows use __hmax2.
 // `codes` (optional, [n,16,C] bytes): tap index dy*3+dx of the FIRST maximum of every window in row-major window

@@ -113,9 +113,12 @@ struct ProfScope {
 static unsigned long long g_attr_done = 0;
 static int tc_prepare() {
   if (first_call_on_this_device(&g_attr_done)) {
-    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
-    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
-    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kTcSmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
+    C2D_CUDA_OK(cudaFuncSetAttribute(tc::conv_gemm_tc2_multi_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::k2SmemBytes));
     C2D_CUDA_OK(cudaFuncSetAttribute(tc::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kWgSmemBytes));
   }
   return C2D_OK;
@@ -154,15 +157,16 @@ static int launch_conv(const CUtensorMap maps[4], const CUtensorMap& mapB, tc::C
   int tiles = p.num_m_tiles * p.num_n_tiles;
   if (tiles <= 0) return C2D_OK;
   ProfScope prof(st, 0, flops);
+  const bool generic = tc::epilogue_mode(p) == tc::kEpiGeneric;      // which epilogue instance set the launch needs
   if (two) {
     int pairs = num_sms() / 2;
     if (tiles < pairs) pairs = tiles;
-    C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc2_kernel, 2 * pairs, tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1],
-                           maps[2], maps[3], mapB, p));
+    C2D_CUDA_OK(launch_pdl(generic ? tc::conv_gemm_tc2_kernel<true> : tc::conv_gemm_tc2_kernel<false>, 2 * pairs,
+                           tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1], maps[2], maps[3], mapB, p));
   } else {
     int grid = tiles < num_sms() ? tiles : num_sms();
-    C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc_kernel, grid, tc::kTcThreads, tc::kTcSmemBytes, st, maps[0], maps[1], maps[2],
-                           maps[3], mapB, p));
+    C2D_CUDA_OK(launch_pdl(generic ? tc::conv_gemm_tc_kernel<true> : tc::conv_gemm_tc_kernel<false>, grid, tc::kTcThreads,
+                           tc::kTcSmemBytes, st, maps[0], maps[1], maps[2], maps[3], mapB, p));
   }
   count_launch();
   C2D_LAUNCH_OK();
@@ -386,8 +390,10 @@ int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16* wt
   }
   mp.pair_begin[4] = given;
   ProfScope prof(st, 0, flops);
-  C2D_CUDA_OK(launch_pdl(tc::conv_gemm_tc2_multi_kernel, 2 * given, tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1],
-                         maps[2], maps[3], mapB, mp));
+  bool generic = false;                                // the classes share every epilogue option
+  for (int cls = 0; cls < mp.count; ++cls) generic = generic || tc::epilogue_mode(mp.p[cls]) == tc::kEpiGeneric;
+  C2D_CUDA_OK(launch_pdl(generic ? tc::conv_gemm_tc2_multi_kernel<true> : tc::conv_gemm_tc2_multi_kernel<false>, 2 * given,
+                         tc::kTcThreads, tc::k2SmemBytes, st, maps[0], maps[1], maps[2], maps[3], mapB, mp));
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -37,7 +37,8 @@ constexpr int kTcThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps
 // and wgrad 1.28 -> 1.18 ms per step.  The two epilogue experiments prepared with it (BN-shift loads before the
 // TMEM read; rolling prefetch of the accumulate / mask operands) measured no change and were removed.
 constexpr int kWgThreads = 192;
-constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kEpiShiftBytes = 8 * 128 * 4;      // per epilogue warp: the BN shifts of its <= 128 tile columns
+constexpr int kTcSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiShiftBytes;
 constexpr int kTmemCols = 512;                   // 2 accumulator stages x 2 accumulators x 128 columns
 constexpr int kMaxTaps = 9;
 
@@ -129,6 +130,260 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue of one warp: its row of the tile, tile columns [j_lo, j_hi), 16 columns (one 32-byte sector of bf16)
+// at a time.  taddr = TMEM address of tile column 0 in this warp's lane quarter; ncol0 = first output column
+// of the tile; orow = output row of this thread (or -1).
+//
+// epilogue_generic: every option (fp32 / bf16 output, shift, ReLU, accumulate, mask), used for fp32 outputs and for
+// option combinations that have no specialised instance.
+// epilogue_bf16<RMW, MASK, ACT>: the bf16 instances the head runs (forward: ACT; data gradients: MASK and / or RMW).
+// The round-2 profile of the generic form (profiles/r2_tc_epilogue.md) showed the eight epilogue warps busy 95 % of
+// the time on output-heavy launches with 18 instructions per output element -- bf16 -> fp32 conversions and
+// compare / select pairs for an accumulate operand and a mask that most launches do not have, a TMEM load waited
+// for right after its issue, and the BN shift fetched from global memory chunk by chunk.  The instances do only
+// what their launch needs (~4 instructions per element), keep the next chunk's TMEM load in flight while the
+// current one is processed, read the shifts as shared-memory broadcasts staged once per tile, apply the ReLU mask
+// as a packed bf16 compare on the rounded result, and re-use a chunk's operand registers for the prefetch of the
+// chunk 64 columns ahead.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_generic(const ConvGemmParams& p, const uint32_t taddr, const int j_lo, const int j_hi,
+                                                 const int ncol0, const long long orow) {
+  const bool bf16_rmw = !p.out_f32 && p.accum;
+#pragma unroll 1
+  for (int j0 = j_lo; j0 < j_hi; j0 += 64) {
+    if (ncol0 + j0 >= p.n_total) break;               // warp-uniform
+    uint4 oldv[4][2], mskv[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int col0 = ncol0 + j0 + u * 16;
+      const bool live = orow >= 0 && j0 + u * 16 < j_hi && col0 < p.n_total;
+      oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);
+      mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+      if (live && bf16_rmw) {     // single output segment when accumulating
+        const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
+        ld_global_256(o, oldv[u][0], oldv[u][1]);
+      }
+      if (live && p.mask != nullptr && col0 < p.mask_cols) {
+        const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
+        ld_global_256(y, mskv[u][0], mskv[u][1]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 16;
+      const int col0 = ncol0 + j;
+      if (j >= j_hi || col0 >= p.n_total) break;            // warp-uniform
+      uint32_t v[16];
+      tmem_ld_32x16(taddr + j, v);
+      tmem_ld_wait();
+      if (orow >= 0) {
+        int sgm = 0;
+        if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
+        if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+        if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
+        const int scol = col0 - p.seg_begin[sgm];
+        const long long ooff = orow * p.seg_ld[sgm] + scol;
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        const bool act = col0 < p.act_cols;
+        if (p.shift != nullptr && act) {
+          const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 s4 = __ldg(sp + i);
+            f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
+          }
+        }
+        if (p.relu && act) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
+        if (p.out_f32) {
+          float* o = reinterpret_cast<float*>(p.seg_out[sgm]) + ooff;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (p.accum) {
+              uint4 a, c;
+              ld_global_256(o + 8 * i, a, c);
+              f[8 * i] += __uint_as_float(a.x); f[8 * i + 1] += __uint_as_float(a.y);
+              f[8 * i + 2] += __uint_as_float(a.z); f[8 * i + 3] += __uint_as_float(a.w);
+              f[8 * i + 4] += __uint_as_float(c.x); f[8 * i + 5] += __uint_as_float(c.y);
+              f[8 * i + 6] += __uint_as_float(c.z); f[8 * i + 7] += __uint_as_float(c.w);
+            }
+            st_global_256(o + 8 * i,
+                          make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
+                                     __float_as_uint(f[8 * i + 3])),
+                          make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
+                                     __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
+          const uint32_t old[8] = {oldv[u][0].x, oldv[u][0].y, oldv[u][0].z, oldv[u][0].w,
+                                   oldv[u][1].x, oldv[u][1].y, oldv[u][1].z, oldv[u][1].w};
+          const uint32_t yy[8] = {mskv[u][0].x, mskv[u][0].y, mskv[u][0].z, mskv[u][0].w,
+                                  mskv[u][1].x, mskv[u][1].y, mskv[u][1].z, mskv[u][1].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
+            float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]));
+            f[2 * i] += fo.x; f[2 * i + 1] += fo.y;                 // zeros unless accumulating
+            if (!(fy.x > 0.f)) f[2 * i] = 0.f;                      // ones unless masking
+            if (!(fy.y > 0.f)) f[2 * i + 1] = 0.f;
+          }
+          uint4 w0, w1;
+          w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
+          w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
+          w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
+          w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
+          st_global_256(o, w0, w1);
+        }
+      }
+    }
+  }
+}
+
+// tcgen05.wait::ld with the destination registers of the load as in/out operands: nothing that reads them can be
+// scheduled above the wait.
+__device__ __forceinline__ void tmem_ld_wait_on(uint32_t (&r)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
+struct EpiOperand { uint4 old0, old1, msk0, msk1; };
+
+template <bool RMW, bool MASK>
+__device__ __forceinline__ void epi_fetch(const ConvGemmParams& p, EpiOperand& e, const int j, const int j_hi, const int ncol0,
+                                          const long long orow) {
+  if (!RMW && !MASK) return;
+  const int col0 = ncol0 + j;
+  const bool live = orow >= 0 && j < j_hi;
+  if (RMW) {
+    e.old0 = e.old1 = make_uint4(0u, 0u, 0u, 0u);
+    if (live) ld_global_256(reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0, e.old0, e.old1);
+  }
+  if (MASK) {
+    e.msk0 = e.msk1 = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    if (live && col0 < p.mask_cols) ld_global_256(p.mask + orow * p.mask_ld + col0, e.msk0, e.msk1);
+  }
+}
+
+template <bool RMW, bool MASK, bool ACT>
+__device__ __forceinline__ void epi_chunk(const ConvGemmParams& p, const uint32_t (&v)[16], const EpiOperand& e, const int j,
+                                          const int ncol0, const long long orow, const float* ssh) {
+  if (orow < 0) return;
+  const int col0 = ncol0 + j;
+  int sgm = 0;
+  if (!RMW) {                                   // accumulation implies a single output segment
+    if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
+    if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
+    if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
+  }
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + (orow * p.seg_ld[sgm] + (col0 - p.seg_begin[sgm]));
+  float f[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+  if (ACT && col0 < p.act_cols) {
+    const float4* sp = reinterpret_cast<const float4*>(ssh + j);       // same address in every lane: a broadcast
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 s4 = sp[i];
+      f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+    }
+  }
+  if (RMW) {
+    const uint32_t old[8] = {e.old0.x, e.old0.y, e.old0.z, e.old0.w, e.old1.x, e.old1.y, e.old1.z, e.old1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[2 * i] += __uint_as_float(old[i] << 16);
+      f[2 * i + 1] += __uint_as_float(old[i] & 0xffff0000u);
+    }
+  }
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack_bf16(f[2 * i], f[2 * i + 1]);
+  if (MASK) {                                   // out = (y > 0) ? out : 0, on the rounded pair
+    const uint32_t yy[8] = {e.msk0.x, e.msk0.y, e.msk0.z, e.msk0.w, e.msk1.x, e.msk1.y, e.msk1.z, e.msk1.w};
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]), zero2);
+  }
+  st_global_256(o, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+}
+
+// ssh[j] = shift of tile column j (ACT only).
+template <bool RMW, bool MASK, bool ACT>
+__device__ __forceinline__ void epilogue_bf16(const ConvGemmParams& p, const uint32_t taddr, const int j_lo, int j_hi,
+                                              const int ncol0, const long long orow, const float* ssh) {
+  j_hi = min(j_hi, p.n_total - ncol0);            // n_total is a multiple of 16; warp-uniform
+  if (j_hi <= j_lo) return;
+  constexpr int D = (RMW && MASK) ? 2 : 4;         // operand prefetch distance in chunks (32 registers either way)
+  EpiOperand e[D];
+#pragma unroll
+  for (int u = 0; u < D; ++u) epi_fetch<RMW, MASK>(p, e[u], j_lo + 16 * u, j_hi, ncol0, orow);
+  uint32_t va[16], vb[16];
+  tmem_ld_32x16(taddr + j_lo, va);
+#pragma unroll 1
+  for (int j0 = j_lo; j0 < j_hi; j0 += 16 * D) {
+#pragma unroll
+    for (int u = 0; u < D; u += 2) {
+      const int j = j0 + 16 * u;
+      if (j >= j_hi) break;
+      tmem_ld_wait_on(va);
+      if (j + 16 < j_hi) tmem_ld_32x16(taddr + j + 16, vb);
+      epi_chunk<RMW, MASK, ACT>(p, va, e[u], j, ncol0, orow, ssh);
+      epi_fetch<RMW, MASK>(p, e[u], j + 16 * D, j_hi, ncol0, orow);
+      if (j + 16 >= j_hi) break;
+      tmem_ld_wait_on(vb);
+      if (j + 32 < j_hi) tmem_ld_32x16(taddr + j + 32, va);
+      epi_chunk<RMW, MASK, ACT>(p, vb, e[u + 1], j + 16, ncol0, orow, ssh);
+      epi_fetch<RMW, MASK>(p, e[u + 1], j + 16 + 16 * D, j_hi, ncol0, orow);
+    }
+  }
+}
+
+// Epilogue mode of a launch (warp-uniform, fixed per kernel).
+enum { kEpiGeneric = 0, kEpiAct, kEpiPlain, kEpiMask, kEpiRmw, kEpiRmwMask };
+__host__ __device__ __forceinline__ int epilogue_mode(const ConvGemmParams& p) {
+  if (p.out_f32) return kEpiGeneric;
+  const bool act = p.shift != nullptr || p.relu, rmw = p.accum != 0, msk = p.mask != nullptr;
+  if (act) return (rmw || msk || p.shift == nullptr) ? kEpiGeneric : kEpiAct;
+  return rmw ? (msk ? kEpiRmwMask : kEpiRmw) : (msk ? kEpiMask : kEpiPlain);
+}
+// Stage the shifts of tile columns [j_lo, j_lo + 128) into this warp's shared-memory slot (indexed by tile column).
+__device__ __forceinline__ void epilogue_stage_shift(const ConvGemmParams& p, float* ssh, const int j_lo, const int ncol0,
+                                                     const int lane) {
+  const int col = ncol0 + j_lo + 4 * lane;
+  float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (col < p.n_total) s4 = __ldg(reinterpret_cast<const float4*>(p.shift + col));
+  __syncwarp();
+  reinterpret_cast<float4*>(ssh + j_lo)[lane] = s4;
+  __syncwarp();
+}
+// GENERIC kernels carry only the generic epilogue, the others only the bf16 instances (together they exceed the
+// 168 registers a 320-thread CTA can have and spill); `conv_epilogue_is_generic` is the host-side selector.
+template <bool GENERIC>
+__device__ __forceinline__ void epilogue_run(const ConvGemmParams& p, const int mode, const uint32_t taddr, const int j_lo,
+                                             const int j_hi, const int ncol0, const long long orow, const float* ssh) {
+  if (GENERIC) { epilogue_generic(p, taddr, j_lo, j_hi, ncol0, orow); return; }
+  switch (mode) {
+    case kEpiAct: epilogue_bf16<false, false, true>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+    case kEpiPlain: epilogue_bf16<false, false, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+    case kEpiMask: epilogue_bf16<false, true, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+    case kEpiRmw: epilogue_bf16<true, false, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+    default: epilogue_bf16<true, true, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+  }
+}
+
+template <bool GENERIC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                     const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -228,109 +483,21 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
     // their latency overlaps the TMEM reads instead of serialising with them.
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int a = (warp - 2) >> 2;           // accumulator (rows a*128 ..) handled by this warp
+    const int mode = epilogue_mode(p);
+    float* ssh = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256) + (warp - 2) * 128;
+    int staged_nt = -1;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      if (mode == kEpiAct && nt != staged_nt) { epilogue_stage_shift(p, ssh, 0, nt * p.n_tile, lane); staged_nt = nt; }
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = a * 128 + q * 32 + lane;       // row inside the tile
       const long long orow = conv_out_row(p, mt, r);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256 + a * 128);
-      const bool bf16_rmw = !p.out_f32 && p.accum;
-#pragma unroll 1
-      for (int j0 = 0; j0 < p.n_tile; j0 += 64) {
-        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
-        uint4 oldv[4][2], mskv[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int col0 = nt * p.n_tile + j0 + u * 16;
-          const bool live = orow >= 0 && j0 + u * 16 < p.n_tile && col0 < p.n_total;
-          oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);
-          mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-          if (live && bf16_rmw) {     // single output segment when accumulating
-            const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
-            ld_global_256(o, oldv[u][0], oldv[u][1]);
-          }
-          if (live && p.mask != nullptr && col0 < p.mask_cols) {
-            const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
-            ld_global_256(y, mskv[u][0], mskv[u][1]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u * 16;
-          const int col0 = nt * p.n_tile + j;
-          if (j >= p.n_tile || col0 >= p.n_total) break;            // warp-uniform
-          uint32_t v[16];
-          tmem_ld_32x16(taddr + j, v);
-          tmem_ld_wait();
-          if (orow >= 0) {
-            int sgm = 0;
-            if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
-            if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
-            if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
-            const int scol = col0 - p.seg_begin[sgm];
-            const long long ooff = orow * p.seg_ld[sgm] + scol;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            const bool act = col0 < p.act_cols;
-            if (p.shift != nullptr && act) {
-              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 s4 = __ldg(sp + i);
-                f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
-              }
-            }
-            if (p.relu && act) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.seg_out[sgm]) + ooff;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (p.accum) {
-                  uint4 a, c;
-                  ld_global_256(o + 8 * i, a, c);
-                  f[8 * i] += __uint_as_float(a.x); f[8 * i + 1] += __uint_as_float(a.y);
-                  f[8 * i + 2] += __uint_as_float(a.z); f[8 * i + 3] += __uint_as_float(a.w);
-                  f[8 * i + 4] += __uint_as_float(c.x); f[8 * i + 5] += __uint_as_float(c.y);
-                  f[8 * i + 6] += __uint_as_float(c.z); f[8 * i + 7] += __uint_as_float(c.w);
-                }
-                st_global_256(o + 8 * i,
-                              make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
-                                         __float_as_uint(f[8 * i + 3])),
-                              make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
-                                         __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
-              }
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
-              const uint32_t old[8] = {oldv[u][0].x, oldv[u][0].y, oldv[u][0].z, oldv[u][0].w,
-                                       oldv[u][1].x, oldv[u][1].y, oldv[u][1].z, oldv[u][1].w};
-              const uint32_t yy[8] = {mskv[u][0].x, mskv[u][0].y, mskv[u][0].z, mskv[u][0].w,
-                                      mskv[u][1].x, mskv[u][1].y, mskv[u][1].z, mskv[u][1].w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
-                float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]));
-                f[2 * i] += fo.x; f[2 * i + 1] += fo.y;                 // zeros unless accumulating
-                if (!(fy.x > 0.f)) f[2 * i] = 0.f;                      // ones unless masking
-                if (!(fy.y > 0.f)) f[2 * i + 1] = 0.f;
-              }
-              uint4 w0, w1;
-              w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
-              w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
-              w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
-              w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
-              st_global_256(o, w0, w1);
-            }
-          }
-        }
-      }
+      epilogue_run<GENERIC>(p, mode, taddr, 0, p.n_tile, nt * p.n_tile, orow, ssh);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pipe->tmem_empty[as]);
@@ -357,7 +524,7 @@ constexpr int k2Stages = 6;
 constexpr int k2StageABytes = 16384;
 constexpr int k2StageBBytes = 16384;
 constexpr int k2StageBytes = k2StageABytes + k2StageBBytes;
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + kEpiShiftBytes;
 
 struct Tc2Pipe {
   uint64_t full[k2Stages];
@@ -369,6 +536,7 @@ struct Tc2Pipe {
 
 // Body shared by the single-problem kernel and the multi-problem kernel below: the CTA pair `pair` of
 // `num_pairs` pairs works through the tiles of problem `p`.
+template <bool GENERIC>
 __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, const CUtensorMap& mapA1,
                                                    const CUtensorMap& mapA2, const CUtensorMap& mapA3,
                                                    const CUtensorMap& mapB, const ConvGemmParams& p, const int pair,
@@ -469,109 +637,22 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
     const int q = warp & 3;
     const int g = (warp - 2) >> 2;
     const int col_lo = g * n_half, col_hi = col_lo + n_half;
+    const int mode = epilogue_mode(p);
+    // this warp's shift slot is indexed by the tile column minus col_lo
+    float* ssh = reinterpret_cast<float*>(smem + k2Stages * k2StageBytes + 256) + (warp - 2) * 128 - col_lo;
+    int staged_nt = -1;
     int it = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
+      if (mode == kEpiAct && nt != staged_nt) { epilogue_stage_shift(p, ssh, col_lo, nt * p.n_tile, lane); staged_nt = nt; }
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = q * 32 + lane;                  // row inside this CTA's half tile
       const long long orow = conv_out_row(p, 2 * mt + (int)rank, r);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
-      const bool bf16_rmw = !p.out_f32 && p.accum;
-#pragma unroll 1
-      for (int j0 = col_lo; j0 < col_hi; j0 += 64) {
-        if (nt * p.n_tile + j0 >= p.n_total) break;               // warp-uniform
-        uint4 oldv[4][2], mskv[4][2];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int col0 = nt * p.n_tile + j0 + u * 16;
-          const bool live = orow >= 0 && j0 + u * 16 < col_hi && col0 < p.n_total;
-          oldv[u][0] = oldv[u][1] = make_uint4(0u, 0u, 0u, 0u);
-          mskv[u][0] = mskv[u][1] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-          if (live && bf16_rmw) {
-            const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(p.seg_out[0]) + orow * p.seg_ld[0] + col0;
-            ld_global_256(o, oldv[u][0], oldv[u][1]);
-          }
-          if (live && p.mask != nullptr && col0 < p.mask_cols) {
-            const __nv_bfloat16* y = p.mask + orow * p.mask_ld + col0;
-            ld_global_256(y, mskv[u][0], mskv[u][1]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j0 + u * 16;
-          const int col0 = nt * p.n_tile + j;
-          if (j >= col_hi || col0 >= p.n_total) break;              // warp-uniform
-          uint32_t v[16];
-          tmem_ld_32x16(taddr + j, v);
-          tmem_ld_wait();
-          if (orow >= 0) {
-            int sgm = 0;
-            if (p.nseg > 1 && col0 >= p.seg_begin[1]) sgm = 1;
-            if (p.nseg > 2 && col0 >= p.seg_begin[2]) sgm = 2;
-            if (p.nseg > 3 && col0 >= p.seg_begin[3]) sgm = 3;
-            const int scol = col0 - p.seg_begin[sgm];
-            const long long ooff = orow * p.seg_ld[sgm] + scol;
-            float f[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-            const bool act = col0 < p.act_cols;
-            if (p.shift != nullptr && act) {
-              const float4* sp = reinterpret_cast<const float4*>(p.shift + col0);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float4 s4 = __ldg(sp + i);
-                f[4 * i] += s4.x; f[4 * i + 1] += s4.y; f[4 * i + 2] += s4.z; f[4 * i + 3] += s4.w;
-              }
-            }
-            if (p.relu && act) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-            }
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.seg_out[sgm]) + ooff;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (p.accum) {
-                  uint4 a, c;
-                  ld_global_256(o + 8 * i, a, c);
-                  f[8 * i] += __uint_as_float(a.x); f[8 * i + 1] += __uint_as_float(a.y);
-                  f[8 * i + 2] += __uint_as_float(a.z); f[8 * i + 3] += __uint_as_float(a.w);
-                  f[8 * i + 4] += __uint_as_float(c.x); f[8 * i + 5] += __uint_as_float(c.y);
-                  f[8 * i + 6] += __uint_as_float(c.z); f[8 * i + 7] += __uint_as_float(c.w);
-                }
-                st_global_256(o + 8 * i,
-                              make_uint4(__float_as_uint(f[8 * i]), __float_as_uint(f[8 * i + 1]), __float_as_uint(f[8 * i + 2]),
-                                         __float_as_uint(f[8 * i + 3])),
-                              make_uint4(__float_as_uint(f[8 * i + 4]), __float_as_uint(f[8 * i + 5]),
-                                         __float_as_uint(f[8 * i + 6]), __float_as_uint(f[8 * i + 7])));
-              }
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.seg_out[sgm]) + ooff;
-              const uint32_t old[8] = {oldv[u][0].x, oldv[u][0].y, oldv[u][0].z, oldv[u][0].w,
-                                       oldv[u][1].x, oldv[u][1].y, oldv[u][1].z, oldv[u][1].w};
-              const uint32_t yy[8] = {mskv[u][0].x, mskv[u][0].y, mskv[u][0].z, mskv[u][0].w,
-                                      mskv[u][1].x, mskv[u][1].y, mskv[u][1].z, mskv[u][1].w};
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float2 fo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&old[i]));
-                float2 fy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]));
-                f[2 * i] += fo.x; f[2 * i + 1] += fo.y;
-                if (!(fy.x > 0.f)) f[2 * i] = 0.f;
-                if (!(fy.y > 0.f)) f[2 * i + 1] = 0.f;
-              }
-              uint4 w0, w1;
-              w0.x = pack_bf16(f[0], f[1]);  w0.y = pack_bf16(f[2], f[3]);
-              w0.z = pack_bf16(f[4], f[5]);  w0.w = pack_bf16(f[6], f[7]);
-              w1.x = pack_bf16(f[8], f[9]);  w1.y = pack_bf16(f[10], f[11]);
-              w1.z = pack_bf16(f[12], f[13]); w1.w = pack_bf16(f[14], f[15]);
-              st_global_256(o, w0, w1);
-            }
-          }
-        }
-      }
+      epilogue_run<GENERIC>(p, mode, taddr, col_lo, col_hi, nt * p.n_tile, orow, ssh);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&pipe->tmem_empty[as]);      // 8 warps x 2 CTAs arrive on the leader
@@ -586,11 +667,12 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
   }
 }
 
+template <bool GENERIC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                      const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
                      const __grid_constant__ CUtensorMap mapB, const __grid_constant__ ConvGemmParams p) {
-  conv_gemm_tc2_body(mapA0, mapA1, mapA2, mapA3, mapB, p, blockIdx.x >> 1, gridDim.x >> 1);
+  conv_gemm_tc2_body<GENERIC>(mapA0, mapA1, mapA2, mapA3, mapB, p, blockIdx.x >> 1, gridDim.x >> 1);
 }
 
 // Up to four independent problems that share the B operand (weights) and the N tiling, each with its own A
@@ -602,6 +684,7 @@ struct ConvGemmMulti {
   int pair_begin[5];          // pairs [pair_begin[c], pair_begin[c+1]) work on problem c
   ConvGemmParams p[4];
 };
+template <bool GENERIC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 conv_gemm_tc2_multi_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                            const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapA3,
@@ -609,7 +692,7 @@ conv_gemm_tc2_multi_kernel(const __grid_constant__ CUtensorMap mapA0, const __gr
   const int pair = blockIdx.x >> 1;
   int cls = 0;
   while (cls + 1 < mp.count && pair >= mp.pair_begin[cls + 1]) ++cls;
-  conv_gemm_tc2_body(mapA0, mapA1, mapA2, mapA3, mapB, mp.p[cls], pair - mp.pair_begin[cls],
+  conv_gemm_tc2_body<GENERIC>(mapA0, mapA1, mapA2, mapA3, mapB, mp.p[cls], pair - mp.pair_begin[cls],
                      mp.pair_begin[cls + 1] - mp.pair_begin[cls]);
 }
 

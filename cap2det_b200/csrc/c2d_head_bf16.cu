@@ -144,7 +144,8 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       count_launch();
     }
     if (i == 18) {
-      pool3x3_s1_4x4_fwd_kernel<bf16, 0><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X2], 1024, act[P2], 1024, n, 1024);
+      maxpool3x3_s1_4x4_codes_fwd_kernel<1024><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
+          act[X2], act[P2], n, reinterpret_cast<unsigned char*>(ws + pl.pool5c_code_off));
       count_launch();
     }
     if (head_in_group_tail(i) || i == kHead5bPoolConv) continue;   // computed together with the first member of its group
@@ -199,7 +200,8 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
   C2D_CUDA_OK(cudaMemsetAsync(dwsf, 0, pl.w_only_total * sizeof(float), st));
   C2D_CUDA_OK(cudaMemsetAsync(dshf, 0, pl.ch_total * sizeof(float), st));
   bool written[NBUF] = {false};
-  // every gradient buffer is written as du = dy * (y > 0) by its LAST writer (fused ReLU backward);
+  // every gradient buffer is written as du = dy * (y > 0) by its LAST writer (fused ReLU backward; for X2 that is
+  // the code-driven max-pool backward kernel, for the others a data-gradient GEMM);
   // the BN-shift gradients come out of the weight-gradient kernel (ones-vector MMA).
   avgpool_dropout_bwd_kernel<bf16><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(dfeat, keep_mask, keep_prob, 16, 1024, grad[X3], n,
                                                                               act[X3]);
@@ -260,9 +262,11 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       // the destination is complete after this GEMM (the max-pool backward into X2 runs BEFORE the merged
       // sibling dgrad), so it applies the ReLU mask of the convolutions that produced the buffer:
       // all columns for conv outputs, [0,448) for X1 (the rest is the max-pool branch), none for X0 / P*.
+      // X2: Mixed_5c's max-pool backward runs AFTER this GEMM as the last writer (routed pool gradient added, ReLU mask
+      // from its forward codes), so this output-heavy GEMM keeps a store-only epilogue.
       const bf16* mask = nullptr;
       int mask_cols = 0;
-      if (c.src != X0 && c.src != P1 && c.src != P2) {
+      if (c.src != X0 && c.src != P1 && c.src != P2 && c.src != X2) {
         mask = act[c.src] + c.src_off;
         mask_cols = c.src == X1 ? 448 : kHeadBufs[c.src].ch;
       }
@@ -270,12 +274,11 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
                          written[c.src] ? 1 : 0, 0, st, mask, mask_cols);
       if (rc != C2D_OK) return rc;
       written[c.src] = true;
-    }
-    if (i == 18) {
-      pool3x3_s1_4x4_bwd_kernel<bf16, 0><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
-          act[X2], 1024, grad[P2], 1024, grad[X2], 1024, n, 1024);
-      count_launch();
-      written[X2] = true;
+      if (c.src == X2) {
+        maxpool3x3_s1_4x4_codes_bwd_kernel<1024><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(
+            reinterpret_cast<const unsigned char*>(ws + pl.pool5c_code_off), grad[P2], grad[X2], n);
+        count_launch();
+      }
     }
     if (i == 5 && dx0 != nullptr && !fold_pool5a) {
       pool3x3_bwd_kernel<bf16, 7, 2, 0, false><<<dim3(cdiv(576 / 2, 128), n), 128, 0, st>>>(

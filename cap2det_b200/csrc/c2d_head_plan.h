@@ -85,6 +85,7 @@ struct HeadPlan {
   size_t ws_off, wt_off, shift_off, dws_off, dshift_off;   // fp32 folded weights etc.
   size_t ws16_off, wt16_off;                         // bf16 copies (bf16 path only)
   size_t pool5a_code_off;                            // [n,16,576] u8: arg-max tap of Mixed_5a/Branch_2's max-pool (bf16 path)
+  size_t pool5c_code_off;                            // [n,16,1024] u8: arg-max tap + ReLU flags of Mixed_5c/Branch_3's max-pool
   size_t total_bytes;
 };
 
@@ -126,6 +127,7 @@ static inline HeadPlan make_head_plan(int n_rois, int elt_bytes) {
   p.ws16_off = off; off += align_up(wo * 2, 1024);
   p.wt16_off = off; off += align_up(wo * 2, 1024);
   p.pool5a_code_off = off; off += align_up((size_t)n_rois * 16 * 576, 1024);
+  p.pool5c_code_off = off; off += align_up((size_t)n_rois * 16 * 1024, 1024);
   p.total_bytes = off + 1024;
   return p;
 }

@@ -387,7 +387,7 @@ def test_pool_backward_folded_into_roi_backward_matches_separate_kernel():
     model.raise_if_assert_failed()
     grads.append((fm.grad.cpu().numpy(), model.head_params.grad.cpu().numpy()))
     losses.append(float(sum(loss.values())))
-  assert losses[0] == losses[1]
+  assert abs(losses[0] - losses[1]) <= 2e-6 * abs(losses[1])      # same forward; the loss means are summed with fp32 atomics
   assert np.abs(grads[0][0]).max() > 0
   assert l2_err(grads[0][0], grads[1][0]) < 5e-3, l2_err(grads[0][0], grads[1][0])
   assert l2_err(grads[0][1], grads[1][1]) < 1e-5      # the head's own gradients do not depend on the fold (fp32 atomics order only)
