@@ -37,10 +37,17 @@ def _trunc_normal_(t, std, gen):
   torch.nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2 * std, b=2 * std, generator=gen)
 
 
+class LossDict(dict):
+  """build_loss's result: the reference's {name: loss} dict, plus `.total` = their sum when the fused loss head computed
+  it on the device (TrainStep then skips the host-side chain of adds)."""
+  total = None
+
+
 class Model(ModelBase):
   """Cap2Det model."""
 
   fold_pool_backward = True      # see ops.PoolFold; False keeps the head's own max-pool backward kernel (tests compare both)
+  fused_loss_head = True         # see ops.loss_head; False runs build_loss op by op (tests compare both)
 
   def __init__(self, model_proto, is_training=False, device=None, head_dtype=torch.float32, seed=0,
                first_stage=False):
@@ -65,6 +72,8 @@ class Model(ModelBase):
     self._oicr_postprocess_fn = build_post_processor(options.oicr_post_processor)
     self._label_extractor = build_label_extractor(options.label_extractor, self._device)
     self._assert_status = None
+    self._seed = int(seed)
+    self._dropout_state = None     # device counter of the library's dropout mask generator (ops.dropout_keep_mask)
     self._init_variables(seed)
     self.backbone_params = None
     if first_stage:
@@ -198,7 +207,11 @@ class Model(ModelBase):
     if is_training and keep_prob < 1.0:
       keep_mask = examples.get(InputDataFields.dropout_keep_mask)
       if keep_mask is None:   # TF1 slim.dropout: floor(keep_prob + uniform[0,1))
-        keep_mask = torch.floor(keep_prob + torch.rand((B * P, ops.HEAD_FEATURE_DIMS), device=x0.device))
+        if self._dropout_state is None:             # per-rank stream: replicas must not share their dropout masks
+          rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+          self._dropout_seed = (self._seed * 7919 + rank * 104729 + 12345) & 0xffffffff
+          self._dropout_state = torch.zeros((2,), dtype=torch.int64, device=x0.device)
+        keep_mask = ops.dropout_keep_mask(self._dropout_state, self._dropout_seed, (B * P, ops.HEAD_FEATURE_DIMS), keep_prob)
     feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
                            need_dx0=features_to_crop.requires_grad, fold=fold)
     # models/cap2det_model.py:79-88,190-197: the five FC layers as one product
@@ -301,30 +314,44 @@ class Model(ModelBase):
   def build_loss(self, predictions, examples, **kwargs):
     """models/cap2det_model.py:274-330."""
     options = self._model_proto
-    loss_dict = {}
+    loss_dict = LossDict()
     labels = examples.get('_labels')            # precomputed image-level labels (GraphedTrainStep), else extract
     if labels is None:
       labels = self._label_extractor.extract_labels(examples)
-    loss_dict['midn_cross_entropy_loss'] = ops.sigmoid_ce_mean(
-        labels, predictions[Cap2DetPredictions.midn_class_logits], options.midn_loss_weight)
     num_proposals = predictions[DetectionResultFields.num_proposals]
     proposals = predictions[DetectionResultFields.proposal_boxes]
     logits_all = predictions['_logits_all']
     C = self._num_classes
+    K = len(self._col_oicr)
     scores_0 = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_0']
     if options.oicr_use_proba_r_given_c:
       scores_0 = predictions[Cap2DetPredictions.midn_proba_r_given_c]
     scores_0 = scores_0.detach()
     aux = []
-    for i, col in enumerate(self._col_oicr):
-      ind, proposal_labels, status = ops.oicr_assign(labels, num_proposals, proposals, scores_0,
-                                                     options.oicr_iou_threshold)
+    if self.fused_loss_head and K <= 4 and all(col == self._col_oicr[0] + i * (C + 1) for i, col in enumerate(self._col_oicr)):
+      # one autograd node for the MIDN loss and all OICR stages (5 + 2 launches, ops.loss_head)
+      midn_loss, oicr_losses, total, ind, proposal_labels, status = ops.loss_head(
+          logits_all, labels, num_proposals, proposals, predictions[Cap2DetPredictions.midn_class_logits],
+          predictions[Cap2DetPredictions.midn_proba_r_given_c], scores_0, C, K, self._col_r, self._col_c,
+          self._col_oicr[0] if K else 0, options.oicr_iou_threshold, options.midn_loss_weight, options.oicr_loss_weight)
+      loss_dict['midn_cross_entropy_loss'] = midn_loss
+      for i in range(K):
+        loss_dict['oicr_cross_entropy_loss_at_{}'.format(i + 1)] = oicr_losses[i]
+        aux.append((ind[i], proposal_labels[i]))
+      loss_dict.total = total
       self._assert_status = status if self._assert_status is None else (self._assert_status | status)
-      loss_dict['oicr_cross_entropy_loss_at_{}'.format(i + 1)] = ops.oicr_cross_entropy(
-          logits_all, col, proposal_labels, num_proposals, options.oicr_loss_weight)
-      aux.append((ind, proposal_labels))
-      if i + 1 < len(self._col_oicr):
-        scores_0 = ops.softmax_rows(logits_all.detach()[:, :, col:col + C + 1])[:, :, 1:]      # :328
+    else:
+      loss_dict['midn_cross_entropy_loss'] = ops.sigmoid_ce_mean(
+          labels, predictions[Cap2DetPredictions.midn_class_logits], options.midn_loss_weight)
+      for i, col in enumerate(self._col_oicr):
+        ind, proposal_labels, status = ops.oicr_assign(labels, num_proposals, proposals, scores_0,
+                                                       options.oicr_iou_threshold)
+        self._assert_status = status if self._assert_status is None else (self._assert_status | status)
+        loss_dict['oicr_cross_entropy_loss_at_{}'.format(i + 1)] = ops.oicr_cross_entropy(
+            logits_all, col, proposal_labels, num_proposals, options.oicr_loss_weight)
+        aux.append((ind, proposal_labels))
+        if i + 1 < len(self._col_oicr):
+          scores_0 = ops.softmax_rows(logits_all.detach()[:, :, col:col + C + 1])[:, :, 1:]      # :328
     self.last_oicr_assignments = aux
     self.last_labels = labels
     return loss_dict

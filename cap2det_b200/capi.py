@@ -88,6 +88,12 @@ SIGNATURES = {
                                            _c_float, _p, _p, _p, _p]),
     'c2d_adagrad_update': (_c_int, [_p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _p]),
     'c2d_l2_loss': (_c_int, [_p, _c_ll, _c_float, _p, _p]),
+    'c2d_dropout_keep_mask': (_c_int, [_p, ctypes.c_uint, _c_ll, _c_float, _p, _p]),
+    'c2d_l2_loss_add': (_c_int, [_p, _c_ll, _c_float, _p, _p, _p]),
+    'c2d_loss_head_fwd': (_c_int, [_p, _c_int, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float,
+                                   _c_float, _p, _p, _p, _p, _p, _p]),
+    'c2d_loss_head_bwd': (_c_int, [_p, _c_int, _p, _p, _p, _p, _p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                   _c_float, _c_float, _p, _p, _p, _p, _p, _p, _p, _p]),
     'c2d_wordvec_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int]),
     'c2d_wordvec_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _c_int, _p, _p, _p, _p, _p]),
 }

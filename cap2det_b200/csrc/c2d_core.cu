@@ -187,6 +187,38 @@ __global__ void l2_loss_kernel(const float* __restrict__ w, long long n, float s
   }
 }
 
+// ---- slim.dropout keep mask: floor(keep_prob + uniform[0,1)), Philox4x32-10 ---------------------
+// state[0] = number of masks drawn so far (the Philox key's high word), state[1] = blocks finished in this launch.
+// Every block reads state[0] when it starts; the block that finishes last advances it, so consecutive launches --
+// also replays of one captured CUDA graph -- draw different masks without any host involvement.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__global__ void __launch_bounds__(256)
+dropout_keep_mask_kernel(unsigned long long* __restrict__ state, unsigned seed, long long n4, float keep_prob,
+                         float4* __restrict__ mask) {
+  const unsigned long long draw = state[0];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)i, (unsigned)(i >> 32), (unsigned)draw, (unsigned)(draw >> 32)),
+                                  make_uint2(seed, 0x5EED5EEDu));
+    const float s = 1.0f / 16777216.0f;          // 24 random bits -> [0, 1)
+    mask[i] = make_float4(floorf(keep_prob + (float)(r.x >> 8) * s), floorf(keep_prob + (float)(r.y >> 8) * s),
+                          floorf(keep_prob + (float)(r.z >> 8) * s), floorf(keep_prob + (float)(r.w >> 8) * s));
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&state[1], 1ull) == (unsigned long long)gridDim.x - 1ull) { state[1] = 0ull; state[0] = draw + 1ull; }
+  }
+}
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -277,6 +309,32 @@ int c2d_l2_loss(const float* w, long long n, float scale, float* out, c2d_stream
   C2D_CHECK_ARG(n >= 0, "l2_loss: n must be >= 0");
   cudaStream_t st = (cudaStream_t)stream;
   C2D_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148) blocks = 148;
+  l2_loss_kernel<<<blocks, 256, 0, st>>>(w, n, scale, out);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_dropout_keep_mask(unsigned long long* state, unsigned seed, long long n, float keep_prob, float* mask,
+                          c2d_stream_t stream) {
+  C2D_CHECK_ARG(state != nullptr && n >= 0 && n % 4 == 0, "dropout_keep_mask: n must be a multiple of 4");
+  if (n == 0) return C2D_OK;
+  const long long n4 = n / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dropout_keep_mask_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(state, seed, n4, keep_prob, reinterpret_cast<float4*>(mask));
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_l2_loss_add(const float* w, long long n, float scale, const float* base, float* out, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0 && base != nullptr && out != nullptr, "l2_loss_add: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (base != out) C2D_CUDA_OK(cudaMemcpyAsync(out, base, sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (n == 0) return C2D_OK;
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148) blocks = 148;

@@ -83,7 +83,11 @@ __global__ void __launch_bounds__(kColThreads)
 midn_bwd_kernel(const float* __restrict__ lc, int ld, const int* __restrict__ nprop, int P, int C,
                 const float* __restrict__ class_logits, const float* __restrict__ proba,
                 const float* __restrict__ d_cl, const float* __restrict__ d_sc, const float* __restrict__ d_pr,
-                float* __restrict__ d_lr, float* __restrict__ d_lc, int ldd) {
+                float* __restrict__ d_lr, float* __restrict__ d_lc, int ldd,
+                const float* __restrict__ ce_labels, float ce_scale, const float* __restrict__ ce_g0,
+                const float* __restrict__ ce_g1) {
+  // ce_labels != null (fused loss head): d class_logits also receives the gradient of
+  // weight * mean(sigmoid CE) = (g0 + g1) * ce_scale * (sigmoid(cl) - label), ce_scale = weight / (B * C)
   __shared__ float sm[kColThreads];
   const int b = blockIdx.y;
   const int cl = threadIdx.x % kColsPerCta, r = threadIdx.x / kColsPerCta;
@@ -100,6 +104,10 @@ midn_bwd_kernel(const float* __restrict__ lc, int ld, const int* __restrict__ np
   if (live) {
     sg = sigmoidf_(class_logits[(size_t)b * C + c]);
     dcl = d_cl ? d_cl[(size_t)b * C + c] : 0.f;
+    if (ce_labels != nullptr) {
+      const float g = (ce_g0 ? *ce_g0 : 0.f) + (ce_g1 ? *ce_g1 : 0.f);
+      dcl += g * ce_scale * (sg - ce_labels[(size_t)b * C + c]);
+    }
   }
   if (d_sc) {   // d class_logits through scores = sigmoid(cl) * proba
     float a = 0.f;
@@ -133,7 +141,7 @@ midn_bwd_kernel(const float* __restrict__ lc, int ld, const int* __restrict__ np
 
 // ---- sigmoid cross entropy mean (single CTA; n = B*C is tiny) -----------------------------
 __global__ void sigmoid_ce_mean_fwd_kernel(const float* __restrict__ labels, const float* __restrict__ logits,
-                                           int n, float weight, float* __restrict__ loss) {
+                                           int n, float weight, float* __restrict__ loss, float* __restrict__ total) {
   __shared__ float sm[32];
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -147,6 +155,7 @@ __global__ void sigmoid_ce_mean_fwd_kernel(const float* __restrict__ labels, con
     float t = 0.f;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
     *loss = t / (float)n * weight;
+    if (total != nullptr) atomicAdd(total, t / (float)n * weight);
   }
 }
 __global__ void sigmoid_ce_mean_bwd_kernel(const float* __restrict__ labels, const float* __restrict__ logits,
@@ -157,12 +166,13 @@ __global__ void sigmoid_ce_mean_bwd_kernel(const float* __restrict__ labels, con
 }
 
 // ---- softmax over the last axis; one warp per row -------------------------------------------
+// grid.y = independent column blocks of the same rows: block s reads x + s * x_step, writes y + s * y_step.
 __global__ void softmax_rows_kernel(const float* __restrict__ x, int ldx, int rows, int n, float* __restrict__ y,
-                                    int ldy) {
+                                    int ldy, long long x_step, long long y_step) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + (size_t)row * ldx;
-  float* yr = y + (size_t)row * ldy;
+  const float* xr = x + (size_t)row * ldx + blockIdx.y * x_step;
+  float* yr = y + (size_t)row * ldy + blockIdx.y * y_step;
   float mx = -INFINITY;
   for (int j = lane; j < n; j += 32) mx = fmaxf(mx, xr[j]);
   mx = warp_max(mx);
@@ -172,13 +182,29 @@ __global__ void softmax_rows_kernel(const float* __restrict__ x, int ldx, int ro
   for (int j = lane; j < n; j += 32) yr[j] = __fdiv_rn(expf(__fsub_rn(xr[j], mx)), s);
 }
 
+// The K refinement stages are independent given the logits (stage k seeds from the scores of stage k-1, which are
+// a softmax of that stage's own logits), so every OICR kernel runs all stages in one launch: grid.z = stage.
+constexpr int kMaxOicrStages = 4;
+struct OicrStages {
+  const float* s0[kMaxOicrStages]; int ld0[kMaxOicrStages];     // class scores a stage seeds from
+  long long* ind[kMaxOicrStages];                               // [B,C] seed proposal per class
+  float* pl[kMaxOicrStages];                                    // [B,P,C+1] pseudo labels
+  const float* s1[kMaxOicrStages];                              // the stage's own logits (row stride ld1)
+  float* loss[kMaxOicrStages];
+  float* total;                                                 // optional: sum of all losses
+  const float* dloss[kMaxOicrStages]; const float* dtotal;      // backward: upstream gradients (each may be null)
+  float* ds1[kMaxOicrStages];
+};
+
 // ---- OICR stage 1/2: per-class masked arg-max seed (models/utils.py:44-47) -------------------
 // argmax_p((s - min_p s) * mask), min over ALL P rows, ties -> lowest p.  grid (ceil(C/8), B).
 __global__ void __launch_bounds__(kColThreads)
-oicr_seed_kernel(const float* __restrict__ s0, int ld0, const int* __restrict__ nprop, int P, int C,
-                 long long* __restrict__ ind) {
+oicr_seed_kernel(const OicrStages a, const int* __restrict__ nprop, int P, int C) {
   __shared__ float sm[kColThreads];
   __shared__ int smi[kColThreads];
+  const float* __restrict__ s0 = a.s0[blockIdx.z];
+  const int ld0 = a.ld0[blockIdx.z];
+  long long* __restrict__ ind = a.ind[blockIdx.z];
   const int b = blockIdx.y;
   const int cl = threadIdx.x % kColsPerCta, r = threadIdx.x / kColsPerCta;
   const int c = blockIdx.x * kColsPerCta + cl;
@@ -214,9 +240,10 @@ oicr_seed_kernel(const float* __restrict__ s0, int ld0, const int* __restrict__ 
 // (models/utils.py:55-95).  grid (ceil(P/256), B), block 256; up to 128 classes.
 constexpr int kMaxOicrClasses = 128;
 __global__ void __launch_bounds__(256)
-oicr_labels_kernel(const float* __restrict__ labels, const float4* __restrict__ proposals,
-                   const long long* __restrict__ ind, float thr, int P, int C, float* __restrict__ out,
-                   int* __restrict__ status) {
+oicr_labels_kernel(const float* __restrict__ labels, const float4* __restrict__ proposals, const OicrStages a,
+                   float thr, int P, int C, int* __restrict__ status) {
+  const long long* __restrict__ ind = a.ind[blockIdx.z];
+  float* __restrict__ out = a.pl[blockIdx.z];
   __shared__ float4 seed[kMaxOicrClasses];
   __shared__ int gate[kMaxOicrClasses];
   __shared__ uint32_t bits[256][4];
@@ -264,8 +291,10 @@ oicr_labels_kernel(const float* __restrict__ labels, const float4* __restrict__ 
 // ---- OICR soft-label cross entropy (models/utils.py:99-103), one warp per proposal row -------
 // loss += weight / B * sum_p mask*CE / max(1e-10, n_b);  grid (ceil(P/8), B), block 256.
 __global__ void __launch_bounds__(256)
-oicr_ce_fwd_kernel(const float* __restrict__ pl, const float* __restrict__ s1, int ld1,
-                   const int* __restrict__ nprop, int B, int P, int C, float weight, float* __restrict__ loss) {
+oicr_ce_fwd_kernel(const OicrStages a, int ld1, const int* __restrict__ nprop, int B, int P, int C, float weight) {
+  const float* __restrict__ pl = a.pl[blockIdx.z];
+  const float* __restrict__ s1 = a.s1[blockIdx.z];
+  float* __restrict__ loss = a.loss[blockIdx.z];
   __shared__ float sm[8];
   const int b = blockIdx.y;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -292,13 +321,19 @@ oicr_ce_fwd_kernel(const float* __restrict__ pl, const float* __restrict__ s1, i
     float t = 0.f;
     for (int i = 0; i < 8; ++i) t += sm[i];
     float den = fmaxf(1e-10f, (float)min(max(np, 0), P));
-    if (t != 0.f) atomicAdd(loss, t / den / (float)B * weight);
+    if (t != 0.f) {
+      atomicAdd(loss, t / den / (float)B * weight);
+      if (a.total != nullptr) atomicAdd(a.total, t / den / (float)B * weight);
+    }
   }
 }
 __global__ void __launch_bounds__(256)
-oicr_ce_bwd_kernel(const float* __restrict__ pl, const float* __restrict__ s1, int ld1,
-                   const int* __restrict__ nprop, int B, int P, int C, float weight,
-                   const float* __restrict__ dloss, float* __restrict__ ds1, int ldd) {
+oicr_ce_bwd_kernel(const OicrStages a, int ld1, const int* __restrict__ nprop, int B, int P, int C, float weight,
+                   int ldd) {
+  const float* __restrict__ pl = a.pl[blockIdx.z];
+  const float* __restrict__ s1 = a.s1[blockIdx.z];
+  float* __restrict__ ds1 = a.ds1[blockIdx.z];
+  const float up = (a.dloss[blockIdx.z] ? *a.dloss[blockIdx.z] : 0.f) + (a.dtotal ? *a.dtotal : 0.f);
   const int b = blockIdx.y;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int p = blockIdx.x * 8 + wid;
@@ -319,7 +354,7 @@ oicr_ce_bwd_kernel(const float* __restrict__ pl, const float* __restrict__ s1, i
   for (int j = lane; j < C1; j += 32) s += expf(x[j] - mx);
   s = warp_sum(s);
   float den = fmaxf(1e-10f, (float)min(max(np, 0), P));
-  float g = (*dloss) * weight / den / (float)B;
+  float g = up * weight / den / (float)B;
   for (int j = lane; j < C1; j += 32) d[j] = g * (expf(x[j] - mx) / s - t[j]);
 }
 
@@ -347,7 +382,7 @@ int c2d_midn_bwd(const float* lc, int ld, const int* nprop, int B, int P, int C,
   if (B == 0) return C2D_OK;
   dim3 grid(cdiv(C, kColsPerCta), B);
   midn_bwd_kernel<<<grid, kColThreads, 0, (cudaStream_t)stream>>>(lc, ld, nprop, P, C, class_logits, proba, d_cl,
-                                                                  d_sc, d_pr, d_lr, d_lc, ldd);
+                                                                  d_sc, d_pr, d_lr, d_lc, ldd, nullptr, 0.f, nullptr, nullptr);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -356,7 +391,7 @@ int c2d_midn_bwd(const float* lc, int ld, const int* nprop, int B, int P, int C,
 int c2d_sigmoid_ce_mean_fwd(const float* labels, const float* logits, int n, float weight, float* loss,
                             c2d_stream_t stream) {
   C2D_CHECK_ARG(n >= 1, "sigmoid_ce: n must be >= 1");
-  sigmoid_ce_mean_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(labels, logits, n, weight, loss);
+  sigmoid_ce_mean_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(labels, logits, n, weight, loss, nullptr);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -373,7 +408,7 @@ int c2d_sigmoid_ce_mean_bwd(const float* labels, const float* logits, int n, flo
 int c2d_softmax_rows(const float* x, int ldx, int rows, int n, float* y, int ldy, c2d_stream_t stream) {
   C2D_CHECK_ARG(rows >= 0 && n >= 1 && ldx >= n && ldy >= n, "softmax_rows: bad shape");
   if (rows == 0) return C2D_OK;
-  softmax_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, n, y, ldy);
+  softmax_rows_kernel<<<cdiv((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, n, y, ldy, 0, 0);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -390,9 +425,11 @@ int c2d_oicr_assign(const float* labels, const int* nprop, const float* proposal
   cudaStream_t st = (cudaStream_t)stream;
   C2D_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), st));
   if (B == 0) return C2D_OK;
-  oicr_seed_kernel<<<dim3(cdiv(C, kColsPerCta), B), kColThreads, 0, st>>>(scores0_cls, ld0, nprop, P, C, proposal_ind);
-  oicr_labels_kernel<<<dim3(cdiv(P, 256), B), 256, 0, st>>>(labels, (const float4*)proposals, proposal_ind,
-                                                            iou_threshold, P, C, proposal_labels, status);
+  OicrStages a;
+  memset(&a, 0, sizeof(a));
+  a.s0[0] = scores0_cls; a.ld0[0] = ld0; a.ind[0] = proposal_ind; a.pl[0] = proposal_labels;
+  oicr_seed_kernel<<<dim3(cdiv(C, kColsPerCta), B), kColThreads, 0, st>>>(a, nprop, P, C);
+  oicr_labels_kernel<<<dim3(cdiv(P, 256), B), 256, 0, st>>>(labels, (const float4*)proposals, a, iou_threshold, P, C, status);
   count_launch(2);
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -403,7 +440,10 @@ int c2d_oicr_ce_fwd(const float* pl, const float* s1, int ld1, const int* nprop,
   C2D_CHECK_ARG(B >= 1 && P >= 1 && C >= 1 && ld1 >= C + 1, "oicr_ce_fwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   C2D_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  oicr_ce_fwd_kernel<<<dim3(cdiv(P, 8), B), 256, 0, st>>>(pl, s1, ld1, nprop, B, P, C, weight, loss);
+  OicrStages a;
+  memset(&a, 0, sizeof(a));
+  a.pl[0] = const_cast<float*>(pl); a.s1[0] = s1; a.loss[0] = loss;
+  oicr_ce_fwd_kernel<<<dim3(cdiv(P, 8), B), 256, 0, st>>>(a, ld1, nprop, B, P, C, weight);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
@@ -411,9 +451,95 @@ int c2d_oicr_ce_fwd(const float* pl, const float* s1, int ld1, const int* nprop,
 int c2d_oicr_ce_bwd(const float* pl, const float* s1, int ld1, const int* nprop, int B, int P, int C, float weight,
                     const float* dloss, float* ds1, int ldd, c2d_stream_t stream) {
   C2D_CHECK_ARG(B >= 1 && P >= 1 && C >= 1 && ld1 >= C + 1 && ldd >= C + 1, "oicr_ce_bwd: bad shape");
-  oicr_ce_bwd_kernel<<<dim3(cdiv(P, 8), B), 256, 0, (cudaStream_t)stream>>>(pl, s1, ld1, nprop, B, P, C, weight,
-                                                                           dloss, ds1, ldd);
+  OicrStages a;
+  memset(&a, 0, sizeof(a));
+  a.pl[0] = const_cast<float*>(pl); a.s1[0] = s1; a.dloss[0] = dloss; a.ds1[0] = ds1;
+  oicr_ce_bwd_kernel<<<dim3(cdiv(P, 8), B), 256, 0, (cudaStream_t)stream>>>(a, ld1, nprop, B, P, C, weight, ldd);
   count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused loss head (models/cap2det_model.py:274-330 + models/utils.py:15-105): the MIDN sigmoid cross entropy and all
+// K OICR stages from one [B,P,ld] logits tensor in 5 launches (sigmoid CE, softmax of stages 0..K-2, seeds, pseudo
+// labels, soft-label CE; the last three with grid.z = stage), and their gradients in 2 (MIDN backward with the
+// sigmoid-CE gradient formed in place; soft-label CE backward) that write one gradient tensor with disjoint
+// columns -- instead of 17 + 16 launches with full-size zero fills and adds between five autograd nodes.
+//   columns of stage k: [col_oicr0 + k (C+1), col_oicr0 + (k+1)(C+1));  losses = [midn, oicr_1 .. oicr_K, total].
+// ---------------------------------------------------------------------------------------------
+int c2d_loss_head_fwd(const float* logits_all, int ld, const int* nprop, const float* proposals, const float* labels,
+                      const float* class_logits, const float* scores0, int B, int P, int C, int K, int col_oicr0,
+                      float iou_threshold, float midn_weight, float oicr_weight, float* softmax_ws,
+                      long long* proposal_ind, float* proposal_labels, float* losses, int* status,
+                      c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 1 && P >= 1 && C >= 1 && K >= 0 && K <= kMaxOicrStages && col_oicr0 >= 0 &&
+                ld >= col_oicr0 + K * (C + 1), "loss_head_fwd: bad shape B=%d P=%d C=%d K=%d ld=%d", B, P, C, K, ld);
+  if (C > kMaxOicrClasses) {
+    set_error("loss_head_fwd: at most %d classes supported (got %d)", kMaxOicrClasses, C);
+    return C2D_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C1 = C + 1;
+  C2D_CUDA_OK(cudaMemsetAsync(losses, 0, (K + 2) * sizeof(float), st));
+  C2D_CUDA_OK(cudaMemsetAsync(status, 0, sizeof(int), st));
+  sigmoid_ce_mean_fwd_kernel<<<1, 256, 0, st>>>(labels, class_logits, B * C, midn_weight, losses, losses + K + 1);
+  count_launch();
+  if (K > 0) {
+    OicrStages a;
+    memset(&a, 0, sizeof(a));
+    const size_t stage_rows = (size_t)B * P;
+    for (int k = 0; k < K; ++k) {
+      a.s0[k] = k == 0 ? scores0 : softmax_ws + (size_t)(k - 1) * stage_rows * C1 + 1;     // class columns, background skipped
+      a.ld0[k] = k == 0 ? C : C1;
+      a.ind[k] = proposal_ind + (size_t)k * B * C;
+      a.pl[k] = proposal_labels + (size_t)k * stage_rows * C1;
+      a.s1[k] = logits_all + col_oicr0 + k * C1;
+      a.loss[k] = losses + 1 + k;
+    }
+    a.total = losses + K + 1;
+    if (K > 1) {
+      softmax_rows_kernel<<<dim3(cdiv((long long)stage_rows * 32, 256), K - 1), 256, 0, st>>>(
+          logits_all + col_oicr0, ld, (int)stage_rows, C1, softmax_ws, C1, C1, (long long)stage_rows * C1);
+      count_launch();
+    }
+    oicr_seed_kernel<<<dim3(cdiv(C, kColsPerCta), B, K), kColThreads, 0, st>>>(a, nprop, P, C);
+    oicr_labels_kernel<<<dim3(cdiv(P, 256), B, K), 256, 0, st>>>(labels, (const float4*)proposals, a, iou_threshold, P, C, status);
+    oicr_ce_fwd_kernel<<<dim3(cdiv(P, 8), B, K), 256, 0, st>>>(a, ld, nprop, B, P, C, oicr_weight);
+    count_launch(3);
+  }
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_loss_head_bwd(const float* logits_all, int ld, const int* nprop, const float* labels, const float* class_logits,
+                      const float* proba, const float* proposal_labels, int B, int P, int C, int K, int col_r, int col_c,
+                      int col_oicr0, float midn_weight, float oicr_weight, const float* d_midn, const float* d_oicr0,
+                      const float* d_oicr1, const float* d_oicr2, const float* d_oicr3, const float* d_total,
+                      float* d_logits, c2d_stream_t stream) {
+  C2D_CHECK_ARG(B >= 1 && P >= 1 && C >= 1 && K >= 0 && K <= kMaxOicrStages && ld >= col_oicr0 + K * (C + 1) &&
+                col_r >= 0 && col_c >= 0 && ld >= col_r + C && ld >= col_c + C, "loss_head_bwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int C1 = C + 1;
+  C2D_CUDA_OK(cudaMemsetAsync(d_logits, 0, (size_t)B * P * ld * sizeof(float), st));      // padding columns
+  midn_bwd_kernel<<<dim3(cdiv(C, kColsPerCta), B), kColThreads, 0, st>>>(
+      logits_all + col_c, ld, nprop, P, C, class_logits, proba, nullptr, nullptr, nullptr, d_logits + col_r, d_logits + col_c,
+      ld, labels, midn_weight / (float)(B * C), d_midn, d_total);
+  count_launch();
+  if (K > 0) {
+    OicrStages a;
+    memset(&a, 0, sizeof(a));
+    const float* dl[kMaxOicrStages] = {d_oicr0, d_oicr1, d_oicr2, d_oicr3};
+    for (int k = 0; k < K; ++k) {
+      a.pl[k] = const_cast<float*>(proposal_labels) + (size_t)k * B * P * C1;
+      a.s1[k] = logits_all + col_oicr0 + k * C1;
+      a.dloss[k] = dl[k];
+      a.ds1[k] = d_logits + col_oicr0 + k * C1;
+    }
+    a.dtotal = d_total;
+    oicr_ce_bwd_kernel<<<dim3(cdiv(P, 8), B, K), 256, 0, st>>>(a, ld, nprop, B, P, C, oicr_weight, ld);
+    count_launch();
+  }
   C2D_LAUNCH_OK();
   return C2D_OK;
 }

@@ -182,6 +182,15 @@ def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True, fold=N
 # ---------------------------------------------------------------------------------------------
 # Reader-side image / box contract  (readers/cap2det_reader.py:143-199, core/imgproc.py:300-352)
 # ---------------------------------------------------------------------------------------------
+def dropout_keep_mask(state, seed, shape, keep_prob):
+  """slim.dropout's keep mask floor(keep_prob + uniform[0,1)) (models/utils.py:176-177) from the library's Philox kernel.
+  state: int64[2] device tensor, zero-initialised once and then owned by the kernel (it counts the masks drawn)."""
+  require_cuda(state)
+  mask = torch.empty(tuple(shape), dtype=torch.float32, device=state.device)
+  call('c2d_dropout_keep_mask', ptr(state), int(seed) & 0xffffffff, mask.numel(), float(keep_prob), ptr(mask), stream())
+  return mask
+
+
 def resize_bilinear(image, new_height, new_width):
   """tf.image.resize_images(image, [new_height, new_width]) (bilinear, align_corners False, TF1 sampling).
   image [B,H,W,C] or [H,W,C], fp32 or uint8 -> fp32."""
@@ -323,7 +332,8 @@ class _FcConcat(torch.autograd.Function):
     M, D = x.shape
     N = w.shape[0]
     ld = _ld16(N)
-    y = torch.zeros((M, ld), dtype=torch.float32, device=x.device)
+    # the tensor-core path writes all ld columns (padding = zero weights + zero bias); the CUDA-core path only the first N
+    y = (torch.empty if dtype_code == capi.C2D_BF16 else torch.zeros)((M, ld), dtype=torch.float32, device=x.device)
     ws, nbytes = None, 0
     if dtype_code == capi.C2D_BF16:
       nbytes = capi.load().c2d_fc_workspace_bytes(M, D, N, dtype_code)
@@ -488,6 +498,58 @@ class _OicrCe(torch.autograd.Function):
 def oicr_cross_entropy(logits_all, col, proposal_labels, num_proposals, weight=1.0):
   """weight * calc_oicr_loss's soft-label CE on columns [col, col+1+C) of logits_all."""
   return _OicrCe.apply(logits_all, col, proposal_labels.contiguous(), num_proposals, weight)
+
+
+class _LossHead(torch.autograd.Function):
+  """models/cap2det_model.py:274-330 as ONE autograd node over the concatenated logits (c2d_loss_head_fwd / _bwd)."""
+
+  @staticmethod
+  def forward(ctx, logits_all, labels, num_proposals, proposals, class_logits, proba, scores0, cfg):
+    require_cuda(logits_all, labels, num_proposals, proposals, class_logits, proba, scores0)
+    C, K, col_r, col_c, col_oicr0, thr, w_midn, w_oicr = cfg
+    B, P, ld = logits_all.shape
+    dev = logits_all.device
+    losses = torch.empty((K + 2,), dtype=torch.float32, device=dev)
+    ind = torch.empty((max(K, 1), B, C), dtype=torch.int64, device=dev)
+    pl = torch.empty((max(K, 1), B, P, C + 1), dtype=torch.float32, device=dev)
+    sm = torch.empty((max(K - 1, 1), B, P, C + 1), dtype=torch.float32, device=dev)
+    status = torch.empty((1,), dtype=torch.int32, device=dev)
+    call('c2d_loss_head_fwd', ptr(logits_all), ld, ptr(num_proposals), ptr(proposals), ptr(labels), ptr(class_logits),
+         ptr(scores0), B, P, C, K, col_oicr0, float(thr), float(w_midn), float(w_oicr), ptr(sm), ptr(ind), ptr(pl),
+         ptr(losses), ptr(status), stream())
+    ctx.save_for_backward(logits_all, labels, num_proposals, class_logits, proba, pl)
+    ctx.cfg = cfg
+    ctx.set_materialize_grads(False)
+    outs = tuple(losses[i] for i in range(K + 2))
+    ctx.mark_non_differentiable(ind, pl, status)
+    return outs + (ind, pl, status)
+
+  @staticmethod
+  def backward(ctx, *grads):
+    logits_all, labels, num_proposals, class_logits, proba, pl = ctx.saved_tensors
+    C, K, col_r, col_c, col_oicr0, thr, w_midn, w_oicr = ctx.cfg
+    B, P, ld = logits_all.shape
+    g = [x.contiguous() if x is not None else None for x in grads[:K + 2]]
+    d_oicr = [g[1 + k] if k < K else None for k in range(4)]
+    d_all = torch.empty_like(logits_all)
+    call('c2d_loss_head_bwd', ptr(logits_all), ld, ptr(num_proposals), ptr(labels), ptr(class_logits), ptr(proba), ptr(pl),
+         B, P, C, K, col_r, col_c, col_oicr0, float(w_midn), float(w_oicr), ptr(g[0]), ptr(d_oicr[0]), ptr(d_oicr[1]),
+         ptr(d_oicr[2]), ptr(d_oicr[3]), ptr(g[K + 1]), ptr(d_all), stream())
+    return d_all, None, None, None, None, None, None, None
+
+
+def loss_head(logits_all, labels, num_proposals, proposals, class_logits, proba, scores0, num_classes, num_stages, col_r,
+              col_c, col_oicr0, iou_threshold, midn_weight, oicr_weight):
+  """The whole of build_loss from the [B,P,ld] logits (needs num_stages <= 4 and stage k in columns
+  col_oicr0 + k (C+1) ...).  class_logits / proba / scores0: the MIDN outputs (no gradient flows through them here; the
+  MIDN backward is part of this node).  Returns (midn_loss, [oicr_loss_1 .. K], total, proposal_ind [K,B,C],
+  proposal_labels [K,B,P,C+1], status)."""
+  cfg = (int(num_classes), int(num_stages), int(col_r), int(col_c), int(col_oicr0), float(iou_threshold),
+         float(midn_weight), float(oicr_weight))
+  out = _LossHead.apply(logits_all, labels.contiguous(), num_proposals, proposals.contiguous(),
+                        class_logits.detach().contiguous(), proba.detach().contiguous(), scores0.detach().contiguous(), cfg)
+  K = cfg[1]
+  return out[0], list(out[1:1 + K]), out[K + 1], out[K + 2], out[K + 3], out[K + 4]
 
 
 # ---------------------------------------------------------------------------------------------

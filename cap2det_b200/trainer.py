@@ -173,6 +173,7 @@ class TrainStep(object):
     self.world_size = world_size
     self.global_step = 0
     self._pending = []
+    self._one = None                 # cached seed gradient of the total loss
     self.overlap_hooks = True
     if world_size > 1 and hasattr(torch.Tensor, 'register_post_accumulate_grad_hook'):
       # Start the all-reduce of a gradient buffer the moment autograd has finished it: the head's 24 MB buffer
@@ -222,53 +223,18 @@ class TrainStep(object):
     d = tc.learning_rate_decay
     return exponential_decay(self.base_lr, self.global_step, d.decay_steps, d.decay_rate, d.staircase)
 
-  def regularization_loss(self):
-    """sum of slim l2_regularizer terms, scale * sum(w^2) / 2 each (core/training_utils.py:45-50)."""
-    total = None
+  def regularization_loss(self, base=None):
+    """sum of slim l2_regularizer terms, scale * sum(w^2) / 2 each (core/training_utils.py:45-50), added to `base`
+    (a device scalar) when given; None without terms and base."""
+    total = base
     for v, scale in self.reg_terms:
       out = torch.empty((), dtype=torch.float32, device=v.device)
-      call('c2d_l2_loss', ptr(v.data), v.numel(), float(scale), ptr(out), stream())
-      total = out if total is None else total + out
+      if total is None:
+        call('c2d_l2_loss', ptr(v.data), v.numel(), float(scale), ptr(out), stream())
+      else:
+        call('c2d_l2_loss_add', ptr(v.data), v.numel(), float(scale), ptr(total), ptr(out), stream())
+      total = out
     return total
-
-  # ---- the three phases of a step (GraphedTrainStep captures them as separate CUDA graphs when world_size > 1) ----
-  def forward_backward(self, examples):
-    """Forward, losses and the backward of everything that has trainable variables.  With
-    model.split_backward_at_roi the gradient stops at the ROI output (see backward_below_roi)."""
-    model = self.model
-    self.opt.zero_grad()
-    self.opt.lr = self.learning_rate()
-    predictions = model.build_prediction(examples)
-    loss_dict = model.build_loss(predictions, examples)
-    total = None
-    for v in loss_dict.values():
-      total = v if total is None else total + v
-    self._pending = []
-    total.backward()
-    self.last_loss_dict = loss_dict
-    return total.detach()
-
-  def backward_below_roi(self):
-    """The rest of the backward pass: ROI crop / max-pool (and the first stage) from the gradient of the ROI output."""
-    split = getattr(self.model, '_roi_split', None)
-    if split is not None and split[1].grad is not None:
-      split[0].backward(split[1].grad)
-      self.model._roi_split = None
-
-  def reduce_gradients(self):
-    if self.world_size > 1:
-      # gradient buffers whose hook fired are already being reduced (see _reduce_when_ready); reduce the rest
-      started = {id(v) for v, _ in self._pending}
-      c2d_dist.allreduce_sum([v.grad for v in self.model.get_variables_to_train() if v.grad is not None and id(v) not in started])
-      for _, work in self._pending:
-        work.wait()
-      self._pending = []
-
-  def update(self, total):
-    self.opt.step(grad_scale=1.0 / self.world_size)
-    self.global_step += 1
-    reg = self.regularization_loss()
-    return total + reg if reg is not None else total
 
   # ---- the phases of a step (GraphedTrainStep captures them as separate CUDA graphs when world_size > 1) ----
   def forward_backward(self, examples):
@@ -279,11 +245,14 @@ class TrainStep(object):
     self.opt.lr = self.learning_rate()
     predictions = model.build_prediction(examples)
     loss_dict = model.build_loss(predictions, examples)
-    total = None
-    for v in loss_dict.values():
-      total = v if total is None else total + v
+    total = getattr(loss_dict, 'total', None)          # summed on the device by the fused loss head
+    if total is None:
+      for v in loss_dict.values():
+        total = v if total is None else total + v
     self._pending = []
-    total.backward()
+    if self._one is None or self._one.device != total.device:
+      self._one = torch.ones((), dtype=torch.float32, device=total.device)
+    total.backward(self._one)                          # a cached seed gradient: no fill kernel per step
     self.last_loss_dict = loss_dict
     return total.detach()
 
@@ -306,8 +275,7 @@ class TrainStep(object):
   def update(self, total):
     self.opt.step(grad_scale=1.0 / self.world_size)
     self.global_step += 1
-    reg = self.regularization_loss()
-    return total + reg if reg is not None else total
+    return self.regularization_loss(total)
 
   def __call__(self, examples):
     """One step; returns the (device) total loss tensor of this rank (train/trainer.py:55-61)."""

@@ -258,6 +258,27 @@ int c2d_oicr_ce_bwd(const float* proposal_labels, const float* scores1, int ld1,
                     int B, int P, int C, float weight, const float* dloss, float* dscores1, int ldd,
                     c2d_stream_t stream);
 
+/* ---- Fused loss head: models/cap2det_model.py:274-330 (build_loss) over models/utils.py:15-105 ----------
+ * Everything build_loss computes from the [B,P,ld] logits of the concatenated FC layers, all K <= 4 OICR stages per
+ * launch (the stages are independent given the logits: stage k seeds from softmax(stage k-1 logits), stage 0 from
+ * `scores0` = midn_proba_r_given_c or the MIDN scores, [B,P,C] contiguous).  Stage k's logits are the C+1 columns
+ * from col_oicr0 + k (C+1).  class_logits [B,C] = MIDN image logits (c2d_midn_fwd).
+ * Outputs: softmax_ws [(K-1),B,P,C+1] scratch (the scores of stages 0..K-2), proposal_ind [K,B,C] int64,
+ * proposal_labels [K,B,P,C+1], losses [K+2] = {midn_weight * sigmoid CE mean, oicr_weight * stage losses ..., their
+ * sum}, *status as c2d_oicr_assign. */
+int c2d_loss_head_fwd(const float* logits_all, int ld, const int* num_proposals, const float* proposals,
+                      const float* labels, const float* class_logits, const float* scores0, int B, int P, int C, int K,
+                      int col_oicr0, float iou_threshold, float midn_weight, float oicr_weight, float* softmax_ws,
+                      long long* proposal_ind, float* proposal_labels, float* losses, int* status, c2d_stream_t stream);
+/* Gradient of those losses w.r.t. logits_all: d_logits [B,P,ld] is written completely (padding columns zero).
+ * proba [B,P,C] = midn_proba_r_given_c; col_r / col_c = first column of the two MIDN streams.  d_midn, d_oicr0..3,
+ * d_total: device scalars with the upstream gradient of each loss and of their sum (each may be null = 0). */
+int c2d_loss_head_bwd(const float* logits_all, int ld, const int* num_proposals, const float* labels,
+                      const float* class_logits, const float* proba, const float* proposal_labels, int B, int P, int C,
+                      int K, int col_r, int col_c, int col_oicr0, float midn_weight, float oicr_weight,
+                      const float* d_midn, const float* d_oicr0, const float* d_oicr1, const float* d_oicr2,
+                      const float* d_oicr3, const float* d_total, float* d_logits, c2d_stream_t stream);
+
 /* ---- K7: core/builder.py:31-65 (_post_process -> batch_multiclass_non_max_suppression) --
  * boxes [B,P,4]; scores [B,P,C] with row stride lds.  Outputs: num_detections [B] int32,
  * boxes [B,max_total,4], scores [B,max_total], classes [B,max_total] (1-based float, padding
@@ -296,8 +317,15 @@ int c2d_text_classifier_match(const int* token_ids, int B, int T, const float* e
  * accum += g*g ; var -= lr * g * rsqrt(accum)                (tf.train.AdagradOptimizer, accum0 = 0.1) */
 int c2d_adagrad_update(float* var, float* accum, const float* grad, long long n, float lr, float grad_scale,
                        float l2_scale, c2d_stream_t stream);
+/* slim.dropout's keep mask (models/utils.py:176-177): mask[i] = floor(keep_prob + u_i), u_i uniform in [0,1) from
+ * Philox4x32-10 keyed by `seed`; state = two device uint64 {masks drawn so far, 0}, advanced by the kernel itself so
+ * that replays of a captured CUDA graph draw fresh masks.  n = number of mask elements (multiple of 4). */
+int c2d_dropout_keep_mask(unsigned long long* state, unsigned seed, long long n, float keep_prob, float* mask,
+                          c2d_stream_t stream);
 /* slim l2_regularizer loss term: out (device scalar) = scale * sum(w^2) / 2 */
 int c2d_l2_loss(const float* w, long long n, float scale, float* out, c2d_stream_t stream);
+/* out = *base + scale * sum(w^2) / 2 (base: device scalar, may equal out): adds a term to a running total */
+int c2d_l2_loss_add(const float* w, long long n, float scale, const float* base, float* out, c2d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -551,6 +551,92 @@ def test_model_train_step_end_to_end_fp32():
   assert pred['class_labels'] == classes
 
 
+@pytest.mark.parametrize('num_oicr', [1, 3, 4])
+def test_fused_loss_head_matches_op_by_op(num_oicr):
+  """ops.loss_head (one autograd node, all OICR stages per launch) against build_loss run op by op: same losses, bit-equal
+  seeds and soft labels, same gradients; `.total` is the sum of the dict's values."""
+  from cap2det_b200 import synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  B, P = 2, 150
+  rng = np.random.default_rng(70 + num_oicr)
+  fmap = synthetic.make_feature_map(rng, B, 160, 208)
+  props = synthetic.make_proposals(rng, B, P, 160, 208)
+  npr = np.array([P - 20, P], np.int32)
+  props[0, P - 20:] = 0
+  texts = synthetic.make_object_texts(rng, B, classes)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  results = []
+  for fused in (True, False):
+    model = _build_model(20, ('groundtruth_extractor', "label_file: '%s'" % synthetic.write_label_file(d, classes)),
+                         num_oicr=num_oicr)
+    model.fused_loss_head = fused
+    with torch.no_grad():
+      model.fc_weights.mul_(8.0)
+    examples = {F.features_to_crop: dev(fmap), F.num_proposals: dev(npr), F.proposals: dev(props), F.object_texts: texts,
+                F.dropout_keep_mask: dev(keep)}
+    loss = model.build_loss(model.build_prediction(examples), examples)
+    assert (loss.total is not None) == fused
+    total = loss.total if fused else sum(loss.values())
+    if fused:
+      assert abs(float(total) - sum(float(v) for v in loss.values())) <= 1e-6 * abs(float(total))
+    total.backward(torch.ones((), device='cuda'))
+    model.raise_if_assert_failed()
+    results.append(({k: float(v) for k, v in loss.items()}, model.last_oicr_assignments,
+                    model.fc_weights.grad.cpu().numpy(), model.fc_biases.grad.cpu().numpy()))
+  (la, auxa, wa, ba), (lb, auxb, wb, bb) = results
+  assert sorted(la) == sorted(lb) and len(la) == 1 + num_oicr
+  for k in la:
+    assert abs(la[k] - lb[k]) <= 2e-6 * abs(lb[k]), k
+  for (ia, pa), (ib, pb) in zip(auxa, auxb):
+    np.testing.assert_array_equal(ia.cpu().numpy(), ib.cpu().numpy())
+    np.testing.assert_array_equal(pa.cpu().numpy(), pb.cpu().numpy())
+  assert rel_err(wa, wb) < 1e-5 and rel_err(ba, bb) < 1e-5
+
+
+def test_dropout_keep_mask_generator():
+  """ops.dropout_keep_mask: floor(keep_prob + u) in {0, 1}, the right keep rate, a fresh mask per call (the kernel
+  advances its own device counter, also under graph replay), reproducible from (seed, counter)."""
+  from cap2det_b200 import ops
+  state = torch.zeros((2,), dtype=torch.int64, device='cuda')
+  m1 = ops.dropout_keep_mask(state, 1234, (4000, 1024), 0.5)
+  m2 = ops.dropout_keep_mask(state, 1234, (4000, 1024), 0.5)
+  assert state.cpu().tolist() == [2, 0]
+  assert set(torch.unique(m1).cpu().tolist()) == {0.0, 1.0}
+  assert abs(float(m1.mean()) - 0.5) < 2e-3 and abs(float(m2.mean()) - 0.5) < 2e-3
+  assert 0.45 < float((m1 != m2).float().mean()) < 0.55            # independent draws
+  assert abs(float(m1.mean(dim=0).std()) - 0.5 / np.sqrt(4000)) < 2e-3   # columns are not correlated
+  state.zero_()
+  np.testing.assert_array_equal(ops.dropout_keep_mask(state, 1234, (4000, 1024), 0.5).cpu().numpy(), m1.cpu().numpy())
+  state.zero_()
+  assert float((ops.dropout_keep_mask(state, 99, (4000, 1024), 0.5) != m1).float().mean()) > 0.45     # another seed
+  m8 = ops.dropout_keep_mask(state, 5, (1000, 1024), 0.8)
+  assert abs(float(m8.mean()) - 0.8) < 3e-3
+  # replays of one captured graph draw different masks
+  st = torch.zeros((2,), dtype=torch.int64, device='cuda')
+  side = torch.cuda.Stream()
+  with torch.cuda.stream(side):
+    ops.dropout_keep_mask(st, 7, (256, 1024), 0.5)
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=side):
+      out = ops.dropout_keep_mask(st, 7, (256, 1024), 0.5)
+    g.replay(); torch.cuda.synchronize(); a = out.clone()
+    g.replay(); torch.cuda.synchronize(); b = out.clone()
+  assert float((a != b).float().mean()) > 0.45 and int(st[0]) == 3
+
+
+def test_l2_loss_add():
+  from cap2det_b200.capi import call, ptr, stream
+  w = dev(np.random.default_rng(3).standard_normal(5000).astype(np.float32))
+  base = torch.full((), 2.5, device='cuda')
+  out = torch.empty((), device='cuda')
+  call('c2d_l2_loss_add', ptr(w), w.numel(), 1e-3, ptr(base), ptr(out), stream())
+  want = 2.5 + 1e-3 * float((w.double() ** 2).sum()) / 2
+  assert abs(float(out) - want) < 1e-5 * want
+
+
 def test_model_multiscale_eval_and_errors():
   from cap2det_b200 import synthetic, config, cap2det_model
   from cap2det_b200.standard_fields import InputDataFields as F
