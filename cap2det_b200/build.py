@@ -34,37 +34,61 @@ def _fingerprint():
   return h.hexdigest()
 
 
-def build_library(force=False, verbose=False):
-  """Compiles every .cu under csrc/ and links the shared library.  Returns its path."""
-  os.makedirs(LIB_DIR, exist_ok=True)
+def _up_to_date(fp):
   stamp = os.path.join(LIB_DIR, 'build.stamp')
-  fp = _fingerprint()
-  if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp):
+  if os.path.exists(LIB_PATH) and os.path.exists(stamp):
     with open(stamp) as fid:
-      if fid.read().strip() == fp:
-        return LIB_PATH
+      return fid.read().strip() == fp
+  return False
+
+
+def build_library(force=False, verbose=False):
+  """Compiles every .cu under csrc/ and links the shared library.  Returns its path.
+
+  Safe under torchrun: an exclusive file lock serialises the ranks of one node (the first one builds, the others find
+  the stamp up to date), objects are compiled into a private directory and the library and its stamp are moved into
+  place with os.replace(), so no process can dlopen a half-written file."""
+  import fcntl
+  import shutil
+  import tempfile
+  os.makedirs(LIB_DIR, exist_ok=True)
+  fp = _fingerprint()
+  if not force and _up_to_date(fp):
+    return LIB_PATH
   if not os.path.exists(NVCC):
     raise RuntimeError('nvcc not found at %s and no up-to-date %s' % (NVCC, LIB_PATH))
-  objs = []
+  with open(os.path.join(LIB_DIR, '.build.lock'), 'w') as lock:
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+      if not force and _up_to_date(fp):          # another rank built it while this one waited for the lock
+        return LIB_PATH
+      tmp = tempfile.mkdtemp(prefix='.build-', dir=LIB_DIR)
+      try:
+        def compile_one(src):
+          obj = os.path.join(tmp, src[:-3] + '.o')
+          cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+          r = subprocess.run(cmd, capture_output=True, text=True)
+          if r.returncode != 0:
+            raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
+          if verbose:
+            sys.stderr.write(r.stderr)
+          return obj
 
-  def compile_one(src):
-    obj = os.path.join(LIB_DIR, src[:-3] + '.o')
-    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-      raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
-    if verbose:
-      sys.stderr.write(r.stderr)
-    return obj
-
-  with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
-    objs = list(ex.map(compile_one, _sources()))
-  cmd = [NVCC, '-shared', '-o', LIB_PATH] + objs + ['-lcudart']
-  r = subprocess.run(cmd, capture_output=True, text=True)
-  if r.returncode != 0:
-    raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
-  with open(stamp, 'w') as fid:
-    fid.write(fp)
+        with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
+          objs = list(ex.map(compile_one, _sources()))
+        tmp_lib = os.path.join(tmp, 'libcap2det_b200.so')
+        r = subprocess.run([NVCC, '-shared', '-o', tmp_lib] + objs + ['-lcudart'], capture_output=True, text=True)
+        if r.returncode != 0:
+          raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
+        tmp_stamp = os.path.join(tmp, 'build.stamp')
+        with open(tmp_stamp, 'w') as fid:
+          fid.write(fp)
+        os.replace(tmp_lib, LIB_PATH)
+        os.replace(tmp_stamp, os.path.join(LIB_DIR, 'build.stamp'))
+      finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    finally:
+      fcntl.flock(lock, fcntl.LOCK_UN)
   return LIB_PATH
 
 

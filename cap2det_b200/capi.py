@@ -51,6 +51,9 @@ SIGNATURES = {
     'c2d_head_mixed5_bwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p]),
     'c2d_head_mixed5_bwd_fold': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p, _p, _p, _p]),
     'c2d_roi_crop_maxpool_bwd_codes_fold': (_c_int, [_c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _c_int, _p, _p]),
+    'c2d_roi_bwd_tiles_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    'c2d_roi_crop_maxpool_bwd_tiles': (_c_int, [_c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _c_int,
+                                                _p, _p, _c_int, _p, _c_sz, _p, _p]),
     'c2d_resize_bilinear': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _p]),
     'c2d_image_flip_left_right': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _p, _p]),
     'c2d_box_scale_batch': (_c_int, [_p, _p, _c_int, _c_int, _c_int, _c_int, _p, _p]),

@@ -21,28 +21,39 @@ struct RoiCoords {
   int valid[2][kMaxCrop];
 };
 
+// Sample coordinate i of one axis, with the un-fused fp32 rounding of the TF CPU kernel.  lo_n / hi_n = normalised
+// box edges of that axis.  Returns false for a sample outside the map (extrapolation value 0, no gradient).
+__device__ __forceinline__ bool roi_sample_coord(float lo_n, float hi_n, int size, int crop, int i, int& lo, int& hi,
+                                                 float& lerp) {
+  const float sm1 = (float)(size - 1);
+  float coord;
+  if (crop > 1) {
+    float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi_n, lo_n), sm1), (float)(crop - 1));
+    coord = __fadd_rn(__fmul_rn(lo_n, sm1), __fmul_rn((float)i, scale));
+  } else {
+    coord = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo_n, hi_n)), sm1);
+  }
+  const bool valid = !(coord < 0.0f || coord > sm1);
+  if (!valid) coord = 0.0f;
+  const float fl = floorf(coord);
+  lo = (int)fl;
+  hi = (int)ceilf(coord);
+  lerp = __fsub_rn(coord, fl);
+  return valid;
+}
+
 __device__ __forceinline__ void roi_setup_coords(RoiCoords& sc, float4 box, int Hf, int Wf, int crop) {
   // threads [0,crop) -> y samples, threads [32, 32+crop) -> x samples
   int t = threadIdx.x;
   int axis = t >> 5, i = t & 31;
   if (axis < 2 && i < crop) {
-    int size = axis == 0 ? Hf : Wf;
-    float lo = axis == 0 ? box.x : box.y;
-    float hi = axis == 0 ? box.z : box.w;
-    float sm1 = (float)(size - 1);
-    float coord;
-    if (crop > 1) {
-      float scale = __fdiv_rn(__fmul_rn(__fsub_rn(hi, lo), sm1), (float)(crop - 1));
-      coord = __fadd_rn(__fmul_rn(lo, sm1), __fmul_rn((float)i, scale));
-    } else {
-      coord = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(lo, hi)), sm1);
-    }
-    bool valid = !(coord < 0.0f || coord > sm1);
-    if (!valid) coord = 0.0f;
-    float fl = floorf(coord);
-    sc.lo[axis][i] = (int)fl;
-    sc.hi[axis][i] = (int)ceilf(coord);
-    sc.lerp[axis][i] = __fsub_rn(coord, fl);
+    int lo, hi;
+    float lerp;
+    const bool valid = roi_sample_coord(axis == 0 ? box.x : box.y, axis == 0 ? box.z : box.w, axis == 0 ? Hf : Wf,
+                                        crop, i, lo, hi, lerp);
+    sc.lo[axis][i] = lo;
+    sc.hi[axis][i] = hi;
+    sc.lerp[axis][i] = lerp;
     sc.valid[axis][i] = valid ? 1 : 0;
   }
 }
@@ -564,6 +575,404 @@ roi_crop_maxpool_bwd_codes_kernel(int Hf, int Wf, int Cf, const float4* __restri
 // per pixel, 1.48 GB) was built, verified and measured at 0.90 ms against 0.61 ms (406 M warp instructions, 144
 // registers): removed again, see profiles/r2_roi_kernels.md section 3 and commit 10c67a5 for the code.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// K1', tile-owner backward (round 2, second half).
+//
+// The per-proposal scatter above sits on the L2's fp32 add rate (3.2 GB of addends per step at ~6 TB/s,
+// profiles/r2_roi_kernels.md section 3); every feature pixel is touched by ~140 proposals, so the way below that
+// roof is to add ACROSS proposals on chip.  The feature map is cut into tiles of kTileR x kTileS pixels.  A tile OWNS
+// the crop samples whose top-left bilinear corner lies in it; a warp keeps fp32 accumulators for the tile's
+// (kTileR+1) x (kTileS+1) pixel support x 64 channels in shared memory, laid out [pixel][2][lane] so that a lane's
+// accumulators live in ITS bank whatever pixel its channel routes to -- plain load / FFMA / store, no atomics, no
+// conflicts, although every channel picks its own sample (arg-max code) and therefore its own pixels.  A warp walks
+// the proposals that own samples in its tile, and of each only the pooling bins with an owned sample; the sample a
+// channel selected indexes a 28-entry per-proposal table {accumulator offset, 1 - lerp, lerp} (zero weights for
+// samples another tile owns), and wx * (wy * g) keeps CropAndResizeGradImage's operation order.  The accumulators
+// are flushed ONCE per work item with red.global.add.v2.f32: ~50 MB of addends per step instead of 3.2 GB.
+//
+// Work list (three small kernels' worth of set-up, two launches): roi_tiles_coords_kernel writes every proposal's
+// 14 + 14 sample records {floor index, lerp} (same arithmetic as the forward) and, per tile row / column, the bit
+// mask of the samples that fall into it; roi_tiles_bin_kernel (one CTA per tile) lists, in proposal order, the
+// proposals of each tile and cuts the list into segments of ~kSegWork work units (4 per bin in range + 8 per
+// proposal).  A work item of the main kernel = (segment, 64-channel chunk), pulled from a device counter by persistent
+// one-warp CTAs; operands of the NEXT proposal are prefetched into L2 while the current one is accumulated.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileR = 4, kTileS = 8;
+constexpr int kTilePx = (kTileR + 1) * (kTileS + 1);
+constexpr int kTileRowStride = (kTileS + 1) * 64;      // floats between accumulator rows
+constexpr int kSegWork = 1024;
+constexpr int kPairWorkMax = 4 * 49 + 8;
+constexpr int kMaxTilesTotal = 1024;                   // prefix of the segment counts lives in shared memory
+constexpr int kTileCrop = 14;
+constexpr int kMaxTilesAxis = 32;                      // tile rows / columns per image (mask table width)
+
+// One warp per proposal: lanes 0..13 = y samples, 16..29 = x samples.
+__global__ void __launch_bounds__(256)
+roi_tiles_coords_kernel(int Hf, int Wf, const float4* __restrict__ boxes, int n_rois, int tiles_y, int tiles_x,
+                        int2* __restrict__ coords, unsigned short* __restrict__ masks) {
+  const int roi = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (roi >= n_rois) return;
+  const float4 box = boxes[roi];
+  const int i = lane & 15, axis = lane >> 4;
+  int lo = -1, hi;
+  float l = 0.f;
+  if (i < kTileCrop) {
+    const int size = axis ? Wf : Hf;
+    bool v = roi_sample_coord(axis ? box.y : box.x, axis ? box.w : box.z, size, kTileCrop, i, lo, hi, l);
+    v = v && lo >= 0 && lo < size;                       // (a NaN box passes the range test of the TF kernel)
+    if (!v) lo = -1;
+  }
+  coords[(size_t)roi * 32 + lane] = make_int2(lo, __float_as_int(l));
+  const int ti = lo < 0 ? -1 : (axis ? lo / kTileS : lo / kTileR);
+  const int nt = tiles_y > tiles_x ? tiles_y : tiles_x;
+  unsigned mine = 0;
+  for (int r = 0; r < nt; ++r) {
+    const unsigned m = __ballot_sync(0xffffffffu, ti == r);
+    if (lane == r) mine = m;
+  }
+  // masks[roi][0][r] = y samples in tile row r, masks[roi][1][c] = x samples in tile column c
+  if (lane < tiles_y) masks[((size_t)roi * 2) * kMaxTilesAxis + lane] = (unsigned short)(mine & 0x3fffu);
+  if (lane < tiles_x) masks[((size_t)roi * 2 + 1) * kMaxTilesAxis + lane] = (unsigned short)((mine >> 16) & 0x3fffu);
+}
+
+__global__ void __launch_bounds__(256)
+roi_tiles_bin_kernel(const unsigned short* __restrict__ masks, int P, int tiles_y, int tiles_x, int seg_max1,
+                     int* __restrict__ ctrl, int* __restrict__ nseg, int* __restrict__ seg_start, int* __restrict__ list) {
+  const int tile = blockIdx.x, tpi = tiles_y * tiles_x;
+  const int b = tile / tpi, tt = tile - b * tpi;
+  const int tr = tt / tiles_x, tc = tt - tr * tiles_x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __shared__ int warp_n[8], warp_w[8], run_n, run_w;
+  if (tile == 0 && threadIdx.x == 0) ctrl[0] = 0;
+  if (threadIdx.x == 0) { run_n = 0; run_w = 0; }
+  __syncthreads();
+  int* my_list = list + (size_t)tile * P;
+  int* my_seg = seg_start + (size_t)tile * seg_max1;
+  for (int c0 = 0; c0 < P; c0 += 256) {
+    const int p = c0 + threadIdx.x;
+    int work = 0;
+    if (p < P) {
+      const size_t roi = (size_t)b * P + p;
+      const unsigned my = masks[(roi * 2) * kMaxTilesAxis + tr], mx = masks[(roi * 2 + 1) * kMaxTilesAxis + tc];
+      if (my != 0 && mx != 0) {
+        const int nby = ((31 - __clz(my)) >> 1) - ((__ffs(my) - 1) >> 1) + 1;
+        const int nbx = ((31 - __clz(mx)) >> 1) - ((__ffs(mx) - 1) >> 1) + 1;
+        work = 4 * nby * nbx + 8;
+      }
+    }
+    const int flag = work > 0 ? 1 : 0;
+    int sn = flag, sw = work;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, sn, o), c = __shfl_up_sync(0xffffffffu, sw, o);
+      if (lane >= o) { sn += a; sw += c; }
+    }
+    if (lane == 31) { warp_n[warp] = sn; warp_w[warp] = sw; }
+    __syncthreads();
+    int bn = run_n, bw = run_w;
+    for (int w = 0; w < warp; ++w) { bn += warp_n[w]; bw += warp_w[w]; }
+    if (flag) {
+      const int pos = bn + sn - 1, incl = bw + sw, excl = incl - work;
+      my_list[pos] = p;
+      if (incl / kSegWork > excl / kSegWork) my_seg[incl / kSegWork] = pos + 1;   // this pair ends its segment
+    }
+    __syncthreads();
+    if (threadIdx.x == 255) { run_n = bn + sn; run_w = bw + sw; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int total = run_w, ns = total > 0 ? (total - 1) / kSegWork + 1 : 0;
+    my_seg[0] = 0;
+    my_seg[ns] = run_n;
+    nseg[tile] = ns;
+  }
+}
+
+template <typename GradT> struct RoiRaw;
+template <> struct RoiRaw<__nv_bfloat16> {
+  typedef unsigned type;
+  static __device__ __forceinline__ unsigned ld(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
+  static __device__ __forceinline__ float lo(unsigned u) { return __uint_as_float(u << 16); }
+  static __device__ __forceinline__ float hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
+};
+template <> struct RoiRaw<float> {
+  typedef float2 type;
+  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ float lo(float2 u) { return u.x; }
+  static __device__ __forceinline__ float hi(float2 u) { return u.y; }
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Raw operands of one pooling bin for this lane's two channels (converted only when the bin is processed, so the
+// loads of the bins ahead stay in flight): gradient, arg-max code byte and -- FOLD -- code / output gradient of the
+// up to four Mixed_5a max-pool windows that contain the bin.
+template <typename GradT, bool FOLD>
+struct RoiBinLoad {
+  typename RoiRaw<GradT>::type g;
+  unsigned code;
+  unsigned pc[FOLD ? 4 : 1];
+  typename RoiRaw<GradT>::type dp[FOLD ? 4 : 1];
+};
+
+// Per (proposal, lane) operand pointers.
+template <typename GradT>
+struct RoiPairPtr {
+  const GradT* g;               // dout[roi, 0, 0, c0]
+  const unsigned char* code;    // codes[roi, 0, 0, quad(c0)]
+  const unsigned char* pc;      // pool_codes[roi, 0, c0]
+  const GradT* dp;              // pool_grad[roi * 16, c0]
+};
+
+template <typename GradT, bool FOLD, int CF>
+__device__ __forceinline__ void roi_tiles_load_bin(RoiBinLoad<GradT, FOLD>& L, const RoiPairPtr<GradT>& pp, int by, int bx,
+                                                   int pool_ld) {
+  const int bi = by * 7 + bx;
+  L.g = RoiRaw<GradT>::ld(pp.g + bi * CF);
+  L.code = __ldg(pp.code + bi * (CF / 4));
+  if (FOLD) {
+    // position (by, bx) of the 7x7 tensor lies in window by/2 (tap 1, even) or in (by-1)/2 (tap 2) and (by+1)/2 (tap 0)
+    const int o = (by >> 1) * 4 + (bx >> 1);
+    const unsigned char* pc = pp.pc + o * CF;
+    const GradT* dp = pp.dp + o * pool_ld;
+    L.pc[0] = __ldg(reinterpret_cast<const unsigned short*>(pc));
+    L.dp[0] = RoiRaw<GradT>::ld(dp);
+    if (bx & 1) {
+      L.pc[1] = __ldg(reinterpret_cast<const unsigned short*>(pc + CF));
+      L.dp[1] = RoiRaw<GradT>::ld(dp + pool_ld);
+    }
+    if (by & 1) {
+      L.pc[2] = __ldg(reinterpret_cast<const unsigned short*>(pc + 4 * CF));
+      L.dp[2] = RoiRaw<GradT>::ld(dp + 4 * pool_ld);
+      if (bx & 1) {
+        L.pc[3] = __ldg(reinterpret_cast<const unsigned short*>(pc + 5 * CF));
+        L.dp[3] = RoiRaw<GradT>::ld(dp + 5 * pool_ld);
+      }
+    }
+  }
+}
+
+template <typename GradT>
+__device__ __forceinline__ void roi_tiles_fold(unsigned pc, typename RoiRaw<GradT>::type dp, unsigned tap, float& g0, float& g1) {
+  g0 += (pc & 0xffu) == tap ? RoiRaw<GradT>::lo(dp) : 0.f;
+  g1 += (pc >> 8) == tap ? RoiRaw<GradT>::hi(dp) : 0.f;
+}
+
+// One bin.  rec_s = shared-memory address of the proposal's sample table: [0..14) y samples, [16..30) x samples, each
+// {accumulator byte offset, 1 - lerp, lerp, -} (all zero for a sample another tile owns); the four entries of the bin
+// are warp-uniform (broadcast loads) and each channel SELECTS by its arg-max bits; acc_s = shared-memory address of
+// this lane's accumulator column.  The whole kernel keeps ONE copy of this code per operand buffer (two): a version
+// unrolled over the bins of a row ran out of instruction cache (no_instruction stalls, profiles/r2_roi_kernels.md).
+template <typename GradT, bool FOLD>
+__device__ __forceinline__ void roi_tiles_bin(const RoiBinLoad<GradT, FOLD>& L, int by, int bx, unsigned rec_s, unsigned acc_s,
+                                              int sh0) {
+  float g0 = RoiRaw<GradT>::lo(L.g), g1 = RoiRaw<GradT>::hi(L.g);
+  if (FOLD) {
+    const unsigned ty = (by & 1) ? 2u : 1u, tx = (bx & 1) ? 2u : 1u;
+    roi_tiles_fold<GradT>(L.pc[0], L.dp[0], ty * 3 + tx, g0, g1);
+    if (bx & 1) roi_tiles_fold<GradT>(L.pc[1], L.dp[1], ty * 3, g0, g1);
+    if (by & 1) {
+      roi_tiles_fold<GradT>(L.pc[2], L.dp[2], tx, g0, g1);
+      if (bx & 1) roi_tiles_fold<GradT>(L.pc[3], L.dp[3], 0u, g0, g1);
+    }
+  }
+  const unsigned c = L.code >> sh0;                     // bit 0 / 1: column / row of channel 0's sample, bits 2 / 3: channel 1
+  const unsigned ry_s = rec_s + by * 32, rx_s = rec_s + 256 + bx * 32;
+  const float4 yA = lds128(ry_s), yB = lds128(ry_s + 16), xA = lds128(rx_s), xB = lds128(rx_s + 16);
+  const bool px0 = (c & 1u) != 0, py0 = (c & 2u) != 0, px1 = (c & 4u) != 0, py1 = (c & 8u) != 0;
+  const unsigned a0 = acc_s + __float_as_uint(py0 ? yB.x : yA.x) + __float_as_uint(px0 ? xB.x : xA.x);
+  const unsigned a1 = acc_s + 128u + __float_as_uint(py1 ? yB.x : yA.x) + __float_as_uint(px1 ? xB.x : xA.x);
+  const float t0 = (py0 ? yB.y : yA.y) * g0, b0 = (py0 ? yB.z : yA.z) * g0;           // dtop, dbottom
+  const float t1 = (py1 ? yB.y : yA.y) * g1, b1 = (py1 ? yB.z : yA.z) * g1;
+  const float l0 = px0 ? xB.y : xA.y, r0 = px0 ? xB.z : xA.z, l1 = px1 ? xB.y : xA.y, r1 = px1 ? xB.z : xA.z;
+  float v00, v01, v02, v03, v10, v11, v12, v13;
+  constexpr int RS = kTileRowStride * 4;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v00) : "r"(a0));
+  asm volatile("ld.shared.f32 %0, [%1+256];" : "=f"(v01) : "r"(a0));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v02) : "r"(a0), "n"(RS));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v03) : "r"(a0), "n"(RS + 256));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v10) : "r"(a1));
+  asm volatile("ld.shared.f32 %0, [%1+256];" : "=f"(v11) : "r"(a1));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v12) : "r"(a1), "n"(RS));
+  asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v13) : "r"(a1), "n"(RS + 256));
+  v00 = fmaf(l0, t0, v00); v01 = fmaf(r0, t0, v01); v02 = fmaf(l0, b0, v02); v03 = fmaf(r0, b0, v03);
+  v10 = fmaf(l1, t1, v10); v11 = fmaf(r1, t1, v11); v12 = fmaf(l1, b1, v12); v13 = fmaf(r1, b1, v13);
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0), "f"(v00) : "memory");
+  asm volatile("st.shared.f32 [%0+256], %1;" ::"r"(a0), "f"(v01) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(a0), "f"(v02), "n"(RS) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(a0), "f"(v03), "n"(RS + 256) : "memory");
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(a1), "f"(v10) : "memory");
+  asm volatile("st.shared.f32 [%0+256], %1;" ::"r"(a1), "f"(v11) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(a1), "f"(v12), "n"(RS) : "memory");
+  asm volatile("st.shared.f32 [%0+%2], %1;" ::"r"(a1), "f"(v13), "n"(RS + 256) : "memory");
+}
+
+__device__ __forceinline__ void roi_tiles_next_bin(int& by, int& bx, int bx_lo, int bx_hi) {
+  if (++bx > bx_hi) { bx = bx_lo; ++by; }
+}
+
+template <typename GradT, bool FOLD, int CF>
+__global__ void __launch_bounds__(32)
+roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int seg_max1, int l2_prefetch,
+                     const int* __restrict__ nseg, const int* __restrict__ seg_start, const int* __restrict__ list,
+                     const int2* __restrict__ coords, int* __restrict__ ctrl, const unsigned char* __restrict__ codes,
+                     const GradT* __restrict__ dout, const unsigned char* __restrict__ pool_codes,
+                     const GradT* __restrict__ pool_grad, int pool_ld, float* __restrict__ dfmap) {
+  extern __shared__ __align__(16) unsigned char roi_tiles_smem[];
+  float* acc = reinterpret_cast<float*>(roi_tiles_smem);                    // [kTilePx][2][32]
+  float4* rec = reinterpret_cast<float4*>(acc + kTilePx * 64);              // [32] sample table of the current proposal
+  int* pref = reinterpret_cast<int*>(rec + 32);                             // [T + 1]
+  const int lane = threadIdx.x;
+  constexpr int n_chunks = CF / 64;
+  const int tpi = tiles_y * tiles_x;
+  int run = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane, v = t < T ? nseg[t] : 0;
+    int sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int a = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += a; }
+    if (t < T) pref[t] = run + sc - v;
+    run += __shfl_sync(0xffffffffu, sc, 31);
+  }
+  if (lane == 0) pref[T] = run;
+  for (int i = lane; i < kTilePx * 64; i += 32) acc[i] = 0.f;
+  __syncwarp();
+  const int total_items = run * n_chunks;
+  const int sh0 = (lane & 1) * 4;                       // this lane's two channels inside its quad's code byte
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc) + lane * 4;
+  const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
+  const int pf_r = lane >> 3, pf_c = lane & 7;          // L2 prefetch: lane -> (bin row, bin column) of a 4 x 8 block
+  while (true) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(ctrl, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total_items) break;
+    const int sg = item / n_chunks, chunk = item - sg * n_chunks;
+    int tlo = 0, thi = T;
+    while (thi - tlo > 1) { const int mid = (tlo + thi) >> 1; if (pref[mid] <= sg) tlo = mid; else thi = mid; }
+    const int tile = tlo, s = sg - pref[tile];
+    const int b = tile / tpi, tt = tile - b * tpi;
+    const int ty0 = (tt / tiles_x) * kTileR, tx0 = (tt % tiles_x) * kTileS;
+    const int i0 = seg_start[(size_t)tile * seg_max1 + s], i1 = seg_start[(size_t)tile * seg_max1 + s + 1];
+    const int* my_list = list + (size_t)tile * P;
+    const int c0 = chunk * 64 + 2 * lane;
+    const int t0rel = lane < 16 ? ty0 : tx0, ext = lane < 16 ? kTileR : kTileS;
+    const int off_unit = lane < 16 ? kTileRowStride * 4 : 256;
+    const unsigned roi_base = (unsigned)(b * P);
+    int p0 = i0 < i1 ? my_list[i0] : 0, p1 = i0 + 1 < i1 ? my_list[i0 + 1] : 0;
+    int2 rec0 = coords[(size_t)(roi_base + p0) * 32 + lane];
+    for (int i = i0; i < i1; ++i) {
+      const int p2 = i + 2 < i1 ? my_list[i + 2] : 0;
+      const int2 rec1 = coords[(size_t)(roi_base + p1) * 32 + lane];
+      const unsigned roi = roi_base + p0;
+      const int rel = rec0.x - t0rel;
+      const bool own = rec0.x >= 0 && (unsigned)rel < (unsigned)ext;
+      const unsigned m = __ballot_sync(0xffffffffu, own);
+      const unsigned my = m & 0x3fffu, mx = (m >> 16) & 0x3fffu;
+      if (my != 0 && mx != 0) {
+        __syncwarp();
+        const float lerp = __int_as_float(rec0.y);
+        rec[lane] = own ? make_float4(__int_as_float(rel * off_unit), 1.0f - lerp, lerp, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int by_lo = (__ffs(my) - 1) >> 1, by_hi = (31 - __clz(my)) >> 1;
+        const int bx_lo = (__ffs(mx) - 1) >> 1, bx_hi = (31 - __clz(mx)) >> 1;
+        const int nb = (by_hi - by_lo + 1) * (bx_hi - bx_lo + 1);
+        RoiPairPtr<GradT> pp;
+        pp.g = dout + (size_t)roi * (49 * CF) + c0;
+        pp.code = codes + (size_t)roi * (49 * (CF / 4)) + (c0 >> 2);
+        pp.pc = FOLD ? pool_codes + (size_t)roi * (16 * CF) + c0 : nullptr;
+        pp.dp = FOLD ? pool_grad + (size_t)roi * 16 * pool_ld + c0 : nullptr;
+        RoiBinLoad<GradT, FOLD> La, Lb;
+        int by = by_lo, bx = bx_lo, lby = by_lo, lbx = bx_lo;        // accumulate position / load position (2 bins ahead)
+        roi_tiles_load_bin<GradT, FOLD, CF>(La, pp, lby, lbx, pool_ld);
+        roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
+        if (nb > 1) roi_tiles_load_bin<GradT, FOLD, CF>(Lb, pp, lby, lbx, pool_ld);
+        roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
+        if (l2_prefetch && i + 1 < i1) {
+          // operands of the next proposal of the list -> L2 (its demand loads then see L2 latency, not DRAM latency)
+          const int rel1 = rec1.x - t0rel;
+          const unsigned m1 = __ballot_sync(0xffffffffu, rec1.x >= 0 && (unsigned)rel1 < (unsigned)ext);
+          const unsigned my1 = m1 & 0x3fffu, mx1 = (m1 >> 16) & 0x3fffu;
+          if (my1 != 0 && mx1 != 0) {
+            const int ylo = (__ffs(my1) - 1) >> 1, yhi = (31 - __clz(my1)) >> 1;
+            const int xlo = (__ffs(mx1) - 1) >> 1, xhi = (31 - __clz(mx1)) >> 1;
+            const unsigned roi1 = roi_base + p1;
+            const int cb = chunk * 64;
+            const int c = xlo + pf_c;
+            for (int r = ylo + pf_r; r <= yhi; r += 4)
+              if (c <= xhi) {
+                prefetch_l2(dout + ((size_t)roi1 * 49 + r * 7 + c) * CF + cb);
+                prefetch_l2(codes + ((size_t)roi1 * 49 + r * 7 + c) * (CF / 4) + (cb >> 2));
+              }
+            if (FOLD && lane < 16) {
+              const int oy = lane >> 2, ox = lane & 3;
+              if (oy >= (ylo >> 1) && oy <= ((yhi + 1) >> 1) && ox >= (xlo >> 1) && ox <= ((xhi + 1) >> 1)) {
+                prefetch_l2(pool_codes + ((size_t)roi1 * 16 + lane) * CF + cb);
+                prefetch_l2(pool_grad + ((size_t)roi1 * 16 + lane) * pool_ld + cb);
+              }
+            }
+          }
+        }
+        __syncwarp();
+        for (int j = 0; j < nb; j += 2) {
+          roi_tiles_bin<GradT, FOLD>(La, by, bx, rec_s, acc_s, sh0);
+          roi_tiles_next_bin(by, bx, bx_lo, bx_hi);
+          if (j + 2 < nb) roi_tiles_load_bin<GradT, FOLD, CF>(La, pp, lby, lbx, pool_ld);
+          roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
+          if (j + 1 >= nb) break;
+          roi_tiles_bin<GradT, FOLD>(Lb, by, bx, rec_s, acc_s, sh0);
+          roi_tiles_next_bin(by, bx, bx_lo, bx_hi);
+          if (j + 3 < nb) roi_tiles_load_bin<GradT, FOLD, CF>(Lb, pp, lby, lbx, pool_ld);
+          roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
+        }
+      }
+      p0 = p1; p1 = p2; rec0 = rec1;
+    }
+    // flush the tile's support once (its last row / column also belongs to the neighbouring tiles' supports)
+    __syncwarp();
+    float* dimg = dfmap + (size_t)b * Hf * Wf * CF + c0;
+    for (int r = 0; r <= kTileR; ++r) {
+      const int y = ty0 + r;
+#pragma unroll
+      for (int c = 0; c <= kTileS; ++c) {
+        const int x = tx0 + c, px = r * (kTileS + 1) + c;
+        const float v0 = acc[px * 64 + lane], v1 = acc[px * 64 + 32 + lane];
+        acc[px * 64 + lane] = 0.f; acc[px * 64 + 32 + lane] = 0.f;
+        if (y < Hf && x < Wf && (v0 != 0.f || v1 != 0.f))
+          atomicAdd(reinterpret_cast<float2*>(dimg + ((size_t)y * Wf + x) * CF), make_float2(v0, v1));
+      }
+    }
+    __syncwarp();
+  }
+}
+
+
+struct RoiTilesPlan {
+  int tiles_y, tiles_x, T, seg_max1;
+  size_t off_nseg, off_seg, off_list, off_coords, off_masks, bytes;
+};
+static RoiTilesPlan roi_tiles_plan(int B, int Hf, int Wf, int P) {
+  RoiTilesPlan pl;
+  pl.tiles_y = cdiv(Hf, kTileR); pl.tiles_x = cdiv(Wf, kTileS);
+  pl.T = B * pl.tiles_y * pl.tiles_x;
+  pl.seg_max1 = (int)(((long long)P * kPairWorkMax) / kSegWork) + 3;
+  const size_t n_rois = (size_t)B * (P > 0 ? P : 1);
+  size_t o = 64;                                           // control words
+  pl.off_nseg = o; o += (size_t)pl.T * 4;
+  pl.off_seg = o; o += (size_t)pl.T * pl.seg_max1 * 4;
+  pl.off_list = o; o += (size_t)pl.T * (P > 0 ? P : 1) * 4;
+  o = (o + 15) & ~(size_t)15;
+  pl.off_coords = o; o += n_rois * 32 * sizeof(int2);
+  pl.off_masks = o; o += n_rois * 2 * kMaxTilesAxis * sizeof(unsigned short);
+  pl.bytes = o;
+  return pl;
+}
+
+
 static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k, int pool_s) {
   C2D_CHECK_ARG(B >= 0 && P >= 0 && Hf >= 1 && Wf >= 1, "roi: bad shape B=%d P=%d Hf=%d Wf=%d", B, P, Hf, Wf);
   C2D_CHECK_ARG(Cf >= 4 && Cf % 4 == 0, "roi: feature depth %d must be a multiple of 4", Cf);
@@ -573,6 +982,70 @@ static int roi_check(int B, int Hf, int Wf, int Cf, int P, int crop, int pool_k,
     return C2D_ERR_UNSUPPORTED;
   }
   return C2D_OK;
+}
+
+static bool roi_tiles_supported(int B, int Hf, int Wf, int Cf, int P, int crop) {
+  if (crop != kTileCrop || !(Cf == 64 || Cf == 128 || Cf == 576) || B <= 0 || P <= 0) return false;   // instantiated depths
+  if (cdiv(Hf, kTileR) > kMaxTilesAxis || cdiv(Wf, kTileS) > kMaxTilesAxis) return false;
+  return (long long)B * cdiv(Hf, kTileR) * cdiv(Wf, kTileS) <= kMaxTilesTotal;
+}
+
+static int roi_tiles_l2_prefetch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("C2D_ROI_TILES_PREFETCH"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+template <typename GradT, bool FOLD, int CF>
+static int roi_tiles_launch_cf(const RoiTilesPlan& pl, int B, int Hf, int Wf, int P, const float* boxes,
+                               const unsigned char* codes, const void* dout, const unsigned char* pool_codes,
+                               const void* pool_grad, int pool_ld, unsigned char* ws, float* dfmap, cudaStream_t st) {
+  static unsigned long long attr_mask = 0;
+  static int n_sm[64];
+  const size_t smem = (size_t)kTilePx * 64 * 4 + 32 * 16 + (size_t)(pl.T + 1) * 4;
+  int dev = 0;
+  C2D_CUDA_OK(cudaGetDevice(&dev));
+  auto kern = roi_tiles_bwd_kernel<GradT, FOLD, CF>;
+  if (first_call_on_this_device(&attr_mask)) {
+    C2D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    C2D_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+  }
+  int per_sm = 0;                                          // resident one-warp CTAs per SM: bounded by shared memory
+  C2D_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  int* ctrl = reinterpret_cast<int*>(ws);
+  int* nseg = reinterpret_cast<int*>(ws + pl.off_nseg);
+  int* seg = reinterpret_cast<int*>(ws + pl.off_seg);
+  int* list = reinterpret_cast<int*>(ws + pl.off_list);
+  int2* coords = reinterpret_cast<int2*>(ws + pl.off_coords);
+  unsigned short* masks = reinterpret_cast<unsigned short*>(ws + pl.off_masks);
+  roi_tiles_coords_kernel<<<cdiv((long long)B * P, 8), 256, 0, st>>>(Hf, Wf, (const float4*)boxes, B * P, pl.tiles_y,
+                                                                    pl.tiles_x, coords, masks);
+  C2D_LAUNCH_OK();
+  roi_tiles_bin_kernel<<<pl.T, 256, 0, st>>>(masks, P, pl.tiles_y, pl.tiles_x, pl.seg_max1, ctrl, nseg, seg, list);
+  C2D_LAUNCH_OK();
+  kern<<<n_sm[dev & 63] * per_sm, 32, smem, st>>>(
+      Hf, Wf, P, pl.T, pl.tiles_y, pl.tiles_x, pl.seg_max1, roi_tiles_l2_prefetch(), nseg, seg, list, coords, ctrl, codes,
+      (const GradT*)dout, pool_codes, (const GradT*)pool_grad, pool_ld, dfmap);
+  count_launch(3);
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+template <typename GradT, bool FOLD>
+static int roi_tiles_launch(const RoiTilesPlan& pl, int B, int Hf, int Wf, int Cf, int P, const float* boxes,
+                            const unsigned char* codes, const void* dout, const unsigned char* pool_codes,
+                            const void* pool_grad, int pool_ld, unsigned char* ws, float* dfmap, cudaStream_t st) {
+#define C2D_ROI_TILES_CF(CF)                                                                                          \
+  if (Cf == CF)                                                                                                       \
+    return roi_tiles_launch_cf<GradT, FOLD, CF>(pl, B, Hf, Wf, P, boxes, codes, dout, pool_codes, pool_grad, pool_ld, \
+                                                ws, dfmap, st)
+  C2D_ROI_TILES_CF(576);
+  C2D_ROI_TILES_CF(128);
+  C2D_ROI_TILES_CF(64);
+#undef C2D_ROI_TILES_CF
+  set_error("roi_bwd_tiles: depth %d is not instantiated", Cf);
+  return C2D_ERR_UNSUPPORTED;
 }
 
 }  // namespace c2d
@@ -687,6 +1160,42 @@ int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const flo
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;
+}
+
+size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size) {
+  if (!roi_tiles_supported(B, Hf, Wf, Cf, P, crop_size)) return 0;
+  return roi_tiles_plan(B, Hf, Wf, P).bytes;
+}
+
+int c2d_roi_crop_maxpool_bwd_tiles(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size, int pool_k,
+                                   int pool_s, const unsigned char* codes, const void* dout, int dout_dtype,
+                                   const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,
+                                   void* workspace, size_t workspace_bytes, float* dfmap, c2d_stream_t stream) {
+  int rc = roi_check(B, Hf, Wf, Cf, P, crop_size, pool_k, pool_s);
+  if (rc != C2D_OK) return rc;
+  C2D_CHECK_ARG(dout_dtype == C2D_F32 || dout_dtype == C2D_BF16, "roi: bad dtype %d", dout_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) return C2D_OK;
+  C2D_CUDA_OK(cudaMemsetAsync(dfmap, 0, (size_t)B * Hf * Wf * Cf * sizeof(float), st));
+  if (P == 0) return C2D_OK;
+  if (!roi_tiles_supported(B, Hf, Wf, Cf, P, crop_size)) {
+    set_error("roi_bwd_tiles: needs crop 14, depth 64 / 128 / 576 and <= %d tiles (got crop=%d Cf=%d B=%d %dx%d)",
+              kMaxTilesTotal, crop_size, Cf, B, Hf, Wf);
+    return C2D_ERR_UNSUPPORTED;
+  }
+  const RoiTilesPlan pl = roi_tiles_plan(B, Hf, Wf, P);
+  C2D_CHECK_ARG(codes != nullptr && dout != nullptr && workspace != nullptr && workspace_bytes >= pl.bytes,
+                "roi_bwd_tiles: null operand or workspace of %zu bytes < %zu", workspace_bytes, pl.bytes);
+  const bool fold = pool_codes != nullptr;
+  C2D_CHECK_ARG(!fold || (dout_dtype == C2D_BF16 && pool_grad != nullptr && pool_grad_ld >= Cf),
+                "roi_bwd_tiles: the folded max-pool backward takes bf16 gradients with leading dimension >= Cf");
+  unsigned char* ws = (unsigned char*)workspace;
+  if (fold)
+    return roi_tiles_launch<__nv_bfloat16, true>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, pool_codes, pool_grad,
+                                                 pool_grad_ld, ws, dfmap, st);
+  if (dout_dtype == C2D_BF16)
+    return roi_tiles_launch<__nv_bfloat16, false>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
+  return roi_tiles_launch<float, false>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
 }
 
 }  // extern "C"

@@ -90,13 +90,22 @@ class _RoiCropMaxPool(torch.autograd.Function):
     dout = dout.contiguous()
     dfmap = torch.empty((B, Hf, Wf, Cf), dtype=torch.float32, device=dout.device)
     fold = ctx.fold
-    if fold is not None and fold.ready:
+    folded = fold is not None and fold.ready
+    ws_bytes = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, crop_size)
+    if ws_bytes:
+      # tile-owner backward: gradients are summed across proposals on chip (csrc/c2d_roi.cu)
+      ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dout.device)
+      call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
+           ptr(dout), capi.dtype_code(dout.dtype), fold.pool_codes if folded else None,
+           fold.pool_grad if folded else None, fold.pool_grad_ld if folded else 0, ptr(ws), ws_bytes, ptr(dfmap), stream())
+    elif folded:
       call('c2d_roi_crop_maxpool_bwd_codes_fold', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
            ptr(dout), fold.pool_codes, fold.pool_grad, fold.pool_grad_ld, ptr(dfmap), stream())
-      fold.ws = None
     else:
       call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(proposals), P, crop_size, pool_k, pool_s, ptr(codes),
            ptr(dout), capi.dtype_code(dout.dtype), ptr(dfmap), stream())
+    if folded:
+      fold.ws = None
     return dfmap, None, None, None, None, None, None
 
 

@@ -126,6 +126,18 @@ int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const flo
                                         const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,
                                         float* dfmap, c2d_stream_t stream);
 
+/* Tile-owner form of the two calls above (crop_size 14, Cf % 64 == 0): gradients are added ACROSS proposals in
+ * shared memory by the warp that owns a 4 x 8 pixel tile of the feature map and reach dfmap once per work item,
+ * instead of one vector atomic per (bin, distinct pixel, channel quad).  pool_codes / pool_grad NULL: plain
+ * backward (dout fp32 or bf16); non-NULL: the folded Mixed_5a max-pool backward of ..._bwd_codes_fold (bf16).
+ * workspace: c2d_roi_bwd_tiles_workspace_bytes(...) bytes of device memory, contents irrelevant on entry;
+ * that function returns 0 where this form is not available (use ..._bwd_codes[_fold] then). */
+size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size);
+int c2d_roi_crop_maxpool_bwd_tiles(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size, int pool_k,
+                                   int pool_s, const unsigned char* codes, const void* dout, int dout_dtype,
+                                   const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,
+                                   void* workspace, size_t workspace_bytes, float* dfmap, c2d_stream_t stream);
+
 /* ---- K2/K3: box-classifier head, models/utils.py:165-177 ---------------------------
  * extract_box_classifier_features (Inception-v2 Mixed_5a..5c, OD-API) -> reduce_mean over
  * (1,2) -> slim.dropout.  Parameters live in ONE packed fp32 buffer; conv i stores

@@ -53,6 +53,20 @@ def main():
   bwd = lambda: call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
                      capi.dtype_code(dt), ptr(dfm), stream())
 
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14)
+  ws = torch.empty((max(n_ws, 1),), dtype=torch.uint8, device=dev)
+  dfm_t = torch.empty_like(fmap)
+  bwd_tiles = lambda: call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
+                           capi.dtype_code(dt), None, None, 0, ptr(ws), n_ws, ptr(dfm_t), stream())
+
+  # the training step's form: the backward of Mixed_5a's max-pool folded in (bf16 only)
+  pool_codes = torch.randint(0, 9, (B * P, 16, Cf), dtype=torch.uint8, device=dev)
+  pool_grad = torch.randn((B * P * 16, Cf), device=dev).to(torch.bfloat16)
+  bwd_fold = lambda: call('c2d_roi_crop_maxpool_bwd_codes_fold', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
+                          ptr(pool_codes), ptr(pool_grad), Cf, ptr(dfm), stream())
+  bwd_tiles_fold = lambda: call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
+                                capi.dtype_code(dt), ptr(pool_codes), ptr(pool_grad), Cf, ptr(ws), n_ws, ptr(dfm_t), stream())
+
   def time_it(fn):
     for _ in range(args.warm):
       fn()
@@ -72,12 +86,24 @@ def main():
     peak = json.load(open(p))['hbm_gbs']
   out = dict(shape=dict(images=B, proposals=P, fmap=[Hf, Wf, Cf], dtype=args.dtype), hbm_peak_gbs=peak)
   total_ms, total_bytes = 0.0, 0
+  fwd(); torch.cuda.synchronize()
   for name, fn, nbytes in (('K1 fwd', fwd, B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s)),
-                           ("K1' bwd", bwd, B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4))):
+                           ("K1' bwd scatter", bwd, B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4)),
+                           ("K1' bwd", bwd_tiles, B * (P * 49 * Cf * s + P * 16 + 2 * Hf * Wf * Cf * 4))):
     ms, all_ms = time_it(fn)
     out[name] = dict(ms=ms, all_ms=all_ms, algorithmic_bytes=nbytes, gbs=nbytes / ms / 1e6, frac=nbytes / ms / 1e6 / peak)
+    if name.endswith('scatter'):
+      continue                                   # the per-proposal scatter is timed for comparison only
     total_ms += ms; total_bytes += nbytes
   out['group'] = dict(ms=total_ms, gbs=total_bytes / total_ms / 1e6, frac=total_bytes / total_ms / 1e6 / peak)
+  bwd(); bwd_tiles(); torch.cuda.synchronize()
+  out['tiles_vs_scatter'] = dict(max_abs_diff=float((dfm - dfm_t).abs().max()), max_abs=float(dfm.abs().max()))
+  if dt == torch.bfloat16:
+    for name, fn in (("K1' bwd + pool fold, scatter", bwd_fold), ("K1' bwd + pool fold", bwd_tiles_fold)):
+      ms, all_ms = time_it(fn)
+      out[name] = dict(ms=ms, all_ms=all_ms)
+    bwd_fold(); bwd_tiles_fold(); torch.cuda.synchronize()
+    out['fold_tiles_vs_scatter'] = dict(max_abs_diff=float((dfm - dfm_t).abs().max()), max_abs=float(dfm.abs().max()))
   if args.dump:
     fwd(); bwd(); torch.cuda.synchronize()
     torch.save(dict(x0=x0.cpu(), codes=codes.cpu(), dfm=dfm.cpu()), args.dump)

@@ -150,6 +150,54 @@ def test_roi_crop_maxpool_backward():
     assert int(codes.max()) <= 255 and codes.numel() == B * P * 49 * C // 4
 
 
+@pytest.mark.parametrize('shape', [(2, 37, 9, 13, 64), (2, 150, 38, 63, 128), (3, 5, 4, 8, 64), (2, 300, 5, 9, 64)])
+def test_roi_backward_tile_owner(shape):
+  """c2d_roi_crop_maxpool_bwd_tiles (gradients summed across proposals in shared memory, one flush per work item)
+  against the oracle and against the per-proposal scatter, fp32 and bf16 gradients, with and without the folded
+  Mixed_5a max-pool backward.  Shapes: the edge-case boxes of _roi_inputs, the benchmark map, a map of exactly one
+  tile, and one tile row with 300 proposals (several list segments per tile)."""
+  from cap2det_b200 import capi
+  from cap2det_b200.capi import call, ptr, stream
+  B, P, Hf, Wf, C = shape
+  fmap, props = _roi_inputs(50 + P, B=B, P=P, Hf=Hf, Wf=Wf, C=C)
+  rng = np.random.default_rng(P)
+  g = rng.standard_normal((B * P, 7, 7, C)).astype(np.float32)
+  fm, pr = dev(fmap), dev(props)
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14)
+  assert n_ws > 0
+  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, 24, P, 14) == 0      # depth % 64 != 0: not available
+  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 10) == 0
+  ws = torch.full((n_ws,), 0xA5, dtype=torch.uint8, device='cuda')                       # contents irrelevant on entry
+  for dt in (torch.float32, torch.bfloat16):
+    gd = dev(g).to(dt)
+    codes = torch.empty((capi.load().c2d_roi_argmax_code_bytes(B * P, C, 14),), dtype=torch.uint8, device='cuda')
+    out = torch.empty((B * P, 7, 7, C), dtype=dt, device='cuda')
+    call('c2d_roi_crop_maxpool_fwd_codes', ptr(fm), B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(out), capi.dtype_code(dt),
+         ptr(codes), stream())
+    want = oroi.roi_crop_maxpool_bwd(fmap, props, gd.float().cpu().numpy())
+    for rep in range(2):                                                                 # second call re-uses the workspace
+      d = torch.full((B, Hf, Wf, C), 7.0, dtype=torch.float32, device='cuda')
+      call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd), capi.dtype_code(dt),
+           None, None, 0, ptr(ws), n_ws, ptr(d), stream())
+      assert rel_err(d.cpu().numpy(), want) < RTOL_F32
+  # folded pool backward: same operands into both kernels
+  gd = dev(g).to(torch.bfloat16)
+  pool_codes = torch.from_numpy(rng.integers(0, 9, (B * P, 16, C)).astype(np.uint8)).cuda()
+  ld = C + 64
+  pool_grad = torch.from_numpy(rng.standard_normal((B * P * 16, ld)).astype(np.float32)).cuda().to(torch.bfloat16)
+  d1 = torch.empty((B, Hf, Wf, C), dtype=torch.float32, device='cuda')
+  d2 = torch.empty_like(d1)
+  call('c2d_roi_crop_maxpool_bwd_codes_fold', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd), ptr(pool_codes),
+       ptr(pool_grad), ld, ptr(d1), stream())
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd), capi.dtype_code(torch.bfloat16),
+       ptr(pool_codes), ptr(pool_grad), ld, ptr(ws), n_ws, ptr(d2), stream())
+  assert float(d1.abs().max()) > 0
+  assert rel_err(d2.cpu().numpy(), d1.cpu().numpy()) < RTOL_F32
+  with pytest.raises(ValueError):                                                        # short workspace is refused
+    call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd),
+         capi.dtype_code(torch.bfloat16), None, None, 0, ptr(ws), n_ws - 1, ptr(d2), stream())
+
+
 @pytest.mark.parametrize('crop', [2, 6, 10, 28, 32])
 def test_roi_other_crop_sizes(crop):
   """initial_crop_size other than 14: <= 28 runs the row-rolling kernel, 30 / 32 the per-window kernel."""
