@@ -841,9 +841,9 @@ roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int
   }
   if (lane == 0) pref[T] = run;
   for (int i = lane; i < kTilePx * 64; i += 32) acc[i] = 0.f;
+  const int sh0 = (lane & 1) * 4;                       // this lane's two channels inside its quad's code byte
   __syncwarp();
   const int total_items = run * n_chunks;
-  const int sh0 = (lane & 1) * 4;                       // this lane's two channels inside its quad's code byte
   const unsigned acc_s = (unsigned)__cvta_generic_to_shared(acc) + lane * 4;
   const unsigned rec_s = (unsigned)__cvta_generic_to_shared(rec);
   const int pf_r = lane >> 3, pf_c = lane & 7;          // L2 prefetch: lane -> (bin row, bin column) of a 4 x 8 block
@@ -1163,6 +1163,9 @@ int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const flo
 }
 
 size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size) {
+  static int enabled = -1;                                 // C2D_ROI_TILES=0: measurement switch, per-proposal scatter instead
+  if (enabled < 0) { const char* e = getenv("C2D_ROI_TILES"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return 0;
   if (!roi_tiles_supported(B, Hf, Wf, Cf, P, crop_size)) return 0;
   return roi_tiles_plan(B, Hf, Wf, P).bytes;
 }
