@@ -173,6 +173,12 @@ class Model(ModelBase):
       out['oicr/iter%d/biases' % (i + 1)] = fb[col:col + C + 1]
     return out
 
+  def _ensure_dropout_state(self, device):
+    if self._dropout_state is None:             # per-rank stream: replicas must not share their dropout masks
+      rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
+      self._dropout_seed = (self._seed * 7919 + rank * 104729 + 12345) & 0xffffffff
+      self._dropout_state = torch.zeros((2,), dtype=torch.int64, device=device)
+
   # ---- forward --------------------------------------------------------------------------------
   def _build_prediction(self, examples, features_to_crop):
     """models/cap2det_model.py:152-216 for one feature map."""
@@ -183,8 +189,14 @@ class Model(ModelBase):
     proposals = examples[InputDataFields.proposals].contiguous()
     B, P, _ = proposals.shape
     C = self._num_classes
-    if frcnn.dropout_on_feature_map:
-      raise NotImplementedError('dropout_on_feature_map is off in every reference config (configs/*.pbtxt:55)')
+    if frcnn.dropout_on_feature_map and is_training and frcnn.dropout_keep_prob < 1.0:
+      # models/utils.py:138-142 (off in every reference config, configs/*.pbtxt:55): slim.dropout on the feature map
+      fmask = examples.get(InputDataFields.feature_map_keep_mask)
+      if fmask is None:
+        self._ensure_dropout_state(features_to_crop.device)
+        fmask = ops.dropout_keep_mask(self._dropout_state, self._dropout_seed, tuple(features_to_crop.shape),
+                                      frcnn.dropout_keep_prob)
+      features_to_crop = ops.dropout_apply(features_to_crop, fmask, frcnn.dropout_keep_prob)
     # models/utils.py:147-160
     # bf16 training: the backward of the head's first max-pool is applied inside the ROI backward (ops.PoolFold)
     fold = None
@@ -207,10 +219,7 @@ class Model(ModelBase):
     if is_training and keep_prob < 1.0:
       keep_mask = examples.get(InputDataFields.dropout_keep_mask)
       if keep_mask is None:   # TF1 slim.dropout: floor(keep_prob + uniform[0,1))
-        if self._dropout_state is None:             # per-rank stream: replicas must not share their dropout masks
-          rank = torch.distributed.get_rank() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 0
-          self._dropout_seed = (self._seed * 7919 + rank * 104729 + 12345) & 0xffffffff
-          self._dropout_state = torch.zeros((2,), dtype=torch.int64, device=x0.device)
+        self._ensure_dropout_state(x0.device)
         keep_mask = ops.dropout_keep_mask(self._dropout_state, self._dropout_seed, (B * P, ops.HEAD_FEATURE_DIMS), keep_prob)
     feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
                            need_dx0=features_to_crop.requires_grad, fold=fold)

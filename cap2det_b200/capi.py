@@ -89,6 +89,10 @@ SIGNATURES = {
     'c2d_label_lut': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _p]),
     'c2d_text_classifier_match': (_c_int, [_p, _c_int, _c_int, _p, _c_int, _c_int, _p, _p, _c_int, _p, _p, _c_int,
                                            _c_float, _p, _p, _p, _p]),
+    'c2d_optimizer_update': (_c_int, [_c_int, _p, _p, _p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _c_float, _c_float,
+                                      _c_float, _c_int, _p]),
+    'c2d_ema_update': (_c_int, [_p, _p, _c_ll, _c_float, _p]),
+    'c2d_dropout_apply': (_c_int, [_p, _p, _c_float, _p, _c_ll, _p]),
     'c2d_adagrad_update': (_c_int, [_p, _p, _p, _c_ll, _c_float, _c_float, _c_float, _p]),
     'c2d_l2_loss': (_c_int, [_p, _c_ll, _c_float, _p, _p]),
     'c2d_dropout_keep_mask': (_c_int, [_p, ctypes.c_uint, _c_ll, _c_float, _p, _p]),

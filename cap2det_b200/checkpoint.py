@@ -116,17 +116,19 @@ def init_from_checkpoint(model, checkpoint_path=None, scopes=FEATURE_EXTRACTOR_S
 
 
 def _slot_views(model, train_step):
-  """TF variable name -> view into the Adagrad accumulator of the packed buffer that holds the variable."""
+  """(TF variable name, slot suffix) -> view into the optimizer slot of the packed buffer that holds the variable
+  (``<name>/Adagrad``; ``/Momentum``; ``/Adam``, ``/Adam_1``; ``/RMSProp``, ``/RMSProp_1`` [, ``/RMSProp_2``])."""
   buffers = model.get_variables_to_train()
-  accum = {id(v): a for v, a in zip(train_step.opt.variables, train_step.opt.accum)}
   out = {}
-  for name, view in model.named_variables().items():
-    for b in buffers:
-      off = view.data_ptr() - b.data_ptr()
-      if 0 <= off < b.numel() * b.element_size() and id(b) in accum:
-        start = off // b.element_size()
-        out[name] = accum[id(b)].view(-1)[start:start + view.numel()].view(view.shape)
-        break
+  for suffix, tensors in train_step.opt.slots.items():
+    slot = {id(v): a for v, a in zip(train_step.opt.variables, tensors)}
+    for name, view in model.named_variables().items():
+      for b in buffers:
+        off = view.data_ptr() - b.data_ptr()
+        if 0 <= off < b.numel() * b.element_size() and id(b) in slot:
+          start = off // b.element_size()
+          out[(name, suffix)] = slot[id(b)].view(-1)[start:start + view.numel()].view(view.shape)
+          break
   return out
 
 
@@ -135,12 +137,15 @@ def _is_moving_stat(name):
 
 
 def save_checkpoint(path, train_step):
-  """Variables + Adagrad accumulators (``<name>/Adagrad``) + ``global_step`` -> one .npz (resume point)."""
+  """Variables + optimizer slots (``<name>/Adagrad`` ...) + non-slot optimizer scalars + ``global_step`` -> one .npz
+  (resume point)."""
   model = train_step.model
   out = export_variables(model)
-  for name, view in _slot_views(model, train_step).items():
+  for (name, suffix), view in _slot_views(model, train_step).items():
     if not _is_moving_stat(name):                      # not trainable in TF: no slot
-      out[name + _SLOT] = _to_tf(name, view).contiguous().cpu().numpy()
+      out[name + '/' + suffix] = _to_tf(name, view).contiguous().cpu().numpy()
+  for key, value in train_step.opt.scalar_state().items():
+    out[key] = np.asarray(value)
   out[GLOBAL_STEP] = np.asarray(train_step.global_step, np.int64)
   path = path if path.endswith('.npz') else path + '.npz'
   np.savez(path, **out)
@@ -148,14 +153,16 @@ def save_checkpoint(path, train_step):
 
 
 def load_checkpoint(path, train_step, strict=True):
-  """Inverse of save_checkpoint: restores variables, accumulators (where present) and the global step."""
+  """Inverse of save_checkpoint: restores variables, optimizer slots (where present) and the global step."""
   variables = read_variables(path)
   model = train_step.model
   restored = import_variables(model, variables, strict=strict)
   with torch.no_grad():
-    for name, view in _slot_views(model, train_step).items():
-      if name + _SLOT in variables:
-        view.copy_(_from_tf(name, variables[name + _SLOT], view).to(view.device))
+    for (name, suffix), view in _slot_views(model, train_step).items():
+      key = name + '/' + suffix
+      if key in variables:
+        view.copy_(_from_tf(name, variables[key], view).to(view.device))
+  train_step.opt.load_scalar_state({k: v for k, v in variables.items() if k in ('adam_step', 'beta1_power', 'beta2_power')})
   if GLOBAL_STEP in variables:
     train_step.global_step = int(variables[GLOBAL_STEP])
   return restored

@@ -172,6 +172,64 @@ __global__ void adagrad_kernel(float* __restrict__ var, float* __restrict__ accu
   }
 }
 
+// The other tf.train optimizers core/training_utils.py:37-70 can select (TensorFlow 1.x training_ops):
+//   0 sgd       var -= lr * g
+//   1 momentum  accum = momentum * accum + g ; var -= lr * accum            (use_nesterov: var -= lr * (g + momentum * accum))
+//   2 adam      m += (g - m)(1 - b1) ; v += (g*g - v)(1 - b2) ; var -= lr_t * m / (sqrt(v) + eps), lr_t set by the host
+//   3 rmsprop   ms += (g*g - ms)(1 - decay) ; [centered: mg += (g - mg)(1 - decay)] ;
+//               mom = momentum * mom + lr * g * rsqrt(ms [- mg*mg] + eps) ; var -= mom
+// g = grad * grad_scale + l2_scale * var as in adagrad_kernel.  s0 / s1 / s2 = the slot variables of the optimizer.
+__global__ void optimizer_kernel(int kind, float* __restrict__ var, float* __restrict__ s0, float* __restrict__ s1,
+                                 float* __restrict__ s2, const float* __restrict__ grad, long long n, float lr,
+                                 float grad_scale, float l2_scale, float p0, float p1, float p2, int flag) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float v = var[i];
+    const float g = grad[i] * grad_scale + l2_scale * v;
+    if (kind == 0) {
+      var[i] = v - lr * g;
+    } else if (kind == 1) {
+      const float a = s0[i] * p0 + g;
+      s0[i] = a;
+      var[i] = flag ? v - (g * lr + a * p0 * lr) : v - lr * a;
+    } else if (kind == 2) {
+      const float m = s0[i] + (g - s0[i]) * (1.0f - p0);
+      const float q = s1[i] + (g * g - s1[i]) * (1.0f - p1);
+      s0[i] = m; s1[i] = q;
+      var[i] = v - (m * lr) / (sqrtf(q) + p2);
+    } else {
+      const float ms = s0[i] + (g * g - s0[i]) * (1.0f - p0);
+      s0[i] = ms;
+      float denom = ms;
+      if (flag) {
+        const float mg = s2[i] + (g - s2[i]) * (1.0f - p0);
+        s2[i] = mg;
+        denom = ms - mg * mg;
+      }
+      const float mom = s1[i] * p1 + (g * lr) * rsqrtf(denom + p2);
+      s1[i] = mom;
+      var[i] = v - mom;
+    }
+  }
+}
+
+// slim.dropout on a tensor (tf.nn.dropout of TF 1.x: div(x, keep_prob) * binary_tensor), models/utils.py:138-142.
+__global__ void dropout_apply_kernel(const float* __restrict__ x, const float* __restrict__ mask, float keep_prob,
+                                     float* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) out[i] = __fmul_rn(__fdiv_rn(x[i], keep_prob), mask[i]);
+}
+
+// tf.train.ExponentialMovingAverage.apply as MovingAverageOptimizer runs it after every step (train/trainer.py:98-100):
+// shadow -= (1 - decay) * (shadow - var).
+__global__ void ema_kernel(float* __restrict__ shadow, const float* __restrict__ var, long long n, float one_minus_decay) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) shadow[i] = shadow[i] - one_minus_decay * (shadow[i] - var[i]);
+}
+
 __global__ void l2_loss_kernel(const float* __restrict__ w, long long n, float scale, float* __restrict__ out) {
   __shared__ float sm[32];
   float s = 0.f;
@@ -300,6 +358,46 @@ int c2d_adagrad_update(float* var, float* accum, const float* grad, long long n,
   int blocks = (int)((n + 255) / 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   adagrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(var, accum, grad, n, lr, grad_scale, l2_scale);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_optimizer_update(int kind, float* var, float* slot0, float* slot1, float* slot2, const float* grad, long long n,
+                         float lr, float grad_scale, float l2_scale, float p0, float p1, float p2, int flag,
+                         c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0, "optimizer: n must be >= 0");
+  C2D_CHECK_ARG(kind >= C2D_OPT_SGD && kind <= C2D_OPT_RMSPROP, "optimizer: unknown kind %d", kind);
+  C2D_CHECK_ARG(kind == C2D_OPT_SGD || slot0 != nullptr, "optimizer: kind %d needs slot0", kind);
+  C2D_CHECK_ARG((kind != C2D_OPT_ADAM && kind != C2D_OPT_RMSPROP) || slot1 != nullptr, "optimizer: kind %d needs slot1", kind);
+  C2D_CHECK_ARG(!(kind == C2D_OPT_RMSPROP && flag) || slot2 != nullptr, "optimizer: centered rmsprop needs slot2");
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  optimizer_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(kind, var, slot0, slot1, slot2, grad, n, lr, grad_scale,
+                                                             l2_scale, p0, p1, p2, flag);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_dropout_apply(const float* x, const float* mask, float keep_prob, float* out, long long n, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0 && keep_prob > 0.f && keep_prob <= 1.f, "dropout_apply: n >= 0 and 0 < keep_prob <= 1 required");
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dropout_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, mask, keep_prob, out, n);
+  count_launch();
+  C2D_LAUNCH_OK();
+  return C2D_OK;
+}
+
+int c2d_ema_update(float* shadow, const float* var, long long n, float decay, c2d_stream_t stream) {
+  C2D_CHECK_ARG(n >= 0, "ema_update: n must be >= 0");
+  if (n == 0) return C2D_OK;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ema_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(shadow, var, n, 1.0f - decay);
   count_launch();
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -191,6 +191,34 @@ def head_mixed5(x0, params, keep_mask=None, keep_prob=1.0, need_dx0=True, fold=N
 # ---------------------------------------------------------------------------------------------
 # Reader-side image / box contract  (readers/cap2det_reader.py:143-199, core/imgproc.py:300-352)
 # ---------------------------------------------------------------------------------------------
+class _DropoutApply(torch.autograd.Function):
+  @staticmethod
+  def forward(ctx, x, mask, keep_prob):
+    require_cuda(x, mask)
+    _f32(x); _f32(mask)
+    if mask.shape != x.shape:
+      raise ValueError('keep mask %s does not match the tensor %s' % (tuple(mask.shape), tuple(x.shape)))
+    out = torch.empty_like(x)
+    call('c2d_dropout_apply', ptr(x), ptr(mask), float(keep_prob), ptr(out), x.numel(), stream())
+    ctx.save_for_backward(mask)
+    ctx.keep_prob = float(keep_prob)
+    return out
+
+  @staticmethod
+  def backward(ctx, dout):
+    (mask,) = ctx.saved_tensors
+    dout = dout.contiguous()
+    dx = torch.empty_like(dout)
+    call('c2d_dropout_apply', ptr(dout), ptr(mask), ctx.keep_prob, ptr(dx), dout.numel(), stream())
+    return dx, None, None
+
+
+def dropout_apply(x, keep_mask, keep_prob):
+  """slim.dropout with a given {0,1} keep mask: (x / keep_prob) * mask (tf.nn.dropout of TF 1.x), differentiable in x.
+  Used for frcnn_options.dropout_on_feature_map (models/utils.py:138-142)."""
+  return _DropoutApply.apply(x.contiguous(), keep_mask.contiguous(), keep_prob)
+
+
 def dropout_keep_mask(state, seed, shape, keep_prob):
   """slim.dropout's keep mask floor(keep_prob + uniform[0,1)) (models/utils.py:176-177) from the library's Philox kernel.
   state: int64[2] device tensor, zero-initialised once and then owned by the kernel (it counts the masks drawn)."""

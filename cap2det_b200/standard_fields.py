@@ -24,6 +24,7 @@ class InputDataFields(object):
   features_to_crop = 'features_to_crop'
   # Added key (tests only): an injected {0,1} dropout keep mask [B*P,1024].
   dropout_keep_mask = 'dropout_keep_mask'
+  feature_map_keep_mask = 'feature_map_keep_mask'      # injected mask for frcnn_options.dropout_on_feature_map
 
 
 class DetectionResultFields(object):

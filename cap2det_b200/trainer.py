@@ -52,27 +52,42 @@ def resolve_gradient_multipliers(variable_names, gradient_multipliers):
   return trainable, mults
 
 
-class Adagrad(object):
-  """tf.train.AdagradOptimizer(lr, initial_accumulator_value=0.1): accum += g^2; w -= lr*g/sqrt(accum).
+class PackedOptimizer(object):
+  """Common part of the tf.train optimizers of core/training_utils.py:14-70 over packed parameter buffers.
 
   ``variables`` are the packed parameter buffers.  ``segments`` (optional) lists, per buffer, the named
   sub-ranges ``(name, start, numel, multiplier or None if dropped, l2)``; when every segment of a buffer agrees
   the whole buffer is one fused launch, otherwise each live segment is its own launch and dropped segments are
-  left untouched (weights and accumulator)."""
+  left untouched (weights and slot variables).  ``slots``: TF slot suffix -> one tensor per buffer, in TF's creation
+  order (so a checkpoint names them ``<variable>/<suffix>``)."""
 
-  def __init__(self, variables, learning_rate, initial_accumulator_value=0.1, l2_scales=None, grad_multipliers=None,
-               segments=None):
+  graph_safe = True            # every per-step scalar is a launch constant (False: see Adam)
+
+  def __init__(self, variables, learning_rate, l2_scales=None, grad_multipliers=None, segments=None):
     self.variables = list(variables)
     self.lr = float(learning_rate)
-    self.accum = [torch.full_like(v, initial_accumulator_value) for v in self.variables]
+    self.slots = {}
     self.l2 = list(l2_scales) if l2_scales is not None else [0.0] * len(self.variables)
     self.mult = list(grad_multipliers) if grad_multipliers is not None else [1.0] * len(self.variables)
     self.segments = segments
     self.static_grads = None
     self.clip_norm = None       # tf.contrib.training.clip_gradient_norms: per-variable clip_by_norm
 
-  def _update(self, w, a, g, n, scale, l2):
-    call('c2d_adagrad_update', ptr(w), ptr(a), ptr(g), n, self.lr, float(scale), float(l2), stream())
+  def state_tensors(self):
+    """Every slot tensor (what a snapshot / restore of the optimizer has to cover besides ``scalar_state``)."""
+    return [t for ts in self.slots.values() for t in ts]
+
+  def scalar_state(self):
+    return {}
+
+  def load_scalar_state(self, state):
+    pass
+
+  def _begin_step(self):
+    pass
+
+  def _update(self, w, slots, g, n, scale, l2):
+    raise NotImplementedError
 
   def _clip_factor(self, w, g, scale, l2):
     """tf.clip_by_norm on the total gradient scale*g + l2*w of one variable: factor = clip / max(norm, clip).
@@ -88,18 +103,22 @@ class Adagrad(object):
   def step(self, grad_scale=1.0):
     """The regularisation loss is part of the reference's total loss, so a variable's gradient multiplier
     scales its L2 term as well: g_total = m * (grad_scale * grad + l2 * w)."""
-    for i, (v, a) in enumerate(zip(self.variables, self.accum)):
+    self._begin_step()
+    names = list(self.slots.keys())
+    for i, v in enumerate(self.variables):
       if v.grad is None:
         continue
+      mine = [self.slots[k][i] for k in names]
       segs = self.segments[i] if self.segments is not None else None
       uniform = segs is None or len({(m, l2) for _, _, _, m, l2 in segs}) == 1
       if uniform and self.clip_norm is None:
         m, l2 = (self.mult[i], self.l2[i]) if segs is None else (segs[0][3], segs[0][4])
         if m is None or m == 0.0:   # multiplier 0 => variable dropped from the train list (train/trainer.py:104-125)
           continue
-        self._update(v.data, a, v.grad, v.numel(), grad_scale * m, l2 * m)
+        self._update(v.data, mine, v.grad, v.numel(), grad_scale * m, l2 * m)
         continue
-      wf, af, gf = v.data.view(-1), a.view(-1), v.grad.view(-1)
+      wf, gf = v.data.view(-1), v.grad.view(-1)
+      flat = [t.view(-1) for t in mine]
       if segs is None:
         segs = [('', 0, v.numel(), self.mult[i], self.l2[i])]
       for _, start, numel, m, l2 in segs:
@@ -107,7 +126,7 @@ class Adagrad(object):
           continue
         w, g = wf[start:start + numel], gf[start:start + numel]
         clip = self._clip_factor(w, g, grad_scale * m, l2 * m)
-        self._update(w, af[start:start + numel], g, numel, grad_scale * m * clip, l2 * m * clip)
+        self._update(w, [t[start:start + numel] for t in flat], g, numel, grad_scale * m * clip, l2 * m * clip)
 
   def zero_grad(self):
     if self.static_grads is not None:     # gradients are views of one flat bucket (GraphedTrainStep, data parallel)
@@ -117,15 +136,111 @@ class Adagrad(object):
       v.grad = None
 
 
+class Adagrad(PackedOptimizer):
+  """tf.train.AdagradOptimizer(lr, initial_accumulator_value=0.1): accum += g^2; w -= lr*g/sqrt(accum)."""
+
+  def __init__(self, variables, learning_rate, initial_accumulator_value=0.1, **kwargs):
+    super(Adagrad, self).__init__(variables, learning_rate, **kwargs)
+    self.accum = [torch.full_like(v, initial_accumulator_value) for v in self.variables]
+    self.slots['Adagrad'] = self.accum
+
+  def _update(self, w, slots, g, n, scale, l2):
+    call('c2d_adagrad_update', ptr(w), ptr(slots[0]), ptr(g), n, self.lr, float(scale), float(l2), stream())
+
+
+_OPT_SGD, _OPT_MOMENTUM, _OPT_ADAM, _OPT_RMSPROP = 0, 1, 2, 3
+
+
+class GradientDescent(PackedOptimizer):
+  """tf.train.GradientDescentOptimizer: w -= lr * g (no slot variables)."""
+
+  def _update(self, w, slots, g, n, scale, l2):
+    call('c2d_optimizer_update', _OPT_SGD, ptr(w), None, None, None, ptr(g), n, self.lr, float(scale), float(l2), 0.0, 0.0,
+         0.0, 0, stream())
+
+
+class Momentum(PackedOptimizer):
+  """tf.train.MomentumOptimizer: accum = momentum * accum + g; w -= lr * accum (use_nesterov: w -= lr * (g + momentum *
+  accum))."""
+
+  def __init__(self, variables, learning_rate, momentum=0.0, use_nesterov=False, **kwargs):
+    super(Momentum, self).__init__(variables, learning_rate, **kwargs)
+    self.momentum, self.use_nesterov = float(momentum), bool(use_nesterov)
+    self.slots['Momentum'] = [torch.zeros_like(v) for v in self.variables]
+
+  def _update(self, w, slots, g, n, scale, l2):
+    call('c2d_optimizer_update', _OPT_MOMENTUM, ptr(w), ptr(slots[0]), None, None, ptr(g), n, self.lr, float(scale), float(l2),
+         self.momentum, 0.0, 0.0, int(self.use_nesterov), stream())
+
+
+class Adam(PackedOptimizer):
+  """tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t); m, v moving averages; w -= lr_t * m /
+  (sqrt(v) + epsilon).  lr_t changes every step, so a step of this optimizer cannot be baked into a CUDA graph."""
+
+  graph_safe = False
+
+  def __init__(self, variables, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, **kwargs):
+    super(Adam, self).__init__(variables, learning_rate, **kwargs)
+    self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
+    self.t = 0                                   # beta1_power = beta1^(t+1), beta2_power likewise (TF non-slot variables)
+    self.slots['Adam'] = [torch.zeros_like(v) for v in self.variables]
+    self.slots['Adam_1'] = [torch.zeros_like(v) for v in self.variables]
+
+  def scalar_state(self):
+    return {'beta1_power': self.beta1 ** (self.t + 1), 'beta2_power': self.beta2 ** (self.t + 1), 'adam_step': self.t}
+
+  def load_scalar_state(self, state):
+    if 'adam_step' in state:
+      self.t = int(state['adam_step'])
+
+  def _begin_step(self):
+    import math
+    self.t += 1
+    self._lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
+
+  def _update(self, w, slots, g, n, scale, l2):
+    call('c2d_optimizer_update', _OPT_ADAM, ptr(w), ptr(slots[0]), ptr(slots[1]), None, ptr(g), n, self._lr_t, float(scale),
+         float(l2), self.beta1, self.beta2, self.epsilon, 0, stream())
+
+
+class RMSProp(PackedOptimizer):
+  """tf.train.RMSPropOptimizer: ms (initialised to one) and momentum slots, mg when centered."""
+
+  def __init__(self, variables, learning_rate, decay=0.9, momentum=0.0, epsilon=1e-10, centered=False, **kwargs):
+    super(RMSProp, self).__init__(variables, learning_rate, **kwargs)
+    self.decay, self.momentum, self.epsilon, self.centered = float(decay), float(momentum), float(epsilon), bool(centered)
+    self.slots['RMSProp'] = [torch.ones_like(v) for v in self.variables]               # rms
+    if self.centered:
+      self.slots['RMSProp_1'] = [torch.zeros_like(v) for v in self.variables]          # mg
+      self.slots['RMSProp_2'] = [torch.zeros_like(v) for v in self.variables]          # momentum
+    else:
+      self.slots['RMSProp_1'] = [torch.zeros_like(v) for v in self.variables]          # momentum
+
+  def _update(self, w, slots, g, n, scale, l2):
+    ms, mom, mg = (slots[0], slots[2], slots[1]) if self.centered else (slots[0], slots[1], None)
+    call('c2d_optimizer_update', _OPT_RMSPROP, ptr(w), ptr(ms), ptr(mom), ptr(mg), ptr(g), n, self.lr, float(scale), float(l2),
+         self.decay, self.momentum, self.epsilon, int(self.centered), stream())
+
+
 def build_optimizer(options, variables, learning_rate, **kwargs):
-  """core/training_utils.py:14-70.  Only adagrad has a device kernel on this path (it is what all nine
-  reference configs select, e.g. configs/voc07_groundtruth.pbtxt:108-111)."""
+  """core/training_utils.py:14-70: the optimizer oneof -> its tf.train counterpart.  All nine reference configs select
+  adagrad (e.g. configs/voc07_groundtruth.pbtxt:108-111); use_locking has no meaning on one stream."""
   which = options.WhichOneof('optimizer')
+  if which == 'sgd':
+    return GradientDescent(variables, learning_rate, **kwargs)
+  if which == 'momentum':
+    o = options.momentum
+    return Momentum(variables, learning_rate, momentum=o.momentum, use_nesterov=o.use_nesterov, **kwargs)
   if which == 'adagrad':
     return Adagrad(variables, learning_rate,
                    initial_accumulator_value=options.adagrad.initial_accumulator_value, **kwargs)
-  if which in ('sgd', 'momentum', 'adam', 'rmsprop'):
-    raise ValueError('optimizer %r has no sm_100a kernel in cap2det_b200; use adagrad' % which)
+  if which == 'adam':
+    o = options.adam
+    return Adam(variables, learning_rate, beta1=o.beta1, beta2=o.beta2, epsilon=o.epsilon, **kwargs)
+  if which == 'rmsprop':
+    o = options.rmsprop
+    return RMSProp(variables, learning_rate, decay=o.decay, momentum=o.momentum, epsilon=o.epsilon, centered=o.centered,
+                   **kwargs)
   raise ValueError('Invalid optimizer: {}.'.format(which))
 
 
@@ -175,6 +290,8 @@ class TrainStep(object):
     self._pending = []
     self._one = None                 # cached seed gradient of the total loss
     self.overlap_hooks = True
+    self.shadow = None               # moving averages of the packed buffers (moving_average_decay != 0)
+    self.moving_average_decay = 0.0
     if world_size > 1 and hasattr(torch.Tensor, 'register_post_accumulate_grad_hook'):
       # Start the all-reduce of a gradient buffer the moment autograd has finished it: the head's 24 MB buffer
       # is complete before the ROI backward (and the first-stage backward) run, so NCCL overlaps with them.
@@ -197,10 +314,12 @@ class TrainStep(object):
     segs = _variable_segments(model, mults, trainable, l2)
     self.trainable_names, self.gradient_multipliers = trainable, mults
     self.opt = build_optimizer(train_config.optimizer, variables, self.base_lr, segments=segs)
-    # MovingAverageOptimizer(decay): every reference config sets 0.0, which makes the shadow copy equal the
-    # variable (train/trainer.py:98-100); any other value would need the shadow set, which this path lacks.
+    # MovingAverageOptimizer(decay), train/trainer.py:98-100: a shadow copy of every optimised variable, updated after
+    # each step (shadow -= (1 - decay) * (shadow - var)).  Every reference config sets 0.0, which makes the shadow equal
+    # the variable, so the copies are only kept for a non-zero decay.
     if train_config.HasField('moving_average_decay') and train_config.moving_average_decay != 0.0:
-      raise ValueError('moving_average_decay != 0 is not supported on this path')
+      self.moving_average_decay = float(train_config.moving_average_decay)
+      self.shadow = [v.detach().clone() for v in variables]
     if train_config.HasField('max_gradient_norm'):          # train/trainer.py:134-136
       self.opt.clip_norm = float(train_config.max_gradient_norm)
 
@@ -274,6 +393,9 @@ class TrainStep(object):
 
   def update(self, total):
     self.opt.step(grad_scale=1.0 / self.world_size)
+    if self.shadow is not None:
+      for v, sh in zip(self.model.get_variables_to_train(), self.shadow):
+        call('c2d_ema_update', ptr(sh), ptr(v.data), v.numel(), self.moving_average_decay, stream())
     self.global_step += 1
     return self.regularization_loss(total)
 
@@ -317,7 +439,9 @@ class GraphedTrainStep(object):
     # need them); constructing this object must not train, so weights, Adagrad accumulators and the step counter are
     # put back afterwards.  (Capture itself records the kernels without running them.)
     variables = model.get_variables_to_train()
-    saved = ([v.detach().clone() for v in variables], [a.clone() for a in train_step.opt.accum], train_step.global_step)
+    if not train_step.opt.graph_safe:
+      raise ValueError('%s changes a launch constant every step (lr_t); run TrainStep eagerly' % type(train_step.opt).__name__)
+    saved = ([v.detach().clone() for v in variables], [a.clone() for a in train_step.opt.state_tensors()], train_step.global_step)
     self.split = self.world_size > 1 if split_graphs is None else bool(split_graphs)
     if self.split:
       # gradients live in ONE flat bucket (a single all-reduce); autograd accumulates into the views in place
@@ -369,7 +493,7 @@ class GraphedTrainStep(object):
     with torch.no_grad():
       for v, w in zip(variables, saved[0]):
         v.copy_(w)
-      for a, b in zip(train_step.opt.accum, saved[1]):
+      for a, b in zip(train_step.opt.state_tensors(), saved[1]):
         a.copy_(b)
     train_step.global_step = saved[2]
     model._assert_status = None

@@ -329,6 +329,23 @@ int c2d_text_classifier_match(const int* token_ids, int B, int T, const float* e
  * accum += g*g ; var -= lr * g * rsqrt(accum)                (tf.train.AdagradOptimizer, accum0 = 0.1) */
 int c2d_adagrad_update(float* var, float* accum, const float* grad, long long n, float lr, float grad_scale,
                        float l2_scale, c2d_stream_t stream);
+/* The other optimizers core/training_utils.py:37-70 builds (tf.train.GradientDescent / Momentum / Adam / RMSProp
+ * Optimizer, TensorFlow 1.x training_ops formulas), same fused g = grad * grad_scale + l2_scale * var:
+ *   C2D_OPT_SGD       var -= lr*g
+ *   C2D_OPT_MOMENTUM  slot0 = p0*slot0 + g ; var -= lr*slot0     (flag: use_nesterov, var -= lr*(g + p0*slot0)); p0 = momentum
+ *   C2D_OPT_ADAM      slot0 = m, slot1 = v, p0 = beta1, p1 = beta2, p2 = epsilon; lr = lr*sqrt(1-beta2^t)/(1-beta1^t) (host)
+ *   C2D_OPT_RMSPROP   slot0 = ms (init 1), slot1 = momentum slot, slot2 = mg (flag: centered); p0 = decay, p1 = momentum,
+ *                     p2 = epsilon */
+enum { C2D_OPT_SGD = 0, C2D_OPT_MOMENTUM = 1, C2D_OPT_ADAM = 2, C2D_OPT_RMSPROP = 3 };
+int c2d_optimizer_update(int kind, float* var, float* slot0, float* slot1, float* slot2, const float* grad, long long n,
+                         float lr, float grad_scale, float l2_scale, float p0, float p1, float p2, int flag,
+                         c2d_stream_t stream);
+/* tf.contrib.opt.MovingAverageOptimizer's shadow update after a step (train/trainer.py:98-100):
+ * shadow -= (1 - decay) * (shadow - var). */
+int c2d_ema_update(float* shadow, const float* var, long long n, float decay, c2d_stream_t stream);
+/* slim.dropout applied to a tensor with a given keep mask (frcnn_options.dropout_on_feature_map, models/utils.py:138-142):
+ * out = (x / keep_prob) * mask; the backward pass is the same call on the output gradient. */
+int c2d_dropout_apply(const float* x, const float* mask, float keep_prob, float* out, long long n, c2d_stream_t stream);
 /* slim.dropout's keep mask (models/utils.py:176-177): mask[i] = floor(keep_prob + u_i), u_i uniform in [0,1) from
  * Philox4x32-10 keyed by `seed`; state = two device uint64 {masks drawn so far, 0}, advanced by the kernel itself so
  * that replays of a captured CUDA graph draw fresh masks.  n = number of mask elements (multiple of 4). */

@@ -1169,3 +1169,104 @@ def test_text_model_trains_and_feeds_the_text_classifier_extractor(tmp_path):
   logits = model.build_prediction({F.concat_caption_string: caps})['logits']
   # same network, same variables (only the out-of-vocabulary embedding row is drawn independently - masked out)
   np.testing.assert_allclose(probas.cpu().numpy(), torch.sigmoid(logits).detach().cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('which', ['sgd', 'momentum', 'nesterov', 'adam', 'rmsprop', 'rmsprop_centered'])
+def test_other_optimizers_match_the_tensorflow_update_rules(which):
+  """core/training_utils.py:37-70: sgd / momentum / adam / rmsprop through trainer.build_optimizer on packed buffers,
+  three steps with a gradient multiplier and an L2 term, against oracle/optimizers.py (TF 1.x training_ops rules)."""
+  from cap2det_b200 import config, trainer
+  from oracle import optimizers as oopt
+  text = {'sgd': 'sgd { }', 'momentum': 'momentum { momentum: 0.9 }',
+          'nesterov': 'momentum { momentum: 0.8 use_nesterov: true }', 'adam': 'adam { beta1: 0.85 epsilon: 1e-6 }',
+          'rmsprop': 'rmsprop { decay: 0.8 momentum: 0.5 epsilon: 1e-4 }',
+          'rmsprop_centered': 'rmsprop { decay: 0.8 momentum: 0.5 epsilon: 1e-3 centered: true }'}[which]
+  options = config.parse_text(text, config.Optimizer)
+  rng = np.random.default_rng(11)
+  w0 = rng.standard_normal(5003).astype(np.float32)
+  v = torch.nn.Parameter(dev(w0.copy()))
+  lr, scale, l2 = 0.05, 0.5, 0.01
+  opt = trainer.build_optimizer(options, [v], lr, l2_scales=[l2], grad_multipliers=[1.0])
+  w = w0.copy()
+  slots = {k: t[0].cpu().numpy().copy() for k, t in opt.slots.items()}
+  for t in range(1, 4):
+    g = rng.standard_normal(5003).astype(np.float32)
+    v.grad = dev(g)
+    opt.step(grad_scale=scale)
+    gt = g * np.float32(scale) + np.float32(l2) * w
+    if which == 'sgd':
+      oopt.sgd(w, gt, lr)
+    elif which in ('momentum', 'nesterov'):
+      oopt.momentum(w, slots['Momentum'], gt, lr, options.momentum.momentum, which == 'nesterov')
+    elif which == 'adam':
+      oopt.adam(w, slots['Adam'], slots['Adam_1'], gt, lr, options.adam.beta1, options.adam.beta2, options.adam.epsilon, t)
+    elif which == 'rmsprop':
+      oopt.rmsprop(w, slots['RMSProp'], slots['RMSProp_1'], gt, lr, 0.8, 0.5, options.rmsprop.epsilon)
+    else:
+      oopt.rmsprop(w, slots['RMSProp'], slots['RMSProp_2'], gt, lr, 0.8, 0.5, options.rmsprop.epsilon, mg=slots['RMSProp_1'])
+    assert rel_err(v.detach().cpu().numpy(), w) < RTOL_F32, (which, t)
+    for k, ts in opt.slots.items():
+      assert rel_err(ts[0].cpu().numpy(), slots[k]) < RTOL_F32, (which, k, t)
+  if which == 'adam':
+    assert opt.scalar_state()['adam_step'] == 3 and not opt.graph_safe
+
+
+def test_feature_map_dropout_and_moving_average():
+  """frcnn_options.dropout_on_feature_map (models/utils.py:138-142): slim.dropout on the feature map = div(x, keep_prob)
+  * mask, forward and gradient; moving_average_decay (train/trainer.py:98-100): shadow -= (1 - decay) * (shadow - var)
+  after every step."""
+  from cap2det_b200 import ops
+  rng = np.random.default_rng(21)
+  x = rng.standard_normal((2, 5, 7, 16)).astype(np.float32)
+  mask = (rng.uniform(size=x.shape) < 0.7).astype(np.float32)
+  g = rng.standard_normal(x.shape).astype(np.float32)
+  xt = dev(x).requires_grad_(True)
+  y = ops.dropout_apply(xt, dev(mask), 0.7)
+  np.testing.assert_array_equal(y.detach().cpu().numpy(), (x / np.float32(0.7)) * mask)
+  y.backward(dev(g))
+  np.testing.assert_array_equal(xt.grad.cpu().numpy(), (g / np.float32(0.7)) * mask)
+  with pytest.raises(ValueError):
+    ops.dropout_apply(xt, dev(mask[:1]), 0.7)
+  # the model applies it before the ROI crop: same predictions as a model without the option on the pre-masked map
+  from cap2det_b200 import builder, config, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  import tempfile
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  B, P = 1, 12
+  fmap = synthetic.make_feature_map(rng, B, 128, 160)
+  props = synthetic.make_proposals(rng, B, P, 128, 160)
+  fmask = (rng.uniform(size=fmap.shape) < 0.5).astype(np.float32)
+  keep = (rng.uniform(size=(B * P, 1024)) < 0.5).astype(np.float32)
+  preds = []
+  for on in (True, False):
+    text = synthetic.model_options_text(extractor='groundtruth_extractor',
+                                        extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+    text = text.replace('dropout_on_feature_map: false', 'dropout_on_feature_map: %s' % ('true' if on else 'false'))
+    m = config.Model()
+    m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+    model = builder.build(m, is_training=True)
+    fm = dev(fmap) if on else dev((fmap / np.float32(0.5)) * fmask)
+    ex = {F.features_to_crop: fm, F.num_proposals: dev(np.array([P], np.int32)), F.proposals: dev(props),
+          F.object_texts: synthetic.make_object_texts(np.random.default_rng(3), B, classes), F.dropout_keep_mask: dev(keep),
+          F.feature_map_keep_mask: dev(fmask)}
+    preds.append(model.build_prediction(ex)['_logits_all'].detach().cpu().numpy())
+  np.testing.assert_array_equal(preds[0], preds[1])
+  # moving averages
+  from cap2det_b200 import trainer
+  tc = config.parse_text('learning_rate: 0.1  optimizer { adagrad { } }  moving_average_decay: 0.9', config.TrainConfig)
+  step = trainer.TrainStep(model, train_config=tc)
+  before = [v.detach().clone() for v in model.get_variables_to_train()]
+  ex = {F.features_to_crop: dev(fmap).requires_grad_(True), F.num_proposals: dev(np.array([P], np.int32)), F.proposals: dev(props),
+        F.object_texts: synthetic.make_object_texts(np.random.default_rng(3), B, classes), F.dropout_keep_mask: dev(keep)}
+  omd = torch.tensor(1.0, dtype=torch.float32) - torch.tensor(0.9, dtype=torch.float32)          # the kernel's 1 - decay
+  want = [b.clone() for b in before]
+  for _ in range(2):
+    step(ex)
+    for w, v in zip(want, model.get_variables_to_train()):
+      w.copy_(w - omd.to(w.device) * (w - v.detach()))
+  torch.cuda.synchronize()
+  assert step.shadow is not None and step.moving_average_decay == pytest.approx(0.9)
+  for sh, w, b in zip(step.shadow, want, before):
+    assert rel_err(sh.cpu().numpy(), w.cpu().numpy()) < 1e-6
+    assert bool((sh != b).any())

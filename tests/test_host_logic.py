@@ -174,10 +174,15 @@ def test_exponential_decay_and_optimizer_selection():
   assert tc.optimizer.adagrad.initial_accumulator_value == pytest.approx(0.1)
   assert tc.learning_rate_decay.decay_steps == 100000 and tc.HasField('learning_rate_decay')
   assert not tc.HasField('max_gradient_norm')
-  for other in ('sgd', 'adam', 'rmsprop', 'momentum'):
-    opt = config.parse_text('%s { }' % other, config.Optimizer)
-    with pytest.raises(ValueError, match='no sm_100a kernel'):
-      trainer.build_optimizer(opt, [], 0.01)
+  for other, cls, slots in (('sgd', trainer.GradientDescent, []), ('adam', trainer.Adam, ['Adam', 'Adam_1']),
+                            ('rmsprop', trainer.RMSProp, ['RMSProp', 'RMSProp_1']), ('momentum', trainer.Momentum, ['Momentum'])):
+    opt = trainer.build_optimizer(config.parse_text('%s { }' % other, config.Optimizer), [], 0.01)
+    assert type(opt) is cls and list(opt.slots.keys()) == slots          # TF slot names, in TF's creation order
+  centered = trainer.build_optimizer(config.parse_text('rmsprop { centered: true }', config.Optimizer), [], 0.01)
+  assert list(centered.slots.keys()) == ['RMSProp', 'RMSProp_1', 'RMSProp_2'] and centered.centered
+  adam = trainer.build_optimizer(config.parse_text('adam { }', config.Optimizer), [], 0.01)
+  assert (adam.beta1, adam.beta2, adam.epsilon) == (pytest.approx(0.9), pytest.approx(0.999), pytest.approx(1e-8))
+  assert not adam.graph_safe                                             # lr_t changes every step
   with pytest.raises(ValueError, match='Invalid optimizer'):
     trainer.build_optimizer(config.Optimizer(), [], 0.01)
 
@@ -947,3 +952,23 @@ def test_build_has_no_experimental_switches():
     text = open(os.path.join(csrc, name)).read()
     for macro in ('C2D_UNIFORM_ISSUE', 'C2D_EPILOGUE_EARLY_SHIFT', 'C2D_EPILOGUE_PREFETCH'):
       assert macro not in text.replace('-D' + macro, ''), (name, macro)
+
+
+def test_oracle_optimizers_closed_forms():
+  import numpy as np
+  """oracle/optimizers.py on cases with a known answer (TF 1.x update rules, first step from the initial slots)."""
+  from oracle import optimizers as oopt
+  g = np.array([2.0, -1.0], np.float32)
+  w = np.array([1.0, 1.0], np.float32)
+  np.testing.assert_allclose(oopt.sgd(w.copy(), g, 0.1), [0.8, 1.1], rtol=1e-6)
+  wv, acc = oopt.momentum(w.copy(), np.zeros(2, np.float32), g, 0.1, 0.9)
+  np.testing.assert_allclose(wv, [0.8, 1.1], rtol=1e-6); np.testing.assert_allclose(acc, g)
+  wv, acc = oopt.momentum(w.copy(), np.ones(2, np.float32), g, 0.1, 0.5, use_nesterov=True)     # accum = 0.5 + g
+  np.testing.assert_allclose(wv, w - (g * 0.1 + (0.5 + g) * 0.5 * 0.1), rtol=1e-6)
+  wv, m, v = oopt.adam(w.copy(), np.zeros(2, np.float32), np.zeros(2, np.float32), g, 0.1, 0.9, 0.999, 1e-8, 1)
+  np.testing.assert_allclose(wv, w - 0.1 * np.sign(g), rtol=1e-4)       # first Adam step moves by lr * sign(g)
+  wv, ms, mom = oopt.rmsprop(w.copy(), np.ones(2, np.float32), np.zeros(2, np.float32), g, 0.1, 0.9, 0.0, 1e-10)
+  np.testing.assert_allclose(ms, 1 + (g * g - 1) * 0.1, rtol=1e-6)
+  np.testing.assert_allclose(wv, w - 0.1 * g / np.sqrt(ms), rtol=1e-6)
+  wv, acc = oopt.adagrad(w.copy(), np.full(2, 0.1, np.float32), g, 0.1)
+  np.testing.assert_allclose(wv, w - 0.1 * g / np.sqrt(0.1 + g * g), rtol=1e-6)
