@@ -177,3 +177,47 @@ def test_full_size_word_vector_labels():
   rows_with_tokens = [i for i in range(8) if i != 6]
   assert rel_err(sim.cpu().numpy()[rows_with_tokens], pooled[rows_with_tokens]) < 1e-4
   assert want[6].sum() == 0 and want[1].sum() == 1 and want[4].sum() == 1      # no token -> zeros; cosine path -> one-hot
+
+
+def test_full_size_roi_backward_tile_owner():
+  """K1' at the benchmark shape (2 x 2000 proposals, 38 x 63 x 576 map): the tile-owner backward against the
+  per-proposal scatter (itself checked against the oracle in tests/test_gpu_parity.py), plain and with the folded
+  Mixed_5a max-pool backward, and against the oracle on the first image's first 300 proposals."""
+  from cap2det_b200 import capi, synthetic
+  from cap2det_b200.capi import call, ptr, stream
+  B, P, Cf = 2, 2000, 576
+  rng = np.random.default_rng(77)
+  fmap = synthetic.make_feature_map(rng, B)
+  props = synthetic.make_proposals(rng, B, P)
+  _, Hf, Wf, _ = fmap.shape
+  fm, pr = dev(fmap), dev(props)
+  codes = torch.empty((capi.load().c2d_roi_argmax_code_bytes(B * P, Cf, 14),), dtype=torch.uint8, device='cuda')
+  x0 = torch.empty((B * P, 7, 7, Cf), dtype=torch.bfloat16, device='cuda')
+  call('c2d_roi_crop_maxpool_fwd_codes', ptr(fm), B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(x0), capi.dtype_code(torch.bfloat16),
+       ptr(codes), stream())
+  g = torch.randn(x0.shape, device='cuda').to(torch.bfloat16)
+  pool_codes = torch.randint(0, 9, (B * P, 16, Cf), dtype=torch.uint8, device='cuda')
+  pool_grad = torch.randn((B * P * 16, Cf), device='cuda').to(torch.bfloat16)
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14)
+  assert n_ws > 0
+  ws = torch.empty((n_ws,), dtype=torch.uint8, device='cuda')
+  d_scatter, d_tiles = torch.empty_like(fm), torch.empty_like(fm)
+  bf16 = capi.dtype_code(torch.bfloat16)
+  call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), bf16, ptr(d_scatter), stream())
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), bf16, None, None, 0,
+       ptr(ws), n_ws, ptr(d_tiles), stream())
+  assert rel_err(d_tiles.cpu().numpy(), d_scatter.cpu().numpy()) < 1e-5
+  call('c2d_roi_crop_maxpool_bwd_codes_fold', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), ptr(pool_codes),
+       ptr(pool_grad), Cf, ptr(d_scatter), stream())
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), bf16, ptr(pool_codes),
+       ptr(pool_grad), Cf, ptr(ws), n_ws, ptr(d_tiles), stream())
+  assert rel_err(d_tiles.cpu().numpy(), d_scatter.cpu().numpy()) < 1e-5
+  # oracle on a slice: one image, 300 proposals (the other gradients zeroed)
+  n = 300
+  g1 = torch.zeros_like(g)
+  g1[:n] = g[:n]
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g1), bf16, None, None, 0,
+       ptr(ws), n_ws, ptr(d_tiles), stream())
+  want = oroi.roi_crop_maxpool_bwd(fmap[:1], props[:1, :n], g[:n].float().cpu().numpy())
+  assert rel_err(d_tiles[:1].cpu().numpy(), want) < 1e-5
+  assert float(d_tiles[1].abs().max()) == 0.0
