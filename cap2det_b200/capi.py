@@ -51,7 +51,7 @@ SIGNATURES = {
     'c2d_head_mixed5_bwd': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p]),
     'c2d_head_mixed5_bwd_fold': (_c_int, [_p, _c_int, _c_int, _p, _p, _c_sz, _p, _c_float, _p, _p, _p, _p, _p, _p, _p]),
     'c2d_roi_crop_maxpool_bwd_codes_fold': (_c_int, [_c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _p, _p, _c_int, _p, _p]),
-    'c2d_roi_bwd_tiles_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
+    'c2d_roi_bwd_tiles_workspace_bytes': (_c_sz, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int]),
     'c2d_roi_crop_maxpool_bwd_tiles': (_c_int, [_c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _c_int, _c_int, _p, _p, _c_int,
                                                 _p, _p, _c_int, _p, _c_sz, _p, _p]),
     'c2d_resize_bilinear': (_c_int, [_p, _c_int, _c_int, _c_int, _c_int, _c_int, _p, _c_int, _c_int, _p]),

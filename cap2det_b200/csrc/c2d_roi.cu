@@ -712,12 +712,15 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
 // Raw operands of one pooling bin for this lane's two channels (converted only when the bin is processed, so the
 // loads of the bins ahead stay in flight): gradient, arg-max code byte and -- FOLD -- code / output gradient of the
 // up to four Mixed_5a max-pool windows that contain the bin.
-template <typename GradT, bool FOLD>
+// MODE: kRoiPlain; kRoiFold = the Mixed_5a max-pool backward applied per bin from the window codes; kRoiRouted = a
+// second, dense gradient tensor [n, 7, 7, CF] added per bin (that backward pre-routed by roi_pool5a_route_kernel).
+enum { kRoiPlain = 0, kRoiFold = 1, kRoiRouted = 2 };
+template <typename GradT, int MODE>
 struct RoiBinLoad {
   typename RoiRaw<GradT>::type g;
   unsigned code;
-  unsigned pc[FOLD ? 4 : 1];
-  typename RoiRaw<GradT>::type dp[FOLD ? 4 : 1];
+  unsigned pc[MODE == kRoiFold ? 4 : 1];
+  typename RoiRaw<GradT>::type dp[MODE == kRoiFold ? 4 : 1];      // kRoiRouted: dp[0] = the routed gradient of the bin
 };
 
 // Per (proposal, lane) operand pointers.
@@ -726,16 +729,17 @@ struct RoiPairPtr {
   const GradT* g;               // dout[roi, 0, 0, c0]
   const unsigned char* code;    // codes[roi, 0, 0, quad(c0)]
   const unsigned char* pc;      // pool_codes[roi, 0, c0]
-  const GradT* dp;              // pool_grad[roi * 16, c0]
+  const GradT* dp;              // pool_grad[roi * 16, c0]   (kRoiRouted: routed[roi, 0, 0, c0])
 };
 
-template <typename GradT, bool FOLD, int CF>
-__device__ __forceinline__ void roi_tiles_load_bin(RoiBinLoad<GradT, FOLD>& L, const RoiPairPtr<GradT>& pp, int by, int bx,
+template <typename GradT, int MODE, int CF>
+__device__ __forceinline__ void roi_tiles_load_bin(RoiBinLoad<GradT, MODE>& L, const RoiPairPtr<GradT>& pp, int by, int bx,
                                                    int pool_ld) {
   const int bi = by * 7 + bx;
   L.g = RoiRaw<GradT>::ld(pp.g + bi * CF);
   L.code = __ldg(pp.code + bi * (CF / 4));
-  if (FOLD) {
+  if (MODE == kRoiRouted) L.dp[0] = RoiRaw<GradT>::ld(pp.dp + bi * CF);
+  if (MODE == kRoiFold) {
     // position (by, bx) of the 7x7 tensor lies in window by/2 (tap 1, even) or in (by-1)/2 (tap 2) and (by+1)/2 (tap 0)
     const int o = (by >> 1) * 4 + (bx >> 1);
     const unsigned char* pc = pp.pc + o * CF;
@@ -768,11 +772,12 @@ __device__ __forceinline__ void roi_tiles_fold(unsigned pc, typename RoiRaw<Grad
 // are warp-uniform (broadcast loads) and each channel SELECTS by its arg-max bits; acc_s = shared-memory address of
 // this lane's accumulator column.  The whole kernel keeps ONE copy of this code per operand buffer (two): a version
 // unrolled over the bins of a row ran out of instruction cache (no_instruction stalls, profiles/r2_roi_kernels.md).
-template <typename GradT, bool FOLD>
-__device__ __forceinline__ void roi_tiles_bin(const RoiBinLoad<GradT, FOLD>& L, int by, int bx, unsigned rec_s, unsigned acc_s,
+template <typename GradT, int MODE>
+__device__ __forceinline__ void roi_tiles_bin(const RoiBinLoad<GradT, MODE>& L, int by, int bx, unsigned rec_s, unsigned acc_s,
                                               int sh0) {
   float g0 = RoiRaw<GradT>::lo(L.g), g1 = RoiRaw<GradT>::hi(L.g);
-  if (FOLD) {
+  if (MODE == kRoiRouted) { g0 += RoiRaw<GradT>::lo(L.dp[0]); g1 += RoiRaw<GradT>::hi(L.dp[0]); }
+  if (MODE == kRoiFold) {
     const unsigned ty = (by & 1) ? 2u : 1u, tx = (bx & 1) ? 2u : 1u;
     roi_tiles_fold<GradT>(L.pc[0], L.dp[0], ty * 3 + tx, g0, g1);
     if (bx & 1) roi_tiles_fold<GradT>(L.pc[1], L.dp[1], ty * 3, g0, g1);
@@ -816,7 +821,7 @@ __device__ __forceinline__ void roi_tiles_next_bin(int& by, int& bx, int bx_lo, 
   if (++bx > bx_hi) { bx = bx_lo; ++by; }
 }
 
-template <typename GradT, bool FOLD, int CF>
+template <typename GradT, int MODE, int CF>
 __global__ void __launch_bounds__(32)
 roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int seg_max1, int l2_prefetch,
                      const int* __restrict__ nseg, const int* __restrict__ seg_start, const int* __restrict__ list,
@@ -884,13 +889,14 @@ roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int
         RoiPairPtr<GradT> pp;
         pp.g = dout + (size_t)roi * (49 * CF) + c0;
         pp.code = codes + (size_t)roi * (49 * (CF / 4)) + (c0 >> 2);
-        pp.pc = FOLD ? pool_codes + (size_t)roi * (16 * CF) + c0 : nullptr;
-        pp.dp = FOLD ? pool_grad + (size_t)roi * 16 * pool_ld + c0 : nullptr;
-        RoiBinLoad<GradT, FOLD> La, Lb;
+        pp.pc = MODE == kRoiFold ? pool_codes + (size_t)roi * (16 * CF) + c0 : nullptr;
+        pp.dp = MODE == kRoiFold ? pool_grad + (size_t)roi * 16 * pool_ld + c0
+                                 : (MODE == kRoiRouted ? pool_grad + (size_t)roi * (49 * CF) + c0 : nullptr);
+        RoiBinLoad<GradT, MODE> La, Lb;
         int by = by_lo, bx = bx_lo, lby = by_lo, lbx = bx_lo;        // accumulate position / load position (2 bins ahead)
-        roi_tiles_load_bin<GradT, FOLD, CF>(La, pp, lby, lbx, pool_ld);
+        roi_tiles_load_bin<GradT, MODE, CF>(La, pp, lby, lbx, pool_ld);
         roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
-        if (nb > 1) roi_tiles_load_bin<GradT, FOLD, CF>(Lb, pp, lby, lbx, pool_ld);
+        if (nb > 1) roi_tiles_load_bin<GradT, MODE, CF>(Lb, pp, lby, lbx, pool_ld);
         roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
         if (l2_prefetch && i + 1 < i1) {
           // operands of the next proposal of the list -> L2 (its demand loads then see L2 latency, not DRAM latency)
@@ -907,8 +913,9 @@ roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int
               if (c <= xhi) {
                 prefetch_l2(dout + ((size_t)roi1 * 49 + r * 7 + c) * CF + cb);
                 prefetch_l2(codes + ((size_t)roi1 * 49 + r * 7 + c) * (CF / 4) + (cb >> 2));
+                if (MODE == kRoiRouted) prefetch_l2(pool_grad + ((size_t)roi1 * 49 + r * 7 + c) * CF + cb);
               }
-            if (FOLD && lane < 16) {
+            if (MODE == kRoiFold && lane < 16) {
               const int oy = lane >> 2, ox = lane & 3;
               if (oy >= (ylo >> 1) && oy <= ((yhi + 1) >> 1) && ox >= (xlo >> 1) && ox <= ((xhi + 1) >> 1)) {
                 prefetch_l2(pool_codes + ((size_t)roi1 * 16 + lane) * CF + cb);
@@ -919,14 +926,14 @@ roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int
         }
         __syncwarp();
         for (int j = 0; j < nb; j += 2) {
-          roi_tiles_bin<GradT, FOLD>(La, by, bx, rec_s, acc_s, sh0);
+          roi_tiles_bin<GradT, MODE>(La, by, bx, rec_s, acc_s, sh0);
           roi_tiles_next_bin(by, bx, bx_lo, bx_hi);
-          if (j + 2 < nb) roi_tiles_load_bin<GradT, FOLD, CF>(La, pp, lby, lbx, pool_ld);
+          if (j + 2 < nb) roi_tiles_load_bin<GradT, MODE, CF>(La, pp, lby, lbx, pool_ld);
           roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
           if (j + 1 >= nb) break;
-          roi_tiles_bin<GradT, FOLD>(Lb, by, bx, rec_s, acc_s, sh0);
+          roi_tiles_bin<GradT, MODE>(Lb, by, bx, rec_s, acc_s, sh0);
           roi_tiles_next_bin(by, bx, bx_lo, bx_hi);
-          if (j + 3 < nb) roi_tiles_load_bin<GradT, FOLD, CF>(Lb, pp, lby, lbx, pool_ld);
+          if (j + 3 < nb) roi_tiles_load_bin<GradT, MODE, CF>(Lb, pp, lby, lbx, pool_ld);
           roi_tiles_next_bin(lby, lbx, bx_lo, bx_hi);
         }
       }
@@ -951,11 +958,55 @@ roi_tiles_bwd_kernel(int Hf, int Wf, int P, int T, int tiles_y, int tiles_x, int
 }
 
 
+// The backward of Mixed_5a/Branch_2's 3x3 / stride-2 max-pool as a dense tensor: routed[n, y, x, c] = sum of the output
+// gradients of the (1, 2 or 4) windows that contain (y, x) and whose arg-max code names it -- the term the folded K1'
+// adds per bin, computed ONCE per element here (the tile-owner kernel visits 1.37 bins per bin and is issue bound, so
+// the per-bin byte compares cost it 0.19 ms; this pass moves 340 MB in 75 us).  One thread per (ROI, channel quad): the
+// 16 windows' codes and gradients stay in registers, the 49 sums are written as bf16 (a thread per row of the 7x7
+// tensor re-reads the windows and was slower, 106 us).  Summation order = the fold's.
+__global__ void __launch_bounds__(256)
+roi_pool5a_route_kernel(const unsigned char* __restrict__ pool_codes, const __nv_bfloat16* __restrict__ pool_grad, int pool_ld,
+                        int n_rois, int C, __nv_bfloat16* __restrict__ routed) {
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int n = blockIdx.y;
+  if (c >= C || n >= n_rois) return;
+  unsigned pc[16];
+  float4 dp[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) {
+    pc[o] = __ldg(reinterpret_cast<const unsigned*>(pool_codes + ((size_t)n * 16 + o) * C + c));
+    dp[o] = ld4(pool_grad + ((size_t)n * 16 + o) * pool_ld + c);
+  }
+#pragma unroll
+  for (int y = 0; y < 7; ++y)
+#pragma unroll
+    for (int x = 0; x < 7; ++x) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        if (a == 1 && !(y & 1)) continue;
+        const int oy = (y & 1) ? ((y - 1) >> 1) + a : (y >> 1), ty = (y & 1) ? (a == 0 ? 2 : 0) : 1;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          if (b == 1 && !(x & 1)) continue;
+          const int ox = (x & 1) ? ((x - 1) >> 1) + b : (x >> 1), tx = (x & 1) ? (b == 0 ? 2 : 0) : 1;
+          const unsigned m = __vcmpeq4(pc[oy * 4 + ox], (unsigned)(ty * 3 + tx) * 0x01010101u);
+          const float4 d = dp[oy * 4 + ox];
+          g.x += (m & 0x000000ffu) ? d.x : 0.f;
+          g.y += (m & 0x0000ff00u) ? d.y : 0.f;
+          g.z += (m & 0x00ff0000u) ? d.z : 0.f;
+          g.w += (m & 0xff000000u) ? d.w : 0.f;
+        }
+      }
+      st4(routed + ((size_t)n * 49 + y * 7 + x) * C + c, g);
+    }
+}
+
 struct RoiTilesPlan {
   int tiles_y, tiles_x, T, seg_max1;
-  size_t off_nseg, off_seg, off_list, off_coords, off_masks, bytes;
+  size_t off_nseg, off_seg, off_list, off_coords, off_masks, off_routed, bytes, bytes_routed;
 };
-static RoiTilesPlan roi_tiles_plan(int B, int Hf, int Wf, int P) {
+static RoiTilesPlan roi_tiles_plan(int B, int Hf, int Wf, int Cf, int P) {
   RoiTilesPlan pl;
   pl.tiles_y = cdiv(Hf, kTileR); pl.tiles_x = cdiv(Wf, kTileS);
   pl.T = B * pl.tiles_y * pl.tiles_x;
@@ -969,6 +1020,9 @@ static RoiTilesPlan roi_tiles_plan(int B, int Hf, int Wf, int P) {
   pl.off_coords = o; o += n_rois * 32 * sizeof(int2);
   pl.off_masks = o; o += n_rois * 2 * kMaxTilesAxis * sizeof(unsigned short);
   pl.bytes = o;
+  o = (o + 255) & ~(size_t)255;                            // + the pre-routed pool gradient [n, 7, 7, Cf] bf16
+  pl.off_routed = o; o += n_rois * 49 * (size_t)Cf * sizeof(__nv_bfloat16);
+  pl.bytes_routed = o;
   return pl;
 }
 
@@ -990,13 +1044,18 @@ static bool roi_tiles_supported(int B, int Hf, int Wf, int Cf, int P, int crop) 
   return (long long)B * cdiv(Hf, kTileR) * cdiv(Wf, kTileS) <= kMaxTilesTotal;
 }
 
+static int roi_tiles_fold_routed() {
+  static int v = -1;                  // C2D_ROI_FOLD_ROUTED=0: measurement switch, per-bin fold inside the tile-owner kernel
+  if (v < 0) { const char* e = getenv("C2D_ROI_FOLD_ROUTED"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static int roi_tiles_l2_prefetch() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("C2D_ROI_TILES_PREFETCH"); v = e ? atoi(e) : 1; }
   return v;
 }
 
-template <typename GradT, bool FOLD, int CF>
+template <typename GradT, int MODE, int CF>
 static int roi_tiles_launch_cf(const RoiTilesPlan& pl, int B, int Hf, int Wf, int P, const float* boxes,
                                const unsigned char* codes, const void* dout, const unsigned char* pool_codes,
                                const void* pool_grad, int pool_ld, unsigned char* ws, float* dfmap, cudaStream_t st) {
@@ -1005,7 +1064,7 @@ static int roi_tiles_launch_cf(const RoiTilesPlan& pl, int B, int Hf, int Wf, in
   const size_t smem = (size_t)kTilePx * 64 * 4 + 32 * 16 + (size_t)(pl.T + 1) * 4;
   int dev = 0;
   C2D_CUDA_OK(cudaGetDevice(&dev));
-  auto kern = roi_tiles_bwd_kernel<GradT, FOLD, CF>;
+  auto kern = roi_tiles_bwd_kernel<GradT, MODE, CF>;
   if (first_call_on_this_device(&attr_mask)) {
     C2D_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     C2D_CUDA_OK(cudaDeviceGetAttribute(&n_sm[dev & 63], cudaDevAttrMultiProcessorCount, dev));
@@ -1032,13 +1091,13 @@ static int roi_tiles_launch_cf(const RoiTilesPlan& pl, int B, int Hf, int Wf, in
   return C2D_OK;
 }
 
-template <typename GradT, bool FOLD>
+template <typename GradT, int MODE>
 static int roi_tiles_launch(const RoiTilesPlan& pl, int B, int Hf, int Wf, int Cf, int P, const float* boxes,
                             const unsigned char* codes, const void* dout, const unsigned char* pool_codes,
                             const void* pool_grad, int pool_ld, unsigned char* ws, float* dfmap, cudaStream_t st) {
 #define C2D_ROI_TILES_CF(CF)                                                                                          \
   if (Cf == CF)                                                                                                       \
-    return roi_tiles_launch_cf<GradT, FOLD, CF>(pl, B, Hf, Wf, P, boxes, codes, dout, pool_codes, pool_grad, pool_ld, \
+    return roi_tiles_launch_cf<GradT, MODE, CF>(pl, B, Hf, Wf, P, boxes, codes, dout, pool_codes, pool_grad, pool_ld, \
                                                 ws, dfmap, st)
   C2D_ROI_TILES_CF(576);
   C2D_ROI_TILES_CF(128);
@@ -1162,12 +1221,13 @@ int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const flo
   return C2D_OK;
 }
 
-size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size) {
+size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size, int with_pool_fold) {
   static int enabled = -1;                                 // C2D_ROI_TILES=0: measurement switch, per-proposal scatter instead
   if (enabled < 0) { const char* e = getenv("C2D_ROI_TILES"); enabled = e ? atoi(e) : 1; }
   if (!enabled) return 0;
   if (!roi_tiles_supported(B, Hf, Wf, Cf, P, crop_size)) return 0;
-  return roi_tiles_plan(B, Hf, Wf, P).bytes;
+  const RoiTilesPlan pl = roi_tiles_plan(B, Hf, Wf, Cf, P);
+  return (with_pool_fold && roi_tiles_fold_routed()) ? pl.bytes_routed : pl.bytes;
 }
 
 int c2d_roi_crop_maxpool_bwd_tiles(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size, int pool_k,
@@ -1186,19 +1246,30 @@ int c2d_roi_crop_maxpool_bwd_tiles(int B, int Hf, int Wf, int Cf, const float* b
               kMaxTilesTotal, crop_size, Cf, B, Hf, Wf);
     return C2D_ERR_UNSUPPORTED;
   }
-  const RoiTilesPlan pl = roi_tiles_plan(B, Hf, Wf, P);
+  const RoiTilesPlan pl = roi_tiles_plan(B, Hf, Wf, Cf, P);
   C2D_CHECK_ARG(codes != nullptr && dout != nullptr && workspace != nullptr && workspace_bytes >= pl.bytes,
                 "roi_bwd_tiles: null operand or workspace of %zu bytes < %zu", workspace_bytes, pl.bytes);
   const bool fold = pool_codes != nullptr;
   C2D_CHECK_ARG(!fold || (dout_dtype == C2D_BF16 && pool_grad != nullptr && pool_grad_ld >= Cf),
                 "roi_bwd_tiles: the folded max-pool backward takes bf16 gradients with leading dimension >= Cf");
   unsigned char* ws = (unsigned char*)workspace;
+  if (fold && roi_tiles_fold_routed() && workspace_bytes >= pl.bytes_routed) {
+    // the pool backward as a dense pre-pass, then the tile-owner kernel with two gradient tensors
+    __nv_bfloat16* routed = reinterpret_cast<__nv_bfloat16*>(ws + pl.off_routed);
+    const int quads = Cf / 4, rt = quads >= 256 ? 256 : (quads + 31) / 32 * 32;        // 576 channels: one 160-thread CTA per ROI
+    roi_pool5a_route_kernel<<<dim3(cdiv(quads, rt), B * P), rt, 0, st>>>(pool_codes, (const __nv_bfloat16*)pool_grad,
+                                                                        pool_grad_ld, B * P, Cf, routed);
+    count_launch();
+    C2D_LAUNCH_OK();
+    return roi_tiles_launch<__nv_bfloat16, kRoiRouted>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, routed, Cf, ws,
+                                                       dfmap, st);
+  }
   if (fold)
-    return roi_tiles_launch<__nv_bfloat16, true>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, pool_codes, pool_grad,
-                                                 pool_grad_ld, ws, dfmap, st);
+    return roi_tiles_launch<__nv_bfloat16, kRoiFold>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, pool_codes, pool_grad,
+                                                     pool_grad_ld, ws, dfmap, st);
   if (dout_dtype == C2D_BF16)
-    return roi_tiles_launch<__nv_bfloat16, false>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
-  return roi_tiles_launch<float, false>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
+    return roi_tiles_launch<__nv_bfloat16, kRoiPlain>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
+  return roi_tiles_launch<float, kRoiPlain>(pl, B, Hf, Wf, Cf, P, boxes, codes, dout, nullptr, nullptr, 0, ws, dfmap, st);
 }
 
 }  // extern "C"

@@ -91,7 +91,7 @@ class _RoiCropMaxPool(torch.autograd.Function):
     dfmap = torch.empty((B, Hf, Wf, Cf), dtype=torch.float32, device=dout.device)
     fold = ctx.fold
     folded = fold is not None and fold.ready
-    ws_bytes = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, crop_size)
+    ws_bytes = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, crop_size, 1 if folded else 0)
     if ws_bytes:
       # tile-owner backward: gradients are summed across proposals on chip (csrc/c2d_roi.cu)
       ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dout.device)

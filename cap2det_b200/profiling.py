@@ -71,7 +71,7 @@ def kernel_table(model, example, peaks, head_dtype):
   add('K1 roi_crop_maxpool_fwd', ms, 'hbm', B * (Hf * Wf * Cf * 4 + P * 16 + P * 49 * Cf * s), None)   # arg-max codes: a by-product, not counted
   g0 = torch.randn(x0.shape, device=dev).to(dt)
   dfm = torch.empty_like(fmap)
-  n_rws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14)
+  n_rws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14, 0)
   if n_rws:                                   # the path ops.roi_crop_maxpool's backward takes (tile-owner kernel)
     rws = torch.empty((n_rws,), dtype=torch.uint8, device=dev)
     ms = _time(lambda: call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),

@@ -131,8 +131,10 @@ int c2d_roi_crop_maxpool_bwd_codes_fold(int B, int Hf, int Wf, int Cf, const flo
  * instead of one vector atomic per (bin, distinct pixel, channel quad).  pool_codes / pool_grad NULL: plain
  * backward (dout fp32 or bf16); non-NULL: the folded Mixed_5a max-pool backward of ..._bwd_codes_fold (bf16).
  * workspace: c2d_roi_bwd_tiles_workspace_bytes(...) bytes of device memory, contents irrelevant on entry;
- * that function returns 0 where this form is not available (use ..._bwd_codes[_fold] then). */
-size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size);
+ * that function returns 0 where this form is not available (use ..._bwd_codes[_fold] then).  with_pool_fold != 0
+ * adds room for the pool term as a dense bf16 tensor [B*P, 7, 7, Cf]: it is then computed once per element by a
+ * pre-pass and added per bin (a workspace sized without it makes the kernel apply the term per bin itself). */
+size_t c2d_roi_bwd_tiles_workspace_bytes(int B, int Hf, int Wf, int Cf, int P, int crop_size, int with_pool_fold);
 int c2d_roi_crop_maxpool_bwd_tiles(int B, int Hf, int Wf, int Cf, const float* boxes, int P, int crop_size, int pool_k,
                                    int pool_s, const unsigned char* codes, const void* dout, int dout_dtype,
                                    const unsigned char* pool_codes, const void* pool_grad, int pool_grad_ld,

@@ -53,7 +53,7 @@ def main():
   bwd = lambda: call('c2d_roi_crop_maxpool_bwd_codes', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
                      capi.dtype_code(dt), ptr(dfm), stream())
 
-  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14)
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14, 1)
   ws = torch.empty((max(n_ws, 1),), dtype=torch.uint8, device=dev)
   dfm_t = torch.empty_like(fmap)
   bwd_tiles = lambda: call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes), ptr(g0),
@@ -99,7 +99,12 @@ def main():
   bwd(); bwd_tiles(); torch.cuda.synchronize()
   out['tiles_vs_scatter'] = dict(max_abs_diff=float((dfm - dfm_t).abs().max()), max_abs=float(dfm.abs().max()))
   if dt == torch.bfloat16:
-    for name, fn in (("K1' bwd + pool fold, scatter", bwd_fold), ("K1' bwd + pool fold", bwd_tiles_fold)):
+    n_small = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14, 0)
+    bwd_tiles_fold_in_kernel = lambda: call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(props), P, 14, 2, 2, ptr(codes),
+                                            ptr(g0), capi.dtype_code(dt), ptr(pool_codes), ptr(pool_grad), Cf, ptr(ws), n_small,
+                                            ptr(dfm_t), stream())
+    for name, fn in (("K1' bwd + pool fold, scatter", bwd_fold), ("K1' bwd + pool fold, per bin", bwd_tiles_fold_in_kernel),
+                     ("K1' bwd + pool fold", bwd_tiles_fold)):
       ms, all_ms = time_it(fn)
       out[name] = dict(ms=ms, all_ms=all_ms)
     bwd_fold(); bwd_tiles_fold(); torch.cuda.synchronize()

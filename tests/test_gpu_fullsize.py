@@ -198,7 +198,7 @@ def test_full_size_roi_backward_tile_owner():
   g = torch.randn(x0.shape, device='cuda').to(torch.bfloat16)
   pool_codes = torch.randint(0, 9, (B * P, 16, Cf), dtype=torch.uint8, device='cuda')
   pool_grad = torch.randn((B * P * 16, Cf), device='cuda').to(torch.bfloat16)
-  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14)
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14, 1)
   assert n_ws > 0
   ws = torch.empty((n_ws,), dtype=torch.uint8, device='cuda')
   d_scatter, d_tiles = torch.empty_like(fm), torch.empty_like(fm)
@@ -211,7 +211,11 @@ def test_full_size_roi_backward_tile_owner():
        ptr(pool_grad), Cf, ptr(d_scatter), stream())
   call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), bf16, ptr(pool_codes),
        ptr(pool_grad), Cf, ptr(ws), n_ws, ptr(d_tiles), stream())
-  assert rel_err(d_tiles.cpu().numpy(), d_scatter.cpu().numpy()) < 1e-5
+  assert rel_err(d_tiles.cpu().numpy(), d_scatter.cpu().numpy()) < 2e-3       # pool term pre-routed as bf16
+  n_small = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, Cf, P, 14, 0)
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, Cf, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(g), bf16, ptr(pool_codes),
+       ptr(pool_grad), Cf, ptr(ws), n_small, ptr(d_tiles), stream())
+  assert rel_err(d_tiles.cpu().numpy(), d_scatter.cpu().numpy()) < 1e-5       # per-bin fold inside the kernel
   # oracle on a slice: one image, 300 proposals (the other gradients zeroed)
   n = 300
   g1 = torch.zeros_like(g)

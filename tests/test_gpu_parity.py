@@ -163,10 +163,12 @@ def test_roi_backward_tile_owner(shape):
   rng = np.random.default_rng(P)
   g = rng.standard_normal((B * P, 7, 7, C)).astype(np.float32)
   fm, pr = dev(fmap), dev(props)
-  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14)
+  n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14, 0)
+  n_ws_fold = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14, 1)
+  assert n_ws_fold >= n_ws + B * P * 49 * C * 2                                          # + the pre-routed pool gradient
   assert n_ws > 0
-  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, 24, P, 14) == 0      # depth % 64 != 0: not available
-  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 10) == 0
+  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, 24, P, 14, 0) == 0      # depth % 64 != 0: not available
+  assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 10, 0) == 0
   ws = torch.full((n_ws,), 0xA5, dtype=torch.uint8, device='cuda')                       # contents irrelevant on entry
   for dt in (torch.float32, torch.bfloat16):
     gd = dev(g).to(dt)
@@ -192,7 +194,14 @@ def test_roi_backward_tile_owner(shape):
   call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd), capi.dtype_code(torch.bfloat16),
        ptr(pool_codes), ptr(pool_grad), ld, ptr(ws), n_ws, ptr(d2), stream())
   assert float(d1.abs().max()) > 0
-  assert rel_err(d2.cpu().numpy(), d1.cpu().numpy()) < RTOL_F32
+  assert rel_err(d2.cpu().numpy(), d1.cpu().numpy()) < RTOL_F32                          # workspace without room: per-bin fold
+  # workspace with room for the dense pool term: a pre-pass routes the pool gradient once per element (stored as bf16:
+  # an element that two windows route to is rounded once more, 2^-9 of that term)
+  ws2 = torch.full((n_ws_fold,), 0x5A, dtype=torch.uint8, device='cuda')
+  d3 = torch.empty_like(d1)
+  call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd), capi.dtype_code(torch.bfloat16),
+       ptr(pool_codes), ptr(pool_grad), ld, ptr(ws2), n_ws_fold, ptr(d3), stream())
+  assert rel_err(d3.cpu().numpy(), d1.cpu().numpy()) < 2e-3
   with pytest.raises(ValueError):                                                        # short workspace is refused
     call('c2d_roi_crop_maxpool_bwd_tiles', B, Hf, Wf, C, ptr(pr), P, 14, 2, 2, ptr(codes), ptr(gd),
          capi.dtype_code(torch.bfloat16), None, None, 0, ptr(ws), n_ws - 1, ptr(d2), stream())
