@@ -220,13 +220,19 @@ def eval_sweep(dev, world, rank, head_dtype, workdir, peaks, n_images=16, warm=3
   out_host = [dict(n=torch.zeros((1,), dtype=torch.int32).pin_memory(), boxes=torch.zeros((1, 300, 4)).pin_memory(),
                    scores=torch.zeros((1, 300)).pin_memory(), classes=torch.zeros((1, 300)).pin_memory()) for _ in range(4)]
 
+  # the public predict call of the package: Model.build_prediction replayed as a CUDA graph per input-shape signature
+  # (~250 kernel launches per image make the eager sweep host bound); the eager call is timed beside it
+  from cap2det_b200 import predictor
+  graphed = predictor.GraphedPredictor(model)
+  predict = graphed
+
   def one_image(i, from_host):
     p = pool[i % len(pool)]
     nb = dict(non_blocking=True)
     ex = {F.features_to_crop: [f.to(dev, **nb) for f in p['fmaps']] if from_host else resident[i % len(pool)][0],
           F.proposals: p['proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][1],
           F.num_proposals: p['num_proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][2]}
-    pred = model.build_prediction(ex)
+    pred = predict(ex)
     if from_host:                       # what train/predict.py:367-376 reads back, every stage
       for st in range(4):
         out_host[st]['n'].copy_(pred['num_detections_at_%d' % st], **nb)
@@ -238,7 +244,8 @@ def eval_sweep(dev, world, rank, head_dtype, workdir, peaks, n_images=16, warm=3
   resident = [([f.to(dev) for f in p['fmaps']], p['proposals'].to(dev), p['num_proposals'].to(dev)) for p in pool]
   flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
   res = {}
-  for mode, from_host in (('resident', False), ('e2e', True)):
+  for mode, from_host in (('resident', False), ('e2e', True), ('eager', False)):
+    predict = model.build_prediction if mode == 'eager' else graphed
     for i in range(warm):
       one_image(i, from_host)
     torch.cuda.synchronize()
@@ -280,6 +287,8 @@ def eval_sweep(dev, world, rank, head_dtype, workdir, peaks, n_images=16, warm=3
               images_timed_per_gpu=n_images, sharding='contiguous image-index shards, no communication',
               images_in_shard_of_4952=len(c2d_dist.shard_indices(4952, rank, world, mode='contiguous')),
               images_per_sec=world * n_images / (res['resident'][0] / 1e3), ms_per_image=res['resident'][0] / n_images,
+              launch='CUDA graph replay per input-shape signature (predictor.GraphedPredictor)',
+              eager_images_per_sec=world * n_images / (res['eager'][0] / 1e3),
               e2e=dict(images_per_sec=world * n_images / (res['e2e'][1] / 1e3), ms_per_image_wall=res['e2e'][1] / n_images,
                        ms_per_image_device=res['e2e'][0] / n_images, h2d_bytes_per_image=int(h2d), d2h_bytes_per_image=int(d2h),
                        clock='time.perf_counter around the synchronised loop (host-pinned inputs in, detections out)'),

@@ -10,6 +10,7 @@
 // so far (all threads), then resolved inside the tile with a 64x64 suppression bitmask walked by
 // one thread.  Result is identical to the sequential greedy loop.
 // Kernel 2 (one CTA per image): merge the per-class lists with a second bitonic sort.
+#include <stdlib.h>
 #include "c2d_common.cuh"
 
 namespace c2d {
@@ -57,6 +58,7 @@ nms_per_class_kernel(const float4* __restrict__ boxes, const float* __restrict__
   __shared__ float4 tile_box[kTile];
   __shared__ unsigned long long tile_mask[kTile];
   __shared__ int tile_supp[kTile];
+  __shared__ unsigned char kept_slot[kTile];
   __shared__ int s_nkept, s_ncand;
   const int c = blockIdx.x, b = blockIdx.y;
   const float4* bx = boxes + (size_t)b * P;
@@ -105,20 +107,32 @@ nms_per_class_kernel(const float4* __restrict__ boxes, const float* __restrict__
       if (j > i && nms_iou(tile_box[j], tile_box[i]) > iou_thresh) atomicOr(&tile_mask[i], 1ull << j);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned long long dead = 0ull;
-      int nk = nkept;
-      for (int i = 0; i < nt && nk < max_per_class; ++i) {
-        if (tile_supp[i] || ((dead >> i) & 1ull)) continue;
-        dead |= tile_mask[i];
-        unsigned long long key = keys[t0 + i];
-        uint32_t idx = (uint32_t)(key & 0xffffffffull);
-        kept_box[nk] = tile_box[i];
-        cls_index[out_base + nk] = (int)idx;
-        cls_score[out_base + nk] = sc[(size_t)idx * lds];
-        ++nk;
+    // Resolve the tile in rank order.  Only candidates that are still alive are visited (lowest set bit of `alive`), and
+    // the walk touches shared memory only; the kept entries are written out by all threads afterwards (the scores come
+    // back out of the sort keys, bit for bit -- round 1 had thread 0 load each one from global memory inside this loop).
+    if (threadIdx.x < 32) {
+      const unsigned lo = __ballot_sync(0xffffffffu, tile_supp[threadIdx.x] != 0);
+      const unsigned hi = __ballot_sync(0xffffffffu, tile_supp[threadIdx.x + 32] != 0);
+      if (threadIdx.x == 0) {
+        const unsigned long long valid = nt >= 64 ? ~0ull : ((1ull << nt) - 1ull);
+        unsigned long long alive = valid & ~(((unsigned long long)hi << 32) | lo);
+        int nk = nkept;
+        while (alive != 0ull && nk < max_per_class) {
+          const int i = __ffsll((long long)alive) - 1;
+          alive &= ~(tile_mask[i] | (1ull << i));
+          kept_box[nk] = tile_box[i];
+          kept_slot[nk - nkept] = (unsigned char)i;
+          ++nk;
+        }
+        s_nkept = nk;
       }
-      s_nkept = nk;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < s_nkept - nkept; w += blockDim.x) {
+      const unsigned long long key = keys[t0 + kept_slot[w]];
+      const uint32_t u = ~(uint32_t)(key >> 32);
+      cls_index[out_base + nkept + w] = (int)(uint32_t)(key & 0xffffffffull);
+      cls_score[out_base + nkept + w] = __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
     }
     __syncthreads();
   }
@@ -171,6 +185,73 @@ nms_merge_kernel(const float4* __restrict__ boxes, int P, int C, int max_per_cla
       out_classes[o] = 1.0f;                                   // 0 + 1 on the zero padding
       out_index[o] = -1;
     }
+  }
+}
+
+// Merge by rank instead of a second sort: every per-class list is already in final order (descending score, ties by
+// NMS rank), so the position of an element in the merged list = its rank in its own class + the number of elements of
+// every other class that precede it (score greater; equal scores: the lower class first) -- one binary search per
+// class.  One thread per element over (B, slices) CTAs; same order as the stable sort of the concatenated lists
+// (nms_merge_kernel: 35 us in one CTA for 20 x 100 slots, this: a few us).
+__device__ __forceinline__ uint32_t nms_score_order(float s) {       // float order -> unsigned order
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__global__ void __launch_bounds__(256)
+nms_merge_rank_kernel(const float4* __restrict__ boxes, int P, int C, int max_per_class, int max_total,
+                      const int* __restrict__ cls_count, const int* __restrict__ cls_index,
+                      const float* __restrict__ cls_score, int* __restrict__ num_det, float4* __restrict__ out_boxes,
+                      float* __restrict__ out_scores, float* __restrict__ out_classes, int* __restrict__ out_index) {
+  extern __shared__ int s_cnt[];                                      // [C]
+  __shared__ int s_n;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_cnt[c] = cls_count[b * C + c];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int total = 0;
+    for (int c = 0; c < C; ++c) total += s_cnt[c];
+    s_n = min(total, max_total);
+    if (blockIdx.y == 0) num_det[b] = s_n;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const float* sc = cls_score + (size_t)b * C * max_per_class;
+  const int slot = blockIdx.y * blockDim.x + threadIdx.x;
+  if (slot < C * max_per_class) {
+    const int c = slot / max_per_class, r = slot - c * max_per_class;
+    if (r < s_cnt[c]) {
+      const float s = sc[slot];
+      const uint32_t key = nms_score_order(s);
+      int rank = r;
+      for (int c2 = 0; c2 < C; ++c2) {
+        if (c2 == c) continue;
+        const float* l = sc + c2 * max_per_class;
+        // elements of class c2 that precede: key2 > key, or key2 == key and c2 < c (lists are in descending key order)
+        int lo = 0, hi = s_cnt[c2];
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          const uint32_t k2 = nms_score_order(l[mid]);
+          if (k2 > key || (k2 == key && c2 < c)) lo = mid + 1; else hi = mid;
+        }
+        rank += lo;
+      }
+      if (rank < max_total) {
+        const size_t o = (size_t)b * max_total + rank;
+        const int idx = cls_index[(size_t)b * C * max_per_class + slot];
+        out_boxes[o] = boxes[(size_t)b * P + idx];
+        out_scores[o] = s;
+        out_classes[o] = (float)(c + 1);                         // core/builder.py:65
+        out_index[o] = idx;
+      }
+    }
+  }
+  // zero padding behind the detections (the CTAs stride over it together)
+  for (int i = n + blockIdx.y * blockDim.x + threadIdx.x; i < max_total; i += gridDim.y * blockDim.x) {
+    const size_t o = (size_t)b * max_total + i;
+    out_boxes[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+    out_scores[o] = 0.f;
+    out_classes[o] = 1.0f;                                       // 0 + 1 on the zero padding
+    out_index[o] = -1;
   }
 }
 
@@ -372,10 +453,17 @@ int c2d_multiclass_nms(const float* boxes, const float* scores, int lds, int B, 
   nms_per_class_kernel<<<dim3(C, B), kNmsThreads, (size_t)n_pad * 8, st>>>(
       (const float4*)boxes, scores, lds, P, C, n_pad, score_thresh, iou_thresh, max_size_per_class, cls_count,
       cls_index, cls_score);
-  nms_merge_kernel<<<B, kNmsThreads, (size_t)m_pad * 8, st>>>((const float4*)boxes, P, C, max_size_per_class,
-                                                             max_total_size, m_pad, cls_count, cls_index, cls_score,
-                                                             num_detections, (float4*)out_boxes, out_scores,
-                                                             out_classes, out_index);
+  static int merge_sort = -1;                 // C2D_NMS_MERGE_SORT=1: measurement switch, the round-1 single-CTA sort
+  if (merge_sort < 0) { const char* e = getenv("C2D_NMS_MERGE_SORT"); merge_sort = e ? atoi(e) : 0; }
+  if (merge_sort)
+    nms_merge_kernel<<<B, kNmsThreads, (size_t)m_pad * 8, st>>>((const float4*)boxes, P, C, max_size_per_class,
+                                                               max_total_size, m_pad, cls_count, cls_index, cls_score,
+                                                               num_detections, (float4*)out_boxes, out_scores,
+                                                               out_classes, out_index);
+  else
+    nms_merge_rank_kernel<<<dim3(B, cdiv(C * max_size_per_class, 256)), 256, (size_t)C * sizeof(int), st>>>(
+        (const float4*)boxes, P, C, max_size_per_class, max_total_size, cls_count, cls_index, cls_score, num_detections,
+        (float4*)out_boxes, out_scores, out_classes, out_index);
   count_launch(2);
   C2D_LAUNCH_OK();
   return C2D_OK;

@@ -1279,3 +1279,41 @@ def test_feature_map_dropout_and_moving_average():
   for sh, w, b in zip(step.shadow, want, before):
     assert rel_err(sh.cpu().numpy(), w.cpu().numpy()) < 1e-6
     assert bool((sh != b).any())
+
+
+def test_graphed_predictor_matches_eager_prediction():
+  """predictor.GraphedPredictor: the multi-scale evaluation path (4 feature maps, mean of the scores, 1 + K NMS passes)
+  replayed as a CUDA graph returns exactly what Model.build_prediction returns, for two input-shape signatures and after
+  the inputs change; one capture per signature."""
+  import tempfile
+  from cap2det_b200 import builder, config, predictor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor', eval_min_dimension=(160, 96),
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=False)
+  with torch.no_grad():
+    model.fc_weights.mul_(8.0)
+  pred = predictor.GraphedPredictor(model)
+  rng = np.random.default_rng(31)
+
+  def example(P, sizes):
+    fm = [dev(np.maximum(rng.standard_normal((1, h, w, 576)).astype(np.float32), 0)) for h, w in sizes]
+    return {F.features_to_crop: fm, F.proposals: dev(synthetic.make_proposals(rng, 1, P, 160, 256)),
+            F.num_proposals: dev(np.array([P - 3], np.int32))}
+
+  keys = ['num_detections_at_0', 'detection_boxes_at_0', 'detection_scores_at_3', 'detection_classes_at_3',
+          'oicr_proposal_scores_at_1']
+  for P, sizes in ((40, [(10, 16), (6, 10)]), (40, [(10, 16), (6, 10)]), (24, [(9, 13), (6, 9)]), (40, [(10, 16), (6, 10)])):
+    ex = example(P, sizes)
+    want = {k: v.clone() for k, v in model.build_prediction(ex).items() if torch.is_tensor(v)}
+    got = pred(ex)
+    for k in keys:
+      assert torch.equal(got[k], want[k]), k
+    assert got['class_labels'] == classes
+  assert pred.captures == 2
+  with pytest.raises(ValueError):
+    predictor.GraphedPredictor(builder.build(m, is_training=True))
