@@ -187,9 +187,14 @@ class Model(ModelBase):
     is_training = self._is_training
     num_proposals = examples[InputDataFields.num_proposals].to(torch.int32).contiguous()
     proposals = examples[InputDataFields.proposals].contiguous()
+    multi = isinstance(features_to_crop, (list, tuple))      # several scales of ONE image: a batch of S (evaluation)
+    if multi:
+      S = len(features_to_crop)
+      proposals = proposals.expand(S, -1, -1).contiguous()
+      num_proposals = num_proposals.expand(S).contiguous()
     B, P, _ = proposals.shape
     C = self._num_classes
-    if frcnn.dropout_on_feature_map and is_training and frcnn.dropout_keep_prob < 1.0:
+    if frcnn.dropout_on_feature_map and is_training and frcnn.dropout_keep_prob < 1.0 and not isinstance(features_to_crop, (list, tuple)):
       # models/utils.py:138-142 (off in every reference config, configs/*.pbtxt:55): slim.dropout on the feature map
       fmask = examples.get(InputDataFields.feature_map_keep_mask)
       if fmask is None:
@@ -200,11 +205,16 @@ class Model(ModelBase):
     # models/utils.py:147-160
     # bf16 training: the backward of the head's first max-pool is applied inside the ROI backward (ops.PoolFold)
     fold = None
-    if (self.fold_pool_backward and self._head_dtype == torch.bfloat16 and features_to_crop.requires_grad
+    if (not isinstance(features_to_crop, (list, tuple)) and self.fold_pool_backward and self._head_dtype == torch.bfloat16
+        and features_to_crop.requires_grad
         and frcnn.initial_crop_size == 14 and torch.is_grad_enabled()):
       fold = ops.PoolFold()
-    x0 = ops.roi_crop_maxpool(features_to_crop, proposals, frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
-                              frcnn.maxpool_stride, out_dtype=self._head_dtype, fold=fold)
+    if multi:
+      x0 = ops.roi_crop_maxpool_multi(features_to_crop, proposals[:1], frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
+                                      frcnn.maxpool_stride, out_dtype=self._head_dtype)
+    else:
+      x0 = ops.roi_crop_maxpool(features_to_crop, proposals, frcnn.initial_crop_size, frcnn.maxpool_kernel_size,
+                                frcnn.maxpool_stride, out_dtype=self._head_dtype, fold=fold)
     self._roi_split = None
     if getattr(self, 'split_backward_at_roi', False) and x0.requires_grad:
       # Data-parallel steps cut the autograd graph here: the backward of everything above (all trainable head / FC
@@ -222,7 +232,7 @@ class Model(ModelBase):
         self._ensure_dropout_state(x0.device)
         keep_mask = ops.dropout_keep_mask(self._dropout_state, self._dropout_seed, (B * P, ops.HEAD_FEATURE_DIMS), keep_prob)
     feat = ops.head_mixed5(x0, self.head_params, keep_mask, keep_prob if keep_mask is not None else 1.0,
-                           need_dx0=features_to_crop.requires_grad, fold=fold)
+                           need_dx0=(not multi) and features_to_crop.requires_grad, fold=fold)
     # models/cap2det_model.py:79-88,190-197: the five FC layers as one product
     logits_all = ops.fc_concat(feat, self.fc_weights, self.fc_biases, compute_dtype=self._head_dtype).view(B, P, -1)
     midn_class_logits, midn_proposal_scores, midn_proba_r_given_c = ops.midn(
@@ -306,16 +316,24 @@ class Model(ModelBase):
     if fmaps[0].shape[0] != 1:
       raise ValueError('multi-scale evaluation needs batch size 1 (models/cap2det_model.py:237)')
     K = options.oicr_iterations
-    sums = [None] * (1 + K)
-    predictions = None
     with torch.no_grad():
-      for fmap in fmaps:
-        predictions = self._build_prediction(examples, fmap)
-        for i in range(1 + K):
-          s = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)]
-          sums[i] = s.clone() if sums[i] is None else sums[i] + s
-      for i in range(1 + K):   # tf.reduce_mean over the stacked scales (:263-267)
-        predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)] = sums[i] / float(len(fmaps))
+      # All scales as ONE batch: the ROI crop runs per feature map (their sizes differ) into one tensor, the head, the
+      # FC layers and MIDN once over S * P proposals (every row is computed exactly as in a per-scale pass: rows of
+      # the GEMMs and images of MIDN are independent).  The reference keeps the LAST scale's predictions and replaces
+      # the scores by their mean over the scales, accumulated in scale order (:248-267).
+      S = len(fmaps)
+      batched = self._build_prediction(examples, list(fmaps))
+      predictions = {}
+      for k, v in batched.items():
+        predictions[k] = v[S - 1:S] if (torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == S) else v
+      predictions['_proposal_features'] = batched['_proposal_features'][(S - 1) * batched['_logits_all'].shape[1]:]
+      for i in range(1 + K):
+        key = Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)
+        s = batched[key]
+        acc = s[0:1].clone()
+        for j in range(1, S):
+          acc = acc + s[j:j + 1]
+        predictions[key] = acc / float(S)
       predictions.update(self._postprocess(predictions))
     return predictions
 

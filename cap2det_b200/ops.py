@@ -114,6 +114,30 @@ def roi_crop_maxpool(fmap, proposals, crop_size=14, pool_k=2, pool_s=2, out_dtyp
   return _RoiCropMaxPool.apply(fmap.contiguous(), proposals.contiguous(), crop_size, pool_k, pool_s, out_dtype, fold)
 
 
+def roi_crop_maxpool_multi(fmaps, proposals, crop_size=14, pool_k=2, pool_s=2, out_dtype=torch.float32):
+  """Inference only: the SAME proposals [1,P,4] cropped from several feature maps [1,Hf_s,Wf_s,C] of different sizes
+  (multi-scale evaluation, models/cap2det_model.py:231-272) into ONE tensor [S*P, crop/2, crop/2, C], scale-major -- so
+  that the head, the FC layers and MIDN run once over all scales as a batch of S.  Every slice is exactly what
+  roi_crop_maxpool returns for that feature map."""
+  require_cuda(proposals, *fmaps)
+  _f32(proposals)
+  proposals = proposals.contiguous()
+  if proposals.shape[0] != 1:
+    raise ValueError('roi_crop_maxpool_multi takes one image (proposals [1,P,4])')
+  P = proposals.shape[1]
+  hp = crop_size // pool_s
+  Cf = fmaps[0].shape[-1]
+  out = torch.empty((len(fmaps) * P, hp, hp, Cf), dtype=out_dtype, device=proposals.device)
+  for s, fmap in enumerate(fmaps):
+    _f32(fmap)
+    fmap = fmap.contiguous()
+    if fmap.shape[0] != 1 or fmap.shape[-1] != Cf:
+      raise ValueError('feature maps must be [1,Hf,Wf,%d]' % Cf)
+    call('c2d_roi_crop_maxpool_fwd_codes', ptr(fmap), 1, fmap.shape[1], fmap.shape[2], Cf, ptr(proposals), P, crop_size,
+         pool_k, pool_s, ptr(out[s * P:(s + 1) * P]), capi.dtype_code(out_dtype), None, stream())
+  return out
+
+
 # ---------------------------------------------------------------------------------------------
 # K2/K3: Mixed_5a..5c head + spatial mean + dropout  (models/utils.py:165-177)
 # ---------------------------------------------------------------------------------------------
