@@ -257,17 +257,27 @@ class Model(ModelBase):
     results = {}
     oicr_iterations = self._model_proto.oicr_iterations
     proposals = predictions[DetectionResultFields.proposal_boxes]
-    for i in range(1 + oicr_iterations):
-      post_process_fn = self._midn_postprocess_fn
-      proposal_scores = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)].detach()
-      if i > 0:
-        post_process_fn = self._oicr_postprocess_fn
-        proposal_scores = ops.softmax_rows(proposal_scores)[:, :, 1:]
-      num_detections, boxes, scores, classes, _ = post_process_fn(proposals, proposal_scores)
+    B = proposals.shape[0]
+
+    def put(i, num_detections, boxes, scores, classes):
       results[DetectionResultFields.num_detections + '_at_{}'.format(i)] = num_detections
       results[DetectionResultFields.detection_boxes + '_at_{}'.format(i)] = boxes
       results[DetectionResultFields.detection_scores + '_at_{}'.format(i)] = scores
       results[DetectionResultFields.detection_classes + '_at_{}'.format(i)] = classes
+
+    midn_scores = predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_0'].detach()
+    put(0, *self._midn_postprocess_fn(proposals, midn_scores)[:4])
+    if oicr_iterations > 0:
+      # The K refinement stages share one post-processor and the same boxes: their NMS passes run as ONE call over a
+      # batch of K * B score matrices (images are independent in K7, so every stage's detections are what a call of
+      # its own returns) -- K times the CTAs on a kernel that is latency bound with 20 classes.
+      stacked = torch.cat([predictions[Cap2DetPredictions.oicr_proposal_scores + '_at_{}'.format(i)].detach()
+                           for i in range(1, 1 + oicr_iterations)], dim=0)
+      probs = ops.softmax_rows(stacked)[:, :, 1:]
+      num_detections, boxes, scores, classes, _ = self._oicr_postprocess_fn(proposals.repeat(oicr_iterations, 1, 1), probs)
+      for i in range(1, 1 + oicr_iterations):
+        sl = slice((i - 1) * B, i * B)
+        put(i, num_detections[sl], boxes[sl], scores[sl], classes[sl])
     return results
 
   def _first_stage(self, images):
