@@ -226,13 +226,44 @@ def eval_sweep(dev, world, rank, head_dtype, workdir, peaks, n_images=16, warm=3
   graphed = predictor.GraphedPredictor(model)
   predict = graphed
 
+  # e2e: the inputs of image i + 1 are copied from pinned host memory on a copy stream while image i is computed
+  # (two device-side staging sets, re-used alternately once the prediction that read them has finished)
+  copy_stream = torch.cuda.Stream(device=dev)
+  stage_bufs = [dict(fmaps=[torch.empty_like(f, device=dev) for f in pool[0]['fmaps']],
+                     proposals=torch.empty_like(pool[0]['proposals'], device=dev),
+                     num_proposals=torch.empty_like(pool[0]['num_proposals'], device=dev)) for _ in range(2)]
+  stage_ready, stage_free = {}, [None, None]
+
+  def stage(i):
+    p, k = pool[i % len(pool)], i % 2
+    with torch.cuda.stream(copy_stream):
+      if stage_free[k] is not None:
+        copy_stream.wait_event(stage_free[k])
+      for d, f in zip(stage_bufs[k]['fmaps'], p['fmaps']):
+        d.copy_(f, non_blocking=True)
+      stage_bufs[k]['proposals'].copy_(p['proposals'], non_blocking=True)
+      stage_bufs[k]['num_proposals'].copy_(p['num_proposals'], non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(copy_stream)
+    stage_ready[i] = ev
+
   def one_image(i, from_host):
-    p = pool[i % len(pool)]
     nb = dict(non_blocking=True)
-    ex = {F.features_to_crop: [f.to(dev, **nb) for f in p['fmaps']] if from_host else resident[i % len(pool)][0],
-          F.proposals: p['proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][1],
-          F.num_proposals: p['num_proposals'].to(dev, **nb) if from_host else resident[i % len(pool)][2]}
+    if from_host:
+      if i not in stage_ready:
+        stage(i)
+      torch.cuda.current_stream().wait_event(stage_ready.pop(i))
+      k = i % 2
+      ex = {F.features_to_crop: stage_bufs[k]['fmaps'], F.proposals: stage_bufs[k]['proposals'],
+            F.num_proposals: stage_bufs[k]['num_proposals']}
+    else:
+      ex = {F.features_to_crop: resident[i % len(pool)][0], F.proposals: resident[i % len(pool)][1],
+            F.num_proposals: resident[i % len(pool)][2]}
     pred = predict(ex)
+    if from_host:
+      stage_free[i % 2] = torch.cuda.Event()
+      stage_free[i % 2].record()
+      stage(i + 1)
     if from_host:                       # what train/predict.py:367-376 reads back, every stage
       for st in range(4):
         out_host[st]['n'].copy_(pred['num_detections_at_%d' % st], **nb)
