@@ -165,7 +165,9 @@ def test_roi_backward_tile_owner(shape):
   fm, pr = dev(fmap), dev(props)
   n_ws = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14, 0)
   n_ws_fold = capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 14, 1)
-  assert n_ws_fold >= n_ws + B * P * 49 * C * 2                                          # + the pre-routed pool gradient
+  import os
+  if os.environ.get('C2D_ROI_FOLD_ROUTED', '1') != '0':                                    # (measurement switch of the library)
+    assert n_ws_fold >= n_ws + B * P * 49 * C * 2                                        # + the pre-routed pool gradient
   assert n_ws > 0
   assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, 24, P, 14, 0) == 0      # depth % 64 != 0: not available
   assert capi.load().c2d_roi_bwd_tiles_workspace_bytes(B, Hf, Wf, C, P, 10, 0) == 0
