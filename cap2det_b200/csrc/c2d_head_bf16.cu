@@ -181,6 +181,49 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   return C2D_OK;
 }
 
+// Weight gradients on a second stream.  They are off the critical path of the backward pass (nothing reads dW before
+// the BN unfold at the end), and a weight-gradient launch is ONE wave of unequal work items: its last CTAs leave most
+// SMs idle.  Launched on a side stream -- each after an event that marks its output gradient complete -- their tails
+// are filled by the data-gradient GEMMs, pools and the like that continue on the main stream (and vice versa).  The two
+// streams join before the BN unfold.  Under stream capture the fork / join becomes edges of the CUDA graph.
+// C2D_WGRAD_STREAM=0/1 is a measurement switch.
+struct WgradSide {
+  cudaStream_t stream;
+  cudaEvent_t ev[32];
+  int next;
+};
+static WgradSide* wgrad_side() {
+  static WgradSide side[64];
+  static unsigned long long made = 0;
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("C2D_WGRAD_STREAM"); enabled = e ? atoi(e) : 1; }
+  if (!enabled) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  WgradSide* s = &side[dev & 63];
+  if (first_call_on_this_device(&made)) {
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) { enabled = 0; return nullptr; }
+    for (int i = 0; i < 32; ++i) cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming);
+    s->next = 0;
+  }
+  return s;
+}
+// side waits for everything issued on `st` so far
+static cudaError_t wgrad_fork(WgradSide* s, cudaStream_t st) {
+  cudaEvent_t e = s->ev[s->next];
+  s->next = (s->next + 1) & 31;
+  cudaError_t r = cudaEventRecord(e, st);
+  if (r != cudaSuccess) return r;
+  return cudaStreamWaitEvent(s->stream, e, 0);
+}
+static cudaError_t wgrad_join(WgradSide* s, cudaStream_t st) {
+  cudaEvent_t e = s->ev[s->next];
+  s->next = (s->next + 1) & 31;
+  cudaError_t r = cudaEventRecord(e, s->stream);
+  if (r != cudaSuccess) return r;
+  return cudaStreamWaitEvent(st, e, 0);
+}
+
 // fold_pool5a != 0: the backward of Mixed_5a/Branch_2's max-pool is NOT applied here; dx0 then lacks that term and the
 // ROI backward adds it on the fly from the pool's arg-max codes and its output gradient (both stay in `ws`).
 int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const HeadPlan& pl, char* ws,
@@ -199,6 +242,7 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
   float* dshf = reinterpret_cast<float*>(ws + pl.dshift_off);
   C2D_CUDA_OK(cudaMemsetAsync(dwsf, 0, pl.w_only_total * sizeof(float), st));
   C2D_CUDA_OK(cudaMemsetAsync(dshf, 0, pl.ch_total * sizeof(float), st));
+  WgradSide* side = wgrad_side();
   bool written[NBUF] = {false};
   // every gradient buffer is written as du = dy * (y > 0) by its LAST writer (fused ReLU backward; for X2 that is
   // the code-driven max-pool backward kernel, for the others a data-gradient GEMM);
@@ -241,9 +285,11 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
         mdw[nm] = dwsf + pl.poff[kHead5bPoolConv].w_only; mds[nm] = dshf + pl.poff[kHead5bPoolConv].ch;
         ++nm;
       }
-      rc = conv_wgrad_group_tc(d, members, nm, mdw, mds, st);
+      if (side) C2D_CUDA_OK(wgrad_fork(side, st));
+      rc = conv_wgrad_group_tc(d, members, nm, mdw, mds, side ? side->stream : st);
     } else if (!head_in_group_tail(i)) {
-      rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, st, dshf + o.ch);
+      if (side) C2D_CUDA_OK(wgrad_fork(side, st));
+      rc = conv_wgrad_tc(d, dy, ldd, dwsf + o.w_only, side ? side->stream : st, dshf + o.ch);
     }
     if (rc != C2D_OK) return rc;
     // data gradient: a sibling group is reduced by ONE GEMM once its first (lowest) member is reached
@@ -287,6 +333,7 @@ int c2d_head_mixed5_bwd_bf16(const void* x0, int n, const float* params, const H
       written[X0] = true;
     }
   }
+  if (side) C2D_CUDA_OK(wgrad_join(side, st));
   unfold_bn_all_kernel<<<dim3(cdiv(352, 8), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), dwsf, dshf, dparams);
   count_launch();
   C2D_LAUNCH_OK();
