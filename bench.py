@@ -723,6 +723,9 @@ def main():
     for k, v in dominant['per_kernel'].items():
       v['tflops'] = v['flops_per_step'] / (v['ms_per_step'] * 1e-3) / 1e12
       v['frac_of_peak'] = v['tflops'] / peak
+    dominant['note'] = ('per-launch CUDA events, one kernel at a time: while they are on, the head backward keeps its '
+                        'weight-gradient launches on the main stream; the timed step runs them on a side stream, '
+                        'overlapping the data-gradient chain, so the per-kernel times add up to more than their share of the step')
   if not args.no_extra_configs:
     out['eval_sweep'] = eval_sweep(dev, world, rank, head_dtype, workdir, peaks)        # every rank: its shard
   if rank == 0:

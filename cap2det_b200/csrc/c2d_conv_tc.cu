@@ -687,6 +687,9 @@ using namespace c2d;
 extern "C" {
 
 void c2d_profile_enable(int on) { g_prof_on = on != 0; }
+}  // extern "C"
+namespace c2d { bool tc_profile_enabled() { return g_prof_on; } }
+extern "C" {
 void c2d_profile_reset(void) {
   for (size_t i = 0; i < g_prof.size(); ++i) { cudaEventDestroy(g_prof[i].a); cudaEventDestroy(g_prof[i].b); }
   g_prof.clear();

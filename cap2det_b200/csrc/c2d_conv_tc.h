@@ -31,6 +31,8 @@ int conv_fwd_tc(const ConvDesc& c, const bf16_t* w16, const float* shift, int re
 int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16_t* wt16, void* dx, int lddx, int accum,
                   int out_f32, cudaStream_t st, const bf16_t* mask = nullptr, int mask_cols = 0);
 // Weight gradient: dw [cout][k*k][cin] (fp32, pre-zeroed) += du^T x ; dshift [cout] (optional) += column sums of du.
+// Per-launch timing of the tensor-core kernels is on (c2d_profile_enable): callers keep one kernel at a time on the GPU.
+bool tc_profile_enabled();
 int conv_wgrad_tc(const ConvDesc& c, const bf16_t* du, int lddu, float* dw, cudaStream_t st, float* dshift = nullptr);
 
 // Weight gradients of up to four sibling 1x1 convolutions on the same input x (c.x, c.ldx, c.cin, c.n, c.hin) in one

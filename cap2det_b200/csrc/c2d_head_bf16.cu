@@ -197,7 +197,7 @@ static WgradSide* wgrad_side() {
   static unsigned long long made = 0;
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("C2D_WGRAD_STREAM"); enabled = e ? atoi(e) : 1; }
-  if (!enabled) return nullptr;
+  if (!enabled || tc_profile_enabled()) return nullptr;      // per-launch timing wants one kernel at a time on the GPU
   int dev = 0;
   cudaGetDevice(&dev);
   WgradSide* s = &side[dev & 63];
