@@ -77,7 +77,8 @@ def build_library(force=False, verbose=False):
         with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
           objs = list(ex.map(compile_one, _sources()))
         tmp_lib = os.path.join(tmp, 'libcap2det_b200.so')
-        r = subprocess.run([NVCC, '-shared', '-o', tmp_lib] + objs + ['-lcudart'], capture_output=True, text=True)
+        r = subprocess.run([NVCC, '-shared', '-o', tmp_lib] + objs + ['-lcudart', '-Xlinker', '--no-undefined'],
+                           capture_output=True, text=True)      # an unresolved c2d_* symbol fails the build, not the first dlopen
         if r.returncode != 0:
           raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))
         tmp_stamp = os.path.join(tmp, 'build.stamp')
