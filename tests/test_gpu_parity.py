@@ -1319,3 +1319,55 @@ def test_graphed_predictor_matches_eager_prediction():
   assert pred.captures == 2
   with pytest.raises(ValueError):
     predictor.GraphedPredictor(builder.build(m, is_training=True))
+
+
+def test_multi_scale_roi_and_small_abi_checks():
+  """ops.roi_crop_maxpool_multi: every scale's slice is exactly what roi_crop_maxpool returns for that feature map
+  (the batched multi-scale evaluation relies on it); GraphedPredictor evicts its least recently used graph;
+  c2d_optimizer_update / c2d_dropout_apply refuse bad arguments."""
+  from cap2det_b200 import capi, ops
+  from cap2det_b200.capi import call, ptr, stream
+  rng = np.random.default_rng(61)
+  _, props = _roi_inputs(61, B=2, P=29, Hf=9, Wf=13, C=8)
+  props = props[:1]
+  fmaps = [np.maximum(rng.standard_normal((1, h, w, 576)).astype(np.float32), 0) for h, w in ((9, 13), (14, 22), (5, 7))]
+  for dt in (torch.float32, torch.bfloat16):
+    both = ops.roi_crop_maxpool_multi([dev(f) for f in fmaps], dev(props), out_dtype=dt)
+    assert both.shape == (3 * 29, 7, 7, 576)
+    for s, f in enumerate(fmaps):
+      one = ops.roi_crop_maxpool(dev(f), dev(props), out_dtype=dt)
+      assert torch.equal(both[s * 29:(s + 1) * 29], one)
+  with pytest.raises(ValueError):
+    ops.roi_crop_maxpool_multi([dev(fmaps[0])], dev(np.concatenate([props, props], 0)))
+  w = torch.zeros(8, device='cuda'); g = torch.ones(8, device='cuda')
+  with pytest.raises(ValueError):                        # unknown optimizer kind
+    call('c2d_optimizer_update', 7, ptr(w), None, None, None, ptr(g), 8, 0.1, 1.0, 0.0, 0.0, 0.0, 0.0, 0, stream())
+  with pytest.raises(ValueError):                        # momentum without its slot
+    call('c2d_optimizer_update', 1, ptr(w), None, None, None, ptr(g), 8, 0.1, 1.0, 0.0, 0.9, 0.0, 0.0, 0, stream())
+  with pytest.raises(ValueError):                        # keep_prob out of range
+    call('c2d_dropout_apply', ptr(w), ptr(g), 0.0, ptr(w), 8, stream())
+
+
+def test_graphed_predictor_evicts_least_recently_used():
+  import tempfile
+  from cap2det_b200 import builder, config, predictor, synthetic
+  from cap2det_b200.standard_fields import InputDataFields as F
+  d = tempfile.mkdtemp()
+  classes = synthetic.VOC_CLASSES
+  text = synthetic.model_options_text(extractor='groundtruth_extractor', eval_min_dimension=(96,),
+                                      extractor_fields="label_file: '%s'" % synthetic.write_label_file(d, classes))
+  m = config.Model()
+  m.set_extension(config.Cap2DetModel.ext, config.parse_text(text, config.Cap2DetModel))
+  model = builder.build(m, is_training=False)
+  pred = predictor.GraphedPredictor(model, max_graphs=2)
+  rng = np.random.default_rng(5)
+
+  def example(h, w):
+    return {F.features_to_crop: [dev(np.maximum(rng.standard_normal((1, h, w, 576)).astype(np.float32), 0))],
+            F.proposals: dev(synthetic.make_proposals(rng, 1, 16, 96, 160)), F.num_proposals: dev(np.array([16], np.int32))}
+
+  for h, w in ((6, 10), (7, 10), (6, 10), (8, 10), (7, 10)):      # third call hits; (8,10) evicts (7,10); last one recaptures
+    ex = example(h, w)
+    want = model.build_prediction(ex)['detection_scores_at_3'].clone()
+    assert torch.equal(pred(ex)['detection_scores_at_3'], want)
+  assert pred.captures == 4 and len(pred._cache) == 2
