@@ -261,17 +261,19 @@ __device__ __forceinline__ void roi_setup_plan(RoiPlan& pl, float4 box, int Hf, 
   __syncthreads();
 }
 
-__device__ __forceinline__ float2 lerp2_rn(float2 a, float2 b, float2 t) {
+__device__ __forceinline__ float2 lerp2_rn(float2 a, float2 b, float2 t, float2 one) {
   // a + (b - a) * t, three separately rounded operations per lane.  fma(a, -1, b) is the correctly rounded b - a.
-  // The final addition is scalar ON PURPOSE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2
-  // (even with --fmad=false), which would change the rounding; FMUL2 followed by two FADDs is left alone
-  // (checked in the SASS and by the bit-exact parity test against the oracle).
+  // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (even with --fmad=false, even through opaque
+  // moves), which would change the rounding.  The final addition is therefore written as fma(a, one, p) with `one` a
+  // RUN-TIME 1.0 (a kernel argument the compiler cannot fold): a * 1 is exact, so the result is the correctly rounded
+  // a + p, the multiply stays its own FMUL2, and the lerp is three packed instructions (FFMA2, FMUL2, FFMA2) instead
+  // of FFMA2 + FMUL2 + two scalar FADDs (checked in the SASS and by the bit-exact parity test against the oracle).
   const float2 p = __fmul2_rn(__ffma2_rn(a, make_float2(-1.f, -1.f), b), t);
-  return make_float2(__fadd_rn(a.x, p.x), __fadd_rn(a.y, p.y));
+  return __ffma2_rn(a, one, p);
 }
-__device__ __forceinline__ float4 lerp4_rn(float4 a, float4 b, float2 t) {
-  const float2 lo = lerp2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), t);
-  const float2 hi = lerp2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), t);
+__device__ __forceinline__ float4 lerp4_rn(float4 a, float4 b, float2 t, float2 one) {
+  const float2 lo = lerp2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y), t, one);
+  const float2 hi = lerp2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w), t, one);
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
@@ -286,17 +288,17 @@ __device__ __forceinline__ const float4* roi_addr(const float4* base, unsigned i
 // the image as float4; c0..c3 = float4 index of this thread's channel quad at the corner columns (l0, r0, l1, r1).
 template <int XP>
 __device__ __forceinline__ void roi_xrow(const float4* __restrict__ row, unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-                                         float2 xl0, float2 xl1, float4& h0, float4& h1) {
+                                         float2 xl0, float2 xl1, float2 one, float4& h0, float4& h1) {
   if (XP == 0) {
     const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1));
-    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(a, b, xl1);
+    h0 = lerp4_rn(a, b, xl0, one); h1 = lerp4_rn(a, b, xl1, one);
   } else if (XP == 1) {
     const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1)), c = __ldg(roi_addr(row, c3));
-    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(b, c, xl1);
+    h0 = lerp4_rn(a, b, xl0, one); h1 = lerp4_rn(b, c, xl1, one);
   } else {
     const float4 a = __ldg(roi_addr(row, c0)), b = __ldg(roi_addr(row, c1)), c = __ldg(roi_addr(row, c2)),
                  d = __ldg(roi_addr(row, c3));
-    h0 = lerp4_rn(a, b, xl0); h1 = lerp4_rn(c, d, xl1);
+    h0 = lerp4_rn(a, b, xl0, one); h1 = lerp4_rn(c, d, xl1, one);
   }
 }
 
@@ -315,7 +317,7 @@ __device__ __forceinline__ unsigned code_field(float v00, float v01, float v10, 
 // One work item: pooled column px of channel quad q, all pooled rows.
 template <int XP, bool CODES, bool ALL_VALID, typename OutT>
 __device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const RoiPlan& pl, int px, int q, int C4, int crop,
-                                          OutT* __restrict__ o, unsigned char* __restrict__ cd) {
+                                          OutT* __restrict__ o, unsigned char* __restrict__ cd, float2 one) {
   const int cx0 = 2 * px, cx1 = cx0 + 1, hp = crop >> 1;
   const unsigned c0 = pl.sc.lo[1][cx0] * C4 + q, c1 = pl.sc.hi[1][cx0] * C4 + q, c2 = pl.sc.lo[1][cx1] * C4 + q,
                  c3 = pl.sc.hi[1][cx1] * C4 + q;
@@ -334,19 +336,19 @@ __device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const
       const int f = rp.flags;
       if (__builtin_expect((f & (kRowLoadA | kRowLoadB)) != 0, 0)) {        // warp-uniform; most sample rows re-use both rows
         if ((f & (kRowLoadA | kRowLoadB)) == (kRowLoadA | kRowLoadB)) {      // all loads of both rows in flight together
-          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, A0, A1);
-          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, B0, B1);
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, one, A0, A1);
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, one, B0, B1);
         } else if (f & kRowLoadA) {
-          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, A0, A1);
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_a), c0, c1, c2, c3, xl0, xl1, one, A0, A1);
         } else {
-          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, B0, B1);
+          roi_xrow<XP>(roi_addr(imgq, (unsigned)rp.off_b), c0, c1, c2, c3, xl0, xl1, one, B0, B1);
         }
       }
       if (__builtin_expect((f & kRowCopy) != 0, 0)) { if (f & kRowTopIsB) { A0 = B0; A1 = B1; } else { B0 = A0; B1 = A1; } }
       const float2 yl2 = make_float2(rp.yl, rp.yl);
       float4 v0, v1;
-      if (f & kRowTopIsB) { v0 = lerp4_rn(B0, A0, yl2); v1 = lerp4_rn(B1, A1, yl2); }
-      else { v0 = lerp4_rn(A0, B0, yl2); v1 = lerp4_rn(A1, B1, yl2); }
+      if (f & kRowTopIsB) { v0 = lerp4_rn(B0, A0, yl2, one); v1 = lerp4_rn(B1, A1, yl2, one); }
+      else { v0 = lerp4_rn(A0, B0, yl2, one); v1 = lerp4_rn(A1, B1, yl2, one); }
       if (!ALL_VALID) {
         const bool vy = (f & kRowValid) != 0;
         if (!(vy && vx0)) v0 = zero;
@@ -368,8 +370,9 @@ __device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const
 template <bool CODES, typename OutT>
 __global__ void __launch_bounds__(448, 2)
 roi_crop_maxpool_fwd_rows_kernel(const float* __restrict__ fmap, int Hf, int Wf, int Cf, const float4* __restrict__ boxes,
-                                 int P, int crop, OutT* __restrict__ out, unsigned char* __restrict__ codes) {
+                                 int P, int crop, OutT* __restrict__ out, unsigned char* __restrict__ codes, float one) {
   __shared__ RoiPlan pl;
+  const float2 one2 = make_float2(one, one);          // run-time 1.0, see lerp2_rn
   const int roi = blockIdx.x;
   const int b = roi / P;
   const int C4 = Cf >> 2, hp = crop >> 1;
@@ -386,13 +389,13 @@ roi_crop_maxpool_fwd_rows_kernel(const float* __restrict__ fmap, int Hf, int Wf,
     OutT* o = oroi + 4 * q;
     unsigned char* cd = CODES ? croi + q : nullptr;
     if (all_valid) {
-      if (xp == 0) roi_strip<0, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
-      else if (xp == 1) roi_strip<1, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
-      else roi_strip<2, CODES, true>(img4, pl, px, q, C4, crop, o, cd);
+      if (xp == 0) roi_strip<0, CODES, true>(img4, pl, px, q, C4, crop, o, cd, one2);
+      else if (xp == 1) roi_strip<1, CODES, true>(img4, pl, px, q, C4, crop, o, cd, one2);
+      else roi_strip<2, CODES, true>(img4, pl, px, q, C4, crop, o, cd, one2);
     } else {
-      if (xp == 0) roi_strip<0, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
-      else if (xp == 1) roi_strip<1, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
-      else roi_strip<2, CODES, false>(img4, pl, px, q, C4, crop, o, cd);
+      if (xp == 0) roi_strip<0, CODES, false>(img4, pl, px, q, C4, crop, o, cd, one2);
+      else if (xp == 1) roi_strip<1, CODES, false>(img4, pl, px, q, C4, crop, o, cd, one2);
+      else roi_strip<2, CODES, false>(img4, pl, px, q, C4, crop, o, cd, one2);
     }
   }
 }
@@ -1147,7 +1150,7 @@ int c2d_roi_crop_maxpool_fwd_codes(const float* fmap, int B, int Hf, int Wf, int
     const int threads = hp * W * 32 < 64 ? 64 : hp * W * 32;   // the plan set-up uses warps 0 (y) and 1 (x)
 #define C2D_ROI_FWD_LAUNCH(CODES, T)                                                                                  \
     roi_crop_maxpool_fwd_rows_kernel<CODES, T><<<B * P, threads, 0, st>>>(fmap, Hf, Wf, Cf, (const float4*)boxes, P,   \
-                                                                          crop_size, (T*)out, codes)
+                                                                          crop_size, (T*)out, codes, 1.0f)
     if (out_dtype == C2D_F32) { if (codes) C2D_ROI_FWD_LAUNCH(true, float); else C2D_ROI_FWD_LAUNCH(false, float); }
     else { if (codes) C2D_ROI_FWD_LAUNCH(true, __nv_bfloat16); else C2D_ROI_FWD_LAUNCH(false, __nv_bfloat16); }
 #undef C2D_ROI_FWD_LAUNCH
