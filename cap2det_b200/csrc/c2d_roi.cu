@@ -327,6 +327,9 @@ __device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 A0 = zero, A1 = zero, B0 = zero, B1 = zero;
   RowPlan rp = pl.row[0];
+  // the two output pointers advance by one pooled row per iteration (recomputing them from the proposal index cost ~35
+  // integer instructions per row: 64-bit multiplies by run-time extents)
+  const size_t o_step = (size_t)hp * (4 * C4), cd_step = (size_t)hp * C4;
   for (int py = 0; py < hp; ++py) {
     float4 a, b, t0, t1, u0, u1;           // t = the two samples of the top sample row, u = of the bottom one
 #pragma unroll
@@ -358,11 +361,13 @@ __device__ __forceinline__ void roi_strip(const float4* __restrict__ imgq, const
       else { b = max4(v0, v1); u0 = v0; u1 = v1; }
       rp = nx;
     }
-    st4(o + (size_t)py * hp * (4 * C4), max4(a, b));
+    st4(o, max4(a, b));
+    o += o_step;
     if (CODES) {
       const unsigned code = code_field<0>(t0.x, t1.x, u0.x, u1.x, a.x, b.x) + code_field<2>(t0.y, t1.y, u0.y, u1.y, a.y, b.y) +
                             code_field<4>(t0.z, t1.z, u0.z, u1.z, a.z, b.z) + code_field<6>(t0.w, t1.w, u0.w, u1.w, a.w, b.w);
-      cd[(size_t)py * hp * C4] = (unsigned char)code;
+      *cd = (unsigned char)code;
+      cd += cd_step;
     }
   }
 }
