@@ -223,7 +223,7 @@ static int b_box_rows(const tc::ConvGemmParams& p, bool two) { return two ? p.n_
 // Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift) with the output columns split over `segs`.
 //   w16: [sum cols][k*k][cin] bf16 (K-major); shift: [sum cols] or null.
 int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
-                int out_f32, cudaStream_t st, int act_cols) {
+                int out_f32, cudaStream_t st, int act_cols, const PoolFuse* pool) {
   tc::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   CUtensorMap maps[4], mapB;
@@ -234,6 +234,14 @@ int conv_fwd_tc(const ConvDesc& c, const bf16* w16, const float* shift, int relu
   const int cout = p.n_total;
   set_n_tiles(p, two);
   p.shift = shift; p.out_f32 = out_f32; p.relu = relu; p.accum = 0;
+  if (pool != nullptr) {
+    // the epilogue's half warps are ROIs: 16 rows per ROI (tiles hold whole ROIs), whole 16-column chunks inside segment 0
+    C2D_CHECK_ARG(c.hout == 4 && !out_f32 && shift != nullptr && pool->out != nullptr && pool->cols % 16 == 0 &&
+                      pool->cols > 0 && pool->cols <= segs[0].cols && (act_cols < 0 || pool->cols <= act_cols),
+                  "conv_fwd: the fused spatial mean needs a bf16 activation output on 4x4 planes");
+    p.pool_out = pool->out; p.pool_keep = pool->keep; p.pool_ld = pool->ld; p.pool_cols = pool->cols;
+    p.pool_keep_prob = pool->keep_prob;
+  }
   const int chunks = (c.cin + 63) / 64;
   if (c.k == 1) {
     const long long M = (long long)c.n * c.hin * c.hin;

@@ -22,10 +22,15 @@ struct ConvDesc {
   bf16_t* y; int ldy;              // output activation [n, hout, hout, cout]   (forward)
 };
 
+// Fused K3 (models/utils.py:169-174) for a forward convolution on 4x4 planes: the first `cols` output columns (inside
+// segment 0) are, besides being stored, averaged over the 16 positions of their ROI:
+//   out[roi * ld + col] = mean_pos y[roi, pos, col] (/ keep_prob * keep[roi * ld + col] when keep != null).
+struct PoolFuse { float* out; const float* keep; int ld; int cols; float keep_prob; };
+
 // Forward: [y_0 | y_1 | ...] = act(conv(x, w) + shift), output columns split over `segs` (<= 4);
 //   w16 [sum cols][k*k][cin]; act_cols >= 0: shift / ReLU only for columns < act_cols (1x1 only).
 int conv_fwd_tc(const ConvDesc& c, const bf16_t* w16, const float* shift, int relu, const OutSeg* segs, int nseg,
-                int out_f32, cudaStream_t st, int act_cols = -1);
+                int out_f32, cudaStream_t st, int act_cols = -1, const PoolFuse* pool = nullptr);
 // Data gradient: dx (+)= conv_transpose([du_0 | du_1 | ...], w).  k == 1: up to 4 sources (a merged sibling group),
 //   wt16 [cin][sum cols]; k == 3: one source, wt16 [cin][9][cols].  mask: fused ReLU backward for columns < mask_cols.
 int conv_dgrad_tc(const ConvDesc& c, const InSeg* srcs, int nsrc, const bf16_t* wt16, void* dx, int lddx, int accum,

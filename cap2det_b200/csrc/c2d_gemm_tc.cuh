@@ -70,6 +70,10 @@ struct ConvGemmParams {
   // flat == 2 (whole feature maps, backbone): a (half) tile is an img_tw x (rows_per_tile / img_tw) patch of
   // the Hf x Wf output plane of image n; A box = (64, img_tw, th, 1) at (x0 + tap_x, y0 + tap_y, n).
   int img_tw, img_tiles_x, img_tiles_y;
+  // fused K3 (models/utils.py:169-174; forward of the block whose output feeds the spatial mean, 16
+  // positions per ROI = 16 consecutive output rows): besides being stored, output columns < pool_cols (segment 0) are
+  // averaged over their ROI and written to pool_out[roi * pool_ld + column] (* pool_keep / pool_keep_prob).
+  float* pool_out; const float* pool_keep; int pool_ld, pool_cols; float pool_keep_prob;
 };
 
 struct ImgTile { int n, x0, y0; };
@@ -272,10 +276,25 @@ __device__ __forceinline__ void epi_fetch(const ConvGemmParams& p, EpiOperand& e
   }
 }
 
-template <bool RMW, bool MASK, bool ACT>
+// Sum over the 16 lanes of a half warp (the 16 positions of one ROI) of 16 values per lane: a butterfly in which a
+// lane hands half of its partial sums to its partner at every step (8 + 4 + 2 + 1 shuffles instead of 64); lane l
+// of the half warp ends with the total of value l.
+__device__ __forceinline__ float half_warp_column_sums(const float (&f)[16], const int lane) {
+  float s8[8], s4[4], s2[2];
+  const bool b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s8[i] = (b3 ? f[i + 8] : f[i]) + __shfl_xor_sync(0xffffffffu, b3 ? f[i] : f[i + 8], 8);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s4[i] = (b2 ? s8[i + 4] : s8[i]) + __shfl_xor_sync(0xffffffffu, b2 ? s8[i] : s8[i + 4], 4);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) s2[i] = (b1 ? s4[i + 2] : s4[i]) + __shfl_xor_sync(0xffffffffu, b1 ? s4[i] : s4[i + 2], 2);
+  return (b0 ? s2[1] : s2[0]) + __shfl_xor_sync(0xffffffffu, b0 ? s2[0] : s2[1], 1);
+}
+
+template <bool RMW, bool MASK, bool ACT, bool POOL = false>
 __device__ __forceinline__ void epi_chunk(const ConvGemmParams& p, const uint32_t (&v)[16], const EpiOperand& e, const int j,
-                                          const int ncol0, const long long orow, const float* ssh) {
-  if (orow < 0) return;
+                                          const int ncol0, const long long orow, const float* ssh, const float keep = 1.f) {
+  if (!POOL && orow < 0) return;                // POOL: every lane takes part in the shuffles, the stores are guarded
   const int col0 = ncol0 + j;
   int sgm = 0;
   if (!RMW) {                                   // accumulation implies a single output segment
@@ -316,15 +335,53 @@ __device__ __forceinline__ void epi_chunk(const ConvGemmParams& p, const uint32_
 #pragma unroll
     for (int i = 0; i < 8; ++i) w[i] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yy[i]), zero2);
   }
-  st_global_256(o, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+  if (!POOL || orow >= 0) st_global_256(o, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+  if (POOL && col0 < p.pool_cols) {             // warp-uniform; the mean of the ROUNDED activations, like the separate kernel
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { r[2 * i] = __uint_as_float(w[i] << 16); r[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    const int lane = threadIdx.x & 31;
+    float m = half_warp_column_sums(r, lane) / 16.f;
+    if (orow >= 0) {
+      if (p.pool_keep != nullptr) m = m / p.pool_keep_prob * keep;
+      p.pool_out[(orow >> 4) * p.pool_ld + col0 + (lane & 15)] = m;
+    }
+  }
 }
 
 // ssh[j] = shift of tile column j (ACT only).
-template <bool RMW, bool MASK, bool ACT>
+template <bool RMW, bool MASK, bool ACT, bool POOL = false>
 __device__ __forceinline__ void epilogue_bf16(const ConvGemmParams& p, const uint32_t taddr, const int j_lo, int j_hi,
                                               const int ncol0, const long long orow, const float* ssh) {
   j_hi = min(j_hi, p.n_total - ncol0);            // n_total is a multiple of 16; warp-uniform
   if (j_hi <= j_lo) return;
+  if (POOL) {
+    // The launches with the fused mean are reduction heavy (K >= 1024): their epilogue hides behind the next tile's
+    // main loop, and this instance has no accumulate / mask operands to prefetch.
+    const EpiOperand none = {};
+    uint32_t va[16], vb[16];
+    // this lane's dropout keep factors, one chunk ahead of their use (a load behind the reduction would stall every chunk)
+    const float* kp = nullptr;
+    if (p.pool_keep != nullptr && orow >= 0) kp = p.pool_keep + (orow >> 4) * p.pool_ld + ncol0 + (threadIdx.x & 15);
+    const int pool_hi = min(j_hi, p.pool_cols - ncol0);
+    float keep_next = (kp != nullptr && j_lo < pool_hi) ? kp[j_lo] : 1.f;
+    tmem_ld_32x16(taddr + j_lo, va);
+#pragma unroll 1
+    for (int j = j_lo; j < j_hi; j += 32) {
+      float keep = keep_next;
+      keep_next = (kp != nullptr && j + 16 < pool_hi) ? kp[j + 16] : 1.f;
+      tmem_ld_wait_on(va);
+      if (j + 16 < j_hi) tmem_ld_32x16(taddr + j + 16, vb);
+      epi_chunk<RMW, MASK, ACT, POOL>(p, va, none, j, ncol0, orow, ssh, keep);
+      if (j + 16 >= j_hi) break;
+      keep = keep_next;
+      keep_next = (kp != nullptr && j + 32 < pool_hi) ? kp[j + 32] : 1.f;
+      tmem_ld_wait_on(vb);
+      if (j + 32 < j_hi) tmem_ld_32x16(taddr + j + 32, va);
+      epi_chunk<RMW, MASK, ACT, POOL>(p, vb, none, j + 16, ncol0, orow, ssh, keep);
+    }
+    return;
+  }
   constexpr int D = (RMW && MASK) ? 2 : 4;         // operand prefetch distance in chunks (32 registers either way)
   EpiOperand e[D];
 #pragma unroll
@@ -339,23 +396,23 @@ __device__ __forceinline__ void epilogue_bf16(const ConvGemmParams& p, const uin
       if (j >= j_hi) break;
       tmem_ld_wait_on(va);
       if (j + 16 < j_hi) tmem_ld_32x16(taddr + j + 16, vb);
-      epi_chunk<RMW, MASK, ACT>(p, va, e[u], j, ncol0, orow, ssh);
+      epi_chunk<RMW, MASK, ACT, POOL>(p, va, e[u], j, ncol0, orow, ssh);
       epi_fetch<RMW, MASK>(p, e[u], j + 16 * D, j_hi, ncol0, orow);
       if (j + 16 >= j_hi) break;
       tmem_ld_wait_on(vb);
       if (j + 32 < j_hi) tmem_ld_32x16(taddr + j + 32, va);
-      epi_chunk<RMW, MASK, ACT>(p, vb, e[u + 1], j + 16, ncol0, orow, ssh);
+      epi_chunk<RMW, MASK, ACT, POOL>(p, vb, e[u + 1], j + 16, ncol0, orow, ssh);
       epi_fetch<RMW, MASK>(p, e[u + 1], j + 16 + 16 * D, j_hi, ncol0, orow);
     }
   }
 }
 
 // Epilogue mode of a launch (warp-uniform, fixed per kernel).
-enum { kEpiGeneric = 0, kEpiAct, kEpiPlain, kEpiMask, kEpiRmw, kEpiRmwMask };
+enum { kEpiGeneric = 0, kEpiAct, kEpiPlain, kEpiMask, kEpiRmw, kEpiRmwMask, kEpiActPool };
 __host__ __device__ __forceinline__ int epilogue_mode(const ConvGemmParams& p) {
   if (p.out_f32) return kEpiGeneric;
   const bool act = p.shift != nullptr || p.relu, rmw = p.accum != 0, msk = p.mask != nullptr;
-  if (act) return (rmw || msk || p.shift == nullptr) ? kEpiGeneric : kEpiAct;
+  if (act) return (rmw || msk || p.shift == nullptr) ? kEpiGeneric : (p.pool_out != nullptr ? kEpiActPool : kEpiAct);
   return rmw ? (msk ? kEpiRmwMask : kEpiRmw) : (msk ? kEpiMask : kEpiPlain);
 }
 // Stage the shifts of tile columns [j_lo, j_lo + 128) into this warp's shared-memory slot (indexed by tile column).
@@ -376,6 +433,7 @@ __device__ __forceinline__ void epilogue_run(const ConvGemmParams& p, const int 
   if (GENERIC) { epilogue_generic(p, taddr, j_lo, j_hi, ncol0, orow); return; }
   switch (mode) {
     case kEpiAct: epilogue_bf16<false, false, true>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
+    case kEpiActPool: epilogue_bf16<false, false, true, true>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
     case kEpiPlain: epilogue_bf16<false, false, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
     case kEpiMask: epilogue_bf16<false, true, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
     case kEpiRmw: epilogue_bf16<true, false, false>(p, taddr, j_lo, j_hi, ncol0, orow, ssh); break;
@@ -491,7 +549,7 @@ conv_gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_cons
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      if (mode == kEpiAct && nt != staged_nt) { epilogue_stage_shift(p, ssh, 0, nt * p.n_tile, lane); staged_nt = nt; }
+      if ((mode == kEpiAct || mode == kEpiActPool) && nt != staged_nt) { epilogue_stage_shift(p, ssh, 0, nt * p.n_tile, lane); staged_nt = nt; }
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = a * 128 + q * 32 + lane;       // row inside the tile
@@ -646,7 +704,7 @@ __device__ __forceinline__ void conv_gemm_tc2_body(const CUtensorMap& mapA0, con
       const int mt = tile / p.num_n_tiles, nt = tile - mt * p.num_n_tiles;
       const int as = it & 1;
       const uint32_t aphase = (uint32_t)(it >> 1) & 1u;
-      if (mode == kEpiAct && nt != staged_nt) { epilogue_stage_shift(p, ssh, col_lo, nt * p.n_tile, lane); staged_nt = nt; }
+      if ((mode == kEpiAct || mode == kEpiActPool) && nt != staged_nt) { epilogue_stage_shift(p, ssh, col_lo, nt * p.n_tile, lane); staged_nt = nt; }
       mbar_wait(&pipe->tmem_full[as], aphase);
       tc_fence_after();
       const int r = q * 32 + lane;                  // row inside this CTA's half tile

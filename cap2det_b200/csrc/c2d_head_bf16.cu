@@ -135,6 +135,7 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   float* shf = reinterpret_cast<float*>(ws + pl.shift_off);
   bf16* ws16 = reinterpret_cast<bf16*>(ws + pl.ws16_off);
   bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
+  static const bool fuse_k3 = [] { const char* e = getenv("C2D_FUSE_K3"); return !(e && e[0] == '0'); }();   // measurement switch
   fold_bn_bf16_kernel<<<dim3(cdiv(9 * 256, 64), cdiv(352, 32), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), ws16, wt16, shf);
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
@@ -166,7 +167,17 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       segs[gsz].out = act[P1]; segs[gsz].ld = cp.cout; segs[gsz].cols = cp.cout;
       ++gsz;
     }
-    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, segs, gsz, 0, st, act_cols);
+    // K3 in the epilogue of the four launches that write Mixed_5c's output (X3): the spatial mean (+ dropout) of their
+    // columns goes straight to `feat`
+    PoolFuse pool;
+    const HeadConv& c0 = kHeadConvs[i];
+    const bool to_x3 = fuse_k3 && c0.dst == X3;
+    if (to_x3) {
+      pool.out = feat + c0.dst_off; pool.keep = keep_mask ? keep_mask + c0.dst_off : nullptr;
+      pool.ld = kHeadBufs[X3].ch; pool.cols = c0.cout; pool.keep_prob = keep_prob;
+    }
+    int rc = conv_fwd_tc(head_conv_desc(i, n, act), ws16 + o.w_only, shf + o.ch, 1, segs, gsz, 0, st, act_cols,
+                         to_x3 ? &pool : nullptr);
     if (rc != C2D_OK) return rc;
     if (i == kHeadGroups[1].first) {
       const HeadConv& cp = kHeadConvs[kHead5bPoolConv];
@@ -175,8 +186,10 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
       count_launch();
     }
   }
-  avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
-  count_launch();
+  if (!fuse_k3) {
+    avgpool_dropout_fwd_kernel<bf16><<<dim3(cdiv(1024 / 4, 128), n), 128, 0, st>>>(act[X3], 16, 1024, keep_mask, keep_prob, feat, n);
+    count_launch();
+  }
   C2D_LAUNCH_OK();
   return C2D_OK;
 }
