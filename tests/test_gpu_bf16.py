@@ -391,3 +391,45 @@ def test_pool_backward_folded_into_roi_backward_matches_separate_kernel():
   assert np.abs(grads[0][0]).max() > 0
   assert l2_err(grads[0][0], grads[1][0]) < 5e-3, l2_err(grads[0][0], grads[1][0])
   assert l2_err(grads[0][1], grads[1][1]) < 1e-5      # the head's own gradients do not depend on the fold (fp32 atomics order only)
+
+
+_K3_SNIPPET = r'''
+import sys
+import numpy as np
+import torch
+sys.path.insert(0, sys.argv[1])
+from cap2det_b200 import ops
+from tests.test_gpu_parity import _head_setup
+_, flat, x0 = _head_setup(n=int(sys.argv[3]), seed=51)
+keep = (np.random.default_rng(52).uniform(size=(x0.shape[0], 1024)) < 0.5).astype(np.float32)
+xd = torch.from_numpy(x0).cuda().to(torch.bfloat16)
+pd = torch.from_numpy(flat).cuda()
+with torch.no_grad():
+  a = ops.head_mixed5(xd, pd, torch.from_numpy(keep).cuda(), 0.5, need_dx0=False).cpu().numpy()
+  b = ops.head_mixed5(xd, pd, None, 1.0, need_dx0=False).cpu().numpy()
+np.savez(sys.argv[2], dropout=a, plain=b)
+'''
+
+
+@pytest.mark.parametrize('n', [37, 256])
+def test_fused_k3_epilogue_matches_separate_kernel(tmp_path, n):
+  """K3 (models/utils.py:169-174): the spatial mean + dropout computed in the epilogue of the GEMM launches that write
+  Mixed_5c's output (default) against the separate avgpool_dropout_fwd kernel (C2D_FUSE_K3=0, read once per process,
+  hence the subprocess).  Both average the same bf16-rounded activations; only the order of the 16 additions
+  differs, so the features agree to fp32 rounding.  n = 37: a ragged last tile; n = 256: whole tiles only."""
+  import os
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  out = {}
+  for fuse in ('1', '0'):
+    path = str(tmp_path / ('feat_%s.npz' % fuse))
+    env = dict(os.environ, C2D_FUSE_K3=fuse)
+    subprocess.run([sys.executable, '-c', _K3_SNIPPET, root, path, str(n)], check=True, env=env, cwd=root, timeout=600)
+    out[fuse] = np.load(path)
+  for key in ('dropout', 'plain'):
+    a, b = out['1'][key], out['0'][key]
+    assert a.shape == (n, 1024) and np.isfinite(a).all()
+    assert float(np.abs(b).max()) > 0
+    np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7)
+  assert (out['1']['dropout'] == 0).mean() > 0.4        # the keep mask was applied
