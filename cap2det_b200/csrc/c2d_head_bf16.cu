@@ -135,7 +135,11 @@ int c2d_head_mixed5_fwd_bf16(const void* x0, int n, const float* params, const H
   float* shf = reinterpret_cast<float*>(ws + pl.shift_off);
   bf16* ws16 = reinterpret_cast<bf16*>(ws + pl.ws16_off);
   bf16* wt16 = reinterpret_cast<bf16*>(ws + pl.wt16_off);
-  static const bool fuse_k3 = [] { const char* e = getenv("C2D_FUSE_K3"); return !(e && e[0] == '0'); }();   // measurement switch
+  // K3 in the GEMM epilogue (PoolFuse) or as its own kernel.  Measured on one box: without dropout
+  // (evaluation) the fused form wins (eval sweep +1.2 %); with a keep mask the longer epilogues cost the four launches
+  // 35 us against the 28 us kernel they replace, so training keeps the separate kernel.  C2D_FUSE_K3=1 / 0 forces one.
+  static const int k3_mode = [] { const char* e = getenv("C2D_FUSE_K3"); return e && e[0] == '0' ? 0 : (e && e[0] == '1' ? 1 : 2); }();
+  const bool fuse_k3 = k3_mode == 1 || (k3_mode == 2 && keep_mask == nullptr);
   fold_bn_bf16_kernel<<<dim3(cdiv(9 * 256, 64), cdiv(352, 32), kNumHeadConvs), 256, 0, st>>>(params, make_fold_table(pl), ws16, wt16, shf);
   count_launch();
   for (int i = 0; i < kNumHeadConvs; ++i) {
